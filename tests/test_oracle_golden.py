@@ -115,7 +115,12 @@ def test_oracle_against_live_reference_random_shapes():
         assert O.rel_err(O.gcn_conv(v, ei, w), ref.gcn_conv(v, ei, w)) < 1e-5
         # fp64 arbiter
         qd, kd, vd = q.double(), k.double(), v.double()
-        assert O.rel_err(O.simple_attention(qd, kd, vd), ref.full_attention_conv(qd, kd, vd, "simple")) < 1e-12
+        torch.set_default_dtype(torch.float64)      # the reference builds its `ones` in the default dtype
+        try:
+            want = ref.full_attention_conv(qd, kd, vd, "simple")
+        finally:
+            torch.set_default_dtype(torch.float32)
+        assert O.rel_err(O.simple_attention(qd, kd, vd), want) < 1e-12
     nn_ = torch.tensor([3, 10, 1, 25])
     q, k, v = O.synthetic_qkv(39, 1, 16, seed=4)
     assert O.rel_err(O.segmented_simple_attention(q, k, v, nn_),
