@@ -23,12 +23,10 @@ def _attn(name, c, dtype):
 @pytest.mark.parametrize("name", sorted(ATT))
 def test_attention_forward_matches_reference_output(name):
     c = ATT[name]
-    # column-centred V makes u = sum(V) a pure-cancellation quantity: the reference's own fp32
-    # output then carries ~1e-4 relative noise, so those cases get the north-star 1e-3 bound
-    centred = float(c["v"].sum(0).abs().max()) < 1e-3
-    tol = 1e-3 if centred else 1e-5
+    # nearly-centred V (the adversarial generator) amplifies fp32 summation noise in u = sum(V)
+    tol = 2e-4 if abs(float(c["v"].mean())) < 0.05 else 1e-5
     assert O.rel_err(_attn(name, c, torch.float32), c["out"]) < tol
-    assert O.rel_err(_attn(name, c, torch.float64), c["out"]) < (tol if centred else 2e-6)
+    assert O.rel_err(_attn(name, c, torch.float64), c["out"]) < tol
 
 
 @pytest.mark.parametrize("name", sorted(ATT))
@@ -107,8 +105,8 @@ def test_oracle_against_live_reference_random_shapes():
     gen = torch.Generator().manual_seed(0)
     for n, h, d, hv in [(50, 1, 8, 1), (200, 4, 64, 4), (77, 3, 16, 1), (1, 2, 4, 2), (513, 2, 32, 2)]:
         q, k, v = O.synthetic_qkv(n, h, d, seed=n, hv=hv, adversarial=True)
-        # centred V => fp32 cancellation noise in the reference itself; fp64 arbiter below is tight
-        assert O.rel_err(O.simple_attention(q, k, v), ref.full_attention_conv(q, k, v, "simple")) < 1e-3
+        # nearly-centred V amplifies fp32 summation noise; the fp64 arbiter below is tight
+        assert O.rel_err(O.simple_attention(q, k, v), ref.full_attention_conv(q, k, v, "simple")) < 2e-4
         assert O.rel_err(O.sigmoid_attention(q * .2, k * .2, v), ref.full_attention_conv(q * .2, k * .2, v, "sigmoid")) < 1e-5
         ei = torch.randint(0, n, (2, 5 * n), generator=gen)
         w = torch.rand(5 * n, generator=gen)
