@@ -1,0 +1,86 @@
+// C ABI glue: error reporting, capability query and the 'simple' forward dispatch
+// (tcgen05 path when the shape qualifies, generic FFMA path otherwise).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dif {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char* file, int line) {
+    const char* base = strrchr(file, '/');
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line);
+    (void)cudaGetLastError();   // clear the sticky-free error so later calls can proceed
+    return DIF_ECUDA;
+}
+
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" int dif_version(void) { return 100; }   // 0.1.0
+
+extern "C" const char* dif_last_error(void) { return g_err; }
+
+extern "C" int dif_device_supported(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return major == 10 ? 1 : 0;
+}
+
+extern "C" int64_t dif_simple_partials_len(int H, int Hv, int M, int D) { return SimpleLayout{H, Hv, M, D}.len(); }
+
+extern "C" int64_t dif_simple_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
+    if (N < 1 || H < 1 || M < 1 || D < 1) return -1;
+    int64_t a = simple_generic_workspace_bytes(N, H, Hv, M, D);
+    int64_t b = simple_tc_supported(N, H, Hv, M, D) ? simple_tc_workspace_bytes(N, H, Hv, M, D) : 0;
+    return a > b ? a : b;
+}
+
+static int pick_impl(int impl, int64_t N, int H, int Hv, int M, int D, bool* use_tc) {
+    const bool ok = simple_tc_supported(N, H, Hv, M, D);
+    if (impl == DIF_IMPL_AUTO) { *use_tc = ok; return DIF_OK; }
+    if (impl == DIF_IMPL_GENERIC) { *use_tc = false; return DIF_OK; }
+    if (impl == DIF_IMPL_TCGEN05) {
+        DIF_REQUIRE(ok, DIF_EUNSUPPORTED, "simple: tcgen05 path needs M == D == 64, Hv == H, H even (got H=%d Hv=%d M=%d D=%d)", H, Hv, M, D);
+        *use_tc = true;
+        return DIF_OK;
+    }
+    return set_error(DIF_EARG, "simple: unknown impl %d", impl);
+}
+
+extern "C" int dif_simple_reduce(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
+                                 float* partials, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+    DIF_REQUIRE(q && k && v && partials && workspace, DIF_EARG, "simple_reduce: null pointer");
+    bool tc = false;
+    int rc = pick_impl(impl, N, H, Hv, M, D, &tc);
+    if (rc) return rc;
+    return tc ? simple_reduce_tc(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream)
+              : simple_reduce_generic(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dif_simple_apply(const float* q, const float* partials, double n_total, int64_t N, int H, int Hv, int M, int D,
+                                float* out, const dif_epilogue_t* epilogue, int impl, void* stream) {
+    DIF_REQUIRE(q && partials && out, DIF_EARG, "simple_apply: null pointer");
+    DIF_REQUIRE(n_total > 0, DIF_EARG, "simple_apply: n_total must be positive");
+    if (epilogue) {
+        DIF_REQUIRE(epilogue->n_add >= 0 && epilogue->n_add <= 3, DIF_EARG, "simple_apply: n_add=%d", epilogue->n_add);
+        for (int j = 0; j < epilogue->n_add; ++j) DIF_REQUIRE(epilogue->add[j], DIF_EARG, "simple_apply: addend %d is null", j);
+    }
+    bool tc = false;
+    int rc = pick_impl(impl, N, H, Hv, M, D, &tc);
+    if (rc) return rc;
+    return tc ? simple_apply_tc(q, partials, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream)
+              : simple_apply_generic(q, partials, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream);
+}

@@ -1,0 +1,100 @@
+// Shared helpers for the difformer_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/difformer_b200.h"
+
+namespace dif {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* file, int line);
+
+#define DIF_CUDA_OK(expr)                                                  \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return dif::cuda_error(_e, __FILE__, __LINE__); \
+    } while (0)
+
+#define DIF_LAUNCH_OK() DIF_CUDA_OK(cudaGetLastError())
+
+#define DIF_REQUIRE(cond, code, ...)                       \
+    do {                                                   \
+        if (!(cond)) return dif::set_error(code, __VA_ARGS__); \
+    } while (0)
+
+// ---- partial-buffer layouts (floats) --------------------------------------------------------
+struct SimpleLayout {
+    int H, Hv, M, D;
+    __host__ __device__ int64_t offS() const { return 0; }
+    __host__ __device__ int64_t offZ() const { return (int64_t)H * M * D; }
+    __host__ __device__ int64_t offU() const { return offZ() + (int64_t)H * M; }
+    __host__ __device__ int64_t offSq() const { return offU() + (int64_t)Hv * D; }
+    __host__ __device__ int64_t offSk() const { return offSq() + 1; }
+    __host__ __device__ int64_t len() const { return offSk() + 1; }
+    // per-chunk workspace record of the generic reduce: sq/sk get one slot per head
+    __host__ __device__ int64_t wsLen() const { return offSq() + 2 * (int64_t)H; }
+};
+
+struct BwdLayout {
+    int H, M, D;
+    __host__ __device__ int64_t offS() const { return 0; }
+    __host__ __device__ int64_t offZ() const { return (int64_t)H * M * D; }
+    __host__ __device__ int64_t offU() const { return offZ() + (int64_t)H * M; }
+    __host__ __device__ int64_t offTq() const { return offU() + (int64_t)H * D; }
+    __host__ __device__ int64_t offTk() const { return offTq() + 1; }
+    __host__ __device__ int64_t len() const { return offTk() + 1; }
+    __host__ __device__ int64_t wsLen() const { return offTq() + (int64_t)H; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in every thread; `red` is >= 33 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nw ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---- implemented in the per-feature translation units ----------------------------------------
+int simple_reduce_generic(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
+                          float* partials, void* ws, int64_t ws_bytes, cudaStream_t st);
+int simple_apply_generic(const float* q, const float* partials, double n_total, int64_t N, int H, int Hv, int M, int D,
+                         float* out, const dif_epilogue_t* ep, cudaStream_t st);
+int64_t simple_generic_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
+
+bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D);
+int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
+int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
+                     float* partials, void* ws, int64_t ws_bytes, cudaStream_t st);
+int simple_apply_tc(const float* q, const float* partials, double n_total, int64_t N, int H, int Hv, int M, int D,
+                    float* out, const dif_epilogue_t* ep, cudaStream_t st);
+
+}  // namespace dif

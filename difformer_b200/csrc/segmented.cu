@@ -1,0 +1,475 @@
+// Batched-graph 'simple' attention -- TransConv.full_attention, physical particle/difformer-v2.py:80-111.
+//
+// The reference pads every graph to [B, maxN, H, D] with Python loops over the B graphs
+// (make_batch_mask / make_batch, :8-20; 164 ms per call at B = 8192) and runs the einsums on the
+// padded tensors.  Semantics: per graph g with n_g rows,
+//     out_n = (q^_n S^_g + u_g) / (q^_n z^_g + n_g)         (:96-109)
+// with S_g, z_g, u_g summed over the rows of g only, but ||Q||_F, ||K||_F taken over the whole batch
+// (:82-83).  Here: no padding and no host loop -- seg_ptr[B+1] on device, one CTA per graph, which
+// builds S_g in registers/shared memory and applies it to its own rows straight away.
+//
+// Backward = per-graph a-1b with two global scalars (t_q, t_k):
+//   phase A: per graph t_q,g and t_k,g -> summed in fixed order (deterministic)
+//   phase B: per graph recompute S_g, dS_g and emit dq, dk, dv.
+#include "common.cuh"
+#include "tile.cuh"
+
+namespace dif {
+namespace {
+
+constexpr int kSegRows = 32;
+
+struct SegArgs {
+    const float *q, *k, *v, *g, *out;
+    const int32_t* seg;
+    const float* norms;   // [sum q^2, sum k^2]
+    const float* scal;    // bwd phase B: [t_q, t_k]
+    int64_t N;
+    int B, H, Hv, M, D;
+    float *o, *dq, *dk, *dv;
+    float* part;          // bwd phase A: [B][2]
+};
+
+__device__ __forceinline__ void seg_load(float* __restrict__ dst, int ld, const float* __restrict__ src, int64_t row0, int nr,
+                                         int heads, int head, int W) {
+    const int w4 = W >> 2;
+    for (int idx = threadIdx.x; idx < kSegRows * w4; idx += kThreads) {
+        const int r = idx / w4, c4 = idx - r * w4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nr) x = ldg4(src + ((row0 + r) * heads + head) * W + 4 * c4);
+        *reinterpret_cast<float4*>(dst + r * ld + 4 * c4) = x;
+    }
+}
+
+// S[M][D] (+ z[M], u[D]) of rows [s,e) of head h into shared memory (raw, un-normalised).
+// `wrow` (optional, shared) weights the z sum per row; A rows come from `a`, B rows from sb tiles
+// already prepared by the caller when PREP (backward: B = dnum).
+template <int TPT>
+__device__ __forceinline__ void seg_store_tiles(float (&acc)[TPT][4][4], float* __restrict__ Sd, int D, int tilesD, int ntile, float scale) {
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+        const int tile = threadIdx.x + t * kThreads;
+        if (tile < ntile) {
+            const int mi = tile / tilesD, di = tile - mi * tilesD;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(Sd + (4 * mi + i) * D + 4 * di) =
+                    make_float4(acc[t][i][0] * scale, acc[t][i][1] * scale, acc[t][i][2] * scale, acc[t][i][3] * scale);
+        }
+    }
+}
+
+template <int TPT>
+__device__ __forceinline__ void zero_acc(float (&acc)[TPT][4][4]) {
+#pragma unroll
+    for (int t = 0; t < TPT; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+}
+
+// forward reduce of one graph/head: Ws = c*S_g, zs = c*z_g, us = u_g
+template <int TPT>
+__device__ __forceinline__ void seg_reduce_kv(const SegArgs& p, int64_t s, int64_t e, int h, int hv, float c,
+                                              float* Ws, float* zs, float* us, float* ta, float* tb) {
+    const int M = p.M, D = p.D, lda = M + 4, ldb = D + 4;
+    const int tid = threadIdx.x, tilesD = D >> 2, ntile = (M >> 2) * tilesD;
+    float acc[TPT][4][4];
+    zero_acc<TPT>(acc);
+    float zacc = 0.f, uacc = 0.f;
+    for (int64_t r0 = s; r0 < e; r0 += kSegRows) {
+        const int nr = (int)min((int64_t)kSegRows, e - r0);
+        seg_load(ta, lda, p.k, r0, nr, p.H, h, M);
+        seg_load(tb, ldb, p.v, r0, nr, p.Hv, hv, D);
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            const int tile = tid + t * kThreads;
+            if (tile < ntile) tile_atb_acc(ta, lda, tb, ldb, kSegRows, tile / tilesD, tile % tilesD, acc[t]);
+        }
+        if (tid < M) { for (int r = 0; r < kSegRows; ++r) zacc += ta[r * lda + tid]; }
+        else if (tid < M + D) { for (int r = 0; r < kSegRows; ++r) uacc += tb[r * ldb + tid - M]; }
+        __syncthreads();
+    }
+    seg_store_tiles<TPT>(acc, Ws, D, tilesD, ntile, c);
+    if (tid < M) zs[tid] = zacc * c;
+    else if (tid < M + D) us[tid - M] = uacc;
+    __syncthreads();
+}
+
+template <int TPT>
+__global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int M = p.M, D = p.D, H = p.H;
+    const int lda = M + 4, ldb = D + 4;
+    float* Ws = smem;                       // [M][D]
+    float* zs = Ws + M * D;                 // [M]
+    float* us = zs + M;                     // [D]
+    float* ta = us + D;                     // [32][M+4]
+    float* tb = ta + kSegRows * lda;        // [32][D+4]
+    float* sden = tb + kSegRows * ldb;      // [32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+    const int tilesJ = D >> 2, ntileA = (kSegRows >> 2) * tilesJ;
+    for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
+        const int64_t s = p.seg[g], e = p.seg[g + 1];
+        if (e <= s) continue;
+        const float ng = (float)(e - s);
+        for (int h = 0; h < H; ++h) {
+            const int hv = (p.Hv == H) ? h : 0;
+            seg_reduce_kv<TPT>(p, s, e, h, hv, c, Ws, zs, us, ta, tb);
+            for (int64_t r0 = s; r0 < e; r0 += kSegRows) {
+                const int nr = (int)min((int64_t)kSegRows, e - r0);
+                seg_load(ta, lda, p.q, r0, nr, H, h, M);
+                __syncthreads();
+                for (int r = warp; r < kSegRows; r += kThreads / 32) {
+                    float qz = 0.f;
+                    for (int i = lane; i < M; i += 32) qz = fmaf(ta[r * lda + i], zs[i], qz);
+                    qz = warp_sum(qz);
+                    if (lane == 0) sden[r] = qz + ng;
+                }
+                __syncthreads();
+                for (int tile = tid; tile < ntileA; tile += kThreads) {
+                    const int ri = tile / tilesJ, ji = tile - ri * tilesJ;
+                    float acc[4][4];
+                    tile_mm(ta, lda, Ws, D, M, ri, ji, acc);
+                    const float4 u4 = *reinterpret_cast<const float4*>(us + 4 * ji);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = 4 * ri + a;
+                        if (r >= nr) continue;
+                        const float den = sden[r];
+                        *reinterpret_cast<float4*>(p.o + ((r0 + r) * H + h) * D + 4 * ji) =
+                            make_float4((acc[a][0] + u4.x) / den, (acc[a][1] + u4.y) / den, (acc[a][2] + u4.z) / den, (acc[a][3] + u4.w) / den);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// backward reduce of one graph/head given Ws=c*S, zs=c*z, us=u: dS (raw, scaled by `scale` into
+// dWs), dzs = scale*dz, dus = du; returns this thread's t_q contribution and, through `tk`, its
+// share of sum S o dS + z . dz (both raw*c products).
+template <int TPT>
+__device__ __forceinline__ void seg_reduce_bwd(const SegArgs& p, int64_t s, int64_t e, int h, float ng, float scale,
+                                               const float* Ws, const float* zs, const float* us,
+                                               float* dWs, float* dzs, float* dus,
+                                               float* tq_, float* tg, float* to, float* sw, float& tq, float& tk) {
+    const int M = p.M, D = p.D, H = p.H, lda = M + 4, ldb = D + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tilesD = D >> 2, ntile = (M >> 2) * tilesD;
+    float acc[TPT][4][4];
+    zero_acc<TPT>(acc);
+    float zacc = 0.f, uacc = 0.f;
+    for (int64_t r0 = s; r0 < e; r0 += kSegRows) {
+        const int nr = (int)min((int64_t)kSegRows, e - r0);
+        seg_load(tq_, lda, p.q, r0, nr, H, h, M);
+        seg_load(tg, ldb, p.g, r0, nr, H, h, D);
+        seg_load(to, ldb, p.out, r0, nr, H, h, D);
+        __syncthreads();
+        for (int r = warp; r < kSegRows; r += kThreads / 32) {
+            float qz = 0.f, go = 0.f, gu = 0.f;
+            for (int i = lane; i < M; i += 32) qz = fmaf(tq_[r * lda + i], zs[i], qz);
+            for (int i = lane; i < D; i += 32) {
+                const float gg = tg[r * ldb + i];
+                go = fmaf(gg, to[r * ldb + i], go);
+                gu = fmaf(gg, us[i], gu);
+            }
+            qz = warp_sum(qz); go = warp_sum(go); gu = warp_sum(gu);
+            const float inv = 1.f / (qz + ng);
+            const float dden = -go * inv;
+            for (int i = lane; i < D; i += 32) tg[r * ldb + i] *= inv;
+            if (lane == 0) { sw[r] = dden; if (r < nr) tq += go - inv * gu + dden * qz; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            const int tile = tid + t * kThreads;
+            if (tile < ntile) tile_atb_acc(tq_, lda, tg, ldb, kSegRows, tile / tilesD, tile % tilesD, acc[t]);
+        }
+        if (tid < M) { for (int r = 0; r < kSegRows; ++r) zacc = fmaf(tq_[r * lda + tid], sw[r], zacc); }
+        else if (tid < M + D) { for (int r = 0; r < kSegRows; ++r) uacc += tg[r * ldb + tid - M]; }
+        __syncthreads();
+    }
+    // t_k share: (c S) o dS_raw  + (c z) . dz_raw
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+        const int tile = tid + t * kThreads;
+        if (tile < ntile) {
+            const int mi = tile / tilesD, di = tile - mi * tilesD;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tk = fmaf(Ws[(4 * mi + i) * D + 4 * di + j], acc[t][i][j], tk);
+        }
+    }
+    if (tid < M) tk = fmaf(zs[tid], zacc, tk);
+    if (dWs) {
+        seg_store_tiles<TPT>(acc, dWs, D, tilesD, ntile, scale);
+        if (tid < M) dzs[tid] = zacc * scale;
+        else if (tid < M + D) dus[tid - M] = uacc;
+    }
+    __syncthreads();
+}
+
+template <int TPT>
+__global__ void __launch_bounds__(kThreads) seg_bwd_scalars_kernel(SegArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int M = p.M, D = p.D, H = p.H, lda = M + 4, ldb = D + 4;
+    float* Ws = smem;
+    float* zs = Ws + M * D;
+    float* us = zs + M;
+    float* ta = us + D;
+    float* tb = ta + kSegRows * lda;
+    float* tc = tb + kSegRows * ldb;
+    float* sw = tc + kSegRows * ldb;
+    float* red = sw + kSegRows;
+    const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+    for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
+        const int64_t s = p.seg[g], e = p.seg[g + 1];
+        float tq = 0.f, tk = 0.f;
+        if (e > s) {
+            for (int h = 0; h < H; ++h) {
+                const int hv = (p.Hv == H) ? h : 0;
+                seg_reduce_kv<TPT>(p, s, e, h, hv, c, Ws, zs, us, ta, tb);
+                seg_reduce_bwd<TPT>(p, s, e, h, (float)(e - s), 1.f, Ws, zs, us, nullptr, nullptr, nullptr, ta, tb, tc, sw, tq, tk);
+            }
+        }
+        const float a = block_sum(tq, red);
+        const float b = block_sum(tk, red);
+        if (threadIdx.x == 0) { p.part[2 * (int64_t)g] = a; p.part[2 * (int64_t)g + 1] = b; }
+    }
+}
+
+__global__ void seg_sum_pairs_kernel(const float* __restrict__ part, int64_t n, float* __restrict__ out2) {
+    __shared__ float red[33];
+    double a = 0.0, b = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { a += (double)part[2 * i]; b += (double)part[2 * i + 1]; }
+    const float fa = block_sum((float)a, red);
+    const float fb = block_sum((float)b, red);
+    if (threadIdx.x == 0) { out2[0] = fa; out2[1] = fb; }
+}
+
+template <int TPT>
+__global__ void __launch_bounds__(kThreads) seg_bwd_main_kernel(SegArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int M = p.M, D = p.D, H = p.H, lda = M + 4, ldb = D + 4;
+    float* Ws = smem;                      // c*S_g
+    float* dWs = Ws + M * D;               // c*dS_g
+    float* zs = dWs + M * D;               // c*z
+    float* us = zs + M;                    // u
+    float* dzs = us + D;                   // c*dz
+    float* dus = dzs + M;                  // du
+    float* ta = dus + D;                   // [32][M+4]  q / k
+    float* tb = ta + kSegRows * lda;       // [32][D+4]  g->dnum / v
+    float* tc = tb + kSegRows * ldb;       // [32][D+4]  out
+    float* sw = tc + kSegRows * ldb;       // [32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float sq = p.norms[0], sk = p.norms[1];
+    const float c = 1.f / (sqrtf(sq) * sqrtf(sk));
+    const float tq_over = p.scal[0] / sq, tk_over = p.scal[1] / sk;
+    const int tilesM = M >> 2, ntM = (kSegRows >> 2) * tilesM;   // outputs with M columns (dq, dk)
+    const int tilesD = D >> 2, ntD = (kSegRows >> 2) * tilesD;   // dv
+    const int BS = M >> 2;                                        // interleave stride of tile_abt B rows
+    const bool bcast = (p.Hv != H);
+    for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
+        const int64_t s = p.seg[g], e = p.seg[g + 1];
+        if (e <= s) continue;
+        const float ng = (float)(e - s);
+        for (int h = 0; h < H; ++h) {
+            const int hv = bcast ? 0 : h;
+            float dummy_q = 0.f, dummy_k = 0.f;
+            seg_reduce_kv<TPT>(p, s, e, h, hv, c, Ws, zs, us, ta, tb);
+            seg_reduce_bwd<TPT>(p, s, e, h, ng, c, Ws, zs, us, dWs, dzs, dus, ta, tb, tc, sw, dummy_q, dummy_k);
+            for (int64_t r0 = s; r0 < e; r0 += kSegRows) {
+                const int nr = (int)min((int64_t)kSegRows, e - r0);
+                // ---- dq = dnum (cS)^T + dden (cz) - q t_q/sq
+                seg_load(ta, lda, p.q, r0, nr, H, h, M);
+                seg_load(tb, ldb, p.g, r0, nr, H, h, D);
+                seg_load(tc, ldb, p.out, r0, nr, H, h, D);
+                __syncthreads();
+                for (int r = warp; r < kSegRows; r += kThreads / 32) {
+                    float qz = 0.f, go = 0.f;
+                    for (int i = lane; i < M; i += 32) qz = fmaf(ta[r * lda + i], zs[i], qz);
+                    for (int i = lane; i < D; i += 32) go = fmaf(tb[r * ldb + i], tc[r * ldb + i], go);
+                    qz = warp_sum(qz); go = warp_sum(go);
+                    const float inv = 1.f / (qz + ng);
+                    for (int i = lane; i < D; i += 32) tb[r * ldb + i] *= inv;
+                    if (lane == 0) sw[r] = -go * inv;
+                }
+                __syncthreads();
+                for (int tile = tid; tile < ntM; tile += kThreads) {
+                    const int ri = tile / tilesM, ci = tile - ri * tilesM;
+                    float acc[4][4];
+                    // acc[a][b] = sum_d dnum[4ri+a][d] * cS[ci + BS*b][d]
+                    if (BS == 16) tile_abt<16>(tb, ldb, Ws, D, D, ri, ci, acc);
+                    else if (BS == 8) tile_abt<8>(tb, ldb, Ws, D, D, ri, ci, acc);
+                    else tile_abt<4>(tb, ldb, Ws, D, D, ri, ci, acc);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = 4 * ri + a;
+                        if (r >= nr) continue;
+                        const float dd = sw[r];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int m = ci + BS * b;
+                            p.dq[((r0 + r) * H + h) * M + m] = acc[a][b] + dd * zs[m] - ta[r * lda + m] * tq_over;
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- dk = v (c dS)^T + c dz - k t_k/sk ;  dv = k (c dS) + du
+                seg_load(ta, lda, p.k, r0, nr, H, h, M);
+                seg_load(tb, ldb, p.v, r0, nr, p.Hv, hv, D);
+                __syncthreads();
+                for (int tile = tid; tile < ntM; tile += kThreads) {
+                    const int ri = tile / tilesM, ci = tile - ri * tilesM;
+                    float acc[4][4];
+                    if (BS == 16) tile_abt<16>(tb, ldb, dWs, D, D, ri, ci, acc);
+                    else if (BS == 8) tile_abt<8>(tb, ldb, dWs, D, D, ri, ci, acc);
+                    else tile_abt<4>(tb, ldb, dWs, D, D, ri, ci, acc);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = 4 * ri + a;
+                        if (r >= nr) continue;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int m = ci + BS * b;
+                            p.dk[((r0 + r) * H + h) * M + m] = acc[a][b] + dzs[m] - ta[r * lda + m] * tk_over;
+                        }
+                    }
+                }
+                for (int tile = tid; tile < ntD; tile += kThreads) {
+                    const int ri = tile / tilesD, ji = tile - ri * tilesD;
+                    float acc[4][4];
+                    tile_mm(ta, lda, dWs, D, M, ri, ji, acc);
+                    const float4 u4 = *reinterpret_cast<const float4*>(dus + 4 * ji);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = 4 * ri + a;
+                        if (r >= nr) continue;
+                        float4* dst = reinterpret_cast<float4*>(p.dv + ((r0 + r) * p.Hv + hv) * D + 4 * ji);
+                        float4 o = make_float4(acc[a][0] + u4.x, acc[a][1] + u4.y, acc[a][2] + u4.z, acc[a][3] + u4.w);
+                        if (bcast && h > 0) {     // V shared by all heads: accumulate (same thread, same address, fixed order)
+                            const float4 prev = *dst;
+                            o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                        }
+                        *dst = o;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+__global__ void sumsq2_stage1(const float* __restrict__ q, const float* __restrict__ k, int64_t count, float* __restrict__ part) {
+    __shared__ float red[33];
+    float a = 0.f, b = 0.f;
+    const int64_t n4 = count >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = ldg4(q + 4 * i), y = ldg4(k + 4 * i);
+        a += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        b += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = 4 * n4 + threadIdx.x; i < count; i += blockDim.x) { a += q[i] * q[i]; b += k[i] * k[i]; }
+    const float fa = block_sum(a, red);
+    const float fb = block_sum(b, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = fa; part[2 * blockIdx.x + 1] = fb; }
+}
+
+constexpr int kSumBlocks = 592;
+
+int seg_check(int64_t N, int B, int H, int Hv, int M, int D, bool bwd) {
+    DIF_REQUIRE(N >= 1 && B >= 1 && H >= 1, DIF_EARG, "segmented: bad N/B/H");
+    DIF_REQUIRE(Hv == H || Hv == 1, DIF_EARG, "segmented: Hv=%d must equal H=%d or 1", Hv, H);
+    DIF_REQUIRE(M >= 4 && D >= 4 && (M % 4) == 0 && (D % 4) == 0 && M <= 128 && D <= 128, DIF_EUNSUPPORTED,
+                "segmented: need M,D multiples of 4 in [4,128] (got M=%d D=%d)", M, D);
+    if (bwd)
+        DIF_REQUIRE((M == 16 || M == 32 || M == 64) && D <= 64, DIF_EUNSUPPORTED,
+                    "segmented backward: need M in {16,32,64} and D <= 64 (got M=%d D=%d)", M, D);
+    return DIF_OK;
+}
+
+template <typename K>
+int seg_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) DIF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DIF_OK;
+}
+
+}  // namespace
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" int64_t dif_segmented_workspace_bytes(int32_t B) {
+    const int64_t n = (int64_t)(B > kSumBlocks ? B : kSumBlocks) * 2 + 2;
+    return n * (int64_t)sizeof(float);
+}
+
+extern "C" int dif_sumsq2(const float* q, const float* k, int64_t count, float* norms, void* workspace, int64_t workspace_bytes, void* stream) {
+    DIF_REQUIRE(q && k && norms && workspace && count >= 1, DIF_EARG, "sumsq2: bad argument");
+    DIF_REQUIRE(workspace_bytes >= (int64_t)kSumBlocks * 2 * 4, DIF_EARG, "sumsq2: workspace too small");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k) & 15) == 0, DIF_EARG, "sumsq2: pointers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    sumsq2_stage1<<<kSumBlocks, 256, 0, st>>>(q, k, count, (float*)workspace);
+    DIF_LAUNCH_OK();
+    seg_sum_pairs_kernel<<<1, 1024, 0, st>>>((const float*)workspace, kSumBlocks, norms);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+extern "C" int dif_segmented_simple_fwd(const float* q, const float* k, const float* v, const int32_t* seg_ptr, int32_t B,
+                                        const float* norms, int64_t N, int H, int Hv, int M, int D, float* out, void* stream) {
+    int rc = seg_check(N, B, H, Hv, M, D, false);
+    if (rc) return rc;
+    DIF_REQUIRE(q && k && v && seg_ptr && norms && out, DIF_EARG, "segmented_fwd: null pointer");
+    SegArgs a{};
+    a.q = q; a.k = k; a.v = v; a.seg = seg_ptr; a.norms = norms; a.N = N; a.B = B; a.H = H; a.Hv = Hv; a.M = M; a.D = D; a.o = out;
+    const size_t smem = ((size_t)M * D + M + D + (size_t)kSegRows * (M + 4) + (size_t)kSegRows * (D + 4) + kSegRows) * sizeof(float);
+    const int grid = B < 148 * 16 ? B : 148 * 16;
+    const int ntile = (M / 4) * (D / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ntile <= kThreads) { if ((rc = seg_smem(seg_fwd_kernel<1>, smem))) return rc; seg_fwd_kernel<1><<<grid, kThreads, smem, st>>>(a); }
+    else if (ntile <= 2 * kThreads) { if ((rc = seg_smem(seg_fwd_kernel<2>, smem))) return rc; seg_fwd_kernel<2><<<grid, kThreads, smem, st>>>(a); }
+    else { if ((rc = seg_smem(seg_fwd_kernel<4>, smem))) return rc; seg_fwd_kernel<4><<<grid, kThreads, smem, st>>>(a); }
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
+                                        const int32_t* seg_ptr, int32_t B, const float* norms,
+                                        int64_t N, int H, int Hv, int M, int D, float* dq, float* dk, float* dv,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = seg_check(N, B, H, Hv, M, D, true);
+    if (rc) return rc;
+    DIF_REQUIRE(q && k && v && g && out && seg_ptr && norms && dq && dk && dv && workspace, DIF_EARG, "segmented_bwd: null pointer");
+    DIF_REQUIRE(workspace_bytes >= ((int64_t)B * 2 + 2) * 4, DIF_EARG, "segmented_bwd: workspace too small");
+    float* part = (float*)workspace;
+    float* scal = part + 2 * (int64_t)B;
+    SegArgs a{};
+    a.q = q; a.k = k; a.v = v; a.g = g; a.out = out; a.seg = seg_ptr; a.norms = norms; a.scal = scal;
+    a.N = N; a.B = B; a.H = H; a.Hv = Hv; a.M = M; a.D = D; a.dq = dq; a.dk = dk; a.dv = dv; a.part = part;
+    const int grid = B < 148 * 16 ? B : 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    // M,D <= 64 => (M/4)*(D/4) <= 256 => one 4x4 tile per thread
+    {
+        const size_t smem = ((size_t)M * D + M + D + (size_t)kSegRows * (M + 4) + 2 * (size_t)kSegRows * (D + 4) + kSegRows + 33) * sizeof(float);
+        if ((rc = seg_smem(seg_bwd_scalars_kernel<1>, smem))) return rc;
+        seg_bwd_scalars_kernel<1><<<grid, kThreads, smem, st>>>(a);
+        DIF_LAUNCH_OK();
+        seg_sum_pairs_kernel<<<1, 1024, 0, st>>>(part, B, scal);
+        DIF_LAUNCH_OK();
+    }
+    {
+        const size_t smem = (2 * (size_t)M * D + 2 * (size_t)(M + D) + (size_t)kSegRows * (M + 4) + 2 * (size_t)kSegRows * (D + 4) + kSegRows) * sizeof(float);
+        if ((rc = seg_smem(seg_bwd_main_kernel<1>, smem))) return rc;
+        seg_bwd_main_kernel<1><<<grid, kThreads, smem, st>>>(a);
+        DIF_LAUNCH_OK();
+    }
+    return DIF_OK;
+}

@@ -1,0 +1,279 @@
+"""nn.Module shell of the reference model, kept name-for-name so the reference harnesses and
+checkpoints work unchanged:
+
+  DIFFormerConv / DIFFormer   <- node classification/difformer.py:81-226
+  TransConv / DIFFormer_v2    <- physical particle/difformer-v2.py:48-223
+
+Submodule names (`convs.{i}.Wq/Wk/Wv`, `fcs.{0,1}`, `bns.{i}`) and ctor signatures are the
+reference's; no extra parameters or persistent buffers are added, so `state_dict()` round-trips
+with reference checkpoints (test_large_dataset.py:86-88).  Linear / LayerNorm / dropout stay
+PyTorch (cuBLAS); the propagation between them runs in libdifformer_b200.so.
+
+Two execution paths through a layer:
+  * grad needed  : unfused ops (`full_attention_conv`, `gcn_conv`) with hand-written CUDA backward;
+  * no grad      : pass 2 of 'simple' carries the whole layer epilogue (head mean, gcn term,
+                   x_0, residual blend, difformer.py:129-140,200-201) -- one write of [N,D].
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _fusable(kernel, *tensors):
+    if kernel != "simple":
+        return False
+    if not torch.is_grad_enabled():
+        return True
+    return not any(t is not None and t.requires_grad for t in tensors)
+
+
+def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0, output_attn,
+                  residual=None, n_nodes=None):
+    """Shared body of DIFFormerConv.forward / TransConv.forward.
+
+    residual = (alpha, prev) folds `alpha*x + (1-alpha)*prev` (difformer.py:200-201) into the fused
+    epilogue; the return flag says whether it was applied."""
+    H, C = conv.num_heads, conv.out_channels
+    query = conv.Wq(query_input).reshape(-1, H, C)
+    key = conv.Wk(source_input).reshape(-1, H, C)
+    if conv.use_weight:
+        value = conv.Wv(source_input).reshape(-1, H, C)
+    else:
+        value = source_input.reshape(-1, 1, C)                      # difformer.py:120
+    segmented = n_nodes is not None
+    use_source = getattr(conv, "use_source", False)
+    gw = conv.graph_weight
+    w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
+
+    if (not output_attn) and (not segmented) and _fusable(conv.kernel, query, key, value, x_0,
+                                                          None if residual is None else residual[1]):
+        # ---- fused inference path: everything after the Linears is two kernels (+ one SpMM)
+        q, k, v = ops._f32c(query), ops._f32c(key), ops._f32c(value)
+        ops._need_cuda(q, k, v)
+        N = q.shape[0]
+        alpha = 1.0 if residual is None else float(residual[0])
+        partials = ops.simple_partials(q, k, v)
+        addends = []
+        if conv.use_graph:
+            csr = ops.graph_csr(edge_index, edge_weight, N)
+            if v.shape[2] in (32, 64, 128) and v.shape[1] <= 8:
+                gmean = ops.spmm(csr, v, head_mean=True)            # mean over heads commutes with the SpMM
+            else:
+                gmean = ops.spmm(csr, v).mean(dim=1)
+            addends.append((gmean, alpha * w_gcn))
+        if use_source:
+            addends.append((ops._f32c(x_0), alpha))
+        if residual is not None:
+            addends.append((ops._f32c(residual[1]), 1.0 - alpha))
+        ep = ops.make_epilogue(alpha * w_attn / H, addends)
+        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=addends)
+        return out, None, residual is not None
+
+    # ---- unfused path (training, sigmoid, batched graphs, attention visualisation)
+    attn = None
+    if segmented:
+        attention_output = ops.segmented_full_attention(query, key, value, conv.kernel, n_nodes)
+    elif output_attn:
+        attention_output, attn = ops.full_attention_conv(query, key, value, conv.kernel, True)
+    else:
+        attention_output = ops.full_attention_conv(query, key, value, conv.kernel)
+    if conv.use_graph:
+        g = ops.gcn_conv(value, edge_index, edge_weight)
+        final_output = w_attn * attention_output + w_gcn * g if gw > 0 else attention_output + g
+    else:
+        final_output = attention_output
+    final_output = final_output.mean(dim=1)
+    if use_source:
+        final_output = final_output + x_0
+    return final_output, attn, False
+
+
+class DIFFormerConv(nn.Module):
+    """one DIFFormer layer (difformer.py:81-145)"""
+
+    def __init__(self, in_channels, out_channels, num_heads, kernel='simple', use_graph=True, use_weight=True,
+                 graph_weight=-1, use_source=False):
+        super(DIFFormerConv, self).__init__()
+        self.Wk = nn.Linear(in_channels, out_channels * num_heads)
+        self.Wq = nn.Linear(in_channels, out_channels * num_heads)
+        if use_weight:
+            self.Wv = nn.Linear(in_channels, out_channels * num_heads)
+        self.out_channels = out_channels
+        self.num_heads = num_heads
+        self.kernel = kernel
+        self.use_graph = use_graph
+        self.use_weight = use_weight
+        self.graph_weight = graph_weight
+        self.use_source = use_source
+
+    def reset_parameters(self):
+        self.Wk.reset_parameters()
+        self.Wq.reset_parameters()
+        if self.use_weight:
+            self.Wv.reset_parameters()
+
+    def forward(self, query_input, source_input, edge_index=None, edge_weight=None, x_0=None, output_attn=False,
+                _residual=None):
+        out, attn, fused_res = _conv_forward(self, query_input, source_input, edge_index, edge_weight, x_0,
+                                             output_attn, residual=_residual)
+        if _residual is not None:
+            return out, fused_res
+        return (out, attn) if output_attn else out
+
+
+class DIFFormer(nn.Module):
+    """DIFFormer model class (difformer.py:147-226)
+    x: input node features [N, D]; edge_index: [2, E]; returns logits [N, C]"""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers=2, num_heads=1, kernel='simple',
+                 alpha=0.5, dropout=0.5, use_bn=True, use_residual=True, use_weight=True, use_graph=True,
+                 graph_weight=-1, use_source=False):
+        super(DIFFormer, self).__init__()
+        self.convs = nn.ModuleList()
+        self.fcs = nn.ModuleList()
+        self.fcs.append(nn.Linear(in_channels, hidden_channels))
+        self.bns = nn.ModuleList()
+        self.bns.append(nn.LayerNorm(hidden_channels))
+        for i in range(num_layers):
+            self.convs.append(DIFFormerConv(hidden_channels, hidden_channels, num_heads=num_heads, kernel=kernel,
+                                            use_graph=use_graph, use_weight=use_weight, graph_weight=graph_weight,
+                                            use_source=use_source))
+            self.bns.append(nn.LayerNorm(hidden_channels))
+        self.fcs.append(nn.Linear(hidden_channels, out_channels))
+        self.dropout = dropout
+        self.activation = F.relu
+        self.use_bn = use_bn
+        self.residual = use_residual
+        self.alpha = alpha
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        for bn in self.bns:
+            bn.reset_parameters()
+        for fc in self.fcs:
+            fc.reset_parameters()
+
+    def forward(self, x, edge_index, edge_weight=None):
+        layer_ = []
+        x = self.fcs[0](x)
+        if self.use_bn:
+            x = self.bns[0](x)
+        x = self.activation(x)
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        layer_.append(x)
+        for i, conv in enumerate(self.convs):
+            res = (self.alpha, layer_[i]) if self.residual else (1.0, None)
+            if self.residual:
+                x, fused = conv(x, x, edge_index, edge_weight, layer_[0], _residual=res)
+                if not fused:
+                    x = self.alpha * x + (1 - self.alpha) * layer_[i]
+            else:
+                x = conv(x, x, edge_index, edge_weight, layer_[0])
+            if self.use_bn:
+                x = self.bns[i + 1](x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+            layer_.append(x)
+        return self.fcs[-1](x)
+
+    def get_attentions(self, x):
+        layer_, attentions = [], []
+        x = self.fcs[0](x)
+        if self.use_bn:
+            x = self.bns[0](x)
+        x = self.activation(x)
+        layer_.append(x)
+        for i, conv in enumerate(self.convs):
+            x, attn = conv(x, x, output_attn=True)
+            attentions.append(attn)
+            if self.residual:
+                x = self.alpha * x + (1 - self.alpha) * layer_[i]
+            if self.use_bn:
+                x = self.bns[i + 1](x)
+            layer_.append(x)
+        return torch.stack(attentions, dim=0)
+
+
+class TransConv(nn.Module):
+    """batched-graph layer (difformer-v2.py:48-163); in_channels must equal out_channels when use_weight is False"""
+
+    def __init__(self, in_channels, out_channels, num_heads=1, kernel='simple', use_graph=True, use_weight=True, graph_weight=-1):
+        super().__init__()
+        self.Wk = nn.Linear(in_channels, out_channels * num_heads)
+        self.Wq = nn.Linear(in_channels, out_channels * num_heads)
+        if use_weight:
+            self.Wv = nn.Linear(in_channels, out_channels * num_heads)
+        self.out_channels = out_channels
+        self.num_heads = num_heads
+        self.kernel = kernel
+        self.use_graph = use_graph
+        self.use_weight = use_weight
+        self.graph_weight = graph_weight
+
+    def reset_parameters(self):
+        self.Wk.reset_parameters()
+        self.Wq.reset_parameters()
+        if self.use_weight:
+            self.Wv.reset_parameters()
+
+    def full_attention(self, qs, ks, vs, kernel, n_nodes):
+        return ops.segmented_full_attention(qs, ks, vs, kernel, n_nodes)
+
+    def forward(self, query_input, source_input, n_nodes, edge_index=None, edge_weight=None):
+        # the reference only binds `value` under use_weight (difformer-v2.py:149-150) and fails with
+        # UnboundLocalError otherwise; here use_weight=False uses the input like DIFFormerConv does
+        out, _, _ = _conv_forward(self, query_input, source_input, edge_index, edge_weight, None, False, n_nodes=n_nodes)
+        return out
+
+
+class DIFFormer_v2(nn.Module):
+    """difformer-v2.py:165-223; forward(x, edge_index, n_nodes)"""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers=2, kernel='simple', alpha=0.5, dropout=0.5,
+                 use_bn=True, use_residual=True, use_weight=True, use_graph=True, graph_weight=-1):
+        super().__init__()
+        self.convs = nn.ModuleList()
+        self.fcs = nn.ModuleList()
+        self.fcs.append(nn.Linear(in_channels, hidden_channels))
+        self.bns = nn.ModuleList()
+        self.bns.append(nn.LayerNorm(hidden_channels))
+        for i in range(num_layers):
+            self.convs.append(TransConv(hidden_channels, hidden_channels, kernel=kernel, use_graph=use_graph,
+                                        use_weight=use_weight, graph_weight=graph_weight))
+            self.bns.append(nn.LayerNorm(hidden_channels))
+        self.fcs.append(nn.Linear(hidden_channels, out_channels))
+        self.dropout = dropout
+        self.activation = F.relu
+        self.use_bn = use_bn
+        self.residual = use_residual
+        self.alpha = alpha
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        for bn in self.bns:
+            bn.reset_parameters()
+        for fc in self.fcs:
+            fc.reset_parameters()
+
+    def forward(self, x, edge_index, n_nodes):
+        layer_ = []
+        x = self.fcs[0](x)
+        if self.use_bn:
+            x = self.bns[0](x)
+        x = self.activation(x)
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        layer_.append(x)
+        for i, conv in enumerate(self.convs):
+            x = conv(x, x, n_nodes, edge_index)
+            if self.residual:
+                x = self.alpha * x + (1 - self.alpha) * layer_[i]
+            if self.use_bn:
+                x = self.bns[i + 1](x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+            x = self.activation(x)
+            layer_.append(x)
+        x_out = self.fcs[-1](x)
+        return F.dropout(x_out, p=self.dropout, training=self.training)

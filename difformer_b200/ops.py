@@ -1,0 +1,350 @@
+"""Host side of the hot path: torch.autograd.Functions over the C ABI (ctypes), mirroring the
+reference operators `full_attention_conv` / `gcn_conv` (node classification/difformer.py:10-79).
+
+PyTorch is plumbing here (device memory, streams, autograd graph, torch.distributed); all
+arithmetic of the path runs in libdifformer_b200.so.  There is no CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import Epilogue, check, lib
+
+_SIMPLE_IMPL = _lib.DIF_IMPL_AUTO
+
+
+def set_simple_impl(impl: str) -> None:
+    """Select the 'simple' kernels: 'auto' (tcgen05 when the shape qualifies), 'generic', 'tcgen05'."""
+    global _SIMPLE_IMPL
+    _SIMPLE_IMPL = {"auto": _lib.DIF_IMPL_AUTO, "generic": _lib.DIF_IMPL_GENERIC, "tcgen05": _lib.DIF_IMPL_TCGEN05}[impl]
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("difformer_b200: the hot path only runs on CUDA (sm_100a) tensors; "
+                               "there is no CPU fallback -- move the model and data to the GPU")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"difformer_b200: expected float32, got {t.dtype} (the reference path is fp32)")
+    return t.contiguous()
+
+
+def _shapes(qs, ks, vs) -> Tuple[int, int, int, int, int, int]:
+    if qs.dim() != 3 or ks.dim() != 3 or vs.dim() != 3:
+        raise ValueError("qs, ks, vs must be [N,H,M], [L,H,M], [L,Hv,D]")
+    N, H, M = qs.shape
+    L, Hk, Mk = ks.shape
+    Lv, Hv, D = vs.shape
+    if Hk != H or Mk != M or Lv != L or Hv not in (H, 1):
+        raise ValueError(f"inconsistent shapes qs{tuple(qs.shape)} ks{tuple(ks.shape)} vs{tuple(vs.shape)}")
+    return N, L, H, Hv, M, D
+
+
+# ----------------------------------------------------------------------------------------------
+# kernel='simple'
+# ----------------------------------------------------------------------------------------------
+def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor) -> torch.Tensor:
+    """Pass 1 on this rank's rows -> partials [S | z | u | sum q^2 | sum k^2] (fp32, additive)."""
+    N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+    if N != L:
+        raise ValueError("kernel='simple' requires N == L (difformer.py:22,29)")
+    partials = torch.empty(lib.dif_simple_partials_len(H, Hv, M, D), dtype=torch.float32, device=qs.device)
+    wsb = lib.dif_simple_workspace_bytes(N, H, Hv, M, D)
+    ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=qs.device)
+    with torch.cuda.device(qs.device):
+        check(lib.dif_simple_reduce(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D,
+                                    partials.data_ptr(), ws.data_ptr(), ws.numel(), _SIMPLE_IMPL, _stream(qs)),
+              "dif_simple_reduce")
+    return partials
+
+
+def simple_apply(qs: torch.Tensor, partials: torch.Tensor, n_total: float, Hv: int, D: int,
+                 epilogue: Optional[Epilogue] = None, keep=()) -> torch.Tensor:
+    """Pass 2.  epilogue=None -> [N,H,D]; mode-1 epilogue -> [N,D] (fused layer epilogue)."""
+    N, H, M = qs.shape
+    fused = epilogue is not None and epilogue.mode == 1
+    out = torch.empty((N, D) if fused else (N, H, D), dtype=torch.float32, device=qs.device)
+    with torch.cuda.device(qs.device):
+        check(lib.dif_simple_apply(qs.data_ptr(), partials.data_ptr(), float(n_total), N, H, Hv, M, D, out.data_ptr(),
+                                   ctypes.byref(epilogue) if epilogue is not None else None, _SIMPLE_IMPL, _stream(qs)),
+              "dif_simple_apply")
+    del keep
+    return out
+
+
+def make_epilogue(attn_scale: float, addends) -> Epilogue:
+    """addends: list of (tensor [N,D] fp32 contiguous, scale)."""
+    ep = Epilogue()
+    ep.mode, ep.attn_scale, ep.n_add = 1, float(attn_scale), len(addends)
+    for j, (t, s) in enumerate(addends):
+        ep.add[j] = t.data_ptr()
+        ep.add_scale[j] = float(s)
+    return ep
+
+
+def _allreduce(t: torch.Tensor, group) -> None:
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class _SimpleAttention(torch.autograd.Function):
+    """out = full_attention_conv(qs, ks, vs, 'simple').  With `group`, rows are a shard of a larger
+    graph: the partials (67.6 KB at H=4, D=64) are all-reduced between the two passes and
+    `n_total` is the global row count."""
+
+    @staticmethod
+    def forward(ctx, qs, ks, vs, group, n_total):
+        _need_cuda(qs, ks, vs)
+        qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
+        N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+        partials = simple_partials(qs, ks, vs)
+        _allreduce(partials, group)
+        n_tot = float(N if n_total is None else n_total)
+        out = simple_apply(qs, partials, n_tot, Hv, D)
+        ctx.save_for_backward(qs, ks, vs, out, partials)
+        ctx.group, ctx.n_tot = group, n_tot
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qs, ks, vs, out, partials = ctx.saved_tensors
+        N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+        g = _f32c(g)
+        dev = qs.device
+        bwd = torch.zeros(lib.dif_simple_bwd_partials_len(H, M, D), dtype=torch.float32, device=dev)
+        ws = torch.empty(max(int(lib.dif_simple_workspace_bytes(N, H, Hv, M, D)), 16), dtype=torch.uint8, device=dev)
+        dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
+        with torch.cuda.device(dev):
+            st = _stream(qs)
+            check(lib.dif_simple_bwd_reduce(qs.data_ptr(), g.data_ptr(), out.data_ptr(), partials.data_ptr(), ctx.n_tot,
+                                            N, H, Hv, M, D, bwd.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                  "dif_simple_bwd_reduce")
+            _allreduce(bwd, ctx.group)
+            check(lib.dif_simple_bwd_apply(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
+                                           partials.data_ptr(), bwd.data_ptr(), ctx.n_tot, N, H, Hv, M, D,
+                                           dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), st),
+                  "dif_simple_bwd_apply")
+        return dq, dk, dv, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# kernel='sigmoid'
+# ----------------------------------------------------------------------------------------------
+class _SigmoidAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qs, ks, vs):
+        _need_cuda(qs, ks, vs)
+        qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
+        N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+        out = torch.empty((N, H, D), dtype=torch.float32, device=qs.device)
+        rowsum = torch.empty((N, H), dtype=torch.float32, device=qs.device)
+        with torch.cuda.device(qs.device):
+            check(lib.dif_sigmoid_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, L, H, Hv, M, D,
+                                      out.data_ptr(), rowsum.data_ptr(), _stream(qs)), "dif_sigmoid_fwd")
+        ctx.save_for_backward(qs, ks, vs, out, rowsum)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qs, ks, vs, out, rowsum = ctx.saved_tensors
+        N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+        g = _f32c(g)
+        dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
+        wsb = int(lib.dif_sigmoid_bwd_workspace_bytes(N, L, H, Hv, M, D))
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=qs.device)
+        with torch.cuda.device(qs.device):
+            check(lib.dif_sigmoid_bwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
+                                      rowsum.data_ptr(), N, L, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream(qs)), "dif_sigmoid_bwd")
+        return dq, dk, dv
+
+
+def _dense_attention(qs, ks, kernel):
+    """output_attn=True branch (difformer.py:42-43, 55): dense [N,L,H] weights for visualisation
+    only (`get_attentions`, no harness caller); plain torch ops, small N."""
+    if kernel == "simple":
+        qh, kh = qs / torch.linalg.vector_norm(qs), ks / torch.linalg.vector_norm(ks)
+        den = torch.einsum("nhm,hm->nh", qh, kh.sum(0)) + qs.shape[0]
+        # NB: the reference divides [N,L,H] by [N,H,1] (difformer.py:43), which only broadcasts
+        # for H == 1; this is the H-general reading of that line.
+        return torch.einsum("nhm,lhm->nlh", qh, kh) / den.unsqueeze(1)
+    p = torch.sigmoid(torch.einsum("nhm,lhm->nlh", qs, ks))
+    return p / p.sum(1, keepdim=True)
+
+
+def full_attention_conv(qs, ks, vs, kernel, output_attn=False, *, group=None, n_total=None):
+    """Drop-in for difformer.py:10-61.  qs [N,H,M], ks [L,H,M], vs [L,Hv,D] -> [N,H,D]."""
+    if kernel == "simple":
+        out = _SimpleAttention.apply(qs, ks, vs, group, n_total)
+    elif kernel == "sigmoid":
+        if group is not None:
+            raise NotImplementedError("kernel='sigmoid' is replicas-only across GPUs (SURVEY.md 8e)")
+        out = _SigmoidAttention.apply(qs, ks, vs)
+    else:
+        raise ValueError(f"unknown kernel {kernel!r} (expected 'simple' or 'sigmoid')")
+    if output_attn:
+        return out, _dense_attention(qs, ks, kernel)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# gcn_conv
+# ----------------------------------------------------------------------------------------------
+class GraphCSR:
+    """Target-sorted CSR of `edge_index` with the reference's symmetric in-degree normalisation
+    baked into `val`, plus the source-sorted transpose for the backward (difformer.py:63-75)."""
+
+    def __init__(self, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int):
+        _need_cuda(edge_index, edge_weight)
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError("edge_index must be [2,E]")
+        ei = edge_index.to(torch.int64).contiguous()
+        w = None if edge_weight is None else edge_weight.to(torch.float32).contiguous()
+        E, N, dev = ei.shape[1], int(num_nodes), ei.device
+        if w is not None and w.numel() != E:
+            raise ValueError("edge_weight must have E entries")
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.N, self.E = N, E
+        self.rowptr, self.rowptr_t = torch.empty(N + 1, **i32), torch.empty(N + 1, **i32)
+        self.src, self.dst_t, self.perm = (torch.empty(max(E, 1), **i32) for _ in range(3))
+        self.val = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+        self.val_t = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+        wsb = int(lib.dif_csr_workspace_bytes(N, E))
+        if wsb < 0:
+            raise ValueError("graph too large for int32 indices")
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.dif_csr_build(ei.data_ptr(), None if w is None else w.data_ptr(), N, E,
+                                    self.rowptr.data_ptr(), self.src.data_ptr(), self.val.data_ptr(), self.perm.data_ptr(),
+                                    self.rowptr_t.data_ptr(), self.dst_t.data_ptr(), self.val_t.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream), "dif_csr_build")
+        # one validation sync per graph build (cached afterwards): out-of-range node ids are skipped
+        # by the histogram, so the row pointer falls short of E exactly when some id is invalid
+        if int(self.rowptr[-1]) != E:
+            raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+        self._keep = (ei, w)
+
+
+_CSR_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CSR_CACHE_MAX = 16
+
+
+def graph_csr(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int) -> GraphCSR:
+    """CSR cache keyed on the storage identity + version counter of edge_index/edge_weight:
+    `edge_index` is constant across layers and epochs in the reference harness (main.py:118)."""
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), int(num_nodes),
+           None if edge_weight is None else (edge_weight.data_ptr(), edge_weight._version))
+    hit = _CSR_CACHE.get(key)
+    if hit is not None:
+        _CSR_CACHE.move_to_end(key)
+        return hit[0]
+    csr = GraphCSR(edge_index, edge_weight, num_nodes)
+    _CSR_CACHE[key] = (csr, edge_index, edge_weight)   # holding the tensors keeps the pointers unique
+    while len(_CSR_CACHE) > _CSR_CACHE_MAX:
+        _CSR_CACHE.popitem(last=False)
+    return csr
+
+
+def spmm(csr: GraphCSR, x: torch.Tensor, transpose: bool = False, head_mean: bool = False) -> torch.Tensor:
+    N, Hx, D = x.shape
+    if N != csr.N:
+        raise ValueError(f"x has {N} rows, graph has {csr.N} nodes")
+    out = torch.empty((N, D) if head_mean else (N, Hx, D), dtype=torch.float32, device=x.device)
+    rp, idx, val = (csr.rowptr_t, csr.dst_t, csr.val_t) if transpose else (csr.rowptr, csr.src, csr.val)
+    with torch.cuda.device(x.device):
+        check(lib.dif_gcn_spmm(x.data_ptr(), rp.data_ptr(), idx.data_ptr(), val.data_ptr(), N, Hx, D,
+                               1 if head_mean else 0, out.data_ptr(), _stream(x)), "dif_gcn_spmm")
+    return out
+
+
+class _GCNConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, csr):
+        _need_cuda(x)
+        x = _f32c(x)
+        ctx.csr = csr
+        return spmm(csr, x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return spmm(ctx.csr, _f32c(g), transpose=True), None
+
+
+def gcn_conv(x, edge_index, edge_weight):
+    """Drop-in for difformer.py:63-79: x [N,H,D] -> [N,H,D] (no grad to edge_index / edge_weight)."""
+    if x.dim() != 3:
+        raise ValueError("x must be [N,H,D]")
+    return _GCNConv.apply(x, graph_csr(edge_index, edge_weight, x.shape[0]))
+
+
+# ----------------------------------------------------------------------------------------------
+# batched graphs (difformer-v2.py:80-111)
+# ----------------------------------------------------------------------------------------------
+def _seg_ptr(n_nodes: torch.Tensor, total: int, device) -> torch.Tensor:
+    nn_ = n_nodes.to(device=device, dtype=torch.int64)
+    ptr = torch.zeros(nn_.numel() + 1, dtype=torch.int32, device=device)
+    ptr[1:] = torch.cumsum(nn_, 0).to(torch.int32)      # one cumsum on device; no Python loops, no padding
+    return ptr
+
+
+class _SegmentedSimple(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qs, ks, vs, seg_ptr, group):
+        _need_cuda(qs, ks, vs, seg_ptr)
+        qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
+        N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+        B = seg_ptr.numel() - 1
+        dev = qs.device
+        norms = torch.empty(2, dtype=torch.float32, device=dev)
+        ws = torch.empty(max(int(lib.dif_segmented_workspace_bytes(B)), 16), dtype=torch.uint8, device=dev)
+        out = torch.empty((N, H, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _stream(qs)
+            check(lib.dif_sumsq2(qs.data_ptr(), ks.data_ptr(), qs.numel(), norms.data_ptr(), ws.data_ptr(), ws.numel(), st), "dif_sumsq2")
+            _allreduce(norms, group)      # graphs shard whole; only the two norms cross ranks
+            check(lib.dif_segmented_simple_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), seg_ptr.data_ptr(), B,
+                                               norms.data_ptr(), N, H, Hv, M, D, out.data_ptr(), st), "dif_segmented_simple_fwd")
+        ctx.save_for_backward(qs, ks, vs, seg_ptr, norms, out)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qs, ks, vs, seg_ptr, norms, out = ctx.saved_tensors
+        if ctx.group is not None and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            raise NotImplementedError("segmented backward across ranks needs an all-reduce of (t_q, t_k); single rank only")
+        N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+        B = seg_ptr.numel() - 1
+        g = _f32c(g)
+        dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
+        ws = torch.empty(max(int(lib.dif_segmented_workspace_bytes(B)), 16), dtype=torch.uint8, device=qs.device)
+        with torch.cuda.device(qs.device):
+            check(lib.dif_segmented_simple_bwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(), seg_ptr.data_ptr(), B,
+                                               norms.data_ptr(), N, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream(qs)), "dif_segmented_simple_bwd")
+        return dq, dk, dv, None, None
+
+
+def segmented_full_attention(qs, ks, vs, kernel, n_nodes, *, group=None):
+    """Drop-in for TransConv.full_attention (difformer-v2.py:71-140), kernel='simple'."""
+    if kernel != "simple":
+        if kernel == "sigmoid":
+            raise NotImplementedError("v2 kernel='sigmoid' (cross-graph same-slot attention, difformer-v2.py:113-135) "
+                                      "is a 'next' row of SURVEY.md 8f and is not built")
+        raise ValueError(f"unknown kernel {kernel!r}")
+    if int(qs.shape[0]) == 0:
+        return qs.new_empty((0, qs.shape[1], vs.shape[2]))
+    return _SegmentedSimple.apply(qs, ks, vs, _seg_ptr(n_nodes, qs.shape[0], qs.device), group)

@@ -1,0 +1,159 @@
+/*
+ * difformer_b200 -- C ABI of the B200 (sm_100a) DIFFormer propagation kernels.
+ *
+ * The reference (qitianwu/DIFFormer) has no FFI: its hot path is ~70 lines of PyTorch in
+ * `node classification/difformer.py:10-79` (+ the batched variant in
+ * `physical particle/difformer-v2.py:71-111`).  This header is the boundary a maintainer binds
+ * instead of those functions (ctypes stub: INTEGRATION.md).  Each entry point cites the
+ * reference lines it replaces.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every pointer is a DEVICE pointer owned by the caller (row-major, contiguous, fp32 unless
+ *     stated); the library never allocates, never synchronises, never throws.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - return 0 on success, DIF_EARG (-1) bad argument, DIF_EUNSUPPORTED (-2) shape not supported,
+ *     DIF_ECUDA (-3) CUDA error; dif_last_error() returns a thread-local message.
+ *   - scratch memory comes from the caller; size it with the matching *_workspace_bytes().
+ *   - reentrant per (stream, workspace); results are deterministic (no float atomics anywhere).
+ *
+ * Tensor names follow the reference: qs[N,H,M], ks[L,H,M], vs[L,Hv,D] with Hv == H or Hv == 1
+ * (use_weight=False, difformer.py:120), N == L (difformer.py:22,29).
+ */
+#ifndef DIFFORMER_B200_H
+#define DIFFORMER_B200_H
+
+#include <stdint.h>
+
+#if defined(DIF_BUILD) && defined(__GNUC__)
+#define DIF_API __attribute__((visibility("default")))
+#else
+#define DIF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIF_OK 0
+#define DIF_EARG (-1)
+#define DIF_EUNSUPPORTED (-2)
+#define DIF_ECUDA (-3)
+
+/* kernel implementation selector for the 'simple' path */
+#define DIF_IMPL_AUTO 0     /* tcgen05 path when the shape qualifies, else generic */
+#define DIF_IMPL_GENERIC 1  /* FFMA kernels, any H, M%4==0, D%4==0, M,D <= 128 */
+#define DIF_IMPL_TCGEN05 2  /* tcgen05/TMEM kernels: M == D == 64, Hv == H, H even */
+
+DIF_API int dif_version(void);
+DIF_API const char* dif_last_error(void);
+/* 1 when the current device is compute capability 10.x (the only one this library targets) */
+DIF_API int dif_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------
+ * kernel='simple'  (full_attention_conv, difformer.py:18-39)
+ *
+ * Pass 1  dif_simple_reduce : row reductions of this rank's rows -> `partials`
+ *           partials = [ S : H*M*D | z : H*M | u : Hv*D | sum q^2 | sum k^2 ]   (fp32, un-normalised)
+ *           S[h,m,d] = sum_l k[l,h,m] v[l,hv,d]   (difformer.py:25)
+ *           z[h,m]   = sum_l k[l,h,m]             (difformer.py:32-33)
+ *           u[hv,d]  = sum_l v[l,hv,d]            (difformer.py:27-28)
+ *           sums of squares replace torch.norm    (difformer.py:20-21)
+ *         The partials are additive over row shards: multi-GPU = one all-reduce(sum) of this
+ *         buffer between pass 1 and pass 2 (dif_simple_partials_len() floats, 67.6 KB at H=4,D=64).
+ * Pass 2  dif_simple_apply  : out = (q^ S^ + u) / (q^ z^ + n_total)   (difformer.py:26,29,34-39)
+ * ------------------------------------------------------------------------------------------ */
+DIF_API int64_t dif_simple_partials_len(int H, int Hv, int M, int D);
+DIF_API int64_t dif_simple_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
+
+DIF_API int dif_simple_reduce(const float* q, const float* k, const float* v,
+                      int64_t N, int H, int Hv, int M, int D,
+                      float* partials, void* workspace, int64_t workspace_bytes,
+                      int impl, void* stream);
+
+/* Epilogue of pass 2.
+ *   mode 0: out[N,H,D] = attention output (what full_attention_conv returns).
+ *   mode 1: layer epilogue fused (DIFFormerConv.forward difformer.py:129-140 + residual :200-201):
+ *           out[N,D] = attn_scale * sum_h attn[n,h,:] + sum_j add_scale[j] * add[j][n,:]
+ *           (attn_scale = alpha*w_attn/H; addends = head-meaned gcn term, x_0, previous layer) */
+typedef struct {
+    int mode;
+    float attn_scale;
+    int n_add;              /* 0..3 */
+    const float* add[3];    /* each [N,D] or NULL */
+    float add_scale[3];
+} dif_epilogue_t;
+
+DIF_API int dif_simple_apply(const float* q, const float* partials, double n_total,
+                     int64_t N, int H, int Hv, int M, int D,
+                     float* out, const dif_epilogue_t* epilogue,
+                     int impl, void* stream);
+
+/* Backward of the 'simple' path (derived analytically; the reference uses autograd).
+ *   bwd_partials = [ dS : H*M*D | dz : H*M | du : H*D | t_q | t_k ]  (raw, additive over shards;
+ *   t_k is filled by dif_simple_bwd_apply after any all-reduce). `out` is the saved forward
+ *   output [N,H,D], `g` = dL/dout. */
+DIF_API int64_t dif_simple_bwd_partials_len(int H, int M, int D);
+DIF_API int dif_simple_bwd_reduce(const float* q, const float* g, const float* out, const float* partials,
+                          double n_total, int64_t N, int H, int Hv, int M, int D,
+                          float* bwd_partials, void* workspace, int64_t workspace_bytes, void* stream);
+DIF_API int dif_simple_bwd_apply(const float* q, const float* k, const float* v, const float* g, const float* out,
+                         const float* partials, float* bwd_partials, double n_total,
+                         int64_t N, int H, int Hv, int M, int D,
+                         float* dq, float* dk, float* dv, void* stream);
+
+/* Batched-graph 'simple' (TransConv.full_attention, difformer-v2.py:80-111): rows are grouped in
+ * B contiguous segments seg_ptr[0..B] (int32, device; seg_ptr[B] == N).  Normalisation by n_g per
+ * graph (:107-109), Frobenius norms over the whole batch (:82-83).
+ * norms = [sum q^2, sum k^2] (device, 2 floats) is produced by dif_sumsq2 (additive over shards). */
+DIF_API int dif_sumsq2(const float* q, const float* k, int64_t count, float* norms,
+               void* workspace, int64_t workspace_bytes, void* stream);
+DIF_API int dif_segmented_simple_fwd(const float* q, const float* k, const float* v, const int32_t* seg_ptr,
+                             int32_t B, const float* norms, int64_t N, int H, int Hv, int M, int D,
+                             float* out, void* stream);
+/* backward: `out` is the saved forward output, g = dL/dout; M in {16,32,64}, D <= 64 */
+DIF_API int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
+                             const int32_t* seg_ptr, int32_t B, const float* norms,
+                             int64_t N, int H, int Hv, int M, int D,
+                             float* dq, float* dk, float* dv,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+DIF_API int64_t dif_segmented_workspace_bytes(int32_t B);
+
+/* ------------------------------------------------------------------------------------------
+ * kernel='sigmoid'  (full_attention_conv, difformer.py:45-56): tiled, never materialises [N,L,H].
+ *   out = (sigmoid(QK^T) / rowsum) V ; rowsum[N,H] is saved for the backward.
+ * ------------------------------------------------------------------------------------------ */
+DIF_API int dif_sigmoid_fwd(const float* q, const float* k, const float* v,
+                    int64_t N, int64_t L, int H, int Hv, int M, int D,
+                    float* out, float* rowsum, void* stream);
+DIF_API int dif_sigmoid_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
+                    const float* rowsum, int64_t N, int64_t L, int H, int Hv, int M, int D,
+                    float* dq, float* dk, float* dv, void* workspace, int64_t workspace_bytes, void* stream);
+DIF_API int64_t dif_sigmoid_bwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D);
+
+/* ------------------------------------------------------------------------------------------
+ * gcn_conv  (difformer.py:63-79)
+ *   dif_csr_build: edge_index int64 [2,E] (row = source, col = target, difformer.py:65) ->
+ *     target-sorted CSR (rowptr[N+1], src[E], val[E]) and its transpose (source-sorted, for the
+ *     backward).  val_e = w_e * d[col]^-1/2 * d[row]^-1/2 with d = in-degree of `col` for both
+ *     factors (:66-73), non-finite -> 0 (:74).  Stable in edge order => deterministic sums;
+ *     duplicates are kept and summed (torch_sparse semantics).  perm[E] = original edge id of each
+ *     CSR slot (bit-exact gather-index check).  Indices must be < 2^31.
+ *   dif_gcn_spmm: out[c, :] = sum_{slots of c} val * x[src, :]   with F = Hx*D floats per row.
+ *     head_mean != 0: out is [N,D] = mean over the Hx heads (used by the fused layer epilogue).
+ * ------------------------------------------------------------------------------------------ */
+DIF_API int64_t dif_csr_workspace_bytes(int64_t N, int64_t E);
+DIF_API int dif_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t N, int64_t E,
+                  int32_t* rowptr, int32_t* src, float* val, int32_t* perm,
+                  int32_t* rowptr_t, int32_t* dst_t, float* val_t,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+DIF_API int dif_gcn_spmm(const float* x, const int32_t* rowptr, const int32_t* idx, const float* val,
+                 int64_t N, int Hx, int D, int head_mean, float* out, void* stream);
+
+/* mean over heads: x[N,Hx,D] -> out[N,D] */
+DIF_API int dif_head_mean(const float* x, int64_t N, int Hx, int D, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFORMER_B200_H */

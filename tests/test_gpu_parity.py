@@ -1,0 +1,302 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every check calls the product path,
+which goes through the C ABI (libdifformer_b200.so); the oracle / golden vectors are only the
+checker.  Tolerance: 1e-3 relative (BASELINE.json north_star), fp32, norm-wise, against the
+committed reference outputs and the fp64 oracle; integer gather indices bit-exact."""
+import pytest
+import torch
+
+import difformer
+from difformer_b200 import ops
+from oracle import difformer_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+ATT, GCN, MODEL, V2 = (load_golden(g) for g in ("attention", "gcn", "model", "v2"))
+IMPLS = ["generic", "auto"]
+
+
+def dev(t):
+    return t.cuda() if torch.is_tensor(t) else t
+
+
+@pytest.fixture(params=IMPLS)
+def impl(request):
+    ops.set_simple_impl(request.param)
+    yield request.param
+    ops.set_simple_impl("auto")
+
+
+def _unpack(flat, H, Hv, M, D):
+    flat = flat.double().cpu()
+    o = 0
+    S = flat[o:o + H * M * D].reshape(H, M, D); o += H * M * D
+    z = flat[o:o + H * M].reshape(H, M); o += H * M
+    u = flat[o:o + Hv * D].reshape(Hv, D); o += Hv * D
+    return S, z, u, flat[o], flat[o + 1]
+
+
+# ---------------------------------------------------------------------------------- simple
+@pytest.mark.parametrize("name", [n for n in sorted(ATT) if n.startswith("simple")])
+def test_simple_forward_matches_reference_golden(name, impl):
+    c = ATT[name]
+    out = difformer.full_attention_conv(dev(c["q"]), dev(c["k"]), dev(c["v"]), "simple")
+    assert O.rel_err(out, c["out"]) < TOL
+    assert O.rel_err(out, O.simple_attention(c["q"].double(), c["k"].double(), c["v"].double())) < TOL
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(ATT) if n.startswith("simple")])
+def test_simple_intermediates(name, impl):
+    """Mean-collapse guard: S, z, u, ||Q||, ||K||, q^S^ and q^z^ are pinned
+    separately against the fp64 oracle -- `out` alone is dominated by mean(V)."""
+    c = ATT[name]
+    q, k, v = c["q"], c["k"], c["v"]
+    H, Hv, M, D = q.shape[1], v.shape[1], q.shape[2], v.shape[2]
+    flat = ops.simple_partials(dev(q), dev(k), dev(v))
+    S, z, u, sq, sk = _unpack(flat, H, Hv, M, D)
+    want = O.simple_partials(q.double(), k.double(), v.double())
+    assert O.rel_err(S, want["S"]) < TOL and O.rel_err(z, want["z"]) < TOL and O.rel_err(u, want["u"]) < TOL
+    assert abs(float(sq) / float(want["sq"]) - 1) < 1e-5 and abs(float(sk) / float(want["sk"]) - 1) < 1e-5
+    _, parts = O.simple_apply(q.double(), want, return_parts=True)
+    n = float(q.shape[0])
+    # pass 2 with u := 0, z := 0  ->  out * N = q^S^
+    only_s = flat.clone()
+    only_s[H * M * D: H * M * D + H * M + Hv * D] = 0
+    qS = ops.simple_apply(dev(q), only_s, n, Hv, D) * n
+    assert O.rel_err(qS, parts["qS"]) < TOL
+    # pass 2 with S := 0, u := 1  ->  1/out - N = q^z^
+    only_z = flat.clone()
+    only_z[:H * M * D] = 0
+    only_z[H * M * D + H * M: H * M * D + H * M + Hv * D] = 1
+    qz = 1.0 / ops.simple_apply(dev(q), only_z, n, Hv, D).double() - n
+    assert O.rel_err(qz[..., 0], parts["qz"]) < 5e-3      # recovered through 1/x - N: fp32 cancellation
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(ATT) if n.startswith("simple")])
+def test_simple_backward_matches_reference_autograd(name):
+    c = ATT[name]
+    q, k, v = (dev(c[n]).requires_grad_(True) for n in "qkv")
+    out = difformer.full_attention_conv(q, k, v, "simple")
+    out.backward(dev(c["g"]))
+    want = O.simple_attention_backward(*(c[n].double() for n in "qkvg"))
+    for got, gold, w64 in ((q.grad, c["dq"], want[0]), (k.grad, c["dk"], want[1]), (v.grad, c["dv"], want[2])):
+        assert O.rel_err(got, w64) < TOL
+        assert O.rel_err(got, gold) < 5e-3      # the reference's own fp32 autograd carries ~1e-4 noise here
+
+
+def test_simple_dense_attention_output(impl):
+    c = ATT["simple_n64_h1_d64"]
+    out, attn = difformer.full_attention_conv(dev(c["q"]), dev(c["k"]), dev(c["v"]), "simple", output_attn=True)
+    assert O.rel_err(attn, c["attn"]) < TOL and O.rel_err(out, c["out"]) < TOL
+
+
+def test_simple_rejects_n_ne_l():
+    q = torch.randn(10, 1, 64, device="cuda")
+    with pytest.raises(ValueError, match="N == L"):
+        difformer.full_attention_conv(q, torch.randn(12, 1, 64, device="cuda"), torch.randn(12, 1, 64, device="cuda"), "simple")
+
+
+@pytest.mark.parametrize("n,h,hv,d", [(1, 1, 1, 64), (31, 2, 2, 64), (64, 4, 4, 64), (65, 4, 1, 64), (1000, 8, 8, 32),
+                                       (777, 1, 1, 128), (513, 3, 3, 16), (4097, 4, 4, 64), (130, 2, 2, 64)])
+def test_simple_shapes_and_edges(n, h, hv, d, impl):
+    q, k, v = O.synthetic_qkv(n, h, d, seed=n, hv=hv, adversarial=True)
+    out = difformer.full_attention_conv(dev(q), dev(k), dev(v), "simple")
+    assert O.rel_err(out, O.simple_attention(q.double(), k.double(), v.double())) < TOL
+
+
+def test_simple_full_size_properties(impl):
+    """BASELINE config A (N=132 534, H=4, D=64): fp64-oracle intermediates + size-independent
+    properties (row-shard additivity of the partials, linearity in V, determinism)."""
+    n, h, d = 132534, 4, 64
+    q, k, v = O.synthetic_qkv(n, h, d, seed=123, adversarial=True)
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    flat = ops.simple_partials(qg, kg, vg)
+    S, z, u, sq, sk = _unpack(flat, h, h, d, d)
+    want = O.simple_partials(q.double(), k.double(), v.double())
+    assert O.rel_err(S, want["S"]) < TOL and O.rel_err(z, want["z"]) < TOL and O.rel_err(u, want["u"]) < TOL
+    assert abs(float(sq) / float(want["sq"]) - 1) < 1e-5 and abs(float(sk) / float(want["sk"]) - 1) < 1e-5
+    out = difformer.full_attention_conv(qg, kg, vg, "simple")
+    assert O.rel_err(out, O.simple_apply(q.double(), want)) < TOL
+    # additivity over row shards (what the all-reduce relies on)
+    cut = 70001
+    both = ops.simple_partials(qg[:cut], kg[:cut], vg[:cut]) + ops.simple_partials(qg[cut:], kg[cut:], vg[cut:])
+    assert O.rel_err(both, flat) < 1e-5
+    # linearity in V for fixed Q, K
+    v2 = dev(O.synthetic_qkv(n, h, d, seed=7)[2])
+    lin = difformer.full_attention_conv(qg, kg, 0.5 * vg - 2.0 * v2, "simple")
+    assert O.rel_err(lin, 0.5 * out - 2.0 * difformer.full_attention_conv(qg, kg, v2, "simple")) < 1e-4
+    # deterministic (no float atomics)
+    assert torch.equal(out, difformer.full_attention_conv(qg, kg, vg, "simple"))
+
+
+# ---------------------------------------------------------------------------------- sigmoid
+@pytest.mark.parametrize("name", [n for n in sorted(ATT) if n.startswith("sigmoid")])
+def test_sigmoid_forward_backward(name):
+    c = ATT[name]
+    q, k, v = (dev(c[n]).requires_grad_(True) for n in "qkv")
+    out = difformer.full_attention_conv(q, k, v, "sigmoid")
+    assert O.rel_err(out, c["out"]) < TOL
+    out.backward(dev(c["g"]))
+    for got, gold in ((q.grad, c["dq"]), (k.grad, c["dk"]), (v.grad, c["dv"])):
+        assert O.rel_err(got, gold) < TOL
+
+
+@pytest.mark.parametrize("n,l,h,hv,d", [(1, 1, 1, 1, 64), (63, 200, 2, 2, 64), (2708, 2708, 1, 1, 64), (300, 129, 4, 1, 32), (70, 70, 1, 1, 128)])
+def test_sigmoid_shapes(n, l, h, hv, d):
+    gen = torch.Generator().manual_seed(n + l)
+    q = torch.randn(n, h, d, generator=gen) * 0.3
+    k = torch.randn(l, h, d, generator=gen) * 0.3
+    v = torch.randn(l, hv, d, generator=gen)
+    out = difformer.full_attention_conv(dev(q), dev(k), dev(v), "sigmoid")
+    assert O.rel_err(out, O.sigmoid_attention(q.double(), k.double(), v.double())) < TOL
+
+
+# ---------------------------------------------------------------------------------- gcn_conv
+@pytest.mark.parametrize("name", sorted(GCN))
+def test_gcn_conv_matches_reference(name):
+    c = GCN[name]
+    x = dev(c["x"]).requires_grad_("dx" in c)
+    out = difformer.gcn_conv(x, dev(c["edge_index"]), dev(c.get("edge_weight")))
+    assert O.rel_err(out, c["out"]) < 1e-5
+    if "dx" in c:
+        out.backward(dev(c["g"]))
+        assert O.rel_err(x.grad, c["dx"]) < 1e-5
+
+
+def test_gcn_gather_indices_are_bit_exact():
+    c = GCN["gcn_directed_weighted"]
+    ei, w, n = c["edge_index"], c["edge_weight"], c["x"].shape[0]
+    csr = ops.GraphCSR(dev(ei), dev(w), n)
+    perm = csr.perm.cpu().long()
+    assert sorted(perm.tolist()) == list(range(ei.shape[1]))             # a permutation of the edges
+    col_sorted = ei[1][perm]
+    assert bool((col_sorted[1:] >= col_sorted[:-1]).all())               # target-sorted
+    same = col_sorted[1:] == col_sorted[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())                # stable: edge order inside a row
+    assert torch.equal(csr.src.cpu().long(), ei[0][perm])                # gather indices, bit-exact
+    assert torch.equal(csr.rowptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(ei[1], minlength=n).cumsum(0)]))
+    want = O.gcn_edge_values(ei, w, n)[perm]
+    assert torch.equal(csr.val.cpu(), want)                              # same fp32 arithmetic as the reference
+    # transpose used by the backward
+    perm_t_cols = csr.dst_t.cpu().long()
+    assert torch.equal(torch.sort(perm_t_cols)[0], torch.sort(ei[1])[0])
+
+
+def test_gcn_rejects_out_of_range_ids():
+    ei = torch.tensor([[0, 1, 5], [1, 0, 2]], device="cuda")
+    with pytest.raises(IndexError):
+        difformer.gcn_conv(torch.randn(4, 1, 64, device="cuda"), ei, None)
+
+
+def test_gcn_empty_and_ragged():
+    x = torch.randn(10, 2, 32, device="cuda")
+    out = difformer.gcn_conv(x, torch.zeros(2, 0, dtype=torch.long, device="cuda"), None)
+    assert float(out.abs().max()) == 0.0
+    ei = torch.tensor([[0] * 700 + [3], [9] * 700 + [3]])                 # one hub row of 700 duplicate edges
+    out = difformer.gcn_conv(x, ei.cuda(), None)
+    assert O.rel_err(out, O.gcn_conv(x.cpu(), ei, None)) < 1e-5
+
+
+def test_gcn_head_mean_variant():
+    c = GCN["gcn_undirected_selfloops"]
+    csr = ops.graph_csr(dev(c["edge_index"]), None, c["x"].shape[0])
+    got = ops.spmm(csr, dev(c["x"]), head_mean=True)
+    assert O.rel_err(got, c["out"].mean(1)) < 1e-5
+
+
+# ---------------------------------------------------------------------------------- model
+def _kw(c):
+    kw = {k[4:]: v for k, v in c.items() if k.startswith("cfg_")}
+    for b in ("use_bn", "use_residual", "use_weight", "use_graph", "use_source"):
+        if b in kw:
+            kw[b] = bool(kw[b])
+    return kw
+
+
+def _model(c):
+    m = difformer.DIFFormer(int(c["cin"]), int(c["hidden"]), int(c["cout"]), **_kw(c))
+    m.load_state_dict({k[3:]: v for k, v in c.items() if k.startswith("sd_")})
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("name", sorted(MODEL))
+def test_model_logits_fused_and_unfused(name):
+    c = MODEL[name]
+    m = _model(c)
+    args = (dev(c["x"]), dev(c["edge_index"])) + ((dev(c["edge_weight"]),) if "edge_weight" in c else ())
+    with torch.no_grad():
+        fused = m(*args)                 # inference path: layer epilogue fused into pass 2
+    unfused = m(*args)                   # autograd path: unfused ops
+    assert O.rel_err(fused, c["out"]) < TOL
+    assert O.rel_err(unfused, c["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", sorted(MODEL))
+def test_model_parameter_gradients(name):
+    c = MODEL[name]
+    m = _model(c)
+    args = (dev(c["x"]), dev(c["edge_index"])) + ((dev(c["edge_weight"]),) if "edge_weight" in c else ())
+    out = m(*args)
+    gen = torch.Generator().manual_seed(77)        # replay make_golden.py's generator to get the same loss weights
+    torch.randn(c["x"].shape, generator=gen)
+    if "edge_weight" in c:
+        torch.rand(c["edge_index"].shape[1], generator=gen)
+    wgt = torch.randn(out.shape, generator=gen)
+    (out * wgt.cuda()).sum().backward()
+    for k_, p in m.named_parameters():
+        if "grad_" + k_ in c:
+            assert O.rel_err(p.grad, c["grad_" + k_]) < 5e-3, k_
+
+
+def test_training_step_through_the_drop_in():
+    """What main.py:104-133 does: reset_parameters, Adam, forward, NLL, backward, step."""
+    torch.manual_seed(0)
+    n, cin, ncls = 500, 32, 5
+    x = torch.randn(n, cin, device="cuda")
+    y = torch.randint(0, ncls, (n,), device="cuda")
+    ei = O.synthetic_graph(n, 1500, seed=2).cuda()
+    m = difformer.DIFFormer(cin, 64, ncls, num_layers=2, num_heads=2, use_bn=True, use_residual=True, use_graph=True).cuda()
+    m.reset_parameters()
+    opt = torch.optim.Adam(m.parameters(), lr=0.01)
+    losses = []
+    for _ in range(15):
+        m.train()
+        opt.zero_grad()
+        loss = torch.nn.functional.nll_loss(torch.log_softmax(m(x, ei), dim=1), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] and all(l == l for l in losses)
+
+
+# ---------------------------------------------------------------------------------- batched graphs (v2)
+def test_v2_segmented_forward_backward():
+    for name in ("v2_simple_segments", "v2_simple_segments_h2"):
+        c = V2[name]
+        q, k, v = (dev(c[n]).requires_grad_(True) for n in "qkv")
+        out = ops.segmented_full_attention(q, k, v, "simple", dev(c["n_nodes"]))
+        assert O.rel_err(out, c["out"]) < TOL
+        if "g" in c:
+            out.backward(dev(c["g"]))
+            want = O.segmented_simple_attention_backward(*(c[n].double() for n in "qkv"), c["n_nodes"], c["g"].double())
+            for got, w64 in ((q.grad, want[0]), (k.grad, want[1]), (v.grad, want[2])):
+                assert O.rel_err(got, w64) < TOL
+
+
+def test_v2_many_small_graphs_and_one_large():
+    gen = torch.Generator().manual_seed(3)
+    n_nodes = torch.cat([torch.randint(1, 41, (300,), generator=gen), torch.tensor([700, 1, 33])])
+    tot = int(n_nodes.sum())
+    q, k, v = O.synthetic_qkv(tot, 1, 64, seed=9, adversarial=True)
+    out = ops.segmented_full_attention(dev(q), dev(k), dev(v), "simple", n_nodes.cuda())
+    assert O.rel_err(out, O.segmented_simple_attention(q.double(), k.double(), v.double(), n_nodes)) < TOL
+
+
+def test_v2_model_forward():
+    c = V2["v2_model_simple"]
+    m = difformer.DIFFormer_v2(16, 64, 3, num_layers=2, kernel="simple", use_graph=True)
+    m.load_state_dict({k[3:]: v for k, v in c.items() if k.startswith("sd_")})
+    m = m.cuda().eval()
+    out = m(dev(c["x"]), dev(c["edge_index"]), dev(c["n_nodes"]))
+    assert O.rel_err(out, c["out"]) < TOL
+    out.sum().backward()      # the particle harness trains through it

@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the drop-in (module surface, state_dict compatibility, sharding
+arithmetic, loud failure without CUDA)."""
+import inspect
+
+import pytest
+import torch
+
+import difformer
+from difformer_b200 import ops
+from difformer_b200.sharded import shard_rows
+from tests.conftest import load_golden
+
+MODEL = load_golden("model")
+V2 = load_golden("v2")
+
+
+def test_module_exports_reference_names():
+    for name in ("DIFFormer", "DIFFormerConv", "full_attention_conv", "gcn_conv", "DIFFormer_v2", "TransConv"):
+        assert hasattr(difformer, name)
+
+
+def test_ctor_signature_matches_reference():
+    # node classification/difformer.py:154-155
+    sig = inspect.signature(difformer.DIFFormer.__init__)
+    want = [("in_channels", inspect._empty), ("hidden_channels", inspect._empty), ("out_channels", inspect._empty),
+            ("num_layers", 2), ("num_heads", 1), ("kernel", "simple"), ("alpha", 0.5), ("dropout", 0.5), ("use_bn", True),
+            ("use_residual", True), ("use_weight", True), ("use_graph", True), ("graph_weight", -1), ("use_source", False)]
+    got = [(n, p.default) for n, p in sig.parameters.items() if n != "self"]
+    assert got == want
+    sig2 = inspect.signature(difformer.DIFFormer_v2.__init__)     # difformer-v2.py:166-167
+    got2 = [(n, p.default) for n, p in sig2.parameters.items() if n != "self"]
+    assert got2 == [("in_channels", inspect._empty), ("hidden_channels", inspect._empty), ("out_channels", inspect._empty),
+                    ("num_layers", 2), ("kernel", "simple"), ("alpha", 0.5), ("dropout", 0.5), ("use_bn", True),
+                    ("use_residual", True), ("use_weight", True), ("use_graph", True), ("graph_weight", -1)]
+    assert list(inspect.signature(difformer.DIFFormer.forward).parameters)[:4] == ["self", "x", "edge_index", "edge_weight"]
+    assert list(inspect.signature(difformer.full_attention_conv).parameters)[:5] == ["qs", "ks", "vs", "kernel", "output_attn"]
+    assert list(inspect.signature(difformer.gcn_conv).parameters) == ["x", "edge_index", "edge_weight"]
+
+
+@pytest.mark.parametrize("name", sorted(MODEL))
+def test_state_dict_round_trips_with_reference_checkpoints(name):
+    c = MODEL[name]
+    kw = {k[4:]: v for k, v in c.items() if k.startswith("cfg_")}
+    for b in ("use_bn", "use_residual", "use_weight", "use_graph", "use_source"):
+        if b in kw:
+            kw[b] = bool(kw[b])
+    m = difformer.DIFFormer(int(c["cin"]), int(c["hidden"]), int(c["cout"]), **kw)
+    ref_sd = {k[3:]: v for k, v in c.items() if k.startswith("sd_")}
+    assert sorted(m.state_dict().keys()) == sorted(ref_sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(ref_sd[k].shape)
+    m.load_state_dict(ref_sd, strict=True)      # test_large_dataset.py:86-88 does exactly this
+    assert not list(m.buffers())                # no extra persistent state
+    m.reset_parameters()
+
+
+def test_v2_state_dict():
+    c = V2["v2_model_simple"]
+    m = difformer.DIFFormer_v2(16, 64, 3, num_layers=2)
+    ref_sd = {k[3:]: v for k, v in c.items() if k.startswith("sd_")}
+    assert sorted(m.state_dict().keys()) == sorted(ref_sd.keys())
+    m.load_state_dict(ref_sd, strict=True)
+
+
+def test_cpu_tensors_raise_instead_of_falling_back():
+    q = torch.randn(8, 1, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        difformer.full_attention_conv(q, q, q, "simple")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        difformer.full_attention_conv(q, q, q, "sigmoid")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        difformer.gcn_conv(q, torch.zeros(2, 4, dtype=torch.long), None)
+    m = difformer.DIFFormer(8, 64, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(5, 8), torch.zeros(2, 4, dtype=torch.long))
+
+
+def test_argument_validation():
+    q = torch.randn(8, 2, 16)
+    with pytest.raises(ValueError):
+        ops._shapes(q, torch.randn(8, 3, 16), q)
+    with pytest.raises(ValueError):
+        ops._shapes(q, q, torch.randn(8, 3, 16))          # Hv must be H or 1
+    assert ops._shapes(q, q, torch.randn(8, 1, 16)) == (8, 8, 2, 1, 16, 16)
+    with pytest.raises(ValueError, match="unknown kernel"):
+        difformer.full_attention_conv(q, q, q, "gaussian")
+    with pytest.raises(TypeError):
+        ops._f32c(q.double())
+
+
+def test_shard_rows_partitions_exactly():
+    for n in (0, 1, 7, 132534, 1632803):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_rows(10, 4, 4)
+
+
+def test_seg_ptr_is_an_exclusive_scan():
+    ptr = ops._seg_ptr(torch.tensor([5, 0, 17, 1]), 23, torch.device("cpu"))
+    assert ptr.dtype == torch.int32 and ptr.tolist() == [0, 5, 5, 22, 23]
+
+
+def test_epilogue_struct_layout():
+    a = torch.zeros(4, 8)
+    ep = ops.make_epilogue(0.125, [(a, 0.5), (a, 2.0)])
+    assert ep.mode == 1 and ep.n_add == 2 and ep.add[0] == a.data_ptr() and abs(ep.add_scale[1] - 2.0) < 1e-7
