@@ -34,7 +34,7 @@ struct SimpleLayout {
     __host__ __device__ int64_t offSk() const { return offSq() + 1; }
     __host__ __device__ int64_t len() const { return offSk() + 1; }
     // per-chunk workspace record of the generic reduce: sq/sk get one slot per head
-    __host__ __device__ int64_t wsLen() const { return offSq() + 2 * (int64_t)H; }
+    __host__ __device__ int64_t wsLen() const { return (offSq() + 2 * (int64_t)H + 3) & ~(int64_t)3; }   // float4-aligned records
 };
 
 struct BwdLayout {
@@ -45,7 +45,7 @@ struct BwdLayout {
     __host__ __device__ int64_t offTq() const { return offU() + (int64_t)H * D; }
     __host__ __device__ int64_t offTk() const { return offTq() + 1; }
     __host__ __device__ int64_t len() const { return offTk() + 1; }
-    __host__ __device__ int64_t wsLen() const { return offTq() + (int64_t)H; }
+    __host__ __device__ int64_t wsLen() const { return (offTq() + (int64_t)H + 3) & ~(int64_t)3; }
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
