@@ -584,6 +584,8 @@ int64_t simple_generic_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
     return (int64_t)chunks * rec * (int64_t)sizeof(float);
 }
 
+int simple_finalize_fwd(const float* ws, int nchunks, int H, int Hv, int M, int D, float* partials, cudaStream_t st);
+
 int simple_reduce_generic(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
                           float* partials, void* ws, int64_t ws_bytes, cudaStream_t st) {
     int rc = check_shape(N, H, Hv, M, D);
@@ -596,9 +598,14 @@ int simple_reduce_generic(const float* q, const float* k, const float* v, int64_
     a.a = k; a.b = v; a.q = q; a.N = N; a.H = H; a.Hb = Hv; a.M = M; a.D = D;
     a.rows_per_cta = rpc; a.ws_len = L.wsLen(); a.ws = (float*)ws;
     if ((rc = launch_reduce<false>(a, chunks, st))) return rc;
+    return simple_finalize_fwd((const float*)ws, chunks, H, Hv, M, D, partials, st);
+}
+
+int simple_finalize_fwd(const float* ws, int nchunks, int H, int Hv, int M, int D, float* partials, cudaStream_t st) {
+    const SimpleLayout L{H, Hv, M, D};
     const int64_t main_len = L.offSq();
     const int blocks = (int)((main_len + 2 + 255) / 256);
-    finalize_kernel<<<blocks, 256, 0, st>>>((const float*)ws, chunks, L.wsLen(), main_len, 2, H, partials);
+    finalize_kernel<<<blocks, 256, 0, st>>>(ws, nchunks, L.wsLen(), main_len, 2, H, partials);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }

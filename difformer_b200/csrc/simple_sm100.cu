@@ -1,15 +1,627 @@
-// kernel='simple' -- tcgen05 / TMEM path for sm_100a (placeholder until the kernels land).
+// kernel='simple' -- tcgen05 / TMEM path for sm_100a (H = 4, M = D = 64, fp32 in / fp32 out).
+//
+// Reference path replaced: full_attention_conv(..., 'simple'), node classification/difformer.py:18-39.
+//
+// Both contractions of the O(N) kernel run on the 5th-gen tensor cores:
+//   pass 1  S_h  = K_h^T V_h      contraction over NODES  -> operands MN-major, M = N = 128 (two heads
+//                                  stacked; the two diagonal 64x64 blocks of D are S_{2p}, S_{2p+1})
+//   pass 2  q_n (c S_h | c z_h)   contraction over m      -> operands K-major, M = 128 rows, N = 80
+//                                  (64 columns of S plus the z column = the denominator)
+// Inputs are fp32; the reference tolerance (1e-3, also on the intermediates) rules out TF32
+// (truncation bias ~1e-3), so every fp32 value x is split on the fly into bf16 hi + bf16 lo
+// (x = hi + lo + O(2^-17 x)) and each product uses 3 MMAs (hi*hi + hi*lo + lo*hi), error ~2^-16.
+// The split runs on the CUDA cores of the warps that stream the rows from HBM (256-bit loads),
+// which write the bf16 tiles straight into the 128B-swizzled UMMA layout in shared memory;
+// an elected thread issues tcgen05.mma with the accumulators in TMEM; mbarrier rings couple
+// producers -> MMA -> epilogue.  The tensor pipe needs ~20% of the HBM time, so the kernels are
+// HBM-bound by design (roofline: 4*H*D*4 B per node).
+//
+// Warp roles (13 warps, 1 CTA per SM, persistent over contiguous row ranges / 128-row tiles):
+//   pass 1: warps 0-7 K/V producers (+ sum k, sum v, sum k^2), warps 8-11 stream Q for sum q^2,
+//           warp 12 MMA issuer; epilogue: warps 0-3 TMEM -> per-CTA record (deterministic 2-stage reduce)
+//   pass 2: warps 0-7 Q producers, warps 8-11 epilogue (TMEM -> registers -> (acc+u)/den -> HBM,
+//           optionally the fused layer epilogue), warp 12 MMA issuer.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dif {
 
-bool simple_tc_supported(int64_t, int, int, int, int) { return false; }
-int64_t simple_tc_workspace_bytes(int64_t, int, int, int, int) { return 0; }
-int simple_reduce_tc(const float*, const float*, const float*, int64_t, int, int, int, int, float*, void*, int64_t, cudaStream_t) {
-    return set_error(DIF_EUNSUPPORTED, "tcgen05 path not built");
+int simple_finalize_fwd(const float* ws, int nchunks, int H, int Hv, int M, int D, float* partials, cudaStream_t st);
+
+namespace {
+
+constexpr int kH = 4;
+constexpr int kDim = 64;
+constexpr int kRowF = kH * kDim;      // floats per node row (256)
+constexpr int kWarps = 13;
+constexpr int kThreadsTC = kWarps * 32;
+
+// ---- descriptor conventions (verified on hardware by csrc/probe_umma.cu) --------------------
+constexpr uint32_t kSwizzle128 = 2;
+// K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused
+constexpr uint32_t kKmajLBO = 0, kKmajSBO = 1024;
+// MN-major SW128: 64-element (128 B) MN blocks are LBO apart, 8-k groups SBO apart
+#ifndef DIF_MN_LBO_IS_MNSTRIDE
+#define DIF_MN_LBO_IS_MNSTRIDE 1
+#endif
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
-int simple_apply_tc(const float*, const float*, double, int64_t, int, int, int, int, float*, const dif_epilogue_t*, cudaStream_t) {
-    return set_error(DIF_EUNSUPPORTED, "tcgen05 path not built");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile("{\n\t.reg .pred pq;\n\tmbarrier.try_wait.parity.shared::cta.b64 pq, [%1], %2;\n\tselp.b32 %0, 1, 0, pq;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;              // descriptor version: Blackwell
+    d |= (uint64_t)kSwizzle128 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                        // D format f32
+    d |= 1u << 7;                        // A format bf16
+    d |= 1u << 10;                       // B format bf16
+    d |= (uint32_t)a_mn << 15;           // A major: 0 = K, 1 = MN
+    d |= (uint32_t)b_mn << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pp;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
+// tcgen05.ld is asynchronous: its destination registers are only valid after wait::ld.  The
+// registers are threaded through the wait as read-write operands so the compiler cannot schedule
+// a consumer above it.
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait1(uint32_t& r) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r) :: "memory"); }
+
+// streaming 256-bit global load (data is consumed once: no L1 allocation, evict-first in L2)
+__device__ __forceinline__ void ldg256_stream(const float* p, float (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
+// 256-bit load that may stay in L2 (pass 1 reads Q only for its norm; pass 2 reads it again)
+__device__ __forceinline__ void ldg256_keep(const float* p, float (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t bf2_bits(float lo_elem, float hi_elem) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo_elem, hi_elem);   // .x (low 16 bits) = first element
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// x[0..7] -> 8 bf16 hi (16 B) + 8 bf16 lo (16 B), x = hi + lo + O(2^-17 |x|)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = bf2_bits(x[2 * j], x[2 * j + 1]);
+        const float h0 = __uint_as_float(h[j] << 16), h1 = __uint_as_float(h[j] & 0xffff0000u);
+        l[j] = bf2_bits(x[2 * j] - h0, x[2 * j + 1] - h1);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// byte offset of 16-byte chunk c of row r in a [rows][128 B] tile, 128B swizzle (Swizzle<3,4,3>)
+__device__ __forceinline__ uint32_t sw128(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((c ^ r) & 7) << 4));
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------
+constexpr int kR1 = 16;                               // nodes per stage = one UMMA K step
+constexpr int kHeadTile1 = kR1 * 128;                 // 2048 B: [16 nodes][64 bf16] of one head
+constexpr int kOp1 = kH * kHeadTile1;                 // 8192 B per operand (Khi / Klo / Vhi / Vlo)
+constexpr int kStage1 = 4 * kOp1;                     // 32 KB
+constexpr int kNS1 = 4;
+constexpr int kSmem1 = kNS1 * kStage1 + 1024;
+
+__global__ void __launch_bounds__(kThreadsTC, 1)
+reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
+                 int rows_per_cta, float* __restrict__ ws, int64_t ws_len) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full[kNS1], empty[kNS1], done;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(N, r0 + (int64_t)rows_per_cta);
+    const int iters = r1 > r0 ? (int)((r1 - r0 + kR1 - 1) / kR1) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kNS1; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    float zacc[8], uacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { zacc[i] = 0.f; uacc[i] = 0.f; }
+    float ss = 0.f;     // producers: sum k^2 ; Q warps: sum q^2
+
+    if (warp < 8) {
+        // ===== K/V producers: warp w owns nodes w and w+8 of every 16-node stage, lane l owns columns 8l..8l+7
+        float kc[2][8], vc[2][8], kn[2][8], vn[2][8];
+        auto load = [&](int it, float (&kk)[2][8], float (&vv)[2][8]) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * j;
+                if (row < r1) {
+                    ldg256_stream(k + row * kRowF + lane * 8, kk[j]);
+                    ldg256_stream(v + row * kRowF + lane * 8, vv[j]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { kk[j][i] = 0.f; vv[j][i] = 0.f; }
+                }
+            }
+        };
+        if (iters > 0) load(0, kc, vc);
+        const uint32_t stage_base = smem_u32(stages);
+        for (int it = 0; it < iters; ++it) {
+            if (it + 1 < iters) load(it + 1, kn, vn);
+            const int s = it % kNS1;
+            if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
+            const uint32_t sb = stage_base + s * kStage1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                // node r = warp + 8j of the stage: (r >> 3) = j, (r & 7) = warp ; head = lane >> 3, chunk = lane & 7
+                const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + j * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
+                uint4 hi, lo;
+                split8(kc[j], hi, lo);
+                sts128(sb + 0 * kOp1 + off, hi);
+                sts128(sb + 1 * kOp1 + off, lo);
+                split8(vc[j], hi, lo);
+                sts128(sb + 2 * kOp1 + off, hi);
+                sts128(sb + 3 * kOp1 + off, lo);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    zacc[i] += kc[j][i];
+                    uacc[i] += vc[j][i];
+                    ss = fmaf(kc[j][i], kc[j][i], ss);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (it + 1 < iters) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { kc[j][i] = kn[j][i]; vc[j][i] = vn[j][i]; }
+            }
+        }
+    } else if (warp < 12) {
+        // ===== Q stream: sum of squares only (the Frobenius norm of difformer.py:20)
+        const int64_t n8 = (r1 > r0 ? (r1 - r0) : 0) * (kRowF / 8);
+        const float* base = q + r0 * kRowF;
+        const int t = tid - 256;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int64_t i = t;
+        for (; i + 3 * 128 < n8; i += 4 * 128) {
+            float x0[8], x1[8], x2[8], x3[8];
+            ldg256_keep(base + i * 8, x0);
+            ldg256_keep(base + (i + 128) * 8, x1);
+            ldg256_keep(base + (i + 256) * 8, x2);
+            ldg256_keep(base + (i + 384) * 8, x3);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                a0 = fmaf(x0[e], x0[e], a0); a1 = fmaf(x1[e], x1[e], a1);
+                a2 = fmaf(x2[e], x2[e], a2); a3 = fmaf(x3[e], x3[e], a3);
+            }
+        }
+        for (; i < n8; i += 128) {
+            float x0[8];
+            ldg256_keep(base + i * 8, x0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a0 = fmaf(x0[e], x0[e], a0);
+        }
+        ss = (a0 + a1) + (a2 + a3);
+    } else if (lane == 0) {
+        // ===== MMA issuer
+        const uint32_t idesc = make_idesc(128, 128, 1, 1);
+#if DIF_MN_LBO_IS_MNSTRIDE
+        const uint32_t lbo = kHeadTile1, sbo = 1024;
+#else
+        const uint32_t lbo = 1024, sbo = kHeadTile1;
+#endif
+        const uint32_t stage_base = smem_u32(stages);
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kNS1;
+            mbar_wait(&full[s], (it / kNS1) & 1);
+            tc_fence_after();
+            const uint32_t sb = stage_base + s * kStage1;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const uint32_t ho = p * 2 * kHeadTile1;          // heads 2p, 2p+1
+                const uint64_t khi = make_desc(sb + 0 * kOp1 + ho, lbo, sbo), klo = make_desc(sb + 1 * kOp1 + ho, lbo, sbo);
+                const uint64_t vhi = make_desc(sb + 2 * kOp1 + ho, lbo, sbo), vlo = make_desc(sb + 3 * kOp1 + ho, lbo, sbo);
+                umma(tmem + p * 128, khi, vhi, idesc, it > 0 ? 1u : 0u);
+                umma(tmem + p * 128, khi, vlo, idesc, 1u);
+                umma(tmem + p * 128, klo, vhi, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+        }
+        if (iters > 0) umma_commit(&done); else mbar_arrive(&done);
+    }
+
+    // ===== epilogue: per-CTA record [S | z | u | sq slots | sk slots]
+    __syncwarp();
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    ss = warp_sum(ss);
+    if (lane == 0) part[warp] = ss;
+    float* red = reinterpret_cast<float*>(stages);      // all MMAs have completed: stage memory is free
+    if (warp < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            red[warp * kRowF + lane * 8 + i] = zacc[i];
+            red[8 * kRowF + warp * kRowF + lane * 8 + i] = uacc[i];
+        }
+    }
+    __syncthreads();
+    float* rec = ws + (int64_t)blockIdx.x * ws_len;
+    const int64_t offZ = (int64_t)kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim;
+    if (tid < kRowF) {
+        float z = 0.f, u = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { z += red[w * kRowF + tid]; u += red[8 * kRowF + w * kRowF + tid]; }
+        rec[offZ + tid] = z;
+        rec[offU + tid] = u;
+    }
+    if (tid == 0) {
+        float sk = 0.f, sq = 0.f;
+        for (int w = 0; w < 8; ++w) sk += part[w];
+        for (int w = 8; w < 12; ++w) sq += part[w];
+        for (int h = 0; h < kH; ++h) { rec[offSq + h] = h == 0 ? sq : 0.f; rec[offSq + kH + h] = h == 0 ? sk : 0.f; }
+    }
+    if (warp < 4) {
+        // D_p rows 0-63 x cols 0-63 = S_{2p}; rows 64-127 x cols 64-127 = S_{2p+1}; warp w reads lanes 32w..32w+31
+        const int hp = warp >> 1, m = (warp * 32 + lane) & 63;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            float* dst = rec + ((int64_t)(2 * p + hp) * kDim + m) * kDim;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                if (iters > 0) {
+                    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p * 128 + hp * 64 + c0, r);
+                    tmem_ld_wait32(r);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 2
+// ------------------------------------------------------------------------------------------
+constexpr int kTile2 = 128;                           // rows per tile = UMMA M
+constexpr int kQOp = kTile2 * 128;                    // 16 KB: [128 rows][64 bf16] of one head
+constexpr int kStage2 = 2 * kQOp;                     // Qhi | Qlo
+constexpr int kNS2 = 3;
+constexpr int kBN = 80;                               // UMMA N: 64 columns of S + z column + padding
+constexpr int kBOp = kBN * 128;                       // 10 KB
+constexpr int kBBytes = kH * 2 * kBOp;                // 80 KB: per head hi | lo
+constexpr int kNAcc = 4, kAccCols = 128;              // TMEM accumulator ring (4 x 128 columns)
+constexpr int kSmem2 = kBBytes + kNS2 * kStage2 + kH * kDim * 4 + 1024;
+
+struct ApplyTcArgs {
+    const float* q;
+    const float* partials;
+    float n_total;
+    int64_t N;
+    float* out;
+    dif_epilogue_t ep;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* Bop = base;                               // [h][hi|lo][80 rows][128 B]
+    uint8_t* stages = base + kBBytes;
+    float* us = reinterpret_cast<float*>(stages + kNS2 * kStage2);   // [H][64]
+    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
+    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const int nsc = my_tiles * kH;                     // (tile, head) stages of this CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(&tmem_slot, 512);
+
+    // ---- B operands: row n < 64: c*S[h][:, n] ; row 64: c*z[h] ; rows 65..79: 0   (K-major SW128, hi/lo split)
+    const int64_t offZ = (int64_t)kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim;
+    const float c = 1.f / (sqrtf(p.partials[offSq]) * sqrtf(p.partials[offSq + 1]));
+    for (int task = tid; task < kH * 8 * kBN; task += kThreadsTC) {
+        const int n = task % kBN, hc = task / kBN, ch = hc & 7, h = hc >> 3;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = ch * 8 + i;
+            x[i] = n < kDim ? p.partials[((int64_t)h * kDim + m) * kDim + n] * c : (n == kDim ? p.partials[offZ + h * kDim + m] * c : 0.f);
+        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = (uint32_t)(h * 2 * kBOp) + sw128(n, ch);
+        sts128(smem_u32(Bop) + off, hi);
+        sts128(smem_u32(Bop) + kBOp + off, lo);
+    }
+    for (int i = tid; i < kH * kDim; i += kThreadsTC) us[i] = p.partials[offU + i];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ===== Q producers: stage = (tile, head): 128 rows x 256 B; task t -> row t>>3, chunk t&7
+        float qc[4][8], qn[4][8];
+        auto load = [&](int sc, float (&qq)[4][8]) {
+            const int64_t tile = blockIdx.x + (int64_t)(sc >> 2) * gridDim.x;
+            const int h = sc & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                const int64_t row = tile * kTile2 + (t >> 3);
+                if (row < p.N) ldg256_stream(p.q + row * kRowF + h * kDim + (t & 7) * 8, qq[j]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) qq[j][i] = 0.f;
+                }
+            }
+        };
+        if (nsc > 0) load(0, qc);
+        const uint32_t stage_base = smem_u32(stages);
+        for (int sc = 0; sc < nsc; ++sc) {
+            if (sc + 1 < nsc) load(sc + 1, qn);
+            const int s = sc % kNS2;
+            if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+            const uint32_t sb = stage_base + s * kStage2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                uint4 hi, lo;
+                split8(qc[j], hi, lo);
+                const uint32_t off = sw128(t >> 3, t & 7);
+                sts128(sb + off, hi);
+                sts128(sb + kQOp + off, lo);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (sc + 1 < nsc) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) qc[j][i] = qn[j][i];
+            }
+        }
+    } else if (warp < 12) {
+        // ===== epilogue: thread = one row of the tile; accumulator lane = 32*(warp%4) + lane
+        const int ew = warp - 8;
+        const int row_in_tile = ew * 32 + lane;
+        float hs[MODE == 1 ? kDim : 1];
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int64_t tile = blockIdx.x + (int64_t)(sc >> 2) * gridDim.x;
+            const int h = sc & 3, slot = sc % kNAcc;
+            const int64_t row = tile * kTile2 + row_in_tile;
+            mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
+            uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q^.z^
+            tmem_ld_wait1(qz_bits);
+            const float den = __uint_as_float(qz_bits) + p.n_total;
+            if (MODE == 1 && h == 0) {
+#pragma unroll
+                for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < kDim; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait32(r);
+                if (c0 == 32) {          // everything of this slot is in registers: hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[slot]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 u4 = *reinterpret_cast<const float4*>(us + h * kDim + c0 + j);
+                    float4 o;
+                    o.x = (__uint_as_float(r[j]) + u4.x) / den;
+                    o.y = (__uint_as_float(r[j + 1]) + u4.y) / den;
+                    o.z = (__uint_as_float(r[j + 2]) + u4.z) / den;
+                    o.w = (__uint_as_float(r[j + 3]) + u4.w) / den;
+                    if (MODE == 0) {
+                        if (row < p.N) *reinterpret_cast<float4*>(p.out + (row * kH + h) * kDim + c0 + j) = o;
+                    } else {
+                        hs[c0 + j] += o.x; hs[c0 + j + 1] += o.y; hs[c0 + j + 2] += o.z; hs[c0 + j + 3] += o.w;
+                    }
+                }
+            }
+            if (MODE == 1 && h == kH - 1 && row < p.N) {
+#pragma unroll
+                for (int j = 0; j < kDim; j += 4) {
+                    float4 o = make_float4(hs[j] * p.ep.attn_scale, hs[j + 1] * p.ep.attn_scale, hs[j + 2] * p.ep.attn_scale,
+                                           hs[j + 3] * p.ep.attn_scale);
+                    for (int a = 0; a < p.ep.n_add; ++a) {
+                        const float4 x = ldg4(p.ep.add[a] + row * kDim + j);
+                        const float s = p.ep.add_scale[a];
+                        o.x = fmaf(s, x.x, o.x); o.y = fmaf(s, x.y, o.y); o.z = fmaf(s, x.z, o.z); o.w = fmaf(s, x.w, o.w);
+                    }
+                    *reinterpret_cast<float4*>(p.out + row * kDim + j) = o;
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer: per (tile, head): 4 K-steps x (hi*hi + lo*hi + hi*lo), M=128 N=80 K=16
+        const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
+        const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int s = sc % kNS2, slot = sc % kNAcc, h = sc & 3;
+            if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+            mbar_wait(&full[s], (sc / kNS2) & 1);
+            tc_fence_after();
+            const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
+            const uint32_t d = tmem + slot * kAccCols;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
+                umma(d, qlo, bhi, idesc, 1u);
+                umma(d, qhi, blo, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+            umma_commit(&tfull[slot]);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+int tc_grid(int64_t units) {
+    const int sms = sm_count();
+    return (int)(units < sms ? (units < 1 ? 1 : units) : sms);
+}
+
+int tc_rows_per_cta(int64_t N, int* grid) {
+    int g = tc_grid((N + kR1 - 1) / kR1);
+    int64_t rpc = (N + g - 1) / g;
+    rpc = (rpc + kR1 - 1) / kR1 * kR1;
+    g = (int)((N + rpc - 1) / rpc);
+    *grid = g;
+    return (int)rpc;
+}
+
+}  // namespace
+
+bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D) {
+    return N >= 1 && H == kH && Hv == kH && M == kDim && D == kDim;
+}
+
+int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
+    int grid;
+    tc_rows_per_cta(N, &grid);
+    return (int64_t)grid * SimpleLayout{H, Hv, M, D}.wsLen() * (int64_t)sizeof(float);
+}
+
+int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
+                     float* partials, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0, DIF_EARG, "tcgen05 path: q/k/v must be 32-byte aligned");
+    int grid;
+    const int rpc = tc_rows_per_cta(N, &grid);
+    const SimpleLayout L{H, Hv, M, D};
+    DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
+    DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1));
+    reduce_tc_kernel<<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen());
+    DIF_LAUNCH_OK();
+    return simple_finalize_fwd((const float*)ws, grid, H, Hv, M, D, partials, st);
+}
+
+int simple_apply_tc(const float* q, const float* partials, double n_total, int64_t N, int H, int Hv, int M, int D,
+                    float* out, const dif_epilogue_t* ep, cudaStream_t st) {
+    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    DIF_REQUIRE(((uintptr_t)q & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG, "tcgen05 path: q must be 32-byte, out 16-byte aligned");
+    ApplyTcArgs a{};
+    a.q = q; a.partials = partials; a.n_total = (float)n_total; a.N = N; a.out = out;
+    if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
+    DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
+    const int grid = tc_grid((N + kTile2 - 1) / kTile2);
+    if (a.ep.mode == 0) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+        apply_tc_kernel<0><<<grid, kThreadsTC, kSmem2, st>>>(a);
+    } else {
+        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+        apply_tc_kernel<1><<<grid, kThreadsTC, kSmem2, st>>>(a);
+    }
+    DIF_LAUNCH_OK();
+    return DIF_OK;
 }
 
 }  // namespace dif

@@ -152,9 +152,9 @@ def gcn_edge_values(edge_index: Tensor, edge_weight: Optional[Tensor], n: int,
     1.7.2 = scatter-add of ones.  The degree arithmetic is float32 in the reference (:66 .float())."""
     row, col = edge_index[0].long(), edge_index[1].long()
     d = torch.bincount(col, minlength=n).to(torch.float32)
-    val = (1.0 / d[col]).sqrt() * (1.0 / d[row]).sqrt()
-    if edge_weight is not None:
-        val = edge_weight.to(torch.float32) * val
+    d_in, d_out = (1.0 / d[col]).sqrt(), (1.0 / d[row]).sqrt()
+    # same association as the reference: (w * d_in) * d_out, w = 1 when absent (:70-73)
+    val = (edge_weight.to(torch.float32) * d_in if edge_weight is not None else d_in) * d_out
     val = torch.where(torch.isfinite(val), val, torch.zeros_like(val))
     return val.to(dtype)
 

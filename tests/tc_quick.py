@@ -1,0 +1,26 @@
+"""Quick tcgen05 bring-up check (run under a short timeout on the GPU box before the full suite)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from difformer_b200 import ops
+from oracle import difformer_oracle as O
+
+for n in (16, 100, 128, 5000, 132534):
+    q, k, v = O.synthetic_qkv(n, 4, 64, seed=n, adversarial=True)
+    qg, kg, vg = q.cuda(), k.cuda(), v.cuda()
+    ops.set_simple_impl("tcgen05")
+    p_tc = ops.simple_partials(qg, kg, vg)
+    torch.cuda.synchronize()
+    want = O.simple_partials(q.double(), k.double(), v.double())
+    S = p_tc[:16384].reshape(4, 64, 64)
+    print(n, "S", O.rel_err(S, want["S"]), "z", O.rel_err(p_tc[16384:16640].reshape(4, 64), want["z"]),
+          "u", O.rel_err(p_tc[16640:16896].reshape(4, 64), want["u"]), "sq", float(p_tc[16896]) / float(want["sq"]) - 1,
+          "sk", float(p_tc[16897]) / float(want["sk"]) - 1, flush=True)
+    o_tc = ops.simple_apply(qg, p_tc, float(n), 4, 64)
+    torch.cuda.synchronize()
+    print(n, "out", O.rel_err(o_tc, O.simple_apply(q.double(), want)), flush=True)
+    only_s = p_tc.clone(); only_s[16384:16896] = 0
+    qS = ops.simple_apply(qg, only_s, float(n), 4, 64) * n
+    _, parts = O.simple_apply(q.double(), want, return_parts=True)
+    print(n, "qS", O.rel_err(qS, parts["qS"]), flush=True)
+print("tc quick ok")
