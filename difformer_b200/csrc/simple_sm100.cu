@@ -205,54 +205,56 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
     float ss = 0.f;     // producers: sum k^2 ; Q warps: sum q^2
 
     if (warp < 8) {
-        // ===== K/V producers: warp w owns nodes w and w+8 of every 16-node stage, lane l owns columns 8l..8l+7
-        float kc[2][8], vc[2][8], kn[2][8], vn[2][8];
-        auto load = [&](int it, float (&kk)[2][8], float (&vv)[2][8]) {
+        // ===== K/V producers: warp w owns nodes w and w+8 of every 16-node stage, lane l owns columns 8l..8l+7.
+        // Register ring of two iterations x 4 chunks (K/V x 2 nodes): as soon as a chunk is converted its
+        // registers are refilled with the load of iteration it+2, so ~8 x 32 B per thread stay in flight.
+        float buf[2][4][8];
+        auto issue = [&](int it, int c, float (&dst)[8]) {
+            if (it >= iters) return;
+            const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * (c >> 1);
+            if (row < r1) {
+                ldg256_stream(((c & 1) ? v : k) + row * kRowF + lane * 8, dst);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * j;
-                if (row < r1) {
-                    ldg256_stream(k + row * kRowF + lane * 8, kk[j]);
-                    ldg256_stream(v + row * kRowF + lane * 8, vv[j]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { kk[j][i] = 0.f; vv[j][i] = 0.f; }
-                }
+                for (int i = 0; i < 8; ++i) dst[i] = 0.f;
             }
         };
-        if (iters > 0) load(0, kc, vc);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) issue(0, c, buf[0][c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) issue(1, c, buf[1][c]);
         const uint32_t stage_base = smem_u32(stages);
-        for (int it = 0; it < iters; ++it) {
-            if (it + 1 < iters) load(it + 1, kn, vn);
-            const int s = it % kNS1;
-            if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
-            const uint32_t sb = stage_base + s * kStage1;
+        for (int it0 = 0; it0 < iters; it0 += 2) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                // node r = warp + 8j of the stage: (r >> 3) = j, (r & 7) = warp ; head = lane >> 3, chunk = lane & 7
-                const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + j * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
-                uint4 hi, lo;
-                split8(kc[j], hi, lo);
-                sts128(sb + 0 * kOp1 + off, hi);
-                sts128(sb + 1 * kOp1 + off, lo);
-                split8(vc[j], hi, lo);
-                sts128(sb + 2 * kOp1 + off, hi);
-                sts128(sb + 3 * kOp1 + off, lo);
+            for (int half = 0; half < 2; ++half) {
+                const int it = it0 + half;
+                if (it < iters) {
+                    const int s = it % kNS1;
+                    if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
+                    const uint32_t sb = stage_base + s * kStage1;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    zacc[i] += kc[j][i];
-                    uacc[i] += vc[j][i];
-                    ss = fmaf(kc[j][i], kc[j][i], ss);
+                    for (int c = 0; c < 4; ++c) {
+                        // chunk c: node r = warp + 8*(c>>1) of the stage ((r>>3) = c>>1, (r&7) = warp); K for even c, V for odd c
+                        const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + (c >> 1) * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
+                        uint4 hi, lo;
+                        split8(buf[half][c], hi, lo);
+                        sts128(sb + ((c & 1) ? 2 : 0) * kOp1 + off, hi);
+                        sts128(sb + ((c & 1) ? 3 : 1) * kOp1 + off, lo);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (c & 1) {
+                                uacc[i] += buf[half][c][i];
+                            } else {
+                                zacc[i] += buf[half][c][i];
+                                ss = fmaf(buf[half][c][i], buf[half][c][i], ss);
+                            }
+                        }
+                        issue(it + 2, c, buf[half][c]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
                 }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            if (it + 1 < iters) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { kc[j][i] = kn[j][i]; vc[j][i] = vn[j][i]; }
             }
         }
     } else if (warp < 12) {
@@ -262,17 +264,17 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
         const int t = tid - 256;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int64_t i = t;
-        for (; i + 3 * 128 < n8; i += 4 * 128) {
-            float x0[8], x1[8], x2[8], x3[8];
-            ldg256_keep(base + i * 8, x0);
-            ldg256_keep(base + (i + 128) * 8, x1);
-            ldg256_keep(base + (i + 256) * 8, x2);
-            ldg256_keep(base + (i + 384) * 8, x3);
+        for (; i + 7 * 128 < n8; i += 8 * 128) {
+            float x[8][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                a0 = fmaf(x0[e], x0[e], a0); a1 = fmaf(x1[e], x1[e], a1);
-                a2 = fmaf(x2[e], x2[e], a2); a3 = fmaf(x3[e], x3[e], a3);
-            }
+            for (int u = 0; u < 8; ++u) ldg256_keep(base + (i + u * 128) * 8, x[u]);
+#pragma unroll
+            for (int u = 0; u < 8; u += 4)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    a0 = fmaf(x[u][e], x[u][e], a0); a1 = fmaf(x[u + 1][e], x[u + 1][e], a1);
+                    a2 = fmaf(x[u + 2][e], x[u + 2][e], a2); a3 = fmaf(x[u + 3][e], x[u + 3][e], a3);
+                }
         }
         for (; i < n8; i += 128) {
             float x0[8];
@@ -413,19 +415,38 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
     // ---- B operands: row n < 64: c*S[h][:, n] ; row 64: c*z[h] ; rows 65..79: 0   (K-major SW128, hi/lo split)
     const int64_t offZ = (int64_t)kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim;
     const float c = 1.f / (sqrtf(p.partials[offSq]) * sqrtf(p.partials[offSq + 1]));
-    for (int task = tid; task < kH * 8 * kBN; task += kThreadsTC) {
-        const int n = task % kBN, hc = task / kBN, ch = hc & 7, h = hc >> 3;
-        float x[8];
+    {
+        // all loads of a thread's (up to 7) tasks are issued before the first use: two L2 round trips, not 50
+        constexpr int kTasks = kH * 8 * kBN, kPer = (kTasks + kThreadsTC - 1) / kThreadsTC;
+        float x[kPer][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = ch * 8 + i;
-            x[i] = n < kDim ? p.partials[((int64_t)h * kDim + m) * kDim + n] * c : (n == kDim ? p.partials[offZ + h * kDim + m] * c : 0.f);
+        for (int u = 0; u < kPer; ++u) {
+            const int task = tid + u * kThreadsTC;
+            const int n = task % kBN, hc = task / kBN, ch = hc & 7, h = hc >> 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = ch * 8 + i;
+                x[u][i] = 0.f;
+                if (task < kTasks) {
+                    if (n < kDim) x[u][i] = __ldg(p.partials + ((int64_t)h * kDim + m) * kDim + n);
+                    else if (n == kDim) x[u][i] = __ldg(p.partials + offZ + h * kDim + m);
+                }
+            }
         }
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t off = (uint32_t)(h * 2 * kBOp) + sw128(n, ch);
-        sts128(smem_u32(Bop) + off, hi);
-        sts128(smem_u32(Bop) + kBOp + off, lo);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int task = tid + u * kThreadsTC;
+            if (task < kTasks) {
+                const int n = task % kBN, hc = task / kBN, ch = hc & 7, h = hc >> 3;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[u][i] *= c;
+                uint4 hi, lo;
+                split8(x[u], hi, lo);
+                const uint32_t off = (uint32_t)(h * 2 * kBOp) + sw128(n, ch);
+                sts128(smem_u32(Bop) + off, hi);
+                sts128(smem_u32(Bop) + kBOp + off, lo);
+            }
+        }
     }
     for (int i = tid; i < kH * kDim; i += kThreadsTC) us[i] = p.partials[offU + i];
     fence_proxy_async();
@@ -435,46 +456,48 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
     const uint32_t tmem = tmem_slot;
 
     if (warp < 8) {
-        // ===== Q producers: stage = (tile, head): 128 rows x 256 B; task t -> row t>>3, chunk t&7
-        float qc[4][8], qn[4][8];
-        auto load = [&](int sc, float (&qq)[4][8]) {
+        // ===== Q producers: stage = (tile, head): 128 rows x 256 B; task t -> row t>>3, chunk t&7.
+        // Two-stage register ring, refilled chunk by chunk (see pass 1).
+        float buf[2][4][8];
+        auto issue = [&](int sc, int j, float (&dst)[8]) {
+            if (sc >= nsc) return;
             const int64_t tile = blockIdx.x + (int64_t)(sc >> 2) * gridDim.x;
-            const int h = sc & 3;
+            const int t = tid + 256 * j;
+            const int64_t row = tile * kTile2 + (t >> 3);
+            if (row < p.N) {
+                ldg256_stream(p.q + row * kRowF + (sc & 3) * kDim + (t & 7) * 8, dst);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int t = tid + 256 * j;
-                const int64_t row = tile * kTile2 + (t >> 3);
-                if (row < p.N) ldg256_stream(p.q + row * kRowF + h * kDim + (t & 7) * 8, qq[j]);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) qq[j][i] = 0.f;
-                }
+                for (int i = 0; i < 8; ++i) dst[i] = 0.f;
             }
         };
-        if (nsc > 0) load(0, qc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(0, j, buf[0][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
         const uint32_t stage_base = smem_u32(stages);
-        for (int sc = 0; sc < nsc; ++sc) {
-            if (sc + 1 < nsc) load(sc + 1, qn);
-            const int s = sc % kNS2;
-            if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
-            const uint32_t sb = stage_base + s * kStage2;
+        for (int sc0 = 0; sc0 < nsc; sc0 += 2) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int t = tid + 256 * j;
-                uint4 hi, lo;
-                split8(qc[j], hi, lo);
-                const uint32_t off = sw128(t >> 3, t & 7);
-                sts128(sb + off, hi);
-                sts128(sb + kQOp + off, lo);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            if (sc + 1 < nsc) {
+            for (int half = 0; half < 2; ++half) {
+                const int sc = sc0 + half;
+                if (sc < nsc) {
+                    const int s = sc % kNS2;
+                    if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+                    const uint32_t sb = stage_base + s * kStage2;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) qc[j][i] = qn[j][i];
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = tid + 256 * j;
+                        uint4 hi, lo;
+                        split8(buf[half][j], hi, lo);
+                        const uint32_t off = sw128(t >> 3, t & 7);
+                        sts128(sb + off, hi);
+                        sts128(sb + kQOp + off, lo);
+                        issue(sc + 2, j, buf[half][j]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                }
             }
         }
     } else if (warp < 12) {
@@ -491,7 +514,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
             uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q^.z^
             tmem_ld_wait1(qz_bits);
-            const float den = __uint_as_float(qz_bits) + p.n_total;
+            const float inv_den = 1.f / (__uint_as_float(qz_bits) + p.n_total);   // one division per (row, head)
             if (MODE == 1 && h == 0) {
 #pragma unroll
                 for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
@@ -510,10 +533,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
                 for (int j = 0; j < 32; j += 4) {
                     const float4 u4 = *reinterpret_cast<const float4*>(us + h * kDim + c0 + j);
                     float4 o;
-                    o.x = (__uint_as_float(r[j]) + u4.x) / den;
-                    o.y = (__uint_as_float(r[j + 1]) + u4.y) / den;
-                    o.z = (__uint_as_float(r[j + 2]) + u4.z) / den;
-                    o.w = (__uint_as_float(r[j + 3]) + u4.w) / den;
+                    o.x = (__uint_as_float(r[j]) + u4.x) * inv_den;
+                    o.y = (__uint_as_float(r[j + 1]) + u4.y) * inv_den;
+                    o.z = (__uint_as_float(r[j + 2]) + u4.z) * inv_den;
+                    o.w = (__uint_as_float(r[j + 3]) + u4.w) * inv_den;
                     if (MODE == 0) {
                         if (row < p.N) *reinterpret_cast<float4*>(p.out + (row * kH + h) * kDim + c0 + j) = o;
                     } else {
