@@ -21,7 +21,9 @@
 //           warp 12 MMA issuer; epilogue: warps 0-3 TMEM -> per-CTA record (deterministic 2-stage reduce)
 //   pass 2: warps 0-7 Q producers, warps 8-11 epilogue (TMEM -> registers -> (acc+u)/den -> HBM,
 //           optionally the fused layer epilogue), warp 12 MMA issuer.
+#include <cuda.h>        // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -144,6 +146,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// TMA 2-D tensor store: shared (128B-swizzled box) -> global, bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t bf2_bits(float lo_elem, float hi_elem) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo_elem, hi_elem);   // .x (low 16 bits) = first element
     return *reinterpret_cast<uint32_t*>(&h);
@@ -175,6 +186,7 @@ constexpr int kStage1 = 4 * kOp1;                     // 32 KB
 constexpr int kNS1 = 4;
 constexpr int kSmem1 = kNS1 * kStage1 + 1024;
 
+template <bool RING, bool EVICT_FIRST>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
                  int rows_per_cta, float* __restrict__ ws, int64_t ws_len) {
@@ -205,55 +217,108 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
     float ss = 0.f;     // producers: sum k^2 ; Q warps: sum q^2
 
     if (warp < 8) {
-        // ===== K/V producers: warp w owns nodes w and w+8 of every 16-node stage, lane l owns columns 8l..8l+7.
-        // Register ring of two iterations x 4 chunks (K/V x 2 nodes): as soon as a chunk is converted its
-        // registers are refilled with the load of iteration it+2, so ~8 x 32 B per thread stay in flight.
-        float buf[2][4][8];
-        auto issue = [&](int it, int c, float (&dst)[8]) {
-            if (it >= iters) return;
-            const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * (c >> 1);
-            if (row < r1) {
-                ldg256_stream(((c & 1) ? v : k) + row * kRowF + lane * 8, dst);
-            } else {
+        if (!RING) {
+            // variant A: whole-iteration double buffer (loads of it+1 issued, then it converted)
+            float kc[2][8], vc[2][8], kn[2][8], vn[2][8];
+            auto load = [&](int it, float (&kk)[2][8], float (&vv)[2][8]) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = 0.f;
-            }
-        };
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * j;
+                    if (row < r1) {
+                        if (EVICT_FIRST) { ldg256_stream(k + row * kRowF + lane * 8, kk[j]); ldg256_stream(v + row * kRowF + lane * 8, vv[j]); }
+                        else { ldg256_keep(k + row * kRowF + lane * 8, kk[j]); ldg256_keep(v + row * kRowF + lane * 8, vv[j]); }
+                    } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) issue(0, c, buf[0][c]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) issue(1, c, buf[1][c]);
-        const uint32_t stage_base = smem_u32(stages);
-        for (int it0 = 0; it0 < iters; it0 += 2) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int it = it0 + half;
-                if (it < iters) {
-                    const int s = it % kNS1;
-                    if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
-                    const uint32_t sb = stage_base + s * kStage1;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        // chunk c: node r = warp + 8*(c>>1) of the stage ((r>>3) = c>>1, (r&7) = warp); K for even c, V for odd c
-                        const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + (c >> 1) * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
-                        uint4 hi, lo;
-                        split8(buf[half][c], hi, lo);
-                        sts128(sb + ((c & 1) ? 2 : 0) * kOp1 + off, hi);
-                        sts128(sb + ((c & 1) ? 3 : 1) * kOp1 + off, lo);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (c & 1) {
-                                uacc[i] += buf[half][c][i];
-                            } else {
-                                zacc[i] += buf[half][c][i];
-                                ss = fmaf(buf[half][c][i], buf[half][c][i], ss);
-                            }
-                        }
-                        issue(it + 2, c, buf[half][c]);
+                        for (int i = 0; i < 8; ++i) { kk[j][i] = 0.f; vv[j][i] = 0.f; }
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[s]);
+                }
+            };
+            if (iters > 0) load(0, kc, vc);
+            const uint32_t stage_base = smem_u32(stages);
+            for (int it = 0; it < iters; ++it) {
+                if (it + 1 < iters) load(it + 1, kn, vn);
+                const int s = it % kNS1;
+                if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
+                const uint32_t sb = stage_base + s * kStage1;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + j * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
+                    uint4 hi, lo;
+                    split8(kc[j], hi, lo);
+                    sts128(sb + 0 * kOp1 + off, hi);
+                    sts128(sb + 1 * kOp1 + off, lo);
+                    split8(vc[j], hi, lo);
+                    sts128(sb + 2 * kOp1 + off, hi);
+                    sts128(sb + 3 * kOp1 + off, lo);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        zacc[i] += kc[j][i];
+                        uacc[i] += vc[j][i];
+                        ss = fmaf(kc[j][i], kc[j][i], ss);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                if (it + 1 < iters) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { kc[j][i] = kn[j][i]; vc[j][i] = vn[j][i]; }
+                }
+            }
+        } else {
+            // ===== K/V producers: warp w owns nodes w and w+8 of every 16-node stage, lane l owns columns 8l..8l+7.
+            // Register ring of two iterations x 4 chunks (K/V x 2 nodes): as soon as a chunk is converted its
+            // registers are refilled with the load of iteration it+2, so ~8 x 32 B per thread stay in flight.
+            float buf[2][4][8];
+            auto issue = [&](int it, int c, float (&dst)[8]) {
+                if (it >= iters) return;
+                const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * (c >> 1);
+                if (row < r1) {
+                    if (EVICT_FIRST) ldg256_stream(((c & 1) ? v : k) + row * kRowF + lane * 8, dst);
+                    else ldg256_keep(((c & 1) ? v : k) + row * kRowF + lane * 8, dst);
+                } else {
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = 0.f;
+                }
+            };
+    #pragma unroll
+            for (int c = 0; c < 4; ++c) issue(0, c, buf[0][c]);
+    #pragma unroll
+            for (int c = 0; c < 4; ++c) issue(1, c, buf[1][c]);
+            const uint32_t stage_base = smem_u32(stages);
+            for (int it0 = 0; it0 < iters; it0 += 2) {
+    #pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int it = it0 + half;
+                    if (it < iters) {
+                        const int s = it % kNS1;
+                        if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
+                        const uint32_t sb = stage_base + s * kStage1;
+    #pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            // chunk c: node r = warp + 8*(c>>1) of the stage ((r>>3) = c>>1, (r&7) = warp); K for even c, V for odd c
+                            const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + (c >> 1) * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
+                            uint4 hi, lo;
+                            split8(buf[half][c], hi, lo);
+                            sts128(sb + ((c & 1) ? 2 : 0) * kOp1 + off, hi);
+                            sts128(sb + ((c & 1) ? 3 : 1) * kOp1 + off, lo);
+    #pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (c & 1) {
+                                    uacc[i] += buf[half][c][i];
+                                } else {
+                                    zacc[i] += buf[half][c][i];
+                                    ss = fmaf(buf[half][c][i], buf[half][c][i], ss);
+                                }
+                            }
+                            issue(it + 2, c, buf[half][c]);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
+                    }
                 }
             }
         }
@@ -380,7 +445,9 @@ constexpr int kBN = 80;                               // UMMA N: 64 columns of S
 constexpr int kBOp = kBN * 128;                       // 10 KB
 constexpr int kBBytes = kH * 2 * kBOp;                // 80 KB: per head hi | lo
 constexpr int kNAcc = 4, kAccCols = 128;              // TMEM accumulator ring (4 x 128 columns)
-constexpr int kSmem2 = kBBytes + kNS2 * kStage2 + kH * kDim * 4 + 1024;
+constexpr int kOutBox = 32 * 128;                     // TMA store box: 32 rows x 32 floats, 128B swizzle
+constexpr int kOutStage = 4 * 2 * kOutBox;            // per epilogue warp: two boxes (column halves of a head)
+constexpr int kSmem2 = kBBytes + kNS2 * kStage2 + kOutStage + kH * kDim * 4 + 1024;
 
 struct ApplyTcArgs {
     const float* q;
@@ -392,12 +459,13 @@ struct ApplyTcArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) {
+__global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_constant__ ApplyTcArgs p, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* Bop = base;                               // [h][hi|lo][80 rows][128 B]
     uint8_t* stages = base + kBBytes;
-    float* us = reinterpret_cast<float*>(stages + kNS2 * kStage2);   // [H][64]
+    uint8_t* ostage = stages + kNS2 * kStage2;                       // [4 warps][2 boxes][32 rows][128 B], 1024-aligned
+    float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
     __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -501,14 +569,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
             }
         }
     } else if (warp < 12) {
-        // ===== epilogue: thread = one row of the tile; accumulator lane = 32*(warp%4) + lane
+        // ===== epilogue: thread = one row of the tile; accumulator lane = 32*(warp%4) + lane.
+        // Results leave through TMA: each lane writes its row into a 128B-swizzled staging box
+        // (conflict-free st.shared), one lane issues cp.async.bulk.tensor stores (rows beyond N are
+        // clipped by the tensor map).  No scattered st.global on the LSU.
         const int ew = warp - 8;
-        const int row_in_tile = ew * 32 + lane;
+        const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
         float hs[MODE == 1 ? kDim : 1];
         for (int sc = 0; sc < nsc; ++sc) {
             const int64_t tile = blockIdx.x + (int64_t)(sc >> 2) * gridDim.x;
             const int h = sc & 3, slot = sc % kNAcc;
-            const int64_t row = tile * kTile2 + row_in_tile;
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
@@ -518,6 +588,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
             if (MODE == 1 && h == 0) {
 #pragma unroll
                 for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
+            }
+            if (MODE == 0 || h == kH - 1) {       // staging is about to be rewritten: previous TMA reads must be done
+                if (lane == 0) tma_wait_read0();
+                __syncwarp();
             }
 #pragma unroll
             for (int c0 = 0; c0 < kDim; c0 += 32) {
@@ -538,26 +612,44 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
                     o.z = (__uint_as_float(r[j + 2]) + u4.z) * inv_den;
                     o.w = (__uint_as_float(r[j + 3]) + u4.w) * inv_den;
                     if (MODE == 0) {
-                        if (row < p.N) *reinterpret_cast<float4*>(p.out + (row * kH + h) * kDim + c0 + j) = o;
+                        sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
+                               make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
                     } else {
                         hs[c0 + j] += o.x; hs[c0 + j + 1] += o.y; hs[c0 + j + 2] += o.z; hs[c0 + j + 3] += o.w;
                     }
                 }
             }
-            if (MODE == 1 && h == kH - 1 && row < p.N) {
+            if (MODE == 1 && h == kH - 1) {
+                const int64_t row = tile * kTile2 + ew * 32 + lane;
+                const bool ok = row < p.N;
 #pragma unroll
                 for (int j = 0; j < kDim; j += 4) {
                     float4 o = make_float4(hs[j] * p.ep.attn_scale, hs[j + 1] * p.ep.attn_scale, hs[j + 2] * p.ep.attn_scale,
                                            hs[j + 3] * p.ep.attn_scale);
                     for (int a = 0; a < p.ep.n_add; ++a) {
-                        const float4 x = ldg4(p.ep.add[a] + row * kDim + j);
-                        const float s = p.ep.add_scale[a];
-                        o.x = fmaf(s, x.x, o.x); o.y = fmaf(s, x.y, o.y); o.z = fmaf(s, x.z, o.z); o.w = fmaf(s, x.w, o.w);
+                        if (ok) {
+                            const float4 x = ldg4(p.ep.add[a] + row * kDim + j);
+                            const float s = p.ep.add_scale[a];
+                            o.x = fmaf(s, x.x, o.x); o.y = fmaf(s, x.y, o.y); o.z = fmaf(s, x.z, o.z); o.w = fmaf(s, x.w, o.w);
+                        }
                     }
-                    *reinterpret_cast<float4*>(p.out + row * kDim + j) = o;
+                    sts128(obox + (j >> 5) * kOutBox + sw128(lane, (j & 31) >> 2),
+                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                }
+            }
+            if (MODE == 0 || h == kH - 1) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const int col = MODE == 0 ? h * kDim : 0;
+                    const int row0 = (int)(tile * kTile2) + ew * 32;
+                    tma_store_2d(&out_map, obox, col, row0);
+                    tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
+                    tma_commit();
                 }
             }
         }
+        if (lane == 0) tma_wait_all0();      // stores must have landed before the CTA exits
     } else if (lane == 0) {
         // ===== MMA issuer: per (tile, head): 4 K-steps x (hi*hi + lo*hi + hi*lo), M=128 N=80 K=16
         const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
@@ -585,6 +677,29 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(ApplyTcArgs p) 
     tc_fence_before();
     __syncthreads();
     if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 [rows][cols] row-major tensor, box = 32 rows x 32 floats (128 B), 128B swizzle
+int make_out_map(CUtensorMap* map, float* base, int64_t rows, int64_t cols) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DIF_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+        DIF_REQUIRE(f && q == cudaDriverEntryPointSuccess, DIF_ECUDA, "cuTensorMapEncodeTiled not available in this driver");
+        fn = (EncodeTiledFn)f;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DIF_REQUIRE(r == CUDA_SUCCESS, DIF_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DIF_OK;
 }
 
 int tc_grid(int64_t units) {
@@ -621,8 +736,22 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     const int rpc = tc_rows_per_cta(N, &grid);
     const SimpleLayout L{H, Hv, M, D};
     DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
-    DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1));
-    reduce_tc_kernel<<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen());
+    static const int variant = [] {       // tuning switches (defaults = measured best): ring | 2*evict_first
+        const char* e = getenv("DIF_TC_P1_VARIANT");
+        return e ? atoi(e) : 3;
+    }();
+#define DIF_P1(R, E)                                                                                                  \
+    do {                                                                                                              \
+        DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tc_kernel<R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1)); \
+        reduce_tc_kernel<R, E><<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen());             \
+    } while (0)
+    switch (variant & 3) {
+        case 0: DIF_P1(false, false); break;
+        case 1: DIF_P1(true, false); break;
+        case 2: DIF_P1(false, true); break;
+        default: DIF_P1(true, true); break;
+    }
+#undef DIF_P1
     DIF_LAUNCH_OK();
     return simple_finalize_fwd((const float*)ws, grid, H, Hv, M, D, partials, st);
 }
@@ -636,12 +765,16 @@ int simple_apply_tc(const float* q, const float* partials, double n_total, int64
     if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
     const int grid = tc_grid((N + kTile2 - 1) / kTile2);
+    DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
+    CUtensorMap map;
+    int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)kH * kDim : (int64_t)kDim);
+    if (rc) return rc;
     if (a.ep.mode == 0) {
         DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
-        apply_tc_kernel<0><<<grid, kThreadsTC, kSmem2, st>>>(a);
+        apply_tc_kernel<0><<<grid, kThreadsTC, kSmem2, st>>>(a, map);
     } else {
         DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
-        apply_tc_kernel<1><<<grid, kThreadsTC, kSmem2, st>>>(a);
+        apply_tc_kernel<1><<<grid, kThreadsTC, kSmem2, st>>>(a, map);
     }
     DIF_LAUNCH_OK();
     return DIF_OK;

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Times the individual C-ABI calls of the 'simple' path at config A with CUDA events (kernel tuning aid).
+   python tools/kbench.py [--n 132534] [--iters 200] [--impl auto]"""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from difformer_b200 import ops
+from oracle import difformer_oracle as O
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=132534)
+ap.add_argument("--iters", type=int, default=200)
+ap.add_argument("--impl", default="auto")
+ap.add_argument("--tag", default="")
+a = ap.parse_args()
+ops.set_simple_impl(a.impl)
+q, k, v = (t.cuda() for t in O.synthetic_qkv(a.n, 4, 64, seed=1))
+T = a.n * 4 * 64 * 4
+
+
+def timeit(fn, iters):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+part = ops.simple_partials(q, k, v)
+t_red = timeit(lambda: ops.simple_partials(q, k, v), a.iters)
+t_app = timeit(lambda: ops.simple_apply(q, part, float(a.n), 4, 64), a.iters)
+t_op = timeit(lambda: ops.simple_apply(q, ops.simple_partials(q, k, v), float(a.n), 4, 64), a.iters)
+print(f"{a.tag} n={a.n} reduce+finalize {t_red:7.1f} us ({3*T/t_red/1e3:6.0f} GB/s)  apply {t_app:7.1f} us ({2*T/t_app/1e3:6.0f} GB/s)  "
+      f"op {t_op:7.1f} us  roofline(4T) {4*T/t_op/1e3/6571.2:5.3f}", flush=True)
