@@ -142,6 +142,10 @@ __device__ __forceinline__ void ldg256_keep(const float* p, float (&r)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
 }
+// fire-and-forget bulk prefetch of a contiguous global range into L2 (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -150,6 +154,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 :: "l"(map), "r"(smem_src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -189,7 +202,7 @@ constexpr int kSmem1 = kNS1 * kStage1 + 1024;
 template <bool RING, bool EVICT_FIRST>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
-                 int rows_per_cta, float* __restrict__ ws, int64_t ws_len) {
+                 int rows_per_cta, float* __restrict__ ws, int64_t ws_len, int pf_dist) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full[kNS1], empty[kNS1], done;
@@ -359,6 +372,17 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
         const uint32_t stage_base = smem_u32(stages);
         for (int it = 0; it < iters; ++it) {
             const int s = it % kNS1;
+            if (pf_dist > 0) {
+                // L2 prefetch of the rows `pf_dist` stages ahead (K, V, Q: 16 KB each, contiguous): the producers'
+                // register loads then hit L2, which roughly triples the bandwidth one load slot sustains
+                const int64_t prow = r0 + (int64_t)(it + pf_dist) * kR1;
+                if (prow < r1) {
+                    const uint32_t bytes = (uint32_t)(min((int64_t)kR1, r1 - prow) * kRowF * 4);
+                    prefetch_l2(k + prow * kRowF, bytes);
+                    prefetch_l2(v + prow * kRowF, bytes);
+                    prefetch_l2(q + prow * kRowF, bytes);
+                }
+            }
             mbar_wait(&full[s], (it / kNS1) & 1);
             tc_fence_after();
             const uint32_t sb = stage_base + s * kStage1;
@@ -455,10 +479,14 @@ struct ApplyTcArgs {
     float n_total;
     int64_t N;
     float* out;
+    int tiles_per_cta;      // > 0: CTA b owns tiles [b*tpc, (b+1)*tpc) -- the row range it reduced in pass 1 -- and walks
+                            //      them backwards, so the Q rows pass 1 touched last are re-read first (L2 hits)
+    int pf_tiles;           // L2 prefetch distance in tiles (0 = off)
+    int store_hint;         // 1: TMA stores carry an L2 evict_first policy (output is not re-read; keeps Q resident)
     dif_epilogue_t ep;
 };
 
-template <int MODE>
+template <int MODE, bool RING>
 __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_constant__ ApplyTcArgs p, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -470,8 +498,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
-    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const bool contiguous = p.tiles_per_cta > 0;
+    const int64_t first_tile = contiguous ? (int64_t)blockIdx.x * p.tiles_per_cta : blockIdx.x;
+    int my_tiles;
+    if (contiguous) {
+        const int64_t rem = ntiles - first_tile;
+        my_tiles = rem <= 0 ? 0 : (rem < p.tiles_per_cta ? (int)rem : p.tiles_per_cta);
+    } else {
+        my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    }
     const int nsc = my_tiles * kH;                     // (tile, head) stages of this CTA
+    auto tile_of = [&](int sc) -> int64_t {
+        const int i = sc >> 2;
+        return contiguous ? first_tile + (my_tiles - 1 - i) : first_tile + (int64_t)i * gridDim.x;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
@@ -529,7 +569,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         float buf[2][4][8];
         auto issue = [&](int sc, int j, float (&dst)[8]) {
             if (sc >= nsc) return;
-            const int64_t tile = blockIdx.x + (int64_t)(sc >> 2) * gridDim.x;
+            const int64_t tile = tile_of(sc);
             const int t = tid + 256 * j;
             const int64_t row = tile * kTile2 + (t >> 3);
             if (row < p.N) {
@@ -544,27 +584,54 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
         const uint32_t stage_base = smem_u32(stages);
-        for (int sc0 = 0; sc0 < nsc; sc0 += 2) {
+        if (RING) {
+            for (int sc0 = 0; sc0 < nsc; sc0 += 2) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int sc = sc0 + half;
-                if (sc < nsc) {
-                    const int s = sc % kNS2;
-                    if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
-                    const uint32_t sb = stage_base + s * kStage2;
+                for (int half = 0; half < 2; ++half) {
+                    const int sc = sc0 + half;
+                    if (sc < nsc) {
+                        const int s = sc % kNS2;
+                        if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+                        const uint32_t sb = stage_base + s * kStage2;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int t = tid + 256 * j;
-                        uint4 hi, lo;
-                        split8(buf[half][j], hi, lo);
-                        const uint32_t off = sw128(t >> 3, t & 7);
-                        sts128(sb + off, hi);
-                        sts128(sb + kQOp + off, lo);
-                        issue(sc + 2, j, buf[half][j]);
+                        for (int j = 0; j < 4; ++j) {
+                            const int t = tid + 256 * j;
+                            uint4 hi, lo;
+                            split8(buf[half][j], hi, lo);
+                            const uint32_t off = sw128(t >> 3, t & 7);
+                            sts128(sb + off, hi);
+                            sts128(sb + kQOp + off, lo);
+                            issue(sc + 2, j, buf[half][j]);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[s]);
+                }
+            }
+        } else {
+            // whole-stage double buffer: buf[0] = current, buf[1] = next (loads of sc+1 issued, then sc converted)
+            for (int sc = 0; sc < nsc; ++sc) {
+                const int s = sc % kNS2;
+                if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+                const uint32_t sb = stage_base + s * kStage2;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = tid + 256 * j;
+                    uint4 hi, lo;
+                    split8(buf[0][j], hi, lo);
+                    const uint32_t off = sw128(t >> 3, t & 7);
+                    sts128(sb + off, hi);
+                    sts128(sb + kQOp + off, lo);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
+                    issue(sc + 2, j, buf[1][j]);
                 }
             }
         }
@@ -577,7 +644,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
         float hs[MODE == 1 ? kDim : 1];
         for (int sc = 0; sc < nsc; ++sc) {
-            const int64_t tile = blockIdx.x + (int64_t)(sc >> 2) * gridDim.x;
+            const int64_t tile = tile_of(sc);
             const int h = sc & 3, slot = sc % kNAcc;
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
@@ -643,8 +710,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                 if (lane == 0) {
                     const int col = MODE == 0 ? h * kDim : 0;
                     const int row0 = (int)(tile * kTile2) + ew * 32;
-                    tma_store_2d(&out_map, obox, col, row0);
-                    tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
+                    if (p.store_hint) {
+                        const uint64_t pol = policy_evict_first();
+                        tma_store_2d_hint(&out_map, obox, col, row0, pol);
+                        tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
+                    } else {
+                        tma_store_2d(&out_map, obox, col, row0);
+                        tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
+                    }
                     tma_commit();
                 }
             }
@@ -656,6 +729,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
         for (int sc = 0; sc < nsc; ++sc) {
             const int s = sc % kNS2, slot = sc % kNAcc, h = sc & 3;
+            if (p.pf_tiles > 0 && h == 0 && sc + 4 * p.pf_tiles < nsc) {
+                const int64_t ptile = tile_of(sc + 4 * p.pf_tiles);
+                const int64_t prow = ptile * kTile2;
+                const int64_t nrows = min((int64_t)kTile2, p.N - prow);
+                for (int64_t r = 0; r < nrows; r += 16)
+                    prefetch_l2(p.q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
+            }
             if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
             mbar_wait(&full[s], (sc / kNS2) & 1);
             tc_fence_after();
@@ -707,13 +787,19 @@ int tc_grid(int64_t units) {
     return (int)(units < sms ? (units < 1 ? 1 : units) : sms);
 }
 
+// Row partition shared by both passes: contiguous ranges of whole 128-row tiles, one per CTA.
 int tc_rows_per_cta(int64_t N, int* grid) {
-    int g = tc_grid((N + kR1 - 1) / kR1);
+    int g = tc_grid((N + kTile2 - 1) / kTile2);
     int64_t rpc = (N + g - 1) / g;
-    rpc = (rpc + kR1 - 1) / kR1 * kR1;
+    rpc = (rpc + kTile2 - 1) / kTile2 * kTile2;
     g = (int)((N + rpc - 1) / rpc);
     *grid = g;
     return (int)rpc;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 }  // namespace
@@ -736,14 +822,12 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     const int rpc = tc_rows_per_cta(N, &grid);
     const SimpleLayout L{H, Hv, M, D};
     DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
-    static const int variant = [] {       // tuning switches (defaults = measured best): ring | 2*evict_first
-        const char* e = getenv("DIF_TC_P1_VARIANT");
-        return e ? atoi(e) : 3;
-    }();
+    static const int variant = env_int("DIF_TC_P1_VARIANT", 2);   // tuning switches: 1 = register ring, 2 = K/V evict_first
+    static const int pf = env_int("DIF_TC_P1_PREFETCH", 0);       // L2 prefetch distance in 16-row stages (0 = off)
 #define DIF_P1(R, E)                                                                                                  \
     do {                                                                                                              \
         DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tc_kernel<R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1)); \
-        reduce_tc_kernel<R, E><<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen());             \
+        reduce_tc_kernel<R, E><<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen(), pf);             \
     } while (0)
     switch (variant & 3) {
         case 0: DIF_P1(false, false); break;
@@ -764,18 +848,29 @@ int simple_apply_tc(const float* q, const float* partials, double n_total, int64
     a.q = q; a.partials = partials; a.n_total = (float)n_total; a.N = N; a.out = out;
     if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
-    const int grid = tc_grid((N + kTile2 - 1) / kTile2);
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
+    // tuning switches: 1 = register ring, 2 = contiguous reversed tile order (pass-1 partition), 4 = evict_first stores
+    static const int variant = env_int("DIF_TC_P2_VARIANT", 6);
+    int grid;
+    if (variant & 2) {
+        a.tiles_per_cta = tc_rows_per_cta(N, &grid) / kTile2;
+    } else {
+        a.tiles_per_cta = 0;
+        grid = tc_grid((N + kTile2 - 1) / kTile2);
+    }
+    a.store_hint = (variant & 4) ? 1 : 0;
+    a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 0);
     CUtensorMap map;
     int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)kH * kDim : (int64_t)kDim);
     if (rc) return rc;
-    if (a.ep.mode == 0) {
-        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
-        apply_tc_kernel<0><<<grid, kThreadsTC, kSmem2, st>>>(a, map);
-    } else {
-        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
-        apply_tc_kernel<1><<<grid, kThreadsTC, kSmem2, st>>>(a, map);
-    }
+#define DIF_P2(MODE, R)                                                                                                    \
+    do {                                                                                                                   \
+        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));  \
+        apply_tc_kernel<MODE, R><<<grid, kThreadsTC, kSmem2, st>>>(a, map);                                                \
+    } while (0)
+    if (a.ep.mode == 0) { if (variant & 1) DIF_P2(0, true); else DIF_P2(0, false); }
+    else                { if (variant & 1) DIF_P2(1, true); else DIF_P2(1, false); }
+#undef DIF_P2
     DIF_LAUNCH_OK();
     return DIF_OK;
 }
