@@ -123,9 +123,9 @@ def cpu_reference_rate(steps, warmup, budget_s, rows=None):
     with torch.no_grad():
         for c in cands:
             torch.set_num_threads(c)
-            O.simple_attention(q[:32768], k[:32768], v[:32768])
+            O.simple_attention_reference_chain(q[:32768], k[:32768], v[:32768])
             t0 = time.perf_counter()
-            O.simple_attention(q[:32768], k[:32768], v[:32768])
+            O.simple_attention_reference_chain(q[:32768], k[:32768], v[:32768])
             dt = time.perf_counter() - t0
             if dt < best[1]:
                 best = (c, dt)
@@ -134,17 +134,17 @@ def cpu_reference_rate(steps, warmup, budget_s, rows=None):
     with torch.no_grad():
         if rows is None:
             t0 = time.perf_counter()
-            O.simple_attention(q, k, v)
+            O.simple_attention_reference_chain(q, k, v)
             t_full = time.perf_counter() - t0
             frac = min(1.0, budget_s / max(t_full * (steps + warmup), 1e-9))
             rows = max(4096, int(N_NODES * frac))
         rows = min(rows, N_NODES)
         qs, ks, vs = q[:rows].contiguous(), k[:rows].contiguous(), v[:rows].contiguous()
         for _ in range(warmup):
-            O.simple_attention(qs, ks, vs)
+            O.simple_attention_reference_chain(qs, ks, vs)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.simple_attention(qs, ks, vs)
+            O.simple_attention_reference_chain(qs, ks, vs)
         dt = (time.perf_counter() - t0) / steps
     return rows / dt, dt, rows, threads
 
@@ -155,7 +155,7 @@ def run_reference(args):
         return
     rate, dt, rows, threads = cpu_reference_rate(args.steps, args.warmup, budget_s=120.0)
     sample = (f"{rows} of {N_NODES} rows per step (cost is linear in rows), H={HEADS} D={DIM} fp32, "
-              f"oracle port of difformer.py:18-39 on torch CPU, {threads} threads")
+              f"oracle transcription of the einsum chain difformer.py:18-39 on torch CPU, {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -294,11 +294,27 @@ def run_ours(args):
             roof["passes"] = [
                 {"name": "pass1 reduce+finalize", "ms": r_ms, "moved_bytes": 3 * T, "gbs": 3 * T / (r_ms * 1e-3) / 1e9},
                 {"name": "pass2 apply", "ms": a_ms, "moved_bytes": 2 * T, "gbs": 2 * T / (a_ms * 1e-3) / 1e9}]
+        torch_gpu = None
+        if world == 1:
+            # the reference's own op chain (einsums + materialised broadcasts) on the same B200, CUDA tensors
+            with torch.no_grad():
+                for _ in range(5):
+                    O.simple_attention_reference_chain(q, k, v)
+                torch.cuda.synchronize(dev)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(20):
+                    O.simple_attention_reference_chain(q, k, v)
+                g1.record()
+                torch.cuda.synchronize(dev)
+            tg = g0.elapsed_time(g1) / 20
+            torch_gpu = {"value": N_NODES / (tg * 1e-3), "unit": UNIT, "ms_per_step": tg,
+                         "what": "reference einsum chain (difformer.py:18-39 transcription) in PyTorch eager on the same GPU"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, dt, rows, threads = cpu_reference_rate(steps=8, warmup=2, budget_s=20.0)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{rows} of {N_NODES} rows x 8 steps, oracle port of difformer.py:18-39, torch CPU fp32"}
+                   "sample": f"{rows} of {N_NODES} rows x 8 steps, oracle transcription of the einsum chain difformer.py:18-39, torch CPU fp32"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -307,7 +323,7 @@ def run_ours(args):
                            "parallelism": "single GPU" if world == 1 else f"row-shard x{world}, one NCCL all-reduce of 16898 fp32 per step",
                            "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps",
                            "simple_impl": args.simple_impl or "auto"},
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
                 "e2e": {"value": N_NODES * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": 3 * T, "d2h_bytes_per_step": T, "steps": e2e_steps,
                         "api": "difformer.full_attention_conv(q, k, v, 'simple') on pinned host tensors"},

@@ -69,6 +69,25 @@ def simple_attention(qs: Tensor, ks: Tensor, vs: Tensor) -> Tensor:
     return simple_apply(qs, simple_partials(qs, ks, vs))
 
 
+def simple_attention_reference_chain(qs: Tensor, ks: Tensor, vs: Tensor) -> Tensor:
+    """Op-for-op transcription of the reference's einsum chain (difformer.py:18-39), including its
+    materialised broadcasts (`repeat`, `ones`), for TIMING the "reference PyTorch path" on CPU or on
+    the same GPU.  Same maths as `simple_attention`; kept separate because
+    the launch count / memory traffic of this exact chain is what the speed-up is quoted against."""
+    qs = qs / torch.norm(qs, p=2)                                                    # :20
+    ks = ks / torch.norm(ks, p=2)                                                    # :21
+    n = qs.shape[0]
+    kvs = torch.einsum("lhm,lhd->hmd", ks, vs)                                       # :25
+    num = torch.einsum("nhm,hmd->nhd", qs, kvs)                                      # :26
+    ones = torch.ones([vs.shape[0]], device=vs.device, dtype=vs.dtype)               # :27
+    vs_sum = torch.einsum("l,lhd->hd", ones, vs)                                     # :28
+    num = num + vs_sum.unsqueeze(0).repeat(vs.shape[0], 1, 1)                        # :29
+    ks_sum = torch.einsum("lhm,l->hm", ks, ones)                                     # :33
+    den = torch.einsum("nhm,hm->nh", qs, ks_sum).unsqueeze(-1)                       # :34,37
+    den = den + torch.ones_like(den) * n                                             # :38
+    return num / den                                                                 # :39
+
+
 def simple_attention_dense_attn(qs: Tensor, ks: Tensor) -> Tensor:
     """output_attn branch, difformer.py:42-43: q^k^T/den WITHOUT the '+1' (rows do not sum to 1)."""
     a, b = torch.linalg.vector_norm(qs), torch.linalg.vector_norm(ks)
