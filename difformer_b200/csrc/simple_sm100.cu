@@ -146,6 +146,24 @@ __device__ __forceinline__ void ldg256_keep(const float* p, float (&r)[8]) {
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2_hint(const void* p, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" :: "l"(p), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first_() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 256-bit load with an explicit L2 eviction policy
+__device__ __forceinline__ void ldg256_policy(const float* p, float (&r)[8], uint64_t policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p), "l"(policy));
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -202,7 +220,7 @@ constexpr int kSmem1 = kNS1 * kStage1 + 1024;
 template <bool RING, bool EVICT_FIRST>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
-                 int rows_per_cta, float* __restrict__ ws, int64_t ws_len, int pf_dist) {
+                 int rows_per_cta, float* __restrict__ ws, int64_t ws_len, int pf_dist, int q_keep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full[kNS1], empty[kNS1], done;
@@ -340,12 +358,16 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
         const int64_t n8 = (r1 > r0 ? (r1 - r0) : 0) * (kRowF / 8);
         const float* base = q + r0 * kRowF;
         const int t = tid - 256;
+        const uint64_t qpol = policy_evict_last();
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int64_t i = t;
         for (; i + 7 * 128 < n8; i += 8 * 128) {
             float x[8][8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) ldg256_keep(base + (i + u * 128) * 8, x[u]);
+            for (int u = 0; u < 8; ++u) {
+                if (q_keep) ldg256_policy(base + (i + u * 128) * 8, x[u], qpol);
+                else ldg256_keep(base + (i + u * 128) * 8, x[u]);
+            }
 #pragma unroll
             for (int u = 0; u < 8; u += 4)
 #pragma unroll
@@ -378,9 +400,15 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
                 const int64_t prow = r0 + (int64_t)(it + pf_dist) * kR1;
                 if (prow < r1) {
                     const uint32_t bytes = (uint32_t)(min((int64_t)kR1, r1 - prow) * kRowF * 4);
-                    prefetch_l2(k + prow * kRowF, bytes);
-                    prefetch_l2(v + prow * kRowF, bytes);
-                    prefetch_l2(q + prow * kRowF, bytes);
+                    if (q_keep) {       // K,V are dead after this pass, Q is re-read by pass 2: tell the L2
+                        prefetch_l2_hint(k + prow * kRowF, bytes, policy_evict_first_());
+                        prefetch_l2_hint(v + prow * kRowF, bytes, policy_evict_first_());
+                        prefetch_l2_hint(q + prow * kRowF, bytes, policy_evict_last());
+                    } else {
+                        prefetch_l2(k + prow * kRowF, bytes);
+                        prefetch_l2(v + prow * kRowF, bytes);
+                        prefetch_l2(q + prow * kRowF, bytes);
+                    }
                 }
             }
             mbar_wait(&full[s], (it / kNS1) & 1);
@@ -822,12 +850,12 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     const int rpc = tc_rows_per_cta(N, &grid);
     const SimpleLayout L{H, Hv, M, D};
     DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
-    static const int variant = env_int("DIF_TC_P1_VARIANT", 2);   // tuning switches: 1 = register ring, 2 = K/V evict_first
+    static const int variant = env_int("DIF_TC_P1_VARIANT", 2);   // tuning switches: 1 = register ring, 2 = K/V evict_first, 4 = Q evict_last (+ policy-hinted prefetch)
     static const int pf = env_int("DIF_TC_P1_PREFETCH", 0);       // L2 prefetch distance in 16-row stages (0 = off)
 #define DIF_P1(R, E)                                                                                                  \
     do {                                                                                                              \
         DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tc_kernel<R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1)); \
-        reduce_tc_kernel<R, E><<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen(), pf);             \
+        reduce_tc_kernel<R, E><<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen(), pf, (variant >> 2) & 1);             \
     } while (0)
     switch (variant & 3) {
         case 0: DIF_P1(false, false); break;
