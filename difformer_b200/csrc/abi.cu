@@ -60,17 +60,19 @@ static int pick_impl(int impl, int64_t N, int H, int Hv, int M, int D, bool* use
     return set_error(DIF_EARG, "simple: unknown impl %d", impl);
 }
 
+extern "C" int64_t dif_simple_prepared_bytes(int H, int Hv, int M, int D) { return simple_tc_prepared_bytes(H, Hv, M, D); }
+
 extern "C" int dif_simple_reduce(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
-                                 float* partials, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+                                 float* partials, void* prepared, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
     DIF_REQUIRE(q && k && v && partials && workspace, DIF_EARG, "simple_reduce: null pointer");
     bool tc = false;
     int rc = pick_impl(impl, N, H, Hv, M, D, &tc);
     if (rc) return rc;
-    return tc ? simple_reduce_tc(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream)
+    return tc ? simple_reduce_tc(q, k, v, N, H, Hv, M, D, partials, prepared, workspace, workspace_bytes, (cudaStream_t)stream)
               : simple_reduce_generic(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int dif_simple_apply(const float* q, const float* partials, double n_total, int64_t N, int H, int Hv, int M, int D,
+extern "C" int dif_simple_apply(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                                 float* out, const dif_epilogue_t* epilogue, int impl, void* stream) {
     DIF_REQUIRE(q && partials && out, DIF_EARG, "simple_apply: null pointer");
     DIF_REQUIRE(n_total > 0, DIF_EARG, "simple_apply: n_total must be positive");
@@ -81,6 +83,6 @@ extern "C" int dif_simple_apply(const float* q, const float* partials, double n_
     bool tc = false;
     int rc = pick_impl(impl, N, H, Hv, M, D, &tc);
     if (rc) return rc;
-    return tc ? simple_apply_tc(q, partials, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream)
+    return tc ? simple_apply_tc(q, partials, prepared, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream)
               : simple_apply_generic(q, partials, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream);
 }

@@ -25,6 +25,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace dif {
@@ -47,6 +49,17 @@ constexpr uint32_t kKmajLBO = 0, kKmajSBO = 1024;
 #ifndef DIF_MN_LBO_IS_MNSTRIDE
 #define DIF_MN_LBO_IS_MNSTRIDE 1
 #endif
+
+// ---- optional in-kernel timeline (DIF_TC_DEBUG_TIMES=1): thread 0 of every CTA stamps %globaltimer
+__device__ __forceinline__ uint64_t gtime() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DIF_STAMP(buf, slot)                                                        \
+    do {                                                                            \
+        if ((buf) != nullptr && threadIdx.x == 0) (buf)[blockIdx.x * 8 + (slot)] = gtime(); \
+    } while (0)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -487,6 +500,289 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
 }
 
 // ------------------------------------------------------------------------------------------
+// pass 1, TMA-staged variant: the K/V/Q rows of a stage (16 nodes x 3 x 1 KB, contiguous in HBM) are
+// fetched with cp.async.bulk into an fp32 staging ring (mbarrier complete_tx), so the loads in
+// flight are bounded by shared memory (3 x 48 KB per SM), not by registers / L1 miss tracking.
+// Converter warps read the staging rows (conflict-free LDS.128), split to bf16 hi/lo and write the
+// swizzled UMMA operand ring.
+// ------------------------------------------------------------------------------------------
+constexpr int kBOpBytes = 80 * 128;                   // one (head, hi|lo) B-operand tile of pass 2: 80 rows x 128 B
+constexpr int kNSG = 3;                               // staging stages
+constexpr int kStgT = kR1 * 1024;                     // 16 KB: 16 rows of one tensor
+constexpr int kStg = 3 * kStgT;                       // K | V | Q
+constexpr int kNO = 2;                                // operand stages
+constexpr int kSmem1T = kNSG * kStg + kNO * kStage1 + 1024;
+constexpr int kThreadsT = 10 * 32;                    // warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" :: "r"(addr), "r"(a), "r"(b) : "memory");
+}
+// 4 floats -> 4 bf16 hi (8 B) + 4 bf16 lo (8 B)
+__device__ __forceinline__ void split4(const float4& x, uint32_t (&hi)[2], uint32_t (&lo)[2]) {
+    hi[0] = bf2_bits(x.x, x.y);
+    hi[1] = bf2_bits(x.z, x.w);
+    lo[0] = bf2_bits(x.x - __uint_as_float(hi[0] << 16), x.y - __uint_as_float(hi[0] & 0xffff0000u));
+    lo[1] = bf2_bits(x.z - __uint_as_float(hi[1] << 16), x.w - __uint_as_float(hi[1] & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(kThreadsT, 1)
+reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
+                  int rows_per_cta, float* __restrict__ ws, int64_t ws_len, unsigned long long* __restrict__ flags,
+                  unsigned long long epoch, float* __restrict__ partials, uint8_t* __restrict__ prepared,
+                  uint64_t* __restrict__ dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* stg = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ops = stg + kNSG * kStg;
+    __shared__ uint64_t sfull[kNSG], sempty[kNSG], ofull[kNO], oempty[kNO], done, tail_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(N, r0 + (int64_t)rows_per_cta);
+    const int iters = r1 > r0 ? (int)((r1 - r0 + kR1 - 1) / kR1) : 0;
+    DIF_STAMP(dbg, 0);
+
+    if (tid == 0) {
+        for (int s = 0; s < kNSG; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); }
+        for (int s = 0; s < kNO; ++s) { mbar_init(&ofull[s], 8); mbar_init(&oempty[s], 1); }
+        mbar_init(&done, 1);
+        mbar_init(&tail_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    DIF_STAMP(dbg, 1);
+
+    float zacc[8], uacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { zacc[i] = 0.f; uacc[i] = 0.f; }
+    float ssk = 0.f, ssq = 0.f;
+
+    if (warp < 8) {
+        // ===== converters: warp w owns nodes w and w+8 of every stage; lane l owns columns 4l..4l+3 and 128+4l..131+4l
+        const uint32_t stg_base = smem_u32(stg), ops_base = smem_u32(ops);
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kNSG, o = it % kNO;
+            const int nrows = (int)min((int64_t)kR1, r1 - (r0 + (int64_t)it * kR1));
+            mbar_wait(&sfull[s], (it / kNSG) & 1);
+            if (it == 0) DIF_STAMP(dbg, 2);
+            float4 x[2][3][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int node = warp + 8 * j;
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        x[j][t][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (node < nrows) x[j][t][g] = lds128(stg_base + s * kStg + t * kStgT + node * 1024 + g * 512 + lane * 16);
+                    }
+            }
+            if (it >= kNO) mbar_wait(&oempty[o], ((it / kNO) - 1) & 1);
+            const uint32_t ob = ops_base + o * kStage1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    // column 128g + 4 lane: head = 2g + (lane>>4), m = 4 (lane & 15): chunk16 = (lane & 15) >> 1, half = lane & 1
+                    const uint32_t off = (uint32_t)((2 * g + (lane >> 4)) * kHeadTile1 + j * 1024 + warp * 128 +
+                                                    ((((lane & 15) >> 1) ^ warp) & 7) * 16 + (lane & 1) * 8);
+                    uint32_t hi[2], lo[2];
+                    split4(x[j][0][g], hi, lo);
+                    sts64(ob + 0 * kOp1 + off, hi[0], hi[1]);
+                    sts64(ob + 1 * kOp1 + off, lo[0], lo[1]);
+                    split4(x[j][1][g], hi, lo);
+                    sts64(ob + 2 * kOp1 + off, hi[0], hi[1]);
+                    sts64(ob + 3 * kOp1 + off, lo[0], lo[1]);
+                    const float4 kk = x[j][0][g], vv = x[j][1][g], qq = x[j][2][g];
+                    zacc[4 * g + 0] += kk.x; zacc[4 * g + 1] += kk.y; zacc[4 * g + 2] += kk.z; zacc[4 * g + 3] += kk.w;
+                    uacc[4 * g + 0] += vv.x; uacc[4 * g + 1] += vv.y; uacc[4 * g + 2] += vv.z; uacc[4 * g + 3] += vv.w;
+                    ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
+                    ssq = fmaf(qq.x, qq.x, ssq); ssq = fmaf(qq.y, qq.y, ssq); ssq = fmaf(qq.z, qq.z, ssq); ssq = fmaf(qq.w, qq.w, ssq);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&ofull[o]); mbar_arrive(&sempty[s]); }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            // ===== TMA issuer: three 16 KB bulk copies per stage
+            const uint32_t stg_base = smem_u32(stg);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kNSG;
+                if (it >= kNSG) mbar_wait(&sempty[s], ((it / kNSG) - 1) & 1);
+                const int64_t row = r0 + (int64_t)it * kR1;
+                const uint32_t bytes = (uint32_t)(min((int64_t)kR1, r1 - row) * kRowF * 4);
+                mbar_expect_tx(&sfull[s], 3 * bytes);
+                tma_load_1d(stg_base + s * kStg + 0 * kStgT, k + row * kRowF, bytes, &sfull[s]);
+                tma_load_1d(stg_base + s * kStg + 1 * kStgT, v + row * kRowF, bytes, &sfull[s]);
+                tma_load_1d(stg_base + s * kStg + 2 * kStgT, q + row * kRowF, bytes, &sfull[s]);
+            }
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer
+        const uint32_t idesc = make_idesc(128, 128, 1, 1);
+        const uint32_t lbo = kHeadTile1, sbo = 1024;
+        const uint32_t ops_base = smem_u32(ops);
+        for (int it = 0; it < iters; ++it) {
+            const int o = it % kNO;
+            mbar_wait(&ofull[o], (it / kNO) & 1);
+            tc_fence_after();
+            const uint32_t sb = ops_base + o * kStage1;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const uint32_t ho = p * 2 * kHeadTile1;
+                const uint64_t khi = make_desc(sb + 0 * kOp1 + ho, lbo, sbo), klo = make_desc(sb + 1 * kOp1 + ho, lbo, sbo);
+                const uint64_t vhi = make_desc(sb + 2 * kOp1 + ho, lbo, sbo), vlo = make_desc(sb + 3 * kOp1 + ho, lbo, sbo);
+                umma(tmem + p * 128, khi, vhi, idesc, it > 0 ? 1u : 0u);
+                umma(tmem + p * 128, khi, vlo, idesc, 1u);
+                umma(tmem + p * 128, klo, vhi, idesc, 1u);
+            }
+            umma_commit(&oempty[o]);
+        }
+        if (iters > 0) umma_commit(&done); else mbar_arrive(&done);
+    }
+
+    // ===== tail: per-CTA record in the partials layout [S | z | u | sq | sk], then the cross-CTA sum fused in:
+    // every CTA publishes its record (flag = epoch), waits for all flags (the grid is launched
+    // cooperatively, all CTAs are resident), TMA-loads "its" column slice of all records into shared
+    // memory and sums it in fixed order (fp64) -> partials (deterministic, no float atomics).
+    // The S / z entries are also emitted as the bf16 hi/lo, 128B-swizzled B operand image of pass 2.
+    __syncwarp();
+    if (warp == 0) DIF_STAMP(dbg, 3);
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    DIF_STAMP(dbg, 4);
+    ssk = warp_sum(ssk);
+    ssq = warp_sum(ssq);
+    if (lane == 0 && warp < 8) { part[warp] = ssk; part[8 + warp] = ssq; }
+    float* red = reinterpret_cast<float*>(ops);         // all MMAs have completed: operand memory is free
+    if (warp < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int col = (i < 4) ? 4 * lane + i : 128 + 4 * lane + (i - 4);
+            red[warp * kRowF + col] = zacc[i];
+            red[8 * kRowF + warp * kRowF + col] = uacc[i];
+        }
+    }
+    __syncthreads();
+    float* rec = ws + (int64_t)blockIdx.x * ws_len;
+    constexpr int offZ = kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim, kP = offSq + 2;
+    if (tid < kRowF) {
+        float z = 0.f, u = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { z += red[w * kRowF + tid]; u += red[8 * kRowF + w * kRowF + tid]; }
+        rec[offZ + tid] = z;
+        rec[offU + tid] = u;
+    }
+    if (tid == 0) {
+        float sk = 0.f, sq = 0.f;
+        for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
+        rec[offSq] = sq;
+        rec[offSq + 1] = sk;
+        for (int64_t i = kP; i < ws_len; ++i) rec[i] = 0.f;
+    }
+    if (warp < 8) {
+        // D_p rows 0-63 x cols 0-63 = S_{2p}, rows 64-127 x cols 64-127 = S_{2p+1}.  Warp w reads TMEM lanes
+        // 32(w%4)..+31 (its quadrant); warps 0-3 take head pair p = 0, warps 4-7 p = 1.  256-bit stores.
+        const int wq = warp & 3, p = warp >> 2;
+        const int hp = wq >> 1, m = (wq * 32 + lane) & 63;
+        float* dst = rec + ((int64_t)(2 * p + hp) * kDim + m) * kDim;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            if (iters > 0) {
+                tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + p * 128 + hp * 64 + c0, r);
+                tmem_ld_wait32(r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                             :: "l"(dst + c0 + j), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]), "r"(r[j + 4]), "r"(r[j + 5]),
+                                "r"(r[j + 6]), "r"(r[j + 7]) : "memory");
+        }
+    }
+    // ---- publish the record
+    __threadfence();
+    __syncthreads();
+    DIF_STAMP(dbg, 5);
+    const int grid = gridDim.x;
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flags + blockIdx.x), "l"(epoch) : "memory");
+    // ---- this CTA's column slice [j0, j1) of the record (multiples of 4 floats = 16 B)
+    const int chunk = (int)((((ws_len + grid - 1) / grid) + 3) & ~(int64_t)3);
+    const int64_t j0 = (int64_t)blockIdx.x * chunk;
+    const int slice = (int)max((int64_t)0, min(ws_len, j0 + chunk) - j0);
+    float* sbuf = reinterpret_cast<float*>(stg);        // [grid][chunk] fp32, the staging ring is idle now
+    if (slice > 0) {
+        for (int r = tid; r < grid; r += kThreadsT) {
+            unsigned long long f;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + r) : "memory");
+                if (f != epoch) __nanosleep(64);
+            } while (f != epoch);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");   // acquired (generic proxy) before the bulk (async proxy) reads
+        __syncthreads();
+        if (tid == 0) mbar_expect_tx(&tail_bar, (uint32_t)grid * (uint32_t)slice * 4u);
+        __syncthreads();
+        for (int r = tid; r < grid; r += kThreadsT)
+            tma_load_1d(smem_u32(sbuf) + (uint32_t)r * chunk * 4, ws + (int64_t)r * ws_len + j0, (uint32_t)slice * 4u, &tail_bar);
+        mbar_wait(&tail_bar, 0);
+        for (int t = tid; t < slice; t += kThreadsT) {
+            const int64_t j = j0 + t;
+            if (j >= kP) break;
+            double acc = 0.0;
+            for (int r = 0; r < grid; ++r) acc += (double)sbuf[r * chunk + t];
+            const float sum = (float)acc;
+            partials[j] = sum;
+            if (prepared != nullptr && j < offU) {
+                // B operand image of pass 2 (un-scaled; pass 2 applies c = 1/(|Q||K|) in its epilogue):
+                // S[h][m][d] -> row n = d, k = m of head h ; z[h][m] -> row 64
+                int h, n, m;
+                if (j < offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
+                else { h = (int)(j - offZ) >> 6; m = (int)(j - offZ) & 63; n = kDim; }
+                const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(sum - __bfloat162float(hi));
+                uint8_t* img = prepared + (size_t)h * 2 * kBOpBytes + sw128(n, m >> 3) + (m & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(img) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(img + kBOpBytes) = lo;
+            }
+        }
+    }
+    if (prepared != nullptr && blockIdx.x == grid - 1) {
+        // zero rows 65..79 of every (head, hi/lo) tile: 15 rows x 128 B, contiguous after row 64 inside the last 8-row group...
+        // rows 64..71 live in group 8 (bytes 8192..9215), rows 72..79 in group 9: zero everything except row 64
+        for (int i = tid; i < kH * 2 * 15 * 8; i += kThreadsT) {
+            const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
+            *reinterpret_cast<uint4*>(prepared + (size_t)t * kBOpBytes + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    DIF_STAMP(dbg, 6);
+    if (warp == 9) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------
 constexpr int kTile2 = 128;                           // rows per tile = UMMA M
@@ -510,6 +806,8 @@ struct ApplyTcArgs {
     int tiles_per_cta;      // > 0: CTA b owns tiles [b*tpc, (b+1)*tpc) -- the row range it reduced in pass 1 -- and walks
                             //      them backwards, so the Q rows pass 1 touched last are re-read first (L2 hits)
     int pf_tiles;           // L2 prefetch distance in tiles (0 = off)
+    uint64_t* dbg;          // optional timeline buffer
+    const uint8_t* prepared; // optional B operand image written by the fused pass-1 tail (un-scaled S|z, bf16 hi/lo, swizzled)
     int store_hint;         // 1: TMA stores carry an L2 evict_first policy (output is not re-read; keeps Q resident)
     dif_epilogue_t ep;
 };
@@ -522,7 +820,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
     uint8_t* stages = base + kBBytes;
     uint8_t* ostage = stages + kNS2 * kStage2;                       // [4 warps][2 boxes][32 rows][128 B], 1024-aligned
     float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
-    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc];
+    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], bbar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
@@ -541,17 +839,35 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         return contiguous ? first_tile + (my_tiles - 1 - i) : first_tile + (int64_t)i * gridDim.x;
     };
 
+    DIF_STAMP(p.dbg, 0);
+    if (tid == 32 && my_tiles > 0) {
+        // the B-operand prologue below takes a few us: have the first tiles of Q on their way to L2 meanwhile
+        for (int i = 0; i < 2 && i < my_tiles; ++i) {
+            const int64_t prow = tile_of(4 * i) * kTile2;
+            const int64_t nrows = min((int64_t)kTile2, p.N - prow);
+            for (int64_t r = 0; r < nrows; r += 16)
+                prefetch_l2(p.q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
+        }
+    }
     if (tid == 0) {
         for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
         for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(&bbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.prepared != nullptr) {
+            // the B operands were prepared by pass 1: one 80 KB TMA fetch instead of a transposing prologue
+            mbar_expect_tx(&bbar, (uint32_t)kBBytes);
+            for (int i = 0; i < kH * 2; ++i)
+                tma_load_1d(smem_u32(Bop) + i * kBOp, p.prepared + (size_t)i * kBOp, (uint32_t)kBOp, &bbar);
+        }
     }
     if (warp == 12) tmem_alloc(&tmem_slot, 512);
 
     // ---- B operands: row n < 64: c*S[h][:, n] ; row 64: c*z[h] ; rows 65..79: 0   (K-major SW128, hi/lo split)
     const int64_t offZ = (int64_t)kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim;
     const float c = 1.f / (sqrtf(p.partials[offSq]) * sqrtf(p.partials[offSq + 1]));
-    {
+    const float cscale = p.prepared != nullptr ? c : 1.f;   // prepared operands are un-scaled: the epilogue applies c
+    if (p.prepared == nullptr) {
         // all loads of a thread's (up to 7) tasks are issued before the first use: two L2 round trips, not 50
         constexpr int kTasks = kH * 8 * kBN, kPer = (kTasks + kThreadsTC - 1) / kThreadsTC;
         float x[kPer][8];
@@ -590,6 +906,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    DIF_STAMP(p.dbg, 1);
 
     if (warp < 8) {
         // ===== Q producers: stage = (tile, head): 128 rows x 256 B; task t -> row t>>3, chunk t&7.
@@ -679,7 +996,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
             uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q^.z^
             tmem_ld_wait1(qz_bits);
-            const float inv_den = 1.f / (__uint_as_float(qz_bits) + p.n_total);   // one division per (row, head)
+            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.n_total));   // one division per (row, head)
             if (MODE == 1 && h == 0) {
 #pragma unroll
                 for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
@@ -702,10 +1019,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                 for (int j = 0; j < 32; j += 4) {
                     const float4 u4 = *reinterpret_cast<const float4*>(us + h * kDim + c0 + j);
                     float4 o;
-                    o.x = (__uint_as_float(r[j]) + u4.x) * inv_den;
-                    o.y = (__uint_as_float(r[j + 1]) + u4.y) * inv_den;
-                    o.z = (__uint_as_float(r[j + 2]) + u4.z) * inv_den;
-                    o.w = (__uint_as_float(r[j + 3]) + u4.w) * inv_den;
+                    o.x = fmaf(__uint_as_float(r[j]), cscale, u4.x) * inv_den;
+                    o.y = fmaf(__uint_as_float(r[j + 1]), cscale, u4.y) * inv_den;
+                    o.z = fmaf(__uint_as_float(r[j + 2]), cscale, u4.z) * inv_den;
+                    o.w = fmaf(__uint_as_float(r[j + 3]), cscale, u4.w) * inv_den;
                     if (MODE == 0) {
                         sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
                                make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
@@ -755,6 +1072,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         // ===== MMA issuer: per (tile, head): 4 K-steps x (hi*hi + lo*hi + hi*lo), M=128 N=80 K=16
         const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
         const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
+        if (p.prepared != nullptr) mbar_wait(&bbar, 0);
         for (int sc = 0; sc < nsc; ++sc) {
             const int s = sc % kNS2, slot = sc % kNAcc, h = sc & 3;
             if (p.pf_tiles > 0 && h == 0 && sc + 4 * p.pf_tiles < nsc) {
@@ -782,8 +1100,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         }
     }
     __syncwarp();
+    if (warp == 0) DIF_STAMP(p.dbg, 3);
     tc_fence_before();
     __syncthreads();
+    DIF_STAMP(p.dbg, 5);
     if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
@@ -825,6 +1145,31 @@ int tc_rows_per_cta(int64_t N, int* grid) {
     return (int)rpc;
 }
 
+// DIF_TC_DEBUG_TIMES=1: per-CTA %globaltimer stamps, summarised on stderr after a device sync (debug only)
+uint64_t* dbg_buffer() {
+    static uint64_t* buf = nullptr;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DIF_TC_DEBUG_TIMES"); on = (e && atoi(e)) ? 1 : 0; }
+    if (!on) return nullptr;
+    if (!buf) cudaMalloc(&buf, 256 * 8 * sizeof(uint64_t));
+    cudaMemset(buf, 0, 256 * 8 * sizeof(uint64_t));
+    return buf;
+}
+void dbg_report(const char* name, uint64_t* buf, int grid) {
+    if (!buf) return;
+    cudaDeviceSynchronize();
+    static uint64_t h[256 * 8];
+    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+    uint64_t t0 = ~0ull;
+    for (int b = 0; b < grid; ++b) if (h[b * 8] && h[b * 8] < t0) t0 = h[b * 8];
+    fprintf(stderr, "[%s] slot: min/avg/max us since first CTA start\n", name);
+    for (int s = 0; s < 7; ++s) {
+        double mn = 1e30, mx = 0, sum = 0; int n = 0;
+        for (int b = 0; b < grid; ++b) { if (!h[b * 8 + s]) continue; double t = (h[b * 8 + s] - t0) * 1e-3; mn = t < mn ? t : mn; mx = t > mx ? t : mx; sum += t; ++n; }
+        if (n) fprintf(stderr, "  stamp %d: %7.2f %7.2f %7.2f  (n=%d)\n", s, mn, sum / n, mx, n);
+    }
+}
+
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -839,17 +1184,42 @@ bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D) {
 int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
     int grid;
     tc_rows_per_cta(N, &grid);
-    return (int64_t)grid * SimpleLayout{H, Hv, M, D}.wsLen() * (int64_t)sizeof(float);
+    // records + one 64-bit ready flag per CTA
+    return (int64_t)grid * SimpleLayout{H, Hv, M, D}.wsLen() * (int64_t)sizeof(float) + (int64_t)grid * 8 + 64;
+}
+
+int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D) {
+    return (H == kH && Hv == kH && M == kDim && D == kDim) ? (int64_t)kBBytes : 0;
 }
 
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
-                     float* partials, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                     float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0, DIF_EARG, "tcgen05 path: q/k/v must be 32-byte aligned");
     int grid;
     const int rpc = tc_rows_per_cta(N, &grid);
     const SimpleLayout L{H, Hv, M, D};
-    DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
+    DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4 + (int64_t)grid * 8, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
+    DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_reduce(tcgen05): prepared buffer must be 16-byte aligned");
+    static const int use_tma = env_int("DIF_TC_P1_TMA", 1);      // 1 = TMA-staged producer (default), 0 = register-path producer
+    if (use_tma) {
+        // cooperative launch: the fused cross-CTA sum spins on per-CTA flags, so all CTAs must be co-resident
+        // (grid <= #SMs, 1 CTA/SM); the runtime refuses the launch otherwise instead of deadlocking
+        static std::atomic<unsigned long long> epoch_src{0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&epoch_src};
+        unsigned long long epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
+        DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1T));
+        uint64_t* dbg = dbg_buffer();
+        float* wsf = (float*)ws;
+        int64_t ws_len = L.wsLen();
+        unsigned long long* flags = (unsigned long long*)(wsf + (int64_t)grid * ws_len);
+        uint8_t* prep = (uint8_t*)prepared;
+        int rpc_ = rpc;
+        void* args[] = {(void*)&q, (void*)&k, (void*)&v, (void*)&N, (void*)&rpc_, (void*)&wsf, (void*)&ws_len, (void*)&flags,
+                        (void*)&epoch, (void*)&partials, (void*)&prep, (void*)&dbg};
+        DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel, dim3(grid), dim3(kThreadsT), args, (size_t)kSmem1T, st));
+        dbg_report("reduce_tma", dbg, grid);
+        return DIF_OK;
+    }
     static const int variant = env_int("DIF_TC_P1_VARIANT", 2);   // tuning switches: 1 = register ring, 2 = K/V evict_first, 4 = Q evict_last (+ policy-hinted prefetch)
     static const int pf = env_int("DIF_TC_P1_PREFETCH", 0);       // L2 prefetch distance in 16-row stages (0 = off)
 #define DIF_P1(R, E)                                                                                                  \
@@ -868,12 +1238,14 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     return simple_finalize_fwd((const float*)ws, grid, H, Hv, M, D, partials, st);
 }
 
-int simple_apply_tc(const float* q, const float* partials, double n_total, int64_t N, int H, int Hv, int M, int D,
+int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE(((uintptr_t)q & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG, "tcgen05 path: q must be 32-byte, out 16-byte aligned");
     ApplyTcArgs a{};
     a.q = q; a.partials = partials; a.n_total = (float)n_total; a.N = N; a.out = out;
+    a.prepared = (const uint8_t*)prepared;
+    DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_apply(tcgen05): prepared buffer must be 16-byte aligned");
     if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
@@ -888,6 +1260,7 @@ int simple_apply_tc(const float* q, const float* partials, double n_total, int64
     }
     a.store_hint = (variant & 4) ? 1 : 0;
     a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 0);
+    a.dbg = dbg_buffer();
     CUtensorMap map;
     int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)kH * kDim : (int64_t)kDim);
     if (rc) return rc;
@@ -899,6 +1272,7 @@ int simple_apply_tc(const float* q, const float* partials, double n_total, int64
     if (a.ep.mode == 0) { if (variant & 1) DIF_P2(0, true); else DIF_P2(0, false); }
     else                { if (variant & 1) DIF_P2(1, true); else DIF_P2(1, false); }
 #undef DIF_P2
+    dbg_report("apply_tc", a.dbg, grid);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }

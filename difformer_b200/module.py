@@ -54,7 +54,7 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         ops._need_cuda(q, k, v)
         N = q.shape[0]
         alpha = 1.0 if residual is None else float(residual[0])
-        partials = ops.simple_partials(q, k, v)
+        partials, prepared = ops.simple_partials(q, k, v, with_prepared=True)
         addends = []
         if conv.use_graph:
             csr = ops.graph_csr(edge_index, edge_weight, N)
@@ -68,7 +68,7 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         if residual is not None:
             addends.append((ops._f32c(residual[1]), 1.0 - alpha))
         ep = ops.make_epilogue(alpha * w_attn / H, addends)
-        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=addends)
+        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=addends, prepared=prepared)
         return out, None, residual is not None
 
     # ---- unfused path (training, sigmoid, batched graphs, attention visualisation)

@@ -56,29 +56,37 @@ def _shapes(qs, ks, vs) -> Tuple[int, int, int, int, int, int]:
 # ----------------------------------------------------------------------------------------------
 # kernel='simple'
 # ----------------------------------------------------------------------------------------------
-def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor) -> torch.Tensor:
-    """Pass 1 on this rank's rows -> partials [S | z | u | sum q^2 | sum k^2] (fp32, additive)."""
+def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_prepared: bool = False):
+    """Pass 1 on this rank's rows -> partials [S | z | u | sum q^2 | sum k^2] (fp32, additive).
+
+    with_prepared=True also returns the pass-2 operand image pass 1 can emit for free on tcgen05
+    shapes (None otherwise).  The image matches exactly these partials: drop it (pass None to
+    `simple_apply`) once the partials are all-reduced or edited."""
     N, L, H, Hv, M, D = _shapes(qs, ks, vs)
     if N != L:
         raise ValueError("kernel='simple' requires N == L (difformer.py:22,29)")
     partials = torch.empty(lib.dif_simple_partials_len(H, Hv, M, D), dtype=torch.float32, device=qs.device)
     wsb = lib.dif_simple_workspace_bytes(N, H, Hv, M, D)
     ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=qs.device)
+    pb = int(lib.dif_simple_prepared_bytes(H, Hv, M, D)) if (with_prepared and _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC) else 0
+    prepared = torch.empty(pb, dtype=torch.uint8, device=qs.device) if pb > 0 else None
     with torch.cuda.device(qs.device):
-        check(lib.dif_simple_reduce(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D,
-                                    partials.data_ptr(), ws.data_ptr(), ws.numel(), _SIMPLE_IMPL, _stream(qs)),
+        check(lib.dif_simple_reduce(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D, partials.data_ptr(),
+                                    None if prepared is None else prepared.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _SIMPLE_IMPL, _stream(qs)),
               "dif_simple_reduce")
-    return partials
+    return (partials, prepared) if with_prepared else partials
 
 
 def simple_apply(qs: torch.Tensor, partials: torch.Tensor, n_total: float, Hv: int, D: int,
-                 epilogue: Optional[Epilogue] = None, keep=()) -> torch.Tensor:
+                 epilogue: Optional[Epilogue] = None, keep=(), prepared: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pass 2.  epilogue=None -> [N,H,D]; mode-1 epilogue -> [N,D] (fused layer epilogue)."""
     N, H, M = qs.shape
     fused = epilogue is not None and epilogue.mode == 1
     out = torch.empty((N, D) if fused else (N, H, D), dtype=torch.float32, device=qs.device)
     with torch.cuda.device(qs.device):
-        check(lib.dif_simple_apply(qs.data_ptr(), partials.data_ptr(), float(n_total), N, H, Hv, M, D, out.data_ptr(),
+        check(lib.dif_simple_apply(qs.data_ptr(), partials.data_ptr(), None if prepared is None else prepared.data_ptr(),
+                                   float(n_total), N, H, Hv, M, D, out.data_ptr(),
                                    ctypes.byref(epilogue) if epilogue is not None else None, _SIMPLE_IMPL, _stream(qs)),
               "dif_simple_apply")
     del keep
@@ -110,10 +118,12 @@ class _SimpleAttention(torch.autograd.Function):
         _need_cuda(qs, ks, vs)
         qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
-        partials = simple_partials(qs, ks, vs)
-        _allreduce(partials, group)
+        partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
+        if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+            prepared = None            # the operand image belongs to the un-reduced partials
         n_tot = float(N if n_total is None else n_total)
-        out = simple_apply(qs, partials, n_tot, Hv, D)
+        out = simple_apply(qs, partials, n_tot, Hv, D, prepared=prepared)
         ctx.save_for_backward(qs, ks, vs, out, partials)
         ctx.group, ctx.n_tot = group, n_tot
         return out

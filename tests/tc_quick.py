@@ -9,7 +9,7 @@ for n in (16, 100, 128, 5000, 132534):
     q, k, v = O.synthetic_qkv(n, 4, 64, seed=n, adversarial=True)
     qg, kg, vg = q.cuda(), k.cuda(), v.cuda()
     ops.set_simple_impl("tcgen05")
-    p_tc = ops.simple_partials(qg, kg, vg)
+    p_tc, prep = ops.simple_partials(qg, kg, vg, with_prepared=True)
     torch.cuda.synchronize()
     want = O.simple_partials(q.double(), k.double(), v.double())
     S = p_tc[:16384].reshape(4, 64, 64)
@@ -17,8 +17,11 @@ for n in (16, 100, 128, 5000, 132534):
           "u", O.rel_err(p_tc[16640:16896].reshape(4, 64), want["u"]), "sq", float(p_tc[16896]) / float(want["sq"]) - 1,
           "sk", float(p_tc[16897]) / float(want["sk"]) - 1, flush=True)
     o_tc = ops.simple_apply(qg, p_tc, float(n), 4, 64)
+    o_pr = ops.simple_apply(qg, p_tc, float(n), 4, 64, prepared=prep)
     torch.cuda.synchronize()
-    print(n, "out", O.rel_err(o_tc, O.simple_apply(q.double(), want)), flush=True)
+    print(n, "out", O.rel_err(o_tc, O.simple_apply(q.double(), want)), "out(prepared)", O.rel_err(o_pr, O.simple_apply(q.double(), want)),
+          "prepared vs prologue", O.rel_err(o_pr, o_tc), flush=True)
+    assert prep is not None and O.rel_err(o_pr, O.simple_apply(q.double(), want)) < 1e-4
     only_s = p_tc.clone(); only_s[16384:16896] = 0
     qS = ops.simple_apply(qg, only_s, float(n), 4, 64) * n
     _, parts = O.simple_apply(q.double(), want, return_parts=True)

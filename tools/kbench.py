@@ -31,9 +31,25 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-part = ops.simple_partials(q, k, v)
-t_red = timeit(lambda: ops.simple_partials(q, k, v), a.iters)
-t_app = timeit(lambda: ops.simple_apply(q, part, float(a.n), 4, 64), a.iters)
-t_op = timeit(lambda: ops.simple_apply(q, ops.simple_partials(q, k, v), float(a.n), 4, 64), a.iters)
+part, prep = ops.simple_partials(q, k, v, with_prepared=True)
+t_red = timeit(lambda: ops.simple_partials(q, k, v, with_prepared=True), a.iters)
+t_app = timeit(lambda: ops.simple_apply(q, part, float(a.n), 4, 64, prepared=prep), a.iters)
+
+
+def op():
+    pp, pr = ops.simple_partials(q, k, v, with_prepared=True)
+    return ops.simple_apply(q, pp, float(a.n), 4, 64, prepared=pr)
+
+
+t_op = timeit(op, a.iters)
 print(f"{a.tag} n={a.n} reduce+finalize {t_red:7.1f} us ({3*T/t_red/1e3:6.0f} GB/s)  apply {t_app:7.1f} us ({2*T/t_app/1e3:6.0f} GB/s)  "
       f"op {t_op:7.1f} us  roofline(4T) {4*T/t_op/1e3/6571.2:5.3f}", flush=True)
+
+# ---- plain-torch streaming references on the same box (what the memory system gives a trivial kernel)
+big = torch.empty(3 * a.n * 256, device="cuda").normal_()
+t_sum = timeit(lambda: big.sum(), 50)
+src, dst = torch.empty(a.n * 256, device="cuda").normal_(), torch.empty(a.n * 256, device="cuda")
+t_cp = timeit(lambda: dst.copy_(src), 50)
+g = torch.empty(1 << 28, device="cuda").normal_(); g2 = torch.empty_like(g)
+t_big = timeit(lambda: g2.copy_(g), 20)
+print(f"  torch.sum over 3T: {t_sum:6.1f} us ({3*T/t_sum/1e3:5.0f} GB/s) | copy T->T: {t_cp:6.1f} us ({2*T/t_cp/1e3:5.0f} GB/s) | copy 1GiB: {2*g.numel()*4/t_big/1e3:5.0f} GB/s", flush=True)
