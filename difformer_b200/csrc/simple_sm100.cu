@@ -750,9 +750,17 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
         for (int t = tid; t < slice; t += kThreadsT) {
             const int64_t j = j0 + t;
             if (j >= kP) break;
-            double acc = 0.0;
-            for (int r = 0; r < grid; ++r) acc += (double)sbuf[r * chunk + t];
-            const float sum = (float)acc;
+            // four independent chains (records r = 4i + k), combined in a fixed order: deterministic, 4x shorter latency
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int r = 0;
+            for (; r + 3 < grid; r += 4) {
+                a0 += (double)sbuf[(r + 0) * chunk + t];
+                a1 += (double)sbuf[(r + 1) * chunk + t];
+                a2 += (double)sbuf[(r + 2) * chunk + t];
+                a3 += (double)sbuf[(r + 3) * chunk + t];
+            }
+            for (; r < grid; ++r) a0 += (double)sbuf[r * chunk + t];
+            const float sum = (float)((a0 + a1) + (a2 + a3));
             partials[j] = sum;
             if (prepared != nullptr && j < offU) {
                 // B operand image of pass 2 (un-scaled; pass 2 applies c = 1/(|Q||K|) in its epilogue):
@@ -1250,7 +1258,7 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
     // tuning switches: 1 = register ring, 2 = contiguous reversed tile order (pass-1 partition), 4 = evict_first stores
-    static const int variant = env_int("DIF_TC_P2_VARIANT", 6);
+    static const int variant = env_int("DIF_TC_P2_VARIANT", 0);
     int grid;
     if (variant & 2) {
         a.tiles_per_cta = tc_rows_per_cta(N, &grid) / kTile2;
@@ -1259,7 +1267,7 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
         grid = tc_grid((N + kTile2 - 1) / kTile2);
     }
     a.store_hint = (variant & 4) ? 1 : 0;
-    a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 0);
+    a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 1);
     a.dbg = dbg_buffer();
     CUtensorMap map;
     int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)kH * kDim : (int64_t)kDim);
