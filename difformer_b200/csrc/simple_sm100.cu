@@ -1197,6 +1197,7 @@ int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
 }
 
 int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D) {
+    if (env_int("DIF_TC_P1_TMA", 1) == 0) return 0;      // only the TMA-staged pass 1 emits the operand image
     return (H == kH && Hv == kH && M == kDim && D == kDim) ? (int64_t)kBBytes : 0;
 }
 
