@@ -521,6 +521,10 @@ __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
 reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
                   int rows_per_cta, float* __restrict__ ws, int64_t ws_len, unsigned long long* __restrict__ flags,
                   unsigned long long epoch, float* __restrict__ partials, uint8_t* __restrict__ prepared,
-                  uint64_t* __restrict__ dbg) {
+                  int pf_tiles, int pf_grid, int l2_hints, uint64_t* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stg = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ops = stg + kNSG * kStg;
@@ -630,9 +634,15 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
                 const int64_t row = r0 + (int64_t)it * kR1;
                 const uint32_t bytes = (uint32_t)(min((int64_t)kR1, r1 - row) * kRowF * 4);
                 mbar_expect_tx(&sfull[s], 3 * bytes);
-                tma_load_1d(stg_base + s * kStg + 0 * kStgT, k + row * kRowF, bytes, &sfull[s]);
-                tma_load_1d(stg_base + s * kStg + 1 * kStgT, v + row * kRowF, bytes, &sfull[s]);
-                tma_load_1d(stg_base + s * kStg + 2 * kStgT, q + row * kRowF, bytes, &sfull[s]);
+                if (l2_hints) {     // K, V are dead after this pass; Q is read again by pass 2
+                    tma_load_1d_hint(stg_base + s * kStg + 0 * kStgT, k + row * kRowF, bytes, &sfull[s], policy_evict_first_());
+                    tma_load_1d_hint(stg_base + s * kStg + 1 * kStgT, v + row * kRowF, bytes, &sfull[s], policy_evict_first_());
+                    tma_load_1d_hint(stg_base + s * kStg + 2 * kStgT, q + row * kRowF, bytes, &sfull[s], policy_evict_last());
+                } else {
+                    tma_load_1d(stg_base + s * kStg + 0 * kStgT, k + row * kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * kStg + 1 * kStgT, v + row * kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * kStg + 2 * kStgT, q + row * kRowF, bytes, &sfull[s]);
+                }
             }
         }
     } else if (lane == 0) {
@@ -727,6 +737,19 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
     DIF_STAMP(dbg, 5);
     const int grid = gridDim.x;
     if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flags + blockIdx.x), "l"(epoch) : "memory");
+    if (tid == 64 && pf_tiles > 0 && (int)blockIdx.x < pf_grid) {
+        // HBM is idle while the grid exchanges its records: pull the first Q tiles pass 2 will read (tiles
+        // b, b + G, ... of "its" CTA b) into L2 now, so pass 2 starts from L2 hits instead of a cold ramp
+        const int64_t ntiles = (N + 127) / 128;
+        for (int i = 0; i < pf_tiles; ++i) {
+            const int64_t tile = blockIdx.x + (int64_t)i * pf_grid;
+            if (tile >= ntiles) break;
+            const int64_t prow = tile * 128;
+            const int64_t nrows = min((int64_t)128, N - prow);
+            for (int64_t r = 0; r < nrows; r += 16)
+                prefetch_l2(q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
+        }
+    }
     // ---- this CTA's column slice [j0, j1) of the record (multiples of 4 floats = 16 B)
     const int chunk = (int)((((ws_len + grid - 1) / grid) + 3) & ~(int64_t)3);
     const int64_t j0 = (int64_t)blockIdx.x * chunk;
@@ -1223,8 +1246,12 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
         unsigned long long* flags = (unsigned long long*)(wsf + (int64_t)grid * ws_len);
         uint8_t* prep = (uint8_t*)prepared;
         int rpc_ = rpc;
+        static const int tail_pf = env_int("DIF_TC_TAIL_PREFETCH", 0);
+        int pf_tiles = (env_int("DIF_TC_P2_VARIANT", 4) & 2) ? 0 : tail_pf;     // matches pass 2's interleaved tile order only
+        int pf_grid = tc_grid((N + kTile2 - 1) / kTile2);
+        int l2_hints = env_int("DIF_TC_P1_HINTS", 1);
         void* args[] = {(void*)&q, (void*)&k, (void*)&v, (void*)&N, (void*)&rpc_, (void*)&wsf, (void*)&ws_len, (void*)&flags,
-                        (void*)&epoch, (void*)&partials, (void*)&prep, (void*)&dbg};
+                        (void*)&epoch, (void*)&partials, (void*)&prep, (void*)&pf_tiles, (void*)&pf_grid, (void*)&l2_hints, (void*)&dbg};
         DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel, dim3(grid), dim3(kThreadsT), args, (size_t)kSmem1T, st));
         dbg_report("reduce_tma", dbg, grid);
         return DIF_OK;
@@ -1259,7 +1286,7 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
     // tuning switches: 1 = register ring, 2 = contiguous reversed tile order (pass-1 partition), 4 = evict_first stores
-    static const int variant = env_int("DIF_TC_P2_VARIANT", 0);
+    static const int variant = env_int("DIF_TC_P2_VARIANT", 4);
     int grid;
     if (variant & 2) {
         a.tiles_per_cta = tc_rows_per_cta(N, &grid) / kTile2;
