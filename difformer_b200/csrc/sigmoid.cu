@@ -25,6 +25,8 @@ struct SigArgs {
     int64_t N, L;
     int H, Hv, M, D;
     float *o, *rs, *dq, *dk, *dv;
+    int ksplit;        // fwd: key tiles are split over gridDim.z CTAs (small-N parallelism); > 1 => partial results
+    float *po, *prs;   // fwd partials: [ksplit][N,H,D] un-normalised sums and [ksplit][N,H] row sums
 };
 
 // tile loader: dst[r][0..W) = src[(row0+r), head, :] (zero beyond nrows)
@@ -65,7 +67,11 @@ __global__ void __launch_bounds__(kThreads) sigmoid_fwd_kernel(SigArgs p) {
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
 
     load_tile(Qs, ldm, p.q, n0, p.N, H, h, M);
-    for (int64_t l0 = 0; l0 < p.L; l0 += kT) {
+    // key range of this CTA (blockIdx.z of p.ksplit): whole 64-key tiles
+    const int64_t ltiles = (p.L + kT - 1) / kT;
+    const int64_t per = (ltiles + p.ksplit - 1) / p.ksplit;
+    const int64_t l_begin = (int64_t)blockIdx.z * per * kT, l_end = min(p.L, l_begin + per * kT);
+    for (int64_t l0 = l_begin; l0 < l_end; l0 += kT) {
         load_tile(Ks, ldm, p.k, l0, p.L, H, h, M);
         load_tile(Vs, ldd, p.v, l0, p.L, p.Hv, hv, D);
         __syncthreads();
@@ -97,7 +103,10 @@ __global__ void __launch_bounds__(kThreads) sigmoid_fwd_kernel(SigArgs p) {
         if (ski == 0) srs[4 * sri + a] = v;
     }
     __syncthreads();
-    if (tid < kT && n0 + tid < p.N) p.rs[(n0 + tid) * H + h] = srs[tid];
+    const bool partial = p.ksplit > 1;
+    float* rs_dst = partial ? p.prs + (int64_t)blockIdx.z * p.N * H : p.rs;
+    float* o_dst = partial ? p.po + (int64_t)blockIdx.z * p.N * H * D : p.o;
+    if (tid < kT && n0 + tid < p.N) rs_dst[(n0 + tid) * H + h] = srs[tid];
 #pragma unroll
     for (int t = 0; t < TPT; ++t) {
         const int tile = tid + t * kThreads;
@@ -107,12 +116,31 @@ __global__ void __launch_bounds__(kThreads) sigmoid_fwd_kernel(SigArgs p) {
             for (int a = 0; a < 4; ++a) {
                 const int64_t row = n0 + 4 * ri + a;
                 if (row >= p.N) continue;
-                const float r = srs[4 * ri + a];
-                *reinterpret_cast<float4*>(p.o + (row * H + h) * D + 4 * di) =
+                const float r = partial ? 1.f : srs[4 * ri + a];
+                *reinterpret_cast<float4*>(o_dst + (row * H + h) * D + 4 * di) =
                     make_float4(acc[t][a][0] / r, acc[t][a][1] / r, acc[t][a][2] / r, acc[t][a][3] / r);
             }
         }
     }
+}
+
+// key-split combine: out = (sum_s po[s]) / (sum_s prs[s]), fixed order => deterministic
+__global__ void sigmoid_combine_kernel(const float* __restrict__ po, const float* __restrict__ prs, int ksplit, int64_t rows, int D,
+                                       float* __restrict__ out, float* __restrict__ rowsum) {
+    const int d4 = D >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * d4) return;
+    const int64_t row = i / d4;
+    const int c = (int)(i - row * d4);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float r = 0.f;
+    for (int s = 0; s < ksplit; ++s) {
+        const float4 x = ldg4(po + ((int64_t)s * rows + row) * D + 4 * c);
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+        r += prs[(int64_t)s * rows + row];
+    }
+    *reinterpret_cast<float4*>(out + row * D + 4 * c) = make_float4(a.x / r, a.y / r, a.z / r, a.w / r);
+    if (c == 0) rowsum[row] = r;
 }
 
 // D_n = g_n . out_n  (one warp per (n,h) row)
@@ -329,15 +357,35 @@ int set_smem_(K kernel, size_t bytes) {
 
 using namespace dif;
 
+static int sigmoid_ksplit(int64_t N, int64_t L, int H) {
+    const int64_t ctas = ((N + kT - 1) / kT) * H, ltiles = (L + kT - 1) / kT;
+    int64_t s = (2 * (int64_t)sm_count() + ctas - 1) / ctas;          // aim at ~2 CTAs per SM
+    if (s > ltiles) s = ltiles;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : (int)s;
+}
+
+extern "C" int64_t dif_sigmoid_fwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D) {
+    (void)Hv; (void)M;
+    const int s = sigmoid_ksplit(N, L, H);
+    return s > 1 ? (int64_t)s * N * H * (D + 1) * (int64_t)sizeof(float) : 0;
+}
+
 extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv, int M, int D,
-                               float* out, float* rowsum, void* stream) {
+                               float* out, float* rowsum, void* workspace, int64_t workspace_bytes, void* stream) {
     int rc = sig_check(N, L, H, Hv, M, D);
     if (rc) return rc;
     DIF_REQUIRE(q && k && v && out && rowsum, DIF_EARG, "sigmoid_fwd: null pointer");
     SigArgs a{};
     a.q = q; a.k = k; a.v = v; a.N = N; a.L = L; a.H = H; a.Hv = Hv; a.M = M; a.D = D; a.o = out; a.rs = rowsum;
+    a.ksplit = sigmoid_ksplit(N, L, H);
+    if (a.ksplit > 1) {
+        DIF_REQUIRE(workspace && workspace_bytes >= (int64_t)a.ksplit * N * H * (D + 1) * 4, DIF_EARG, "sigmoid_fwd: workspace too small");
+        a.po = (float*)workspace;
+        a.prs = a.po + (int64_t)a.ksplit * N * H * D;
+    }
     const size_t smem = ((size_t)2 * kT * (M + 4) + (size_t)kT * (D + 4) + (size_t)kT * kLdp + kT) * sizeof(float);
-    dim3 grid((unsigned)((N + kT - 1) / kT), H);
+    dim3 grid((unsigned)((N + kT - 1) / kT), H, a.ksplit);
     cudaStream_t st = (cudaStream_t)stream;
     if ((kT / 4) * (D / 4) <= kThreads) {
         if ((rc = set_smem_(sigmoid_fwd_kernel<1>, smem))) return rc;
@@ -347,6 +395,11 @@ extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, i
         sigmoid_fwd_kernel<2><<<grid, kThreads, smem, st>>>(a);
     }
     DIF_LAUNCH_OK();
+    if (a.ksplit > 1) {
+        const int64_t n = N * H * (D / 4);
+        sigmoid_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.po, a.prs, a.ksplit, N * H, D, out, rowsum);
+        DIF_LAUNCH_OK();
+    }
     return DIF_OK;
 }
 

@@ -58,10 +58,10 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         addends = []
         if conv.use_graph:
             csr = ops.graph_csr(edge_index, edge_weight, N)
-            if v.shape[2] in (32, 64, 128) and v.shape[1] <= 8:
-                gmean = ops.spmm(csr, v, head_mean=True)            # mean over heads commutes with the SpMM
-            else:
-                gmean = ops.spmm(csr, v).mean(dim=1)
+            # the head mean commutes with the SpMM: gather 256 B rows of mean_h(V) (L2-resident, T/H bytes)
+            # instead of H x 256 B rows of V
+            vbar = ops.head_mean(v) if v.shape[1] > 1 else v
+            gmean = ops.spmm(csr, vbar.view(N, 1, v.shape[2])).view(N, v.shape[2])
             addends.append((gmean, alpha * w_gcn))
         if use_source:
             addends.append((ops._f32c(x_0), alpha))

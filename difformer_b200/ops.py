@@ -161,9 +161,10 @@ class _SigmoidAttention(torch.autograd.Function):
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
         out = torch.empty((N, H, D), dtype=torch.float32, device=qs.device)
         rowsum = torch.empty((N, H), dtype=torch.float32, device=qs.device)
+        ws = torch.empty(max(int(lib.dif_sigmoid_fwd_workspace_bytes(N, L, H, Hv, M, D)), 16), dtype=torch.uint8, device=qs.device)
         with torch.cuda.device(qs.device):
             check(lib.dif_sigmoid_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, L, H, Hv, M, D,
-                                      out.data_ptr(), rowsum.data_ptr(), _stream(qs)), "dif_sigmoid_fwd")
+                                      out.data_ptr(), rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream(qs)), "dif_sigmoid_fwd")
         ctx.save_for_backward(qs, ks, vs, out, rowsum)
         return out
 
@@ -277,6 +278,15 @@ def spmm(csr: GraphCSR, x: torch.Tensor, transpose: bool = False, head_mean: boo
     with torch.cuda.device(x.device):
         check(lib.dif_gcn_spmm(x.data_ptr(), rp.data_ptr(), idx.data_ptr(), val.data_ptr(), N, Hx, D,
                                1 if head_mean else 0, out.data_ptr(), _stream(x)), "dif_gcn_spmm")
+    return out
+
+
+def head_mean(x: torch.Tensor) -> torch.Tensor:
+    """mean over heads: [N,Hx,D] -> [N,D] (dif_head_mean)."""
+    N, Hx, D = x.shape
+    out = torch.empty((N, D), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.dif_head_mean(x.data_ptr(), N, Hx, D, out.data_ptr(), _stream(x)), "dif_head_mean")
     return out
 
 

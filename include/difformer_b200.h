@@ -128,9 +128,10 @@ DIF_API int64_t dif_segmented_workspace_bytes(int32_t B);
  * kernel='sigmoid'  (full_attention_conv, difformer.py:45-56): tiled, never materialises [N,L,H].
  *   out = (sigmoid(QK^T) / rowsum) V ; rowsum[N,H] is saved for the backward.
  * ------------------------------------------------------------------------------------------ */
+DIF_API int64_t dif_sigmoid_fwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D);
 DIF_API int dif_sigmoid_fwd(const float* q, const float* k, const float* v,
                     int64_t N, int64_t L, int H, int Hv, int M, int D,
-                    float* out, float* rowsum, void* stream);
+                    float* out, float* rowsum, void* workspace, int64_t workspace_bytes, void* stream);
 DIF_API int dif_sigmoid_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
                     const float* rowsum, int64_t N, int64_t L, int H, int Hv, int M, int D,
                     float* dq, float* dk, float* dv, void* workspace, int64_t workspace_bytes, void* stream);
