@@ -193,7 +193,17 @@ def run_ours(args):
     q, k, v = (t.to(dev) for t in O.synthetic_qkv(N_NODES, HEADS, DIM, seed=123 + rank))
     T = N_NODES * HEADS * DIM * 4
 
+    comm = None
+    if group is not None and args.collective == "nvlink":
+        from difformer_b200.sharded import RowShardComm
+        comm = RowShardComm(group)
+    plen = int(ops.lib.dif_simple_partials_len(HEADS, HEADS, DIM, DIM))
+
     def step():
+        if comm is not None:          # pass 1 writes into the peer-mapped slot; one-shot NVLink all-reduce kernel
+            ex = comm.exchange(plen, dev)
+            partials = ex.allreduce(ops.simple_partials(q, k, v, out=ex.next_slot()))
+            return ops.simple_apply(q, partials, n_total, HEADS, DIM)
         partials, prepared = ops.simple_partials(q, k, v, with_prepared=True)
         if group is not None:
             dist.all_reduce(partials, group=group)
@@ -251,7 +261,7 @@ def run_ours(args):
     rs = None
     if group is not None:
         from difformer_b200.sharded import RowShardedAttention
-        rs = RowShardedAttention(int(n_total), group)
+        rs = RowShardedAttention(int(n_total), group, nvlink=(args.collective == "nvlink"))
 
     def e2e_step():
         qd, kd, vd = (x.to(dev, non_blocking=True) for x in (qh, kh, vh))
@@ -321,7 +331,9 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": f"full_attention_conv('simple') N={N_NODES} H={HEADS} D={DIM} fp32 per GPU (BASELINE configs[2])",
                            "rows_per_gpu": N_NODES, "global_rows": int(n_total),
-                           "parallelism": "single GPU" if world == 1 else f"row-shard x{world}, one NCCL all-reduce of 16898 fp32 per step",
+                           "parallelism": "single GPU" if world == 1 else (
+                               f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
+                               ("one-shot NVLink kernel over peer-mapped memory (csrc/comm.cu)" if args.collective == "nvlink" else "NCCL")),
                            "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps",
                            "simple_impl": args.simple_impl or "auto"},
                 "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
@@ -329,7 +341,8 @@ def run_ours(args):
                         "h2d_bytes_per_step": 3 * T, "d2h_bytes_per_step": T, "steps": e2e_steps,
                         "api": "difformer.full_attention_conv(q, k, v, 'simple') on pinned host tensors"},
                 # tcgen05 path: reduce (cross-CTA sum fused in) + apply; generic path: reduce + finalize + apply
-                "gpu_launches": (3 if (args.simple_impl == "generic" or os.environ.get("DIF_TC_P1_TMA") == "0") else 2) * args.steps, "clocks": sampler.summary(), "parity": parity}
+                "gpu_launches": ((3 if (args.simple_impl == "generic" or os.environ.get("DIF_TC_P1_TMA") == "0") else 2)
+                                 + (1 if comm is not None else 0)) * args.steps, "clocks": sampler.summary(), "parity": parity}
         print(json.dumps(line), flush=True)
     if group is not None:
         dist.destroy_process_group()
@@ -343,6 +356,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--simple-impl", default=None, choices=[None, "auto", "generic", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="nvlink", choices=["nvlink", "nccl"], help="multi-GPU all-reduce of the partials")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,7 +56,8 @@ def _shapes(qs, ks, vs) -> Tuple[int, int, int, int, int, int]:
 # ----------------------------------------------------------------------------------------------
 # kernel='simple'
 # ----------------------------------------------------------------------------------------------
-def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_prepared: bool = False):
+def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_prepared: bool = False,
+                    out: Optional[torch.Tensor] = None):
     """Pass 1 on this rank's rows -> partials [S | z | u | sum q^2 | sum k^2] (fp32, additive).
 
     with_prepared=True also returns the pass-2 operand image pass 1 can emit for free on tcgen05
@@ -65,7 +66,13 @@ def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_p
     N, L, H, Hv, M, D = _shapes(qs, ks, vs)
     if N != L:
         raise ValueError("kernel='simple' requires N == L (difformer.py:22,29)")
-    partials = torch.empty(lib.dif_simple_partials_len(H, Hv, M, D), dtype=torch.float32, device=qs.device)
+    plen = int(lib.dif_simple_partials_len(H, Hv, M, D))
+    if out is not None:        # e.g. a slot of the peer-mapped all-reduce buffer (sharded.PartialsExchange)
+        if out.numel() != plen or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("simple_partials: `out` must be a contiguous float32 tensor of dif_simple_partials_len() elements")
+        partials = out
+    else:
+        partials = torch.empty(plen, dtype=torch.float32, device=qs.device)
     wsb = lib.dif_simple_workspace_bytes(N, H, Hv, M, D)
     ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=qs.device)
     pb = int(lib.dif_simple_prepared_bytes(H, Hv, M, D)) if (with_prepared and _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC) else 0
@@ -104,6 +111,7 @@ def make_epilogue(attn_scale: float, addends) -> Epilogue:
 
 
 def _allreduce(t: torch.Tensor, group) -> None:
+    group = getattr(group, "group", group)
     if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
@@ -118,10 +126,16 @@ class _SimpleAttention(torch.autograd.Function):
         _need_cuda(qs, ks, vs)
         qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
-        partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
-        if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
-            prepared = None            # the operand image belongs to the un-reduced partials
+        xch = getattr(group, "exchange", None)      # sharded.RowShardComm: one-shot NVLink all-reduce
+        if xch is not None:
+            ex = xch(int(lib.dif_simple_partials_len(H, Hv, M, D)), qs.device)
+            local = simple_partials(qs, ks, vs, out=ex.next_slot())
+            partials, prepared = ex.allreduce(local), None
+        else:
+            partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
+            if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+                prepared = None            # the operand image belongs to the un-reduced partials
         n_tot = float(N if n_total is None else n_total)
         out = simple_apply(qs, partials, n_tot, Hv, D, prepared=prepared)
         ctx.save_for_backward(qs, ks, vs, out, partials)
@@ -142,7 +156,14 @@ class _SimpleAttention(torch.autograd.Function):
             check(lib.dif_simple_bwd_reduce(qs.data_ptr(), g.data_ptr(), out.data_ptr(), partials.data_ptr(), ctx.n_tot,
                                             N, H, Hv, M, D, bwd.data_ptr(), ws.data_ptr(), ws.numel(), st),
                   "dif_simple_bwd_reduce")
-            _allreduce(bwd, ctx.group)
+            xch = getattr(ctx.group, "exchange", None)
+            if xch is not None:
+                ex = xch(bwd.numel(), dev)
+                slot = ex.next_slot()
+                slot.copy_(bwd)
+                bwd = ex.allreduce(slot)
+            else:
+                _allreduce(bwd, ctx.group)
             check(lib.dif_simple_bwd_apply(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
                                            partials.data_ptr(), bwd.data_ptr(), ctx.n_tot, N, H, Hv, M, D,
                                            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), st),

@@ -28,17 +28,96 @@ def allreduce_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
     return partials
 
 
+class _DevicePtr:
+    """Wraps a raw device pointer for torch.as_tensor (zero copy) via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PartialsExchange:
+    """Peer-mapped buffers + the one-shot NVLink all-reduce kernel (`dif_comm_*`, csrc/comm.cu).
+
+    Pass 1 writes its partials straight into a slot of this rank's buffer; `allreduce` launches one
+    small kernel that signals the peers, waits for their flags and sums all ranks' slots in rank
+    order over NVLink (bit-identical result on every rank).  No NCCL call, no host sync."""
+
+    def __init__(self, length: int, group, device: torch.device):
+        import ctypes
+        from ._lib import check, lib
+        self.len, self.group, self.device = int(length), group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._lib, self._check = lib, check
+        nbytes = int(lib.dif_comm_buffer_bytes(self.len))
+        with torch.cuda.device(device):
+            base = ctypes.c_void_p()
+            check(lib.dif_comm_alloc(ctypes.byref(base), nbytes), "dif_comm_alloc")
+            self.base = base.value
+            handle = ctypes.create_string_buffer(64)
+            check(lib.dif_comm_export(self.base, handle), "dif_comm_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(self.base)
+                else:
+                    pp = ctypes.c_void_p()
+                    check(lib.dif_comm_open(ctypes.create_string_buffer(h, 64), ctypes.byref(pp)), "dif_comm_open")
+                    ptrs.append(pp.value)
+        self.ptrs = ptrs
+        self.c_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.seq = 0
+        self._slots = [torch.as_tensor(_DevicePtr(self.base + int(lib.dif_comm_slot_offset_bytes(self.len, s)), self.len), device=device)
+                       for s in (0, 1)]
+        dist.barrier(group=group)
+
+    def next_slot(self) -> torch.Tensor:
+        """The data slot of the next call (fp32 [len], lives in the peer-mapped buffer)."""
+        self.seq += 1
+        return self._slots[self.seq & 1]
+
+    def allreduce(self, slot: torch.Tensor) -> torch.Tensor:
+        assert slot.data_ptr() == self._slots[self.seq & 1].data_ptr(), "allreduce must follow next_slot()"
+        out = torch.empty(self.len, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.dif_comm_allreduce(self.c_ptrs, self.rank, self.world, self.len, self.seq, out.data_ptr(),
+                                                     torch.cuda.current_stream(self.device).cuda_stream), "dif_comm_allreduce")
+        return out
+
+
+class RowShardComm:
+    """Process group + lazily created peer-mapped exchanges (one per payload length).  Pass it as
+    `group=` to `full_attention_conv(..., 'simple')`: the partials are then all-reduced by the
+    one-shot NVLink kernel instead of NCCL."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self._ex = {}
+
+    def exchange(self, length: int, device) -> PartialsExchange:
+        key = (int(length), str(device))
+        if key not in self._ex:
+            self._ex[key] = PartialsExchange(length, self.group, torch.device(device))
+        return self._ex[key]
+
+
 class RowShardedAttention:
     """full_attention_conv(kernel='simple') on this rank's rows of a row-sharded graph."""
 
-    def __init__(self, n_total: int, group=None):
-        self.n_total, self.group = int(n_total), group
+    def __init__(self, n_total: int, group=None, nvlink: bool = False):
+        """nvlink=True: all-reduce through peer-mapped memory (one-shot kernel) instead of NCCL."""
+        self.n_total = int(n_total)
+        self.group = RowShardComm(group) if (nvlink and dist.is_initialized() and dist.get_world_size(group) > 1) else group
 
     def __call__(self, qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor) -> torch.Tensor:
         return ops.full_attention_conv(qs, ks, vs, "simple", group=self.group, n_total=self.n_total)
 
     # the two passes separately (bench / overlap experiments)
     def reduce(self, qs, ks, vs) -> torch.Tensor:
+        if isinstance(self.group, RowShardComm):
+            ex = self.group.exchange(ops.lib.dif_simple_partials_len(qs.shape[1], vs.shape[1], qs.shape[2], vs.shape[2]), qs.device)
+            return ex.allreduce(ops.simple_partials(qs, ks, vs, out=ex.next_slot()))
         return allreduce_partials(ops.simple_partials(qs, ks, vs), self.group)
 
     def apply(self, qs, partials, hv: int, d: int) -> torch.Tensor:

@@ -156,6 +156,27 @@ DIF_API int dif_csr_build(const int64_t* edge_index, const float* edge_weight, i
 DIF_API int dif_gcn_spmm(const float* x, const int32_t* rowptr, const int32_t* idx, const float* val,
                  int64_t N, int Hx, int D, int head_mean, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One-shot NVLink all-reduce of the pass-1 partials (the path's only collective).
+ * Every rank owns a peer-mappable buffer of dif_comm_buffer_bytes(len): [2 data slots | flags].
+ *   dif_comm_alloc / _free      : the one place the library allocates (cudaMalloc: IPC-exportable), zero-filled
+ *   dif_comm_export / _open     : cudaIpc handle (64 bytes) out / peer pointer in (same node, NVLink peers)
+ *   dif_comm_allreduce          : call number `seq` (1,2,3,... identical on all ranks): pass 1 must have written
+ *                                 this rank's partials at offset dif_comm_slot_offset_bytes(len, seq) of its own
+ *                                 buffer; `out` (local) receives the sum over ranks, summed in rank order
+ *                                 (bit-identical on every rank).  bufs[r] = pointer to rank r's buffer as mapped
+ *                                 in this process (HOST array of `world` device pointers, world <= 16).
+ * ------------------------------------------------------------------------------------------ */
+DIF_API int64_t dif_comm_buffer_bytes(int64_t len);
+DIF_API int64_t dif_comm_slot_offset_bytes(int64_t len, unsigned long long seq);
+DIF_API int dif_comm_alloc(void** ptr, int64_t bytes);
+DIF_API int dif_comm_free(void* ptr);
+DIF_API int dif_comm_export(void* ptr, void* handle64);
+DIF_API int dif_comm_open(const void* handle64, void** peer_ptr);
+DIF_API int dif_comm_close(void* peer_ptr);
+DIF_API int dif_comm_allreduce(void* const* bufs, int rank, int world, int64_t len, unsigned long long seq,
+                               float* out, void* stream);
+
 /* mean over heads: x[N,Hx,D] -> out[N,D] */
 DIF_API int dif_head_mean(const float* x, int64_t N, int Hx, int D, float* out, void* stream);
 

@@ -22,14 +22,20 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 n, h, d = 20011, 4, 64
 q, k, v = O.synthetic_qkv(n, h, d, seed=11, adversarial=True)
 b, e = shard_rows(n, rank, world)
-qs, ks, vs = (t[b:e].cuda().requires_grad_(True) for t in (q, k, v))
-out = RowShardedAttention(n, dist.group.WORLD)(qs, ks, vs)
-g = torch.randn(n, h, d, generator=torch.Generator().manual_seed(5))
-out.backward(g[b:e].cuda())
 want = O.simple_attention(q.double(), k.double(), v.double())
+g = torch.randn(n, h, d, generator=torch.Generator().manual_seed(5))
 dq, dk, dv = O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())
-errs = [O.rel_err(out, want[b:e]), O.rel_err(qs.grad, dq[b:e]), O.rel_err(ks.grad, dk[b:e]), O.rel_err(vs.grad, dv[b:e])]
-assert max(errs) < 1e-3, errs
+outs = {}
+for nvlink in (False, True):          # NCCL all-reduce, then the one-shot NVLink kernel over peer-mapped memory
+    attn = RowShardedAttention(n, dist.group.WORLD, nvlink=nvlink)
+    for rep in range(3):              # several calls: exercises the alternating slots / sequence numbers
+        qs, ks, vs = (t[b:e].cuda().requires_grad_(True) for t in (q, k, v))
+        out = attn(qs, ks, vs)
+        out.backward(g[b:e].cuda())
+        errs = [O.rel_err(out, want[b:e]), O.rel_err(qs.grad, dq[b:e]), O.rel_err(ks.grad, dk[b:e]), O.rel_err(vs.grad, dv[b:e])]
+        assert max(errs) < 1e-3, (nvlink, rep, errs)
+    outs[nvlink] = out.detach()
+assert O.rel_err(outs[True], outs[False]) < 1e-5
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok", errs)
