@@ -200,8 +200,11 @@ def run_ours(args):
     plen = int(ops.lib.dif_simple_partials_len(HEADS, HEADS, DIM, DIM))
 
     def step():
-        if comm is not None:          # pass 1 writes into the peer-mapped slot; one-shot NVLink all-reduce kernel
+        if comm is not None:          # pass 1 + all-reduce over peer-mapped NVLink memory in ONE kernel
             ex = comm.exchange(plen, dev)
+            fused = ex.fused_reduce(q, k, v)
+            if fused is not None:
+                return ops.simple_apply(q, fused[0], n_total, HEADS, DIM, prepared=fused[1])
             partials = ex.allreduce(ops.simple_partials(q, k, v, out=ex.next_slot()))
             return ops.simple_apply(q, partials, n_total, HEADS, DIM)
         partials, prepared = ops.simple_partials(q, k, v, with_prepared=True)
@@ -333,7 +336,7 @@ def run_ours(args):
                            "rows_per_gpu": N_NODES, "global_rows": int(n_total),
                            "parallelism": "single GPU" if world == 1 else (
                                f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
-                               ("one-shot NVLink kernel over peer-mapped memory (csrc/comm.cu)" if args.collective == "nvlink" else "NCCL")),
+                               ("fused into the pass-1 kernel tail over peer-mapped NVLink memory (no NCCL call)" if args.collective == "nvlink" else "NCCL")),
                            "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps",
                            "simple_impl": args.simple_impl or "auto"},
                 "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
@@ -342,7 +345,7 @@ def run_ours(args):
                         "api": "difformer.full_attention_conv(q, k, v, 'simple') on pinned host tensors"},
                 # tcgen05 path: reduce (cross-CTA sum fused in) + apply; generic path: reduce + finalize + apply
                 "gpu_launches": ((3 if (args.simple_impl == "generic" or os.environ.get("DIF_TC_P1_TMA") == "0") else 2)
-                                 + (1 if comm is not None else 0)) * args.steps, "clocks": sampler.summary(), "parity": parity}
+) * args.steps, "clocks": sampler.summary(), "parity": parity}
         print(json.dumps(line), flush=True)
     if group is not None:
         dist.destroy_process_group()

@@ -46,6 +46,8 @@ SIGNATURES = {
     "dif_csr_build": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_vp] * 7 + [c_vp, c_i64, c_vp]),
     "dif_gcn_spmm": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dif_head_mean": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "dif_simple_reduce_allreduce": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
+                                            ctypes.POINTER(c_vp), c_i32, c_i32, ctypes.c_uint64, c_vp]),
     "dif_comm_buffer_bytes": (c_i64, [c_i64]),
     "dif_comm_slot_offset_bytes": (c_i64, [c_i64, ctypes.c_uint64]),
     "dif_comm_alloc": (c_i32, [ctypes.POINTER(c_vp), c_i64]),

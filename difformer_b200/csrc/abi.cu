@@ -72,6 +72,18 @@ extern "C" int dif_simple_reduce(const float* q, const float* k, const float* v,
               : simple_reduce_generic(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// pass 1 + the cross-GPU all-reduce of the partials in ONE kernel (tcgen05 shapes only): the tail of the
+// reduce kernel exchanges its column slices with the peers over NVLink (peer-mapped dif_comm_* buffers).
+extern "C" int dif_simple_reduce_allreduce(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
+                                           float* partials, void* prepared, void* workspace, int64_t workspace_bytes,
+                                           void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream) {
+    DIF_REQUIRE(q && k && v && partials && workspace && peer_bufs, DIF_EARG, "simple_reduce_allreduce: null pointer");
+    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED,
+                "simple_reduce_allreduce: fused exchange needs the tcgen05 shapes (M == D == 64, Hv == H == 4); all-reduce separately otherwise");
+    return simple_reduce_tc(q, k, v, N, H, Hv, M, D, partials, prepared, workspace, workspace_bytes, (cudaStream_t)stream,
+                            peer_bufs, rank, world, seq);
+}
+
 extern "C" int dif_simple_apply(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                                 float* out, const dif_epilogue_t* epilogue, int impl, void* stream) {
     DIF_REQUIRE(q && partials && out, DIF_EARG, "simple_apply: null pointer");

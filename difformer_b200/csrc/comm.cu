@@ -26,8 +26,10 @@ struct CommArgs {
     float* out;
 };
 
+// flags: [2 slots][kMaxRanks][256 slices] u64 after the two data slots.  The fused pass-1 tail
+// (simple_sm100.cu) uses one flag per (slot, rank, column slice); this stand-alone kernel uses slice 255.
 __device__ __forceinline__ unsigned long long* flag_ptr(float* base, int64_t slot_floats, int idx) {
-    return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + idx;
+    return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + (size_t)idx * 256 + 255;
 }
 
 __global__ void __launch_bounds__(256) allreduce_kernel(CommArgs a) {
@@ -78,7 +80,7 @@ using namespace dif;
 
 extern "C" int64_t dif_comm_buffer_bytes(int64_t len) {
     const int64_t slot = (len + 63) & ~(int64_t)63;
-    return 2 * slot * (int64_t)sizeof(float) + 2 * kMaxRanks * (int64_t)sizeof(unsigned long long);
+    return 2 * slot * (int64_t)sizeof(float) + 2 * kMaxRanks * 256 * (int64_t)sizeof(unsigned long long);
 }
 
 extern "C" int64_t dif_comm_slot_offset_bytes(int64_t len, unsigned long long seq) {

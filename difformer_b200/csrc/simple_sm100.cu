@@ -507,6 +507,13 @@ reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const
 // swizzled UMMA operand ring.
 // ------------------------------------------------------------------------------------------
 constexpr int kBOpBytes = 80 * 128;                   // one (head, hi|lo) B-operand tile of pass 2: 80 rows x 128 B
+constexpr int kShardMaxRanks = 16;
+struct ShardArgs {            // multi-GPU: peer-mapped exchange buffers [2 data slots | flags], see csrc/comm.cu
+    float* bufs[kShardMaxRanks];
+    int rank, world;
+    unsigned long long seq;
+    int64_t slot_floats;
+};
 constexpr int kNSG = 3;                               // staging stages
 constexpr int kStgT = kR1 * 1024;                     // 16 KB: 16 rows of one tensor
 constexpr int kStg = 3 * kStgT;                       // K | V | Q
@@ -545,7 +552,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
 reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
                   int rows_per_cta, float* __restrict__ ws, int64_t ws_len, unsigned long long* __restrict__ flags,
                   unsigned long long epoch, float* __restrict__ partials, uint8_t* __restrict__ prepared,
-                  int pf_tiles, int pf_grid, int l2_hints, uint64_t* __restrict__ dbg) {
+                  int pf_tiles, int pf_grid, int l2_hints, const ShardArgs sh, uint64_t* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stg = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ops = stg + kNSG * kStg;
@@ -750,29 +757,43 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
                 prefetch_l2(q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
         }
     }
-    // ---- this CTA's column slice [j0, j1) of the record (multiples of 4 floats = 16 B)
-    const int chunk = (int)((((ws_len + grid - 1) / grid) + 3) & ~(int64_t)3);
-    const int64_t j0 = (int64_t)blockIdx.x * chunk;
-    const int slice = (int)max((int64_t)0, min(ws_len, j0 + chunk) - j0);
+    // ---- column slices of the record: kSlices fixed slices of `chunk` floats (multiples of 16 B), slice sl is
+    //      owned by CTA sl % grid -- the partition does not depend on this rank's grid, so slices line up across ranks
+    constexpr int kSlices = 148;
+    const int chunk = (int)((((ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
     float* sbuf = reinterpret_cast<float*>(stg);        // [grid][chunk] fp32, the staging ring is idle now
-    if (slice > 0) {
-        for (int r = tid; r < grid; r += kThreadsT) {
-            unsigned long long f;
-            do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + r) : "memory");
-                if (f != epoch) __nanosleep(64);
-            } while (f != epoch);
+    const bool sharded = sh.world > 1;
+    const int xslot = (int)(sh.seq & 1);
+    bool waited = false;
+    uint32_t tail_phase = 0;
+    for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
+        const int64_t j0 = (int64_t)sl * chunk;
+        const int slice = (int)max((int64_t)0, min(ws_len, j0 + chunk) - j0);
+        if (slice <= 0) break;
+        if (!waited) {
+            for (int r = tid; r < grid; r += kThreadsT) {
+                unsigned long long f;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + r) : "memory");
+                    if (f != epoch) __nanosleep(64);
+                } while (f != epoch);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");   // acquired (generic proxy) before the bulk (async proxy) reads
+            waited = true;
         }
-        asm volatile("fence.proxy.async;" ::: "memory");   // acquired (generic proxy) before the bulk (async proxy) reads
-        __syncthreads();
+        __syncthreads();                                  // also: previous slice's readers of sbuf are done
         if (tid == 0) mbar_expect_tx(&tail_bar, (uint32_t)grid * (uint32_t)slice * 4u);
         __syncthreads();
         for (int r = tid; r < grid; r += kThreadsT)
             tma_load_1d(smem_u32(sbuf) + (uint32_t)r * chunk * 4, ws + (int64_t)r * ws_len + j0, (uint32_t)slice * 4u, &tail_bar);
-        mbar_wait(&tail_bar, 0);
-        for (int t = tid; t < slice; t += kThreadsT) {
-            const int64_t j = j0 + t;
-            if (j >= kP) break;
+        mbar_wait(&tail_bar, tail_phase);
+        tail_phase ^= 1;
+        // local sum of this slice over the grid's records
+        float local = 0.f;
+        const int t = tid;                                // chunk <= kThreadsT is asserted on the host
+        const int64_t j = j0 + t;
+        const bool live = t < slice && j < kP;
+        if (live) {
             // four independent chains (records r = 4i + k), combined in a fixed order: deterministic, 4x shorter latency
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int r = 0;
@@ -783,7 +804,39 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
                 a3 += (double)sbuf[(r + 3) * chunk + t];
             }
             for (; r < grid; ++r) a0 += (double)sbuf[r * chunk + t];
-            const float sum = (float)((a0 + a1) + (a2 + a3));
+            local = (float)((a0 + a1) + (a2 + a3));
+        }
+        float sum = local;
+        if (sharded) {
+            // ---- cross-GPU: the same kernel finishes the all-reduce over NVLink, slice by slice.  Publish the local
+            // slice in this rank's peer-mapped buffer, raise flag (slot, rank, slice) in every peer, wait for the
+            // peers' flags, add the ranks' slices in rank order (bit-identical on all ranks).
+            float* mine = sh.bufs[sh.rank] + (int64_t)xslot * sh.slot_floats;
+            if (live) mine[j] = local;
+            __threadfence_system();
+            __syncthreads();
+            if (tid < sh.world) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(sh.bufs[tid] + 2 * sh.slot_floats) +
+                                        ((size_t)(xslot * kShardMaxRanks + sh.rank) * 256 + sl);
+                asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(sh.seq) : "memory");
+                const unsigned long long* w = reinterpret_cast<const unsigned long long*>(sh.bufs[sh.rank] + 2 * sh.slot_floats) +
+                                              ((size_t)(xslot * kShardMaxRanks + tid) * 256 + sl);
+                unsigned long long got;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(w) : "memory");
+                } while (got != sh.seq);
+            }
+            __syncthreads();
+            if (live) {
+                sum = 0.f;
+                for (int r = 0; r < sh.world; ++r) {
+                    float x;
+                    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(sh.bufs[r] + (int64_t)xslot * sh.slot_floats + j) : "memory");
+                    sum += x;
+                }
+            }
+        }
+        if (live) {
             partials[j] = sum;
             if (prepared != nullptr && j < offU) {
                 // B operand image of pass 2 (un-scaled; pass 2 applies c = 1/(|Q||K|) in its epilogue):
@@ -1225,7 +1278,8 @@ int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D) {
 }
 
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
-                     float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                     float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st,
+                     void* const* peer_bufs, int rank, int world, unsigned long long seq) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0, DIF_EARG, "tcgen05 path: q/k/v must be 32-byte aligned");
     int grid;
@@ -1250,12 +1304,22 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
         int pf_tiles = (env_int("DIF_TC_P2_VARIANT", 4) & 2) ? 0 : tail_pf;     // matches pass 2's interleaved tile order only
         int pf_grid = tc_grid((N + kTile2 - 1) / kTile2);
         int l2_hints = env_int("DIF_TC_P1_HINTS", 1);
+        ShardArgs sh{};
+        sh.world = 1;
+        if (peer_bufs != nullptr && world > 1) {
+            DIF_REQUIRE(world <= kShardMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_reduce(sharded): bad rank/world/seq");
+            for (int r = 0; r < world; ++r) { DIF_REQUIRE(peer_bufs[r], DIF_EARG, "simple_reduce(sharded): null peer buffer"); sh.bufs[r] = (float*)peer_bufs[r]; }
+            sh.rank = rank; sh.world = world; sh.seq = seq;
+            sh.slot_floats = (SimpleLayout{H, Hv, M, D}.len() + 63) & ~(int64_t)63;
+        }
+        static_assert(116 <= kThreadsT, "one thread per slice element");
         void* args[] = {(void*)&q, (void*)&k, (void*)&v, (void*)&N, (void*)&rpc_, (void*)&wsf, (void*)&ws_len, (void*)&flags,
-                        (void*)&epoch, (void*)&partials, (void*)&prep, (void*)&pf_tiles, (void*)&pf_grid, (void*)&l2_hints, (void*)&dbg};
+                        (void*)&epoch, (void*)&partials, (void*)&prep, (void*)&pf_tiles, (void*)&pf_grid, (void*)&l2_hints, (void*)&sh, (void*)&dbg};
         DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel, dim3(grid), dim3(kThreadsT), args, (size_t)kSmem1T, st));
         dbg_report("reduce_tma", dbg, grid);
         return DIF_OK;
     }
+    DIF_REQUIRE(peer_bufs == nullptr || world <= 1, DIF_EUNSUPPORTED, "simple_reduce(sharded) needs the TMA-staged pass 1 (DIF_TC_P1_TMA=1)");
     static const int variant = env_int("DIF_TC_P1_VARIANT", 2);   // tuning switches: 1 = register ring, 2 = K/V evict_first, 4 = Q evict_last (+ policy-hinted prefetch)
     static const int pf = env_int("DIF_TC_P1_PREFETCH", 0);       // L2 prefetch distance in 16-row stages (0 = off)
 #define DIF_P1(R, E)                                                                                                  \

@@ -129,8 +129,12 @@ class _SimpleAttention(torch.autograd.Function):
         xch = getattr(group, "exchange", None)      # sharded.RowShardComm: one-shot NVLink all-reduce
         if xch is not None:
             ex = xch(int(lib.dif_simple_partials_len(H, Hv, M, D)), qs.device)
-            local = simple_partials(qs, ks, vs, out=ex.next_slot())
-            partials, prepared = ex.allreduce(local), None
+            fused = ex.fused_reduce(qs, ks, vs)       # pass 1 + NVLink all-reduce in one kernel (tcgen05 shapes)
+            if fused is not None:
+                partials, prepared = fused
+            else:
+                local = simple_partials(qs, ks, vs, out=ex.next_slot())
+                partials, prepared = ex.allreduce(local), None
         else:
             partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
             if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -72,6 +72,25 @@ class PartialsExchange:
                        for s in (0, 1)]
         dist.barrier(group=group)
 
+    def fused_reduce(self, qs, ks, vs):
+        """Pass 1 + all-reduce in one kernel (dif_simple_reduce_allreduce).  Returns (partials, prepared) summed
+        over all ranks, or None when the shape is not a tcgen05 shape (caller falls back to next_slot/allreduce)."""
+        from . import ops
+        N, L, H, Hv, M, D = ops._shapes(qs, ks, vs)
+        lib = self._lib
+        if ops._SIMPLE_IMPL == ops._lib.DIF_IMPL_GENERIC or int(lib.dif_simple_prepared_bytes(H, Hv, M, D)) == 0:
+            return None
+        partials = torch.empty(self.len, dtype=torch.float32, device=self.device)
+        prepared = torch.empty(int(lib.dif_simple_prepared_bytes(H, Hv, M, D)), dtype=torch.uint8, device=self.device)
+        ws = torch.empty(max(int(lib.dif_simple_workspace_bytes(N, H, Hv, M, D)), 16), dtype=torch.uint8, device=self.device)
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            self._check(lib.dif_simple_reduce_allreduce(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D, partials.data_ptr(),
+                                                        prepared.data_ptr(), ws.data_ptr(), ws.numel(), self.c_ptrs, self.rank, self.world,
+                                                        self.seq, torch.cuda.current_stream(self.device).cuda_stream),
+                        "dif_simple_reduce_allreduce")
+        return partials, prepared
+
     def next_slot(self) -> torch.Tensor:
         """The data slot of the next call (fp32 [len], lives in the peer-mapped buffer)."""
         self.seq += 1
@@ -116,6 +135,9 @@ class RowShardedAttention:
     # the two passes separately (bench / overlap experiments)
     def reduce(self, qs, ks, vs) -> torch.Tensor:
         if isinstance(self.group, RowShardComm):
+            fused = self.group.exchange(ops.lib.dif_simple_partials_len(qs.shape[1], vs.shape[1], qs.shape[2], vs.shape[2]), qs.device).fused_reduce(qs, ks, vs)
+            if fused is not None:
+                return fused[0]
             ex = self.group.exchange(ops.lib.dif_simple_partials_len(qs.shape[1], vs.shape[1], qs.shape[2], vs.shape[2]), qs.device)
             return ex.allreduce(ops.simple_partials(qs, ks, vs, out=ex.next_slot()))
         return allreduce_partials(ops.simple_partials(qs, ks, vs), self.group)

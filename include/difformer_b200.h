@@ -167,6 +167,15 @@ DIF_API int dif_gcn_spmm(const float* x, const int32_t* rowptr, const int32_t* i
  *                                 (bit-identical on every rank).  bufs[r] = pointer to rank r's buffer as mapped
  *                                 in this process (HOST array of `world` device pointers, world <= 16).
  * ------------------------------------------------------------------------------------------ */
+/* Pass 1 with the all-reduce fused into its tail (one kernel: compute + collective over peer memory): every
+ * CTA exchanges "its" column slice of the partials with the peers (flags + direct NVLink loads) right after
+ * the local cross-CTA sum.  Result: `partials` (and `prepared`) already hold the sum over all ranks.
+ * tcgen05 shapes only (DIF_EUNSUPPORTED otherwise: use dif_simple_reduce + dif_comm_allreduce).  `seq` as in
+ * dif_comm_allreduce; the two entry points may share buffers as long as seq keeps increasing. */
+DIF_API int dif_simple_reduce_allreduce(const float* q, const float* k, const float* v,
+                      int64_t N, int H, int Hv, int M, int D,
+                      float* partials, void* prepared, void* workspace, int64_t workspace_bytes,
+                      void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream);
 DIF_API int64_t dif_comm_buffer_bytes(int64_t len);
 DIF_API int64_t dif_comm_slot_offset_bytes(int64_t len, unsigned long long seq);
 DIF_API int dif_comm_alloc(void** ptr, int64_t bytes);
