@@ -1,4 +1,4 @@
-// kernel='simple' -- tcgen05 / TMEM path for sm_100a (H = 4, M = D = 64, fp32 in / fp32 out).
+// kernel='simple' -- tcgen05 / TMEM / TMA path for sm_100a (H in {1, 2, 4}, M = D = 64, fp32 in / fp32 out).
 //
 // Reference path replaced: full_attention_conv(..., 'simple'), node classification/difformer.py:18-39.
 //
@@ -16,11 +16,14 @@
 // producers -> MMA -> epilogue.  The tensor pipe needs ~20% of the HBM time, so the kernels are
 // HBM-bound by design (roofline: 4*H*D*4 B per node).
 //
-// Warp roles (13 warps, 1 CTA per SM, persistent over contiguous row ranges / 128-row tiles):
-//   pass 1: warps 0-7 K/V producers (+ sum k, sum v, sum k^2), warps 8-11 stream Q for sum q^2,
-//           warp 12 MMA issuer; epilogue: warps 0-3 TMEM -> per-CTA record (deterministic 2-stage reduce)
-//   pass 2: warps 0-7 Q producers, warps 8-11 epilogue (TMEM -> registers -> (acc+u)/den -> HBM,
-//           optionally the fused layer epilogue), warp 12 MMA issuer.
+// Pass 1 (reduce_tma_kernel<H>, 10 warps, cooperative launch, 1 CTA/SM, contiguous row range per CTA):
+//   warp 8   TMA issuer: cp.async.bulk of the stage's K | V | Q rows into an fp32 staging ring (3 stages)
+//   warps 0-7 converters: LDS.128 -> bf16 hi/lo split -> swizzled MN-major UMMA operand ring (+ sum k, sum v, sum k^2, sum q^2)
+//   warp 9   MMA issuer (one thread): M = N = 128 (two 64-wide blocks: two heads, or two node halves when H = 1), K = 16
+//   tail     TMEM -> per-CTA record, flag publish, fused deterministic cross-CTA (and cross-GPU) slice sum, pass-2 operand image
+// Pass 2 (apply_tc_kernel<MODE,H>, 13 warps, persistent over 128-row tiles):
+//   warps 0-7 Q producers (LDG.256 -> bf16 hi/lo -> K-major SW128), warps 8-11 epilogue (tcgen05.ld -> (c acc + u)/(c qz + N)
+//   -> swizzled staging -> TMA tensor store; mode 1 = fused layer epilogue), warp 12 MMA issuer.
 #include <cuda.h>        // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -35,9 +38,7 @@ int simple_finalize_fwd(const float* ws, int nchunks, int H, int Hv, int M, int 
 
 namespace {
 
-constexpr int kH = 4;
 constexpr int kDim = 64;
-constexpr int kRowF = kH * kDim;      // floats per node row (256)
 constexpr int kWarps = 13;
 constexpr int kThreadsTC = kWarps * 32;
 
@@ -45,10 +46,7 @@ constexpr int kThreadsTC = kWarps * 32;
 constexpr uint32_t kSwizzle128 = 2;
 // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused
 constexpr uint32_t kKmajLBO = 0, kKmajSBO = 1024;
-// MN-major SW128: 64-element (128 B) MN blocks are LBO apart, 8-k groups SBO apart
-#ifndef DIF_MN_LBO_IS_MNSTRIDE
-#define DIF_MN_LBO_IS_MNSTRIDE 1
-#endif
+// MN-major SW128: 64-element (128 B) MN blocks are LBO apart, 8-k groups SBO (= 1024 B) apart
 
 // ---- optional in-kernel timeline (DIF_TC_DEBUG_TIMES=1): thread 0 of every CTA stamps %globaltimer
 __device__ __forceinline__ uint64_t gtime() {
@@ -220,293 +218,37 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((c ^ r) & 7) << 4));
 }
 
-// ------------------------------------------------------------------------------------------
-// pass 1
-// ------------------------------------------------------------------------------------------
-constexpr int kR1 = 16;                               // nodes per stage = one UMMA K step
-constexpr int kHeadTile1 = kR1 * 128;                 // 2048 B: [16 nodes][64 bf16] of one head
-constexpr int kOp1 = kH * kHeadTile1;                 // 8192 B per operand (Khi / Klo / Vhi / Vlo)
-constexpr int kStage1 = 4 * kOp1;                     // 32 KB
-constexpr int kNS1 = 4;
-constexpr int kSmem1 = kNS1 * kStage1 + 1024;
-
-template <bool RING, bool EVICT_FIRST>
-__global__ void __launch_bounds__(kThreadsTC, 1)
-reduce_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
-                 int rows_per_cta, float* __restrict__ ws, int64_t ws_len, int pf_dist, int q_keep) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full[kNS1], empty[kNS1], done;
-    __shared__ uint32_t tmem_slot;
-    __shared__ float part[16];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r1 = min(N, r0 + (int64_t)rows_per_cta);
-    const int iters = r1 > r0 ? (int)((r1 - r0 + kR1 - 1) / kR1) : 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < kNS1; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
-        mbar_init(&done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 12) tmem_alloc(&tmem_slot, 256);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-
-    float zacc[8], uacc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { zacc[i] = 0.f; uacc[i] = 0.f; }
-    float ss = 0.f;     // producers: sum k^2 ; Q warps: sum q^2
-
-    if (warp < 8) {
-        if (!RING) {
-            // variant A: whole-iteration double buffer (loads of it+1 issued, then it converted)
-            float kc[2][8], vc[2][8], kn[2][8], vn[2][8];
-            auto load = [&](int it, float (&kk)[2][8], float (&vv)[2][8]) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * j;
-                    if (row < r1) {
-                        if (EVICT_FIRST) { ldg256_stream(k + row * kRowF + lane * 8, kk[j]); ldg256_stream(v + row * kRowF + lane * 8, vv[j]); }
-                        else { ldg256_keep(k + row * kRowF + lane * 8, kk[j]); ldg256_keep(v + row * kRowF + lane * 8, vv[j]); }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { kk[j][i] = 0.f; vv[j][i] = 0.f; }
-                    }
-                }
-            };
-            if (iters > 0) load(0, kc, vc);
-            const uint32_t stage_base = smem_u32(stages);
-            for (int it = 0; it < iters; ++it) {
-                if (it + 1 < iters) load(it + 1, kn, vn);
-                const int s = it % kNS1;
-                if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
-                const uint32_t sb = stage_base + s * kStage1;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + j * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
-                    uint4 hi, lo;
-                    split8(kc[j], hi, lo);
-                    sts128(sb + 0 * kOp1 + off, hi);
-                    sts128(sb + 1 * kOp1 + off, lo);
-                    split8(vc[j], hi, lo);
-                    sts128(sb + 2 * kOp1 + off, hi);
-                    sts128(sb + 3 * kOp1 + off, lo);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        zacc[i] += kc[j][i];
-                        uacc[i] += vc[j][i];
-                        ss = fmaf(kc[j][i], kc[j][i], ss);
-                    }
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
-                if (it + 1 < iters) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { kc[j][i] = kn[j][i]; vc[j][i] = vn[j][i]; }
-                }
-            }
-        } else {
-            // ===== K/V producers: warp w owns nodes w and w+8 of every 16-node stage, lane l owns columns 8l..8l+7.
-            // Register ring of two iterations x 4 chunks (K/V x 2 nodes): as soon as a chunk is converted its
-            // registers are refilled with the load of iteration it+2, so ~8 x 32 B per thread stay in flight.
-            float buf[2][4][8];
-            auto issue = [&](int it, int c, float (&dst)[8]) {
-                if (it >= iters) return;
-                const int64_t row = r0 + (int64_t)it * kR1 + warp + 8 * (c >> 1);
-                if (row < r1) {
-                    if (EVICT_FIRST) ldg256_stream(((c & 1) ? v : k) + row * kRowF + lane * 8, dst);
-                    else ldg256_keep(((c & 1) ? v : k) + row * kRowF + lane * 8, dst);
-                } else {
-    #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = 0.f;
-                }
-            };
-    #pragma unroll
-            for (int c = 0; c < 4; ++c) issue(0, c, buf[0][c]);
-    #pragma unroll
-            for (int c = 0; c < 4; ++c) issue(1, c, buf[1][c]);
-            const uint32_t stage_base = smem_u32(stages);
-            for (int it0 = 0; it0 < iters; it0 += 2) {
-    #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int it = it0 + half;
-                    if (it < iters) {
-                        const int s = it % kNS1;
-                        if (it >= kNS1) mbar_wait(&empty[s], ((it / kNS1) - 1) & 1);
-                        const uint32_t sb = stage_base + s * kStage1;
-    #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            // chunk c: node r = warp + 8*(c>>1) of the stage ((r>>3) = c>>1, (r&7) = warp); K for even c, V for odd c
-                            const uint32_t off = (uint32_t)((lane >> 3) * kHeadTile1 + (c >> 1) * 1024 + warp * 128 + ((((lane & 7) ^ warp) & 7) << 4));
-                            uint4 hi, lo;
-                            split8(buf[half][c], hi, lo);
-                            sts128(sb + ((c & 1) ? 2 : 0) * kOp1 + off, hi);
-                            sts128(sb + ((c & 1) ? 3 : 1) * kOp1 + off, lo);
-    #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (c & 1) {
-                                    uacc[i] += buf[half][c][i];
-                                } else {
-                                    zacc[i] += buf[half][c][i];
-                                    ss = fmaf(buf[half][c][i], buf[half][c][i], ss);
-                                }
-                            }
-                            issue(it + 2, c, buf[half][c]);
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full[s]);
-                    }
-                }
-            }
-        }
-    } else if (warp < 12) {
-        // ===== Q stream: sum of squares only (the Frobenius norm of difformer.py:20)
-        const int64_t n8 = (r1 > r0 ? (r1 - r0) : 0) * (kRowF / 8);
-        const float* base = q + r0 * kRowF;
-        const int t = tid - 256;
-        const uint64_t qpol = policy_evict_last();
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int64_t i = t;
-        for (; i + 7 * 128 < n8; i += 8 * 128) {
-            float x[8][8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (q_keep) ldg256_policy(base + (i + u * 128) * 8, x[u], qpol);
-                else ldg256_keep(base + (i + u * 128) * 8, x[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u += 4)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    a0 = fmaf(x[u][e], x[u][e], a0); a1 = fmaf(x[u + 1][e], x[u + 1][e], a1);
-                    a2 = fmaf(x[u + 2][e], x[u + 2][e], a2); a3 = fmaf(x[u + 3][e], x[u + 3][e], a3);
-                }
-        }
-        for (; i < n8; i += 128) {
-            float x0[8];
-            ldg256_keep(base + i * 8, x0);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a0 = fmaf(x0[e], x0[e], a0);
-        }
-        ss = (a0 + a1) + (a2 + a3);
-    } else if (lane == 0) {
-        // ===== MMA issuer
-        const uint32_t idesc = make_idesc(128, 128, 1, 1);
-#if DIF_MN_LBO_IS_MNSTRIDE
-        const uint32_t lbo = kHeadTile1, sbo = 1024;
-#else
-        const uint32_t lbo = 1024, sbo = kHeadTile1;
-#endif
-        const uint32_t stage_base = smem_u32(stages);
-        for (int it = 0; it < iters; ++it) {
-            const int s = it % kNS1;
-            if (pf_dist > 0) {
-                // L2 prefetch of the rows `pf_dist` stages ahead (K, V, Q: 16 KB each, contiguous): the producers'
-                // register loads then hit L2, which roughly triples the bandwidth one load slot sustains
-                const int64_t prow = r0 + (int64_t)(it + pf_dist) * kR1;
-                if (prow < r1) {
-                    const uint32_t bytes = (uint32_t)(min((int64_t)kR1, r1 - prow) * kRowF * 4);
-                    if (q_keep) {       // K,V are dead after this pass, Q is re-read by pass 2: tell the L2
-                        prefetch_l2_hint(k + prow * kRowF, bytes, policy_evict_first_());
-                        prefetch_l2_hint(v + prow * kRowF, bytes, policy_evict_first_());
-                        prefetch_l2_hint(q + prow * kRowF, bytes, policy_evict_last());
-                    } else {
-                        prefetch_l2(k + prow * kRowF, bytes);
-                        prefetch_l2(v + prow * kRowF, bytes);
-                        prefetch_l2(q + prow * kRowF, bytes);
-                    }
-                }
-            }
-            mbar_wait(&full[s], (it / kNS1) & 1);
-            tc_fence_after();
-            const uint32_t sb = stage_base + s * kStage1;
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const uint32_t ho = p * 2 * kHeadTile1;          // heads 2p, 2p+1
-                const uint64_t khi = make_desc(sb + 0 * kOp1 + ho, lbo, sbo), klo = make_desc(sb + 1 * kOp1 + ho, lbo, sbo);
-                const uint64_t vhi = make_desc(sb + 2 * kOp1 + ho, lbo, sbo), vlo = make_desc(sb + 3 * kOp1 + ho, lbo, sbo);
-                umma(tmem + p * 128, khi, vhi, idesc, it > 0 ? 1u : 0u);
-                umma(tmem + p * 128, khi, vlo, idesc, 1u);
-                umma(tmem + p * 128, klo, vhi, idesc, 1u);
-            }
-            umma_commit(&empty[s]);
-        }
-        if (iters > 0) umma_commit(&done); else mbar_arrive(&done);
-    }
-
-    // ===== epilogue: per-CTA record [S | z | u | sq slots | sk slots]
-    __syncwarp();
-    mbar_wait(&done, 0);
-    tc_fence_after();
-    ss = warp_sum(ss);
-    if (lane == 0) part[warp] = ss;
-    float* red = reinterpret_cast<float*>(stages);      // all MMAs have completed: stage memory is free
-    if (warp < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            red[warp * kRowF + lane * 8 + i] = zacc[i];
-            red[8 * kRowF + warp * kRowF + lane * 8 + i] = uacc[i];
-        }
-    }
-    __syncthreads();
-    float* rec = ws + (int64_t)blockIdx.x * ws_len;
-    const int64_t offZ = (int64_t)kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim;
-    if (tid < kRowF) {
-        float z = 0.f, u = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { z += red[w * kRowF + tid]; u += red[8 * kRowF + w * kRowF + tid]; }
-        rec[offZ + tid] = z;
-        rec[offU + tid] = u;
-    }
-    if (tid == 0) {
-        float sk = 0.f, sq = 0.f;
-        for (int w = 0; w < 8; ++w) sk += part[w];
-        for (int w = 8; w < 12; ++w) sq += part[w];
-        for (int h = 0; h < kH; ++h) { rec[offSq + h] = h == 0 ? sq : 0.f; rec[offSq + kH + h] = h == 0 ? sk : 0.f; }
-    }
-    if (warp < 4) {
-        // D_p rows 0-63 x cols 0-63 = S_{2p}; rows 64-127 x cols 64-127 = S_{2p+1}; warp w reads lanes 32w..32w+31
-        const int hp = warp >> 1, m = (warp * 32 + lane) & 63;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            float* dst = rec + ((int64_t)(2 * p + hp) * kDim + m) * kDim;
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t r[32];
-                if (iters > 0) {
-                    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p * 128 + hp * 64 + c0, r);
-                    tmem_ld_wait32(r);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0u;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + c0 + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem, 256);
-}
 
 // ------------------------------------------------------------------------------------------
-// pass 1, TMA-staged variant: the K/V/Q rows of a stage (16 nodes x 3 x 1 KB, contiguous in HBM) are
-// fetched with cp.async.bulk into an fp32 staging ring (mbarrier complete_tx), so the loads in
-// flight are bounded by shared memory (3 x 48 KB per SM), not by registers / L1 miss tracking.
-// Converter warps read the staging rows (conflict-free LDS.128), split to bf16 hi/lo and write the
-// swizzled UMMA operand ring.
+// compile-time geometry for H heads of 64 columns
 // ------------------------------------------------------------------------------------------
-constexpr int kBOpBytes = 80 * 128;                   // one (head, hi|lo) B-operand tile of pass 2: 80 rows x 128 B
+template <int H>
+struct Geo {
+    static_assert(H == 1 || H == 2 || H == 4, "tcgen05 path: H in {1, 2, 4}");
+    static constexpr int kRowF = H * kDim;              // floats per node row
+    static constexpr int kRowB = kRowF * 4;             // bytes per node row
+    // pass 1: the UMMA is M = N = 128 = two 64-wide MN blocks.  A block is a head (H >= 2) or, for H = 1, one of the
+    // two 16-node halves of a 32-node stage (both halves accumulate S; the two diagonal blocks are added at the end).
+    static constexpr int kBlocks = H < 2 ? 2 : H;
+    static constexpr int kPairs = kBlocks / 2;
+    static constexpr int kNodes = 16 * kBlocks / H;     // nodes per stage (32 for H = 1, else 16)
+    static constexpr int kBlockTile = 16 * 128;         // [16 nodes][64 bf16]
+    static constexpr int kOp = kBlocks * kBlockTile;    // one operand (Khi | Klo | Vhi | Vlo) of a stage
+    static constexpr int kOpStage = 4 * kOp;
+    static constexpr int kStgT = kNodes * kRowB;        // fp32 staging bytes of one tensor of a stage (= kBlocks * 4 KB)
+    static constexpr int kStg = 3 * kStgT;              // K | V | Q
+    static constexpr int kNSG = 3, kNO = 2;             // staging / operand ring depths
+    static constexpr int kSmem1 = kNSG * kStg + kNO * kOpStage + 1024;
+    static constexpr int kChunksPerRow = kRowB / 16;    // 16-byte chunks per node row (16 H)
+    static constexpr int kChunksPerThread = kStgT / 16 / 256;   // = kBlocks (256 converter threads)
+    static constexpr int kTmemCols1 = kPairs * 128 < 32 ? 32 : kPairs * 128;
+    // partials layout [S | z | u | sq | sk]
+    static constexpr int offZ = H * kDim * kDim, offU = offZ + H * kDim, offSq = offU + H * kDim, kP = offSq + 2;
+    // pass 2
+    static constexpr int kBBytes = H * 2 * 80 * 128;    // prepared B operands: per head hi | lo, 80 rows x 128 B
+};
+
+constexpr int kBOp = 80 * 128;                        // one (head, hi|lo) B-operand tile of pass 2
 constexpr int kShardMaxRanks = 16;
 struct ShardArgs {            // multi-GPU: peer-mapped exchange buffers [2 data slots | flags], see csrc/comm.cu
     float* bufs[kShardMaxRanks];
@@ -514,12 +256,8 @@ struct ShardArgs {            // multi-GPU: peer-mapped exchange buffers [2 data
     unsigned long long seq;
     int64_t slot_floats;
 };
-constexpr int kNSG = 3;                               // staging stages
-constexpr int kStgT = kR1 * 1024;                     // 16 KB: 16 rows of one tensor
-constexpr int kStg = 3 * kStgT;                       // K | V | Q
-constexpr int kNO = 2;                                // operand stages
-constexpr int kSmem1T = kNSG * kStg + kNO * kStage1 + 1024;
-constexpr int kThreadsT = 10 * 32;                    // warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
+constexpr int kThreadsT = 10 * 32;                    // pass 1: warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
+constexpr int kSlices = 148;                          // column slices of the record for the fused cross-CTA sum
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -548,84 +286,96 @@ __device__ __forceinline__ void split4(const float4& x, uint32_t (&hi)[2], uint3
     lo[1] = bf2_bits(x.z - __uint_as_float(hi[1] << 16), x.w - __uint_as_float(hi[1] & 0xffff0000u));
 }
 
-__global__ void __launch_bounds__(kThreadsT, 1)
-reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t N,
-                  int rows_per_cta, float* __restrict__ ws, int64_t ws_len, unsigned long long* __restrict__ flags,
-                  unsigned long long epoch, float* __restrict__ partials, uint8_t* __restrict__ prepared,
-                  int pf_tiles, int pf_grid, int l2_hints, const ShardArgs sh, uint64_t* __restrict__ dbg) {
+
+struct ReduceArgs1 {
+    const float *q, *k, *v;
+    int64_t N;
+    int rows_per_cta;
+    float* ws;                    // per-CTA records [grid][ws_len]
+    int64_t ws_len;
+    unsigned long long* flags;    // [grid] record-ready flags
+    unsigned long long epoch;
+    float* partials;
+    uint8_t* prepared;            // optional pass-2 operand image
+    int l2_hints;
+    ShardArgs sh;
+    uint64_t* dbg;
+};
+
+template <int H>
+__global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_constant__ ReduceArgs1 a) {
+    using G = Geo<H>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stg = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* ops = stg + kNSG * kStg;
-    __shared__ uint64_t sfull[kNSG], sempty[kNSG], ofull[kNO], oempty[kNO], done, tail_bar;
+    uint8_t* ops = stg + G::kNSG * G::kStg;
+    __shared__ uint64_t sfull[G::kNSG], sempty[G::kNSG], ofull[G::kNO], oempty[G::kNO], done, tail_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float part[16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r1 = min(N, r0 + (int64_t)rows_per_cta);
-    const int iters = r1 > r0 ? (int)((r1 - r0 + kR1 - 1) / kR1) : 0;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    const int64_t r1 = min(a.N, r0 + (int64_t)a.rows_per_cta);
+    const int iters = r1 > r0 ? (int)((r1 - r0 + G::kNodes - 1) / G::kNodes) : 0;
+    uint64_t* dbg = a.dbg;
     DIF_STAMP(dbg, 0);
 
     if (tid == 0) {
-        for (int s = 0; s < kNSG; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); }
-        for (int s = 0; s < kNO; ++s) { mbar_init(&ofull[s], 8); mbar_init(&oempty[s], 1); }
+        for (int s = 0; s < G::kNSG; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); }
+        for (int s = 0; s < G::kNO; ++s) { mbar_init(&ofull[s], 8); mbar_init(&oempty[s], 1); }
         mbar_init(&done, 1);
         mbar_init(&tail_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) tmem_alloc(&tmem_slot, 256);
+    if (warp == 9) tmem_alloc(&tmem_slot, G::kTmemCols1);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     DIF_STAMP(dbg, 1);
 
-    float zacc[8], uacc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { zacc[i] = 0.f; uacc[i] = 0.f; }
+    // a converter thread always sees the same 4 columns: column chunk (tid mod 16H) of every row it touches
+    float zacc[4] = {0.f, 0.f, 0.f, 0.f}, uacc[4] = {0.f, 0.f, 0.f, 0.f};
     float ssk = 0.f, ssq = 0.f;
 
     if (warp < 8) {
-        // ===== converters: warp w owns nodes w and w+8 of every stage; lane l owns columns 4l..4l+3 and 128+4l..131+4l
+        // ===== converters: thread t handles 16-byte chunks u = t + 256 i (i < kBlocks) of each staged tensor
         const uint32_t stg_base = smem_u32(stg), ops_base = smem_u32(ops);
         for (int it = 0; it < iters; ++it) {
-            const int s = it % kNSG, o = it % kNO;
-            const int nrows = (int)min((int64_t)kR1, r1 - (r0 + (int64_t)it * kR1));
-            mbar_wait(&sfull[s], (it / kNSG) & 1);
+            const int s = it % G::kNSG, o = it % G::kNO;
+            const int nrows = (int)min((int64_t)G::kNodes, r1 - (r0 + (int64_t)it * G::kNodes));
+            mbar_wait(&sfull[s], (it / G::kNSG) & 1);
             if (it == 0) DIF_STAMP(dbg, 2);
-            float4 x[2][3][2];
+            float4 x[G::kChunksPerThread][3];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int node = warp + 8 * j;
+            for (int i = 0; i < G::kChunksPerThread; ++i) {
+                const int u = tid + 256 * i, node = u / G::kChunksPerRow;
 #pragma unroll
-                for (int t = 0; t < 3; ++t)
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        x[j][t][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (node < nrows) x[j][t][g] = lds128(stg_base + s * kStg + t * kStgT + node * 1024 + g * 512 + lane * 16);
-                    }
-            }
-            if (it >= kNO) mbar_wait(&oempty[o], ((it / kNO) - 1) & 1);
-            const uint32_t ob = ops_base + o * kStage1;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    // column 128g + 4 lane: head = 2g + (lane>>4), m = 4 (lane & 15): chunk16 = (lane & 15) >> 1, half = lane & 1
-                    const uint32_t off = (uint32_t)((2 * g + (lane >> 4)) * kHeadTile1 + j * 1024 + warp * 128 +
-                                                    ((((lane & 15) >> 1) ^ warp) & 7) * 16 + (lane & 1) * 8);
-                    uint32_t hi[2], lo[2];
-                    split4(x[j][0][g], hi, lo);
-                    sts64(ob + 0 * kOp1 + off, hi[0], hi[1]);
-                    sts64(ob + 1 * kOp1 + off, lo[0], lo[1]);
-                    split4(x[j][1][g], hi, lo);
-                    sts64(ob + 2 * kOp1 + off, hi[0], hi[1]);
-                    sts64(ob + 3 * kOp1 + off, lo[0], lo[1]);
-                    const float4 kk = x[j][0][g], vv = x[j][1][g], qq = x[j][2][g];
-                    zacc[4 * g + 0] += kk.x; zacc[4 * g + 1] += kk.y; zacc[4 * g + 2] += kk.z; zacc[4 * g + 3] += kk.w;
-                    uacc[4 * g + 0] += vv.x; uacc[4 * g + 1] += vv.y; uacc[4 * g + 2] += vv.z; uacc[4 * g + 3] += vv.w;
-                    ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
-                    ssq = fmaf(qq.x, qq.x, ssq); ssq = fmaf(qq.y, qq.y, ssq); ssq = fmaf(qq.z, qq.z, ssq); ssq = fmaf(qq.w, qq.w, ssq);
+                for (int t = 0; t < 3; ++t) {
+                    x[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (node < nrows) x[i][t] = lds128(stg_base + s * G::kStg + t * G::kStgT + u * 16);
                 }
+            }
+            if (it >= G::kNO) mbar_wait(&oempty[o], ((it / G::kNO) - 1) & 1);
+            const uint32_t ob = ops_base + o * G::kOpStage;
+#pragma unroll
+            for (int i = 0; i < G::kChunksPerThread; ++i) {
+                const int u = tid + 256 * i, node = u / G::kChunksPerRow, cc = u % G::kChunksPerRow;   // cc: 4-float column chunk
+                const int head = cc >> 4, m = (cc & 15) * 4;
+                const int blk = (H == 1) ? (node >> 4) : head;      // MN block of the UMMA
+                const int kn = (H == 1) ? (node & 15) : node;        // K index (node inside the block tile)
+                const uint32_t off = (uint32_t)(blk * G::kBlockTile + (kn >> 3) * 1024 + (kn & 7) * 128 +
+                                                ((((m >> 3) ^ kn) & 7) << 4) + ((m >> 2) & 1) * 8);
+                uint32_t hi[2], lo[2];
+                split4(x[i][0], hi, lo);
+                sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
+                sts64(ob + 1 * G::kOp + off, lo[0], lo[1]);
+                split4(x[i][1], hi, lo);
+                sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
+                sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
+                const float4 kk = x[i][0], vv = x[i][1], qq = x[i][2];
+                zacc[0] += kk.x; zacc[1] += kk.y; zacc[2] += kk.z; zacc[3] += kk.w;
+                uacc[0] += vv.x; uacc[1] += vv.y; uacc[2] += vv.z; uacc[3] += vv.w;
+                ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
+                ssq = fmaf(qq.x, qq.x, ssq); ssq = fmaf(qq.y, qq.y, ssq); ssq = fmaf(qq.z, qq.z, ssq); ssq = fmaf(qq.w, qq.w, ssq);
             }
             fence_proxy_async();
             __syncwarp();
@@ -633,40 +383,41 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
         }
     } else if (warp == 8) {
         if (lane == 0) {
-            // ===== TMA issuer: three 16 KB bulk copies per stage
+            // ===== TMA issuer: the stage's rows of K, V, Q are contiguous in HBM: three bulk copies per stage
             const uint32_t stg_base = smem_u32(stg);
+            const uint64_t pol_first = policy_evict_first_(), pol_last = policy_evict_last();
             for (int it = 0; it < iters; ++it) {
-                const int s = it % kNSG;
-                if (it >= kNSG) mbar_wait(&sempty[s], ((it / kNSG) - 1) & 1);
-                const int64_t row = r0 + (int64_t)it * kR1;
-                const uint32_t bytes = (uint32_t)(min((int64_t)kR1, r1 - row) * kRowF * 4);
+                const int s = it % G::kNSG;
+                if (it >= G::kNSG) mbar_wait(&sempty[s], ((it / G::kNSG) - 1) & 1);
+                const int64_t row = r0 + (int64_t)it * G::kNodes;
+                const uint32_t bytes = (uint32_t)(min((int64_t)G::kNodes, r1 - row) * G::kRowB);
                 mbar_expect_tx(&sfull[s], 3 * bytes);
-                if (l2_hints) {     // K, V are dead after this pass; Q is read again by pass 2
-                    tma_load_1d_hint(stg_base + s * kStg + 0 * kStgT, k + row * kRowF, bytes, &sfull[s], policy_evict_first_());
-                    tma_load_1d_hint(stg_base + s * kStg + 1 * kStgT, v + row * kRowF, bytes, &sfull[s], policy_evict_first_());
-                    tma_load_1d_hint(stg_base + s * kStg + 2 * kStgT, q + row * kRowF, bytes, &sfull[s], policy_evict_last());
+                if (a.l2_hints) {     // K, V are dead after this pass; Q is read again by pass 2
+                    tma_load_1d_hint(stg_base + s * G::kStg + 0 * G::kStgT, a.k + row * G::kRowF, bytes, &sfull[s], pol_first);
+                    tma_load_1d_hint(stg_base + s * G::kStg + 1 * G::kStgT, a.v + row * G::kRowF, bytes, &sfull[s], pol_first);
+                    tma_load_1d_hint(stg_base + s * G::kStg + 2 * G::kStgT, a.q + row * G::kRowF, bytes, &sfull[s], pol_last);
                 } else {
-                    tma_load_1d(stg_base + s * kStg + 0 * kStgT, k + row * kRowF, bytes, &sfull[s]);
-                    tma_load_1d(stg_base + s * kStg + 1 * kStgT, v + row * kRowF, bytes, &sfull[s]);
-                    tma_load_1d(stg_base + s * kStg + 2 * kStgT, q + row * kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * G::kStg + 0 * G::kStgT, a.k + row * G::kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * G::kStg + 1 * G::kStgT, a.v + row * G::kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * G::kStg + 2 * G::kStgT, a.q + row * G::kRowF, bytes, &sfull[s]);
                 }
             }
         }
     } else if (lane == 0) {
-        // ===== MMA issuer
+        // ===== MMA issuer: D_p[128 x 128] += A^T B over 16 K-steps-worth of nodes; MN-major operands
         const uint32_t idesc = make_idesc(128, 128, 1, 1);
-        const uint32_t lbo = kHeadTile1, sbo = 1024;
+        const uint32_t lbo = G::kBlockTile, sbo = 1024;
         const uint32_t ops_base = smem_u32(ops);
         for (int it = 0; it < iters; ++it) {
-            const int o = it % kNO;
-            mbar_wait(&ofull[o], (it / kNO) & 1);
+            const int o = it % G::kNO;
+            mbar_wait(&ofull[o], (it / G::kNO) & 1);
             tc_fence_after();
-            const uint32_t sb = ops_base + o * kStage1;
+            const uint32_t sb = ops_base + o * G::kOpStage;
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const uint32_t ho = p * 2 * kHeadTile1;
-                const uint64_t khi = make_desc(sb + 0 * kOp1 + ho, lbo, sbo), klo = make_desc(sb + 1 * kOp1 + ho, lbo, sbo);
-                const uint64_t vhi = make_desc(sb + 2 * kOp1 + ho, lbo, sbo), vlo = make_desc(sb + 3 * kOp1 + ho, lbo, sbo);
+            for (int p = 0; p < G::kPairs; ++p) {
+                const uint32_t ho = p * 2 * G::kBlockTile;
+                const uint64_t khi = make_desc(sb + 0 * G::kOp + ho, lbo, sbo), klo = make_desc(sb + 1 * G::kOp + ho, lbo, sbo);
+                const uint64_t vhi = make_desc(sb + 2 * G::kOp + ho, lbo, sbo), vlo = make_desc(sb + 3 * G::kOp + ho, lbo, sbo);
                 umma(tmem + p * 128, khi, vhi, idesc, it > 0 ? 1u : 0u);
                 umma(tmem + p * 128, khi, vlo, idesc, 1u);
                 umma(tmem + p * 128, klo, vhi, idesc, 1u);
@@ -677,10 +428,9 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
     }
 
     // ===== tail: per-CTA record in the partials layout [S | z | u | sq | sk], then the cross-CTA sum fused in:
-    // every CTA publishes its record (flag = epoch), waits for all flags (the grid is launched
-    // cooperatively, all CTAs are resident), TMA-loads "its" column slice of all records into shared
-    // memory and sums it in fixed order (fp64) -> partials (deterministic, no float atomics).
-    // The S / z entries are also emitted as the bf16 hi/lo, 128B-swizzled B operand image of pass 2.
+    // every CTA publishes its record (flag = epoch), waits for all flags (cooperative launch: all CTAs are resident),
+    // gathers "its" column slices of all records with TMA and sums them in a fixed order (fp64) -> partials
+    // (deterministic, no float atomics).  S / z entries are also emitted as the pass-2 operand image (bf16 hi/lo, swizzled).
     __syncwarp();
     if (warp == 0) DIF_STAMP(dbg, 3);
     mbar_wait(&done, 0);
@@ -692,50 +442,70 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
     float* red = reinterpret_cast<float*>(ops);         // all MMAs have completed: operand memory is free
     if (warp < 8) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int col = (i < 4) ? 4 * lane + i : 128 + 4 * lane + (i - 4);
-            red[warp * kRowF + col] = zacc[i];
-            red[8 * kRowF + warp * kRowF + col] = uacc[i];
-        }
+        for (int i = 0; i < 4; ++i) { red[tid * 4 + i] = zacc[i]; red[1024 + tid * 4 + i] = uacc[i]; }
     }
     __syncthreads();
-    float* rec = ws + (int64_t)blockIdx.x * ws_len;
-    constexpr int offZ = kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim, kP = offSq + 2;
-    if (tid < kRowF) {
+    float* rec = a.ws + (int64_t)blockIdx.x * a.ws_len;
+    if (tid < G::kRowF) {
+        // column tid = chunk (tid >> 2) element (tid & 3); the threads t with t mod 16H == chunk hold its partial sums
         float z = 0.f, u = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { z += red[w * kRowF + tid]; u += red[8 * kRowF + w * kRowF + tid]; }
-        rec[offZ + tid] = z;
-        rec[offU + tid] = u;
+        for (int t = tid >> 2; t < 256; t += G::kChunksPerRow) { z += red[t * 4 + (tid & 3)]; u += red[1024 + t * 4 + (tid & 3)]; }
+        rec[G::offZ + tid] = z;
+        rec[G::offU + tid] = u;
     }
     if (tid == 0) {
         float sk = 0.f, sq = 0.f;
         for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
-        rec[offSq] = sq;
-        rec[offSq + 1] = sk;
-        for (int64_t i = kP; i < ws_len; ++i) rec[i] = 0.f;
+        rec[G::offSq] = sq;
+        rec[G::offSq + 1] = sk;
+        for (int64_t i = G::kP; i < a.ws_len; ++i) rec[i] = 0.f;
     }
-    if (warp < 8) {
-        // D_p rows 0-63 x cols 0-63 = S_{2p}, rows 64-127 x cols 64-127 = S_{2p+1}.  Warp w reads TMEM lanes
-        // 32(w%4)..+31 (its quadrant); warps 0-3 take head pair p = 0, warps 4-7 p = 1.  256-bit stores.
+    __syncthreads();                                   // `red` is re-used below (H == 1)
+    {
+        // D_p rows 0-63 x cols 0-63 = block 2p, rows 64-127 x cols 64-127 = block 2p+1.  Warp w reads TMEM lanes
+        // 32(w%4)..+31 (its quadrant); warps 0-3 take pair 0, warps 4-7 pair 1 (H = 4 only).
         const int wq = warp & 3, p = warp >> 2;
         const int hp = wq >> 1, m = (wq * 32 + lane) & 63;
-        float* dst = rec + ((int64_t)(2 * p + hp) * kDim + m) * kDim;
+        const bool active = warp < 4 * G::kPairs;
+        uint32_t r[2][32];
+        if (active) {
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-            uint32_t r[32];
-            if (iters > 0) {
-                tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + p * 128 + hp * 64 + c0, r);
-                tmem_ld_wait32(r);
-            } else {
+            for (int c = 0; c < 2; ++c) {
+                if (iters > 0) {
+                    tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + p * 128 + hp * 64 + c * 32, r[c]);
+                    tmem_ld_wait32(r[c]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    for (int j = 0; j < 32; ++j) r[c][j] = 0u;
+                }
             }
+        }
+        if (H == 1) {
+            // the two diagonal blocks are the two node halves of every stage: S = block 0 + block 1
+            if (active && hp == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                             :: "l"(dst + c0 + j), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]), "r"(r[j + 4]), "r"(r[j + 5]),
-                                "r"(r[j + 6]), "r"(r[j + 7]) : "memory");
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) red[m * 65 + c * 32 + j] = __uint_as_float(r[c][j]);
+            }
+            __syncthreads();
+            if (active && hp == 0) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[c][j] = __float_as_uint(__uint_as_float(r[c][j]) + red[m * 65 + c * 32 + j]);
+            }
+        }
+        if (active && (H != 1 || hp == 0)) {
+            const int blk = (H == 1) ? 0 : 2 * p + hp;
+            float* dst = rec + ((int64_t)blk * kDim + m) * kDim;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 :: "l"(dst + c * 32 + j), "r"(r[c][j]), "r"(r[c][j + 1]), "r"(r[c][j + 2]), "r"(r[c][j + 3]),
+                                    "r"(r[c][j + 4]), "r"(r[c][j + 5]), "r"(r[c][j + 6]), "r"(r[c][j + 7]) : "memory");
         }
     }
     // ---- publish the record
@@ -743,56 +513,42 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
     __syncthreads();
     DIF_STAMP(dbg, 5);
     const int grid = gridDim.x;
-    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flags + blockIdx.x), "l"(epoch) : "memory");
-    if (tid == 64 && pf_tiles > 0 && (int)blockIdx.x < pf_grid) {
-        // HBM is idle while the grid exchanges its records: pull the first Q tiles pass 2 will read (tiles
-        // b, b + G, ... of "its" CTA b) into L2 now, so pass 2 starts from L2 hits instead of a cold ramp
-        const int64_t ntiles = (N + 127) / 128;
-        for (int i = 0; i < pf_tiles; ++i) {
-            const int64_t tile = blockIdx.x + (int64_t)i * pf_grid;
-            if (tile >= ntiles) break;
-            const int64_t prow = tile * 128;
-            const int64_t nrows = min((int64_t)128, N - prow);
-            for (int64_t r = 0; r < nrows; r += 16)
-                prefetch_l2(q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
-        }
-    }
-    // ---- column slices of the record: kSlices fixed slices of `chunk` floats (multiples of 16 B), slice sl is
-    //      owned by CTA sl % grid -- the partition does not depend on this rank's grid, so slices line up across ranks
-    constexpr int kSlices = 148;
-    const int chunk = (int)((((ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(a.epoch) : "memory");
+    // ---- column slices of the record: kSlices fixed slices of `chunk` floats (multiples of 16 B), slice sl is owned by
+    //      CTA sl % grid -- the partition does not depend on this rank's grid, so slices line up across ranks
+    const int chunk = (int)((((a.ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
     float* sbuf = reinterpret_cast<float*>(stg);        // [grid][chunk] fp32, the staging ring is idle now
+    const ShardArgs& sh = a.sh;
     const bool sharded = sh.world > 1;
     const int xslot = (int)(sh.seq & 1);
     bool waited = false;
     uint32_t tail_phase = 0;
     for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
         const int64_t j0 = (int64_t)sl * chunk;
-        const int slice = (int)max((int64_t)0, min(ws_len, j0 + chunk) - j0);
+        const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
         if (slice <= 0) break;
         if (!waited) {
             for (int r = tid; r < grid; r += kThreadsT) {
                 unsigned long long f;
                 do {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + r) : "memory");
-                    if (f != epoch) __nanosleep(64);
-                } while (f != epoch);
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
+                    if (f != a.epoch) __nanosleep(64);
+                } while (f != a.epoch);
             }
             asm volatile("fence.proxy.async;" ::: "memory");   // acquired (generic proxy) before the bulk (async proxy) reads
             waited = true;
         }
-        __syncthreads();                                  // also: previous slice's readers of sbuf are done
+        __syncthreads();                                  // also: the previous slice's readers of sbuf are done
         if (tid == 0) mbar_expect_tx(&tail_bar, (uint32_t)grid * (uint32_t)slice * 4u);
         __syncthreads();
         for (int r = tid; r < grid; r += kThreadsT)
-            tma_load_1d(smem_u32(sbuf) + (uint32_t)r * chunk * 4, ws + (int64_t)r * ws_len + j0, (uint32_t)slice * 4u, &tail_bar);
+            tma_load_1d(smem_u32(sbuf) + (uint32_t)r * chunk * 4, a.ws + (int64_t)r * a.ws_len + j0, (uint32_t)slice * 4u, &tail_bar);
         mbar_wait(&tail_bar, tail_phase);
         tail_phase ^= 1;
-        // local sum of this slice over the grid's records
-        float local = 0.f;
-        const int t = tid;                                // chunk <= kThreadsT is asserted on the host
+        const int t = tid;                                // chunk <= kThreadsT (checked on the host)
         const int64_t j = j0 + t;
-        const bool live = t < slice && j < kP;
+        const bool live = t < slice && j < G::kP;
+        float local = 0.f;
         if (live) {
             // four independent chains (records r = 4i + k), combined in a fixed order: deterministic, 4x shorter latency
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -808,9 +564,9 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
         }
         float sum = local;
         if (sharded) {
-            // ---- cross-GPU: the same kernel finishes the all-reduce over NVLink, slice by slice.  Publish the local
-            // slice in this rank's peer-mapped buffer, raise flag (slot, rank, slice) in every peer, wait for the
-            // peers' flags, add the ranks' slices in rank order (bit-identical on all ranks).
+            // ---- cross-GPU: the same kernel finishes the all-reduce over NVLink, slice by slice.  Publish the local slice in
+            // this rank's peer-mapped buffer, raise flag (slot, rank, slice) in every peer, wait for the peers' flags, add
+            // the ranks' slices in rank order (bit-identical on all ranks).
             float* mine = sh.bufs[sh.rank] + (int64_t)xslot * sh.slot_floats;
             if (live) mine[j] = local;
             __threadfence_system();
@@ -837,33 +593,32 @@ reduce_tma_kernel(const float* __restrict__ q, const float* __restrict__ k, cons
             }
         }
         if (live) {
-            partials[j] = sum;
-            if (prepared != nullptr && j < offU) {
+            a.partials[j] = sum;
+            if (a.prepared != nullptr && j < G::offU) {
                 // B operand image of pass 2 (un-scaled; pass 2 applies c = 1/(|Q||K|) in its epilogue):
                 // S[h][m][d] -> row n = d, k = m of head h ; z[h][m] -> row 64
                 int h, n, m;
-                if (j < offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
-                else { h = (int)(j - offZ) >> 6; m = (int)(j - offZ) & 63; n = kDim; }
+                if (j < G::offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
+                else { h = (int)(j - G::offZ) >> 6; m = (int)(j - G::offZ) & 63; n = kDim; }
                 const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(sum - __bfloat162float(hi));
-                uint8_t* img = prepared + (size_t)h * 2 * kBOpBytes + sw128(n, m >> 3) + (m & 7) * 2;
+                uint8_t* img = a.prepared + (size_t)h * 2 * kBOp + sw128(n, m >> 3) + (m & 7) * 2;
                 *reinterpret_cast<__nv_bfloat16*>(img) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(img + kBOpBytes) = lo;
+                *reinterpret_cast<__nv_bfloat16*>(img + kBOp) = lo;
             }
         }
     }
-    if (prepared != nullptr && blockIdx.x == grid - 1) {
-        // zero rows 65..79 of every (head, hi/lo) tile: 15 rows x 128 B, contiguous after row 64 inside the last 8-row group...
-        // rows 64..71 live in group 8 (bytes 8192..9215), rows 72..79 in group 9: zero everything except row 64
-        for (int i = tid; i < kH * 2 * 15 * 8; i += kThreadsT) {
+    if (a.prepared != nullptr && blockIdx.x == grid - 1) {
+        // rows 65..79 of every (head, hi|lo) tile are zero padding (N = 80 of the pass-2 UMMA)
+        for (int i = tid; i < H * 2 * 15 * 8; i += kThreadsT) {
             const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
-            *reinterpret_cast<uint4*>(prepared + (size_t)t * kBOpBytes + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(a.prepared + (size_t)t * kBOp + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     tc_fence_before();
     __syncthreads();
     DIF_STAMP(dbg, 6);
-    if (warp == 9) tmem_dealloc(tmem, 256);
+    if (warp == 9) tmem_dealloc(tmem, G::kTmemCols1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -874,12 +629,11 @@ constexpr int kQOp = kTile2 * 128;                    // 16 KB: [128 rows][64 bf
 constexpr int kStage2 = 2 * kQOp;                     // Qhi | Qlo
 constexpr int kNS2 = 3;
 constexpr int kBN = 80;                               // UMMA N: 64 columns of S + z column + padding
-constexpr int kBOp = kBN * 128;                       // 10 KB
-constexpr int kBBytes = kH * 2 * kBOp;                // 80 KB: per head hi | lo
 constexpr int kNAcc = 4, kAccCols = 128;              // TMEM accumulator ring (4 x 128 columns)
 constexpr int kOutBox = 32 * 128;                     // TMA store box: 32 rows x 32 floats, 128B swizzle
 constexpr int kOutStage = 4 * 2 * kOutBox;            // per epilogue warp: two boxes (column halves of a head)
-constexpr int kSmem2 = kBBytes + kNS2 * kStage2 + kOutStage + kH * kDim * 4 + 1024;
+template <int H>
+constexpr int smem2_bytes() { return Geo<H>::kBBytes + kNS2 * kStage2 + kOutStage + H * kDim * 4 + 1024; }
 
 struct ApplyTcArgs {
     const float* q;
@@ -887,50 +641,38 @@ struct ApplyTcArgs {
     float n_total;
     int64_t N;
     float* out;
-    int tiles_per_cta;      // > 0: CTA b owns tiles [b*tpc, (b+1)*tpc) -- the row range it reduced in pass 1 -- and walks
-                            //      them backwards, so the Q rows pass 1 touched last are re-read first (L2 hits)
-    int pf_tiles;           // L2 prefetch distance in tiles (0 = off)
-    uint64_t* dbg;          // optional timeline buffer
+    int pf_tiles;            // L2 prefetch distance in tiles (0 = off)
+    int store_hint;          // 1: TMA stores carry an L2 evict_first policy (the output is not re-read)
+    uint64_t* dbg;           // optional timeline buffer
     const uint8_t* prepared; // optional B operand image written by the fused pass-1 tail (un-scaled S|z, bf16 hi/lo, swizzled)
-    int store_hint;         // 1: TMA stores carry an L2 evict_first policy (output is not re-read; keeps Q resident)
     dif_epilogue_t ep;
 };
 
-template <int MODE, bool RING>
+template <int MODE, int H>
 __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_constant__ ApplyTcArgs p, const __grid_constant__ CUtensorMap out_map) {
+    using G = Geo<H>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* Bop = base;                               // [h][hi|lo][80 rows][128 B]
-    uint8_t* stages = base + kBBytes;
+    uint8_t* Bop = base;                                             // [h][hi|lo][80 rows][128 B]
+    uint8_t* stages = base + G::kBBytes;
     uint8_t* ostage = stages + kNS2 * kStage2;                       // [4 warps][2 boxes][32 rows][128 B], 1024-aligned
     float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
     __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], bbar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
-    const bool contiguous = p.tiles_per_cta > 0;
-    const int64_t first_tile = contiguous ? (int64_t)blockIdx.x * p.tiles_per_cta : blockIdx.x;
-    int my_tiles;
-    if (contiguous) {
-        const int64_t rem = ntiles - first_tile;
-        my_tiles = rem <= 0 ? 0 : (rem < p.tiles_per_cta ? (int)rem : p.tiles_per_cta);
-    } else {
-        my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
-    }
-    const int nsc = my_tiles * kH;                     // (tile, head) stages of this CTA
-    auto tile_of = [&](int sc) -> int64_t {
-        const int i = sc >> 2;
-        return contiguous ? first_tile + (my_tiles - 1 - i) : first_tile + (int64_t)i * gridDim.x;
-    };
+    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const int nsc = my_tiles * H;                       // (tile, head) stages of this CTA
+    auto tile_of = [&](int sc) -> int64_t { return blockIdx.x + (int64_t)(sc / H) * gridDim.x; };
 
     DIF_STAMP(p.dbg, 0);
     if (tid == 32 && my_tiles > 0) {
-        // the B-operand prologue below takes a few us: have the first tiles of Q on their way to L2 meanwhile
+        // have the first tiles of Q on their way to L2 while the prologue runs
         for (int i = 0; i < 2 && i < my_tiles; ++i) {
-            const int64_t prow = tile_of(4 * i) * kTile2;
+            const int64_t prow = tile_of(H * i) * kTile2;
             const int64_t nrows = min((int64_t)kTile2, p.N - prow);
             for (int64_t r = 0; r < nrows; r += 16)
-                prefetch_l2(p.q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
+                prefetch_l2(p.q + (prow + r) * G::kRowF, (uint32_t)(min((int64_t)16, nrows - r) * G::kRowB));
         }
     }
     if (tid == 0) {
@@ -939,21 +681,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         mbar_init(&bbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (p.prepared != nullptr) {
-            // the B operands were prepared by pass 1: one 80 KB TMA fetch instead of a transposing prologue
-            mbar_expect_tx(&bbar, (uint32_t)kBBytes);
-            for (int i = 0; i < kH * 2; ++i)
+            // the B operands were prepared by pass 1: one TMA fetch instead of a transposing prologue
+            mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
+            for (int i = 0; i < H * 2; ++i)
                 tma_load_1d(smem_u32(Bop) + i * kBOp, p.prepared + (size_t)i * kBOp, (uint32_t)kBOp, &bbar);
         }
     }
     if (warp == 12) tmem_alloc(&tmem_slot, 512);
 
-    // ---- B operands: row n < 64: c*S[h][:, n] ; row 64: c*z[h] ; rows 65..79: 0   (K-major SW128, hi/lo split)
-    const int64_t offZ = (int64_t)kH * kDim * kDim, offU = offZ + kH * kDim, offSq = offU + kH * kDim;
-    const float c = 1.f / (sqrtf(p.partials[offSq]) * sqrtf(p.partials[offSq + 1]));
+    // ---- B operands: row n < 64: S[h][:, n] ; row 64: z[h] ; rows 65..79: 0   (K-major SW128, hi/lo split)
+    const float c = 1.f / (sqrtf(p.partials[G::offSq]) * sqrtf(p.partials[G::offSq + 1]));
     const float cscale = p.prepared != nullptr ? c : 1.f;   // prepared operands are un-scaled: the epilogue applies c
     if (p.prepared == nullptr) {
-        // all loads of a thread's (up to 7) tasks are issued before the first use: two L2 round trips, not 50
-        constexpr int kTasks = kH * 8 * kBN, kPer = (kTasks + kThreadsTC - 1) / kThreadsTC;
+        // fallback (partials were edited / all-reduced outside): build the operands here, pre-scaled by c.
+        // All loads of a thread's tasks are issued before the first use: two L2 round trips, not 50.
+        constexpr int kTasks = H * 8 * kBN, kPer = (kTasks + kThreadsTC - 1) / kThreadsTC;
         float x[kPer][8];
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
@@ -965,7 +707,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                 x[u][i] = 0.f;
                 if (task < kTasks) {
                     if (n < kDim) x[u][i] = __ldg(p.partials + ((int64_t)h * kDim + m) * kDim + n);
-                    else if (n == kDim) x[u][i] = __ldg(p.partials + offZ + h * kDim + m);
+                    else if (n == kDim) x[u][i] = __ldg(p.partials + G::offZ + h * kDim + m);
                 }
             }
         }
@@ -984,7 +726,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             }
         }
     }
-    for (int i = tid; i < kH * kDim; i += kThreadsTC) us[i] = p.partials[offU + i];
+    for (int i = tid; i < H * kDim; i += kThreadsTC) us[i] = p.partials[G::offU + i];
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -994,7 +736,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
 
     if (warp < 8) {
         // ===== Q producers: stage = (tile, head): 128 rows x 256 B; task t -> row t>>3, chunk t&7.
-        // Two-stage register ring, refilled chunk by chunk (see pass 1).
+        // Whole-stage double buffer: buf[0] = current, buf[1] = next (its loads are in flight while buf[0] is converted).
         float buf[2][4][8];
         auto issue = [&](int sc, int j, float (&dst)[8]) {
             if (sc >= nsc) return;
@@ -1002,7 +744,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             const int t = tid + 256 * j;
             const int64_t row = tile * kTile2 + (t >> 3);
             if (row < p.N) {
-                ldg256_stream(p.q + row * kRowF + (sc & 3) * kDim + (t & 7) * 8, dst);
+                ldg256_stream(p.q + row * G::kRowF + (sc % H) * kDim + (t & 7) * 8, dst);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dst[i] = 0.f;
@@ -1013,79 +755,51 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
         const uint32_t stage_base = smem_u32(stages);
-        if (RING) {
-            for (int sc0 = 0; sc0 < nsc; sc0 += 2) {
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int s = sc % kNS2;
+            if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+            const uint32_t sb = stage_base + s * kStage2;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int sc = sc0 + half;
-                    if (sc < nsc) {
-                        const int s = sc % kNS2;
-                        if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
-                        const uint32_t sb = stage_base + s * kStage2;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int t = tid + 256 * j;
-                            uint4 hi, lo;
-                            split8(buf[half][j], hi, lo);
-                            const uint32_t off = sw128(t >> 3, t & 7);
-                            sts128(sb + off, hi);
-                            sts128(sb + kQOp + off, lo);
-                            issue(sc + 2, j, buf[half][j]);
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full[s]);
-                    }
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                uint4 hi, lo;
+                split8(buf[0][j], hi, lo);
+                const uint32_t off = sw128(t >> 3, t & 7);
+                sts128(sb + off, hi);
+                sts128(sb + kQOp + off, lo);
             }
-        } else {
-            // whole-stage double buffer: buf[0] = current, buf[1] = next (loads of sc+1 issued, then sc converted)
-            for (int sc = 0; sc < nsc; ++sc) {
-                const int s = sc % kNS2;
-                if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
-                const uint32_t sb = stage_base + s * kStage2;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int t = tid + 256 * j;
-                    uint4 hi, lo;
-                    split8(buf[0][j], hi, lo);
-                    const uint32_t off = sw128(t >> 3, t & 7);
-                    sts128(sb + off, hi);
-                    sts128(sb + kQOp + off, lo);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
-                    issue(sc + 2, j, buf[1][j]);
-                }
+                for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
+                issue(sc + 2, j, buf[1][j]);
             }
         }
     } else if (warp < 12) {
-        // ===== epilogue: thread = one row of the tile; accumulator lane = 32*(warp%4) + lane.
-        // Results leave through TMA: each lane writes its row into a 128B-swizzled staging box
-        // (conflict-free st.shared), one lane issues cp.async.bulk.tensor stores (rows beyond N are
-        // clipped by the tensor map).  No scattered st.global on the LSU.
+        // ===== epilogue: thread = one row of the tile; accumulator lane = 32*(warp%4) + lane.  Results leave through TMA:
+        // each lane writes its row into a 128B-swizzled staging box (conflict-free st.shared), one lane issues
+        // cp.async.bulk.tensor stores (rows beyond N are clipped by the tensor map).  No scattered st.global on the LSU.
         const int ew = warp - 8;
         const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
+        const uint64_t pol = policy_evict_first();
         float hs[MODE == 1 ? kDim : 1];
         for (int sc = 0; sc < nsc; ++sc) {
             const int64_t tile = tile_of(sc);
-            const int h = sc & 3, slot = sc % kNAcc;
+            const int h = sc % H, slot = sc % kNAcc;
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
-            uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q^.z^
+            uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q . z
             tmem_ld_wait1(qz_bits);
             const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.n_total));   // one division per (row, head)
             if (MODE == 1 && h == 0) {
 #pragma unroll
                 for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
             }
-            if (MODE == 0 || h == kH - 1) {       // staging is about to be rewritten: previous TMA reads must be done
+            if (MODE == 0 || h == H - 1) {        // staging is about to be rewritten: previous TMA reads must be done
                 if (lane == 0) tma_wait_read0();
                 __syncwarp();
             }
@@ -1115,7 +829,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                     }
                 }
             }
-            if (MODE == 1 && h == kH - 1) {
+            if (MODE == 1 && h == H - 1) {
                 const int64_t row = tile * kTile2 + ew * 32 + lane;
                 const bool ok = row < p.N;
 #pragma unroll
@@ -1133,14 +847,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                            make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
                 }
             }
-            if (MODE == 0 || h == kH - 1) {
+            if (MODE == 0 || h == H - 1) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     const int col = MODE == 0 ? h * kDim : 0;
                     const int row0 = (int)(tile * kTile2) + ew * 32;
                     if (p.store_hint) {
-                        const uint64_t pol = policy_evict_first();
                         tma_store_2d_hint(&out_map, obox, col, row0, pol);
                         tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
                     } else {
@@ -1158,13 +871,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
         if (p.prepared != nullptr) mbar_wait(&bbar, 0);
         for (int sc = 0; sc < nsc; ++sc) {
-            const int s = sc % kNS2, slot = sc % kNAcc, h = sc & 3;
-            if (p.pf_tiles > 0 && h == 0 && sc + 4 * p.pf_tiles < nsc) {
-                const int64_t ptile = tile_of(sc + 4 * p.pf_tiles);
-                const int64_t prow = ptile * kTile2;
+            const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
+            if (p.pf_tiles > 0 && h == 0 && sc + H * p.pf_tiles < nsc) {
+                const int64_t prow = tile_of(sc + H * p.pf_tiles) * kTile2;
                 const int64_t nrows = min((int64_t)kTile2, p.N - prow);
                 for (int64_t r = 0; r < nrows; r += 16)
-                    prefetch_l2(p.q + (prow + r) * kRowF, (uint32_t)(min((int64_t)16, nrows - r) * kRowF * 4));
+                    prefetch_l2(p.q + (prow + r) * G::kRowF, (uint32_t)(min((int64_t)16, nrows - r) * G::kRowB));
             }
             if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
             mbar_wait(&full[s], (sc / kNS2) & 1);
@@ -1220,7 +932,8 @@ int tc_grid(int64_t units) {
 }
 
 // Row partition shared by both passes: contiguous ranges of whole 128-row tiles, one per CTA.
-int tc_rows_per_cta(int64_t N, int* grid) {
+int tc_rows_per_cta(int64_t N, int H, int* grid) {
+    (void)H;      // whole 128-row tiles per CTA: a multiple of the pass-1 stage (16 or 32 nodes) for every H
     int g = tc_grid((N + kTile2 - 1) / kTile2);
     int64_t rpc = (N + g - 1) / g;
     rpc = (rpc + kTile2 - 1) / kTile2 * kTile2;
@@ -1262,118 +975,97 @@ int env_int(const char* name, int dflt) {
 }  // namespace
 
 bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D) {
-    return N >= 1 && H == kH && Hv == kH && M == kDim && D == kDim;
+    return N >= 1 && (H == 1 || H == 2 || H == 4) && Hv == H && M == kDim && D == kDim;
 }
 
+static int64_t tc_ws_len(int H) { return (SimpleLayout{H, H, kDim, kDim}.len() + 3) & ~(int64_t)3; }
+
 int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
+    (void)Hv; (void)M; (void)D;
     int grid;
-    tc_rows_per_cta(N, &grid);
-    // records + one 64-bit ready flag per CTA
-    return (int64_t)grid * SimpleLayout{H, Hv, M, D}.wsLen() * (int64_t)sizeof(float) + (int64_t)grid * 8 + 64;
+    tc_rows_per_cta(N, H, &grid);
+    // per-CTA records + one 64-bit ready flag per CTA
+    return (int64_t)grid * tc_ws_len(H) * (int64_t)sizeof(float) + (int64_t)grid * 8 + 64;
 }
 
 int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D) {
-    if (env_int("DIF_TC_P1_TMA", 1) == 0) return 0;      // only the TMA-staged pass 1 emits the operand image
-    return (H == kH && Hv == kH && M == kDim && D == kDim) ? (int64_t)kBBytes : 0;
+    return simple_tc_supported(1, H, Hv, M, D) ? (int64_t)H * 2 * kBOp : 0;
+}
+
+template <int H>
+static int launch_reduce(const ReduceArgs1& a, int grid, cudaStream_t st) {
+    DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<H>::kSmem1));
+    void* args[] = {(void*)&a};
+    // cooperative launch: the fused cross-CTA sum spins on per-CTA flags, so all CTAs must be co-resident
+    // (grid <= #SMs, 1 CTA/SM); the runtime refuses the launch otherwise instead of deadlocking
+    DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel<H>, dim3(grid), dim3(kThreadsT), args, (size_t)Geo<H>::kSmem1, st));
+    return DIF_OK;
 }
 
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
                      float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st,
                      void* const* peer_bufs, int rank, int world, unsigned long long seq) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
-    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0, DIF_EARG, "tcgen05 path: q/k/v must be 32-byte aligned");
-    int grid;
-    const int rpc = tc_rows_per_cta(N, &grid);
-    const SimpleLayout L{H, Hv, M, D};
-    DIF_REQUIRE(ws_bytes >= (int64_t)grid * L.wsLen() * 4 + (int64_t)grid * 8, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0, DIF_EARG, "tcgen05 path: q/k/v must be 16-byte aligned");
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_reduce(tcgen05): prepared buffer must be 16-byte aligned");
-    static const int use_tma = env_int("DIF_TC_P1_TMA", 1);      // 1 = TMA-staged producer (default), 0 = register-path producer
-    if (use_tma) {
-        // cooperative launch: the fused cross-CTA sum spins on per-CTA flags, so all CTAs must be co-resident
-        // (grid <= #SMs, 1 CTA/SM); the runtime refuses the launch otherwise instead of deadlocking
-        static std::atomic<unsigned long long> epoch_src{0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&epoch_src};
-        unsigned long long epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
-        DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1T));
-        uint64_t* dbg = dbg_buffer();
-        float* wsf = (float*)ws;
-        int64_t ws_len = L.wsLen();
-        unsigned long long* flags = (unsigned long long*)(wsf + (int64_t)grid * ws_len);
-        uint8_t* prep = (uint8_t*)prepared;
-        int rpc_ = rpc;
-        static const int tail_pf = env_int("DIF_TC_TAIL_PREFETCH", 0);
-        int pf_tiles = (env_int("DIF_TC_P2_VARIANT", 4) & 2) ? 0 : tail_pf;     // matches pass 2's interleaved tile order only
-        int pf_grid = tc_grid((N + kTile2 - 1) / kTile2);
-        int l2_hints = env_int("DIF_TC_P1_HINTS", 1);
-        ShardArgs sh{};
-        sh.world = 1;
-        if (peer_bufs != nullptr && world > 1) {
-            DIF_REQUIRE(world <= kShardMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_reduce(sharded): bad rank/world/seq");
-            for (int r = 0; r < world; ++r) { DIF_REQUIRE(peer_bufs[r], DIF_EARG, "simple_reduce(sharded): null peer buffer"); sh.bufs[r] = (float*)peer_bufs[r]; }
-            sh.rank = rank; sh.world = world; sh.seq = seq;
-            sh.slot_floats = (SimpleLayout{H, Hv, M, D}.len() + 63) & ~(int64_t)63;
-        }
-        static_assert(116 <= kThreadsT, "one thread per slice element");
-        void* args[] = {(void*)&q, (void*)&k, (void*)&v, (void*)&N, (void*)&rpc_, (void*)&wsf, (void*)&ws_len, (void*)&flags,
-                        (void*)&epoch, (void*)&partials, (void*)&prep, (void*)&pf_tiles, (void*)&pf_grid, (void*)&l2_hints, (void*)&sh, (void*)&dbg};
-        DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel, dim3(grid), dim3(kThreadsT), args, (size_t)kSmem1T, st));
-        dbg_report("reduce_tma", dbg, grid);
-        return DIF_OK;
+    int grid;
+    const int rpc = tc_rows_per_cta(N, H, &grid);
+    const int64_t ws_len = tc_ws_len(H);
+    DIF_REQUIRE(ws_bytes >= (int64_t)grid * ws_len * 4 + (int64_t)grid * 8, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
+    DIF_REQUIRE((((ws_len + kSlices - 1) / kSlices + 3) & ~(int64_t)3) <= kThreadsT, DIF_EUNSUPPORTED, "simple_reduce(tcgen05): slice wider than the CTA");
+    static std::atomic<unsigned long long> epoch_src{0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&epoch_src};
+    ReduceArgs1 a{};
+    a.q = q; a.k = k; a.v = v; a.N = N; a.rows_per_cta = rpc;
+    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
+    a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
+    a.partials = partials; a.prepared = (uint8_t*)prepared;
+    a.l2_hints = env_int("DIF_TC_P1_HINTS", 1);
+    a.sh.world = 1;
+    if (peer_bufs != nullptr && world > 1) {
+        DIF_REQUIRE(world <= kShardMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_reduce(sharded): bad rank/world/seq");
+        for (int r = 0; r < world; ++r) { DIF_REQUIRE(peer_bufs[r], DIF_EARG, "simple_reduce(sharded): null peer buffer"); a.sh.bufs[r] = (float*)peer_bufs[r]; }
+        a.sh.rank = rank; a.sh.world = world; a.sh.seq = seq;
+        a.sh.slot_floats = (SimpleLayout{H, Hv, M, D}.len() + 63) & ~(int64_t)63;
     }
-    DIF_REQUIRE(peer_bufs == nullptr || world <= 1, DIF_EUNSUPPORTED, "simple_reduce(sharded) needs the TMA-staged pass 1 (DIF_TC_P1_TMA=1)");
-    static const int variant = env_int("DIF_TC_P1_VARIANT", 2);   // tuning switches: 1 = register ring, 2 = K/V evict_first, 4 = Q evict_last (+ policy-hinted prefetch)
-    static const int pf = env_int("DIF_TC_P1_PREFETCH", 0);       // L2 prefetch distance in 16-row stages (0 = off)
-#define DIF_P1(R, E)                                                                                                  \
-    do {                                                                                                              \
-        DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tc_kernel<R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1)); \
-        reduce_tc_kernel<R, E><<<grid, kThreadsTC, kSmem1, st>>>(q, k, v, N, rpc, (float*)ws, L.wsLen(), pf, (variant >> 2) & 1);             \
-    } while (0)
-    switch (variant & 3) {
-        case 0: DIF_P1(false, false); break;
-        case 1: DIF_P1(true, false); break;
-        case 2: DIF_P1(false, true); break;
-        default: DIF_P1(true, true); break;
-    }
-#undef DIF_P1
+    a.dbg = dbg_buffer();
+    int rc = H == 4 ? launch_reduce<4>(a, grid, st) : H == 2 ? launch_reduce<2>(a, grid, st) : launch_reduce<1>(a, grid, st);
+    if (rc) return rc;
+    dbg_report("reduce_tma", a.dbg, grid);
+    return DIF_OK;
+}
+
+template <int MODE, int H>
+static int launch_apply(const ApplyTcArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
+    DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
+    apply_tc_kernel<MODE, H><<<grid, kThreadsTC, smem2_bytes<H>(), st>>>(a, map);
     DIF_LAUNCH_OK();
-    return simple_finalize_fwd((const float*)ws, grid, H, Hv, M, D, partials, st);
+    return DIF_OK;
 }
 
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE(((uintptr_t)q & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG, "tcgen05 path: q must be 32-byte, out 16-byte aligned");
+    DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
     ApplyTcArgs a{};
     a.q = q; a.partials = partials; a.n_total = (float)n_total; a.N = N; a.out = out;
     a.prepared = (const uint8_t*)prepared;
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_apply(tcgen05): prepared buffer must be 16-byte aligned");
     if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
-    DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
-    // tuning switches: 1 = register ring, 2 = contiguous reversed tile order (pass-1 partition), 4 = evict_first stores
-    static const int variant = env_int("DIF_TC_P2_VARIANT", 4);
-    int grid;
-    if (variant & 2) {
-        a.tiles_per_cta = tc_rows_per_cta(N, &grid) / kTile2;
-    } else {
-        a.tiles_per_cta = 0;
-        grid = tc_grid((N + kTile2 - 1) / kTile2);
-    }
-    a.store_hint = (variant & 4) ? 1 : 0;
     a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 1);
+    a.store_hint = env_int("DIF_TC_P2_STORE_HINT", 1);
     a.dbg = dbg_buffer();
+    const int grid = tc_grid((N + kTile2 - 1) / kTile2);
     CUtensorMap map;
-    int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)kH * kDim : (int64_t)kDim);
+    int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)H * kDim : (int64_t)kDim);
     if (rc) return rc;
-#define DIF_P2(MODE, R)                                                                                                    \
-    do {                                                                                                                   \
-        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));  \
-        apply_tc_kernel<MODE, R><<<grid, kThreadsTC, kSmem2, st>>>(a, map);                                                \
-    } while (0)
-    if (a.ep.mode == 0) { if (variant & 1) DIF_P2(0, true); else DIF_P2(0, false); }
-    else                { if (variant & 1) DIF_P2(1, true); else DIF_P2(1, false); }
+#define DIF_P2(MODE)                                                                                                  \
+    (H == 4 ? launch_apply<MODE, 4>(a, map, grid, st) : H == 2 ? launch_apply<MODE, 2>(a, map, grid, st) : launch_apply<MODE, 1>(a, map, grid, st))
+    rc = a.ep.mode == 0 ? DIF_P2(0) : DIF_P2(1);
 #undef DIF_P2
+    if (rc) return rc;
     dbg_report("apply_tc", a.dbg, grid);
-    DIF_LAUNCH_OK();
     return DIF_OK;
 }
 

@@ -108,9 +108,34 @@ def test_tcgen05_path_is_taken_and_matches_generic():
     with pytest.raises(Exception, match="tcgen05"):
         try:
             ops.set_simple_impl("tcgen05")
-            ops.simple_partials(q[:, :2].contiguous(), k[:, :2].contiguous(), v[:, :2].contiguous())
+            ops.simple_partials(q[:, :3].contiguous(), k[:, :3].contiguous(), v[:, :3].contiguous())   # H = 3: generic only
         finally:
             ops.set_simple_impl("auto")
+
+
+@pytest.mark.parametrize("h", [1, 2, 4])
+@pytest.mark.parametrize("n", [1, 33, 4097, 50000])
+def test_tcgen05_heads_1_2_4(h, n):
+    """The reference's own configs use num_heads = 1 (run.sh): H in {1, 2, 4} x D = 64 all take the tcgen05 kernels."""
+    q, k, v = O.synthetic_qkv(n, h, 64, seed=100 * h + n, adversarial=True)
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    try:
+        ops.set_simple_impl("tcgen05")
+        flat, prep = ops.simple_partials(qg, kg, vg, with_prepared=True)
+        out_p = ops.simple_apply(qg, flat, float(n), h, 64, prepared=prep)
+        out_f = ops.simple_apply(qg, flat, float(n), h, 64)
+        only_s = flat.clone()
+        only_s[h * 4096:h * 4096 + 2 * h * 64] = 0
+        qS = ops.simple_apply(qg, only_s, float(n), h, 64) * n
+    finally:
+        ops.set_simple_impl("auto")
+    want = O.simple_partials(q.double(), k.double(), v.double())
+    S, z, u, sq, sk = _unpack(flat, h, h, 64, 64)
+    assert O.rel_err(S, want["S"]) < 1e-4 and O.rel_err(z, want["z"]) < 1e-5 and O.rel_err(u, want["u"]) < 1e-5
+    assert abs(float(sq) / float(want["sq"]) - 1) < 1e-5 and abs(float(sk) / float(want["sk"]) - 1) < 1e-5
+    ref, parts = O.simple_apply(q.double(), want, return_parts=True)
+    assert O.rel_err(out_p, ref) < 1e-4 and O.rel_err(out_f, ref) < 1e-4
+    assert O.rel_err(qS, parts["qS"]) < 1e-4
 
 
 def test_simple_rejects_n_ne_l():
