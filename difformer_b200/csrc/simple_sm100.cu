@@ -978,7 +978,7 @@ bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D) {
     return N >= 1 && (H == 1 || H == 2 || H == 4) && Hv == H && M == kDim && D == kDim;
 }
 
-static int64_t tc_ws_len(int H) { return (SimpleLayout{H, H, kDim, kDim}.len() + 3) & ~(int64_t)3; }
+static int64_t tc_ws_len(int H) { return (SimpleLayout{H, H, kDim, kDim}.len() + 7) & ~(int64_t)7; }   // 32-byte aligned records (256-bit stores)
 
 int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
     (void)Hv; (void)M; (void)D;
