@@ -12,10 +12,13 @@ ap.add_argument("--n", type=int, default=132534)
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--impl", default="auto")
 ap.add_argument("--tag", default="")
+ap.add_argument("--h", type=int, default=4)
+ap.add_argument("--noref", action="store_true")
 a = ap.parse_args()
 ops.set_simple_impl(a.impl)
-q, k, v = (t.cuda() for t in O.synthetic_qkv(a.n, 4, 64, seed=1))
-T = a.n * 4 * 64 * 4
+H = a.h
+q, k, v = (t.cuda() for t in O.synthetic_qkv(a.n, H, 64, seed=1))
+T = a.n * H * 64 * 4
 
 
 def timeit(fn, iters):
@@ -33,18 +36,20 @@ def timeit(fn, iters):
 
 part, prep = ops.simple_partials(q, k, v, with_prepared=True)
 t_red = timeit(lambda: ops.simple_partials(q, k, v, with_prepared=True), a.iters)
-t_app = timeit(lambda: ops.simple_apply(q, part, float(a.n), 4, 64, prepared=prep), a.iters)
+t_app = timeit(lambda: ops.simple_apply(q, part, float(a.n), H, 64, prepared=prep), a.iters)
 
 
 def op():
     pp, pr = ops.simple_partials(q, k, v, with_prepared=True)
-    return ops.simple_apply(q, pp, float(a.n), 4, 64, prepared=pr)
+    return ops.simple_apply(q, pp, float(a.n), H, 64, prepared=pr)
 
 
 t_op = timeit(op, a.iters)
-print(f"{a.tag} n={a.n} reduce+finalize {t_red:7.1f} us ({3*T/t_red/1e3:6.0f} GB/s)  apply {t_app:7.1f} us ({2*T/t_app/1e3:6.0f} GB/s)  "
+print(f"{a.tag} impl={a.impl} H={H} n={a.n} reduce+finalize {t_red:7.1f} us ({3*T/t_red/1e3:6.0f} GB/s)  apply {t_app:7.1f} us ({2*T/t_app/1e3:6.0f} GB/s)  "
       f"op {t_op:7.1f} us  roofline(4T) {4*T/t_op/1e3/6571.2:5.3f}", flush=True)
 
+if a.noref:
+    sys.exit(0)
 # ---- plain-torch streaming references on the same box (what the memory system gives a trivial kernel)
 big = torch.empty(3 * a.n * 256, device="cuda").normal_()
 t_sum = timeit(lambda: big.sum(), 50)
