@@ -31,8 +31,9 @@ SIGNATURES = {
     "dif_simple_reduce": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "dif_simple_apply": (c_i32, [c_vp, c_vp, c_vp, c_f64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, ctypes.POINTER(Epilogue), c_i32, c_vp]),
     "dif_simple_bwd_partials_len": (c_i64, [c_i32] * 3),
-    "dif_simple_bwd_reduce": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
-    "dif_simple_bwd_apply": (c_i32, [c_vp] * 7 + [c_f64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dif_simple_bwd_rowscal_len": (c_i64, [c_i64, c_i32, c_i32, c_i32, c_i32]),
+    "dif_simple_bwd_reduce": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "dif_simple_bwd_apply": (c_i32, [c_vp] * 8 + [c_f64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "dif_sumsq2": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "dif_segmented_simple_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dif_segmented_simple_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32,

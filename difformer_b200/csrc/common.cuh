@@ -99,4 +99,11 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st);
 
+int64_t simple_tc_rowscal_floats(int64_t N, int H);
+int simple_bwd_reduce_tc(const float* q, const float* g, const float* out, const float* partials, double n_total,
+                         int64_t N, int H, float* bwd_partials, float* rowscal, void* ws, int64_t ws_bytes, cudaStream_t st);
+int simple_bwd_apply_tc(const float* q, const float* k, const float* v, const float* g, const float* partials, const float* bwd_partials,
+                        const float* rowscal, int64_t N, int H, float* dq, float* dk, float* dv, cudaStream_t st);
+void simple_bwd_scalars(const float* partials, float* bwd_partials, int H, int Hv, int M, int D, cudaStream_t st);
+
 }  // namespace dif

@@ -660,12 +660,26 @@ using namespace dif;
 
 extern "C" int64_t dif_simple_bwd_partials_len(int H, int M, int D) { return BwdLayout{H, M, D}.len(); }
 
+namespace dif {
+void simple_bwd_scalars(const float* partials, float* bwd_partials, int H, int Hv, int M, int D, cudaStream_t st) {
+    bwd_scalars_kernel<<<1, 1024, 0, st>>>(partials, bwd_partials, H, Hv, M, D);
+}
+}  // namespace dif
+
+// floats of per-(node, head) scratch the tcgen05 backward passes between its two calls (0: generic path only)
+extern "C" int64_t dif_simple_bwd_rowscal_len(int64_t N, int H, int Hv, int M, int D) {
+    return simple_tc_supported(N, H, Hv, M, D) ? simple_tc_rowscal_floats(N, H) : 0;
+}
+
 extern "C" int dif_simple_bwd_reduce(const float* q, const float* g, const float* out, const float* partials,
                                      double n_total, int64_t N, int H, int Hv, int M, int D,
-                                     float* bwd_partials, void* workspace, int64_t workspace_bytes, void* stream) {
+                                     float* bwd_partials, float* rowscal, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+    DIF_REQUIRE(q && g && out && partials && bwd_partials && workspace, DIF_EARG, "simple_bwd_reduce: null pointer");
+    if (impl != DIF_IMPL_GENERIC && rowscal != nullptr && simple_tc_supported(N, H, Hv, M, D))
+        return simple_bwd_reduce_tc(q, g, out, partials, n_total, N, H, bwd_partials, rowscal, workspace, workspace_bytes, (cudaStream_t)stream);
+    DIF_REQUIRE(impl != DIF_IMPL_TCGEN05, DIF_EUNSUPPORTED, "simple_bwd_reduce: tcgen05 path needs a tcgen05 shape and the rowscal buffer");
     int rc = check_shape(N, H, Hv, M, D);
     if (rc) return rc;
-    DIF_REQUIRE(q && g && out && partials && bwd_partials && workspace, DIF_EARG, "simple_bwd_reduce: null pointer");
     int rpc;
     const int chunks = reduce_chunks(N, H, &rpc);
     const BwdLayout B{H, M, D};
@@ -684,13 +698,19 @@ extern "C" int dif_simple_bwd_reduce(const float* q, const float* g, const float
 }
 
 extern "C" int dif_simple_bwd_apply(const float* q, const float* k, const float* v, const float* g, const float* out,
-                                    const float* partials, float* bwd_partials, double n_total,
+                                    const float* partials, float* bwd_partials, const float* rowscal, double n_total,
                                     int64_t N, int H, int Hv, int M, int D,
-                                    float* dq, float* dk, float* dv, void* stream) {
-    int rc = check_shape(N, H, Hv, M, D);
-    if (rc) return rc;
+                                    float* dq, float* dk, float* dv, int impl, void* stream) {
     DIF_REQUIRE(q && k && v && g && out && partials && bwd_partials && dq && dk && dv, DIF_EARG, "simple_bwd_apply: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (impl != DIF_IMPL_GENERIC && rowscal != nullptr && simple_tc_supported(N, H, Hv, M, D)) {
+        bwd_scalars_kernel<<<1, 1024, 0, st>>>(partials, bwd_partials, H, Hv, M, D);      // t_k from the (reduced) dS
+        DIF_LAUNCH_OK();
+        return simple_bwd_apply_tc(q, k, v, g, partials, bwd_partials, rowscal, N, H, dq, dk, dv, st);
+    }
+    DIF_REQUIRE(impl != DIF_IMPL_TCGEN05, DIF_EUNSUPPORTED, "simple_bwd_apply: tcgen05 path needs a tcgen05 shape and the rowscal buffer");
+    int rc = check_shape(N, H, Hv, M, D);
+    if (rc) return rc;
     bwd_scalars_kernel<<<1, 1024, 0, st>>>(partials, bwd_partials, H, Hv, M, D);
     DIF_LAUNCH_OK();
     BwdArgs a{q, k, v, g, out, partials, bwd_partials, (float)n_total, N, H, Hv, M, D, dq, dk, dv};

@@ -300,9 +300,16 @@ struct ReduceArgs1 {
     int l2_hints;
     ShardArgs sh;
     uint64_t* dbg;
+    // backward (BWD): q -> A role, g -> B role (scaled to dnum = g/den on the fly), out -> third stream
+    const float* fwd_partials;    // forward partials (S, z, u, sq, sk)
+    float n_total;
+    float* rowscal;               // [N][H][2] = (1/den, dden) per (node, head), consumed by the dq kernel
 };
 
-template <int H>
+// BWD = false: forward pass 1 (S = K^T V, z, u, norms).
+// BWD = true : backward pass 1: dS = Q^T dnum, dz = sum q dden, du = sum dnum, t_q, with
+//              den = c q.z + N, dnum = g/den, dden = -(g.out)/den computed per (node, head) from the staged rows.
+template <int H, bool BWD>
 __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_constant__ ReduceArgs1 a) {
     using G = Geo<H>;
     extern __shared__ uint8_t smem_raw[];
@@ -311,12 +318,17 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
     __shared__ uint64_t sfull[G::kNSG], sempty[G::kNSG], ofull[G::kNO], oempty[G::kNO], done, tail_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float part[16];
+    __shared__ __align__(16) float szc[BWD ? H * kDim : 4], su[BWD ? H * kDim : 4];   // BWD: c*z[h][m], u[h][d]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
     const int64_t r1 = min(a.N, r0 + (int64_t)a.rows_per_cta);
     const int iters = r1 > r0 ? (int)((r1 - r0 + G::kNodes - 1) / G::kNodes) : 0;
     uint64_t* dbg = a.dbg;
     DIF_STAMP(dbg, 0);
+    if (BWD) {
+        const float c = 1.f / (sqrtf(a.fwd_partials[G::offSq]) * sqrtf(a.fwd_partials[G::offSq + 1]));
+        for (int i = tid; i < H * kDim; i += kThreadsT) { szc[i] = a.fwd_partials[G::offZ + i] * c; su[i] = a.fwd_partials[G::offU + i]; }
+    }
 
     if (tid == 0) {
         for (int s = 0; s < G::kNSG; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); }
@@ -365,17 +377,49 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                 const uint32_t off = (uint32_t)(blk * G::kBlockTile + (kn >> 3) * 1024 + (kn & 7) * 128 +
                                                 ((((m >> 3) ^ kn) & 7) << 4) + ((m >> 2) & 1) * 8);
                 uint32_t hi[2], lo[2];
-                split4(x[i][0], hi, lo);
-                sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
-                sts64(ob + 1 * G::kOp + off, lo[0], lo[1]);
-                split4(x[i][1], hi, lo);
-                sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
-                sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
-                const float4 kk = x[i][0], vv = x[i][1], qq = x[i][2];
-                zacc[0] += kk.x; zacc[1] += kk.y; zacc[2] += kk.z; zacc[3] += kk.w;
-                uacc[0] += vv.x; uacc[1] += vv.y; uacc[2] += vv.z; uacc[3] += vv.w;
-                ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
-                ssq = fmaf(qq.x, qq.x, ssq); ssq = fmaf(qq.y, qq.y, ssq); ssq = fmaf(qq.z, qq.z, ssq); ssq = fmaf(qq.w, qq.w, ssq);
+                if (!BWD) {
+                    split4(x[i][0], hi, lo);
+                    sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
+                    sts64(ob + 1 * G::kOp + off, lo[0], lo[1]);
+                    split4(x[i][1], hi, lo);
+                    sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
+                    sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
+                    const float4 kk = x[i][0], vv = x[i][1], qq = x[i][2];
+                    zacc[0] += kk.x; zacc[1] += kk.y; zacc[2] += kk.z; zacc[3] += kk.w;
+                    uacc[0] += vv.x; uacc[1] += vv.y; uacc[2] += vv.z; uacc[3] += vv.w;
+                    ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
+                    ssq = fmaf(qq.x, qq.x, ssq); ssq = fmaf(qq.y, qq.y, ssq); ssq = fmaf(qq.z, qq.z, ssq); ssq = fmaf(qq.w, qq.w, ssq);
+                } else {
+                    // x[i][0] = q, x[i][1] = g, x[i][2] = out : 4 columns of (node, head); the 16 lanes of a
+                    // (node, head) are consecutive -> xor-shuffle reductions inside the 16-lane group
+                    const float4 qq = x[i][0], gg = x[i][1], oo = x[i][2];
+                    const float4 zc4 = *reinterpret_cast<const float4*>(szc + cc * 4), u4 = *reinterpret_cast<const float4*>(su + cc * 4);
+                    float qz = qq.x * zc4.x + qq.y * zc4.y + qq.z * zc4.z + qq.w * zc4.w;
+                    float go = gg.x * oo.x + gg.y * oo.y + gg.z * oo.z + gg.w * oo.w;
+                    float gu = gg.x * u4.x + gg.y * u4.y + gg.z * u4.z + gg.w * u4.w;
+#pragma unroll
+                    for (int sh_ = 1; sh_ < 16; sh_ <<= 1) {
+                        qz += __shfl_xor_sync(0xffffffffu, qz, sh_);
+                        go += __shfl_xor_sync(0xffffffffu, go, sh_);
+                        gu += __shfl_xor_sync(0xffffffffu, gu, sh_);
+                    }
+                    const float inv = 1.f / (qz + a.n_total), dden = -go * inv;
+                    const float4 dn = make_float4(gg.x * inv, gg.y * inv, gg.z * inv, gg.w * inv);
+                    split4(qq, hi, lo);
+                    sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
+                    sts64(ob + 1 * G::kOp + off, lo[0], lo[1]);
+                    split4(dn, hi, lo);
+                    sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
+                    sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
+                    zacc[0] = fmaf(qq.x, dden, zacc[0]); zacc[1] = fmaf(qq.y, dden, zacc[1]);
+                    zacc[2] = fmaf(qq.z, dden, zacc[2]); zacc[3] = fmaf(qq.w, dden, zacc[3]);
+                    uacc[0] += dn.x; uacc[1] += dn.y; uacc[2] += dn.z; uacc[3] += dn.w;
+                    if ((cc & 15) == 0 && node < nrows) {
+                        ssq += go - inv * gu + dden * qz;           // t_q contribution of this (node, head)
+                        const int64_t row = r0 + (int64_t)it * G::kNodes + node;
+                        *reinterpret_cast<float2*>(a.rowscal + (row * H + head) * 2) = make_float2(inv, dden);
+                    }
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -456,8 +500,8 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
     if (tid == 0) {
         float sk = 0.f, sq = 0.f;
         for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
-        rec[G::offSq] = sq;
-        rec[G::offSq + 1] = sk;
+        rec[G::offSq] = sq;                  // fwd: sum q^2 ; bwd: t_q
+        rec[G::offSq + 1] = BWD ? 0.f : sk;  // fwd: sum k^2 ; bwd: t_k is filled in later (needs the reduced dS)
         for (int64_t i = G::kP; i < a.ws_len; ++i) rec[i] = 0.f;
     }
     __syncthreads();                                   // `red` is re-used below (H == 1)
@@ -594,7 +638,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
         }
         if (live) {
             a.partials[j] = sum;
-            if (a.prepared != nullptr && j < G::offU) {
+            if (!BWD && a.prepared != nullptr && j < G::offU) {
                 // B operand image of pass 2 (un-scaled; pass 2 applies c = 1/(|Q||K|) in its epilogue):
                 // S[h][m][d] -> row n = d, k = m of head h ; z[h][m] -> row 64
                 int h, n, m;
@@ -608,7 +652,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
             }
         }
     }
-    if (a.prepared != nullptr && blockIdx.x == grid - 1) {
+    if (!BWD && a.prepared != nullptr && blockIdx.x == grid - 1) {
         // rows 65..79 of every (head, hi|lo) tile are zero padding (N = 80 of the pass-2 UMMA)
         for (int i = tid; i < H * 2 * 15 * 8; i += kThreadsT) {
             const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
@@ -903,6 +947,243 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
     if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// backward pass 2: three streaming contractions with the same skeleton as apply_tc_kernel
+//   KIND 0  dq = c (dnum S^T + dden z) - q t_q / sum q^2     A = g * (1/den)   B[n=m][k=d] = c S      rows from q
+//   KIND 1  dk = c (v dS^T + dz)       - k t_k / sum k^2     A = v             B[n=m][k=d] = c dS     rows from k
+//   KIND 2  dv = c  k dS + du                                A = k             B[n=d][k=m] = c dS^T
+// ------------------------------------------------------------------------------------------
+constexpr int kBOpB = 64 * 128;                       // one (head, hi|lo) B tile: 64 rows x 128 B
+template <int H>
+constexpr int smem_bwd_bytes() { return H * 2 * kBOpB + kNS2 * kStage2 + kOutStage + H * kDim * 4 + 1024; }
+
+struct BwdTcArgs {
+    const float* a_src;      // streamed into the A operand: g | v | k        [N,H,64]
+    const float* e_src;      // epilogue row source: q | k | nullptr          [N,H,64]
+    const float* rowscal;    // KIND 0: (1/den, dden) per (node, head)
+    const float* fwd;        // forward partials  [S | z | u | sq | sk]
+    const float* bwd;        // backward partials [dS | dz | du | t_q | t_k]
+    int64_t N;
+    float* out;
+    int pf_tiles, store_hint;
+};
+
+template <int KIND, int H>
+__global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __grid_constant__ BwdTcArgs p, const __grid_constant__ CUtensorMap out_map) {
+    using G = Geo<H>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* Bop = base;                                             // [h][hi|lo][64 rows][128 B]
+    uint8_t* stages = base + H * 2 * kBOpB;
+    uint8_t* ostage = stages + kNS2 * kStage2;
+    float* vec = reinterpret_cast<float*>(ostage + kOutStage);       // [H][64]: c z | c dz | du
+    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
+    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const int nsc = my_tiles * H;
+    auto tile_of = [&](int sc) -> int64_t { return blockIdx.x + (int64_t)(sc / H) * gridDim.x; };
+
+    if (tid == 32 && my_tiles > 0) {
+        for (int i = 0; i < 2 && i < my_tiles; ++i) {
+            const int64_t prow = tile_of(H * i) * kTile2;
+            const int64_t nrows = min((int64_t)kTile2, p.N - prow);
+            for (int64_t r = 0; r < nrows; r += 16)
+                prefetch_l2(p.a_src + (prow + r) * G::kRowF, (uint32_t)(min((int64_t)16, nrows - r) * G::kRowB));
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(&tmem_slot, 512);
+
+    const float sq = p.fwd[G::offSq], sk = p.fwd[G::offSq + 1];
+    const float c = 1.f / (sqrtf(sq) * sqrtf(sk));
+    // coefficient of the epilogue row source: -t_q/sum q^2 (dq), -t_k/sum k^2 (dk)
+    const float escale = KIND == 0 ? -p.bwd[G::offSq] / sq : (KIND == 1 ? -p.bwd[G::offSq + 1] / sk : 0.f);
+    {
+        // ---- B operands (K-major SW128, bf16 hi/lo, pre-scaled by c): row n, k-chunk ch
+        const float* mat = KIND == 0 ? p.fwd : p.bwd;
+        constexpr int kTasks = H * 8 * kDim, kPer = (kTasks + kThreadsTC - 1) / kThreadsTC;
+        float x[kPer][8];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int task = tid + u * kThreadsTC;
+            const int n = task % kDim, hc = task / kDim, ch = hc & 7, h = hc >> 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kk = ch * 8 + i;
+                x[u][i] = 0.f;
+                if (task < kTasks)
+                    x[u][i] = KIND == 2 ? __ldg(mat + ((int64_t)h * kDim + kk) * kDim + n)      // B[n=d][k=m] = dS[m][d]
+                                        : __ldg(mat + ((int64_t)h * kDim + n) * kDim + kk);     // B[n=m][k=d] = (d)S[m][d]
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int task = tid + u * kThreadsTC;
+            if (task < kTasks) {
+                const int n = task % kDim, hc = task / kDim, ch = hc & 7, h = hc >> 3;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[u][i] *= c;
+                uint4 hi, lo;
+                split8(x[u], hi, lo);
+                const uint32_t off = (uint32_t)(h * 2 * kBOpB) + sw128(n, ch);
+                sts128(smem_u32(Bop) + off, hi);
+                sts128(smem_u32(Bop) + kBOpB + off, lo);
+            }
+        }
+        for (int i = tid; i < H * kDim; i += kThreadsTC)
+            vec[i] = KIND == 0 ? p.fwd[G::offZ + i] * c : (KIND == 1 ? p.bwd[G::offZ + i] * c : p.bwd[G::offU + i]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ===== A producers (see apply_tc_kernel); KIND 0 scales the g rows by 1/den of their (node, head)
+        float buf[2][4][8];
+        auto issue = [&](int sc, int j, float (&dst)[8]) {
+            if (sc >= nsc) return;
+            const int64_t tile = tile_of(sc);
+            const int t = tid + 256 * j, h = sc % H;
+            const int64_t row = tile * kTile2 + (t >> 3);
+            if (row < p.N) {
+                ldg256_stream(p.a_src + row * G::kRowF + h * kDim + (t & 7) * 8, dst);
+                if (KIND == 0) {
+                    const float inv = __ldg(p.rowscal + (row * H + h) * 2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] *= inv;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = 0.f;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(0, j, buf[0][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
+        const uint32_t stage_base = smem_u32(stages);
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int s = sc % kNS2;
+            if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+            const uint32_t sb = stage_base + s * kStage2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                uint4 hi, lo;
+                split8(buf[0][j], hi, lo);
+                const uint32_t off = sw128(t >> 3, t & 7);
+                sts128(sb + off, hi);
+                sts128(sb + kQOp + off, lo);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
+                issue(sc + 2, j, buf[1][j]);
+            }
+        }
+    } else if (warp < 12) {
+        // ===== epilogue: thread = one row; out = acc + vec (+ dden vec for dq) + escale * row source
+        const int ew = warp - 8;
+        const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
+        const uint64_t pol = policy_evict_first();
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int64_t tile = tile_of(sc);
+            const int h = sc % H, slot = sc % kNAcc;
+            const int64_t row = tile * kTile2 + ew * 32 + lane;
+            const bool ok = row < p.N;
+            float vmul = 1.f;
+            if (KIND == 0) vmul = ok ? __ldg(p.rowscal + (row * H + h) * 2 + 1) : 0.f;     // dden
+            mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
+            if (lane == 0) tma_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int c0 = 0; c0 < kDim; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait32(r);
+                if (c0 == 32) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[slot]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(vec + h * kDim + c0 + j);
+                    float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (KIND != 2 && ok) e4 = ldg4(p.e_src + (row * H + h) * kDim + c0 + j);
+                    float4 o;
+                    o.x = fmaf(e4.x, escale, fmaf(v4.x, vmul, __uint_as_float(r[j])));
+                    o.y = fmaf(e4.y, escale, fmaf(v4.y, vmul, __uint_as_float(r[j + 1])));
+                    o.z = fmaf(e4.z, escale, fmaf(v4.z, vmul, __uint_as_float(r[j + 2])));
+                    o.w = fmaf(e4.w, escale, fmaf(v4.w, vmul, __uint_as_float(r[j + 3])));
+                    sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
+                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int col = h * kDim, row0 = (int)(tile * kTile2) + ew * 32;
+                if (p.store_hint) {
+                    tma_store_2d_hint(&out_map, obox, col, row0, pol);
+                    tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
+                } else {
+                    tma_store_2d(&out_map, obox, col, row0);
+                    tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
+                }
+                tma_commit();
+            }
+        }
+        if (lane == 0) tma_wait_all0();
+    } else if (lane == 0) {
+        // ===== MMA issuer: M=128, N=64, K=64: 4 K-steps x (hi*hi + lo*hi + hi*lo)
+        const uint32_t idesc = make_idesc(kTile2, kDim, 0, 0);
+        const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
+            if (p.pf_tiles > 0 && h == 0 && sc + H * p.pf_tiles < nsc) {
+                const int64_t prow = tile_of(sc + H * p.pf_tiles) * kTile2;
+                const int64_t nrows = min((int64_t)kTile2, p.N - prow);
+                for (int64_t r = 0; r < nrows; r += 16)
+                    prefetch_l2(p.a_src + (prow + r) * G::kRowF, (uint32_t)(min((int64_t)16, nrows - r) * G::kRowB));
+            }
+            if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+            mbar_wait(&full[s], (sc / kNS2) & 1);
+            tc_fence_after();
+            const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOpB;
+            const uint32_t d = tmem + slot * kAccCols;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ahi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), alo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOpB + ks * 32, kKmajLBO, kKmajSBO);
+                umma(d, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
+                umma(d, alo, bhi, idesc, 1u);
+                umma(d, ahi, blo, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+            umma_commit(&tfull[slot]);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -992,13 +1273,13 @@ int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D) {
     return simple_tc_supported(1, H, Hv, M, D) ? (int64_t)H * 2 * kBOp : 0;
 }
 
-template <int H>
+template <int H, bool BWD>
 static int launch_reduce(const ReduceArgs1& a, int grid, cudaStream_t st) {
-    DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<H>::kSmem1));
+    DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel<H, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<H>::kSmem1));
     void* args[] = {(void*)&a};
     // cooperative launch: the fused cross-CTA sum spins on per-CTA flags, so all CTAs must be co-resident
     // (grid <= #SMs, 1 CTA/SM); the runtime refuses the launch otherwise instead of deadlocking
-    DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel<H>, dim3(grid), dim3(kThreadsT), args, (size_t)Geo<H>::kSmem1, st));
+    DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)reduce_tma_kernel<H, BWD>, dim3(grid), dim3(kThreadsT), args, (size_t)Geo<H>::kSmem1, st));
     return DIF_OK;
 }
 
@@ -1028,7 +1309,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
         a.sh.slot_floats = (SimpleLayout{H, Hv, M, D}.len() + 63) & ~(int64_t)63;
     }
     a.dbg = dbg_buffer();
-    int rc = H == 4 ? launch_reduce<4>(a, grid, st) : H == 2 ? launch_reduce<2>(a, grid, st) : launch_reduce<1>(a, grid, st);
+    int rc = H == 4 ? launch_reduce<4, false>(a, grid, st) : H == 2 ? launch_reduce<2, false>(a, grid, st) : launch_reduce<1, false>(a, grid, st);
     if (rc) return rc;
     dbg_report("reduce_tma", a.dbg, grid);
     return DIF_OK;
@@ -1067,6 +1348,70 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     if (rc) return rc;
     dbg_report("apply_tc", a.dbg, grid);
     return DIF_OK;
+}
+
+// ---- backward on the tensor cores -------------------------------------------------------------
+int64_t simple_tc_rowscal_floats(int64_t N, int H) { return N * H * 2; }
+
+int simple_bwd_reduce_tc(const float* q, const float* g, const float* out, const float* partials, double n_total,
+                         int64_t N, int H, float* bwd_partials, float* rowscal, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    DIF_REQUIRE(simple_tc_supported(N, H, H, kDim, kDim), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)g | (uintptr_t)out) & 15) == 0 && ((uintptr_t)rowscal & 7) == 0, DIF_EARG, "tcgen05 bwd: misaligned pointer");
+    int grid;
+    const int rpc = tc_rows_per_cta(N, H, &grid);
+    const int64_t ws_len = tc_ws_len(H);
+    DIF_REQUIRE(ws_bytes >= (int64_t)grid * ws_len * 4 + (int64_t)grid * 8, DIF_EARG, "simple_bwd_reduce(tcgen05): workspace too small");
+    static std::atomic<unsigned long long> epoch_src{0xD1B54A32D192ED03ull ^ (unsigned long long)(uintptr_t)&epoch_src};
+    ReduceArgs1 a{};
+    a.k = q; a.v = g; a.q = out;                // roles: A <- q, B <- g (-> dnum), third stream <- out
+    a.N = N; a.rows_per_cta = rpc;
+    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
+    a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
+    a.partials = bwd_partials; a.prepared = nullptr;
+    a.l2_hints = 0;
+    a.sh.world = 1;
+    a.fwd_partials = partials; a.n_total = (float)n_total; a.rowscal = rowscal;
+    a.dbg = nullptr;
+    return H == 4 ? launch_reduce<4, true>(a, grid, st) : H == 2 ? launch_reduce<2, true>(a, grid, st) : launch_reduce<1, true>(a, grid, st);
+}
+
+template <int KIND, int H>
+static int launch_bwd_apply(const BwdTcArgs& a, int grid, cudaStream_t st) {
+    CUtensorMap map;
+    int rc = make_out_map(&map, a.out, a.N, (int64_t)H * kDim);
+    if (rc) return rc;
+    DIF_CUDA_OK(cudaFuncSetAttribute(bwd_apply_tc_kernel<KIND, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd_bytes<H>()));
+    bwd_apply_tc_kernel<KIND, H><<<grid, kThreadsTC, smem_bwd_bytes<H>(), st>>>(a, map);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+template <int H>
+static int bwd_apply_all(BwdTcArgs a, const float* q, const float* k, const float* v, const float* g, float* dq, float* dk, float* dv,
+                         int grid, cudaStream_t st) {
+    int rc;
+    a.a_src = g; a.e_src = q; a.out = dq;
+    if ((rc = launch_bwd_apply<0, H>(a, grid, st))) return rc;
+    a.a_src = v; a.e_src = k; a.out = dk;
+    if ((rc = launch_bwd_apply<1, H>(a, grid, st))) return rc;
+    a.a_src = k; a.e_src = nullptr; a.out = dv;
+    return launch_bwd_apply<2, H>(a, grid, st);
+}
+
+int simple_bwd_apply_tc(const float* q, const float* k, const float* v, const float* g, const float* partials, const float* bwd_partials,
+                        const float* rowscal, int64_t N, int H, float* dq, float* dk, float* dv, cudaStream_t st) {
+    DIF_REQUIRE(simple_tc_supported(N, H, H, kDim, kDim), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)g) & 31) == 0 && (((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+                DIF_EARG, "tcgen05 bwd: misaligned pointer");
+    BwdTcArgs a{};
+    a.rowscal = rowscal; a.fwd = partials; a.bwd = bwd_partials; a.N = N;
+    a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 1);
+    a.store_hint = env_int("DIF_TC_P2_STORE_HINT", 1);
+    const int grid = tc_grid((N + kTile2 - 1) / kTile2);
+    return H == 4 ? bwd_apply_all<4>(a, q, k, v, g, dq, dk, dv, grid, st)
+         : H == 2 ? bwd_apply_all<2>(a, q, k, v, g, dq, dk, dv, grid, st)
+                  : bwd_apply_all<1>(a, q, k, v, g, dq, dk, dv, grid, st);
 }
 
 }  // namespace dif

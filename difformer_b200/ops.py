@@ -155,10 +155,13 @@ class _SimpleAttention(torch.autograd.Function):
         bwd = torch.zeros(lib.dif_simple_bwd_partials_len(H, M, D), dtype=torch.float32, device=dev)
         ws = torch.empty(max(int(lib.dif_simple_workspace_bytes(N, H, Hv, M, D)), 16), dtype=torch.uint8, device=dev)
         dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
+        rsl = int(lib.dif_simple_bwd_rowscal_len(N, H, Hv, M, D)) if _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC else 0
+        rowscal = torch.empty(rsl, dtype=torch.float32, device=dev) if rsl > 0 else None    # tcgen05 backward scratch
+        rs_ptr = None if rowscal is None else rowscal.data_ptr()
         with torch.cuda.device(dev):
             st = _stream(qs)
             check(lib.dif_simple_bwd_reduce(qs.data_ptr(), g.data_ptr(), out.data_ptr(), partials.data_ptr(), ctx.n_tot,
-                                            N, H, Hv, M, D, bwd.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                                            N, H, Hv, M, D, bwd.data_ptr(), rs_ptr, ws.data_ptr(), ws.numel(), _SIMPLE_IMPL, st),
                   "dif_simple_bwd_reduce")
             xch = getattr(ctx.group, "exchange", None)
             if xch is not None:
@@ -169,8 +172,8 @@ class _SimpleAttention(torch.autograd.Function):
             else:
                 _allreduce(bwd, ctx.group)
             check(lib.dif_simple_bwd_apply(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
-                                           partials.data_ptr(), bwd.data_ptr(), ctx.n_tot, N, H, Hv, M, D,
-                                           dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), st),
+                                           partials.data_ptr(), bwd.data_ptr(), rs_ptr, ctx.n_tot, N, H, Hv, M, D,
+                                           dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _SIMPLE_IMPL, st),
                   "dif_simple_bwd_apply")
         return dq, dk, dv, None, None
 

@@ -99,13 +99,17 @@ DIF_API int dif_simple_apply(const float* q, const float* partials, const void* 
  *   t_k is filled by dif_simple_bwd_apply after any all-reduce). `out` is the saved forward
  *   output [N,H,D], `g` = dL/dout. */
 DIF_API int64_t dif_simple_bwd_partials_len(int H, int M, int D);
+/* `rowscal`: dif_simple_bwd_rowscal_len() floats of caller-owned scratch ((1/den, dden) per (node, head)) that the
+ * tcgen05 backward hands from its pass 1 to its pass 2; NULL (or len 0) selects the FFMA kernels. */
+DIF_API int64_t dif_simple_bwd_rowscal_len(int64_t N, int H, int Hv, int M, int D);
 DIF_API int dif_simple_bwd_reduce(const float* q, const float* g, const float* out, const float* partials,
                           double n_total, int64_t N, int H, int Hv, int M, int D,
-                          float* bwd_partials, void* workspace, int64_t workspace_bytes, void* stream);
+                          float* bwd_partials, float* rowscal, void* workspace, int64_t workspace_bytes,
+                          int impl, void* stream);
 DIF_API int dif_simple_bwd_apply(const float* q, const float* k, const float* v, const float* g, const float* out,
-                         const float* partials, float* bwd_partials, double n_total,
+                         const float* partials, float* bwd_partials, const float* rowscal, double n_total,
                          int64_t N, int H, int Hv, int M, int D,
-                         float* dq, float* dk, float* dv, void* stream);
+                         float* dq, float* dk, float* dv, int impl, void* stream);
 
 /* Batched-graph 'simple' (TransConv.full_attention, difformer-v2.py:80-111): rows are grouped in
  * B contiguous segments seg_ptr[0..B] (int32, device; seg_ptr[B] == N).  Normalisation by n_g per

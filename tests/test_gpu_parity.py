@@ -138,6 +138,28 @@ def test_tcgen05_heads_1_2_4(h, n):
     assert O.rel_err(qS, parts["qS"]) < 1e-4
 
 
+@pytest.mark.parametrize("h", [1, 2, 4])
+@pytest.mark.parametrize("n", [77, 5001])
+def test_tcgen05_backward(h, n):
+    """Backward on the tensor cores (reduce_tma_kernel<BWD> + bwd_apply_tc_kernel x3) vs the fp64 analytic oracle
+    and vs the FFMA kernels."""
+    q, k, v = O.synthetic_qkv(n, h, 64, seed=7 * h + n, adversarial=True)
+    g = torch.randn(n, h, 64, generator=torch.Generator().manual_seed(n))
+    grads = {}
+    for impl_ in ("tcgen05", "generic"):
+        try:
+            ops.set_simple_impl(impl_)
+            qg, kg, vg = (dev(t).requires_grad_(True) for t in (q, k, v))
+            difformer.full_attention_conv(qg, kg, vg, "simple").backward(dev(g))
+            grads[impl_] = (qg.grad, kg.grad, vg.grad)
+        finally:
+            ops.set_simple_impl("auto")
+    want = O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())
+    for a_, b_, w in zip(grads["tcgen05"], grads["generic"], want):
+        assert O.rel_err(a_, w) < TOL
+        assert O.rel_err(a_, b_) < 1e-4
+
+
 def test_simple_rejects_n_ne_l():
     q = torch.randn(10, 1, 64, device="cuda")
     with pytest.raises(ValueError, match="N == L"):
