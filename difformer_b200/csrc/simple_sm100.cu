@@ -193,6 +193,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// TMA 2-D tensor load: global box -> shared (128B-swizzled), completion on an mbarrier (rows beyond the tensor are zero-filled)
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                         go += __shfl_xor_sync(0xffffffffu, go, sh_);
                         gu += __shfl_xor_sync(0xffffffffu, gu, sh_);
                     }
-                    const float inv = 1.f / (qz + a.n_total), dden = -go * inv;
+                    const float inv = __frcp_rn(qz + a.n_total), dden = -go * inv;
                     const float4 dn = make_float4(gg.x * inv, gg.y * inv, gg.z * inv, gg.w * inv);
                     split4(qq, hi, lo);
                     sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
@@ -969,7 +974,8 @@ struct BwdTcArgs {
 };
 
 template <int KIND, int H>
-__global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __grid_constant__ BwdTcArgs p, const __grid_constant__ CUtensorMap out_map) {
+__global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __grid_constant__ BwdTcArgs p, const __grid_constant__ CUtensorMap out_map,
+                                                                         const __grid_constant__ CUtensorMap e_map) {
     using G = Geo<H>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -977,7 +983,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
     uint8_t* stages = base + H * 2 * kBOpB;
     uint8_t* ostage = stages + kNS2 * kStage2;
     float* vec = reinterpret_cast<float*>(ostage + kOutStage);       // [H][64]: c z | c dz | du
-    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc];
+    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], ebar[4];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
@@ -996,6 +1002,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
     if (tid == 0) {
         for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
         for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 4; ++s) mbar_init(&ebar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 12) tmem_alloc(&tmem_slot, 512);
@@ -1094,7 +1101,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
             }
         }
     } else if (warp < 12) {
-        // ===== epilogue: thread = one row; out = acc + vec (+ dden vec for dq) + escale * row source
+        // ===== epilogue: thread = one row; out = acc + vec (x dden for dq) + escale * row source.  The row source
+        // (q or k rows of this tile/head) is TMA-loaded into the swizzled staging boxes, combined in place and the
+        // boxes are TMA-stored: no scattered global access on the LSU in either direction.
         const int ew = warp - 8;
         const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
         const uint64_t pol = policy_evict_first();
@@ -1103,13 +1112,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
             const int h = sc % H, slot = sc % kNAcc;
             const int64_t row = tile * kTile2 + ew * 32 + lane;
             const bool ok = row < p.N;
+            const int col = h * kDim, row0 = (int)(tile * kTile2) + ew * 32;
+            if (lane == 0) {
+                tma_wait_read0();                         // the previous store has finished reading the boxes
+                if (KIND != 2) {
+                    mbar_expect_tx(&ebar[ew], 2 * kOutBox);
+                    tma_load_2d(obox, &e_map, col, row0, &ebar[ew]);
+                    tma_load_2d(obox + kOutBox, &e_map, col + 32, row0, &ebar[ew]);
+                }
+            }
+            __syncwarp();
             float vmul = 1.f;
             if (KIND == 0) vmul = ok ? __ldg(p.rowscal + (row * H + h) * 2 + 1) : 0.f;     // dden
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
-            if (lane == 0) tma_wait_read0();
-            __syncwarp();
+            if (KIND != 2) mbar_wait(&ebar[ew], sc & 1);
 #pragma unroll
             for (int c0 = 0; c0 < kDim; c0 += 32) {
                 uint32_t r[32];
@@ -1123,21 +1141,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 v4 = *reinterpret_cast<const float4*>(vec + h * kDim + c0 + j);
+                    const uint32_t saddr = obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2);
                     float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (KIND != 2 && ok) e4 = ldg4(p.e_src + (row * H + h) * kDim + c0 + j);
+                    if (KIND != 2) e4 = lds128(saddr);
                     float4 o;
                     o.x = fmaf(e4.x, escale, fmaf(v4.x, vmul, __uint_as_float(r[j])));
                     o.y = fmaf(e4.y, escale, fmaf(v4.y, vmul, __uint_as_float(r[j + 1])));
                     o.z = fmaf(e4.z, escale, fmaf(v4.z, vmul, __uint_as_float(r[j + 2])));
                     o.w = fmaf(e4.w, escale, fmaf(v4.w, vmul, __uint_as_float(r[j + 3])));
-                    sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
-                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                    sts128(saddr, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
                 }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                const int col = h * kDim, row0 = (int)(tile * kTile2) + ew * 32;
                 if (p.store_hint) {
                     tma_store_2d_hint(&out_map, obox, col, row0, pol);
                     tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
@@ -1377,11 +1394,12 @@ int simple_bwd_reduce_tc(const float* q, const float* g, const float* out, const
 
 template <int KIND, int H>
 static int launch_bwd_apply(const BwdTcArgs& a, int grid, cudaStream_t st) {
-    CUtensorMap map;
+    CUtensorMap map, emap;
     int rc = make_out_map(&map, a.out, a.N, (int64_t)H * kDim);
     if (rc) return rc;
+    if ((rc = make_out_map(&emap, const_cast<float*>(a.e_src ? a.e_src : a.a_src), a.N, (int64_t)H * kDim))) return rc;
     DIF_CUDA_OK(cudaFuncSetAttribute(bwd_apply_tc_kernel<KIND, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd_bytes<H>()));
-    bwd_apply_tc_kernel<KIND, H><<<grid, kThreadsTC, smem_bwd_bytes<H>(), st>>>(a, map);
+    bwd_apply_tc_kernel<KIND, H><<<grid, kThreadsTC, smem_bwd_bytes<H>(), st>>>(a, map, emap);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }
