@@ -29,6 +29,8 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -1205,8 +1207,30 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// fp32 [rows][cols] row-major tensor, box = 32 rows x 32 floats (128 B), 128B swizzle
+// fp32 [rows][cols] row-major tensor, box = 32 rows x 32 floats (128 B), 128B swizzle.
+// cuTensorMapEncodeTiled is a driver call (tens of microseconds): encoded maps are cached per (base, rows, cols) --
+// the caching allocator hands the same addresses back every step, so steady-state calls do not encode at all.
+int make_out_map_uncached(CUtensorMap* map, float* base, int64_t rows, int64_t cols);
+
 int make_out_map(CUtensorMap* map, float* base, int64_t rows, int64_t cols) {
+    struct Key { float* b; int64_t r, c; };
+    struct Entry { Key k; CUtensorMap m; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Entry& e : cache)
+            if (e.k.b == base && e.k.r == rows && e.k.c == cols) { *map = e.m; return DIF_OK; }
+    }
+    int rc = make_out_map_uncached(map, base, rows, cols);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() >= 64) cache.erase(cache.begin());
+    cache.push_back(Entry{Key{base, rows, cols}, *map});
+    return DIF_OK;
+}
+
+int make_out_map_uncached(CUtensorMap* map, float* base, int64_t rows, int64_t cols) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* f = nullptr;
@@ -1292,7 +1316,11 @@ int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D) {
 
 template <int H, bool BWD>
 static int launch_reduce(const ReduceArgs1& a, int grid, cudaStream_t st) {
-    DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel<H, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<H>::kSmem1));
+    static bool attr_set = false;       // per (H, BWD) instantiation
+    if (!attr_set) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(reduce_tma_kernel<H, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<H>::kSmem1));
+        attr_set = true;
+    }
     void* args[] = {(void*)&a};
     // cooperative launch: the fused cross-CTA sum spins on per-CTA flags, so all CTAs must be co-resident
     // (grid <= #SMs, 1 CTA/SM); the runtime refuses the launch otherwise instead of deadlocking
@@ -1317,7 +1345,8 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
     a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
     a.partials = partials; a.prepared = (uint8_t*)prepared;
-    a.l2_hints = env_int("DIF_TC_P1_HINTS", 1);
+    static const int hints = env_int("DIF_TC_P1_HINTS", 1);
+    a.l2_hints = hints;
     a.sh.world = 1;
     if (peer_bufs != nullptr && world > 1) {
         DIF_REQUIRE(world <= kShardMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_reduce(sharded): bad rank/world/seq");
@@ -1334,7 +1363,11 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
 
 template <int MODE, int H>
 static int launch_apply(const ApplyTcArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
-    DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
+    static bool attr_set = false;
+    if (!attr_set) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
+        attr_set = true;
+    }
     apply_tc_kernel<MODE, H><<<grid, kThreadsTC, smem2_bytes<H>(), st>>>(a, map);
     DIF_LAUNCH_OK();
     return DIF_OK;
@@ -1351,8 +1384,9 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_apply(tcgen05): prepared buffer must be 16-byte aligned");
     if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
-    a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 1);
-    a.store_hint = env_int("DIF_TC_P2_STORE_HINT", 1);
+    static const int pf = env_int("DIF_TC_P2_PREFETCH", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1);
+    a.pf_tiles = pf;
+    a.store_hint = sth;
     a.dbg = dbg_buffer();
     const int grid = tc_grid((N + kTile2 - 1) / kTile2);
     CUtensorMap map;
@@ -1398,7 +1432,11 @@ static int launch_bwd_apply(const BwdTcArgs& a, int grid, cudaStream_t st) {
     int rc = make_out_map(&map, a.out, a.N, (int64_t)H * kDim);
     if (rc) return rc;
     if ((rc = make_out_map(&emap, const_cast<float*>(a.e_src ? a.e_src : a.a_src), a.N, (int64_t)H * kDim))) return rc;
-    DIF_CUDA_OK(cudaFuncSetAttribute(bwd_apply_tc_kernel<KIND, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd_bytes<H>()));
+    static bool attr_set = false;
+    if (!attr_set) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(bwd_apply_tc_kernel<KIND, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd_bytes<H>()));
+        attr_set = true;
+    }
     bwd_apply_tc_kernel<KIND, H><<<grid, kThreadsTC, smem_bwd_bytes<H>(), st>>>(a, map, emap);
     DIF_LAUNCH_OK();
     return DIF_OK;
@@ -1424,8 +1462,9 @@ int simple_bwd_apply_tc(const float* q, const float* k, const float* v, const fl
                 DIF_EARG, "tcgen05 bwd: misaligned pointer");
     BwdTcArgs a{};
     a.rowscal = rowscal; a.fwd = partials; a.bwd = bwd_partials; a.N = N;
-    a.pf_tiles = env_int("DIF_TC_P2_PREFETCH", 1);
-    a.store_hint = env_int("DIF_TC_P2_STORE_HINT", 1);
+    static const int pf = env_int("DIF_TC_P2_PREFETCH", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1);
+    a.pf_tiles = pf;
+    a.store_hint = sth;
     const int grid = tc_grid((N + kTile2 - 1) / kTile2);
     return H == 4 ? bwd_apply_all<4>(a, q, k, v, g, dq, dk, dv, grid, st)
          : H == 2 ? bwd_apply_all<2>(a, q, k, v, g, dq, dk, dv, grid, st)
