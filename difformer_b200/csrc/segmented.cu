@@ -11,6 +11,8 @@
 // Backward = per-graph a-1b with two global scalars (t_q, t_k):
 //   phase A: per graph t_q,g and t_k,g -> summed in fixed order (deterministic)
 //   phase B: per graph recompute S_g, dS_g and emit dq, dk, dv.
+#include <algorithm>
+
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -28,6 +30,7 @@ struct SegArgs {
     int B, H, Hv, M, D;
     float *o, *dq, *dk, *dv;
     float* part;          // bwd phase A: [B][2]
+    int min_rows;         // fwd CTA kernel: only graphs with more rows than this (0 = all)
 };
 
 __device__ __forceinline__ void seg_load(float* __restrict__ dst, int ld, const float* __restrict__ src, int64_t row0, int nr,
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
     const int tilesJ = D >> 2, ntileA = (kSegRows >> 2) * tilesJ;
     for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
         const int64_t s = p.seg[g], e = p.seg[g + 1];
-        if (e <= s) continue;
+        if (e - s <= p.min_rows) continue;          // small graphs are handled by seg_fwd_warp_kernel
         const float ng = (float)(e - s);
         for (int h = 0; h < H; ++h) {
             const int hv = (p.Hv == H) ? h : 0;
@@ -145,6 +148,72 @@ __global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
                     }
                 }
                 __syncthreads();
+            }
+        }
+    }
+}
+
+// ---- small graphs (n_g <= kWarpMaxRows), M == D == 64: one WARP per graph, direct O(n^2) form
+//      out_n = sum_l (1 + c q_n.k_l) v_l / sum_l (1 + c q_n.k_l)        (same value as (c q S + u)/(c q z + n))
+// which costs 2 n^2 64 MACs per graph instead of 2 n 64^2 -- cheaper for n < 64 -- with no block-level
+// synchronisation at all: lane = query row, K/V rows of the graph broadcast from a per-warp shared buffer.
+constexpr int kWarpMaxRows = 64, kWarpsPerCta = 4;
+__global__ void __launch_bounds__(kWarpsPerCta * 32) seg_fwd_warp_kernel(SegArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* Ks = smem + warp * (2 * 32 * 64);      // [32][64]
+    float* Vs = Ks + 32 * 64;                     // [32][64]
+    const int H = p.H;
+    const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+    const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+    for (int g = gw; g < p.B; g += nw) {
+        const int64_t s = p.seg[g], e = p.seg[g + 1];
+        const int n = (int)(e - s);
+        if (n <= 0 || n > kWarpMaxRows) continue;
+        for (int h = 0; h < H; ++h) {
+            const int hv = (p.Hv == H) ? h : 0;
+            for (int q0 = 0; q0 < n; q0 += 32) {                 // query rows q0 + lane
+                const int qr = q0 + lane;
+                float4 q4[16], acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    q4[i] = qr < n ? ldg4(p.q + ((s + qr) * H + h) * 64 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float den = 0.f;
+                for (int l0 = 0; l0 < n; l0 += 32) {             // key rows l0 .. l0+31 staged in shared memory
+                    const int nl = min(32, n - l0);
+                    __syncwarp();
+                    for (int idx = lane; idx < nl * 16; idx += 32) {
+                        const int r = idx >> 4, c4 = idx & 15;
+                        *reinterpret_cast<float4*>(Ks + r * 64 + 4 * c4) = ldg4(p.k + ((s + l0 + r) * H + h) * 64 + 4 * c4);
+                        *reinterpret_cast<float4*>(Vs + r * 64 + 4 * c4) = ldg4(p.v + ((s + l0 + r) * p.Hv + hv) * 64 + 4 * c4);
+                    }
+                    __syncwarp();
+                    for (int l = 0; l < nl; ++l) {
+                        float sc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 k4 = *reinterpret_cast<const float4*>(Ks + l * 64 + 4 * i);   // broadcast
+                            sc = fmaf(q4[i].x, k4.x, sc); sc = fmaf(q4[i].y, k4.y, sc);
+                            sc = fmaf(q4[i].z, k4.z, sc); sc = fmaf(q4[i].w, k4.w, sc);
+                        }
+                        const float w = fmaf(c, sc, 1.f);
+                        den += w;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 v4 = *reinterpret_cast<const float4*>(Vs + l * 64 + 4 * i);
+                            acc[i].x = fmaf(w, v4.x, acc[i].x); acc[i].y = fmaf(w, v4.y, acc[i].y);
+                            acc[i].z = fmaf(w, v4.z, acc[i].z); acc[i].w = fmaf(w, v4.w, acc[i].w);
+                        }
+                    }
+                }
+                if (qr < n) {
+                    float* o = p.o + ((s + qr) * H + h) * 64;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(acc[i].x / den, acc[i].y / den, acc[i].z / den, acc[i].w / den);
+                }
             }
         }
     }
@@ -434,6 +503,16 @@ extern "C" int dif_segmented_simple_fwd(const float* q, const float* k, const fl
     const int grid = B < 148 * 16 ? B : 148 * 16;
     const int ntile = (M / 4) * (D / 4);
     cudaStream_t st = (cudaStream_t)stream;
+    if (M == 64 && D == 64) {
+        // graphs with <= 64 rows: one warp per graph, direct form (the particle datasets: 10-40 nodes per graph)
+        const size_t wsmem = (size_t)kWarpsPerCta * 2 * 32 * 64 * sizeof(float);
+        static bool attr = false;
+        if (!attr) { DIF_CUDA_OK(cudaFuncSetAttribute(seg_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); attr = true; }
+        const int wgrid = (int)std::min<int64_t>(((int64_t)B + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 12);
+        seg_fwd_warp_kernel<<<wgrid, kWarpsPerCta * 32, wsmem, st>>>(a);
+        DIF_LAUNCH_OK();
+        a.min_rows = kWarpMaxRows;       // the CTA kernel below only takes the larger graphs
+    }
     if (ntile <= kThreads) { if ((rc = seg_smem(seg_fwd_kernel<1>, smem))) return rc; seg_fwd_kernel<1><<<grid, kThreads, smem, st>>>(a); }
     else if (ntile <= 2 * kThreads) { if ((rc = seg_smem(seg_fwd_kernel<2>, smem))) return rc; seg_fwd_kernel<2><<<grid, kThreads, smem, st>>>(a); }
     else { if ((rc = seg_smem(seg_fwd_kernel<4>, smem))) return rc; seg_fwd_kernel<4><<<grid, kThreads, smem, st>>>(a); }
