@@ -156,13 +156,13 @@ __global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
 // ---- small graphs (n_g <= kWarpMaxRows), M == D == 64: one WARP per graph, direct O(n^2) form
 //      out_n = sum_l (1 + c q_n.k_l) v_l / sum_l (1 + c q_n.k_l)        (same value as (c q S + u)/(c q z + n))
 // which costs 2 n^2 64 MACs per graph instead of 2 n 64^2 -- cheaper for n < 64 -- with no block-level
-// synchronisation at all: lane = query row, K/V rows of the graph broadcast from a per-warp shared buffer.
-constexpr int kWarpMaxRows = 64, kWarpsPerCta = 4;
-__global__ void __launch_bounds__(kWarpsPerCta * 32) seg_fwd_warp_kernel(SegArgs p) {
+// synchronisation at all: two lanes per query row, K/V rows of the graph broadcast from a per-warp shared buffer.
+constexpr int kWarpMaxRows = 64, kWarpsPerCta = 4, kWarpStage = 16;
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) seg_fwd_warp_kernel(SegArgs p) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* Ks = smem + warp * (2 * 32 * 64);      // [32][64]
-    float* Vs = Ks + 32 * 64;                     // [32][64]
+    float* Ks = smem + warp * (2 * kWarpStage * 64);      // [16][64]
+    float* Vs = Ks + kWarpStage * 64;                     // [16][64]
     const int H = p.H;
     const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
     const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
@@ -172,47 +172,70 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) seg_fwd_warp_kernel(SegArgs
         if (n <= 0 || n > kWarpMaxRows) continue;
         for (int h = 0; h < H; ++h) {
             const int hv = (p.Hv == H) ? h : 0;
-            for (int q0 = 0; q0 < n; q0 += 32) {                 // query rows q0 + lane
-                const int qr = q0 + lane;
-                float4 q4[16], acc[16];
+            // lane = (row pair rp = lane >> 1, column half = lane & 1): 2 query rows x 32 columns per lane, 32 rows per
+            // pass.  Every K/V value read from shared memory feeds two rows (halves the LDS count), and the two column
+            // halves of a staged row are interleaved in 16-byte chunks so that the two addresses a quarter-warp reads
+            // fall into different banks (a 128-bit broadcast load costs one wavefront per quarter-warp, not two).
+            const int half = lane & 1, rp = lane >> 1;
+            for (int q0 = 0; q0 < n; q0 += 32) {
+                const int qr0 = q0 + 2 * rp, qr1 = qr0 + 1;
+                float4 qa[8], qb[8], aa[8], ab[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    q4[i] = qr < n ? ldg4(p.q + ((s + qr) * H + h) * 64 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i) {
+                    qa[i] = qr0 < n ? ldg4(p.q + ((s + qr0) * H + h) * 64 + 32 * half + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    qb[i] = qr1 < n ? ldg4(p.q + ((s + qr1) * H + h) * 64 + 32 * half + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    aa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                float den = 0.f;
-                for (int l0 = 0; l0 < n; l0 += 32) {             // key rows l0 .. l0+31 staged in shared memory
-                    const int nl = min(32, n - l0);
+                float dena = 0.f, denb = 0.f;
+                for (int l0 = 0; l0 < n; l0 += kWarpStage) {     // key rows staged in shared memory, 16 at a time
+                    const int nl = min(kWarpStage, n - l0);
                     __syncwarp();
                     for (int idx = lane; idx < nl * 16; idx += 32) {
                         const int r = idx >> 4, c4 = idx & 15;
-                        *reinterpret_cast<float4*>(Ks + r * 64 + 4 * c4) = ldg4(p.k + ((s + l0 + r) * H + h) * 64 + 4 * c4);
-                        *reinterpret_cast<float4*>(Vs + r * 64 + 4 * c4) = ldg4(p.v + ((s + l0 + r) * p.Hv + hv) * 64 + 4 * c4);
+                        // chunk c4 (columns 4 c4 ..) of half (c4 >> 3) goes to interleaved slot 2 (c4 & 7) + (c4 >> 3)
+                        const int slot = 2 * (c4 & 7) + (c4 >> 3);
+                        *reinterpret_cast<float4*>(Ks + r * 64 + 4 * slot) = ldg4(p.k + ((s + l0 + r) * H + h) * 64 + 4 * c4);
+                        *reinterpret_cast<float4*>(Vs + r * 64 + 4 * slot) = ldg4(p.v + ((s + l0 + r) * p.Hv + hv) * 64 + 4 * c4);
                     }
                     __syncwarp();
                     for (int l = 0; l < nl; ++l) {
-                        float sc = 0.f;
+                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // independent chains (FMA latency)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float4 k4 = *reinterpret_cast<const float4*>(Ks + l * 64 + 4 * i);   // broadcast
-                            sc = fmaf(q4[i].x, k4.x, sc); sc = fmaf(q4[i].y, k4.y, sc);
-                            sc = fmaf(q4[i].z, k4.z, sc); sc = fmaf(q4[i].w, k4.w, sc);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 k4 = *reinterpret_cast<const float4*>(Ks + l * 64 + 4 * (2 * i + half));
+                            a0 = fmaf(qa[i].x, k4.x, a0); a1 = fmaf(qa[i].y, k4.y, a1);
+                            a0 = fmaf(qa[i].z, k4.z, a0); a1 = fmaf(qa[i].w, k4.w, a1);
+                            b0 = fmaf(qb[i].x, k4.x, b0); b1 = fmaf(qb[i].y, k4.y, b1);
+                            b0 = fmaf(qb[i].z, k4.z, b0); b1 = fmaf(qb[i].w, k4.w, b1);
                         }
-                        const float w = fmaf(c, sc, 1.f);
-                        den += w;
+                        float sa = a0 + a1, sb = b0 + b1;
+                        sa += __shfl_xor_sync(0xffffffffu, sa, 1);            // the other column half of the rows
+                        sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                        const float wa = fmaf(c, sa, 1.f), wb = fmaf(c, sb, 1.f);
+                        dena += wa;
+                        denb += wb;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float4 v4 = *reinterpret_cast<const float4*>(Vs + l * 64 + 4 * i);
-                            acc[i].x = fmaf(w, v4.x, acc[i].x); acc[i].y = fmaf(w, v4.y, acc[i].y);
-                            acc[i].z = fmaf(w, v4.z, acc[i].z); acc[i].w = fmaf(w, v4.w, acc[i].w);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 v4 = *reinterpret_cast<const float4*>(Vs + l * 64 + 4 * (2 * i + half));
+                            aa[i].x = fmaf(wa, v4.x, aa[i].x); aa[i].y = fmaf(wa, v4.y, aa[i].y);
+                            aa[i].z = fmaf(wa, v4.z, aa[i].z); aa[i].w = fmaf(wa, v4.w, aa[i].w);
+                            ab[i].x = fmaf(wb, v4.x, ab[i].x); ab[i].y = fmaf(wb, v4.y, ab[i].y);
+                            ab[i].z = fmaf(wb, v4.z, ab[i].z); ab[i].w = fmaf(wb, v4.w, ab[i].w);
                         }
                     }
                 }
-                if (qr < n) {
-                    float* o = p.o + ((s + qr) * H + h) * 64;
+                if (qr0 < n) {
+                    float* o = p.o + ((s + qr0) * H + h) * 64 + 32 * half;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(acc[i].x / den, acc[i].y / den, acc[i].z / den, acc[i].w / den);
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(aa[i].x / dena, aa[i].y / dena, aa[i].z / dena, aa[i].w / dena);
+                }
+                if (qr1 < n) {
+                    float* o = p.o + ((s + qr1) * H + h) * 64 + 32 * half;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(ab[i].x / denb, ab[i].y / denb, ab[i].z / denb, ab[i].w / denb);
                 }
             }
         }
@@ -505,15 +528,16 @@ extern "C" int dif_segmented_simple_fwd(const float* q, const float* k, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 64 && D == 64) {
         // graphs with <= 64 rows: one warp per graph, direct form (the particle datasets: 10-40 nodes per graph)
-        const size_t wsmem = (size_t)kWarpsPerCta * 2 * 32 * 64 * sizeof(float);
+        const size_t wsmem = (size_t)kWarpsPerCta * 2 * kWarpStage * 64 * sizeof(float);
         static bool attr = false;
         if (!attr) { DIF_CUDA_OK(cudaFuncSetAttribute(seg_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); attr = true; }
-        const int wgrid = (int)std::min<int64_t>(((int64_t)B + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 12);
+        const int wgrid = (int)std::min<int64_t>(((int64_t)B + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 16);
         seg_fwd_warp_kernel<<<wgrid, kWarpsPerCta * 32, wsmem, st>>>(a);
         DIF_LAUNCH_OK();
         a.min_rows = kWarpMaxRows;       // the CTA kernel below only takes the larger graphs
     }
-    if (ntile <= kThreads) { if ((rc = seg_smem(seg_fwd_kernel<1>, smem))) return rc; seg_fwd_kernel<1><<<grid, kThreads, smem, st>>>(a); }
+    const int grid_cta = a.min_rows > 0 ? (grid < 296 ? grid : 296) : grid;     // mostly skipping: a small grid is enough
+    if (ntile <= kThreads) { if ((rc = seg_smem(seg_fwd_kernel<1>, smem))) return rc; seg_fwd_kernel<1><<<grid_cta, kThreads, smem, st>>>(a); }
     else if (ntile <= 2 * kThreads) { if ((rc = seg_smem(seg_fwd_kernel<2>, smem))) return rc; seg_fwd_kernel<2><<<grid, kThreads, smem, st>>>(a); }
     else { if ((rc = seg_smem(seg_fwd_kernel<4>, smem))) return rc; seg_fwd_kernel<4><<<grid, kThreads, smem, st>>>(a); }
     DIF_LAUNCH_OK();
