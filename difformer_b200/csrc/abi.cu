@@ -63,13 +63,17 @@ static int pick_impl(int impl, int64_t N, int H, int Hv, int M, int D, bool* use
 extern "C" int64_t dif_simple_prepared_bytes(int H, int Hv, int M, int D) { return simple_tc_prepared_bytes(H, Hv, M, D); }
 
 extern "C" int dif_simple_reduce(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
-                                 float* partials, void* prepared, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+                                 float* partials, void* prepared, float* vbar, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
     DIF_REQUIRE(q && k && v && partials && workspace, DIF_EARG, "simple_reduce: null pointer");
     bool tc = false;
     int rc = pick_impl(impl, N, H, Hv, M, D, &tc);
     if (rc) return rc;
-    return tc ? simple_reduce_tc(q, k, v, N, H, Hv, M, D, partials, prepared, workspace, workspace_bytes, (cudaStream_t)stream)
-              : simple_reduce_generic(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (tc)
+        return simple_reduce_tc(q, k, v, N, H, Hv, M, D, partials, prepared, workspace, workspace_bytes, (cudaStream_t)stream,
+                                nullptr, 0, 1, 0, vbar);
+    rc = simple_reduce_generic(q, k, v, N, H, Hv, M, D, partials, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc == DIF_OK && vbar != nullptr) rc = dif_head_mean(v, N, Hv, D, vbar, stream);      // generic path: separate kernel
+    return rc;
 }
 
 // pass 1 + the cross-GPU all-reduce of the partials in ONE kernel (tcgen05 shapes only): the tail of the

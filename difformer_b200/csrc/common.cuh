@@ -95,7 +95,7 @@ int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D);
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
                      float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st,
-                     void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0);
+                     void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0, float* vbar = nullptr);
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st);
 

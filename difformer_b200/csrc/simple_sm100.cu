@@ -311,6 +311,7 @@ struct ReduceArgs1 {
     const float* fwd_partials;    // forward partials (S, z, u, sq, sk)
     float n_total;
     float* rowscal;               // [N][H][2] = (1/den, dden) per (node, head), consumed by the dq kernel
+    float* vbar;                  // fwd, optional: mean over heads of V, [N][64] (feeds the gcn SpMM of the fused layer)
 };
 
 // BWD = false: forward pass 1 (S = K^T V, z, u, norms).
@@ -371,6 +372,22 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                 for (int t = 0; t < 3; ++t) {
                     x[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (node < nrows) x[i][t] = lds128(stg_base + s * G::kStg + t * G::kStgT + u * 16);
+                }
+            }
+            if (!BWD && H > 1 && a.vbar != nullptr) {
+                // mean_h V for the fused layer's gcn term (the head mean commutes with the SpMM): thread t -> (node t>>4,
+                // 4 columns t&15); the H head chunks of that (node, columns) are read back from the fp32 staging row
+                const int node = tid >> 4, d4 = tid & 15;
+                for (int nd = node; nd < nrows; nd += 16) {
+                    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int hh = 0; hh < H; ++hh) {
+                        const float4 y = lds128(stg_base + s * G::kStg + 1 * G::kStgT + nd * G::kRowB + hh * 256 + d4 * 16);
+                        m.x += y.x; m.y += y.y; m.z += y.z; m.w += y.w;
+                    }
+                    const float inv = 1.f / (float)H;
+                    const int64_t row = r0 + (int64_t)it * G::kNodes + nd;
+                    *reinterpret_cast<float4*>(a.vbar + row * kDim + 4 * d4) = make_float4(m.x * inv, m.y * inv, m.z * inv, m.w * inv);
                 }
             }
             if (it >= G::kNO) mbar_wait(&oempty[o], ((it / G::kNO) - 1) & 1);
@@ -1330,7 +1347,7 @@ static int launch_reduce(const ReduceArgs1& a, int grid, cudaStream_t st) {
 
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
                      float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st,
-                     void* const* peer_bufs, int rank, int world, unsigned long long seq) {
+                     void* const* peer_bufs, int rank, int world, unsigned long long seq, float* vbar) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0, DIF_EARG, "tcgen05 path: q/k/v must be 16-byte aligned");
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_reduce(tcgen05): prepared buffer must be 16-byte aligned");
@@ -1345,6 +1362,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
     a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
     a.partials = partials; a.prepared = (uint8_t*)prepared;
+    a.vbar = vbar;
     static const int hints = env_int("DIF_TC_P1_HINTS", 1);
     a.l2_hints = hints;
     a.sh.world = 1;

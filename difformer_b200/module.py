@@ -54,14 +54,18 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         ops._need_cuda(q, k, v)
         N = q.shape[0]
         alpha = 1.0 if residual is None else float(residual[0])
-        partials, prepared = ops.simple_partials(q, k, v, with_prepared=True)
+        # pass 1 also emits mean_h(V) when a gcn term follows (V is streaming through the SM anyway)
+        vbar = None
+        if conv.use_graph and v.shape[1] > 1:
+            vbar = torch.empty((N, v.shape[2]), dtype=torch.float32, device=v.device)
+        partials, prepared = ops.simple_partials(q, k, v, with_prepared=True, vbar=vbar)
         addends = []
         if conv.use_graph:
             csr = ops.graph_csr(edge_index, edge_weight, N)
             # the head mean commutes with the SpMM: gather 256 B rows of mean_h(V) (L2-resident, T/H bytes)
             # instead of H x 256 B rows of V
-            vbar = ops.head_mean(v) if v.shape[1] > 1 else v
-            gmean = ops.spmm(csr, vbar.view(N, 1, v.shape[2])).view(N, v.shape[2])
+            src = vbar if vbar is not None else v
+            gmean = ops.spmm(csr, src.view(N, 1, v.shape[2])).view(N, v.shape[2])
             addends.append((gmean, alpha * w_gcn))
         if use_source:
             addends.append((ops._f32c(x_0), alpha))

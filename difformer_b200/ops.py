@@ -57,7 +57,7 @@ def _shapes(qs, ks, vs) -> Tuple[int, int, int, int, int, int]:
 # kernel='simple'
 # ----------------------------------------------------------------------------------------------
 def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_prepared: bool = False,
-                    out: Optional[torch.Tensor] = None):
+                    out: Optional[torch.Tensor] = None, vbar: Optional[torch.Tensor] = None):
     """Pass 1 on this rank's rows -> partials [S | z | u | sum q^2 | sum k^2] (fp32, additive).
 
     with_prepared=True also returns the pass-2 operand image pass 1 can emit for free on tcgen05
@@ -79,7 +79,8 @@ def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_p
     prepared = torch.empty(pb, dtype=torch.uint8, device=qs.device) if pb > 0 else None
     with torch.cuda.device(qs.device):
         check(lib.dif_simple_reduce(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D, partials.data_ptr(),
-                                    None if prepared is None else prepared.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    None if prepared is None else prepared.data_ptr(),
+                                    None if vbar is None else vbar.data_ptr(), ws.data_ptr(), ws.numel(),
                                     _SIMPLE_IMPL, _stream(qs)),
               "dif_simple_reduce")
     return (partials, prepared) if with_prepared else partials

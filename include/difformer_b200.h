@@ -65,7 +65,10 @@ DIF_API int dif_device_supported(void);
  * ------------------------------------------------------------------------------------------ */
 DIF_API int64_t dif_simple_partials_len(int H, int Hv, int M, int D);
 DIF_API int64_t dif_simple_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
-/* `prepared` (optional, may be NULL): when dif_simple_prepared_bytes() > 0 (tcgen05 shapes) pass 1 also writes the
+/* `vbar` (optional, may be NULL): pass 1 also writes mean_h(V) as [N,D] (V is streaming through the SM anyway);
+ * it feeds the gcn SpMM of the fused layer (the head mean commutes with the SpMM).  For Hv == 1 it is a copy-free
+ * no-op on the tcgen05 path (V itself is mean_h(V)): callers should pass NULL then.
+ * `prepared` (optional, may be NULL): when dif_simple_prepared_bytes() > 0 (tcgen05 shapes) pass 1 also writes the
  * pass-2 tensor-core operands derived from `partials` (bf16 hi/lo split, 128B-swizzled) into this caller-owned
  * buffer (16-byte aligned), which saves pass 2 its transposing prologue.  It is only valid for the exact
  * `partials` pass 1 produced: after an all-reduce (or any edit) of `partials` pass NULL to pass 2. */
@@ -73,7 +76,7 @@ DIF_API int64_t dif_simple_prepared_bytes(int H, int Hv, int M, int D);
 
 DIF_API int dif_simple_reduce(const float* q, const float* k, const float* v,
                       int64_t N, int H, int Hv, int M, int D,
-                      float* partials, void* prepared, void* workspace, int64_t workspace_bytes,
+                      float* partials, void* prepared, float* vbar, void* workspace, int64_t workspace_bytes,
                       int impl, void* stream);
 
 /* Epilogue of pass 2.
