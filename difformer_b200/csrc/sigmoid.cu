@@ -384,10 +384,19 @@ static int sigmoid_ksplit(int64_t N, int64_t L, int H) {
     return s < 1 ? 1 : (int)s;
 }
 
+static int g_sigmoid_impl = DIF_IMPL_AUTO;
+
+extern "C" int dif_sigmoid_set_impl(int impl) {
+    DIF_REQUIRE(impl == DIF_IMPL_AUTO || impl == DIF_IMPL_GENERIC || impl == DIF_IMPL_TCGEN05, DIF_EARG, "sigmoid: unknown impl %d", impl);
+    g_sigmoid_impl = impl;
+    return DIF_OK;
+}
+
 extern "C" int64_t dif_sigmoid_fwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D) {
-    (void)Hv; (void)M;
     const int s = sigmoid_ksplit(N, L, H);
-    return s > 1 ? (int64_t)s * N * H * (D + 1) * (int64_t)sizeof(float) : 0;
+    const int t = sigmoid_tc_supported(N, L, H, Hv, M, D) ? sigmoid_tc_ksplit(N, L, H) : 1;
+    const int m = s > t ? s : t;                                      // either implementation fits
+    return m > 1 ? (int64_t)m * N * H * (D + 1) * (int64_t)sizeof(float) : 0;
 }
 
 extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv, int M, int D,
@@ -395,6 +404,25 @@ extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, i
     int rc = sig_check(N, L, H, Hv, M, D);
     if (rc) return rc;
     DIF_REQUIRE(q && k && v && out && rowsum, DIF_EARG, "sigmoid_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_ok = sigmoid_tc_supported(N, L, H, Hv, M, D);
+    DIF_REQUIRE(g_sigmoid_impl != DIF_IMPL_TCGEN05 || tc_ok, DIF_EUNSUPPORTED, "sigmoid: tcgen05 path needs M == D == 64 (got M=%d D=%d)", M, D);
+    if (tc_ok && g_sigmoid_impl != DIF_IMPL_GENERIC) {
+        const int ks = sigmoid_tc_ksplit(N, L, H);
+        float *po = nullptr, *prs = nullptr;
+        if (ks > 1) {
+            DIF_REQUIRE(workspace && workspace_bytes >= (int64_t)ks * N * H * (D + 1) * 4, DIF_EARG, "sigmoid_fwd: workspace too small");
+            po = (float*)workspace;
+            prs = po + (int64_t)ks * N * H * D;
+        }
+        if ((rc = sigmoid_fwd_tc(q, k, v, N, L, H, Hv, out, rowsum, po, prs, ks, st))) return rc;
+        if (ks > 1) {
+            const int64_t n = N * H * (D / 4);
+            sigmoid_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(po, prs, ks, N * H, D, out, rowsum);
+            DIF_LAUNCH_OK();
+        }
+        return DIF_OK;
+    }
     SigArgs a{};
     a.q = q; a.k = k; a.v = v; a.N = N; a.L = L; a.H = H; a.Hv = Hv; a.M = M; a.D = D; a.o = out; a.rs = rowsum;
     a.ksplit = sigmoid_ksplit(N, L, H);
@@ -405,7 +433,6 @@ extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, i
     }
     const size_t smem = ((size_t)2 * kT * (M + 4) + (size_t)kT * (D + 4) + (size_t)kT * kLdp + kT) * sizeof(float);
     dim3 grid((unsigned)((N + kT - 1) / kT), H, a.ksplit);
-    cudaStream_t st = (cudaStream_t)stream;
     if ((kT / 4) * (D / 4) <= kThreads) {
         if ((rc = set_smem_(sigmoid_fwd_kernel<1>, smem))) return rc;
         sigmoid_fwd_kernel<1><<<grid, kThreads, smem, st>>>(a);

@@ -1,0 +1,249 @@
+// kernel='sigmoid' forward on the tensor cores (sm_100a) -- full_attention_conv(..., 'sigmoid'),
+// node classification/difformer.py:45-56:   P = sigmoid(Q K^T),  out = (P V) / rowsum(P).
+//
+// Flash-style: one CTA owns 128 query rows of one head (and one slice of the keys), loops over 128-key tiles and
+// never materialises [N, L]:
+//   S  = Q K^T      tcgen05.mma M=128 N=128 K=64, Q and K split into bf16 hi+lo (3 MMAs per product: the scores go
+//                   through a sigmoid, so they need ~fp32 accuracy), accumulator in TMEM (two S buffers)
+//   P  = sigmoid(S) 128 threads, one query row each: tcgen05.ld -> ex2/rcp -> bf16 hi+lo -> 128B-swizzled shared
+//                   memory (P in (0,1): no running max).  P is split like the other operands: the output is a mean of
+//                   signed values, so a 2^-9 rounding of the weights would show up at the 1e-3 level.
+//   O += P V        tcgen05.mma M=128 N=64 K=128, A = P hi/lo (K-major), B = V hi/lo (MN-major: keys are the K index)
+// Warp roles: 0-7 producers (fp32 rows -> bf16 hi/lo swizzled operand tiles), 8-11 sigmoid, 12 MMA issuer.
+// The MMA thread issues S(j+1) before P V(j), so the sigmoid of tile j+1 overlaps the P V product of tile j.
+// Small N: the key range is split over gridDim.z and the un-normalised partials are combined in fixed order
+// (sigmoid.cu), like the FFMA kernel.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dif {
+namespace {
+
+constexpr int kT = 128;                  // query rows per CTA = keys per tile
+constexpr int kOpT = kT * 128;           // one bf16 [128 rows][64] operand tile: 16 KB
+constexpr int kStageS = 4 * kOpT;        // Khi | Klo | Vhi | Vlo
+constexpr int kSmemSig = 2 * kOpT + 2 * kStageS + 4 * kOpT + 1024;   // Q + 2 stages + P hi/lo (two 64-key sub-tiles each)
+
+struct SigTcArgs {
+    const float *q, *k, *v;
+    int64_t N, L;
+    int H, Hv, ksplit;
+    float *out, *rowsum;     // ksplit == 1: final results
+    float *pout, *prs;       // ksplit  > 1: [ksplit][N,H,64] un-normalised sums, [ksplit][N,H] row sums
+};
+
+__device__ __forceinline__ float sigmoid_fast(float s) { return __frcp_rn(1.f + __expf(-s)); }
+
+__global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __grid_constant__ SigTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* Qop = base;                      // Qhi | Qlo
+    uint8_t* stages = Qop + 2 * kOpT;         // 2 x (Khi | Klo | Vhi | Vlo)
+    uint8_t* Pop = stages + 2 * kStageS;      // Phi keys 0-63 | Phi keys 64-127 | Plo keys 0-63 | Plo keys 64-127
+    __shared__ uint64_t qfull, kfull[2], kempty[2], sfull[2], sempty[2], pfull, pempty, done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = p.H, h = blockIdx.y, hv = (p.Hv == H) ? h : 0;
+    const int64_t n0 = (int64_t)blockIdx.x * kT;
+    const int64_t ltiles = (p.L + kT - 1) / kT, per = (ltiles + p.ksplit - 1) / p.ksplit;
+    const int64_t t0 = (int64_t)blockIdx.z * per, t1 = min(ltiles, t0 + per);
+    const int T = (int)max((int64_t)0, t1 - t0);        // key tiles of this CTA
+
+    if (tid == 0) {
+        mbar_init(&qfull, 8);
+        for (int s = 0; s < 2; ++s) { mbar_init(&kfull[s], 8); mbar_init(&kempty[s], 1); mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 4); }
+        mbar_init(&pfull, 4); mbar_init(&pempty, 1); mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ===== producers: a [128 rows][64 floats] slice (one head) -> bf16 hi/lo, rows of 128 B, 8-row swizzle atoms.
+        // The same layout serves Q / K as K-major operands and V as the MN-major B operand (keys = K index).
+        auto fill = [&](const float* src, int heads, int head, int64_t row0, int64_t nrows, uint32_t dst_hi, uint32_t dst_lo) {
+            float x[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                const int64_t row = row0 + (t >> 3);
+                if (row < nrows) ldg256_keep(src + (row * heads + head) * kDim + (t & 7) * 8, x[j]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[j][i] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                uint4 hi, lo;
+                split8(x[j], hi, lo);
+                const uint32_t off = sw128(t >> 3, t & 7);
+                sts128(dst_hi + off, hi);
+                sts128(dst_lo + off, lo);
+            }
+        };
+        fill(p.q, H, h, n0, p.N, smem_u32(Qop), smem_u32(Qop) + kOpT);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&qfull);
+        for (int i = 0; i < T; ++i) {
+            const int s = i & 1;
+            if (i >= 2) mbar_wait(&kempty[s], ((i >> 1) - 1) & 1);
+            const uint32_t sb = smem_u32(stages) + s * kStageS;
+            const int64_t l0 = (t0 + i) * kT;
+            fill(p.k, H, h, l0, p.L, sb, sb + kOpT);
+            fill(p.v, p.Hv, hv, l0, p.L, sb + 2 * kOpT, sb + 3 * kOpT);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&kfull[s]);
+        }
+    } else if (warp < 12) {
+        // ===== sigmoid: thread = query row r; S row -> p = sigmoid(s) -> bf16 P row (A operand of the P V product)
+        const int ew = warp - 8, r = ew * 32 + lane;
+        const uint32_t pbase = smem_u32(Pop);
+        float rowsum = 0.f;
+        for (int i = 0; i < T; ++i) {
+            const int sbuf = i & 1;
+            const int64_t l0 = (t0 + i) * kT;
+            mbar_wait(&sfull[sbuf], (i >> 1) & 1);
+            tc_fence_after();
+            if (i >= 1) mbar_wait(&pempty, (i - 1) & 1);       // the previous P V product has consumed P
+            const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + sbuf * kT;
+#pragma unroll
+            for (int c0 = 0; c0 < kT; c0 += 32) {
+                uint32_t sreg[32];
+                tmem_ld32(taddr + c0, sreg);
+                tmem_ld_wait32(sreg);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float pv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        pv[e] = l0 + c0 + j + e < p.L ? sigmoid_fast(__uint_as_float(sreg[j + e])) : 0.f;
+                        rowsum += pv[e];
+                    }
+                    uint4 hi, lo;
+                    split8(pv, hi, lo);
+                    const int cc = (c0 + j) >> 3;           // 16-byte chunk of the 128-key row: sub-tile cc>>3, chunk cc&7
+                    const uint32_t off = (cc >> 3) * kOpT + sw128(r, cc & 7);
+                    sts128(pbase + off, hi);
+                    sts128(pbase + 2 * kOpT + off, lo);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&sempty[sbuf]); mbar_arrive(&pfull); }
+        }
+        // ---- O / rowsum
+        mbar_wait(&done, 0);
+        tc_fence_after();
+        const int64_t row = n0 + r;
+        float* o_dst = p.ksplit > 1 ? p.pout + (int64_t)blockIdx.z * p.N * H * kDim : p.out;
+        float* r_dst = p.ksplit > 1 ? p.prs + (int64_t)blockIdx.z * p.N * H : p.rowsum;
+        const float inv = p.ksplit > 1 ? 1.f : 1.f / rowsum;
+#pragma unroll
+        for (int c0 = 0; c0 < kDim; c0 += 32) {
+            uint32_t o[32];
+            if (T > 0) {
+                tmem_ld32(tmem + ((uint32_t)(ew * 32) << 16) + 2 * kT + c0, o);
+                tmem_ld_wait32(o);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = 0u;
+            }
+            if (row < p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(o_dst + (row * H + h) * kDim + c0 + j) =
+                        make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv, __uint_as_float(o[j + 2]) * inv,
+                                    __uint_as_float(o[j + 3]) * inv);
+            }
+        }
+        if (row < p.N) r_dst[row * H + h] = rowsum;
+    } else if (lane == 0) {
+        // ===== MMA issuer
+        const uint32_t idS = make_idesc(kT, kT, 0, 0);          // S = Q K^T : both operands K-major
+        const uint32_t idO = make_idesc(kT, kDim, 0, 1);        // O += P V  : A = P K-major, B = V MN-major
+        const uint32_t qb = smem_u32(Qop), pb = smem_u32(Pop);
+        auto issue_S = [&](int i) {
+            const int s = i & 1;
+            mbar_wait(&kfull[s], (i >> 1) & 1);
+            if (i >= 2) mbar_wait(&sempty[s], ((i >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stages) + s * kStageS;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t qhi = make_desc(qb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(qb + kOpT + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t khi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), klo = make_desc(sb + kOpT + ks * 32, kKmajLBO, kKmajSBO);
+                umma(tmem + s * kT, qhi, khi, idS, ks > 0 ? 1u : 0u);
+                umma(tmem + s * kT, qlo, khi, idS, 1u);
+                umma(tmem + s * kT, qhi, klo, idS, 1u);
+            }
+            umma_commit(&sfull[s]);
+        };
+        auto issue_PV = [&](int i) {
+            const int s = i & 1;
+            mbar_wait(&pfull, i & 1);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stages) + s * kStageS;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {                     // 16 keys per step
+                const uint64_t pa = make_desc(pb + (ks >> 2) * kOpT + (ks & 3) * 32, kKmajLBO, kKmajSBO);
+                const uint64_t pl = make_desc(pb + (2 + (ks >> 2)) * kOpT + (ks & 3) * 32, kKmajLBO, kKmajSBO);
+                const uint64_t vhi = make_desc(sb + 2 * kOpT + ks * 2048, kOpT, 1024), vlo = make_desc(sb + 3 * kOpT + ks * 2048, kOpT, 1024);
+                umma(tmem + 2 * kT, pa, vhi, idO, (i > 0 || ks > 0) ? 1u : 0u);
+                umma(tmem + 2 * kT, pa, vlo, idO, 1u);
+                umma(tmem + 2 * kT, pl, vhi, idO, 1u);
+            }
+            umma_commit(&pempty);
+            umma_commit(&kempty[s]);
+        };
+        mbar_wait(&qfull, 0);
+        if (T > 0) issue_S(0);
+        for (int i = 0; i < T; ++i) {
+            if (i + 1 < T) issue_S(i + 1);
+            issue_PV(i);
+        }
+        if (T > 0) umma_commit(&done); else mbar_arrive(&done);
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool sigmoid_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D) {
+    return N >= 1 && L >= 1 && H >= 1 && H <= 65535 && (Hv == H || Hv == 1) && M == kDim && D == kDim;
+}
+
+int sigmoid_tc_ksplit(int64_t N, int64_t L, int H) {
+    const int64_t ctas = ((N + kT - 1) / kT) * H, ltiles = (L + kT - 1) / kT;
+    int64_t s = ((int64_t)sm_count() + ctas - 1) / ctas;       // one CTA per SM (192 KB of shared memory each)
+    if (s > ltiles) s = ltiles;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : (int)s;
+}
+
+int sigmoid_fwd_tc(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv,
+                   float* out, float* rowsum, float* pout, float* prs, int ksplit, cudaStream_t st) {
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG,
+                "sigmoid(tcgen05): q/k/v must be 32-byte aligned");
+    SigTcArgs a{};
+    a.q = q; a.k = k; a.v = v; a.N = N; a.L = L; a.H = H; a.Hv = Hv; a.ksplit = ksplit;
+    a.out = out; a.rowsum = rowsum; a.pout = pout; a.prs = prs;
+    static bool attr = false;
+    if (!attr) { DIF_CUDA_OK(cudaFuncSetAttribute(sigmoid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSig)); attr = true; }
+    dim3 grid((unsigned)((N + kT - 1) / kT), (unsigned)H, (unsigned)ksplit);
+    sigmoid_fwd_tc_kernel<<<grid, kThreadsTC, kSmemSig, st>>>(a);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+}  // namespace dif

@@ -25,6 +25,12 @@ def set_simple_impl(impl: str) -> None:
     _SIMPLE_IMPL = {"auto": _lib.DIF_IMPL_AUTO, "generic": _lib.DIF_IMPL_GENERIC, "tcgen05": _lib.DIF_IMPL_TCGEN05}[impl]
 
 
+def set_sigmoid_impl(impl: str) -> None:
+    """Select the 'sigmoid' forward kernel: 'auto' (tcgen05 when M == D == 64), 'generic' (fp32 FFMA), 'tcgen05'."""
+    check(lib.dif_sigmoid_set_impl({"auto": _lib.DIF_IMPL_AUTO, "generic": _lib.DIF_IMPL_GENERIC,
+                                            "tcgen05": _lib.DIF_IMPL_TCGEN05}[impl]), "dif_sigmoid_set_impl")
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 

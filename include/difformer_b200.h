@@ -134,7 +134,11 @@ DIF_API int64_t dif_segmented_workspace_bytes(int32_t B);
 /* ------------------------------------------------------------------------------------------
  * kernel='sigmoid'  (full_attention_conv, difformer.py:45-56): tiled, never materialises [N,L,H].
  *   out = (sigmoid(QK^T) / rowsum) V ; rowsum[N,H] is saved for the backward.
+ *   Forward with M == D == 64 runs on tcgen05 (flash-style: S = QK^T with bf16 hi/lo split operands, P = sigmoid(S)
+ *   rounded to bf16 for the P V product, rowsum taken from the rounded P); other shapes and the backward run the
+ *   fp32 FFMA kernels.  dif_sigmoid_set_impl(DIF_IMPL_GENERIC / _TCGEN05 / _AUTO) pins the forward path (process-wide).
  * ------------------------------------------------------------------------------------------ */
+DIF_API int dif_sigmoid_set_impl(int impl);
 DIF_API int64_t dif_sigmoid_fwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D);
 DIF_API int dif_sigmoid_fwd(const float* q, const float* k, const float* v,
                     int64_t N, int64_t L, int H, int Hv, int M, int D,
