@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#include <type_traits>
+
 namespace dif {
 namespace {
 
@@ -32,7 +34,13 @@ struct SigTcArgs {
     float *pout, *prs;       // ksplit  > 1: [ksplit][N,H,64] un-normalised sums, [ksplit][N,H] row sums
 };
 
-__device__ __forceinline__ float sigmoid_fast(float s) { return __frcp_rn(1.f + __expf(-s)); }
+// 1 / (1 + 2^(-s log2 e)): two MUFU ops, branch-free (ex2 overflow -> +inf -> rcp -> 0; underflow -> 1)
+__device__ __forceinline__ float sigmoid_fast(float s) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
 
 __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __grid_constant__ SigTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
         // ===== sigmoid: thread = query row r; S row -> p = sigmoid(s) -> bf16 P row (A operand of the P V product)
         const int ew = warp - 8, r = ew * 32 + lane;
         const uint32_t pbase = smem_u32(Pop);
-        float rowsum = 0.f;
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};
         for (int i = 0; i < T; ++i) {
             const int sbuf = i & 1;
             const int64_t l0 = (t0 + i) * kT;
@@ -113,33 +121,40 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
             tc_fence_after();
             if (i >= 1) mbar_wait(&pempty, (i - 1) & 1);       // the previous P V product has consumed P
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + sbuf * kT;
+            const int valid = (int)min((int64_t)kT, p.L - l0);
+            auto tile = [&](auto masked_t) {
+                constexpr bool kMasked = decltype(masked_t)::value;       // only the last key tile has keys >= L
 #pragma unroll
-            for (int c0 = 0; c0 < kT; c0 += 32) {
-                uint32_t sreg[32];
-                tmem_ld32(taddr + c0, sreg);
-                tmem_ld_wait32(sreg);
+                for (int c0 = 0; c0 < kT; c0 += 32) {
+                    uint32_t sreg[32];
+                    tmem_ld32(taddr + c0, sreg);
+                    tmem_ld_wait32(sreg);
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float pv[8];
+                    for (int j = 0; j < 32; j += 8) {
+                        float pv[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        pv[e] = l0 + c0 + j + e < p.L ? sigmoid_fast(__uint_as_float(sreg[j + e])) : 0.f;
-                        rowsum += pv[e];
+                        for (int e = 0; e < 8; ++e) {
+                            pv[e] = sigmoid_fast(__uint_as_float(sreg[j + e]));
+                            if (kMasked) pv[e] = (int)(c0 + j + e) < valid ? pv[e] : 0.f;
+                            rs[e & 3] += pv[e];
+                        }
+                        uint4 hi, lo;
+                        split8(pv, hi, lo);
+                        const int cc = (c0 + j) >> 3;       // 16-byte chunk of the 128-key row: sub-tile cc>>3, chunk cc&7
+                        const uint32_t off = (cc >> 3) * kOpT + sw128(r, cc & 7);
+                        sts128(pbase + off, hi);
+                        sts128(pbase + 2 * kOpT + off, lo);
                     }
-                    uint4 hi, lo;
-                    split8(pv, hi, lo);
-                    const int cc = (c0 + j) >> 3;           // 16-byte chunk of the 128-key row: sub-tile cc>>3, chunk cc&7
-                    const uint32_t off = (cc >> 3) * kOpT + sw128(r, cc & 7);
-                    sts128(pbase + off, hi);
-                    sts128(pbase + 2 * kOpT + off, lo);
                 }
-            }
+            };
+            if (valid == kT) tile(std::false_type{}); else tile(std::true_type{});
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&sempty[sbuf]); mbar_arrive(&pfull); }
         }
         // ---- O / rowsum
+        const float rowsum = (rs[0] + rs[1]) + (rs[2] + rs[3]);
         mbar_wait(&done, 0);
         tc_fence_after();
         const int64_t row = n0 + r;
@@ -223,12 +238,18 @@ bool sigmoid_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D) {
     return N >= 1 && L >= 1 && H >= 1 && H <= 65535 && (Hv == H || Hv == 1) && M == kDim && D == kDim;
 }
 
+// Key split: CTAs = query tiles x heads x s run in waves of one CTA per SM (224 KB of shared memory each); pick the
+// s that minimises waves x (key tiles per CTA + fixed per-CTA cost), with a small charge for the combine pass.
 int sigmoid_tc_ksplit(int64_t N, int64_t L, int H) {
-    const int64_t ctas = ((N + kT - 1) / kT) * H, ltiles = (L + kT - 1) / kT;
-    int64_t s = ((int64_t)sm_count() + ctas - 1) / ctas;       // one CTA per SM (192 KB of shared memory each)
-    if (s > ltiles) s = ltiles;
-    if (s > 32) s = 32;
-    return s < 1 ? 1 : (int)s;
+    const int64_t ctas = ((N + kT - 1) / kT) * H, ltiles = (L + kT - 1) / kT, sms = sm_count();
+    int best = 1;
+    double best_cost = 1e300;
+    for (int64_t s = 1; s <= ltiles && s <= 32; ++s) {
+        const int64_t waves = (ctas * s + sms - 1) / sms, per = (ltiles + s - 1) / s;
+        const double cost = (double)waves * ((double)per + 1.5) + (s > 1 ? 0.5 + 0.1 * (double)s : 0.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = (int)s; }
+    }
+    return best;
 }
 
 int sigmoid_fwd_tc(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv,

@@ -23,6 +23,8 @@ def timeit(fn, iters=20, warm=3):
 
 
 shapes = [(1, 1, 1, 1), (63, 200, 2, 2), (128, 128, 1, 1), (129, 257, 1, 1), (300, 1000, 4, 1), (2708, 2708, 1, 1), (2708, 2708, 4, 4), (10000, 10000, 1, 1)]
+if os.environ.get("SIG_BIG"):
+    shapes = [(10000, 10000, 1, 1)]
 for (n, l, h, hv) in shapes:
     gen = torch.Generator().manual_seed(n + l)
     q = torch.randn(n, h, 64, generator=gen) * 0.3
