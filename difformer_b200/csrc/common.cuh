@@ -94,8 +94,9 @@ bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D);
 // sigmoid_sm100.cu
 bool sigmoid_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D);
 int sigmoid_tc_ksplit(int64_t N, int64_t L, int H);
+int64_t sigmoid_tc_image_bytes(int64_t L, int H, int Hv);
 int sigmoid_fwd_tc(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv, float* out, float* rowsum,
-                   float* pout, float* prs, int ksplit, cudaStream_t st);
+                   float* pout, float* prs, int ksplit, void* images, cudaStream_t st);
 int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D);
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,

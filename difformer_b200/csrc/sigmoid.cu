@@ -394,9 +394,10 @@ extern "C" int dif_sigmoid_set_impl(int impl) {
 
 extern "C" int64_t dif_sigmoid_fwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D) {
     const int s = sigmoid_ksplit(N, L, H);
-    const int t = sigmoid_tc_supported(N, L, H, Hv, M, D) ? sigmoid_tc_ksplit(N, L, H) : 1;
+    const bool tc = sigmoid_tc_supported(N, L, H, Hv, M, D);
+    const int t = tc ? sigmoid_tc_ksplit(N, L, H) : 1;
     const int m = s > t ? s : t;                                      // either implementation fits
-    return m > 1 ? (int64_t)m * N * H * (D + 1) * (int64_t)sizeof(float) : 0;
+    return (m > 1 ? (int64_t)m * N * H * (D + 1) * (int64_t)sizeof(float) : 0) + (tc ? sigmoid_tc_image_bytes(L, H, Hv) : 0);
 }
 
 extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv, int M, int D,
@@ -410,12 +411,13 @@ extern "C" int dif_sigmoid_fwd(const float* q, const float* k, const float* v, i
     if (tc_ok && g_sigmoid_impl != DIF_IMPL_GENERIC) {
         const int ks = sigmoid_tc_ksplit(N, L, H);
         float *po = nullptr, *prs = nullptr;
+        const int64_t pbytes = ks > 1 ? (int64_t)ks * N * H * (D + 1) * 4 : 0;      // [partials | K, V operand images]
+        DIF_REQUIRE(workspace && workspace_bytes >= pbytes + sigmoid_tc_image_bytes(L, H, Hv), DIF_EARG, "sigmoid_fwd: workspace too small");
         if (ks > 1) {
-            DIF_REQUIRE(workspace && workspace_bytes >= (int64_t)ks * N * H * (D + 1) * 4, DIF_EARG, "sigmoid_fwd: workspace too small");
             po = (float*)workspace;
             prs = po + (int64_t)ks * N * H * D;
         }
-        if ((rc = sigmoid_fwd_tc(q, k, v, N, L, H, Hv, out, rowsum, po, prs, ks, st))) return rc;
+        if ((rc = sigmoid_fwd_tc(q, k, v, N, L, H, Hv, out, rowsum, po, prs, ks, (char*)workspace + pbytes, st))) return rc;
         if (ks > 1) {
             const int64_t n = N * H * (D / 4);
             sigmoid_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(po, prs, ks, N * H, D, out, rowsum);

@@ -5,14 +5,19 @@
 // never materialises [N, L]:
 //   S  = Q K^T      tcgen05.mma M=128 N=128 K=64, Q and K split into bf16 hi+lo (3 MMAs per product: the scores go
 //                   through a sigmoid, so they need ~fp32 accuracy), accumulator in TMEM (two S buffers)
-//   P  = sigmoid(S) 128 threads, one query row each: tcgen05.ld -> ex2/rcp -> bf16 hi+lo -> 128B-swizzled shared
-//                   memory (P in (0,1): no running max).  P is split like the other operands: the output is a mean of
-//                   signed values, so a 2^-9 rounding of the weights would show up at the 1e-3 level.
+//   P  = sigmoid(S) 256 threads (thread = query row x half of the keys): tcgen05.ld -> ex2/rcp -> bf16 hi+lo ->
+//                   128B-swizzled shared memory (P in (0,1): no running max).  P is split like the other operands:
+//                   the output is a mean of signed values, so a 2^-9 rounding of the weights would show up at the
+//                   1e-3 level.
 //   O += P V        tcgen05.mma M=128 N=64 K=128, A = P hi/lo (K-major), B = V hi/lo (MN-major: keys are the K index)
-// Warp roles: 0-7 producers (fp32 rows -> bf16 hi/lo swizzled operand tiles), 8-11 sigmoid, 12 MMA issuer.
-// The MMA thread issues S(j+1) before P V(j), so the sigmoid of tile j+1 overlaps the P V product of tile j.
-// Small N: the key range is split over gridDim.z and the un-normalised partials are combined in fixed order
-// (sigmoid.cu), like the FFMA kernel.
+//
+// K and V are converted ONCE per call into the operand images the MMA reads (bf16 hi|lo, 128B-swizzled, one 32 KB
+// block per 128-key tile and head: sigmoid_prepare_kernel), so the main kernel streams them with one TMA bulk copy
+// per tile instead of re-converting them for every query tile.
+// Warp roles: 0-7 sigmoid, 8 K loader, 9 V loader, 10 MMA issuer.  K stages are released as soon as S = QK^T has
+// been computed, V stages after P V; the MMA thread issues S(j+1) before P V(j), so the sigmoid of tile j+1 overlaps
+// the P V product of tile j.  Small N: the key range is split over gridDim.z and the un-normalised partials are
+// combined in fixed order (sigmoid.cu), like the FFMA kernel.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -23,11 +28,13 @@ namespace {
 
 constexpr int kT = 128;                  // query rows per CTA = keys per tile
 constexpr int kOpT = kT * 128;           // one bf16 [128 rows][64] operand tile: 16 KB
-constexpr int kStageS = 4 * kOpT;        // Khi | Klo | Vhi | Vlo
-constexpr int kSmemSig = 2 * kOpT + 2 * kStageS + 4 * kOpT + 1024;   // Q + 2 stages + P hi/lo (two 64-key sub-tiles each)
+constexpr int kImg = 2 * kOpT;           // hi | lo image of one tile: 32 KB
+constexpr int kSigWarps = 11, kSigThreads = kSigWarps * 32;
+constexpr int kSmemSig = kImg + 2 * kImg + 2 * kImg + 2 * kImg + 1024;   // Q + 2 K stages + 2 V stages + P (hi, lo)
 
 struct SigTcArgs {
-    const float *q, *k, *v;
+    const float* q;
+    const uint8_t *kimg, *vimg;   // [H | Hv][ltiles] x 32 KB operand images
     int64_t N, L;
     int H, Hv, ksplit;
     float *out, *rowsum;     // ksplit == 1: final results
@@ -42,13 +49,55 @@ __device__ __forceinline__ float sigmoid_fast(float s) {
     return r;
 }
 
-__global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __grid_constant__ SigTcArgs p) {
+// [128 rows][64 floats] of one head -> bf16 hi/lo image (rows of 128 B, 8-row swizzle atoms).  The same layout
+// serves Q / K as K-major operands and V as the MN-major B operand (keys = K index).  256 threads.
+template <bool kToShared>
+__device__ __forceinline__ void convert_tile(const float* src, int heads, int head, int64_t row0, int64_t nrows, int tid,
+                                             uint32_t s_hi, uint8_t* g_hi) {
+    float x[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = tid + 256 * j;
+        const int64_t row = row0 + (t >> 3);
+        if (row < nrows) ldg256_keep(src + (row * heads + head) * kDim + (t & 7) * 8, x[j]);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[j][i] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = tid + 256 * j;
+        uint4 hi, lo;
+        split8(x[j], hi, lo);
+        const uint32_t off = sw128(t >> 3, t & 7);
+        if (kToShared) {
+            sts128(s_hi + off, hi);
+            sts128(s_hi + kOpT + off, lo);
+        } else {
+            *reinterpret_cast<uint4*>(g_hi + off) = hi;
+            *reinterpret_cast<uint4*>(g_hi + kOpT + off) = lo;
+        }
+    }
+}
+
+// grid (ltiles, H + Hv): K heads first, then V heads
+__global__ void __launch_bounds__(256) sigmoid_prepare_kernel(const float* __restrict__ k, const float* __restrict__ v, int64_t L, int H,
+                                                              int Hv, uint8_t* __restrict__ kimg, uint8_t* __restrict__ vimg) {
+    const int64_t t = blockIdx.x, ltiles = gridDim.x;
+    const int y = blockIdx.y;
+    if (y < H) convert_tile<false>(k, H, y, t * kT, L, threadIdx.x, 0, kimg + ((int64_t)y * ltiles + t) * kImg);
+    else convert_tile<false>(v, Hv, y - H, t * kT, L, threadIdx.x, 0, vimg + ((int64_t)(y - H) * ltiles + t) * kImg);
+}
+
+__global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __grid_constant__ SigTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* Qop = base;                      // Qhi | Qlo
-    uint8_t* stages = Qop + 2 * kOpT;         // 2 x (Khi | Klo | Vhi | Vlo)
-    uint8_t* Pop = stages + 2 * kStageS;      // Phi keys 0-63 | Phi keys 64-127 | Plo keys 0-63 | Plo keys 64-127
-    __shared__ uint64_t qfull, kfull[2], kempty[2], sfull[2], sempty[2], pfull, pempty, done;
+    uint8_t* Kst = Qop + kImg;                // 2 x (Khi | Klo)
+    uint8_t* Vst = Kst + 2 * kImg;            // 2 x (Vhi | Vlo)
+    uint8_t* Pop = Vst + 2 * kImg;            // Phi keys 0-63 | Phi keys 64-127 | Plo keys 0-63 | Plo keys 64-127
+    __shared__ uint64_t qfull, kfull[2], kempty[2], vfull[2], vempty[2], sfull[2], sempty[2], pfull, pempty, done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, h = blockIdx.y, hv = (p.Hv == H) ? h : 0;
@@ -59,73 +108,41 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
 
     if (tid == 0) {
         mbar_init(&qfull, 8);
-        for (int s = 0; s < 2; ++s) { mbar_init(&kfull[s], 8); mbar_init(&kempty[s], 1); mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 4); }
-        mbar_init(&pfull, 4); mbar_init(&pempty, 1); mbar_init(&done, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&kfull[s], 1); mbar_init(&kempty[s], 1); mbar_init(&vfull[s], 1); mbar_init(&vempty[s], 1);
+            mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8);
+        }
+        mbar_init(&pfull, 8); mbar_init(&pempty, 1); mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12) tmem_alloc(&tmem_slot, 512);
+    if (warp == 10) tmem_alloc(&tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
     if (warp < 8) {
-        // ===== producers: a [128 rows][64 floats] slice (one head) -> bf16 hi/lo, rows of 128 B, 8-row swizzle atoms.
-        // The same layout serves Q / K as K-major operands and V as the MN-major B operand (keys = K index).
-        auto fill = [&](const float* src, int heads, int head, int64_t row0, int64_t nrows, uint32_t dst_hi, uint32_t dst_lo) {
-            float x[4][8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int t = tid + 256 * j;
-                const int64_t row = row0 + (t >> 3);
-                if (row < nrows) ldg256_keep(src + (row * heads + head) * kDim + (t & 7) * 8, x[j]);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[j][i] = 0.f;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int t = tid + 256 * j;
-                uint4 hi, lo;
-                split8(x[j], hi, lo);
-                const uint32_t off = sw128(t >> 3, t & 7);
-                sts128(dst_hi + off, hi);
-                sts128(dst_lo + off, lo);
-            }
-        };
-        fill(p.q, H, h, n0, p.N, smem_u32(Qop), smem_u32(Qop) + kOpT);
+        // ===== sigmoid: thread = (query row r, key half); S row -> p = sigmoid(s) -> bf16 hi/lo P row
+        const int quad = warp & 3, half = warp >> 2, r = quad * 32 + lane;
+        convert_tile<true>(p.q, H, h, n0, p.N, tid, smem_u32(Qop), nullptr);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&qfull);
-        for (int i = 0; i < T; ++i) {
-            const int s = i & 1;
-            if (i >= 2) mbar_wait(&kempty[s], ((i >> 1) - 1) & 1);
-            const uint32_t sb = smem_u32(stages) + s * kStageS;
-            const int64_t l0 = (t0 + i) * kT;
-            fill(p.k, H, h, l0, p.L, sb, sb + kOpT);
-            fill(p.v, p.Hv, hv, l0, p.L, sb + 2 * kOpT, sb + 3 * kOpT);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&kfull[s]);
-        }
-    } else if (warp < 12) {
-        // ===== sigmoid: thread = query row r; S row -> p = sigmoid(s) -> bf16 P row (A operand of the P V product)
-        const int ew = warp - 8, r = ew * 32 + lane;
-        const uint32_t pbase = smem_u32(Pop);
+
+        const uint32_t pbase = smem_u32(Pop) + half * kOpT;
         float rs[4] = {0.f, 0.f, 0.f, 0.f};
         for (int i = 0; i < T; ++i) {
             const int sbuf = i & 1;
             const int64_t l0 = (t0 + i) * kT;
             mbar_wait(&sfull[sbuf], (i >> 1) & 1);
             tc_fence_after();
-            if (i >= 1) mbar_wait(&pempty, (i - 1) & 1);       // the previous P V product has consumed P
-            const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + sbuf * kT;
-            const int valid = (int)min((int64_t)kT, p.L - l0);
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + sbuf * kT + half * 64;
+            const int valid = (int)min((int64_t)kT, p.L - l0) - half * 64;      // keys of this half that exist
+            uint4 ph[8], pl[8];                                 // this thread's 64 weights, bf16 hi / lo, 8 keys per chunk
             auto tile = [&](auto masked_t) {
                 constexpr bool kMasked = decltype(masked_t)::value;       // only the last key tile has keys >= L
 #pragma unroll
-                for (int c0 = 0; c0 < kT; c0 += 32) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t sreg[32];
                     tmem_ld32(taddr + c0, sreg);
                     tmem_ld_wait32(sreg);
@@ -135,51 +152,72 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             pv[e] = sigmoid_fast(__uint_as_float(sreg[j + e]));
-                            if (kMasked) pv[e] = (int)(c0 + j + e) < valid ? pv[e] : 0.f;
+                            if (kMasked) pv[e] = (c0 + j + e) < valid ? pv[e] : 0.f;
                             rs[e & 3] += pv[e];
                         }
-                        uint4 hi, lo;
-                        split8(pv, hi, lo);
-                        const int cc = (c0 + j) >> 3;       // 16-byte chunk of the 128-key row: sub-tile cc>>3, chunk cc&7
-                        const uint32_t off = (cc >> 3) * kOpT + sw128(r, cc & 7);
-                        sts128(pbase + off, hi);
-                        sts128(pbase + 2 * kOpT + off, lo);
+                        split8(pv, ph[(c0 + j) >> 3], pl[(c0 + j) >> 3]);
                     }
                 }
             };
-            if (valid == kT) tile(std::false_type{}); else tile(std::true_type{});
+            if (valid >= 64) tile(std::false_type{}); else tile(std::true_type{});
+            // S has been read: release the S buffer, then wait until the previous P V product has consumed P.  The
+            // sigmoid above therefore overlaps that product; only the stores below are serialised with it.
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sbuf]);
+            if (i >= 1) mbar_wait(&pempty, (i - 1) & 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t off = sw128(r, c);               // 16-byte chunk c of this half's 64-key row
+                sts128(pbase + off, ph[c]);
+                sts128(pbase + 2 * kOpT + off, pl[c]);
+            }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&sempty[sbuf]); mbar_arrive(&pfull); }
+            if (lane == 0) mbar_arrive(&pfull);
         }
-        // ---- O / rowsum
-        const float rowsum = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+        // ---- O / rowsum: the two key halves of a row exchange their partial row sums through (now free) P memory
         mbar_wait(&done, 0);
         tc_fence_after();
+        float* rsx = reinterpret_cast<float*>(Pop);
+        rsx[half * kT + r] = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rowsum = rsx[r] + rsx[kT + r];
         const int64_t row = n0 + r;
         float* o_dst = p.ksplit > 1 ? p.pout + (int64_t)blockIdx.z * p.N * H * kDim : p.out;
         float* r_dst = p.ksplit > 1 ? p.prs + (int64_t)blockIdx.z * p.N * H : p.rowsum;
         const float inv = p.ksplit > 1 ? 1.f : 1.f / rowsum;
+        uint32_t o[32];                                   // this thread: output columns [half * 32, +32)
+        if (T > 0) {
+            tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + 2 * kT + half * 32, o);
+            tmem_ld_wait32(o);
+        } else {
 #pragma unroll
-        for (int c0 = 0; c0 < kDim; c0 += 32) {
-            uint32_t o[32];
-            if (T > 0) {
-                tmem_ld32(tmem + ((uint32_t)(ew * 32) << 16) + 2 * kT + c0, o);
-                tmem_ld_wait32(o);
-            } else {
+            for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        if (row < p.N) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = 0u;
-            }
-            if (row < p.N) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(o_dst + (row * H + h) * kDim + c0 + j) =
-                        make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv, __uint_as_float(o[j + 2]) * inv,
-                                    __uint_as_float(o[j + 3]) * inv);
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o_dst + (row * H + h) * kDim + half * 32 + j) =
+                    make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv, __uint_as_float(o[j + 2]) * inv,
+                                __uint_as_float(o[j + 3]) * inv);
+            if (half == 0) r_dst[row * H + h] = rowsum;
+        }
+    } else if (warp == 8 || warp == 9) {
+        // ===== loaders: one 32 KB bulk copy per tile (warp 8: K images, warp 9: V images)
+        if (lane == 0) {
+            const bool isk = warp == 8;
+            const uint8_t* img = isk ? p.kimg + ((int64_t)h * ltiles + t0) * kImg : p.vimg + ((int64_t)hv * ltiles + t0) * kImg;
+            uint64_t* full = isk ? kfull : vfull;
+            uint64_t* empty = isk ? kempty : vempty;
+            const uint32_t dst = smem_u32(isk ? Kst : Vst);
+            for (int i = 0; i < T; ++i) {
+                const int s = i & 1;
+                if (i >= 2) mbar_wait(&empty[s], ((i >> 1) - 1) & 1);
+                mbar_expect_tx(&full[s], kImg);
+                tma_load_1d(dst + s * kImg, img + (int64_t)i * kImg, kImg, &full[s]);
             }
         }
-        if (row < p.N) r_dst[row * H + h] = rowsum;
     } else if (lane == 0) {
         // ===== MMA issuer
         const uint32_t idS = make_idesc(kT, kT, 0, 0);          // S = Q K^T : both operands K-major
@@ -190,7 +228,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
             mbar_wait(&kfull[s], (i >> 1) & 1);
             if (i >= 2) mbar_wait(&sempty[s], ((i >> 1) - 1) & 1);
             tc_fence_after();
-            const uint32_t sb = smem_u32(stages) + s * kStageS;
+            const uint32_t sb = smem_u32(Kst) + s * kImg;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t qhi = make_desc(qb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(qb + kOpT + ks * 32, kKmajLBO, kKmajSBO);
@@ -200,23 +238,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
                 umma(tmem + s * kT, qhi, klo, idS, 1u);
             }
             umma_commit(&sfull[s]);
+            umma_commit(&kempty[s]);
         };
         auto issue_PV = [&](int i) {
             const int s = i & 1;
+            mbar_wait(&vfull[s], (i >> 1) & 1);
             mbar_wait(&pfull, i & 1);
             tc_fence_after();
-            const uint32_t sb = smem_u32(stages) + s * kStageS;
+            const uint32_t sb = smem_u32(Vst) + s * kImg;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {                     // 16 keys per step
                 const uint64_t pa = make_desc(pb + (ks >> 2) * kOpT + (ks & 3) * 32, kKmajLBO, kKmajSBO);
                 const uint64_t pl = make_desc(pb + (2 + (ks >> 2)) * kOpT + (ks & 3) * 32, kKmajLBO, kKmajSBO);
-                const uint64_t vhi = make_desc(sb + 2 * kOpT + ks * 2048, kOpT, 1024), vlo = make_desc(sb + 3 * kOpT + ks * 2048, kOpT, 1024);
+                const uint64_t vhi = make_desc(sb + ks * 2048, kOpT, 1024), vlo = make_desc(sb + kOpT + ks * 2048, kOpT, 1024);
                 umma(tmem + 2 * kT, pa, vhi, idO, (i > 0 || ks > 0) ? 1u : 0u);
                 umma(tmem + 2 * kT, pa, vlo, idO, 1u);
                 umma(tmem + 2 * kT, pl, vhi, idO, 1u);
             }
             umma_commit(&pempty);
-            umma_commit(&kempty[s]);
+            umma_commit(&vempty[s]);
         };
         mbar_wait(&qfull, 0);
         if (T > 0) issue_S(0);
@@ -229,16 +269,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) sigmoid_fwd_tc_kernel(const __g
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem, 512);
+    if (warp == 10) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
 
 bool sigmoid_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D) {
-    return N >= 1 && L >= 1 && H >= 1 && H <= 65535 && (Hv == H || Hv == 1) && M == kDim && D == kDim;
+    return N >= 1 && L >= 1 && H >= 1 && H + Hv <= 65535 && (Hv == H || Hv == 1) && M == kDim && D == kDim;
 }
 
-// Key split: CTAs = query tiles x heads x s run in waves of one CTA per SM (224 KB of shared memory each); pick the
+// Key split: CTAs = query tiles x heads x s run in waves of one CTA per SM (225 KB of shared memory each); pick the
 // s that minimises waves x (key tiles per CTA + fixed per-CTA cost), with a small charge for the combine pass.
 int sigmoid_tc_ksplit(int64_t N, int64_t L, int H) {
     const int64_t ctas = ((N + kT - 1) / kT) * H, ltiles = (L + kT - 1) / kT, sms = sm_count();
@@ -252,17 +292,25 @@ int sigmoid_tc_ksplit(int64_t N, int64_t L, int H) {
     return best;
 }
 
+// bytes of the K / V operand images (after the key-split partials in the workspace), incl. 1 KB alignment slack
+int64_t sigmoid_tc_image_bytes(int64_t L, int H, int Hv) { return ((L + kT - 1) / kT) * (int64_t)(H + Hv) * kImg + 1024; }
+
 int sigmoid_fwd_tc(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv,
-                   float* out, float* rowsum, float* pout, float* prs, int ksplit, cudaStream_t st) {
+                   float* out, float* rowsum, float* pout, float* prs, int ksplit, void* images, cudaStream_t st) {
     DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG,
                 "sigmoid(tcgen05): q/k/v must be 32-byte aligned");
+    const int64_t ltiles = (L + kT - 1) / kT;
+    uint8_t* kimg = (uint8_t*)(((uintptr_t)images + 1023) & ~(uintptr_t)1023);
+    uint8_t* vimg = kimg + ltiles * H * kImg;
+    sigmoid_prepare_kernel<<<dim3((unsigned)ltiles, (unsigned)(H + Hv)), 256, 0, st>>>(k, v, L, H, Hv, kimg, vimg);
+    DIF_LAUNCH_OK();
     SigTcArgs a{};
-    a.q = q; a.k = k; a.v = v; a.N = N; a.L = L; a.H = H; a.Hv = Hv; a.ksplit = ksplit;
+    a.q = q; a.kimg = kimg; a.vimg = vimg; a.N = N; a.L = L; a.H = H; a.Hv = Hv; a.ksplit = ksplit;
     a.out = out; a.rowsum = rowsum; a.pout = pout; a.prs = prs;
     static bool attr = false;
     if (!attr) { DIF_CUDA_OK(cudaFuncSetAttribute(sigmoid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSig)); attr = true; }
     dim3 grid((unsigned)((N + kT - 1) / kT), (unsigned)H, (unsigned)ksplit);
-    sigmoid_fwd_tc_kernel<<<grid, kThreadsTC, kSmemSig, st>>>(a);
+    sigmoid_fwd_tc_kernel<<<grid, kSigThreads, kSmemSig, st>>>(a);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }
