@@ -14,9 +14,10 @@
 // K and V are converted ONCE per call into the operand images the MMA reads (bf16 hi|lo, 128B-swizzled, one 32 KB
 // block per 128-key tile and head: sigmoid_prepare_kernel), so the main kernel streams them with one TMA bulk copy
 // per tile instead of re-converting them for every query tile.
-// Warp roles: 0-7 sigmoid, 8 K loader, 9 V loader, 10 MMA issuer.  K stages are released as soon as S = QK^T has
-// been computed, V stages after P V; the MMA thread issues S(j+1) before P V(j), so the sigmoid of tile j+1 overlaps
-// the P V product of tile j.  Small N: the key range is split over gridDim.z and the un-normalised partials are
+// Warp roles: 0-7 sigmoid, 8 K loader, 9 V loader, 10 MMA issuer.  The sigmoid (MUFU-bound) is the critical
+// resource, so shared memory goes to a double-buffered P (the sigmoid of tile j+1 never waits for the P V product of
+// tile j) and K / V get one stage each: the K stage is released as soon as S = QK^T is done, the V stage after P V,
+// and the next tile streams in while the sigmoid runs.  The MMA thread issues S(j+1) before P V(j).  Small N: the key range is split over gridDim.z and the un-normalised partials are
 // combined in fixed order (sigmoid.cu), like the FFMA kernel.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -30,7 +31,8 @@ constexpr int kT = 128;                  // query rows per CTA = keys per tile
 constexpr int kOpT = kT * 128;           // one bf16 [128 rows][64] operand tile: 16 KB
 constexpr int kImg = 2 * kOpT;           // hi | lo image of one tile: 32 KB
 constexpr int kSigWarps = 11, kSigThreads = kSigWarps * 32;
-constexpr int kSmemSig = kImg + 2 * kImg + 2 * kImg + 2 * kImg + 1024;   // Q + 2 K stages + 2 V stages + P (hi, lo)
+constexpr int kPBuf = 2 * kImg;          // one P buffer: Phi (keys 0-63 | 64-127) | Plo (same)
+constexpr int kSmemSig = kImg + kImg + kImg + 2 * kPBuf + 1024;          // Q + K + V + 2 P buffers
 
 struct SigTcArgs {
     const float* q;
@@ -41,19 +43,43 @@ struct SigTcArgs {
     float *pout, *prs;       // ksplit  > 1: [ksplit][N,H,64] un-normalised sums, [ksplit][N,H] row sums
 };
 
-// 1 / (1 + 2^(-s log2 e)): two MUFU ops, branch-free (ex2 overflow -> +inf -> rcp -> 0; underflow -> 1)
-__device__ __forceinline__ float sigmoid_fast(float s) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
-    return r;
+// Eight sigmoids from pre-scaled scores x = -s log2(e) (the scale is folded into Q): p = 1 / (1 + 2^x), two MUFU
+// ops per element and branch-free (ex2 overflow -> +inf -> rcp -> 0; underflow -> 1).  Everything else is packed
+// f32x2 arithmetic (FADD2 / FFMA2): the sigmoid warps are issue-bound, not MUFU-bound.
+template <bool kMasked>
+__device__ __forceinline__ void sigmoid8(const uint32_t* x, int nvalid, float2 (&rs)[2], uint4& hi, uint4& lo) {
+    float2 pr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float2 e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(__uint_as_float(x[2 * k])));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(__uint_as_float(x[2 * k + 1])));
+        e = __fadd2_rn(e, make_float2(1.f, 1.f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pr[k].x) : "f"(e.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pr[k].y) : "f"(e.y));
+        if (kMasked) {
+            pr[k].x = 2 * k < nvalid ? pr[k].x : 0.f;
+            pr[k].y = 2 * k + 1 < nvalid ? pr[k].y : 0.f;
+        }
+        rs[k & 1] = __fadd2_rn(rs[k & 1], pr[k]);
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = bf2_bits(pr[k].x, pr[k].y);
+        const float2 hf = make_float2(__uint_as_float(h[k] << 16), __uint_as_float(h[k] & 0xffff0000u));
+        const float2 d = __ffma2_rn(hf, make_float2(-1.f, -1.f), pr[k]);      // exact: p - bf16(p)
+        l[k] = bf2_bits(d.x, d.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // [128 rows][64 floats] of one head -> bf16 hi/lo image (rows of 128 B, 8-row swizzle atoms).  The same layout
 // serves Q / K as K-major operands and V as the MN-major B operand (keys = K index).  256 threads.
 template <bool kToShared>
 __device__ __forceinline__ void convert_tile(const float* src, int heads, int head, int64_t row0, int64_t nrows, int tid,
-                                             uint32_t s_hi, uint8_t* g_hi) {
+                                             uint32_t s_hi, uint8_t* g_hi, float scale = 1.f) {
     float x[4][8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -69,6 +95,10 @@ __device__ __forceinline__ void convert_tile(const float* src, int heads, int he
     for (int j = 0; j < 4; ++j) {
         const int t = tid + 256 * j;
         uint4 hi, lo;
+        if (kToShared) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[j][i] *= scale;
+        }
         split8(x[j], hi, lo);
         const uint32_t off = sw128(t >> 3, t & 7);
         if (kToShared) {
@@ -94,10 +124,10 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* Qop = base;                      // Qhi | Qlo
-    uint8_t* Kst = Qop + kImg;                // 2 x (Khi | Klo)
-    uint8_t* Vst = Kst + 2 * kImg;            // 2 x (Vhi | Vlo)
-    uint8_t* Pop = Vst + 2 * kImg;            // Phi keys 0-63 | Phi keys 64-127 | Plo keys 0-63 | Plo keys 64-127
-    __shared__ uint64_t qfull, kfull[2], kempty[2], vfull[2], vempty[2], sfull[2], sempty[2], pfull, pempty, done;
+    uint8_t* Kst = Qop + kImg;                // Khi | Klo   (one stage: the next tile is fetched while the sigmoid runs)
+    uint8_t* Vst = Kst + kImg;                // Vhi | Vlo
+    uint8_t* Pop = Vst + kImg;                // 2 x (Phi keys 0-63 | Phi keys 64-127 | Plo keys 0-63 | Plo keys 64-127)
+    __shared__ uint64_t qfull, kfull, kempty, vfull, vempty, sfull[2], sempty[2], pfull[2], pempty[2], done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, h = blockIdx.y, hv = (p.Hv == H) ? h : 0;
@@ -108,11 +138,9 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __
 
     if (tid == 0) {
         mbar_init(&qfull, 8);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&kfull[s], 1); mbar_init(&kempty[s], 1); mbar_init(&vfull[s], 1); mbar_init(&vempty[s], 1);
-            mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8);
-        }
-        mbar_init(&pfull, 8); mbar_init(&pempty, 1); mbar_init(&done, 1);
+        mbar_init(&kfull, 1); mbar_init(&kempty, 1); mbar_init(&vfull, 1); mbar_init(&vempty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); mbar_init(&pfull[s], 8); mbar_init(&pempty[s], 1); }
+        mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 10) tmem_alloc(&tmem_slot, 512);
@@ -124,63 +152,50 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __
     if (warp < 8) {
         // ===== sigmoid: thread = (query row r, key half); S row -> p = sigmoid(s) -> bf16 hi/lo P row
         const int quad = warp & 3, half = warp >> 2, r = quad * 32 + lane;
-        convert_tile<true>(p.q, H, h, n0, p.N, tid, smem_u32(Qop), nullptr);
+        convert_tile<true>(p.q, H, h, n0, p.N, tid, smem_u32(Qop), nullptr, -1.4426950408889634f);   // S = -log2(e) Q K^T
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&qfull);
 
-        const uint32_t pbase = smem_u32(Pop) + half * kOpT;
-        float rs[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         for (int i = 0; i < T; ++i) {
             const int sbuf = i & 1;
             const int64_t l0 = (t0 + i) * kT;
+            const uint32_t pbase = smem_u32(Pop) + sbuf * kPBuf + half * kOpT;
             mbar_wait(&sfull[sbuf], (i >> 1) & 1);
             tc_fence_after();
+            if (i >= 2) mbar_wait(&pempty[sbuf], ((i >> 1) - 1) & 1);    // P V of tile i-2 has consumed this P buffer
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + sbuf * kT + half * 64;
             const int valid = (int)min((int64_t)kT, p.L - l0) - half * 64;      // keys of this half that exist
-            uint4 ph[8], pl[8];                                 // this thread's 64 weights, bf16 hi / lo, 8 keys per chunk
             auto tile = [&](auto masked_t) {
                 constexpr bool kMasked = decltype(masked_t)::value;       // only the last key tile has keys >= L
+                uint32_t sa[32], sb[32];
+                tmem_ld32(taddr, sa);
+                tmem_ld32(taddr + 32, sb);
+                tmem_ld_wait32(sa);
+                tmem_ld_wait32(sb);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[sbuf]);      // S is in registers: the MMA may overwrite this buffer
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t sreg[32];
-                    tmem_ld32(taddr + c0, sreg);
-                    tmem_ld_wait32(sreg);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float pv[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            pv[e] = sigmoid_fast(__uint_as_float(sreg[j + e]));
-                            if (kMasked) pv[e] = (c0 + j + e) < valid ? pv[e] : 0.f;
-                            rs[e & 3] += pv[e];
-                        }
-                        split8(pv, ph[(c0 + j) >> 3], pl[(c0 + j) >> 3]);
-                    }
+                for (int j = 0; j < 64; j += 8) {
+                    uint4 hi, lo;
+                    sigmoid8<kMasked>(j < 32 ? &sa[j & 31] : &sb[j & 31], valid - j, rs, hi, lo);
+                    const uint32_t off = sw128(r, j >> 3);      // 16-byte chunk of this half's 64-key row
+                    sts128(pbase + off, hi);
+                    sts128(pbase + 2 * kOpT + off, lo);
                 }
             };
             if (valid >= 64) tile(std::false_type{}); else tile(std::true_type{});
-            // S has been read: release the S buffer, then wait until the previous P V product has consumed P.  The
-            // sigmoid above therefore overlaps that product; only the stores below are serialised with it.
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[sbuf]);
-            if (i >= 1) mbar_wait(&pempty, (i - 1) & 1);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t off = sw128(r, c);               // 16-byte chunk c of this half's 64-key row
-                sts128(pbase + off, ph[c]);
-                sts128(pbase + 2 * kOpT + off, pl[c]);
-            }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pfull);
+            if (lane == 0) mbar_arrive(&pfull[sbuf]);
         }
         // ---- O / rowsum: the two key halves of a row exchange their partial row sums through (now free) P memory
         mbar_wait(&done, 0);
         tc_fence_after();
         float* rsx = reinterpret_cast<float*>(Pop);
-        rsx[half * kT + r] = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+        rsx[half * kT + r] = (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float rowsum = rsx[r] + rsx[kT + r];
         const int64_t row = n0 + r;
@@ -208,27 +223,26 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __
         if (lane == 0) {
             const bool isk = warp == 8;
             const uint8_t* img = isk ? p.kimg + ((int64_t)h * ltiles + t0) * kImg : p.vimg + ((int64_t)hv * ltiles + t0) * kImg;
-            uint64_t* full = isk ? kfull : vfull;
-            uint64_t* empty = isk ? kempty : vempty;
+            uint64_t* full = isk ? &kfull : &vfull;
+            uint64_t* empty = isk ? &kempty : &vempty;
             const uint32_t dst = smem_u32(isk ? Kst : Vst);
             for (int i = 0; i < T; ++i) {
-                const int s = i & 1;
-                if (i >= 2) mbar_wait(&empty[s], ((i >> 1) - 1) & 1);
-                mbar_expect_tx(&full[s], kImg);
-                tma_load_1d(dst + s * kImg, img + (int64_t)i * kImg, kImg, &full[s]);
+                if (i >= 1) mbar_wait(empty, (i - 1) & 1);
+                mbar_expect_tx(full, kImg);
+                tma_load_1d(dst, img + (int64_t)i * kImg, kImg, full);
             }
         }
     } else if (lane == 0) {
         // ===== MMA issuer
         const uint32_t idS = make_idesc(kT, kT, 0, 0);          // S = Q K^T : both operands K-major
         const uint32_t idO = make_idesc(kT, kDim, 0, 1);        // O += P V  : A = P K-major, B = V MN-major
-        const uint32_t qb = smem_u32(Qop), pb = smem_u32(Pop);
+        const uint32_t qb = smem_u32(Qop);
         auto issue_S = [&](int i) {
             const int s = i & 1;
-            mbar_wait(&kfull[s], (i >> 1) & 1);
+            mbar_wait(&kfull, i & 1);
             if (i >= 2) mbar_wait(&sempty[s], ((i >> 1) - 1) & 1);
             tc_fence_after();
-            const uint32_t sb = smem_u32(Kst) + s * kImg;
+            const uint32_t sb = smem_u32(Kst);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t qhi = make_desc(qb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(qb + kOpT + ks * 32, kKmajLBO, kKmajSBO);
@@ -238,14 +252,14 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __
                 umma(tmem + s * kT, qhi, klo, idS, 1u);
             }
             umma_commit(&sfull[s]);
-            umma_commit(&kempty[s]);
+            umma_commit(&kempty);
         };
         auto issue_PV = [&](int i) {
             const int s = i & 1;
-            mbar_wait(&vfull[s], (i >> 1) & 1);
-            mbar_wait(&pfull, i & 1);
+            mbar_wait(&vfull, i & 1);
+            mbar_wait(&pfull[s], (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t sb = smem_u32(Vst) + s * kImg;
+            const uint32_t sb = smem_u32(Vst), pb = smem_u32(Pop) + s * kPBuf;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {                     // 16 keys per step
                 const uint64_t pa = make_desc(pb + (ks >> 2) * kOpT + (ks & 3) * 32, kKmajLBO, kKmajSBO);
@@ -255,8 +269,8 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigmoid_fwd_tc_kernel(const __
                 umma(tmem + 2 * kT, pa, vlo, idO, 1u);
                 umma(tmem + 2 * kT, pl, vhi, idO, 1u);
             }
-            umma_commit(&pempty);
-            umma_commit(&vempty[s]);
+            umma_commit(&pempty[s]);
+            umma_commit(&vempty);
         };
         mbar_wait(&qfull, 0);
         if (T > 0) issue_S(0);

@@ -200,9 +200,20 @@ def test_simple_full_size_properties(impl):
 
 
 # ---------------------------------------------------------------------------------- sigmoid
+@pytest.fixture(params=["generic", "tcgen05"])
+def sigmoid_impl(request):
+    """Run the test once on the fp32 FFMA forward and once on the tcgen05 forward (M == D == 64 only)."""
+    from difformer_b200 import ops
+    ops.set_sigmoid_impl(request.param)
+    yield request.param
+    ops.set_sigmoid_impl("auto")
+
+
 @pytest.mark.parametrize("name", [n for n in sorted(ATT) if n.startswith("sigmoid")])
-def test_sigmoid_forward_backward(name):
+def test_sigmoid_forward_backward(name, sigmoid_impl):
     c = ATT[name]
+    if sigmoid_impl == "tcgen05" and (c["q"].shape[-1] != 64 or c["v"].shape[-1] != 64):
+        pytest.skip("tcgen05 sigmoid needs M == D == 64")
     q, k, v = (dev(c[n]).requires_grad_(True) for n in "qkv")
     out = difformer.full_attention_conv(q, k, v, "sigmoid")
     assert O.rel_err(out, c["out"]) < TOL
@@ -211,14 +222,47 @@ def test_sigmoid_forward_backward(name):
         assert O.rel_err(got, gold) < TOL
 
 
-@pytest.mark.parametrize("n,l,h,hv,d", [(1, 1, 1, 1, 64), (63, 200, 2, 2, 64), (2708, 2708, 1, 1, 64), (300, 129, 4, 1, 32), (70, 70, 1, 1, 128)])
-def test_sigmoid_shapes(n, l, h, hv, d):
+@pytest.mark.parametrize("n,l,h,hv,d", [(1, 1, 1, 1, 64), (63, 200, 2, 2, 64), (2708, 2708, 1, 1, 64), (300, 129, 4, 1, 32), (70, 70, 1, 1, 128),
+                                        (128, 128, 1, 1, 64), (129, 257, 3, 3, 64), (1000, 4500, 2, 1, 64)])
+def test_sigmoid_shapes(n, l, h, hv, d, sigmoid_impl):
+    if sigmoid_impl == "tcgen05" and d != 64:
+        from difformer_b200 import ops
+        with pytest.raises(RuntimeError):      # pinned to tcgen05 on an unsupported shape: loud error, no silent fallback
+            difformer.full_attention_conv(dev(torch.zeros(n, h, d)), dev(torch.zeros(l, h, d)), dev(torch.zeros(l, hv, d)), "sigmoid")
+        return
     gen = torch.Generator().manual_seed(n + l)
     q = torch.randn(n, h, d, generator=gen) * 0.3
     k = torch.randn(l, h, d, generator=gen) * 0.3
     v = torch.randn(l, hv, d, generator=gen)
     out = difformer.full_attention_conv(dev(q), dev(k), dev(v), "sigmoid")
     assert O.rel_err(out, O.sigmoid_attention(q.double(), k.double(), v.double())) < TOL
+
+
+def test_sigmoid_tc_extremes_and_intermediates():
+    """tcgen05 sigmoid: saturated scores (|s| up to ~90: exp overflow / underflow paths), the saved row sums, and
+    run-to-run determinism (fixed-order key-split combine, no atomics)."""
+    from difformer_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    n, l = 300, 700
+    q = torch.randn(n, 1, 64, generator=gen) * 1.5
+    k = torch.randn(l, 1, 64, generator=gen) * 1.5          # s = q.k ~ N(0, 18^2): both tails of the sigmoid
+    v = torch.randn(l, 1, 64, generator=gen)
+    ops.set_sigmoid_impl("tcgen05")
+    try:
+        qd, kd, vd = (dev(t).requires_grad_(True) for t in (q, k, v))
+        out = difformer.full_attention_conv(qd, kd, vd, "sigmoid")
+        ref = O.sigmoid_attention(q.double(), k.double(), v.double())
+        assert torch.isfinite(out).all()
+        assert O.rel_err(out, ref) < TOL
+        assert torch.equal(out, difformer.full_attention_conv(qd, kd, vd, "sigmoid"))
+        rowsum = out.grad_fn.saved_tensors[4] if len(out.grad_fn.saved_tensors) > 4 else None
+        if rowsum is not None:
+            p = torch.sigmoid(torch.einsum("nhm,lhm->nlh", q.double(), k.double())).sum(1)
+            assert O.rel_err(rowsum.cpu().double(), p) < 1e-4
+        out.backward(torch.ones_like(out))      # the FFMA backward consumes the tcgen05 forward's (out, rowsum)
+        assert torch.isfinite(qd.grad).all() and torch.isfinite(kd.grad).all() and torch.isfinite(vd.grad).all()
+    finally:
+        ops.set_sigmoid_impl("auto")
 
 
 # ---------------------------------------------------------------------------------- gcn_conv
