@@ -230,6 +230,19 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    collective = args.collective
+    if comm is not None:
+        # watchdog (csrc/comm.cu): a rank whose kernel waited 2 s for a peer's flag reports it here; then every rank
+        # switches to the NCCL all-reduce of the partials so that the run still produces a valid number
+        bad = torch.tensor([1.0 if comm.exchange(plen, dev).timed_out() else 0.0], dtype=torch.float32, device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+        if float(bad.item()) > 0:
+            comm, collective = None, "nccl"
+            if rank == 0:
+                print("bench: the NVLink exchange timed out waiting for a peer; falling back to NCCL", file=sys.stderr)
+            for _ in range(3):
+                step()
+            barrier()
     sampler = ClockSampler(dev)
     barrier()
     sampler.begin()
@@ -264,7 +277,7 @@ def run_ours(args):
     rs = None
     if group is not None:
         from difformer_b200.sharded import RowShardedAttention
-        rs = RowShardedAttention(int(n_total), group, nvlink=(args.collective == "nvlink"))
+        rs = RowShardedAttention(int(n_total), group, nvlink=(collective == "nvlink"))
 
     # Double-buffered, three streams: the upload of step i+1 (copy engine, H2D) overlaps the kernels of step i and the
     # download of step i-1 (second copy engine, D2H).  Every step still uploads its own Q, K, V from pinned host
@@ -367,7 +380,7 @@ def run_ours(args):
                            "rows_per_gpu": N_NODES, "global_rows": int(n_total),
                            "parallelism": "single GPU" if world == 1 else (
                                f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
-                               ("fused into the pass-1 kernel tail over peer-mapped NVLink memory (no NCCL call)" if args.collective == "nvlink" else "NCCL")),
+                               ("fused into the pass-1 kernel tail over peer-mapped NVLink memory (no NCCL call)" if collective == "nvlink" else "NCCL")),
                            "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps",
                            "simple_impl": args.simple_impl or "auto"},
                 "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,

@@ -15,7 +15,7 @@
 namespace dif {
 namespace {
 
-constexpr int kMaxRanks = 16;
+constexpr int kMaxRanks = kCommMaxRanks;
 
 struct CommArgs {
     float* bufs[kMaxRanks];   // peer-mapped base pointers, index = rank
@@ -26,8 +26,11 @@ struct CommArgs {
     float* out;
 };
 
-// flags: [2 slots][kMaxRanks][256 slices] u64 after the two data slots.  The fused pass-1 tail
-// (simple_sm100.cu) uses one flag per (slot, rank, column slice); this stand-alone kernel uses slice 255.
+// flags: [2 slots][kMaxRanks][256 slices] u64 after the two data slots, then one u64 status word.  The fused pass-1
+// tail (simple_sm100.cu) uses one flag per (slot, rank, column slice); this stand-alone kernel uses slice 255.
+// Watchdog: a wait that sees no flag for kCommTimeoutNs gives up, sets the status word of the LOCAL buffer and lets
+// the kernel finish with a meaningless sum, so that a peer that died or never launched cannot hang the GPU;
+// dif_comm_status() reports it to the host.
 __device__ __forceinline__ unsigned long long* flag_ptr(float* base, int64_t slot_floats, int idx) {
     return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + (size_t)idx * 256 + 255;
 }
@@ -43,10 +46,8 @@ __global__ void __launch_bounds__(256) allreduce_kernel(CommArgs a) {
     // (b) every CTA waits for all ranks' flags in the local buffer
     if (threadIdx.x < a.world) {
         const unsigned long long* f = flag_ptr(a.bufs[a.rank], a.slot_floats, slot * kMaxRanks + threadIdx.x);
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-        } while (v != a.seq);
+        unsigned long long* status = comm_status_ptr(a.bufs[a.rank], a.slot_floats);
+        comm_wait_flag(f, a.seq, status);
     }
     __syncthreads();
     // (c) sum the slots in rank order (fixed order: every rank computes the same bits)
@@ -80,7 +81,16 @@ using namespace dif;
 
 extern "C" int64_t dif_comm_buffer_bytes(int64_t len) {
     const int64_t slot = (len + 63) & ~(int64_t)63;
-    return 2 * slot * (int64_t)sizeof(float) + 2 * kMaxRanks * 256 * (int64_t)sizeof(unsigned long long);
+    return 2 * slot * (int64_t)sizeof(float) + 2 * kMaxRanks * 256 * (int64_t)sizeof(unsigned long long) + 64;   // + status word
+}
+
+extern "C" int dif_comm_status(const void* own_buf, int64_t len, int* timed_out) {
+    DIF_REQUIRE(own_buf && timed_out && len > 0, DIF_EARG, "comm_status: bad argument");
+    const int64_t slot = (len + 63) & ~(int64_t)63;
+    unsigned long long v = 0;
+    DIF_CUDA_OK(cudaMemcpy(&v, comm_status_ptr((float*)own_buf, slot), sizeof(v), cudaMemcpyDeviceToHost));
+    *timed_out = v != 0;
+    return DIF_OK;
 }
 
 extern "C" int64_t dif_comm_slot_offset_bytes(int64_t len, unsigned long long seq) {

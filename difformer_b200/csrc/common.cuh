@@ -91,6 +91,30 @@ int simple_apply_generic(const float* q, const float* partials, double n_total, 
 int64_t simple_generic_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 
 bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D);
+// ---- peer-mapped exchange buffers (comm.cu, simple_sm100.cu): [2 data slots | flags [2][16][256] u64 | status u64]
+constexpr int kCommMaxRanks = 16;
+constexpr unsigned long long kCommTimeoutNs = 2000000000ull;          // 2 s without a peer's flag => give up
+__host__ __device__ __forceinline__ unsigned long long* comm_status_ptr(float* base, int64_t slot_floats) {
+    return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + (size_t)2 * kCommMaxRanks * 256;
+}
+// spin until *flag == seq (system scope); bounded: on timeout (or if an earlier wait already timed out) set *status
+__device__ __forceinline__ void comm_wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned long long* status) {
+    unsigned long long got, t0 = 0;
+    unsigned int spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(flag) : "memory");
+        if (got == seq) return;
+        if ((++spins & 1023u) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kCommTimeoutNs || *reinterpret_cast<volatile unsigned long long*>(status) != 0) {
+                atomicMax(status, 1ull);
+                return;
+            }
+        }
+    }
+}
 // sigmoid_sm100.cu
 bool sigmoid_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D);
 int sigmoid_tc_ksplit(int64_t N, int64_t L, int H);

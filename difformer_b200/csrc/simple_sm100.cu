@@ -430,10 +430,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                 asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(sh.seq) : "memory");
                 const unsigned long long* w = reinterpret_cast<const unsigned long long*>(sh.bufs[sh.rank] + 2 * sh.slot_floats) +
                                               ((size_t)(xslot * kShardMaxRanks + tid) * 256 + sl);
-                unsigned long long got;
-                do {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(w) : "memory");
-                } while (got != sh.seq);
+                comm_wait_flag(w, sh.seq, comm_status_ptr(sh.bufs[sh.rank], sh.slot_floats));   // bounded (watchdog, comm.cu)
             }
             __syncthreads();
             if (live) {

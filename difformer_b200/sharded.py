@@ -91,6 +91,16 @@ class PartialsExchange:
                         "dif_simple_reduce_allreduce")
         return partials, prepared
 
+    def timed_out(self) -> bool:
+        """True if a kernel of this rank gave up waiting for a peer (2 s watchdog): results since then are invalid.
+        Synchronises the device."""
+        import ctypes
+        torch.cuda.synchronize(self.device)
+        flag = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.dif_comm_status(self.base, self.len, ctypes.byref(flag)), "dif_comm_status")
+        return bool(flag.value)
+
     def next_slot(self) -> torch.Tensor:
         """The data slot of the next call (fp32 [len], lives in the peer-mapped buffer)."""
         self.seq += 1

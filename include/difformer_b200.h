@@ -169,7 +169,7 @@ DIF_API int dif_gcn_spmm(const float* x, const int32_t* rowptr, const int32_t* i
 
 /* ------------------------------------------------------------------------------------------
  * One-shot NVLink all-reduce of the pass-1 partials (the path's only collective).
- * Every rank owns a peer-mappable buffer of dif_comm_buffer_bytes(len): [2 data slots | flags].
+ * Every rank owns a peer-mappable buffer of dif_comm_buffer_bytes(len): [2 data slots | flags | status].
  *   dif_comm_alloc / _free      : the one place the library allocates (cudaMalloc: IPC-exportable), zero-filled
  *   dif_comm_export / _open     : cudaIpc handle (64 bytes) out / peer pointer in (same node, NVLink peers)
  *   dif_comm_allreduce          : call number `seq` (1,2,3,... identical on all ranks): pass 1 must have written
@@ -194,6 +194,9 @@ DIF_API int dif_comm_free(void* ptr);
 DIF_API int dif_comm_export(void* ptr, void* handle64);
 DIF_API int dif_comm_open(const void* handle64, void** peer_ptr);
 DIF_API int dif_comm_close(void* peer_ptr);
+/* watchdog: *timed_out = 1 if a kernel of this rank gave up waiting (2 s) for a peer's flag since the buffer was
+ * allocated -- its result is then meaningless.  Synchronous (one 8-byte cudaMemcpy): call it after a stream sync. */
+DIF_API int dif_comm_status(const void* own_buf, int64_t len, int* timed_out);
 DIF_API int dif_comm_allreduce(void* const* bufs, int rank, int world, int64_t len, unsigned long long seq,
                                float* out, void* stream);
 
