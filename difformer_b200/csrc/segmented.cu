@@ -115,7 +115,19 @@ __global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
     const int tilesJ = D >> 2, ntileA = (kSegRows >> 2) * tilesJ;
-    for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
+    // min_rows > 0: the small graphs were taken by seg_fwd_warp_kernel and this kernel mostly skips.  Then every CTA
+    // scans kThreads graphs at once (one coalesced load of their sizes) instead of walking them one by one.
+    const bool scan = p.min_rows > 0;
+    const int step = scan ? gridDim.x * kThreads : gridDim.x;
+    for (int base = scan ? blockIdx.x * kThreads : blockIdx.x; base < p.B; base += step) {
+    int g_end = base + 1;
+    if (scan) {
+        const int gi = base + tid;
+        const bool big = gi < p.B && (p.seg[gi + 1] - p.seg[gi]) > p.min_rows;
+        if (!__syncthreads_or(big)) continue;
+        g_end = min(base + kThreads, p.B);
+    }
+    for (int g = base; g < g_end; ++g) {
         const int64_t s = p.seg[g], e = p.seg[g + 1];
         if (e - s <= p.min_rows) continue;          // small graphs are handled by seg_fwd_warp_kernel
         const float ng = (float)(e - s);
@@ -151,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
             }
         }
     }
+    }
 }
 
 // ---- small graphs (n_g <= kWarpMaxRows), M == D == 64: one WARP per graph, direct O(n^2) form
@@ -158,11 +171,18 @@ __global__ void __launch_bounds__(kThreads) seg_fwd_kernel(SegArgs p) {
 // which costs 2 n^2 64 MACs per graph instead of 2 n 64^2 -- cheaper for n < 64 -- with no block-level
 // synchronisation at all: two lanes per query row, K/V rows of the graph broadcast from a per-warp shared buffer.
 constexpr int kWarpMaxRows = 64, kWarpsPerCta = 4, kWarpStage = 16;
+constexpr int kWarpBufFloats = 2 * kWarpStage * 64;      // one staging buffer: K rows | V rows
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) seg_fwd_warp_kernel(SegArgs p) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* Ks = smem + warp * (2 * kWarpStage * 64);      // [16][64]
-    float* Vs = Ks + kWarpStage * 64;                     // [16][64]
+    float* bufs = smem + warp * (2 * kWarpBufFloats);     // two staging buffers per warp
     const int H = p.H;
     const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
     const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
@@ -177,67 +197,295 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) seg_fwd_warp_kernel(SegA
             // halves of a staged row are interleaved in 16-byte chunks so that the two addresses a quarter-warp reads
             // fall into different banks (a 128-bit broadcast load costs one wavefront per quarter-warp, not two).
             const int half = lane & 1, rp = lane >> 1;
-            for (int q0 = 0; q0 < n; q0 += 32) {
-                const int qr0 = q0 + 2 * rp, qr1 = qr0 + 1;
-                float4 qa[8], qb[8], aa[8], ab[8];
+            // K/V rows are staged 16 at a time with cp.async into a double buffer: the copy of stage t+1 is in flight
+            // while stage t is consumed, with a fixed number of (predicated) copies per lane -- the first version
+            // staged through registers with a data-dependent trip count and spent half its time in exposed
+            // global-load latency (profiles/r1_segmented.md).
+            auto stage_load = [&](int buf, int l0) {
+                const int nl = min(kWarpStage, n - l0);
+                float* Kb = bufs + buf * kWarpBufFloats;
+                float* Vb = Kb + kWarpStage * 64;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    qa[i] = qr0 < n ? ldg4(p.q + ((s + qr0) * H + h) * 64 + 32 * half + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    qb[i] = qr1 < n ? ldg4(p.q + ((s + qr1) * H + h) * 64 + 32 * half + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    aa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float dena = 0.f, denb = 0.f;
-                for (int l0 = 0; l0 < n; l0 += kWarpStage) {     // key rows staged in shared memory, 16 at a time
-                    const int nl = min(kWarpStage, n - l0);
-                    __syncwarp();
-                    for (int idx = lane; idx < nl * 16; idx += 32) {
-                        const int r = idx >> 4, c4 = idx & 15;
+                for (int it = 0; it < (kWarpStage * 16) / 32; ++it) {
+                    const int idx = lane + 32 * it, r = idx >> 4, c4 = idx & 15;
+                    if (r < nl) {
                         // chunk c4 (columns 4 c4 ..) of half (c4 >> 3) goes to interleaved slot 2 (c4 & 7) + (c4 >> 3)
                         const int slot = 2 * (c4 & 7) + (c4 >> 3);
-                        *reinterpret_cast<float4*>(Ks + r * 64 + 4 * slot) = ldg4(p.k + ((s + l0 + r) * H + h) * 64 + 4 * c4);
-                        *reinterpret_cast<float4*>(Vs + r * 64 + 4 * slot) = ldg4(p.v + ((s + l0 + r) * p.Hv + hv) * 64 + 4 * c4);
-                    }
-                    __syncwarp();
-                    for (int l = 0; l < nl; ++l) {
-                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // independent chains (FMA latency)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 k4 = *reinterpret_cast<const float4*>(Ks + l * 64 + 4 * (2 * i + half));
-                            a0 = fmaf(qa[i].x, k4.x, a0); a1 = fmaf(qa[i].y, k4.y, a1);
-                            a0 = fmaf(qa[i].z, k4.z, a0); a1 = fmaf(qa[i].w, k4.w, a1);
-                            b0 = fmaf(qb[i].x, k4.x, b0); b1 = fmaf(qb[i].y, k4.y, b1);
-                            b0 = fmaf(qb[i].z, k4.z, b0); b1 = fmaf(qb[i].w, k4.w, b1);
-                        }
-                        float sa = a0 + a1, sb = b0 + b1;
-                        sa += __shfl_xor_sync(0xffffffffu, sa, 1);            // the other column half of the rows
-                        sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-                        const float wa = fmaf(c, sa, 1.f), wb = fmaf(c, sb, 1.f);
-                        dena += wa;
-                        denb += wb;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 v4 = *reinterpret_cast<const float4*>(Vs + l * 64 + 4 * (2 * i + half));
-                            aa[i].x = fmaf(wa, v4.x, aa[i].x); aa[i].y = fmaf(wa, v4.y, aa[i].y);
-                            aa[i].z = fmaf(wa, v4.z, aa[i].z); aa[i].w = fmaf(wa, v4.w, aa[i].w);
-                            ab[i].x = fmaf(wb, v4.x, ab[i].x); ab[i].y = fmaf(wb, v4.y, ab[i].y);
-                            ab[i].z = fmaf(wb, v4.z, ab[i].z); ab[i].w = fmaf(wb, v4.w, ab[i].w);
-                        }
+                        cp_async16(Kb + r * 64 + 4 * slot, p.k + ((s + l0 + r) * H + h) * 64 + 4 * c4);
+                        cp_async16(Vb + r * 64 + 4 * slot, p.v + ((s + l0 + r) * p.Hv + hv) * 64 + 4 * c4);
                     }
                 }
-                if (qr0 < n) {
-                    float* o = p.o + ((s + qr0) * H + h) * 64 + 32 * half;
+                cp_async_commit();
+            };
+            const int S = (n + kWarpStage - 1) / kWarpStage, P = (n + 31) >> 5, total = S * P;
+            __syncwarp();                                   // the previous graph / head has finished with the buffers
+            stage_load(0, 0);
+            float4 qa[8], qb[8], aa[8], ab[8];
+            float dena = 0.f, denb = 0.f;
+            int st = 0, q0 = 0;
+            for (int t = 0; t < total; ++t) {
+                const int qr0 = q0 + 2 * rp, qr1 = qr0 + 1;
+                if (st == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(aa[i].x / dena, aa[i].y / dena, aa[i].z / dena, aa[i].w / dena);
+                    for (int i = 0; i < 8; ++i) {
+                        qa[i] = qr0 < n ? ldg4(p.q + ((s + qr0) * H + h) * 64 + 32 * half + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        qb[i] = qr1 < n ? ldg4(p.q + ((s + qr1) * H + h) * 64 + 32 * half + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        aa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    dena = 0.f;
+                    denb = 0.f;
                 }
-                if (qr1 < n) {
-                    float* o = p.o + ((s + qr1) * H + h) * 64 + 32 * half;
+                if (t + 1 < total) stage_load((t + 1) & 1, (st + 1 == S ? 0 : st + 1) * kWarpStage);
+                else cp_async_commit();                     // empty group: keeps the wait below uniform
+                cp_async_wait1();                           // everything but the newest group has landed => stage t
+                __syncwarp();
+                const float* Ks = bufs + (t & 1) * kWarpBufFloats;
+                const float* Vs = Ks + kWarpStage * 64;
+                const int nl = min(kWarpStage, n - st * kWarpStage);
+                for (int l = 0; l < nl; ++l) {
+                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // independent chains (FMA latency)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(ab[i].x / denb, ab[i].y / denb, ab[i].z / denb, ab[i].w / denb);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 k4 = *reinterpret_cast<const float4*>(Ks + l * 64 + 4 * (2 * i + half));
+                        a0 = fmaf(qa[i].x, k4.x, a0); a1 = fmaf(qa[i].y, k4.y, a1);
+                        a0 = fmaf(qa[i].z, k4.z, a0); a1 = fmaf(qa[i].w, k4.w, a1);
+                        b0 = fmaf(qb[i].x, k4.x, b0); b1 = fmaf(qb[i].y, k4.y, b1);
+                        b0 = fmaf(qb[i].z, k4.z, b0); b1 = fmaf(qb[i].w, k4.w, b1);
+                    }
+                    float sa = a0 + a1, sb = b0 + b1;
+                    sa += __shfl_xor_sync(0xffffffffu, sa, 1);            // the other column half of the rows
+                    sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                    const float wa = fmaf(c, sa, 1.f), wb = fmaf(c, sb, 1.f);
+                    dena += wa;
+                    denb += wb;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(Vs + l * 64 + 4 * (2 * i + half));
+                        aa[i].x = fmaf(wa, v4.x, aa[i].x); aa[i].y = fmaf(wa, v4.y, aa[i].y);
+                        aa[i].z = fmaf(wa, v4.z, aa[i].z); aa[i].w = fmaf(wa, v4.w, aa[i].w);
+                        ab[i].x = fmaf(wb, v4.x, ab[i].x); ab[i].y = fmaf(wb, v4.y, ab[i].y);
+                        ab[i].z = fmaf(wb, v4.z, ab[i].z); ab[i].w = fmaf(wb, v4.w, ab[i].w);
+                    }
+                }
+                __syncwarp();                               // all lanes are done with this buffer (refilled at t + 2)
+                if (++st == S) {
+                    if (qr0 < n) {
+                        float* o = p.o + ((s + qr0) * H + h) * 64 + 32 * half;
+                        const float inv = 1.f / dena;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4*>(o + 4 * i) = make_float4(aa[i].x * inv, aa[i].y * inv, aa[i].z * inv, aa[i].w * inv);
+                    }
+                    if (qr1 < n) {
+                        float* o = p.o + ((s + qr1) * H + h) * 64 + 32 * half;
+                        const float inv = 1.f / denb;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4*>(o + 4 * i) = make_float4(ab[i].x * inv, ab[i].y * inv, ab[i].z * inv, ab[i].w * inv);
+                    }
+                    st = 0;
+                    q0 += 32;
                 }
             }
+        }
+    }
+}
+
+// ---- backward of the small graphs, same warp-per-graph direct form.  With w_nl = 1 + c q_n.k_l, d_n = sum_l w_nl,
+//      out_n = sum_l w_nl v_l / d_n and D_n = g_n.out_n:
+//          dw_nl = (g_n.v_l - D_n) / d_n
+//          dq_n  = c sum_l dw_nl k_l  - q_n t / |Q|^2         dk_l = c sum_n dw_nl q_n  - k_l t / |K|^2
+//          dv_l  = sum_n (w_nl / d_n) g_n                      t    = sum_{g,n,l} dw_nl c q_n.k_l   (c = 1/(|Q||K|) is global)
+//      The warp kernel writes dq, dk without the t terms, dv, and its graph's share of t; seg_bwd_fixup_kernel subtracts
+//      the t terms once t has been summed over all graphs (fixed order).
+//      lane = (row = lane >> 1, column half = lane & 1): 16 rows per pass, 32 columns per lane.
+template <class F>
+__device__ __forceinline__ void seg_warp_pipeline(float* bufs, int lane, const float* a_src, int a_heads, int a_head, const float* b_src,
+                                                  int b_heads, int b_head, int64_t s, int n, F&& body) {
+    const int S = (n + kWarpStage - 1) / kWarpStage;
+    auto load = [&](int buf, int l0) {
+        const int nl = min(kWarpStage, n - l0);
+        float* Ab = bufs + buf * kWarpBufFloats;
+        float* Bb = Ab + kWarpStage * 64;
+#pragma unroll
+        for (int it = 0; it < (kWarpStage * 16) / 32; ++it) {
+            const int idx = lane + 32 * it, r = idx >> 4, c4 = idx & 15;
+            if (r < nl) {
+                const int slot = 2 * (c4 & 7) + (c4 >> 3);       // column halves interleaved in 16-byte chunks (see forward)
+                cp_async16(Ab + r * 64 + 4 * slot, a_src + ((s + l0 + r) * a_heads + a_head) * 64 + 4 * c4);
+                cp_async16(Bb + r * 64 + 4 * slot, b_src + ((s + l0 + r) * b_heads + b_head) * 64 + 4 * c4);
+            }
+        }
+        cp_async_commit();
+    };
+    __syncwarp();                                   // everybody is done with the buffers
+    load(0, 0);
+    for (int t = 0; t < S; ++t) {
+        if (t + 1 < S) load((t + 1) & 1, (t + 1) * kWarpStage);
+        else cp_async_commit();
+        cp_async_wait1();
+        __syncwarp();
+        const float* A = bufs + (t & 1) * kWarpBufFloats;
+        const float* Bm = A + kWarpStage * 64;
+        const int nl = min(kWarpStage, n - t * kWarpStage);
+        for (int l = 0; l < nl; ++l) body(A + l * 64, Bm + l * 64, t * kWarpStage + l);
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ float dot32(const float4 (&a)[8], const float4 (&b)[8]) {
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x0 = fmaf(a[i].x, b[i].x, x0); x1 = fmaf(a[i].y, b[i].y, x1);
+        x2 = fmaf(a[i].z, b[i].z, x2); x3 = fmaf(a[i].w, b[i].w, x3);
+    }
+    return (x0 + x1) + (x2 + x3);
+}
+__device__ __forceinline__ void lds_row(const float* row, int half, float4 (&x)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(row + 4 * (2 * i + half));
+}
+__device__ __forceinline__ void ldg_row(const float* row32, bool live, float4 (&x)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = live ? ldg4(row32 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void axpy32(float a, const float4 (&x)[8], float4 (&y)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        y[i].x = fmaf(a, x[i].x, y[i].x); y[i].y = fmaf(a, x[i].y, y[i].y);
+        y[i].z = fmaf(a, x[i].z, y[i].z); y[i].w = fmaf(a, x[i].w, y[i].w);
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) seg_bwd_warp_kernel(SegArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* bufs = smem + warp * (2 * kWarpBufFloats + 2 * kWarpMaxRows);
+    float* rowD = bufs + 2 * kWarpBufFloats;              // [64] D_n = g_n . out_n
+    float* rowI = rowD + kWarpMaxRows;                    // [64] 1 / d_n
+    const int H = p.H;
+    const bool bcast = (p.Hv != H);
+    const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+    const int half = lane & 1, rr = lane >> 1;
+    const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+    for (int g = gw; g < p.B; g += nw) {
+        const int64_t s = p.seg[g], e = p.seg[g + 1];
+        const int n = (int)(e - s);
+        if (n > kWarpMaxRows) continue;
+        if (n <= 0) {                                       // empty graph: its share of t is zero
+            if (lane == 0) { p.part[2 * (int64_t)g] = 0.f; p.part[2 * (int64_t)g + 1] = 0.f; }
+            continue;
+        }
+        float tacc = 0.f;
+        for (int h = 0; h < H; ++h) {
+            const int hv = bcast ? 0 : h;
+            // ---- z = sum_l k_l (this lane's 32 columns)
+            float4 z[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            seg_warp_pipeline(bufs, lane, p.k, H, h, p.v, p.Hv, hv, s, n, [&](const float* kr, const float*, int) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(kr + 4 * (2 * i + half));
+                    z[i].x += k4.x; z[i].y += k4.y; z[i].z += k4.z; z[i].w += k4.w;
+                }
+            });
+            // ---- phase A: lanes own query rows; loop over the keys: dq, t, and the per-row scalars D_n, 1/d_n
+            for (int q0 = 0; q0 < n; q0 += 16) {
+                const int r = q0 + rr;
+                const bool live = r < n;
+                float4 qv[8], gv[8], acc[8];
+                ldg_row(p.q + ((s + r) * H + h) * 64 + 32 * half, live, qv);
+                ldg_row(p.g + ((s + r) * H + h) * 64 + 32 * half, live, gv);
+                ldg_row(p.out + ((s + r) * H + h) * 64 + 32 * half, live, acc);      // out row, only for D_n
+                float Dn = dot32(gv, acc), qz = dot32(qv, z);
+                Dn += __shfl_xor_sync(0xffffffffu, Dn, 1);
+                qz += __shfl_xor_sync(0xffffffffu, qz, 1);
+                const float invd = 1.f / fmaf(c, qz, (float)n);
+                if (live && half == 0) { rowD[r] = Dn; rowI[r] = invd; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                seg_warp_pipeline(bufs, lane, p.k, H, h, p.v, p.Hv, hv, s, n, [&](const float* kr, const float* vr, int) {
+                    float4 k4[8], v4[8];
+                    lds_row(kr, half, k4);
+                    lds_row(vr, half, v4);
+                    float sc = dot32(qv, k4), tt = dot32(gv, v4);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                    tt += __shfl_xor_sync(0xffffffffu, tt, 1);
+                    const float dw = (tt - Dn) * invd;
+                    axpy32(dw, k4, acc);
+                    if (live && half == 0) tacc = fmaf(dw * c, sc, tacc);
+                });
+                if (live) {
+                    float* o = p.dq + ((s + r) * H + h) * 64 + 32 * half;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(acc[i].x * c, acc[i].y * c, acc[i].z * c, acc[i].w * c);
+                }
+            }
+            // ---- phase B: lanes own key rows; loop over the queries: dk, dv
+            for (int l0 = 0; l0 < n; l0 += 16) {
+                const int r = l0 + rr;
+                const bool live = r < n;
+                float4 kv[8], vv[8], dka[8], dva[8];
+                ldg_row(p.k + ((s + r) * H + h) * 64 + 32 * half, live, kv);
+                ldg_row(p.v + ((s + r) * p.Hv + hv) * 64 + 32 * half, live, vv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { dka[i] = make_float4(0.f, 0.f, 0.f, 0.f); dva[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                seg_warp_pipeline(bufs, lane, p.q, H, h, p.g, H, h, s, n, [&](const float* qr, const float* gr, int nn) {
+                    float4 q4[8], g4[8];
+                    lds_row(qr, half, q4);
+                    lds_row(gr, half, g4);
+                    float sc = dot32(q4, kv), tt = dot32(g4, vv);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                    tt += __shfl_xor_sync(0xffffffffu, tt, 1);
+                    const float invd = rowI[nn];
+                    const float dw = (tt - rowD[nn]) * invd;
+                    axpy32(dw, q4, dka);
+                    axpy32(fmaf(c, sc, 1.f) * invd, g4, dva);
+                });
+                if (live) {
+                    float* ok = p.dk + ((s + r) * H + h) * 64 + 32 * half;
+                    float* ov = p.dv + ((s + r) * p.Hv + hv) * 64 + 32 * half;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        *reinterpret_cast<float4*>(ok + 4 * i) = make_float4(dka[i].x * c, dka[i].y * c, dka[i].z * c, dka[i].w * c);
+                        float4 o = dva[i];
+                        if (bcast && h > 0) {     // V shared by all heads: accumulate (same lane, same address, fixed order)
+                            const float4 prev = *reinterpret_cast<const float4*>(ov + 4 * i);
+                            o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                        }
+                        *reinterpret_cast<float4*>(ov + 4 * i) = o;
+                    }
+                }
+            }
+        }
+        tacc = warp_sum(tacc);
+        if (lane == 0) { p.part[2 * (int64_t)g] = tacc; p.part[2 * (int64_t)g + 1] = tacc; }
+    }
+}
+
+// dq -= q t_q/|Q|^2, dk -= k t_k/|K|^2 on the rows of the small graphs (one warp per graph, after t has been summed)
+__global__ void __launch_bounds__(256) seg_bwd_fixup_kernel(SegArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const float aq = p.scal[0] / p.norms[0], ak = p.scal[1] / p.norms[1];
+    for (int g = gw; g < p.B; g += nw) {
+        const int64_t s = p.seg[g], e = p.seg[g + 1];
+        const int n = (int)(e - s);
+        if (n <= 0 || n > kWarpMaxRows) continue;
+        const int64_t base = s * p.H * 16, count = (int64_t)n * p.H * 16;      // float4 elements (M = 64)
+        for (int64_t i = lane; i < count; i += 32) {
+            const float4 q4 = ldg4(p.q + 4 * (base + i)), k4 = ldg4(p.k + 4 * (base + i));
+            float4* dq = reinterpret_cast<float4*>(p.dq) + base + i;
+            float4* dk = reinterpret_cast<float4*>(p.dk) + base + i;
+            float4 a = *dq, b = *dk;
+            a.x = fmaf(-aq, q4.x, a.x); a.y = fmaf(-aq, q4.y, a.y); a.z = fmaf(-aq, q4.z, a.z); a.w = fmaf(-aq, q4.w, a.w);
+            b.x = fmaf(-ak, k4.x, b.x); b.y = fmaf(-ak, k4.y, b.y); b.z = fmaf(-ak, k4.z, b.z); b.w = fmaf(-ak, k4.w, b.w);
+            *dq = a;
+            *dk = b;
         }
     }
 }
@@ -322,6 +570,7 @@ __global__ void __launch_bounds__(kThreads) seg_bwd_scalars_kernel(SegArgs p) {
     const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
     for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
         const int64_t s = p.seg[g], e = p.seg[g + 1];
+        if (p.min_rows > 0 && e - s <= p.min_rows) continue;     // small graphs: seg_bwd_warp_kernel wrote their share
         float tq = 0.f, tk = 0.f;
         if (e > s) {
             for (int h = 0; h < H; ++h) {
@@ -369,7 +618,7 @@ __global__ void __launch_bounds__(kThreads) seg_bwd_main_kernel(SegArgs p) {
     const bool bcast = (p.Hv != H);
     for (int g = blockIdx.x; g < p.B; g += gridDim.x) {
         const int64_t s = p.seg[g], e = p.seg[g + 1];
-        if (e <= s) continue;
+        if (e <= s || e - s <= p.min_rows) continue;             // small graphs are handled by seg_bwd_warp_kernel
         const float ng = (float)(e - s);
         for (int h = 0; h < H; ++h) {
             const int hv = bcast ? 0 : h;
@@ -528,7 +777,7 @@ extern "C" int dif_segmented_simple_fwd(const float* q, const float* k, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 64 && D == 64) {
         // graphs with <= 64 rows: one warp per graph, direct form (the particle datasets: 10-40 nodes per graph)
-        const size_t wsmem = (size_t)kWarpsPerCta * 2 * kWarpStage * 64 * sizeof(float);
+        const size_t wsmem = (size_t)kWarpsPerCta * 2 * kWarpBufFloats * sizeof(float);      // double-buffered K/V stages
         static bool attr = false;
         if (!attr) { DIF_CUDA_OK(cudaFuncSetAttribute(seg_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); attr = true; }
         const int wgrid = (int)std::min<int64_t>(((int64_t)B + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 16);
@@ -559,6 +808,17 @@ extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const fl
     a.N = N; a.B = B; a.H = H; a.Hv = Hv; a.M = M; a.D = D; a.dq = dq; a.dk = dk; a.dv = dv; a.part = part;
     const int grid = B < 148 * 16 ? B : 148 * 16;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool warp_path = (M == 64 && D == 64);
+    if (warp_path) {
+        // graphs with <= 64 rows: one warp per graph, direct form; writes dq, dk (without the t terms), dv and part[g]
+        const size_t wsmem = (size_t)kWarpsPerCta * (2 * kWarpBufFloats + 2 * kWarpMaxRows) * sizeof(float);
+        static bool attr = false;
+        if (!attr) { DIF_CUDA_OK(cudaFuncSetAttribute(seg_bwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); attr = true; }
+        const int wgrid = (int)std::min<int64_t>(((int64_t)B + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 16);
+        seg_bwd_warp_kernel<<<wgrid, kWarpsPerCta * 32, wsmem, st>>>(a);
+        DIF_LAUNCH_OK();
+        a.min_rows = kWarpMaxRows;       // the CTA kernels below only take the larger graphs
+    }
     // M,D <= 64 => (M/4)*(D/4) <= 256 => one 4x4 tile per thread
     {
         const size_t smem = ((size_t)M * D + M + D + (size_t)kSegRows * (M + 4) + 2 * (size_t)kSegRows * (D + 4) + kSegRows + 33) * sizeof(float);
@@ -572,6 +832,10 @@ extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const fl
         const size_t smem = (2 * (size_t)M * D + 2 * (size_t)(M + D) + (size_t)kSegRows * (M + 4) + 2 * (size_t)kSegRows * (D + 4) + kSegRows) * sizeof(float);
         if ((rc = seg_smem(seg_bwd_main_kernel<1>, smem))) return rc;
         seg_bwd_main_kernel<1><<<grid, kThreads, smem, st>>>(a);
+        DIF_LAUNCH_OK();
+    }
+    if (warp_path) {
+        seg_bwd_fixup_kernel<<<148 * 8, 256, 0, st>>>(a);
         DIF_LAUNCH_OK();
     }
     return DIF_OK;

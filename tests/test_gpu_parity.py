@@ -421,6 +421,29 @@ def test_v2_many_small_graphs_and_one_large():
     assert O.rel_err(out, O.segmented_simple_attention(q.double(), k.double(), v.double(), n_nodes)) < TOL
 
 
+@pytest.mark.parametrize("h", [1, 2])
+def test_v2_backward_mixed_sizes(h):
+    """Backward over a batch that takes both code paths: graphs of <= 64 rows (warp per graph, direct form, t terms
+    fixed up afterwards) and larger ones (CTA per graph, S form), plus the edge sizes 1, 64, 65 and an empty graph."""
+    gen = torch.Generator().manual_seed(17 + h)
+    n_nodes = torch.cat([torch.randint(1, 41, (150,), generator=gen), torch.tensor([700, 0, 64, 65, 1, 33, 16, 17, 32, 48])])
+    tot = int(n_nodes.sum())
+    q, k, v = O.synthetic_qkv(tot, h, 64, seed=21, adversarial=True)
+    g = torch.randn(tot, h, 64, generator=gen)
+    qd, kd, vd = (dev(t).requires_grad_(True) for t in (q, k, v))
+    out = ops.segmented_full_attention(qd, kd, vd, "simple", n_nodes.cuda())
+    assert O.rel_err(out, O.segmented_simple_attention(q.double(), k.double(), v.double(), n_nodes)) < TOL
+    out.backward(dev(g))
+    want = O.segmented_simple_attention_backward(q.double(), k.double(), v.double(), n_nodes, g.double())
+    for got, w64 in ((qd.grad, want[0]), (kd.grad, want[1]), (vd.grad, want[2])):
+        assert O.rel_err(got, w64) < TOL
+    out2 = ops.segmented_full_attention(qd, kd, vd, "simple", n_nodes.cuda())     # deterministic (no atomics)
+    q2 = qd.grad.clone()
+    qd.grad = None
+    out2.backward(dev(g))
+    assert torch.equal(out, out2) and torch.equal(q2, qd.grad)
+
+
 def test_v2_model_forward():
     c = V2["v2_model_simple"]
     m = difformer.DIFFormer_v2(16, 64, 3, num_layers=2, kernel="simple", use_graph=True)
