@@ -5,7 +5,7 @@ Drop-in for the reference's `difformer` module (see ../difformer.py): `DIFFormer
 """
 from .ops import (full_attention_conv, gcn_conv, segmented_full_attention, GraphCSR, graph_csr,  # noqa: F401
                   simple_partials, simple_apply, set_simple_impl)
-from .module import DIFFormer, DIFFormerConv, DIFFormer_v2, TransConv  # noqa: F401
+from .module import DIFFormer, DIFFormerConv, DIFFormer_v2, TransConv, GraphedForward  # noqa: F401
 from .sharded import RowShardedAttention, RowShardComm, PartialsExchange, shard_rows  # noqa: F401
 
 __version__ = "0.1.0"

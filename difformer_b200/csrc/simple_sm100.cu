@@ -366,7 +366,11 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
     __syncthreads();
     DIF_STAMP(dbg, 5);
     const int grid = gridDim.x;
-    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(a.epoch) : "memory");
+    // epoch = host value + device-side generation word (flags[grid], any initial value; CTA 0 bumps it once every CTA
+    // has published, i.e. after every CTA has read it): a CUDA-graph replay repeats the host value, never the epoch
+    const unsigned long long gen = *reinterpret_cast<volatile unsigned long long*>(a.flags + grid);
+    const unsigned long long epoch = a.epoch + gen * 0x9E3779B97F4A7C15ull;
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(epoch) : "memory");
     // ---- column slices of the record: kSlices fixed slices of `chunk` floats (multiples of 16 B), slice sl is owned by
     //      CTA sl % grid -- the partition does not depend on this rank's grid, so slices line up across ranks
     const int chunk = (int)((((a.ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
@@ -385,8 +389,12 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                 unsigned long long f;
                 do {
                     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
-                    if (f != a.epoch) __nanosleep(64);
-                } while (f != a.epoch);
+                    if (f != epoch) __nanosleep(64);
+                } while (f != epoch);
+            }
+            if (blockIdx.x == 0) {
+                __syncthreads();
+                if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + grid) = gen + 1;
             }
             asm volatile("fence.proxy.async;" ::: "memory");   // acquired (generic proxy) before the bulk (async proxy) reads
             waited = true;
@@ -1109,7 +1117,7 @@ int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
     (void)Hv; (void)M; (void)D;
     int grid;
     tc_rows_per_cta(N, H, &grid);
-    // per-CTA records + one 64-bit ready flag per CTA
+    // per-CTA records + one 64-bit ready flag per CTA + the generation word
     return (int64_t)grid * tc_ws_len(H) * (int64_t)sizeof(float) + (int64_t)grid * 8 + 64;
 }
 
@@ -1140,7 +1148,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     int grid;
     const int rpc = tc_rows_per_cta(N, H, &grid);
     const int64_t ws_len = tc_ws_len(H);
-    DIF_REQUIRE(ws_bytes >= (int64_t)grid * ws_len * 4 + (int64_t)grid * 8, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
+    DIF_REQUIRE(ws_bytes >= (int64_t)grid * ws_len * 4 + (int64_t)(grid + 1) * 8, DIF_EARG, "simple_reduce(tcgen05): workspace too small");
     DIF_REQUIRE((((ws_len + kSlices - 1) / kSlices + 3) & ~(int64_t)3) <= kThreadsT, DIF_EUNSUPPORTED, "simple_reduce(tcgen05): slice wider than the CTA");
     static std::atomic<unsigned long long> epoch_src{0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&epoch_src};
     ReduceArgs1 a{};
@@ -1215,7 +1223,7 @@ int simple_bwd_reduce_tc(const float* q, const float* g, const float* out, const
     int grid;
     const int rpc = tc_rows_per_cta(N, H, &grid);
     const int64_t ws_len = tc_ws_len(H);
-    DIF_REQUIRE(ws_bytes >= (int64_t)grid * ws_len * 4 + (int64_t)grid * 8, DIF_EARG, "simple_bwd_reduce(tcgen05): workspace too small");
+    DIF_REQUIRE(ws_bytes >= (int64_t)grid * ws_len * 4 + (int64_t)(grid + 1) * 8, DIF_EARG, "simple_bwd_reduce(tcgen05): workspace too small");
     static std::atomic<unsigned long long> epoch_src{0xD1B54A32D192ED03ull ^ (unsigned long long)(uintptr_t)&epoch_src};
     ReduceArgs1 a{};
     a.k = q; a.v = g; a.q = out;                // roles: A <- q, B <- g (-> dnum), third stream <- out

@@ -398,6 +398,26 @@ def test_training_step_through_the_drop_in():
     assert losses[-1] < losses[0] and all(l == l for l in losses)
 
 
+def test_model_cuda_graph_replay():
+    """GraphedForward: captured inference replays bit-identically to the eager path and follows new node features."""
+    from difformer_b200 import GraphedForward
+    gen = torch.Generator().manual_seed(4)
+    n = 500
+    x = dev(torch.randn(n, 48, generator=gen))
+    ei = dev(O.synthetic_graph(n, 1500, seed=2))
+    for kern, heads in (("simple", 4), ("sigmoid", 1)):
+        m = difformer.DIFFormer(48, 64, 5, num_layers=2, num_heads=heads, kernel=kern, use_graph=True).to(x.device).eval()
+        with torch.no_grad():
+            want = m(x, ei).clone()
+        gf = GraphedForward(m, x, ei)
+        assert torch.equal(gf(x, ei), want)
+        x2 = dev(torch.randn(n, 48, generator=gen))
+        with torch.no_grad():
+            want2 = m(x2, ei).clone()
+        assert torch.equal(gf(x2, ei), want2)
+        assert torch.equal(gf(x, ei), want)
+
+
 # ---------------------------------------------------------------------------------- batched graphs (v2)
 def test_v2_segmented_forward_backward():
     for name in ("v2_simple_segments", "v2_simple_segments_h2"):

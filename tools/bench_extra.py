@@ -108,4 +108,14 @@ for kern in ("simple", "sigmoid"):
     m = difformer.DIFFormer(cin, 64, 7, num_layers=2, num_heads=1, kernel=kern, use_bn=True, use_residual=True, use_graph=True, use_weight=False).to(dev).eval()
     with torch.no_grad():
         t_m = timeit(lambda: m(x, eic), 50)
-    emit(row="model forward", shape=f"Cora-like N=2708 C=1433 2 layers hidden 64 H=1 kernel={kern}", us=t_m)
+    row = dict(row="model forward", shape=f"Cora-like N=2708 C=1433 2 layers hidden 64 H=1 kernel={kern}", us=t_m)
+    try:
+        from difformer_b200 import GraphedForward
+        with torch.no_grad():
+            want = m(x, eic).clone()
+        gf = GraphedForward(m, x, eic)
+        row["cuda_graph_us"] = timeit(lambda: gf(x, eic), 50)
+        row["cuda_graph_max_abs_diff"] = float((gf(x, eic) - want).abs().max())
+    except Exception as exc:  # noqa: BLE001
+        row["cuda_graph_error"] = repr(exc)[:300]
+    emit(**row)
