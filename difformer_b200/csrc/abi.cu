@@ -53,7 +53,7 @@ static int pick_impl(int impl, int64_t N, int H, int Hv, int M, int D, bool* use
     if (impl == DIF_IMPL_AUTO) { *use_tc = ok; return DIF_OK; }
     if (impl == DIF_IMPL_GENERIC) { *use_tc = false; return DIF_OK; }
     if (impl == DIF_IMPL_TCGEN05) {
-        DIF_REQUIRE(ok, DIF_EUNSUPPORTED, "simple: tcgen05 path needs M == D == 64, Hv == H, H even (got H=%d Hv=%d M=%d D=%d)", H, Hv, M, D);
+        DIF_REQUIRE(ok, DIF_EUNSUPPORTED, "simple: tcgen05 path needs M == D == 64, Hv == H, H in {1, 2, 4} (got H=%d Hv=%d M=%d D=%d)", H, Hv, M, D);
         *use_tc = true;
         return DIF_OK;
     }

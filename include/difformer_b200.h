@@ -43,7 +43,7 @@ extern "C" {
 /* kernel implementation selector for the 'simple' path */
 #define DIF_IMPL_AUTO 0     /* tcgen05 path when the shape qualifies, else generic */
 #define DIF_IMPL_GENERIC 1  /* FFMA kernels, any H, M%4==0, D%4==0, M,D <= 128 */
-#define DIF_IMPL_TCGEN05 2  /* tcgen05/TMEM kernels: M == D == 64, Hv == H, H even */
+#define DIF_IMPL_TCGEN05 2  /* tcgen05/TMEM kernels: M == D == 64, Hv == H, H in {1, 2, 4} */
 
 DIF_API int dif_version(void);
 DIF_API const char* dif_last_error(void);
