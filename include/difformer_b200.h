@@ -123,7 +123,8 @@ DIF_API int dif_sumsq2(const float* q, const float* k, int64_t count, float* nor
 DIF_API int dif_segmented_simple_fwd(const float* q, const float* k, const float* v, const int32_t* seg_ptr,
                              int32_t B, const float* norms, int64_t N, int H, int Hv, int M, int D,
                              float* out, void* stream);
-/* backward: `out` is the saved forward output, g = dL/dout; M in {16,32,64}, D <= 64 */
+/* backward: `out` is the saved forward output, g = dL/dout; M in {16,32,64}, D <= 64.  M == D == 64: graphs of up to
+ * 64 rows run one warp per graph (direct O(n^2) form), larger ones one CTA per graph; no atomics, deterministic. */
 DIF_API int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
                              const int32_t* seg_ptr, int32_t B, const float* norms,
                              int64_t N, int H, int Hv, int M, int D,
@@ -134,9 +135,12 @@ DIF_API int64_t dif_segmented_workspace_bytes(int32_t B);
 /* ------------------------------------------------------------------------------------------
  * kernel='sigmoid'  (full_attention_conv, difformer.py:45-56): tiled, never materialises [N,L,H].
  *   out = (sigmoid(QK^T) / rowsum) V ; rowsum[N,H] is saved for the backward.
- *   Forward with M == D == 64 runs on tcgen05 (flash-style: S = QK^T with bf16 hi/lo split operands, P = sigmoid(S)
- *   rounded to bf16 for the P V product, rowsum taken from the rounded P); other shapes and the backward run the
- *   fp32 FFMA kernels.  dif_sigmoid_set_impl(DIF_IMPL_GENERIC / _TCGEN05 / _AUTO) pins the forward path (process-wide).
+ *   Forward with M == D == 64 runs on tcgen05 (flash-style; Q, K, V and P = sigmoid(S) are all split into bf16
+ *   hi + lo operands, fp32 accumulation, P and Q read by the MMA from tensor memory: ~5e-6 of the fp64 result; scores
+ *   below -43 are clamped to -43, sigmoid = 2e-19); other shapes and the backward run the fp32 FFMA kernels.  The
+ *   workspace holds the key-split partials and the bf16 operand images of K and V (dif_sigmoid_fwd_workspace_bytes).
+ *   dif_sigmoid_set_impl(DIF_IMPL_GENERIC / _TCGEN05 / _AUTO) pins the forward path (process-wide); pinned to
+ *   _TCGEN05, an unsupported shape returns DIF_EUNSUPPORTED instead of falling back.
  * ------------------------------------------------------------------------------------------ */
 DIF_API int dif_sigmoid_set_impl(int impl);
 DIF_API int64_t dif_sigmoid_fwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D);
