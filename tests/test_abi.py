@@ -47,6 +47,23 @@ def test_pure_host_queries():
     assert lib.dif_csr_workspace_bytes(1000, 5000) > 0
     assert lib.dif_csr_workspace_bytes(1 << 31, 10) == -1     # int32 index range
     assert lib.dif_sigmoid_bwd_workspace_bytes(100, 100, 2, 2, 64, 64) >= 100 * 2 * 4
+    # 'sigmoid' forward: tcgen05 shapes (M == D == 64) also need the bf16 hi|lo operand images of K and V, 32 KB per
+    # 128-key tile and head (sigmoid_sm100.cu); other shapes only the key-split partials
+    tiles = (10000 + 127) // 128
+    assert lib.dif_sigmoid_fwd_workspace_bytes(10000, 10000, 1, 1, 64, 64) >= tiles * 2 * 32768
+    assert lib.dif_sigmoid_fwd_workspace_bytes(10000, 10000, 4, 1, 64, 64) >= tiles * 5 * 32768
+    assert lib.dif_sigmoid_fwd_workspace_bytes(100, 100, 1, 1, 32, 32) < 32768
+    # impl selector: AUTO / GENERIC / TCGEN05 accepted, anything else is a bad argument (and says why)
+    for impl in (_lib.DIF_IMPL_GENERIC, _lib.DIF_IMPL_TCGEN05, _lib.DIF_IMPL_AUTO):
+        assert lib.dif_sigmoid_set_impl(impl) == 0
+    assert lib.dif_sigmoid_set_impl(7) == -1 and b"unknown impl" in lib.dif_last_error()
+    # exchange buffer = [2 data slots (64-float aligned) | flags [2][16][256] u64 | status word]
+    n = 16898
+    slot = (n + 63) // 64 * 64
+    assert lib.dif_comm_buffer_bytes(n) == 2 * slot * 4 + 2 * 16 * 256 * 8 + 64
+    assert lib.dif_comm_slot_offset_bytes(n, 1) == slot * 4 and lib.dif_comm_slot_offset_bytes(n, 2) == 0
+    # pass-1 workspace: one record per CTA + ready flags + the generation word
+    assert lib.dif_simple_workspace_bytes(132534, 4, 4, 64, 64) >= 148 * 16898 * 4 + 149 * 8
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
