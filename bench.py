@@ -232,7 +232,7 @@ def run_ours(args):
     barrier()
     collective = args.collective
     if comm is not None:
-        # watchdog (csrc/comm.cu): a rank whose kernel waited 2 s for a peer's flag reports it here; then every rank
+        # watchdog (csrc/comm.cu): a rank whose kernel waited 30 s for a peer's flag reports it here; then every rank
         # switches to the NCCL all-reduce of the partials so that the run still produces a valid number
         bad = torch.tensor([1.0 if comm.exchange(plen, dev).timed_out() else 0.0], dtype=torch.float32, device=dev)
         dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)

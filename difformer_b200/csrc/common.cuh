@@ -93,7 +93,7 @@ int64_t simple_generic_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D);
 // ---- peer-mapped exchange buffers (comm.cu, simple_sm100.cu): [2 data slots | flags [2][16][256] u64 | status u64]
 constexpr int kCommMaxRanks = 16;
-constexpr unsigned long long kCommTimeoutNs = 2000000000ull;          // 2 s without a peer's flag => give up
+constexpr unsigned long long kCommTimeoutNs = 30000000000ull;         // 30 s without a peer's flag => give up
 __host__ __device__ __forceinline__ unsigned long long* comm_status_ptr(float* base, int64_t slot_floats) {
     return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + (size_t)2 * kCommMaxRanks * 256;
 }

@@ -92,7 +92,7 @@ class PartialsExchange:
         return partials, prepared
 
     def timed_out(self) -> bool:
-        """True if a kernel of this rank gave up waiting for a peer (2 s watchdog): results since then are invalid.
+        """True if a kernel of this rank gave up waiting for a peer (30 s watchdog): results since then are invalid.
         Synchronises the device."""
         import ctypes
         torch.cuda.synchronize(self.device)

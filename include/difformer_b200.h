@@ -198,7 +198,7 @@ DIF_API int dif_comm_free(void* ptr);
 DIF_API int dif_comm_export(void* ptr, void* handle64);
 DIF_API int dif_comm_open(const void* handle64, void** peer_ptr);
 DIF_API int dif_comm_close(void* peer_ptr);
-/* watchdog: *timed_out = 1 if a kernel of this rank gave up waiting (2 s) for a peer's flag since the buffer was
+/* watchdog: *timed_out = 1 if a kernel of this rank gave up waiting (30 s) for a peer's flag since the buffer was
  * allocated -- its result is then meaningless.  Synchronous (one 8-byte cudaMemcpy): call it after a stream sync. */
 DIF_API int dif_comm_status(const void* own_buf, int64_t len, int* timed_out);
 DIF_API int dif_comm_allreduce(void* const* bufs, int rank, int world, int64_t len, unsigned long long seq,
