@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- DIFFormer propagation-layer throughput on B200 (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (headline workload)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref, else the oracle port)
+  python bench.py --workload {sigmoid_cora,layer,segmented,fwdbwd}   # the other SURVEY 8 rows, one JSON line each (1 GPU)
 
-Step      = one `full_attention_conv(q, k, v, 'simple')` forward (pass 1 reduce -> [all-reduce] ->
-            pass 2 apply) over one batch of synthetic [N,H,D] fp32 node tensors.
-Workload  = BASELINE configs[2]: N=132 534 (ogbn-proteins shape), H=4, D=64, fp32.  With G>1 ranks
-            every rank holds 132 534 rows of a G*132 534-node graph (weak scaling) and the pass-1
-            partials (67.6 KB) are all-reduced over NCCL between the passes.
-value     = node-updates/s with Q,K,V resident in HBM; e2e = same through the public Python API with
-            pinned HOST tensors (H2D of Q,K,V and D2H of the output inside the timed region).
+Headline workload ("simple")
+  step      = one `full_attention_conv(q, k, v, 'simple')` forward (pass 1 reduce -> [all-reduce] -> pass 2 apply) over
+              one batch of synthetic [N,H,D] fp32 node tensors.
+  config A  = BASELINE configs[2]: N=132 534 (ogbn-proteins shape), H=4, D=64, fp32.  With G>1 ranks every rank holds
+              132 534 rows of a G*132 534-node graph (WEAK scaling); the pass-1 partials (67.6 KB) are all-reduced inside
+              the pass-1 kernel tail over peer-mapped NVLink memory (or by NCCL, --collective nccl).
+  value     = node-updates/s with Q,K,V resident in HBM (inputs + output 543 MB > 126 MB L2; `cold` = same with an L2
+              flush between steps); e2e = same through the public Python API with pinned HOST tensors (H2D of Q,K,V and
+              D2H of the output inside the timed region).
+  parity    = on the exact bench inputs, EVERY rank: out, S, z, u, |Q|, |K|, q^S^, q^z^ against the fp64 oracle of the
+              GLOBAL problem (max over ranks); the run fails when any exceeds 1e-3.
+  cfg_b     = BASELINE configs[3]: N=1 632 803 (pokec shape) rows sharded over the G ranks (STRONG scaling), same
+              kernels, own parity; reported as an extra object in the same JSON line.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -26,18 +33,21 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 N_NODES, HEADS, DIM = 132534, 4, 64
+N_CFG_B = 1632803
 METRIC = "DIFFormer-layer node-updates/sec (full_attention_conv 'simple', N=132534 H=4 D=64 fp32 per GPU)"
 UNIT = "node-updates/s"
+TOL = 1e-3
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1466.2)), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md 6.65 TB/s, 1.4 PFLOP/s sustained)"
 
 
 class ClockSampler:
@@ -110,66 +120,177 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU path, all host threads
+# reference arm / cpu baseline: the reference's own full_attention_conv on the host cores (oracle/_ref, vendored
+# unmodified by oracle/build_ref.py), else the oracle's op-for-op port of it
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(steps, warmup, budget_s, rows=None):
+def cpu_reference_fn():
     from oracle import difformer_oracle as O
+    try:
+        from oracle.ref_shim import load_reference_v1, reference_available
+        if reference_available():
+            ref = load_reference_v1()
+            return (lambda q, k, v: ref.full_attention_conv(q, k, v, "simple")), "reference", \
+                "the reference's own full_attention_conv (node classification/difformer.py:10-61, unmodified copy under oracle/_ref)"
+    except Exception:
+        pass
+    return O.simple_attention_reference_chain, "port", "oracle transcription of the einsum chain difformer.py:18-39"
+
+
+def cpu_reference_rate(steps, warmup, budget_s, rows=None, threads=None):
+    from oracle import difformer_oracle as O
+    fn, kind, what = cpu_reference_fn()
     ncpu = os.cpu_count() or 1
     q, k, v = O.synthetic_qkv(N_NODES, HEADS, DIM, seed=123)
-
-    # 16 on the GPU box), so give the reference its best thread count: one calibration step each
-    cands = sorted({c for c in (ncpu, 64, 32, 16, 8) if c <= ncpu}, reverse=True)
-    best = (None, float("inf"))
     with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            O.simple_attention_reference_chain(q[:32768], k[:32768], v[:32768])
-            t0 = time.perf_counter()
-            O.simple_attention_reference_chain(q[:32768], k[:32768], v[:32768])
-            dt = time.perf_counter() - t0
-            if dt < best[1]:
-                best = (c, dt)
-    threads = best[0]
-    torch.set_num_threads(threads)
-    with torch.no_grad():
+        if threads is None:
+            # MKL/OpenMP do not always scale to every hardware thread: give the reference its best thread count
+            cands = sorted({c for c in (ncpu, 64, 32, 16, 8) if c <= ncpu}, reverse=True)
+            best = (None, float("inf"))
+            for c in cands:
+                torch.set_num_threads(c)
+                fn(q[:32768], k[:32768], v[:32768])
+                t0 = time.perf_counter()
+                fn(q[:32768], k[:32768], v[:32768])
+                dt = time.perf_counter() - t0
+                if dt < best[1]:
+                    best = (c, dt)
+            threads = best[0]
+        torch.set_num_threads(threads)
         if rows is None:
             t0 = time.perf_counter()
-            O.simple_attention_reference_chain(q, k, v)
+            fn(q, k, v)
             t_full = time.perf_counter() - t0
             frac = min(1.0, budget_s / max(t_full * (steps + warmup), 1e-9))
             rows = max(4096, int(N_NODES * frac))
         rows = min(rows, N_NODES)
         qs, ks, vs = q[:rows].contiguous(), k[:rows].contiguous(), v[:rows].contiguous()
         for _ in range(warmup):
-            O.simple_attention_reference_chain(qs, ks, vs)
+            fn(qs, ks, vs)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.simple_attention_reference_chain(qs, ks, vs)
+            fn(qs, ks, vs)
         dt = (time.perf_counter() - t0) / steps
-    return rows / dt, dt, rows, threads
+    torch.set_num_threads(ncpu)
+    return rows / dt, dt, rows, threads, kind, what
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    rate, dt, rows, threads = cpu_reference_rate(args.steps, args.warmup, budget_s=120.0)
-    sample = (f"{rows} of {N_NODES} rows per step (cost is linear in rows), H={HEADS} D={DIM} fp32, "
-              f"oracle transcription of the einsum chain difformer.py:18-39 on torch CPU, {threads} threads")
+    rate, dt, rows, threads, kind, what = cpu_reference_rate(args.steps, args.warmup, budget_s=120.0)
+    sample = f"{rows} of {N_NODES} rows per step (cost is linear in rows), H={HEADS} D={DIM} fp32, {what}, torch CPU, {threads} threads"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"full_attention_conv('simple') N={N_NODES} H={HEADS} D={DIM} fp32 (BASELINE configs[2])",
-                       "rows_per_step": rows},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(max(args.gpus, 1)),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def workload_config(world):
+    """Identical for both arms (the driver compares the dicts)."""
+    return {"workload": f"full_attention_conv('simple') N={N_NODES} H={HEADS} D={DIM} fp32 per GPU (BASELINE configs[2])",
+            "rows_per_gpu": N_NODES, "global_rows": N_NODES * world}
+
+
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+class Problem:
+    """One row-sharded 'simple' problem: this rank's rows of Q, K, V on the device + the step through the C ABI."""
+
+    def __init__(self, rows, n_total, seed, dev, group, comm, collective):
+        from difformer_b200 import ops
+        from oracle import difformer_oracle as O
+        self.ops, self.O = ops, O
+        self.rows, self.n_total, self.dev, self.group, self.comm, self.collective = rows, float(n_total), dev, group, comm, collective
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        # SURVEY 8d: Q, K, V ~ N(0,1) fp32, generated on the device (seeded per rank)
+        self.q, self.k, self.v = (torch.randn(rows, HEADS, DIM, generator=gen, device=dev, dtype=torch.float32) for _ in range(3))
+        self.plen = int(ops.lib.dif_simple_partials_len(HEADS, HEADS, DIM, DIM))
+        self.T = rows * HEADS * DIM * 4
+
+    def reduce(self):
+        """pass 1 (+ all-reduce) -> (reduced partials, prepared operand image or None)"""
+        ops = self.ops
+        if self.comm is not None:          # pass 1 + all-reduce over peer-mapped NVLink memory in ONE kernel
+            ex = self.comm.exchange(self.plen, self.dev)
+            fused = ex.fused_reduce(self.q, self.k, self.v)
+            if fused is not None:
+                return fused
+            return ex.allreduce(ops.simple_partials(self.q, self.k, self.v)), None
+        partials, prepared = ops.simple_partials(self.q, self.k, self.v, with_prepared=True)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(partials, group=self.group)
+            prepared = None       # the pass-2 operand image only matches the un-reduced partials
+        return partials, prepared
+
+    def step(self):
+        partials, prepared = self.reduce()
+        return self.ops.simple_apply(self.q, partials, self.n_total, HEADS, DIM, prepared=prepared)
+
+    def parity(self, oracle_device):
+        """out and the BASELINE.md 4.4 intermediates of THIS rank against the fp64 oracle of the GLOBAL problem."""
+        import torch.distributed as dist
+        O, ops = self.O, self.ops
+        H, D = HEADS, DIM
+        qd, kd, vd = (t.to(oracle_device, torch.float64) for t in (self.q, self.k, self.v))
+        wp = O.simple_partials(qd, kd, vd)
+        flat = torch.cat([wp["S"].reshape(-1), wp["z"].reshape(-1), wp["u"].reshape(-1), wp["sq"].reshape(1), wp["sk"].reshape(1)])
+        if self.group is not None:           # oracle partials are additive over the row shards too
+            flat = flat.to(self.dev)
+            dist.all_reduce(flat, group=self.group)
+            flat = flat.to(oracle_device)
+        nS, nz = H * D * D, H * D
+        want = {"S": flat[:nS].reshape(H, D, D), "z": flat[nS:nS + nz].reshape(H, D), "u": flat[nS + nz:nS + 2 * nz].reshape(H, D),
+                "sq": flat[-2], "sk": flat[-1], "n": torch.tensor(self.n_total, dtype=torch.float64)}
+        want_out, parts = O.simple_apply(qd, want, self.n_total, return_parts=True)
+        got_out = self.step()
+        got = self.reduce()[0].double().to(oracle_device)
+        err = {"out": O.rel_err(got_out, want_out),
+               "S": O.rel_err(got[:nS].reshape(H, D, D), want["S"]), "z": O.rel_err(got[nS:nS + nz].reshape(H, D), want["z"]),
+               "u": O.rel_err(got[nS + nz:nS + 2 * nz].reshape(H, D), want["u"]),
+               "normQ": abs(float(got[-2].sqrt() / want["sq"].sqrt()) - 1.0), "normK": abs(float(got[-1].sqrt() / want["sk"].sqrt()) - 1.0)}
+        # q^S^ and q^z^ through pass 2 itself with edited partials and a small n_total (at n_total = N the fp32 denominator
+        # q^z^ + N swallows q^z^ -- in the reference too):  u := 0, z := 0, n := 1 -> out = q^S^ ;  S := 0, u := 1 -> out = 1/(q^z^ + n)
+        red = self.reduce()[0]
+        only_s = red.clone()
+        only_s[nS:nS + 2 * nz] = 0
+        err["qS"] = O.rel_err(ops.simple_apply(self.q, only_s, 1.0, H, D), parts["qS"])
+        only_z = red.clone()
+        only_z[:nS] = 0
+        only_z[nS + nz:nS + 2 * nz] = 1
+        nz_ = 2.0 ** -13                      # comparable to |q^z^| (~1e-4 for N(0,1) inputs): no cancellation in 1/out - n
+        qz = 1.0 / ops.simple_apply(self.q, only_z, nz_, H, D).double() - nz_
+        err["qz"] = O.rel_err(qz[..., 0], parts["qz"])
+        t = torch.tensor([err[k_] for k_ in sorted(err)], dtype=torch.float64, device=self.dev)
+        if self.group is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        out = {k_: float(x) for k_, x in zip(sorted(err), t.tolist())}
+        out["max"] = max(out.values())
+        out["ok"] = bool(out["max"] < TOL)
+        out["what"] = "max over ranks of the rel. error vs the fp64 oracle of the global problem; tolerance 1e-3"
+        return out
+
+
+def timed(fn, steps, barrier, dev, group):
+    import torch.distributed as dist
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(steps):
+        fn()
+    ev[1].record()
+    barrier()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / steps], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank, world, local = dist_env()
@@ -185,99 +306,76 @@ def run_ours(args):
         group = dist.group.WORLD
 
     from difformer_b200 import ops
+    from difformer_b200.sharded import shard_rows
     from oracle import difformer_oracle as O
     if args.simple_impl:
         ops.set_simple_impl(args.simple_impl)
 
-    n_total = float(N_NODES * world)
-    q, k, v = (t.to(dev) for t in O.synthetic_qkv(N_NODES, HEADS, DIM, seed=123 + rank))
-    T = N_NODES * HEADS * DIM * 4
-
-    comm = None
+    comm, collective = None, args.collective if world > 1 else None
     if group is not None and args.collective == "nvlink":
         from difformer_b200.sharded import RowShardComm
         comm = RowShardComm(group)
-    plen = int(ops.lib.dif_simple_partials_len(HEADS, HEADS, DIM, DIM))
-
-    def step():
-        if comm is not None:          # pass 1 + all-reduce over peer-mapped NVLink memory in ONE kernel
-            ex = comm.exchange(plen, dev)
-            fused = ex.fused_reduce(q, k, v)
-            if fused is not None:
-                return ops.simple_apply(q, fused[0], n_total, HEADS, DIM, prepared=fused[1])
-            partials = ex.allreduce(ops.simple_partials(q, k, v, out=ex.next_slot()))
-            return ops.simple_apply(q, partials, n_total, HEADS, DIM)
-        partials, prepared = ops.simple_partials(q, k, v, with_prepared=True)
-        if group is not None:
-            dist.all_reduce(partials, group=group)
-            prepared = None       # the pass-2 operand image only matches the un-reduced partials
-        return ops.simple_apply(q, partials, n_total, HEADS, DIM, prepared=prepared)
 
     def barrier():
         if group is not None:
             dist.barrier(group=group)
         torch.cuda.synchronize(dev)
 
-    # ---- parity spot check on the exact bench inputs (rank 0, N=1 only: fp64 oracle intermediates)
-    parity = None
-    if world == 1:
-        out = step()
-        want = O.simple_partials(q.double().cpu(), k.double().cpu(), v.double().cpu())
-        parity = {"out_rel_err": O.rel_err(out, O.simple_apply(q.double().cpu(), want))}
-        flat = ops.simple_partials(q, k, v).double().cpu()
-        parity["S_rel_err"] = O.rel_err(flat[:HEADS * DIM * DIM].reshape(HEADS, DIM, DIM), want["S"])
+    prob = Problem(N_NODES, N_NODES * world, 123 + rank, dev, group, comm, collective)
+    T = prob.T
+
+    # ---- parity on the exact bench inputs, every rank (fp64 oracle on the host cores)
+    parity = prob.parity(torch.device("cpu"))
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        prob.step()
     barrier()
-    collective = args.collective
     if comm is not None:
-        # watchdog (csrc/comm.cu): a rank whose kernel waited 30 s for a peer's flag reports it here; then every rank
-        # switches to the NCCL all-reduce of the partials so that the run still produces a valid number
-        bad = torch.tensor([1.0 if comm.exchange(plen, dev).timed_out() else 0.0], dtype=torch.float32, device=dev)
+        # watchdog (common.cuh): a rank whose kernel gave up waiting for a peer reports it here; then every rank switches
+        # to the NCCL all-reduce of the partials so that the run still produces a valid number
+        bad = torch.tensor([1.0 if comm.exchange(prob.plen, dev).timed_out() else 0.0], dtype=torch.float32, device=dev)
         dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
         if float(bad.item()) > 0:
             comm, collective = None, "nccl"
+            prob.comm = None
             if rank == 0:
                 print("bench: the NVLink exchange timed out waiting for a peer; falling back to NCCL", file=sys.stderr)
             for _ in range(3):
-                step()
+                prob.step()
             barrier()
     sampler = ClockSampler(dev)
     barrier()
     sampler.begin()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kev = []          # per-kernel events of a subset of steps (pass 1 / pass 2 split)
-    ev[0].record()
-    for i in range(args.steps):
-        if i % 16 == 0 and world == 1:
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e[0].record()
-            partials, prepared = ops.simple_partials(q, k, v, with_prepared=True)
-            e[1].record()
-            ops.simple_apply(q, partials, n_total, HEADS, DIM, prepared=prepared)
-            e[2].record()
-            kev.append(e)
-        else:
-            step()
-    ev[1].record()
-    barrier()
+    ms = timed(prob.step, args.steps, barrier, dev, group)
     sampler.end()
-    ms = ev[0].elapsed_time(ev[1]) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if group is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    ms = float(t.item())
     value = N_NODES * world / (ms * 1e-3)
+
+    # ---- cold-cache number: L2 flushed (256 MB written) before every step, each step timed on its own
+    cold_ms = None
+    if world == 1:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pairs = []
+        for _ in range(min(args.steps, 20)):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            prob.step()
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        ts = sorted(a.elapsed_time(b) for a, b in pairs)
+        cold_ms = ts[len(ts) // 2]
+        del flush
 
     # ---- end to end through the public API with pinned host buffers
     import difformer
+    q, k, v = prob.q, prob.k, prob.v
     qh, kh, vh = (x.cpu().pin_memory() for x in (q, k, v))
     oh = torch.empty((N_NODES, HEADS, DIM), dtype=torch.float32).pin_memory()
     rs = None
     if group is not None:
         from difformer_b200.sharded import RowShardedAttention
-        rs = RowShardedAttention(int(n_total), group, nvlink=(collective == "nvlink"))
+        rs = RowShardedAttention(N_NODES * world, group, nvlink=(collective == "nvlink"))
 
     # Double-buffered, three streams: the upload of step i+1 (copy engine, H2D) overlaps the kernels of step i and the
     # download of step i-1 (second copy engine, D2H).  Every step still uploads its own Q, K, V from pinned host
@@ -331,82 +429,219 @@ def run_ours(args):
     if group is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     e2e_ms = float(t.item())
+    e2e_out_err = O.rel_err(ohs[(e2e_steps - 1) & 1], prob.step())      # the downloaded result is the kernels' result
+    del dbuf, ohs, qh, kh, vh, live
+
+    # ---- BASELINE configs[3]: N = 1 632 803 rows sharded over the ranks (strong scaling), own parity (fp64 oracle on the GPU)
+    cfg_b = None
+    if not args.no_cfg_b:
+        b0, b1 = shard_rows(N_CFG_B, rank, world)
+        pb = Problem(b1 - b0, N_CFG_B, 1000 + rank, dev, group, prob.comm, collective)
+        par_b = pb.parity(dev)
+        for _ in range(3):
+            pb.step()
+        ms_b = timed(pb.step, max(5, min(args.steps, 20)), barrier, dev, group)
+        cfg_b = {"workload": f"full_attention_conv('simple') N={N_CFG_B} H={HEADS} D={DIM} fp32 row-sharded over {world} GPU(s) (BASELINE configs[3])",
+                 "scaling": "strong", "rows_this_rank": b1 - b0, "ms_per_step": ms_b, "value": N_CFG_B / (ms_b * 1e-3), "unit": UNIT,
+                 "roofline_frac": 4 * N_CFG_B * HEADS * DIM * 4 / (ms_b * 1e-3) / 1e9 / (measured_peaks()[0] * world), "parity": par_b}
+        del pb
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
+        peak, _, peak_src = measured_peaks()
         alg_bytes = 4 * T                      # read Q,K,V once + write out once
         achieved = alg_bytes / (ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "simple op = pass 1 (reduce, cross-CTA sum fused) + pass 2 (apply): one launch sequence per step",
+                "kernel": "simple op = pass 1 (reduce, cross-CTA [+cross-GPU] sum fused) + pass 2 (apply): one launch sequence per step",
                 "algorithmic_bytes_per_step": alg_bytes}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             try:
-                roof["traffic"] = json.load(open(tp)).get("simple_step_dram_bytes")
+                tj = json.load(open(tp))
+                roof["traffic"] = tj.get("simple_step_dram_bytes")
+                roof["traffic_source"] = "ncu --set full capture committed under profiles/ (not re-measured in this run): " + str(tj.get("source", ""))[:160]
             except Exception:
                 pass
-        if kev:
-            r_ms = sum(e[0].elapsed_time(e[1]) for e in kev) / len(kev)
-            a_ms = sum(e[1].elapsed_time(e[2]) for e in kev) / len(kev)
-            roof["passes"] = [
-                {"name": "pass1 reduce (+fused finalize)", "ms": r_ms, "moved_bytes": 3 * T, "gbs": 3 * T / (r_ms * 1e-3) / 1e9},
-                {"name": "pass2 apply", "ms": a_ms, "moved_bytes": 2 * T, "gbs": 2 * T / (a_ms * 1e-3) / 1e9}]
+        if cold_ms is not None:
+            roof["cold"] = {"ms_per_step": cold_ms, "frac": alg_bytes / (cold_ms * 1e-3) / 1e9 / peak,
+                            "what": "median of per-step CUDA-event times with the L2 flushed (256 MB memset) before every step"}
         torch_gpu = None
         if world == 1:
             # the reference's own op chain (einsums + materialised broadcasts) on the same B200, CUDA tensors
+            fn, kind, what = cpu_reference_fn()
             with torch.no_grad():
                 for _ in range(5):
-                    O.simple_attention_reference_chain(q, k, v)
+                    fn(q, k, v)
                 torch.cuda.synchronize(dev)
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 g0.record()
                 for _ in range(20):
-                    O.simple_attention_reference_chain(q, k, v)
+                    fn(q, k, v)
                 g1.record()
                 torch.cuda.synchronize(dev)
             tg = g0.elapsed_time(g1) / 20
-            torch_gpu = {"value": N_NODES / (tg * 1e-3), "unit": UNIT, "ms_per_step": tg,
-                         "what": "reference einsum chain (difformer.py:18-39 transcription) in PyTorch eager on the same GPU"}
+            torch_gpu = {"value": N_NODES / (tg * 1e-3), "unit": UNIT, "ms_per_step": tg, "kind": kind,
+                         "what": f"{what} in PyTorch eager on the same GPU"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, dt, rows, threads = cpu_reference_rate(steps=8, warmup=2, budget_s=20.0)
-            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{rows} of {N_NODES} rows x 8 steps, oracle transcription of the einsum chain difformer.py:18-39, torch CPU fp32"}
+            rate, dt, rows, threads, kind, what = cpu_reference_rate(steps=8, warmup=2, budget_s=20.0)
+            r1, dt1, rows1, _, _, _ = cpu_reference_rate(steps=3, warmup=1, budget_s=5.0, rows=16384, threads=1)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"{rows} of {N_NODES} rows x 8 steps, {what}, torch CPU fp32 (host has {os.cpu_count()} hardware threads)",
+                   "one_thread": {"value": r1, "unit": UNIT, "cores": 1, "sample": f"{rows1} rows x 3 steps"}}
+        cfg = workload_config(world)      # identical in both arms; everything specific to this arm goes to `notes`
+        notes = {"parallelism": "single GPU" if world == 1 else (
+                     f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
+                     ("fused into the pass-1 kernel tail, LL push over peer-mapped NVLink memory (no NCCL call)" if collective == "nvlink" else "NCCL")),
+                 "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps (roofline.cold: flushed)",
+                 "simple_impl": args.simple_impl or "auto"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"full_attention_conv('simple') N={N_NODES} H={HEADS} D={DIM} fp32 per GPU (BASELINE configs[2])",
-                           "rows_per_gpu": N_NODES, "global_rows": int(n_total),
-                           "parallelism": "single GPU" if world == 1 else (
-                               f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
-                               ("fused into the pass-1 kernel tail over peer-mapped NVLink memory (no NCCL call)" if collective == "nvlink" else "NCCL")),
-                           "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps",
-                           "simple_impl": args.simple_impl or "auto"},
+                "data": "synthetic", "config": cfg, "notes": notes,
                 "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
                 "e2e": {"value": N_NODES * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": 3 * T, "d2h_bytes_per_step": T, "steps": e2e_steps,
+                        "h2d_bytes_per_step": 3 * T, "d2h_bytes_per_step": T, "steps": e2e_steps, "result_rel_err_vs_device_run": e2e_out_err,
                         "api": "difformer.full_attention_conv(q, k, v, 'simple') on pinned host tensors; double-buffered (upload of step i+1 overlaps download of step i-1)"},
                 # tcgen05 path: reduce (cross-CTA sum fused in) + apply; generic path: reduce + finalize + apply
-                "gpu_launches": ((3 if (args.simple_impl == "generic" or os.environ.get("DIF_TC_P1_TMA") == "0") else 2)
-) * args.steps, "clocks": sampler.summary(), "parity": parity}
+                "gpu_launches": (3 if args.simple_impl == "generic" else 2) * args.steps,
+                "clocks": sampler.summary(), "parity": parity, "cfg_b": cfg_b}
         print(json.dumps(line), flush=True)
+    ok = parity["ok"] and (cfg_b is None or cfg_b["parity"]["ok"])
     if group is not None:
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: PARITY FAILURE (see the `parity` objects of the JSON line): the timing above is void")
+
+
+# ------------------------------------------------------------------------------------------------
+# the other SURVEY 8 rows (1 GPU), one JSON line each
+# ------------------------------------------------------------------------------------------------
+def run_extra(args):
+    import difformer
+    from difformer_b200 import ops
+    from oracle import difformer_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    hbm, tens, src = measured_peaks()
+
+    def timeit(fn, iters):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    steps = min(args.steps, 200)
+    w = args.workload
+    line = {"workload": w, "n_gpus": 1, "steps": steps, "data": "synthetic", "peak_source": src}
+    if w == "sigmoid_cora":          # BASELINE configs[1]: Cora shape
+        n, h, d = 2708, 1, 64
+        q, k, v = (t.to(dev) for t in O.synthetic_qkv(n, h, d, seed=1))
+        q, k = q * 0.3, k * 0.3
+        ms = timeit(lambda: difformer.full_attention_conv(q, k, v, "sigmoid"), steps)
+        qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+
+        def fb():
+            o = difformer.full_attention_conv(qg, kg, vg, "sigmoid")
+            o.backward(torch.ones_like(o))
+        ms_fb = timeit(fb, steps)
+        out = difformer.full_attention_conv(q, k, v, "sigmoid")
+        want = O.sigmoid_attention(q.double().cpu(), k.double().cpu(), v.double().cpu())
+        flops = 4.0 * n * n * h * d
+        line.update({"metric": "node-updates/s, full_attention_conv('sigmoid') N=2708 H=1 D=64 fp32 (Cora shape)", "value": n / (ms * 1e-3),
+                     "unit": UNIT, "ms_per_step": ms, "fwd_bwd_ms": ms_fb, "dtype": "f32 (bf16x3 split on the tensor cores)",
+                     "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tens, "unit": "TFLOP/s",
+                                  "frac": flops / (ms * 1e-3) / 1e12 / tens, "flops": flops},
+                     "parity": {"out": O.rel_err(out, want)}})
+    elif w == "layer":               # a-4/a-5: attention + gcn + head mean + residual, no grad, config A with E = 17 N
+        n, h, d = N_NODES, HEADS, DIM
+        q, k, v = (t.to(dev) for t in O.synthetic_qkv(n, h, d, seed=3))
+        ei = O.synthetic_graph(n, 8 * n, seed=4).to(dev)
+        E = ei.shape[1]
+        csr = ops.graph_csr(ei, None, n)
+        prev = torch.randn(n, d, device=dev)
+
+        def layer():
+            vb_ = torch.empty((n, d), dtype=torch.float32, device=dev)
+            part, prep = ops.simple_partials(q, k, v, with_prepared=True, vbar=vb_)
+            g = ops.spmm(csr, vb_.view(n, 1, d)).view(n, d)
+            ep = ops.make_epilogue(0.5 / h, [(g, 0.5), (prev, 0.5)])
+            return ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)
+        ms = timeit(layer, steps)
+        alg = n * (3 * h * d * 4 + 2 * d * 4) + E * 8 + (n + 1) * 4
+        attn = O.simple_attention(q.double().cpu(), k.double().cpu(), v.double().cpu())
+        gcn = O.gcn_conv(v.double().cpu(), ei.cpu(), None)
+        want = 0.5 * (0.5 * attn + 0.5 * gcn).mean(1) + 0.5 * prev.double().cpu()
+        line.update({"metric": f"node-updates/s, fused propagation layer (attention + gcn E={E} + head mean + residual) N={n} H=4 D=64 fp32",
+                     "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f32",
+                     "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": alg / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": alg},
+                     "parity": {"out": O.rel_err(layer(), want)}})
+    elif w == "segmented":           # BASELINE configs[4]: B = 8192 graphs, n_g ~ U[10,40], H = 1, D = 64
+        gen = torch.Generator().manual_seed(5)
+        nn_ = torch.randint(10, 41, (8192,), generator=gen)
+        tot = int(nn_.sum())
+        qs, ks, vs = (t.to(dev) for t in O.synthetic_qkv(tot, 1, 64, seed=6))
+        nn_d = nn_.to(dev)
+        ms = timeit(lambda: ops.segmented_full_attention(qs, ks, vs, "simple", nn_d), steps)
+        qsg, ksg, vsg = (t.clone().requires_grad_(True) for t in (qs, ks, vs))
+        gs = torch.randn(tot, 1, 64, device=dev)
+
+        def fb3():
+            o = ops.segmented_full_attention(qsg, ksg, vsg, "simple", nn_d)
+            o.backward(gs)
+        ms_fb = timeit(fb3, steps)
+        want = O.segmented_simple_attention(qs.double().cpu(), ks.double().cpu(), vs.double().cpu(), nn_)
+        alg = 4 * tot * 64 * 4
+        line.update({"metric": f"node-updates/s, batched-graph 'simple' (difformer-v2) B=8192 sumN={tot} H=1 D=64 fp32", "value": tot / (ms * 1e-3),
+                     "unit": UNIT, "ms_per_step": ms, "fwd_bwd_ms": ms_fb, "dtype": "f32",
+                     "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm,
+                                  "algorithmic_bytes_per_step": alg},
+                     "parity": {"out": O.rel_err(ops.segmented_full_attention(qs, ks, vs, "simple", nn_d), want)}})
+    elif w == "fwdbwd":              # a-1 + a-1b at config A through torch.autograd
+        n, h, d = N_NODES, HEADS, DIM
+        q, k, v = (t.to(dev) for t in O.synthetic_qkv(n, h, d, seed=3))
+        qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+        go = torch.randn(n, h, d, device=dev)
+
+        def fb2():
+            qg.grad = kg.grad = vg.grad = None
+            o = difformer.full_attention_conv(qg, kg, vg, "simple")
+            o.backward(go)
+        ms = timeit(fb2, steps)
+        dq, dk, dv = O.simple_attention_backward(q.double().cpu(), k.double().cpu(), v.double().cpu(), go.double().cpu())
+        alg = (4 + 11) * n * h * d * 4     # fwd 4T; bwd: pass 1 reads q,g,out (3T), dq/dk/dv read 2T+2T+1T and write 3T
+        line.update({"metric": f"node-updates/s, full_attention_conv('simple') forward+backward N={n} H=4 D=64 fp32", "value": n / (ms * 1e-3),
+                     "unit": UNIT, "ms_per_step": ms, "dtype": "f32",
+                     "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm,
+                                  "algorithmic_bytes_per_step": alg},
+                     "parity": {"dq": O.rel_err(qg.grad, dq), "dk": O.rel_err(kg.grad, dk), "dv": O.rel_err(vg.grad, dv)}})
+    else:
+        raise SystemExit(f"unknown workload {w}")
+    print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="simple", choices=["simple", "sigmoid_cora", "layer", "segmented", "fwdbwd"])
     ap.add_argument("--simple-impl", default=None, choices=[None, "auto", "generic", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg-b", action="store_true", help="skip the BASELINE configs[3] (N=1.6M strong-scaling) leg")
     ap.add_argument("--collective", default="nvlink", choices=["nvlink", "nccl"], help="multi-GPU all-reduce of the partials")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "simple":
+        run_extra(args)
     else:
         run_ours(args)
 

@@ -51,14 +51,14 @@ SIGNATURES = {
     "dif_simple_reduce_allreduce": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
                                             ctypes.POINTER(c_vp), c_i32, c_i32, ctypes.c_uint64, c_vp]),
     "dif_comm_buffer_bytes": (c_i64, [c_i64]),
-    "dif_comm_slot_offset_bytes": (c_i64, [c_i64, ctypes.c_uint64]),
     "dif_comm_alloc": (c_i32, [ctypes.POINTER(c_vp), c_i64]),
     "dif_comm_free": (c_i32, [c_vp]),
     "dif_comm_export": (c_i32, [c_vp, c_vp]),
     "dif_comm_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
     "dif_comm_close": (c_i32, [c_vp]),
-    "dif_comm_status": (c_i32, [c_vp, c_i64, ctypes.POINTER(c_i32)]),
-    "dif_comm_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, ctypes.c_uint64, c_vp, c_vp]),
+    "dif_comm_status": (c_i32, [c_vp, ctypes.POINTER(c_i32)]),
+    "dif_comm_reset": (c_i32, [c_vp]),
+    "dif_comm_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
 }
 
 

@@ -1,78 +1,55 @@
 // One-shot NVLink all-reduce of the pass-1 partials: the only collective of the path.
 //
 // Payload: dif_simple_partials_len() floats (67.6 KB at H=4, D=64), independent of N => latency bound.
-// Every rank owns a peer-mapped buffer [2 data slots | flag slots]; pass 1 writes its partials straight
-// into the local data slot.  The kernel (a) publishes "slot ready" flags into every peer's buffer with
-// system-scope release stores over NVLink, (b) waits for all peers' flags, (c) sums the G slots in rank
-// order reading peer memory directly (NVSwitch: every peer at full bandwidth, 7 x 68 KB per rank).  Same
-// summation order on every rank => bit-identical results, no NCCL launch, no host sync.  Slots alternate
-// by sequence number; a slot is only rewritten two calls later, after every peer has signalled the call
-// in between (which it sends after finishing its reads).
+// Every rank owns a peer-mapped buffer [header | LL region] (layout and protocol: common.cuh).  A rank PUSHES each
+// element of its contribution into every peer's region as one 64-bit word {call number | fp32} and polls the words the
+// peers pushed into its own region: one NVLink traversal, no fences, no flag round trip, no NCCL launch, no host sync.
+// Ranks are summed in rank order => bit-identical results everywhere.  The same protocol runs inside the tail of the
+// pass-1 kernel (simple_sm100.cu: compute + collective in one kernel); this file holds the stand-alone kernel, the
+// buffer management and the watchdog plumbing (a wait that sees nothing for 30 s gives up, marks every rank's status
+// word and raises a pinned host flag that dif_comm_status() reads without synchronising).
 #include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
 namespace dif {
 namespace {
 
-constexpr int kMaxRanks = kCommMaxRanks;
-
 struct CommArgs {
-    float* bufs[kMaxRanks];   // peer-mapped base pointers, index = rank
-    int rank, world;
+    CommPeers peers;
     int64_t len;              // floats
-    int64_t slot_floats;      // data slot stride (floats)
-    unsigned long long seq;
-    float* out;
+    const float* src;         // this rank's contribution (any device memory)
+    float* out;               // sum over ranks (local)
 };
 
-// flags: [2 slots][kMaxRanks][256 slices] u64 after the two data slots, then one u64 status word.  The fused pass-1
-// tail (simple_sm100.cu) uses one flag per (slot, rank, column slice); this stand-alone kernel uses slice 255.
-// Watchdog: a wait that sees no flag for kCommTimeoutNs gives up, sets the status word of the LOCAL buffer and lets
-// the kernel finish with a meaningless sum, so that a peer that died or never launched cannot hang the GPU;
-// dif_comm_status() reports it to the host.
-__device__ __forceinline__ unsigned long long* flag_ptr(float* base, int64_t slot_floats, int idx) {
-    return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + (size_t)idx * 256 + 255;
+// Stand-alone one-shot all-reduce (backward partials, shapes on the generic path): same LL push protocol as the fused
+// pass-1 tail.  Thread i owns element i: push it to every peer, poll the peers' words in the local region, add in rank
+// order (every rank computes the same bits).
+__global__ void __launch_bounds__(256) allreduce_kernel(const __grid_constant__ CommArgs a) {
+    const CommPeers& c = a.peers;
+    const int slot = (int)(c.seq & 1);
+    const uint32_t tag = (uint32_t)c.seq;
+    if (blockIdx.x == 0 && threadIdx.x == 0) comm_check_status(c);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.len; i += (int64_t)gridDim.x * blockDim.x) {
+        const float mine = a.src[i];
+        for (int p = 1; p < c.world; ++p) {
+            int r = c.rank + p;
+            if (r >= c.world) r -= c.world;
+            comm_ll_send(comm_ll_ptr(c.bufs[r], c.lenpad, slot, c.rank) + i, mine, tag);
+        }
+        float s = 0.f;
+        for (int r = 0; r < c.world; ++r)
+            s += r == c.rank ? mine : comm_ll_recv(comm_ll_ptr(c.bufs[c.rank], c.lenpad, slot, r) + i, tag, c);
+        a.out[i] = s;
+    }
 }
 
-__global__ void __launch_bounds__(256) allreduce_kernel(CommArgs a) {
-    const int slot = (int)(a.seq & 1);
-    // (a) one CTA signals: flag[slot][my_rank] := seq in every peer's buffer (and my own)
-    if (blockIdx.x == 0 && threadIdx.x < a.world) {
-        __threadfence_system();
-        unsigned long long* f = flag_ptr(a.bufs[threadIdx.x], a.slot_floats, slot * kMaxRanks + a.rank);
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(a.seq) : "memory");
-    }
-    // (b) every CTA waits for all ranks' flags in the local buffer
-    if (threadIdx.x < a.world) {
-        const unsigned long long* f = flag_ptr(a.bufs[a.rank], a.slot_floats, slot * kMaxRanks + threadIdx.x);
-        unsigned long long* status = comm_status_ptr(a.bufs[a.rank], a.slot_floats);
-        comm_wait_flag(f, a.seq, status);
-    }
-    __syncthreads();
-    // (c) sum the slots in rank order (fixed order: every rank computes the same bits)
-    const int64_t n4 = a.len >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < a.world; ++r) {
-            float4 x;   // system-scope load: peer memory over NVLink, never served from a stale line
-            asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                         : "l"(a.bufs[r] + slot * a.slot_floats + 4 * i) : "memory");
-            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
-        }
-        *reinterpret_cast<float4*>(a.out + 4 * i) = s;
-    }
-    if (blockIdx.x == 0)
-        for (int64_t i = 4 * n4 + threadIdx.x; i < a.len; i += blockDim.x) {
-            float s = 0.f;
-            for (int r = 0; r < a.world; ++r) {
-                float x;
-                asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.bufs[r] + slot * a.slot_floats + i) : "memory");
-                s += x;
-            }
-            a.out[i] = s;
-        }
-}
+// device buffer -> pinned, mapped host flag (written by comm_fail, read by dif_comm_status without a device sync)
+std::mutex g_mu;
+std::unordered_map<void*, unsigned long long*> g_host_flags;
 
 }  // namespace
 }  // namespace dif
@@ -80,34 +57,59 @@ __global__ void __launch_bounds__(256) allreduce_kernel(CommArgs a) {
 using namespace dif;
 
 extern "C" int64_t dif_comm_buffer_bytes(int64_t len) {
-    const int64_t slot = (len + 63) & ~(int64_t)63;
-    return 2 * slot * (int64_t)sizeof(float) + 2 * kMaxRanks * 256 * (int64_t)sizeof(unsigned long long) + 64;   // + status word
+    return (int64_t)kCommHeaderBytes + 2 * (int64_t)kCommMaxRanks * comm_lenpad(len) * (int64_t)sizeof(unsigned long long);
 }
 
-extern "C" int dif_comm_status(const void* own_buf, int64_t len, int* timed_out) {
-    DIF_REQUIRE(own_buf && timed_out && len > 0, DIF_EARG, "comm_status: bad argument");
-    const int64_t slot = (len + 63) & ~(int64_t)63;
-    unsigned long long v = 0;
-    DIF_CUDA_OK(cudaMemcpy(&v, comm_status_ptr((float*)own_buf, slot), sizeof(v), cudaMemcpyDeviceToHost));
-    *timed_out = v != 0;
+extern "C" int dif_comm_status(const void* own_buf, int* timed_out) {
+    DIF_REQUIRE(own_buf && timed_out, DIF_EARG, "comm_status: bad argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_host_flags.find(const_cast<void*>(own_buf));
+    DIF_REQUIRE(it != g_host_flags.end(), DIF_EARG, "comm_status: not a dif_comm_alloc buffer of this process");
+    *timed_out = *reinterpret_cast<volatile unsigned long long*>(it->second) != 0;
     return DIF_OK;
 }
 
-extern "C" int64_t dif_comm_slot_offset_bytes(int64_t len, unsigned long long seq) {
-    const int64_t slot = (len + 63) & ~(int64_t)63;
-    return (int64_t)(seq & 1) * slot * (int64_t)sizeof(float);
+extern "C" int dif_comm_reset(void* own_buf) {
+    DIF_REQUIRE(own_buf, DIF_EARG, "comm_reset: null pointer");
+    unsigned long long* host = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_host_flags.find(own_buf);
+        DIF_REQUIRE(it != g_host_flags.end(), DIF_EARG, "comm_reset: not a dif_comm_alloc buffer of this process");
+        host = it->second;
+    }
+    DIF_CUDA_OK(cudaDeviceSynchronize());
+    DIF_CUDA_OK(cudaMemset(own_buf, 0, 8));          // status word only: the LL words keep their (stale) tags
+    DIF_CUDA_OK(cudaDeviceSynchronize());
+    *reinterpret_cast<volatile unsigned long long*>(host) = 0;
+    return DIF_OK;
 }
 
 extern "C" int dif_comm_alloc(void** ptr, int64_t bytes) {
-    DIF_REQUIRE(ptr && bytes > 0, DIF_EARG, "comm_alloc: bad argument");
+    DIF_REQUIRE(ptr && bytes >= kCommHeaderBytes, DIF_EARG, "comm_alloc: bad argument");
     DIF_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));
     DIF_CUDA_OK(cudaMemset(*ptr, 0, (size_t)bytes));
+    unsigned long long *host = nullptr, *host_dev = nullptr;
+    DIF_CUDA_OK(cudaHostAlloc((void**)&host, 64, cudaHostAllocMapped));
+    *host = 0;
+    DIF_CUDA_OK(cudaHostGetDevicePointer((void**)&host_dev, host, 0));
+    DIF_CUDA_OK(cudaMemcpy(reinterpret_cast<char*>(*ptr) + 8, &host_dev, sizeof(host_dev), cudaMemcpyHostToDevice));
     DIF_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_host_flags[*ptr] = host;
     return DIF_OK;
 }
 
 extern "C" int dif_comm_free(void* ptr) {
-    if (ptr) DIF_CUDA_OK(cudaFree(ptr));
+    if (!ptr) return DIF_OK;
+    unsigned long long* host = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_host_flags.find(ptr);
+        if (it != g_host_flags.end()) { host = it->second; g_host_flags.erase(it); }
+    }
+    DIF_CUDA_OK(cudaFree(ptr));
+    if (host) DIF_CUDA_OK(cudaFreeHost(host));
     return DIF_OK;
 }
 
@@ -131,16 +133,17 @@ extern "C" int dif_comm_close(void* peer_ptr) {
     return DIF_OK;
 }
 
-extern "C" int dif_comm_allreduce(void* const* bufs, int rank, int world, int64_t len, unsigned long long seq, float* out, void* stream) {
-    DIF_REQUIRE(bufs && out && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && len > 0 && seq > 0, DIF_EARG,
-                "comm_allreduce: bad argument (world <= %d, seq >= 1)", kMaxRanks);
+extern "C" int dif_comm_allreduce(void* const* bufs, int rank, int world, int64_t len, unsigned long long seq,
+                                  const float* src, float* out, void* stream) {
+    DIF_REQUIRE(bufs && src && out && world >= 1 && world <= kCommMaxRanks && rank >= 0 && rank < world && len > 0 && seq > 0, DIF_EARG,
+                "comm_allreduce: bad argument (world <= %d, seq >= 1)", kCommMaxRanks);
     CommArgs a{};
-    for (int r = 0; r < world; ++r) { DIF_REQUIRE(bufs[r], DIF_EARG, "comm_allreduce: null peer buffer %d", r); a.bufs[r] = (float*)bufs[r]; }
-    a.rank = rank; a.world = world; a.len = len; a.slot_floats = (len + 63) & ~(int64_t)63; a.seq = seq; a.out = out;
-    const int64_t n4 = len / 4;
-    int grid = (int)((n4 + 255) / 256);
+    for (int r = 0; r < world; ++r) { DIF_REQUIRE(bufs[r], DIF_EARG, "comm_allreduce: null peer buffer %d", r); a.peers.bufs[r] = bufs[r]; }
+    a.peers.rank = rank; a.peers.world = world; a.peers.seq = seq; a.peers.lenpad = comm_lenpad(len); a.peers.timeout_ns = comm_timeout_ns();
+    a.len = len; a.src = src; a.out = out;
+    int grid = (int)((len + 255) / 256);
     if (grid < 1) grid = 1;
-    if (grid > 32) grid = 32;
+    if (grid > 74) grid = 74;
     allreduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     DIF_LAUNCH_OK();
     return DIF_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/difformer_b200.h"
 
@@ -91,27 +92,70 @@ int simple_apply_generic(const float* q, const float* partials, double n_total, 
 int64_t simple_generic_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 
 bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D);
-// ---- peer-mapped exchange buffers (comm.cu, simple_sm100.cu): [2 data slots | flags [2][16][256] u64 | status u64]
+// ---- peer-mapped exchange buffers (comm.cu, simple_sm100.cu) ----------------------------------------------------
+// Layout of one rank's buffer: [header 128 B: status u64 | device pointer of this rank's pinned host flag u64]
+//                              [LL region: u64 [2 slots][kCommMaxRanks source ranks][lenpad]]
+// LL ("low latency") protocol: a sender writes 64-bit words {tag = call number (32 bits) | fp32 payload} straight
+// into the receiver's LL region with one scalar store per word (single-copy atomic), the receiver polls the word
+// until the tag matches.  Data and flag travel together: no fence, no flag round trip, one NVLink traversal.
+// Slots alternate by call number; a slot is rewritten two calls later, which a peer can only reach after this
+// rank has sent (i.e. finished reading for) the call in between.
 constexpr int kCommMaxRanks = 16;
-constexpr unsigned long long kCommTimeoutNs = 30000000000ull;         // 30 s without a peer's flag => give up
-__host__ __device__ __forceinline__ unsigned long long* comm_status_ptr(float* base, int64_t slot_floats) {
-    return reinterpret_cast<unsigned long long*>(base + 2 * slot_floats) + (size_t)2 * kCommMaxRanks * 256;
+constexpr int kCommHeaderBytes = 128;
+constexpr unsigned long long kCommTimeoutNs = 30000000000ull;         // default: 30 s without a peer's word => give up
+__host__ __device__ __forceinline__ int64_t comm_lenpad(int64_t len) { return (len + 63) & ~(int64_t)63; }
+__host__ __device__ __forceinline__ unsigned long long* comm_status_ptr(void* base) { return reinterpret_cast<unsigned long long*>(base); }
+__host__ __device__ __forceinline__ unsigned long long* comm_ll_ptr(void* base, int64_t lenpad, int slot, int src_rank) {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + kCommHeaderBytes) +
+           ((size_t)slot * kCommMaxRanks + (size_t)src_rank) * (size_t)lenpad;
 }
-// spin until *flag == seq (system scope); bounded: on timeout (or if an earlier wait already timed out) set *status
-__device__ __forceinline__ void comm_wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned long long* status) {
-    unsigned long long got, t0 = 0;
+struct CommPeers {            // kernel argument: every rank's buffer as mapped in this process
+    void* bufs[kCommMaxRanks];
+    int rank, world;
+    unsigned long long seq;   // call number 1, 2, 3, ... identical on all ranks
+    int64_t lenpad;
+    unsigned long long timeout_ns;   // watchdog bound (comm_timeout_ns(): DIF_COMM_TIMEOUT_MS, default 30 s)
+};
+inline unsigned long long comm_timeout_ns() {
+    static unsigned long long v = 0;
+    if (v == 0) {
+        const char* e = getenv("DIF_COMM_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 0;
+        v = ms > 0 ? (unsigned long long)ms * 1000000ull : kCommTimeoutNs;
+    }
+    return v;
+}
+// A wait gave up (or found the status word already set): mark EVERY rank's status word (a peer that is not waiting right
+// now sees it at its next call) and raise this rank's pinned host flag (read by the host without a device sync).
+static __device__ __noinline__ void comm_fail(const CommPeers& c) {
+    for (int r = 0; r < c.world; ++r)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(comm_status_ptr(c.bufs[r])), "l"(1ull) : "memory");
+    unsigned long long* host = *reinterpret_cast<unsigned long long* volatile*>(reinterpret_cast<char*>(c.bufs[c.rank]) + 8);
+    if (host) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(host), "l"(1ull) : "memory");
+}
+// one thread per call: a peer reported a failure since the last call -> surface it on this rank's host flag too
+__device__ __forceinline__ void comm_check_status(const CommPeers& c) {
+    unsigned long long s;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(comm_status_ptr(c.bufs[c.rank])) : "memory");
+    if (s != 0) comm_fail(c);
+}
+__device__ __forceinline__ void comm_ll_send(unsigned long long* dst, float x, uint32_t tag) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(x);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst), "l"(w) : "memory");
+}
+// poll one LL word until its tag matches; bounded (watchdog): on timeout the result is meaningless and comm_fail() has run
+__device__ __forceinline__ float comm_ll_recv(const unsigned long long* src, uint32_t tag, const CommPeers& c) {
+    unsigned long long w, t0 = 0;
     unsigned int spins = 0;
     for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(flag) : "memory");
-        if (got == seq) return;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+        if ((uint32_t)(w >> 32) == tag) return __uint_as_float((uint32_t)w);
         if ((++spins & 1023u) == 0) {
-            unsigned long long now;
+            unsigned long long now, s;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            if (now - t0 > kCommTimeoutNs || *reinterpret_cast<volatile unsigned long long*>(status) != 0) {
-                atomicMax(status, 1ull);
-                return;
-            }
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(comm_status_ptr(c.bufs[c.rank])) : "memory");
+            if (now - t0 > c.timeout_ns || s != 0) { comm_fail(c); return 0.f; }
         }
     }
 }

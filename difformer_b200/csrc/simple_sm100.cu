@@ -69,13 +69,7 @@ struct Geo {
 };
 
 constexpr int kBOp = 80 * 128;                        // one (head, hi|lo) B-operand tile of pass 2
-constexpr int kShardMaxRanks = 16;
-struct ShardArgs {            // multi-GPU: peer-mapped exchange buffers [2 data slots | flags], see csrc/comm.cu
-    float* bufs[kShardMaxRanks];
-    int rank, world;
-    unsigned long long seq;
-    int64_t slot_floats;
-};
+using ShardArgs = CommPeers;  // multi-GPU: peer-mapped LL exchange buffers (common.cuh, csrc/comm.cu)
 constexpr int kThreadsT = 10 * 32;                    // pass 1: warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
 constexpr int kSlices = 148;                          // column slices of the record for the fused cross-CTA sum
 
@@ -378,6 +372,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
     const ShardArgs& sh = a.sh;
     const bool sharded = sh.world > 1;
     const int xslot = (int)(sh.seq & 1);
+    if (sharded && blockIdx.x == 0 && tid == 0) comm_check_status(sh);
     bool waited = false;
     uint32_t tail_phase = 0;
     for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
@@ -425,29 +420,20 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
         }
         float sum = local;
         if (sharded) {
-            // ---- cross-GPU: the same kernel finishes the all-reduce over NVLink, slice by slice.  Publish the local slice in
-            // this rank's peer-mapped buffer, raise flag (slot, rank, slice) in every peer, wait for the peers' flags, add
-            // the ranks' slices in rank order (bit-identical on all ranks).
-            float* mine = sh.bufs[sh.rank] + (int64_t)xslot * sh.slot_floats;
-            if (live) mine[j] = local;
-            __threadfence_system();
-            __syncthreads();
-            if (tid < sh.world) {
-                unsigned long long* f = reinterpret_cast<unsigned long long*>(sh.bufs[tid] + 2 * sh.slot_floats) +
-                                        ((size_t)(xslot * kShardMaxRanks + sh.rank) * 256 + sl);
-                asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(sh.seq) : "memory");
-                const unsigned long long* w = reinterpret_cast<const unsigned long long*>(sh.bufs[sh.rank] + 2 * sh.slot_floats) +
-                                              ((size_t)(xslot * kShardMaxRanks + tid) * 256 + sl);
-                comm_wait_flag(w, sh.seq, comm_status_ptr(sh.bufs[sh.rank], sh.slot_floats));   // bounded (watchdog, comm.cu)
-            }
-            __syncthreads();
+            // ---- cross-GPU: the same kernel finishes the all-reduce over NVLink, slice by slice, LL push protocol
+            // (common.cuh): element j of the local slice goes straight into every peer's LL region as one 64-bit word
+            // {call number | fp32}; then the peers' words are polled in the LOCAL region and added in rank order
+            // (bit-identical on all ranks).  One NVLink traversal on the critical path, no fence, no flag round trip.
+            const uint32_t tag = (uint32_t)sh.seq;
             if (live) {
-                sum = 0.f;
-                for (int r = 0; r < sh.world; ++r) {
-                    float x;
-                    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(sh.bufs[r] + (int64_t)xslot * sh.slot_floats + j) : "memory");
-                    sum += x;
+                for (int p = 1; p < sh.world; ++p) {          // start at the next rank: spreads the targets over the switch
+                    int r = sh.rank + p;
+                    if (r >= sh.world) r -= sh.world;
+                    comm_ll_send(comm_ll_ptr(sh.bufs[r], sh.lenpad, xslot, sh.rank) + j, local, tag);
                 }
+                sum = 0.f;
+                for (int r = 0; r < sh.world; ++r)
+                    sum += r == sh.rank ? local : comm_ll_recv(comm_ll_ptr(sh.bufs[sh.rank], sh.lenpad, xslot, r) + j, tag, sh);
             }
         }
         if (live) {
@@ -1161,10 +1147,11 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     a.l2_hints = hints;
     a.sh.world = 1;
     if (peer_bufs != nullptr && world > 1) {
-        DIF_REQUIRE(world <= kShardMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_reduce(sharded): bad rank/world/seq");
-        for (int r = 0; r < world; ++r) { DIF_REQUIRE(peer_bufs[r], DIF_EARG, "simple_reduce(sharded): null peer buffer"); a.sh.bufs[r] = (float*)peer_bufs[r]; }
+        DIF_REQUIRE(world <= kCommMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_reduce(sharded): bad rank/world/seq");
+        for (int r = 0; r < world; ++r) { DIF_REQUIRE(peer_bufs[r], DIF_EARG, "simple_reduce(sharded): null peer buffer"); a.sh.bufs[r] = peer_bufs[r]; }
         a.sh.rank = rank; a.sh.world = world; a.sh.seq = seq;
-        a.sh.slot_floats = (SimpleLayout{H, Hv, M, D}.len() + 63) & ~(int64_t)63;
+        a.sh.lenpad = comm_lenpad(SimpleLayout{H, Hv, M, D}.len());
+        a.sh.timeout_ns = comm_timeout_ns();
     }
     a.dbg = dbg_buffer();
     int rc = H == 4 ? launch_reduce<4, false>(a, grid, st) : H == 2 ? launch_reduce<2, false>(a, grid, st) : launch_reduce<1, false>(a, grid, st);

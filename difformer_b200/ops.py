@@ -35,6 +35,24 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+_WS_CACHE: dict = {}
+
+
+def workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, current stream): the C ABI never allocates and a `torch.empty` per call is
+    pure host overhead.  Stream-ordered reuse is safe (every kernel that touches it is enqueued on that stream).  During
+    CUDA-graph capture a fresh tensor from the capture pool is returned instead (a cached buffer must not grow there)."""
+    nbytes = max(int(nbytes), 16)
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
+
+
 def _need_cuda(*ts: torch.Tensor) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -80,7 +98,7 @@ def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_p
     else:
         partials = torch.empty(plen, dtype=torch.float32, device=qs.device)
     wsb = lib.dif_simple_workspace_bytes(N, H, Hv, M, D)
-    ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=qs.device)
+    ws = workspace(qs.device, wsb)
     pb = int(lib.dif_simple_prepared_bytes(H, Hv, M, D)) if (with_prepared and _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC) else 0
     prepared = torch.empty(pb, dtype=torch.uint8, device=qs.device) if pb > 0 else None
     with torch.cuda.device(qs.device):
@@ -140,8 +158,7 @@ class _SimpleAttention(torch.autograd.Function):
             if fused is not None:
                 partials, prepared = fused
             else:
-                local = simple_partials(qs, ks, vs, out=ex.next_slot())
-                partials, prepared = ex.allreduce(local), None
+                partials, prepared = ex.allreduce(simple_partials(qs, ks, vs)), None
         else:
             partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
             if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -160,7 +177,7 @@ class _SimpleAttention(torch.autograd.Function):
         g = _f32c(g)
         dev = qs.device
         bwd = torch.zeros(lib.dif_simple_bwd_partials_len(H, M, D), dtype=torch.float32, device=dev)
-        ws = torch.empty(max(int(lib.dif_simple_workspace_bytes(N, H, Hv, M, D)), 16), dtype=torch.uint8, device=dev)
+        ws = workspace(dev, lib.dif_simple_workspace_bytes(N, H, Hv, M, D))
         dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
         rsl = int(lib.dif_simple_bwd_rowscal_len(N, H, Hv, M, D)) if _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC else 0
         rowscal = torch.empty(rsl, dtype=torch.float32, device=dev) if rsl > 0 else None    # tcgen05 backward scratch
@@ -172,10 +189,7 @@ class _SimpleAttention(torch.autograd.Function):
                   "dif_simple_bwd_reduce")
             xch = getattr(ctx.group, "exchange", None)
             if xch is not None:
-                ex = xch(bwd.numel(), dev)
-                slot = ex.next_slot()
-                slot.copy_(bwd)
-                bwd = ex.allreduce(slot)
+                bwd = xch(bwd.numel(), dev).allreduce(bwd)
             else:
                 _allreduce(bwd, ctx.group)
             check(lib.dif_simple_bwd_apply(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
@@ -196,7 +210,7 @@ class _SigmoidAttention(torch.autograd.Function):
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
         out = torch.empty((N, H, D), dtype=torch.float32, device=qs.device)
         rowsum = torch.empty((N, H), dtype=torch.float32, device=qs.device)
-        ws = torch.empty(max(int(lib.dif_sigmoid_fwd_workspace_bytes(N, L, H, Hv, M, D)), 16), dtype=torch.uint8, device=qs.device)
+        ws = workspace(qs.device, lib.dif_sigmoid_fwd_workspace_bytes(N, L, H, Hv, M, D))
         with torch.cuda.device(qs.device):
             check(lib.dif_sigmoid_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, L, H, Hv, M, D,
                                       out.data_ptr(), rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream(qs)), "dif_sigmoid_fwd")
@@ -210,7 +224,7 @@ class _SigmoidAttention(torch.autograd.Function):
         g = _f32c(g)
         dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
         wsb = int(lib.dif_sigmoid_bwd_workspace_bytes(N, L, H, Hv, M, D))
-        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=qs.device)
+        ws = workspace(qs.device, wsb)
         with torch.cuda.device(qs.device):
             check(lib.dif_sigmoid_bwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
                                       rowsum.data_ptr(), N, L, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
@@ -364,7 +378,7 @@ class _SegmentedSimple(torch.autograd.Function):
         B = seg_ptr.numel() - 1
         dev = qs.device
         norms = torch.empty(2, dtype=torch.float32, device=dev)
-        ws = torch.empty(max(int(lib.dif_segmented_workspace_bytes(B)), 16), dtype=torch.uint8, device=dev)
+        ws = workspace(dev, lib.dif_segmented_workspace_bytes(B))
         out = torch.empty((N, H, D), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             st = _stream(qs)
@@ -385,7 +399,7 @@ class _SegmentedSimple(torch.autograd.Function):
         B = seg_ptr.numel() - 1
         g = _f32c(g)
         dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
-        ws = torch.empty(max(int(lib.dif_segmented_workspace_bytes(B)), 16), dtype=torch.uint8, device=qs.device)
+        ws = workspace(qs.device, lib.dif_segmented_workspace_bytes(B))
         with torch.cuda.device(qs.device):
             check(lib.dif_segmented_simple_bwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(), seg_ptr.data_ptr(), B,
                                                norms.data_ptr(), N, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),

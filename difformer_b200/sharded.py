@@ -28,19 +28,13 @@ def allreduce_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
     return partials
 
 
-class _DevicePtr:
-    """Wraps a raw device pointer for torch.as_tensor (zero copy) via __cuda_array_interface__."""
-
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 class PartialsExchange:
-    """Peer-mapped buffers + the one-shot NVLink all-reduce kernel (`dif_comm_*`, csrc/comm.cu).
+    """Peer-mapped buffers + the LL-push NVLink all-reduce (`dif_comm_*`, csrc/comm.cu, common.cuh).
 
-    Pass 1 writes its partials straight into a slot of this rank's buffer; `allreduce` launches one
-    small kernel that signals the peers, waits for their flags and sums all ranks' slots in rank
-    order over NVLink (bit-identical result on every rank).  No NCCL call, no host sync."""
+    Every rank pushes each element of its partials straight into its peers' buffers as a 64-bit word {call number |
+    fp32} and polls the words the peers pushed into its own buffer; ranks are added in rank order (bit-identical
+    result on every rank).  No NCCL call, no fences, no host sync.  Either fused into the tail of the pass-1 kernel
+    (`fused_reduce`, tcgen05 shapes) or as a stand-alone kernel (`allreduce`: backward partials, other shapes)."""
 
     def __init__(self, length: int, group, device: torch.device):
         import ctypes
@@ -68,21 +62,50 @@ class PartialsExchange:
         self.ptrs = ptrs
         self.c_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
         self.seq = 0
-        self._slots = [torch.as_tensor(_DevicePtr(self.base + int(lib.dif_comm_slot_offset_bytes(self.len, s)), self.len), device=device)
-                       for s in (0, 1)]
+        self._flag = ctypes.c_int32(0)
+        # per-(shape) buffers of the fused call are cached: the library never allocates and Python should not either
+        self._cache = {}
         dist.barrier(group=group)
 
+    # ---- watchdog ---------------------------------------------------------------------------------------------
+    def failed(self) -> bool:
+        """Non-blocking: True once a kernel of this rank (that has already run) gave up waiting for a peer, or a peer told
+        this rank that it gave up.  Reads a pinned host flag -- no device synchronisation."""
+        self._check(self._lib.dif_comm_status(self.base, ctypes_byref(self._flag)), "dif_comm_status")
+        return bool(self._flag.value)
+
+    def raise_if_failed(self) -> None:
+        if self.failed():
+            raise RuntimeError("difformer_b200: the NVLink exchange of the partials timed out on some rank (a peer died, hung or "
+                               "never launched): every result since then is invalid.  Quiesce all ranks, call "
+                               "PartialsExchange.reset() on each of them (or fall back to the NCCL group) and retry.")
+
+    def timed_out(self) -> bool:
+        """Synchronises the device, then reports `failed()`."""
+        torch.cuda.synchronize(self.device)
+        return self.failed()
+
+    def reset(self) -> None:
+        """Clear the watchdog state.  Collective: every rank must call it, with no exchange in flight."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.dif_comm_reset(self.base), "dif_comm_reset")
+        dist.barrier(group=self.group)
+
+    # ---- collectives --------------------------------------------------------------------------------------------
     def fused_reduce(self, qs, ks, vs):
         """Pass 1 + all-reduce in one kernel (dif_simple_reduce_allreduce).  Returns (partials, prepared) summed
-        over all ranks, or None when the shape is not a tcgen05 shape (caller falls back to next_slot/allreduce)."""
+        over all ranks, or None when the shape is not a tcgen05 shape (caller falls back to `allreduce`)."""
         from . import ops
         N, L, H, Hv, M, D = ops._shapes(qs, ks, vs)
         lib = self._lib
         if ops._SIMPLE_IMPL == ops._lib.DIF_IMPL_GENERIC or int(lib.dif_simple_prepared_bytes(H, Hv, M, D)) == 0:
             return None
+        self.raise_if_failed()
         partials = torch.empty(self.len, dtype=torch.float32, device=self.device)
         prepared = torch.empty(int(lib.dif_simple_prepared_bytes(H, Hv, M, D)), dtype=torch.uint8, device=self.device)
-        ws = torch.empty(max(int(lib.dif_simple_workspace_bytes(N, H, Hv, M, D)), 16), dtype=torch.uint8, device=self.device)
+        ws = ops.workspace(self.device, int(lib.dif_simple_workspace_bytes(N, H, Hv, M, D)))
         self.seq += 1
         with torch.cuda.device(self.device):
             self._check(lib.dif_simple_reduce_allreduce(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D, partials.data_ptr(),
@@ -91,28 +114,22 @@ class PartialsExchange:
                         "dif_simple_reduce_allreduce")
         return partials, prepared
 
-    def timed_out(self) -> bool:
-        """True if a kernel of this rank gave up waiting for a peer (30 s watchdog): results since then are invalid.
-        Synchronises the device."""
-        import ctypes
-        torch.cuda.synchronize(self.device)
-        flag = ctypes.c_int32(0)
-        with torch.cuda.device(self.device):
-            self._check(self._lib.dif_comm_status(self.base, self.len, ctypes.byref(flag)), "dif_comm_status")
-        return bool(flag.value)
-
-    def next_slot(self) -> torch.Tensor:
-        """The data slot of the next call (fp32 [len], lives in the peer-mapped buffer)."""
-        self.seq += 1
-        return self._slots[self.seq & 1]
-
-    def allreduce(self, slot: torch.Tensor) -> torch.Tensor:
-        assert slot.data_ptr() == self._slots[self.seq & 1].data_ptr(), "allreduce must follow next_slot()"
+    def allreduce(self, src: torch.Tensor) -> torch.Tensor:
+        """out = sum over ranks of `src` (fp32 [len], contiguous, this device): one small kernel, LL push over NVLink."""
+        if src.numel() != self.len or src.dtype != torch.float32 or not src.is_contiguous():
+            raise ValueError("allreduce: `src` must be a contiguous float32 tensor of the exchange's length")
+        self.raise_if_failed()
         out = torch.empty(self.len, dtype=torch.float32, device=self.device)
+        self.seq += 1
         with torch.cuda.device(self.device):
-            self._check(self._lib.dif_comm_allreduce(self.c_ptrs, self.rank, self.world, self.len, self.seq, out.data_ptr(),
+            self._check(self._lib.dif_comm_allreduce(self.c_ptrs, self.rank, self.world, self.len, self.seq, src.data_ptr(), out.data_ptr(),
                                                      torch.cuda.current_stream(self.device).cuda_stream), "dif_comm_allreduce")
         return out
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
 
 
 class RowShardComm:
@@ -149,7 +166,7 @@ class RowShardedAttention:
             if fused is not None:
                 return fused[0]
             ex = self.group.exchange(ops.lib.dif_simple_partials_len(qs.shape[1], vs.shape[1], qs.shape[2], vs.shape[2]), qs.device)
-            return ex.allreduce(ops.simple_partials(qs, ks, vs, out=ex.next_slot()))
+            return ex.allreduce(ops.simple_partials(qs, ks, vs))
         return allreduce_partials(ops.simple_partials(qs, ks, vs), self.group)
 
     def apply(self, qs, partials, hv: int, d: int) -> torch.Tensor:

@@ -173,18 +173,26 @@ DIF_API int dif_gcn_spmm(const float* x, const int32_t* rowptr, const int32_t* i
 
 /* ------------------------------------------------------------------------------------------
  * One-shot NVLink all-reduce of the pass-1 partials (the path's only collective).
- * Every rank owns a peer-mappable buffer of dif_comm_buffer_bytes(len): [2 data slots | flags | status].
- *   dif_comm_alloc / _free      : the one place the library allocates (cudaMalloc: IPC-exportable), zero-filled
+ * Every rank owns a peer-mappable buffer of dif_comm_buffer_bytes(len) bytes:
+ *   [header: status word | pinned-host-flag pointer][LL region: u64 [2 slots][16 source ranks][len padded to 64]].
+ * Protocol (LL push): a rank writes every element of its contribution into each peer's region as one 64-bit word
+ * {call number | fp32} and polls the words its peers wrote into its own region -- data and flag travel together, one
+ * NVLink traversal, no fences.  Ranks are added in rank order (bit-identical on every rank).
+ *   dif_comm_alloc / _free      : the one place the library allocates (cudaMalloc: IPC-exportable, zero-filled; plus a
+ *                                 64-byte pinned host flag for the watchdog)
  *   dif_comm_export / _open     : cudaIpc handle (64 bytes) out / peer pointer in (same node, NVLink peers)
- *   dif_comm_allreduce          : call number `seq` (1,2,3,... identical on all ranks): pass 1 must have written
- *                                 this rank's partials at offset dif_comm_slot_offset_bytes(len, seq) of its own
- *                                 buffer; `out` (local) receives the sum over ranks, summed in rank order
- *                                 (bit-identical on every rank).  bufs[r] = pointer to rank r's buffer as mapped
- *                                 in this process (HOST array of `world` device pointers, world <= 16).
+ *   dif_comm_allreduce          : call number `seq` (1,2,3,... identical on all ranks): out[i] = sum over ranks of
+ *                                 src[i], i < len (src, out: local device memory).  bufs[r] = pointer to rank r's
+ *                                 buffer as mapped in this process (HOST array of `world` device pointers, world <= 16).
+ *   dif_comm_status             : *timed_out = 1 once a kernel of this rank gave up waiting (30 s) for a peer, or was
+ *                                 told by a peer that IT gave up: results since then are meaningless on every rank.
+ *                                 Reads a pinned host flag: no device synchronisation (a timeout of a kernel that is
+ *                                 still running shows up later).  dif_comm_reset clears it (device sync; all ranks
+ *                                 must have quiesced and must reset before the next call).
  * ------------------------------------------------------------------------------------------ */
 /* Pass 1 with the all-reduce fused into its tail (one kernel: compute + collective over peer memory): every
- * CTA exchanges "its" column slice of the partials with the peers (flags + direct NVLink loads) right after
- * the local cross-CTA sum.  Result: `partials` (and `prepared`) already hold the sum over all ranks.
+ * CTA exchanges "its" column slice of the partials with the peers (LL push, above) right after the local
+ * cross-CTA sum.  Result: `partials` (and `prepared`) already hold the sum over all ranks.
  * tcgen05 shapes only (DIF_EUNSUPPORTED otherwise: use dif_simple_reduce + dif_comm_allreduce).  `seq` as in
  * dif_comm_allreduce; the two entry points may share buffers as long as seq keeps increasing. */
 DIF_API int dif_simple_reduce_allreduce(const float* q, const float* k, const float* v,
@@ -192,17 +200,15 @@ DIF_API int dif_simple_reduce_allreduce(const float* q, const float* k, const fl
                       float* partials, void* prepared, void* workspace, int64_t workspace_bytes,
                       void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream);
 DIF_API int64_t dif_comm_buffer_bytes(int64_t len);
-DIF_API int64_t dif_comm_slot_offset_bytes(int64_t len, unsigned long long seq);
 DIF_API int dif_comm_alloc(void** ptr, int64_t bytes);
 DIF_API int dif_comm_free(void* ptr);
 DIF_API int dif_comm_export(void* ptr, void* handle64);
 DIF_API int dif_comm_open(const void* handle64, void** peer_ptr);
 DIF_API int dif_comm_close(void* peer_ptr);
-/* watchdog: *timed_out = 1 if a kernel of this rank gave up waiting (30 s) for a peer's flag since the buffer was
- * allocated -- its result is then meaningless.  Synchronous (one 8-byte cudaMemcpy): call it after a stream sync. */
-DIF_API int dif_comm_status(const void* own_buf, int64_t len, int* timed_out);
+DIF_API int dif_comm_status(const void* own_buf, int* timed_out);
+DIF_API int dif_comm_reset(void* own_buf);
 DIF_API int dif_comm_allreduce(void* const* bufs, int rank, int world, int64_t len, unsigned long long seq,
-                               float* out, void* stream);
+                               const float* src, float* out, void* stream);
 
 /* mean over heads: x[N,Hx,D] -> out[N,D] */
 DIF_API int dif_head_mean(const float* x, int64_t N, int Hx, int D, float* out, void* stream);

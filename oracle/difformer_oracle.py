@@ -365,7 +365,9 @@ def synthetic_graph(n: int, n_pairs: int, seed: int = 123, self_loops: bool = Tr
 
 
 def rel_err(x: Tensor, ref: Tensor) -> float:
-    """Norm-wise relative error ||x-ref||/||ref|| evaluated in fp64."""
-    x, ref = x.detach().double().cpu(), ref.detach().double().cpu()
+    """Norm-wise relative error ||x-ref||/||ref|| evaluated in fp64 (on the GPU when either side lives there: the
+    full-size bench checks compare multi-GB tensors)."""
+    dev = x.device if x.is_cuda else ref.device
+    x, ref = x.detach().to(dev, torch.float64), ref.detach().to(dev, torch.float64)
     den = float(torch.linalg.vector_norm(ref))
     return float(torch.linalg.vector_norm(x - ref)) / (den if den > 0 else 1.0)

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference modules from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference modules from /root/reference, or, where that does not
+exist (the GPU box), from the byte-for-byte copies `oracle/build_ref.py` placed under oracle/_ref/ (git-ignored).
 
 The reference hot path (`node classification/difformer.py:6-7`,
 `physical particle/difformer-v2.py:5-6`) imports two third-party packages that are not
@@ -10,10 +11,11 @@ installable in this image (no wheel, no network):
     occurrence count as float
 
 This file injects minimal stand-ins for exactly those three names (documented semantics of the
-pinned versions) so the reference files import *unmodified*.  It only works where
-/root/reference exists (the build container); nothing on the GPU box may import it.  It is
-used by `oracle/make_golden.py` (fixture generation) and by CPU tests that pin the restatement
-in `oracle/difformer_oracle.py` against the real reference.
+pinned versions) so the reference files import *unmodified*.  It is used by
+`oracle/make_golden.py` (fixture generation), by CPU tests that pin the restatement in
+`oracle/difformer_oracle.py` against the real reference, and by `bench.py`'s CPU-baseline leg
+(the reference's own `full_attention_conv` timed on the host cores).  The product path never
+imports it.
 """
 import importlib.util
 import os
@@ -22,7 +24,18 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("DIFFORMER_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("DIFFORMER_REFERENCE_ROOT")
+    for root in ([env] if env else []) + ["/root/reference", _VENDORED]:
+        if os.path.isfile(os.path.join(root, "node classification", "difformer.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

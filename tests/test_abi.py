@@ -57,11 +57,10 @@ def test_pure_host_queries():
     for impl in (_lib.DIF_IMPL_GENERIC, _lib.DIF_IMPL_TCGEN05, _lib.DIF_IMPL_AUTO):
         assert lib.dif_sigmoid_set_impl(impl) == 0
     assert lib.dif_sigmoid_set_impl(7) == -1 and b"unknown impl" in lib.dif_last_error()
-    # exchange buffer = [2 data slots (64-float aligned) | flags [2][16][256] u64 | status word]
+    # exchange buffer = [128-byte header | LL words u64 [2 slots][16 source ranks][len padded to 64]]
     n = 16898
     slot = (n + 63) // 64 * 64
-    assert lib.dif_comm_buffer_bytes(n) == 2 * slot * 4 + 2 * 16 * 256 * 8 + 64
-    assert lib.dif_comm_slot_offset_bytes(n, 1) == slot * 4 and lib.dif_comm_slot_offset_bytes(n, 2) == 0
+    assert lib.dif_comm_buffer_bytes(n) == 128 + 2 * 16 * slot * 8
     # pass-1 workspace: one record per CTA + ready flags + the generation word
     assert lib.dif_simple_workspace_bytes(132534, 4, 4, 64, 64) >= 148 * 16898 * 4 + 149 * 8
 

@@ -1,4 +1,8 @@
-"""GPU, >= 2 devices: row-sharded 'simple' over NCCL == unsharded result (skipped on 1-GPU boxes)."""
+"""GPU, >= 2 devices: the row-sharded 'simple' path == the unsharded fp64 oracle, on 2 / 4 / 8 ranks (each world size is
+skipped when the box has fewer GPUs).  Covers, at HEAD: the all-reduce fused into the pass-1 kernel tail
+(`dif_simple_reduce_allreduce`, LL push over NVLink), the stand-alone `dif_comm_allreduce` (backward partials, generic
+shapes), the NCCL baseline, row counts that do not divide by the world size, repeated calls (slot alternation), the
+reduced partials themselves, and the watchdog."""
 import os
 import socket
 import subprocess
@@ -13,56 +17,97 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["DIF_ROOT"])
-from difformer_b200.sharded import RowShardedAttention, shard_rows
+from difformer_b200.sharded import RowShardedAttention, RowShardComm, shard_rows
 from difformer_b200 import ops
 from oracle import difformer_oracle as O
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
-dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-n, h, d = 20011, 4, 64
-q, k, v = O.synthetic_qkv(n, h, d, seed=11, adversarial=True)
-b, e = shard_rows(n, rank, world)
-want = O.simple_attention(q.double(), k.double(), v.double())
-g = torch.randn(n, h, d, generator=torch.Generator().manual_seed(5))
-dq, dk, dv = O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())
-outs = {}
-for nvlink in (False, True):          # NCCL all-reduce, then the one-shot NVLink kernel over peer-mapped memory
-    attn = RowShardedAttention(n, dist.group.WORLD, nvlink=nvlink)
-    for rep in range(3):              # several calls: exercises the alternating slots / sequence numbers
-        qs, ks, vs = (t[b:e].cuda().requires_grad_(True) for t in (q, k, v))
-        out = attn(qs, ks, vs)
-        out.backward(g[b:e].cuda())
-        errs = [O.rel_err(out, want[b:e]), O.rel_err(qs.grad, dq[b:e]), O.rel_err(ks.grad, dk[b:e]), O.rel_err(vs.grad, dv[b:e])]
-        assert max(errs) < 1e-3, (nvlink, rep, errs)
-    outs[nvlink] = out.detach()
-assert O.rel_err(outs[True], outs[False]) < 1e-5
-# watchdog: rank 0 launches an exchange its peer never joins -> the kernel gives up after 30 s instead of hanging the
-# GPU, and the status word says so
-from difformer_b200.sharded import PartialsExchange
-ex = PartialsExchange(1024, dist.group.WORLD, torch.device("cuda", rank))
-assert not ex.timed_out()
-slot = ex.next_slot()
-slot.fill_(float(rank + 1))
-if rank == 0:
-    ex.allreduce(slot)
-    assert ex.timed_out()
-else:
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+worst = 0.0
+# (n, h, hv, d): tcgen05 shapes (fused exchange) and shapes on the generic path (stand-alone exchange); n never divides
+for (n, h, hv, d) in ((20011, 4, 4, 64), (4999, 1, 1, 64), (3001, 3, 3, 32), (2503, 2, 1, 64)):
+    q, k, v = O.synthetic_qkv(n, h, d, seed=11 + n, adversarial=True)
+    if hv != h:
+        v = v[:, :1].contiguous()
+    b, e = shard_rows(n, rank, world)
+    want = O.simple_attention(q.double(), k.double(), v.double())
+    wp = O.simple_partials(q.double(), k.double(), v.double())
+    g = torch.randn(n, h, d, generator=torch.Generator().manual_seed(5))
+    dq, dk, dv = O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())
+    outs = {}
+    for nvlink in (False, True):          # NCCL all-reduce, then the LL-push exchange over peer-mapped memory
+        attn = RowShardedAttention(n, dist.group.WORLD, nvlink=nvlink)
+        for rep in range(3):              # several calls: exercises the alternating slots / call numbers
+            qs, ks, vs = (t[b:e].to(dev).requires_grad_(True) for t in (q, k, v))
+            out = attn(qs, ks, vs)
+            out.backward(g[b:e].to(dev))
+            errs = [O.rel_err(out, want[b:e]), O.rel_err(qs.grad, dq[b:e]), O.rel_err(ks.grad, dk[b:e]), O.rel_err(vs.grad, dv[b:e])]
+            assert max(errs) < 1e-3, (n, h, hv, d, nvlink, rep, errs)
+            worst = max(worst, max(errs))
+        outs[nvlink] = out.detach()
+        # the reduced partials themselves (S, z, u, sum q^2, sum k^2) against the oracle of the GLOBAL problem
+        flat = attn.reduce(qs.detach(), ks.detach(), vs.detach()).double().cpu()
+        nS, nz = h * d * d, h * d
+        perr = [O.rel_err(flat[:nS].reshape(h, d, d), wp["S"]), O.rel_err(flat[nS:nS + nz].reshape(h, d), wp["z"]),
+                O.rel_err(flat[nS + nz:nS + nz + hv * d].reshape(hv, d), wp["u"]),
+                abs(float(flat[-2]) - float(wp["sq"])) / float(wp["sq"]), abs(float(flat[-1]) - float(wp["sk"])) / float(wp["sk"])]
+        assert max(perr) < 1e-4, (n, h, hv, d, nvlink, perr)
+        if nvlink:
+            # bit-identical on every rank (fixed rank order of the sum)
+            mine = attn.reduce(qs.detach(), ks.detach(), vs.detach())
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(mine, ref), "reduced partials differ between ranks"
+            assert not attn.group.exchange(flat.numel(), dev).timed_out()
+    assert O.rel_err(outs[True], outs[False]) < 1e-5
+dist.barrier()
+if world == 2 and os.environ.get("DIF_TEST_WATCHDOG", "1") == "1":
+    # watchdog: rank 0 launches an exchange its peer never joins -> the kernel gives up (DIF_COMM_TIMEOUT_MS) instead of
+    # hanging the GPU, raises its host flag AND marks the peer's status word: the peer learns at its next call
+    from difformer_b200.sharded import PartialsExchange
+    ex = PartialsExchange(1024, dist.group.WORLD, dev)
     assert not ex.timed_out()
+    src = torch.full((1024,), float(rank + 1), device=dev)
+    if rank == 0:
+        ex.allreduce(src)
+        assert ex.timed_out()
+        try:
+            ex.allreduce(src)
+            raise SystemExit("expected the failed exchange to raise")
+        except RuntimeError:
+            pass
+    dist.barrier()
+    if rank == 1:
+        ex.allreduce(src)                 # sees rank 0's mark in its status word and raises its own host flag
+        assert ex.timed_out()
+    ex.reset()
+    assert not ex.failed()
+    ex.seq = 10                           # both ranks restart from the same call number
+    got = ex.allreduce(src)
+    assert torch.allclose(got, torch.full_like(got, 3.0)) and not ex.timed_out()
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok", errs)
+print("rank", rank, "ok", worst)
 """
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_row_sharded_nccl_matches_unsharded(tmp_path):
+def _run(world, tmp_path, extra_env=None):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    env = dict(os.environ, DIF_ROOT=ROOT)
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", str(port), str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-    assert res.returncode == 0, res.stdout[-3000:]
-    assert res.stdout.count(" ok ") == 2
+    env = dict(os.environ, DIF_ROOT=ROOT, DIF_COMM_TIMEOUT_MS="1500")
+    env.update(extra_env or {})
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-4000:]
+    assert res.stdout.count(" ok ") == world
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_row_sharded_matches_unsharded(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    _run(world, tmp_path)

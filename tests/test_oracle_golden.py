@@ -2,6 +2,8 @@
 made by oracle/make_golden.py from the unmodified reference) and, when /root/reference is
 present, against the live reference.  Tolerances: 1e-5 rel in fp32 (pure reassociation noise),
 2e-6 when the oracle runs in fp64 on the fp32 inputs."""
+import os
+
 import pytest
 import torch
 
@@ -123,3 +125,23 @@ def test_oracle_against_live_reference_random_shapes():
     q, k, v = O.synthetic_qkv(39, 1, 16, seed=4)
     assert O.rel_err(O.segmented_simple_attention(q, k, v, nn_),
                      ref2.TransConv(16, 16).full_attention(q, k, v, "simple", nn_)) < 1e-5
+
+
+@pytest.mark.skipif(not reference_available(), reason="no reference tree (neither /root/reference nor oracle/_ref)")
+def test_timing_port_is_bit_equal_to_the_reference_function():
+    """`bench.py`'s CPU baseline times the real `full_attention_conv` when oracle/_ref exists and this port of it otherwise:
+    the port must compute exactly the reference's values (same op chain, fp32)."""
+    ref = load_reference_v1()
+    for n, h, d in [(300, 4, 64), (129, 1, 32)]:
+        q, k, v = O.synthetic_qkv(n, h, d, seed=n)
+        assert torch.equal(O.simple_attention_reference_chain(q, k, v), ref.full_attention_conv(q, k, v, "simple"))
+
+
+def test_vendored_reference_is_a_byte_copy():
+    """oracle/_ref (git-ignored build output of oracle/build_ref.py) must be the unmodified files."""
+    import filecmp
+    from oracle import build_ref as B
+    if not os.path.isfile(os.path.join(B.SRC, B.FILES[0])) or not os.path.isdir(B.DST):
+        pytest.skip("needs both /root/reference and oracle/_ref")
+    for rel in B.FILES:
+        assert filecmp.cmp(os.path.join(B.SRC, rel), os.path.join(B.DST, rel), shallow=False)
