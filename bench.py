@@ -228,7 +228,14 @@ class Problem:
             prepared = None       # the pass-2 operand image only matches the un-reduced partials
         return partials, prepared
 
+    one_kernel = True      # dif_simple_forward: pass 1 + (all-)reduce + pass 2 in one cooperative launch (--path twopass: off)
+
     def step(self):
+        if self.one_kernel and (self.group is None or self.comm is not None):
+            ex = self.comm.exchange(self.plen, self.dev) if self.comm is not None else None
+            res = self.ops.simple_forward(self.q, self.k, self.v, self.n_total, ex)
+            if res is not None:
+                return res[0]
         partials, prepared = self.reduce()
         return self.ops.simple_apply(self.q, partials, self.n_total, HEADS, DIM, prepared=prepared)
 
@@ -311,6 +318,8 @@ def run_ours(args):
     if args.simple_impl:
         ops.set_simple_impl(args.simple_impl)
 
+    Problem.one_kernel = args.path == "fused"
+    ops.set_fused_forward(args.path == "fused")
     comm, collective = None, args.collective if world > 1 else None
     if group is not None and args.collective == "nvlink":
         from difformer_b200.sharded import RowShardComm
@@ -446,13 +455,17 @@ def run_ours(args):
                  "roofline_frac": 4 * N_CFG_B * HEADS * DIM * 4 / (ms_b * 1e-3) / 1e9 / (measured_peaks()[0] * world), "parity": par_b}
         del pb
 
+    launches_per_step = 3 if args.simple_impl == "generic" else (1 if (args.path == "fused" and (world == 1 or collective == "nvlink")) else 2)
+    if world > 1 and collective == "nccl":
+        launches_per_step += 1
     if rank == 0:
         peak, _, peak_src = measured_peaks()
         alg_bytes = 4 * T                      # read Q,K,V once + write out once
         achieved = alg_bytes / (ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "simple op = pass 1 (reduce, cross-CTA [+cross-GPU] sum fused) + pass 2 (apply): one launch sequence per step",
+                "kernel": ("simple_fused_kernel: pass 1 + grid-wide [+ cross-GPU] sum + pass 2 in ONE cooperative launch per step" if launches_per_step == 1 else
+                           "simple op = pass 1 (reduce, cross-CTA [+cross-GPU] sum fused) + pass 2 (apply): one launch sequence per step"),
                 "algorithmic_bytes_per_step": alg_bytes}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
@@ -494,7 +507,7 @@ def run_ours(args):
                      f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
                      ("fused into the pass-1 kernel tail, LL push over peer-mapped NVLink memory (no NCCL call)" if collective == "nvlink" else "NCCL")),
                  "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps (roofline.cold: flushed)",
-                 "simple_impl": args.simple_impl or "auto"}
+                 "simple_impl": args.simple_impl or "auto", "path": args.path}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg, "notes": notes,
@@ -502,8 +515,7 @@ def run_ours(args):
                 "e2e": {"value": N_NODES * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": 3 * T, "d2h_bytes_per_step": T, "steps": e2e_steps, "result_rel_err_vs_device_run": e2e_out_err,
                         "api": "difformer.full_attention_conv(q, k, v, 'simple') on pinned host tensors; double-buffered (upload of step i+1 overlaps download of step i-1)"},
-                # tcgen05 path: reduce (cross-CTA sum fused in) + apply; generic path: reduce + finalize + apply
-                "gpu_launches": (3 if args.simple_impl == "generic" else 2) * args.steps,
+                "gpu_launches": launches_per_step * args.steps,
                 "clocks": sampler.summary(), "parity": parity, "cfg_b": cfg_b}
         print(json.dumps(line), flush=True)
     ok = parity["ok"] and (cfg_b is None or cfg_b["parity"]["ok"])
@@ -634,6 +646,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="simple", choices=["simple", "sigmoid_cora", "layer", "segmented", "fwdbwd"])
     ap.add_argument("--simple-impl", default=None, choices=[None, "auto", "generic", "tcgen05"])
+    ap.add_argument("--path", default="fused", choices=["fused", "twopass"], help="'simple' forward: one cooperative kernel, or pass 1 / pass 2 as two launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg-b", action="store_true", help="skip the BASELINE configs[3] (N=1.6M strong-scaling) leg")
     ap.add_argument("--collective", default="nvlink", choices=["nvlink", "nccl"], help="multi-GPU all-reduce of the partials")

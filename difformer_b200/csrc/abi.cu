@@ -88,6 +88,24 @@ extern "C" int dif_simple_reduce_allreduce(const float* q, const float* k, const
                             peer_bufs, rank, world, seq);
 }
 
+// The whole forward in ONE cooperative kernel (tcgen05 shapes): pass 1 -> grid-wide (and, with peer buffers, cross-GPU) sum
+// -> pass 2.  `partials` receives the reduced partials (saved for the backward).
+extern "C" int64_t dif_simple_forward_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
+    if (N < 1 || H < 1 || M < 1 || D < 1) return -1;
+    return simple_fused_workspace_bytes(N, H, Hv, M, D);
+}
+
+extern "C" int dif_simple_forward(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
+                                  float* partials, float* out, void* workspace, int64_t workspace_bytes,
+                                  void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream) {
+    DIF_REQUIRE(q && k && v && partials && out && workspace, DIF_EARG, "simple_forward: null pointer");
+    DIF_REQUIRE(n_total > 0, DIF_EARG, "simple_forward: n_total must be positive");
+    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED,
+                "simple_forward: the one-kernel forward needs the tcgen05 shapes (M == D == 64, Hv == H, H in {1, 2, 4}); use dif_simple_reduce + dif_simple_apply");
+    return simple_forward_tc(q, k, v, N, H, Hv, M, D, n_total, partials, out, workspace, workspace_bytes, (cudaStream_t)stream,
+                             peer_bufs, rank, world, seq);
+}
+
 extern "C" int dif_simple_apply(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                                 float* out, const dif_epilogue_t* epilogue, int impl, void* stream) {
     DIF_REQUIRE(q && partials && out, DIF_EARG, "simple_apply: null pointer");

@@ -173,6 +173,11 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st);
 
+int64_t simple_fused_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
+int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
+                      float* partials, float* out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                      void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0);
+
 int64_t simple_tc_rowscal_floats(int64_t N, int H);
 int simple_bwd_reduce_tc(const float* q, const float* g, const float* out, const float* partials, double n_total,
                          int64_t N, int H, float* bwd_partials, float* rowscal, void* ws, int64_t ws_bytes, cudaStream_t st);

@@ -996,6 +996,485 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
     if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// forward in ONE kernel: pass 1 -> grid-wide (and cross-GPU) sum -> pass 2, one cooperative persistent launch.
+//
+// Same pipelines as reduce_tma_kernel + apply_tc_kernel<0>, glued by the fused tail that already is a grid barrier:
+//   * no second launch, prologue, TMEM allocation or kernel-boundary drain between the passes;
+//   * the Q producers of pass 2 start streaming as soon as their converter role of pass 1 ends, i.e. WHILE the epilogue
+//     warps run the record / slice-sum / exchange tail (HBM is otherwise idle there): three shared-memory stages + two
+//     register stages of Q are in flight before the first pass-2 MMA can issue;
+//   * a CTA applies pass 2 to the rows it streamed in pass 1, last tile first: the Q rows it read most recently (L2
+//     evict_last) are consumed while they are still resident.
+// Warps: 0-7 converters -> Q producers; 8-11 TMA issuer (warp 8) + tail -> epilogue; 12 MMA issuer of both passes.
+// Shared memory: the two passes alias one dynamic allocation ([stg | ops] vs [Bop | Q stages | out staging | u]); the
+// slice-sum buffer of the tail lies over Bop (loaded afterwards), so the Q stages are free for the prefetch.
+// ------------------------------------------------------------------------------------------
+struct FusedArgs {
+    ReduceArgs1 r;            // pass 1 (+ tail, exchange) arguments; r.prepared = global scratch for the B-operand image (required)
+    float* out;
+    int store_hint, reverse;
+    unsigned long long* flags2;   // [grid] second grid barrier (B image complete)
+};
+template <int H>
+constexpr int smem_fused_bytes() { return (Geo<H>::kSmem1 > smem2_bytes<H>() ? Geo<H>::kSmem1 : smem2_bytes<H>()); }
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+template <int H>
+__global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __grid_constant__ FusedArgs fa, const __grid_constant__ CUtensorMap out_map) {
+    using G = Geo<H>;
+    const ReduceArgs1& a = fa.r;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // pass 1 view
+    uint8_t* stg = base;
+    uint8_t* ops = stg + G::kNSG * G::kStg;
+    // pass 2 view
+    uint8_t* Bop = base;                                             // [h][hi|lo][80 rows][128 B]
+    uint8_t* stages = base + G::kBBytes;
+    uint8_t* ostage = stages + kNS2 * kStage2;                       // [4 warps][2 boxes][32 rows][128 B], 1024-aligned
+    float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
+    static_assert(kSlices * 4 * ((((G::kP + 7) / 8 * 8 + kSlices - 1) / kSlices + 3) / 4 * 4) <= G::kBBytes, "the slice buffer of the tail must stay below the Q stages");
+    __shared__ uint64_t sfull[G::kNSG], sempty[G::kNSG], ofull[G::kNO], oempty[G::kNO], done, tail_bar;
+    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], bbar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part[16];
+    __shared__ float red[H == 1 ? 64 * 65 : 2048];                  // z / u partial sums of the converters (H == 1: + block-1 half of S)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    const int64_t r1 = min(a.N, r0 + (int64_t)a.rows_per_cta);
+    const int iters = r1 > r0 ? (int)((r1 - r0 + G::kNodes - 1) / G::kNodes) : 0;
+    const int my_tiles = r1 > r0 ? (int)((r1 - r0 + kTile2 - 1) / kTile2) : 0;
+    const int nsc = my_tiles * H;                       // (tile, head) stages of pass 2
+    auto row0_of = [&](int sc) -> int64_t { const int t = sc / H; return r0 + (int64_t)(fa.reverse ? my_tiles - 1 - t : t) * kTile2; };
+    uint64_t* dbg = a.dbg;
+    DIF_STAMP(dbg, 0);
+
+    if (tid == 0) {
+        for (int s = 0; s < G::kNSG; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); }
+        for (int s = 0; s < G::kNO; ++s) { mbar_init(&ofull[s], 8); mbar_init(&oempty[s], 1); }
+        mbar_init(&done, 1);
+        mbar_init(&tail_bar, 1);
+        for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(&bbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    DIF_STAMP(dbg, 1);
+
+    if (warp < 8) {
+        // =================== pass 1: converters (see reduce_tma_kernel) ===================
+        float zacc[4] = {0.f, 0.f, 0.f, 0.f}, uacc[4] = {0.f, 0.f, 0.f, 0.f};
+        float ssk = 0.f, ssq = 0.f;
+        {
+            const uint32_t stg_base = smem_u32(stg), ops_base = smem_u32(ops);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % G::kNSG, o = it % G::kNO;
+                const int nrows = (int)min((int64_t)G::kNodes, r1 - (r0 + (int64_t)it * G::kNodes));
+                mbar_wait(&sfull[s], (it / G::kNSG) & 1);
+                float4 x[G::kChunksPerThread][3];
+#pragma unroll
+                for (int i = 0; i < G::kChunksPerThread; ++i) {
+                    const int u = tid + 256 * i, node = u / G::kChunksPerRow;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        x[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (node < nrows) x[i][t] = lds128(stg_base + s * G::kStg + t * G::kStgT + u * 16);
+                    }
+                }
+                if (it >= G::kNO) mbar_wait(&oempty[o], ((it / G::kNO) - 1) & 1);
+                const uint32_t ob = ops_base + o * G::kOpStage;
+#pragma unroll
+                for (int i = 0; i < G::kChunksPerThread; ++i) {
+                    const int u = tid + 256 * i, node = u / G::kChunksPerRow, cc = u % G::kChunksPerRow;
+                    const int head = cc >> 4, m = (cc & 15) * 4;
+                    const int blk = (H == 1) ? (node >> 4) : head;
+                    const int kn = (H == 1) ? (node & 15) : node;
+                    const uint32_t off = (uint32_t)(blk * G::kBlockTile + (kn >> 3) * 1024 + (kn & 7) * 128 +
+                                                    ((((m >> 3) ^ kn) & 7) << 4) + ((m >> 2) & 1) * 8);
+                    uint32_t hi[2], lo[2];
+                    split4(x[i][0], hi, lo);
+                    sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
+                    sts64(ob + 1 * G::kOp + off, lo[0], lo[1]);
+                    split4(x[i][1], hi, lo);
+                    sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
+                    sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
+                    const float4 kk = x[i][0], vv = x[i][1], qq = x[i][2];
+                    zacc[0] += kk.x; zacc[1] += kk.y; zacc[2] += kk.z; zacc[3] += kk.w;
+                    uacc[0] += vv.x; uacc[1] += vv.y; uacc[2] += vv.z; uacc[3] += vv.w;
+                    ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
+                    ssq = fmaf(qq.x, qq.x, ssq); ssq = fmaf(qq.y, qq.y, ssq); ssq = fmaf(qq.z, qq.z, ssq); ssq = fmaf(qq.w, qq.w, ssq);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&ofull[o]); mbar_arrive(&sempty[s]); }
+            }
+        }
+        // hand the column sums to the tail warps (static shared memory: nothing of pass 2 aliases it)
+        ssk = warp_sum(ssk);
+        ssq = warp_sum(ssq);
+        if (lane == 0) { part[warp] = ssk; part[8 + warp] = ssq; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { red[tid * 4 + i] = zacc[i]; red[1024 + tid * 4 + i] = uacc[i]; }
+        __threadfence_block();
+        bar_arrive_named(1, 384);                      // barrier A: 256 arrivals here + the 128 tail threads' sync
+        // pass 1 still reads the staging / operand rings of the LAST stages (TMA landed, MMAs pending): the Q stages of
+        // pass 2 alias them, so the prefetch into shared memory waits for `done` (all MMAs complete); the register
+        // stages are loaded right away
+        // =================== pass 2: Q producers (see apply_tc_kernel) ===================
+        float buf[2][4][8];
+        auto issue = [&](int sc, int j, float (&dst)[8]) {
+            if (sc >= nsc) return;
+            const int t = tid + 256 * j;
+            const int64_t row = row0_of(sc) + (t >> 3);
+            if (row < r1) {
+                ldg256_stream(a.q + row * G::kRowF + (sc % H) * kDim + (t & 7) * 8, dst);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = 0.f;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(0, j, buf[0][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
+        mbar_wait(&done, 0);
+        DIF_STAMP(dbg, 3);
+        const uint32_t stage_base = smem_u32(stages);
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int s = sc % kNS2;
+            if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+            const uint32_t sb = stage_base + s * kStage2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                uint4 hi, lo;
+                split8(buf[0][j], hi, lo);
+                const uint32_t off = sw128(t >> 3, t & 7);
+                sts128(sb + off, hi);
+                sts128(sb + kQOp + off, lo);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
+                issue(sc + 2, j, buf[1][j]);
+            }
+        }
+    } else if (warp < 12) {
+        const int te = tid - 256, ew = warp - 8;        // 128 tail / epilogue threads
+        if (warp == 8 && lane == 0) {
+            // =================== pass 1: TMA issuer ===================
+            const uint32_t stg_base = smem_u32(stg);
+            const uint64_t pol_first = policy_evict_first_(), pol_last = policy_evict_last();
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % G::kNSG;
+                if (it >= G::kNSG) mbar_wait(&sempty[s], ((it / G::kNSG) - 1) & 1);
+                const int64_t row = r0 + (int64_t)it * G::kNodes;
+                const uint32_t bytes = (uint32_t)(min((int64_t)G::kNodes, r1 - row) * G::kRowB);
+                mbar_expect_tx(&sfull[s], 3 * bytes);
+                if (a.l2_hints) {
+                    tma_load_1d_hint(stg_base + s * G::kStg + 0 * G::kStgT, a.k + row * G::kRowF, bytes, &sfull[s], pol_first);
+                    tma_load_1d_hint(stg_base + s * G::kStg + 1 * G::kStgT, a.v + row * G::kRowF, bytes, &sfull[s], pol_first);
+                    tma_load_1d_hint(stg_base + s * G::kStg + 2 * G::kStgT, a.q + row * G::kRowF, bytes, &sfull[s], pol_last);
+                } else {
+                    tma_load_1d(stg_base + s * G::kStg + 0 * G::kStgT, a.k + row * G::kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * G::kStg + 1 * G::kStgT, a.v + row * G::kRowF, bytes, &sfull[s]);
+                    tma_load_1d(stg_base + s * G::kStg + 2 * G::kStgT, a.q + row * G::kRowF, bytes, &sfull[s]);
+                }
+            }
+        }
+        __syncwarp();
+        // =================== tail (see reduce_tma_kernel): record, grid-wide slice sum (+ cross-GPU LL exchange) ===================
+        mbar_wait(&done, 0);
+        tc_fence_after();
+        bar_sync_named(1, 384);                          // barrier A: the converters' column sums are in `red` / `part`
+        if (dbg != nullptr && te == 0) dbg[blockIdx.x * 8 + 4] = gtime();
+        float* rec = a.ws + (int64_t)blockIdx.x * a.ws_len;
+        for (int col = te; col < G::kRowF; col += 128) {
+            float z = 0.f, u = 0.f;
+            for (int t = col >> 2; t < 256; t += G::kChunksPerRow) { z += red[t * 4 + (col & 3)]; u += red[1024 + t * 4 + (col & 3)]; }
+            rec[G::offZ + col] = z;
+            rec[G::offU + col] = u;
+        }
+        if (te == 0) {
+            float sk = 0.f, sq = 0.f;
+            for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
+            rec[G::offSq] = sq;
+            rec[G::offSq + 1] = sk;
+            for (int64_t i = G::kP; i < a.ws_len; ++i) rec[i] = 0.f;
+        }
+        if (H == 1) bar_sync_named(2, 128);              // `red` is re-used below
+#pragma unroll 1
+        for (int p = 0; p < G::kPairs; ++p) {
+            const int wq = ew, hp = wq >> 1, m = (wq * 32 + lane) & 63;
+            uint32_t r[2][32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (iters > 0) {
+                    tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + p * 128 + hp * 64 + c * 32, r[c]);
+                    tmem_ld_wait32(r[c]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[c][j] = 0u;
+                }
+            }
+            if (H == 1) {
+                if (hp == 1) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) red[m * 65 + c * 32 + j] = __uint_as_float(r[c][j]);
+                }
+                bar_sync_named(2, 128);
+                if (hp == 0) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[c][j] = __float_as_uint(__uint_as_float(r[c][j]) + red[m * 65 + c * 32 + j]);
+                }
+            }
+            if (H != 1 || hp == 0) {
+                const int blk = (H == 1) ? 0 : 2 * p + hp;
+                float* dst = rec + ((int64_t)blk * kDim + m) * kDim;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                     :: "l"(dst + c * 32 + j), "r"(r[c][j]), "r"(r[c][j + 1]), "r"(r[c][j + 2]), "r"(r[c][j + 3]),
+                                        "r"(r[c][j + 4]), "r"(r[c][j + 5]), "r"(r[c][j + 6]), "r"(r[c][j + 7]) : "memory");
+            }
+        }
+        tc_fence_before();
+        __threadfence();
+        bar_sync_named(2, 128);
+        if (dbg != nullptr && te == 0) dbg[blockIdx.x * 8 + 5] = gtime();
+        const int grid = gridDim.x;
+        const unsigned long long gen = *reinterpret_cast<volatile unsigned long long*>(a.flags + grid);
+        const unsigned long long epoch = a.epoch + gen * 0x9E3779B97F4A7C15ull;
+        if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(epoch) : "memory");
+        const int chunk = (int)((((a.ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
+        float* sbuf = reinterpret_cast<float*>(stg);    // [grid][chunk] fp32 over the (not yet loaded) B operands
+        const ShardArgs& sh = a.sh;
+        const bool sharded = sh.world > 1;
+        const int xslot = (int)(sh.seq & 1);
+        if (sharded && blockIdx.x == 0 && te == 0) comm_check_status(sh);
+        bool waited = false;
+        uint32_t tail_phase = 0;
+        for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
+            const int64_t j0 = (int64_t)sl * chunk;
+            const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
+            if (slice <= 0) break;
+            if (!waited) {
+                for (int r = te; r < grid; r += 128) {
+                    unsigned long long f;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
+                        if (f != epoch) __nanosleep(32);
+                    } while (f != epoch);
+                }
+                if (blockIdx.x == 0) {
+                    bar_sync_named(2, 128);
+                    if (te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + grid) = gen + 1;
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");
+                waited = true;
+            }
+            bar_sync_named(2, 128);
+            if (te == 0) mbar_expect_tx(&tail_bar, (uint32_t)grid * (uint32_t)slice * 4u);
+            bar_sync_named(2, 128);
+            for (int r = te; r < grid; r += 128)
+                tma_load_1d(smem_u32(sbuf) + (uint32_t)r * chunk * 4, a.ws + (int64_t)r * a.ws_len + j0, (uint32_t)slice * 4u, &tail_bar);
+            mbar_wait(&tail_bar, tail_phase);
+            tail_phase ^= 1;
+            const int64_t j = j0 + te;
+            const bool live = te < slice && j < G::kP;
+            float local = 0.f;
+            if (live) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int r = 0;
+                for (; r + 3 < grid; r += 4) {
+                    a0 += (double)sbuf[(r + 0) * chunk + te];
+                    a1 += (double)sbuf[(r + 1) * chunk + te];
+                    a2 += (double)sbuf[(r + 2) * chunk + te];
+                    a3 += (double)sbuf[(r + 3) * chunk + te];
+                }
+                for (; r < grid; ++r) a0 += (double)sbuf[r * chunk + te];
+                local = (float)((a0 + a1) + (a2 + a3));
+            }
+            float sum = local;
+            if (sharded && live) {
+                const uint32_t tag = (uint32_t)sh.seq;
+                for (int p = 1; p < sh.world; ++p) {
+                    int r = sh.rank + p;
+                    if (r >= sh.world) r -= sh.world;
+                    comm_ll_send(comm_ll_ptr(sh.bufs[r], sh.lenpad, xslot, sh.rank) + j, local, tag);
+                }
+                sum = 0.f;
+                for (int r = 0; r < sh.world; ++r)
+                    sum += r == sh.rank ? local : comm_ll_recv(comm_ll_ptr(sh.bufs[sh.rank], sh.lenpad, xslot, r) + j, tag, sh);
+            }
+            if (live) {
+                a.partials[j] = sum;
+                if (j < G::offU) {
+                    int h, n, m;
+                    if (j < G::offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
+                    else { h = (int)(j - G::offZ) >> 6; m = (int)(j - G::offZ) & 63; n = kDim; }
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(sum - __bfloat162float(hi));
+                    uint8_t* img = a.prepared + (size_t)h * 2 * kBOp + sw128(n, m >> 3) + (m & 7) * 2;
+                    *reinterpret_cast<__nv_bfloat16*>(img) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(img + kBOp) = lo;
+                }
+            }
+        }
+        if (blockIdx.x == grid - 1) {
+            for (int i = te; i < H * 2 * 15 * 8; i += 128) {
+                const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
+                *reinterpret_cast<uint4*>(a.prepared + (size_t)t * kBOp + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        // ---- second grid barrier: the B-operand image and the partials are complete
+        __threadfence();
+        bar_sync_named(2, 128);
+        const unsigned long long epoch2 = epoch + 1;
+        if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(fa.flags2 + blockIdx.x), "l"(epoch2) : "memory");
+        for (int r = te; r < grid; r += 128) {
+            unsigned long long f;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(fa.flags2 + r) : "memory");
+                if (f != epoch2) __nanosleep(32);
+            } while (f != epoch2);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        bar_sync_named(2, 128);
+        if (dbg != nullptr && te == 0) dbg[blockIdx.x * 8 + 6] = gtime();
+        if (te == 0) {
+            mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
+            for (int i = 0; i < H * 2; ++i)
+                tma_load_1d(smem_u32(Bop) + i * kBOp, a.prepared + (size_t)i * kBOp, (uint32_t)kBOp, &bbar);
+        }
+        for (int i = te; i < H * kDim; i += 128) us[i] = __ldcg(a.partials + G::offU + i);
+        const float cscale = 1.f / (sqrtf(__ldcg(a.partials + G::offSq)) * sqrtf(__ldcg(a.partials + G::offSq + 1)));
+        bar_sync_named(2, 128);
+        // =================== pass 2: epilogue (see apply_tc_kernel, MODE 0) ===================
+        const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
+        const uint64_t pol = policy_evict_first();
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int64_t trow = row0_of(sc);
+            const int h = sc % H, slot = sc % kNAcc;
+            mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
+            uint32_t qz_bits = tmem_ld1(taddr + kDim);
+            tmem_ld_wait1(qz_bits);
+            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, a.n_total));
+            if (lane == 0) tma_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int c0 = 0; c0 < kDim; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait32(r);
+                if (c0 == 32) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[slot]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 u4 = *reinterpret_cast<const float4*>(us + h * kDim + c0 + j);
+                    float4 o;
+                    o.x = fmaf(__uint_as_float(r[j]), cscale, u4.x) * inv_den;
+                    o.y = fmaf(__uint_as_float(r[j + 1]), cscale, u4.y) * inv_den;
+                    o.z = fmaf(__uint_as_float(r[j + 2]), cscale, u4.z) * inv_den;
+                    o.w = fmaf(__uint_as_float(r[j + 3]), cscale, u4.w) * inv_den;
+                    sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
+                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int col = h * kDim;
+                const int row0 = (int)trow + ew * 32;
+                if (fa.store_hint) {
+                    tma_store_2d_hint(&out_map, obox, col, row0, pol);
+                    tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
+                } else {
+                    tma_store_2d(&out_map, obox, col, row0);
+                    tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
+                }
+                tma_commit();
+            }
+        }
+        if (lane == 0) tma_wait_all0();
+    } else if (lane == 0) {
+        // =================== MMA issuer: pass 1 ... ===================
+        {
+            const uint32_t idesc = make_idesc(128, 128, 1, 1);
+            const uint32_t lbo = G::kBlockTile, sbo = 1024;
+            const uint32_t ops_base = smem_u32(ops);
+            for (int it = 0; it < iters; ++it) {
+                const int o = it % G::kNO;
+                mbar_wait(&ofull[o], (it / G::kNO) & 1);
+                tc_fence_after();
+                const uint32_t sb = ops_base + o * G::kOpStage;
+#pragma unroll
+                for (int p = 0; p < G::kPairs; ++p) {
+                    const uint32_t ho = p * 2 * G::kBlockTile;
+                    const uint64_t khi = make_desc(sb + 0 * G::kOp + ho, lbo, sbo), klo = make_desc(sb + 1 * G::kOp + ho, lbo, sbo);
+                    const uint64_t vhi = make_desc(sb + 2 * G::kOp + ho, lbo, sbo), vlo = make_desc(sb + 3 * G::kOp + ho, lbo, sbo);
+                    umma(tmem + p * 128, khi, vhi, idesc, it > 0 ? 1u : 0u);
+                    umma(tmem + p * 128, khi, vlo, idesc, 1u);
+                    umma(tmem + p * 128, klo, vhi, idesc, 1u);
+                }
+                umma_commit(&oempty[o]);
+            }
+            if (iters > 0) umma_commit(&done); else mbar_arrive(&done);
+        }
+        // =================== ... and pass 2 ===================
+        const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
+        const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
+        mbar_wait(&bbar, 0);
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
+            if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+            mbar_wait(&full[s], (sc / kNS2) & 1);
+            tc_fence_after();
+            const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
+            const uint32_t d = tmem + slot * kAccCols;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
+                umma(d, qlo, bhi, idesc, 1u);
+                umma(d, qhi, blo, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+            umma_commit(&tfull[slot]);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    DIF_STAMP(dbg, 7);
+    if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace (kernels)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1079,7 +1558,7 @@ void dbg_report(const char* name, uint64_t* buf, int grid) {
     uint64_t t0 = ~0ull;
     for (int b = 0; b < grid; ++b) if (h[b * 8] && h[b * 8] < t0) t0 = h[b * 8];
     fprintf(stderr, "[%s] slot: min/avg/max us since first CTA start\n", name);
-    for (int s = 0; s < 7; ++s) {
+    for (int s = 0; s < 8; ++s) {
         double mn = 1e30, mx = 0, sum = 0; int n = 0;
         for (int b = 0; b < grid; ++b) { if (!h[b * 8 + s]) continue; double t = (h[b * 8 + s] - t0) * 1e-3; mn = t < mn ? t : mn; mx = t > mx ? t : mx; sum += t; ++n; }
         if (n) fprintf(stderr, "  stamp %d: %7.2f %7.2f %7.2f  (n=%d)\n", s, mn, sum / n, mx, n);
@@ -1197,6 +1676,77 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
 #undef DIF_P2
     if (rc) return rc;
     dbg_report("apply_tc", a.dbg, grid);
+    return DIF_OK;
+}
+
+
+// ---- forward in one kernel ----------------------------------------------------------------------
+// workspace: [records grid x ws_len f32][flags (grid + 1) u64][flags2 grid u64][pad to 128][B-operand image]
+static int64_t fused_ws_prepared_off(int grid, int64_t ws_len) {
+    const int64_t off = (int64_t)grid * ws_len * 4 + (int64_t)(2 * grid + 1) * 8;
+    return (off + 127) & ~(int64_t)127;
+}
+
+int64_t simple_fused_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
+    if (!simple_tc_supported(N, H, Hv, M, D)) return 0;
+    int grid;
+    tc_rows_per_cta(N, H, &grid);
+    return fused_ws_prepared_off(grid, tc_ws_len(H)) + (int64_t)H * 2 * kBOp + 128;
+}
+
+template <int H>
+static int launch_fused(const FusedArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(simple_fused_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused_bytes<H>()));
+        attr_set = true;
+    }
+    void* args[] = {(void*)&a, (void*)&map};
+    DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)simple_fused_kernel<H>, dim3(grid), dim3(kThreadsTC), args, (size_t)smem_fused_bytes<H>(), st));
+    return DIF_OK;
+}
+
+int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
+                      float* partials, float* out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                      void* const* peer_bufs, int rank, int world, unsigned long long seq) {
+    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG, "simple_forward: q/k/v must be 32-byte, out 16-byte aligned");
+    DIF_REQUIRE(((uintptr_t)ws & 127) == 0, DIF_EARG, "simple_forward: workspace must be 128-byte aligned");
+    DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
+    int grid;
+    const int rpc = tc_rows_per_cta(N, H, &grid);
+    const int64_t ws_len = tc_ws_len(H);
+    const int64_t poff = fused_ws_prepared_off(grid, ws_len);
+    DIF_REQUIRE(ws_bytes >= poff + (int64_t)H * 2 * kBOp, DIF_EARG, "simple_forward: workspace too small");
+    DIF_REQUIRE((((ws_len + kSlices - 1) / kSlices + 3) & ~(int64_t)3) <= 128, DIF_EUNSUPPORTED, "simple_forward: slice wider than the tail warps");
+    static std::atomic<unsigned long long> epoch_src{0xA24BAED4963EE407ull ^ (unsigned long long)(uintptr_t)&epoch_src};
+    FusedArgs fa{};
+    ReduceArgs1& a = fa.r;
+    a.q = q; a.k = k; a.v = v; a.N = N; a.rows_per_cta = rpc;
+    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
+    fa.flags2 = a.flags + grid + 1;
+    a.epoch = (epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull) & ~2ull;      // epoch + 1 (second barrier) never collides with an epoch
+    a.partials = partials; a.prepared = (uint8_t*)ws + poff;
+    a.vbar = nullptr;
+    static const int hints = env_int("DIF_TC_P1_HINTS", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1), rev = env_int("DIF_TC_FUSED_REVERSE", 1);
+    a.l2_hints = hints;
+    a.n_total = (float)n_total;
+    a.sh.world = 1;
+    if (peer_bufs != nullptr && world > 1) {
+        DIF_REQUIRE(world <= kCommMaxRanks && rank >= 0 && rank < world && seq > 0, DIF_EARG, "simple_forward(sharded): bad rank/world/seq");
+        for (int r = 0; r < world; ++r) { DIF_REQUIRE(peer_bufs[r], DIF_EARG, "simple_forward(sharded): null peer buffer"); a.sh.bufs[r] = peer_bufs[r]; }
+        a.sh.rank = rank; a.sh.world = world; a.sh.seq = seq;
+        a.sh.lenpad = comm_lenpad(SimpleLayout{H, Hv, M, D}.len());
+        a.sh.timeout_ns = comm_timeout_ns();
+    }
+    a.dbg = dbg_buffer();
+    fa.out = out; fa.store_hint = sth; fa.reverse = rev;
+    CUtensorMap map;
+    int rc = make_out_map(&map, out, N, (int64_t)H * kDim);
+    if (rc) return rc;
+    rc = H == 4 ? launch_fused<4>(fa, map, grid, st) : H == 2 ? launch_fused<2>(fa, map, grid, st) : launch_fused<1>(fa, map, grid, st);
+    if (rc) return rc;
+    dbg_report("simple_fused", a.dbg, grid);
     return DIF_OK;
 }
 

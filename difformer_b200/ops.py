@@ -110,6 +110,42 @@ def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_p
     return (partials, prepared) if with_prepared else partials
 
 
+_FUSED_FORWARD = True
+
+
+def set_fused_forward(on: bool) -> None:
+    """One-kernel forward (dif_simple_forward) on tcgen05 shapes (default on); off = pass 1 and pass 2 as two launches."""
+    global _FUSED_FORWARD
+    _FUSED_FORWARD = bool(on)
+
+
+def simple_forward(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, n_total: Optional[float] = None, exchange=None):
+    """The whole 'simple' forward in one cooperative kernel (dif_simple_forward) -> (out [N,H,D], reduced partials), or
+    None when the shape is not a tcgen05 shape / the kernels are pinned to 'generic' / the fused path is switched off.
+    `exchange` (sharded.PartialsExchange): rows are a shard; the partials are all-reduced inside the kernel over NVLink."""
+    N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+    if not _FUSED_FORWARD or _SIMPLE_IMPL == _lib.DIF_IMPL_GENERIC or N != L:
+        return None
+    wsb = int(lib.dif_simple_forward_workspace_bytes(N, H, Hv, M, D))
+    if wsb <= 0:
+        return None
+    dev = qs.device
+    partials = torch.empty(int(lib.dif_simple_partials_len(H, Hv, M, D)), dtype=torch.float32, device=dev)
+    out = torch.empty((N, H, D), dtype=torch.float32, device=dev)
+    ws = workspace(dev, wsb)
+    if exchange is not None:
+        exchange.raise_if_failed()
+        exchange.seq += 1
+        peers, rank, world, seq = exchange.c_ptrs, exchange.rank, exchange.world, exchange.seq
+    else:
+        peers, rank, world, seq = None, 0, 1, 0
+    with torch.cuda.device(dev):
+        check(lib.dif_simple_forward(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D, float(N if n_total is None else n_total),
+                                     partials.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), peers, rank, world, seq, _stream(qs)),
+              "dif_simple_forward")
+    return out, partials
+
+
 def simple_apply(qs: torch.Tensor, partials: torch.Tensor, n_total: float, Hv: int, D: int,
                  epilogue: Optional[Epilogue] = None, keep=(), prepared: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pass 2.  epilogue=None -> [N,H,D]; mode-1 epilogue -> [N,D] (fused layer epilogue)."""
@@ -151,21 +187,26 @@ class _SimpleAttention(torch.autograd.Function):
         _need_cuda(qs, ks, vs)
         qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
-        xch = getattr(group, "exchange", None)      # sharded.RowShardComm: one-shot NVLink all-reduce
-        if xch is not None:
-            ex = xch(int(lib.dif_simple_partials_len(H, Hv, M, D)), qs.device)
-            fused = ex.fused_reduce(qs, ks, vs)       # pass 1 + NVLink all-reduce in one kernel (tcgen05 shapes)
-            if fused is not None:
-                partials, prepared = fused
-            else:
-                partials, prepared = ex.allreduce(simple_partials(qs, ks, vs)), None
-        else:
-            partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
-            if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-                dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
-                prepared = None            # the operand image belongs to the un-reduced partials
+        xch = getattr(group, "exchange", None)      # sharded.RowShardComm: LL-push NVLink all-reduce
         n_tot = float(N if n_total is None else n_total)
-        out = simple_apply(qs, partials, n_tot, Hv, D, prepared=prepared)
+        nccl = xch is None and group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+        ex = xch(int(lib.dif_simple_partials_len(H, Hv, M, D)), qs.device) if xch is not None else None
+        one = None if nccl else simple_forward(qs, ks, vs, n_tot, ex)     # pass 1 + (all-)reduce + pass 2 in ONE kernel
+        if one is not None:
+            out, partials = one
+        else:
+            if ex is not None:
+                fused = ex.fused_reduce(qs, ks, vs)       # pass 1 + NVLink all-reduce in one kernel (tcgen05 shapes)
+                if fused is not None:
+                    partials, prepared = fused
+                else:
+                    partials, prepared = ex.allreduce(simple_partials(qs, ks, vs)), None
+            else:
+                partials, prepared = simple_partials(qs, ks, vs, with_prepared=True)
+                if nccl:
+                    dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+                    prepared = None            # the operand image belongs to the un-reduced partials
+            out = simple_apply(qs, partials, n_tot, Hv, D, prepared=prepared)
         ctx.save_for_backward(qs, ks, vs, out, partials)
         ctx.group, ctx.n_tot = group, n_tot
         return out

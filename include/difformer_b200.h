@@ -97,6 +97,19 @@ DIF_API int dif_simple_apply(const float* q, const float* partials, const void* 
                      float* out, const dif_epilogue_t* epilogue,
                      int impl, void* stream);
 
+/* The forward in ONE kernel (tcgen05 shapes: dif_simple_forward_workspace_bytes() > 0): a cooperative persistent launch runs
+ * pass 1, the grid-wide deterministic sum of the partials (with `peer_bufs` != NULL and world > 1 also the cross-GPU
+ * LL-push all-reduce, see dif_comm_* below) and pass 2 on the rows each CTA just streamed -- no second launch, the Q rows
+ * of pass 2 are prefetched while the sum is in flight.  out[N,H,D] = full_attention_conv(q,k,v,'simple'); `partials`
+ * receives the (all-reduced) pass-1 partials, which the backward needs.  n_total = global row count (= N unsharded).
+ * `workspace` must be 128-byte aligned.  peer_bufs / rank / world / seq as in dif_simple_reduce_allreduce (NULL, 0, 1, 0
+ * for a single GPU).  Other shapes return DIF_EUNSUPPORTED: call dif_simple_reduce + dif_simple_apply. */
+DIF_API int64_t dif_simple_forward_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
+DIF_API int dif_simple_forward(const float* q, const float* k, const float* v,
+                       int64_t N, int H, int Hv, int M, int D, double n_total,
+                       float* partials, float* out, void* workspace, int64_t workspace_bytes,
+                       void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream);
+
 /* Backward of the 'simple' path (derived analytically; the reference uses autograd).
  *   bwd_partials = [ dS : H*M*D | dz : H*M | du : H*D | t_q | t_k ]  (raw, additive over shards;
  *   t_k is filled by dif_simple_bwd_apply after any all-reduce). `out` is the saved forward

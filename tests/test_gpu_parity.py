@@ -160,6 +160,36 @@ def test_tcgen05_backward(h, n):
         assert O.rel_err(a_, b_) < 1e-4
 
 
+@pytest.mark.parametrize("h", [1, 2, 4])
+@pytest.mark.parametrize("n", [1, 33, 128, 4097, 50000, 132534])
+def test_one_kernel_forward_equals_two_pass(h, n):
+    """dif_simple_forward (pass 1 + grid-wide sum + pass 2 in one cooperative launch) computes exactly what the two-launch
+    path computes -- same per-CTA row ranges, same summation order, same pass-2 arithmetic => bit-identical -- and both
+    match the fp64 oracle.  Repeated calls exercise the epoch / generation words of the two in-kernel grid barriers."""
+    q, k, v = O.synthetic_qkv(n, h, 64, seed=31 * h + n, adversarial=True)
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    flat, prep = ops.simple_partials(qg, kg, vg, with_prepared=True)
+    two = ops.simple_apply(qg, flat, float(n), h, 64, prepared=prep)
+    for rep in range(3):
+        res = ops.simple_forward(qg, kg, vg)
+        assert res is not None, "the one-kernel forward must take every tcgen05 shape"
+        out, partials = res
+        assert torch.equal(partials, flat) and torch.equal(out, two), (rep, O.rel_err(out, two))
+    assert O.rel_err(out, O.simple_attention(q.double(), k.double(), v.double())) < 1e-4
+    # and it is what the public op runs (autograd included: the saved partials feed the backward)
+    try:
+        ops.set_fused_forward(False)
+        qa, ka, va = (t.clone().requires_grad_(True) for t in (qg, kg, vg))
+        o2 = difformer.full_attention_conv(qa, ka, va, "simple")
+        o2.sum().backward()
+    finally:
+        ops.set_fused_forward(True)
+    qb, kb, vb = (t.clone().requires_grad_(True) for t in (qg, kg, vg))
+    o1 = difformer.full_attention_conv(qb, kb, vb, "simple")
+    o1.sum().backward()
+    assert torch.equal(o1, o2) and torch.equal(qb.grad, qa.grad) and torch.equal(kb.grad, ka.grad) and torch.equal(vb.grad, va.grad)
+
+
 def test_simple_rejects_n_ne_l():
     q = torch.randn(10, 1, 64, device="cuda")
     with pytest.raises(ValueError, match="N == L"):

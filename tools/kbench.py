@@ -14,6 +14,7 @@ ap.add_argument("--impl", default="auto")
 ap.add_argument("--tag", default="")
 ap.add_argument("--h", type=int, default=4)
 ap.add_argument("--noref", action="store_true")
+ap.add_argument("--fused", action="store_true", help="also time the one-kernel forward (dif_simple_forward)")
 a = ap.parse_args()
 ops.set_simple_impl(a.impl)
 H = a.h
@@ -48,6 +49,10 @@ t_op = timeit(op, a.iters)
 print(f"{a.tag} impl={a.impl} H={H} n={a.n} reduce+finalize {t_red:7.1f} us ({3*T/t_red/1e3:6.0f} GB/s)  apply {t_app:7.1f} us ({2*T/t_app/1e3:6.0f} GB/s)  "
       f"op {t_op:7.1f} us  roofline(4T) {4*T/t_op/1e3/6571.2:5.3f}", flush=True)
 
+if a.fused:
+    assert ops.simple_forward(q, k, v) is not None
+    t_f = timeit(lambda: ops.simple_forward(q, k, v), a.iters)
+    print(f"{a.tag} one-kernel forward {t_f:7.1f} us  roofline(4T) {4*T/t_f/1e3/6571.2:5.3f}", flush=True)
 if a.noref:
     sys.exit(0)
 # ---- plain-torch streaming references on the same box (what the memory system gives a trivial kernel)
