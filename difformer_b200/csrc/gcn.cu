@@ -32,13 +32,14 @@ __global__ void degree_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t
 }
 
 // CSR slot s holds original edge perm[s]; val uses the in-degree histogram for BOTH endpoints.
-__global__ void fill_kernel(const int64_t* __restrict__ ei, const float* __restrict__ w, int64_t E,
+__global__ void fill_kernel(const int64_t* __restrict__ ei, const float* __restrict__ w, int64_t E, int64_t N,
                             const int32_t* __restrict__ deg_in, const int32_t* __restrict__ perm, int transpose,
                             int32_t* __restrict__ idx, float* __restrict__ val) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= E) return;
     const int32_t e = perm[s];
     const int64_t r = ei[e], c = ei[E + e];
+    if (r < 0 || r >= N || c < 0 || c >= N) { idx[s] = 0; val[s] = 0.f; return; }   // invalid id: the host raises (rowptr[N] != E)
     // (1./d[col]).sqrt() and (1./d[row]).sqrt() in fp32, IEEE division / square root
     const float d_in = __fsqrt_rn(__fdiv_rn(1.f, (float)deg_in[c]));
     const float d_out = __fsqrt_rn(__fdiv_rn(1.f, (float)deg_in[r]));
@@ -189,11 +190,11 @@ extern "C" int dif_csr_build(const int64_t* edge_index, const float* edge_weight
         const int blocks = (int)((E + 255) / 256);
         cb = s.cub_bytes;   // stable LSD radix sort: slots of one target keep edge order
         DIF_CUDA_OK(cub::DeviceRadixSort::SortPairs(s.cub, cb, s.key_col, s.key_out, s.eid, perm, (int)E, 0, nbits, st));
-        fill_kernel<<<blocks, 256, 0, st>>>(edge_index, edge_weight, E, s.deg_in, perm, 0, src, val);
+        fill_kernel<<<blocks, 256, 0, st>>>(edge_index, edge_weight, E, N, s.deg_in, perm, 0, src, val);
         DIF_LAUNCH_OK();
         cb = s.cub_bytes;
         DIF_CUDA_OK(cub::DeviceRadixSort::SortPairs(s.cub, cb, s.key_row, s.key_out, s.eid, s.perm_t, (int)E, 0, nbits, st));
-        fill_kernel<<<blocks, 256, 0, st>>>(edge_index, edge_weight, E, s.deg_in, s.perm_t, 1, dst_t, val_t);
+        fill_kernel<<<blocks, 256, 0, st>>>(edge_index, edge_weight, E, N, s.deg_in, s.perm_t, 1, dst_t, val_t);
         DIF_LAUNCH_OK();
     }
     // out-of-range node ids are reported through rowptr[N] != E on the host side (bad flag => -1 sentinel)

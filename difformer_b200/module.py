@@ -47,7 +47,7 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
 
-    if (not output_attn) and (not segmented) and _fusable(conv.kernel, query, key, value, x_0,
+    if (not output_attn) and (not segmented) and C <= ops._MAX_NATIVE_WIDTH and _fusable(conv.kernel, query, key, value, x_0,
                                                           None if residual is None else residual[1]):
         # ---- fused inference path: everything after the Linears is two kernels (+ one SpMM)
         q, k, v = ops._f32c(query), ops._f32c(key), ops._f32c(value)
@@ -292,6 +292,8 @@ class GraphedForward:
 
     Only floating-point tensors (node features, edge weights) may change between calls; integer tensors
     (`edge_index`, `n_nodes`) and all shapes are frozen at capture time -- build a new GraphedForward for a new graph.
+    When an `edge_weight` is passed, the build of the normalised CSR values is part of the captured graph
+    (`ops.graph_csr` bypasses its cache while capturing), so new edge weights take effect on every replay.
     The returned tensor is the captured output buffer: clone it if it must survive the next call."""
 
     def __init__(self, model: nn.Module, *example_args, warmup: int = 3):

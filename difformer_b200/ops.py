@@ -286,8 +286,45 @@ def _dense_attention(qs, ks, kernel):
     return p / p.sum(1, keepdim=True)
 
 
+_MAX_NATIVE_WIDTH = 128
+_warned_wide = False
+
+
+def _wide_torch_ops(qs, ks, vs, kernel, n_total=None):
+    """Widths beyond the native kernels (M or D > 128: the `image and text/run.sh` configs use hidden_channels 300 / 400
+    with one head).  NOT a silent CPU path: CUDA tensors only, plain torch ops on the GPU (cuBLAS matmuls, autograd by
+    torch), same arithmetic as the kernels (`difformer.py:18-39,45-56` in matmul form, never materialising the [N,L,H]
+    'simple' weights).  Documented limit of the hand-written path: README.md / INTEGRATION.md."""
+    global _warned_wide
+    _need_cuda(qs, ks, vs)
+    if not _warned_wide:
+        import warnings
+        warnings.warn(f"difformer_b200: M or D > {_MAX_NATIVE_WIDTH} runs plain torch CUDA ops, not the hand-written kernels "
+                      f"(qs {tuple(qs.shape)}, vs {tuple(vs.shape)})", RuntimeWarning, stacklevel=3)
+        _warned_wide = True
+    H = qs.shape[1]
+    vb = vs if vs.shape[1] == H else vs.expand(-1, H, -1)
+    if kernel == "simple":
+        n = float(qs.shape[0] if n_total is None else n_total)
+        c = 1.0 / (torch.linalg.vector_norm(qs) * torch.linalg.vector_norm(ks))
+        S = torch.matmul(ks.permute(1, 2, 0), vb.permute(1, 0, 2))                       # [H,M,D]
+        num = torch.matmul(qs.permute(1, 0, 2), S).permute(1, 0, 2) * c + vb.sum(0).unsqueeze(0)
+        den = (qs * ks.sum(0).unsqueeze(0)).sum(-1, keepdim=True) * c + n
+        return num / den
+    out = []
+    for h in range(H):                                                                   # one head at a time: [N,L] temporaries
+        p = torch.sigmoid(qs[:, h] @ ks[:, h].t())
+        out.append((p / p.sum(1, keepdim=True)) @ vb[:, h])
+    return torch.stack(out, 1)
+
+
 def full_attention_conv(qs, ks, vs, kernel, output_attn=False, *, group=None, n_total=None):
     """Drop-in for difformer.py:10-61.  qs [N,H,M], ks [L,H,M], vs [L,Hv,D] -> [N,H,D]."""
+    if kernel in ("simple", "sigmoid") and (qs.shape[-1] > _MAX_NATIVE_WIDTH or vs.shape[-1] > _MAX_NATIVE_WIDTH):
+        if group is not None:
+            raise NotImplementedError("row-sharded propagation needs M, D <= 128 (the native kernels)")
+        out = _wide_torch_ops(qs, ks, vs, kernel, n_total)
+        return (out, _dense_attention(qs, ks, kernel)) if output_attn else out
     if kernel == "simple":
         out = _SimpleAttention.apply(qs, ks, vs, group, n_total)
     elif kernel == "sigmoid":
@@ -308,7 +345,7 @@ class GraphCSR:
     """Target-sorted CSR of `edge_index` with the reference's symmetric in-degree normalisation
     baked into `val`, plus the source-sorted transpose for the backward (difformer.py:63-75)."""
 
-    def __init__(self, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int, validate: bool = True):
         _need_cuda(edge_index, edge_weight)
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError("edge_index must be [2,E]")
@@ -334,7 +371,8 @@ class GraphCSR:
                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream), "dif_csr_build")
         # one validation sync per graph build (cached afterwards): out-of-range node ids are skipped
         # by the histogram, so the row pointer falls short of E exactly when some id is invalid
-        if int(self.rowptr[-1]) != E:
+        # (skipped when the build is being captured into a CUDA graph: the ids were validated by the eager warm-up run)
+        if validate and int(self.rowptr[-1]) != E:
             raise IndexError("edge_index contains node ids outside [0, num_nodes)")
         self._keep = (ei, w)
 
@@ -346,6 +384,11 @@ _CSR_CACHE_MAX = 16
 def graph_csr(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int) -> GraphCSR:
     """CSR cache keyed on the storage identity + version counter of edge_index/edge_weight:
     `edge_index` is constant across layers and epochs in the reference harness (main.py:118)."""
+    if edge_weight is not None and torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture (GraphedForward): the values of `edge_weight` may change between replays, so the build of
+        # the normalised CSR values is recorded INTO the graph (kernels + CUB on caller-owned scratch: capture-safe)
+        # instead of being served from the cache
+        return GraphCSR(edge_index, edge_weight, num_nodes, validate=False)
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), int(num_nodes),
            None if edge_weight is None else (edge_weight.data_ptr(), edge_weight._version))
     hit = _CSR_CACHE.get(key)

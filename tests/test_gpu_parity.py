@@ -2,6 +2,8 @@
 which goes through the C ABI (libdifformer_b200.so); the oracle / golden vectors are only the
 checker.  Tolerance: 1e-3 relative (BASELINE.json north_star), fp32, norm-wise, against the
 committed reference outputs and the fp64 oracle; integer gather indices bit-exact."""
+from contextlib import nullcontext as _nullcontext
+
 import pytest
 import torch
 
@@ -202,6 +204,37 @@ def test_simple_shapes_and_edges(n, h, hv, d, impl):
     q, k, v = O.synthetic_qkv(n, h, d, seed=n, hv=hv, adversarial=True)
     out = difformer.full_attention_conv(dev(q), dev(k), dev(v), "simple")
     assert O.rel_err(out, O.simple_attention(q.double(), k.double(), v.double())) < TOL
+
+
+@pytest.mark.parametrize("kernel", ["simple", "sigmoid"])
+def test_wide_hidden_channels_300_400(kernel):
+    """`image and text/run.sh` runs hidden_channels 300 / 400 with one head: wider than the hand-written kernels (M, D <= 128),
+    served by the documented torch-CUDA-op path (ops._wide_torch_ops) -- forward, backward and through the model."""
+    for d in (300, 400):
+        q, k, v = O.synthetic_qkv(257, 1, d, seed=d, adversarial=True)
+        if kernel == "sigmoid":
+            q, k = q * 0.1, k * 0.1
+        qg, kg, vg = (dev(t).requires_grad_(True) for t in (q, k, v))
+        with pytest.warns(RuntimeWarning) if not ops._warned_wide else _nullcontext():
+            out = difformer.full_attention_conv(qg, kg, vg, kernel)
+        g = torch.randn(257, 1, d, generator=torch.Generator().manual_seed(1))
+        out.backward(dev(g))
+        if kernel == "simple":
+            want = O.simple_attention(q.double(), k.double(), v.double())
+            grads = O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())
+        else:
+            want = O.sigmoid_attention(q.double(), k.double(), v.double())
+            grads = O.sigmoid_attention_backward(q.double(), k.double(), v.double(), g.double())
+        assert O.rel_err(out, want) < TOL
+        for got, w in zip((qg.grad, kg.grad, vg.grad), grads):
+            assert O.rel_err(got, w) < TOL
+    x = dev(torch.randn(300, 20))
+    ei = dev(O.synthetic_graph(300, 900, seed=2))
+    m = difformer.DIFFormer(20, 300, 4, num_layers=1, num_heads=1, kernel=kernel, use_graph=True, use_weight=False).cuda().eval()
+    sd = {k_: t.detach().cpu().clone() for k_, t in m.state_dict().items()}
+    want = O.difformer_forward(sd, x.cpu(), ei.cpu(), hidden_channels=300, num_layers=1, num_heads=1, kernel=kernel, use_weight=False)
+    with torch.no_grad():
+        assert O.rel_err(m(x, ei), want) < TOL
 
 
 def test_simple_full_size_properties(impl):
@@ -446,6 +479,19 @@ def test_model_cuda_graph_replay():
             want2 = m(x2, ei).clone()
         assert torch.equal(gf(x2, ei), want2)
         assert torch.equal(gf(x, ei), want)
+    # edge weights are floating-point inputs too (spatial-temporal snapshots pass them): the build of the normalised CSR
+    # values is recorded into the graph, so a replay with new weights must follow them
+    m = difformer.DIFFormer(48, 64, 5, num_layers=2, num_heads=2, kernel="simple", use_graph=True).to(x.device).eval()
+    w1 = dev(torch.rand(ei.shape[1], generator=gen))
+    w2 = dev(torch.rand(ei.shape[1], generator=gen) * 3.0)
+    with torch.no_grad():
+        want1, want2 = m(x, ei, w1).clone(), m(x, ei, w2).clone()
+    assert O.rel_err(want1, want2) > 1e-3          # the weights matter
+    gf = GraphedForward(m, x, ei, w1)
+    assert torch.equal(gf(x, ei, w1), want1)
+    assert torch.equal(gf(x, ei, w2), want2)
+    with torch.no_grad():
+        assert torch.equal(gf(x2, ei, w1), m(x2, ei, w1))
 
 
 # ---------------------------------------------------------------------------------- batched graphs (v2)
