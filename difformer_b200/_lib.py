@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdifformer_b200.so")
 
 DIF_IMPL_AUTO, DIF_IMPL_GENERIC, DIF_IMPL_TCGEN05 = 0, 1, 2
+DIF_DTYPE_F32, DIF_DTYPE_BF16, DIF_DTYPE_F16 = 0, 1, 2
 
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -31,7 +32,7 @@ SIGNATURES = {
     "dif_simple_reduce": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "dif_simple_apply": (c_i32, [c_vp, c_vp, c_vp, c_f64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, ctypes.POINTER(Epilogue), c_i32, c_vp]),
     "dif_simple_forward_workspace_bytes": (c_i64, [c_i64] + [c_i32] * 4),
-    "dif_simple_forward": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_vp, c_vp, c_vp, c_i64,
+    "dif_simple_forward": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_vp, c_vp, c_vp, c_i64,
                                    ctypes.POINTER(c_vp), c_i32, c_i32, ctypes.c_uint64, c_vp]),
     "dif_simple_bwd_partials_len": (c_i64, [c_i32] * 3),
     "dif_simple_bwd_rowscal_len": (c_i64, [c_i64, c_i32, c_i32, c_i32, c_i32]),

@@ -95,15 +95,19 @@ extern "C" int64_t dif_simple_forward_workspace_bytes(int64_t N, int H, int Hv, 
     return simple_fused_workspace_bytes(N, H, Hv, M, D);
 }
 
-extern "C" int dif_simple_forward(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
-                                  float* partials, float* out, void* workspace, int64_t workspace_bytes,
+extern "C" int dif_simple_forward(const void* q, const void* k, const void* v, int dtype, int64_t N, int H, int Hv, int M, int D, double n_total,
+                                  float* partials, void* out, void* workspace, int64_t workspace_bytes,
                                   void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream) {
     DIF_REQUIRE(q && k && v && partials && out && workspace, DIF_EARG, "simple_forward: null pointer");
     DIF_REQUIRE(n_total > 0, DIF_EARG, "simple_forward: n_total must be positive");
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED,
                 "simple_forward: the one-kernel forward needs the tcgen05 shapes (M == D == 64, Hv == H, H in {1, 2, 4}); use dif_simple_reduce + dif_simple_apply");
-    return simple_forward_tc(q, k, v, N, H, Hv, M, D, n_total, partials, out, workspace, workspace_bytes, (cudaStream_t)stream,
-                             peer_bufs, rank, world, seq);
+    if (dtype == DIF_DTYPE_BF16 || dtype == DIF_DTYPE_F16)
+        return simple_forward_lp(q, k, v, dtype, N, H, Hv, M, D, n_total, partials, out, workspace, workspace_bytes, (cudaStream_t)stream,
+                                 peer_bufs, rank, world, seq);
+    DIF_REQUIRE(dtype == DIF_DTYPE_F32, DIF_EARG, "simple_forward: unknown dtype %d", dtype);
+    return simple_forward_tc((const float*)q, (const float*)k, (const float*)v, N, H, Hv, M, D, n_total, partials, (float*)out, workspace,
+                             workspace_bytes, (cudaStream_t)stream, peer_bufs, rank, world, seq);
 }
 
 extern "C" int dif_simple_apply(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,

@@ -178,6 +178,10 @@ int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N,
                       float* partials, float* out, void* ws, int64_t ws_bytes, cudaStream_t st,
                       void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0);
 
+int simple_forward_lp(const void* q, const void* k, const void* v, int dtype, int64_t N, int H, int Hv, int M, int D, double n_total,
+                      float* partials, void* out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                      void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0);
+
 int64_t simple_tc_rowscal_floats(int64_t N, int H);
 int simple_bwd_reduce_tc(const float* q, const float* g, const float* out, const float* partials, double n_total,
                          int64_t N, int H, float* bwd_partials, float* rowscal, void* ws, int64_t ws_bytes, cudaStream_t st);

@@ -30,68 +30,13 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
-#include "tc_ptx.cuh"
+#include "simple_tc.cuh"
 
 namespace dif {
 
 int simple_finalize_fwd(const float* ws, int nchunks, int H, int Hv, int M, int D, float* partials, cudaStream_t st);
 
 namespace {
-
-// ------------------------------------------------------------------------------------------
-// compile-time geometry for H heads of 64 columns
-// ------------------------------------------------------------------------------------------
-template <int H>
-struct Geo {
-    static_assert(H == 1 || H == 2 || H == 4, "tcgen05 path: H in {1, 2, 4}");
-    static constexpr int kRowF = H * kDim;              // floats per node row
-    static constexpr int kRowB = kRowF * 4;             // bytes per node row
-    // pass 1: the UMMA is M = N = 128 = two 64-wide MN blocks.  A block is a head (H >= 2) or, for H = 1, one of the
-    // two 16-node halves of a 32-node stage (both halves accumulate S; the two diagonal blocks are added at the end).
-    static constexpr int kBlocks = H < 2 ? 2 : H;
-    static constexpr int kPairs = kBlocks / 2;
-    static constexpr int kNodes = 16 * kBlocks / H;     // nodes per stage (32 for H = 1, else 16)
-    static constexpr int kBlockTile = 16 * 128;         // [16 nodes][64 bf16]
-    static constexpr int kOp = kBlocks * kBlockTile;    // one operand (Khi | Klo | Vhi | Vlo) of a stage
-    static constexpr int kOpStage = 4 * kOp;
-    static constexpr int kStgT = kNodes * kRowB;        // fp32 staging bytes of one tensor of a stage (= kBlocks * 4 KB)
-    static constexpr int kStg = 3 * kStgT;              // K | V | Q
-    static constexpr int kNSG = 3, kNO = 2;             // staging / operand ring depths
-    static constexpr int kSmem1 = kNSG * kStg + kNO * kOpStage + 1024;
-    static constexpr int kChunksPerRow = kRowB / 16;    // 16-byte chunks per node row (16 H)
-    static constexpr int kChunksPerThread = kStgT / 16 / 256;   // = kBlocks (256 converter threads)
-    static constexpr int kTmemCols1 = kPairs * 128 < 32 ? 32 : kPairs * 128;
-    // partials layout [S | z | u | sq | sk]
-    static constexpr int offZ = H * kDim * kDim, offU = offZ + H * kDim, offSq = offU + H * kDim, kP = offSq + 2;
-    // pass 2
-    static constexpr int kBBytes = H * 2 * 80 * 128;    // prepared B operands: per head hi | lo, 80 rows x 128 B
-};
-
-constexpr int kBOp = 80 * 128;                        // one (head, hi|lo) B-operand tile of pass 2
-using ShardArgs = CommPeers;  // multi-GPU: peer-mapped LL exchange buffers (common.cuh, csrc/comm.cu)
-constexpr int kThreadsT = 10 * 32;                    // pass 1: warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
-constexpr int kSlices = 148;                          // column slices of the record for the fused cross-CTA sum
-
-struct ReduceArgs1 {
-    const float *q, *k, *v;
-    int64_t N;
-    int rows_per_cta;
-    float* ws;                    // per-CTA records [grid][ws_len]
-    int64_t ws_len;
-    unsigned long long* flags;    // [grid] record-ready flags
-    unsigned long long epoch;
-    float* partials;
-    uint8_t* prepared;            // optional pass-2 operand image
-    int l2_hints;
-    ShardArgs sh;
-    uint64_t* dbg;
-    // backward (BWD): q -> A role, g -> B role (scaled to dnum = g/den on the fly), out -> third stream
-    const float* fwd_partials;    // forward partials (S, z, u, sq, sk)
-    float n_total;
-    float* rowscal;               // [N][H][2] = (1/den, dden) per (node, head), consumed by the dq kernel
-    float* vbar;                  // fwd, optional: mean over heads of V, [N][64] (feeds the gcn SpMM of the fused layer)
-};
 
 // BWD = false: forward pass 1 (S = K^T V, z, u, norms).
 // BWD = true : backward pass 1: dS = Q^T dnum, dz = sum q dden, du = sum dnum, t_q, with
@@ -468,17 +413,6 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------
-constexpr int kTile2 = 128;                           // rows per tile = UMMA M
-constexpr int kQOp = kTile2 * 128;                    // 16 KB: [128 rows][64 bf16] of one head
-constexpr int kStage2 = 2 * kQOp;                     // Qhi | Qlo
-constexpr int kNS2 = 3;
-constexpr int kBN = 80;                               // UMMA N: 64 columns of S + z column + padding
-constexpr int kNAcc = 4, kAccCols = 128;              // TMEM accumulator ring (4 x 128 columns)
-constexpr int kOutBox = 32 * 128;                     // TMA store box: 32 rows x 32 floats, 128B swizzle
-constexpr int kOutStage = 4 * 2 * kOutBox;            // per epilogue warp: two boxes (column halves of a head)
-template <int H>
-constexpr int smem2_bytes() { return Geo<H>::kBBytes + kNS2 * kStage2 + kOutStage + H * kDim * 4 + 1024; }
-
 struct ApplyTcArgs {
     const float* q;
     const float* partials;
@@ -1011,18 +945,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
 // Shared memory: the two passes alias one dynamic allocation ([stg | ops] vs [Bop | Q stages | out staging | u]); the
 // slice-sum buffer of the tail lies over Bop (loaded afterwards), so the Q stages are free for the prefetch.
 // ------------------------------------------------------------------------------------------
-struct FusedArgs {
-    ReduceArgs1 r;            // pass 1 (+ tail, exchange) arguments; r.prepared = global scratch for the B-operand image (required)
-    float* out;
-    int store_hint, reverse;
-    unsigned long long* flags2;   // [grid] second grid barrier (B image complete)
-};
-template <int H>
-constexpr int smem_fused_bytes() { return (Geo<H>::kSmem1 > smem2_bytes<H>() ? Geo<H>::kSmem1 : smem2_bytes<H>()); }
-
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
-
 template <int H>
 __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __grid_constant__ FusedArgs fa, const __grid_constant__ CUtensorMap out_map) {
     using G = Geo<H>;
@@ -1037,8 +959,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
     uint8_t* stages = base + G::kBBytes;
     uint8_t* ostage = stages + kNS2 * kStage2;                       // [4 warps][2 boxes][32 rows][128 B], 1024-aligned
     float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
-    static_assert(kSlices * 4 * ((((G::kP + 7) / 8 * 8 + kSlices - 1) / kSlices + 3) / 4 * 4) <= G::kBBytes, "the slice buffer of the tail must stay below the Q stages");
-    __shared__ uint64_t sfull[G::kNSG], sempty[G::kNSG], ofull[G::kNO], oempty[G::kNO], done, tail_bar;
+    __shared__ uint64_t sfull[G::kNSG], sempty[G::kNSG], ofull[G::kNO], oempty[G::kNO], done;
     __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], bbar;
     __shared__ uint32_t tmem_slot;
     __shared__ float part[16];
@@ -1057,7 +978,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
         for (int s = 0; s < G::kNSG; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 8); }
         for (int s = 0; s < G::kNO; ++s) { mbar_init(&ofull[s], 8); mbar_init(&oempty[s], 1); }
         mbar_init(&done, 1);
-        mbar_init(&tail_bar, 1);
         for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
         for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(&bbar, 1);
@@ -1068,6 +988,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();                                         // programmatic dependent launch: everything above overlapped the previous kernel
     DIF_STAMP(dbg, 1);
 
     if (warp < 8) {
@@ -1194,13 +1115,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
                     tma_load_1d(stg_base + s * G::kStg + 2 * G::kStgT, a.q + row * G::kRowF, bytes, &sfull[s]);
                 }
             }
+            // HBM idles from here until pass 2 starts (CTA finish spread + tail): pull the Q tiles pass 2 will read LAST
+            // (the ones pass 1 streamed first, least likely still in L2) into L2 now
+            const int npf = min(fa.pf_tiles, my_tiles);
+            for (int t = 0; t < npf; ++t) {
+                const int64_t prow = r0 + (int64_t)t * kTile2;
+                prefetch_l2(a.q + prow * G::kRowF, (uint32_t)(min((int64_t)kTile2, r1 - prow) * G::kRowB));
+            }
         }
         __syncwarp();
         // =================== tail (see reduce_tma_kernel): record, grid-wide slice sum (+ cross-GPU LL exchange) ===================
         mbar_wait(&done, 0);
         tc_fence_after();
         bar_sync_named(1, 384);                          // barrier A: the converters' column sums are in `red` / `part`
-        if (dbg != nullptr && te == 0) dbg[blockIdx.x * 8 + 4] = gtime();
+        if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 4] = gtime();
         float* rec = a.ws + (int64_t)blockIdx.x * a.ws_len;
         for (int col = te; col < G::kRowF; col += 128) {
             float z = 0.f, u = 0.f;
@@ -1213,154 +1141,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
             for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
             rec[G::offSq] = sq;
             rec[G::offSq + 1] = sk;
-            for (int64_t i = G::kP; i < a.ws_len; ++i) rec[i] = 0.f;
         }
-        if (H == 1) bar_sync_named(2, 128);              // `red` is re-used below
-#pragma unroll 1
-        for (int p = 0; p < G::kPairs; ++p) {
-            const int wq = ew, hp = wq >> 1, m = (wq * 32 + lane) & 63;
-            uint32_t r[2][32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (iters > 0) {
-                    tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + p * 128 + hp * 64 + c * 32, r[c]);
-                    tmem_ld_wait32(r[c]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[c][j] = 0u;
-                }
-            }
-            if (H == 1) {
-                if (hp == 1) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) red[m * 65 + c * 32 + j] = __uint_as_float(r[c][j]);
-                }
-                bar_sync_named(2, 128);
-                if (hp == 0) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) r[c][j] = __float_as_uint(__uint_as_float(r[c][j]) + red[m * 65 + c * 32 + j]);
-                }
-            }
-            if (H != 1 || hp == 0) {
-                const int blk = (H == 1) ? 0 : 2 * p + hp;
-                float* dst = rec + ((int64_t)blk * kDim + m) * kDim;
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                                     :: "l"(dst + c * 32 + j), "r"(r[c][j]), "r"(r[c][j + 1]), "r"(r[c][j + 2]), "r"(r[c][j + 3]),
-                                        "r"(r[c][j + 4]), "r"(r[c][j + 5]), "r"(r[c][j + 6]), "r"(r[c][j + 7]) : "memory");
-            }
-        }
-        tc_fence_before();
-        __threadfence();
-        bar_sync_named(2, 128);
-        if (dbg != nullptr && te == 0) dbg[blockIdx.x * 8 + 5] = gtime();
-        const int grid = gridDim.x;
-        const unsigned long long gen = *reinterpret_cast<volatile unsigned long long*>(a.flags + grid);
-        const unsigned long long epoch = a.epoch + gen * 0x9E3779B97F4A7C15ull;
-        if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(epoch) : "memory");
-        const int chunk = (int)((((a.ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
-        float* sbuf = reinterpret_cast<float*>(stg);    // [grid][chunk] fp32 over the (not yet loaded) B operands
-        const ShardArgs& sh = a.sh;
-        const bool sharded = sh.world > 1;
-        const int xslot = (int)(sh.seq & 1);
-        if (sharded && blockIdx.x == 0 && te == 0) comm_check_status(sh);
-        bool waited = false;
-        uint32_t tail_phase = 0;
-        for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
-            const int64_t j0 = (int64_t)sl * chunk;
-            const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
-            if (slice <= 0) break;
-            if (!waited) {
-                for (int r = te; r < grid; r += 128) {
-                    unsigned long long f;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
-                        if (f != epoch) __nanosleep(32);
-                    } while (f != epoch);
-                }
-                if (blockIdx.x == 0) {
-                    bar_sync_named(2, 128);
-                    if (te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + grid) = gen + 1;
-                }
-                asm volatile("fence.proxy.async;" ::: "memory");
-                waited = true;
-            }
-            bar_sync_named(2, 128);
-            if (te == 0) mbar_expect_tx(&tail_bar, (uint32_t)grid * (uint32_t)slice * 4u);
-            bar_sync_named(2, 128);
-            for (int r = te; r < grid; r += 128)
-                tma_load_1d(smem_u32(sbuf) + (uint32_t)r * chunk * 4, a.ws + (int64_t)r * a.ws_len + j0, (uint32_t)slice * 4u, &tail_bar);
-            mbar_wait(&tail_bar, tail_phase);
-            tail_phase ^= 1;
-            const int64_t j = j0 + te;
-            const bool live = te < slice && j < G::kP;
-            float local = 0.f;
-            if (live) {
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int r = 0;
-                for (; r + 3 < grid; r += 4) {
-                    a0 += (double)sbuf[(r + 0) * chunk + te];
-                    a1 += (double)sbuf[(r + 1) * chunk + te];
-                    a2 += (double)sbuf[(r + 2) * chunk + te];
-                    a3 += (double)sbuf[(r + 3) * chunk + te];
-                }
-                for (; r < grid; ++r) a0 += (double)sbuf[r * chunk + te];
-                local = (float)((a0 + a1) + (a2 + a3));
-            }
-            float sum = local;
-            if (sharded && live) {
-                const uint32_t tag = (uint32_t)sh.seq;
-                for (int p = 1; p < sh.world; ++p) {
-                    int r = sh.rank + p;
-                    if (r >= sh.world) r -= sh.world;
-                    comm_ll_send(comm_ll_ptr(sh.bufs[r], sh.lenpad, xslot, sh.rank) + j, local, tag);
-                }
-                sum = 0.f;
-                for (int r = 0; r < sh.world; ++r)
-                    sum += r == sh.rank ? local : comm_ll_recv(comm_ll_ptr(sh.bufs[sh.rank], sh.lenpad, xslot, r) + j, tag, sh);
-            }
-            if (live) {
-                a.partials[j] = sum;
-                if (j < G::offU) {
-                    int h, n, m;
-                    if (j < G::offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
-                    else { h = (int)(j - G::offZ) >> 6; m = (int)(j - G::offZ) & 63; n = kDim; }
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
-                    const __nv_bfloat16 lo = __float2bfloat16_rn(sum - __bfloat162float(hi));
-                    uint8_t* img = a.prepared + (size_t)h * 2 * kBOp + sw128(n, m >> 3) + (m & 7) * 2;
-                    *reinterpret_cast<__nv_bfloat16*>(img) = hi;
-                    *reinterpret_cast<__nv_bfloat16*>(img + kBOp) = lo;
-                }
-            }
-        }
-        if (blockIdx.x == grid - 1) {
-            for (int i = te; i < H * 2 * 15 * 8; i += 128) {
-                const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
-                *reinterpret_cast<uint4*>(a.prepared + (size_t)t * kBOp + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-        // ---- second grid barrier: the B-operand image and the partials are complete
-        __threadfence();
-        bar_sync_named(2, 128);
-        const unsigned long long epoch2 = epoch + 1;
-        if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(fa.flags2 + blockIdx.x), "l"(epoch2) : "memory");
-        for (int r = te; r < grid; r += 128) {
-            unsigned long long f;
-            do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(fa.flags2 + r) : "memory");
-                if (f != epoch2) __nanosleep(32);
-            } while (f != epoch2);
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");
-        bar_sync_named(2, 128);
-        if (dbg != nullptr && te == 0) dbg[blockIdx.x * 8 + 6] = gtime();
+        if (H == 1) bar_sync_named(2, 128);              // `red` is re-used by the tail
+        fused_tail<H>(a, fa.flags2, rec, te, ew, lane, tmem, iters > 0, red);
         if (te == 0) {
             mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
             for (int i = 0; i < H * 2; ++i)
@@ -1448,6 +1231,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
         // =================== ... and pass 2 ===================
         const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
         const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
+        pdl_launch_dependents();                        // the next kernel of the stream may start its prologue as SMs free up
         mbar_wait(&bbar, 0);
         for (int sc = 0; sc < nsc; ++sc) {
             const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
@@ -1522,61 +1306,10 @@ int make_out_map_uncached(CUtensorMap* map, float* base, int64_t rows, int64_t c
     return DIF_OK;
 }
 
-namespace {
-
-int tc_grid(int64_t units) {
-    const int sms = sm_count();
-    return (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-}
-
-// Row partition shared by both passes: contiguous ranges of whole 128-row tiles, one per CTA.
-int tc_rows_per_cta(int64_t N, int H, int* grid) {
-    (void)H;      // whole 128-row tiles per CTA: a multiple of the pass-1 stage (16 or 32 nodes) for every H
-    int g = tc_grid((N + kTile2 - 1) / kTile2);
-    int64_t rpc = (N + g - 1) / g;
-    rpc = (rpc + kTile2 - 1) / kTile2 * kTile2;
-    g = (int)((N + rpc - 1) / rpc);
-    *grid = g;
-    return (int)rpc;
-}
-
-// DIF_TC_DEBUG_TIMES=1: per-CTA %globaltimer stamps, summarised on stderr after a device sync (debug only)
-uint64_t* dbg_buffer() {
-    static uint64_t* buf = nullptr;
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("DIF_TC_DEBUG_TIMES"); on = (e && atoi(e)) ? 1 : 0; }
-    if (!on) return nullptr;
-    if (!buf) cudaMalloc(&buf, 256 * 8 * sizeof(uint64_t));
-    cudaMemset(buf, 0, 256 * 8 * sizeof(uint64_t));
-    return buf;
-}
-void dbg_report(const char* name, uint64_t* buf, int grid) {
-    if (!buf) return;
-    cudaDeviceSynchronize();
-    static uint64_t h[256 * 8];
-    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
-    uint64_t t0 = ~0ull;
-    for (int b = 0; b < grid; ++b) if (h[b * 8] && h[b * 8] < t0) t0 = h[b * 8];
-    fprintf(stderr, "[%s] slot: min/avg/max us since first CTA start\n", name);
-    for (int s = 0; s < 8; ++s) {
-        double mn = 1e30, mx = 0, sum = 0; int n = 0;
-        for (int b = 0; b < grid; ++b) { if (!h[b * 8 + s]) continue; double t = (h[b * 8 + s] - t0) * 1e-3; mn = t < mn ? t : mn; mx = t > mx ? t : mx; sum += t; ++n; }
-        if (n) fprintf(stderr, "  stamp %d: %7.2f %7.2f %7.2f  (n=%d)\n", s, mn, sum / n, mx, n);
-    }
-}
-
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
-}  // namespace
-
 bool simple_tc_supported(int64_t N, int H, int Hv, int M, int D) {
     return N >= 1 && (H == 1 || H == 2 || H == 4) && Hv == H && M == kDim && D == kDim;
 }
 
-static int64_t tc_ws_len(int H) { return (SimpleLayout{H, H, kDim, kDim}.len() + 7) & ~(int64_t)7; }   // 32-byte aligned records (256-bit stores)
 
 int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
     (void)Hv; (void)M; (void)D;
@@ -1681,12 +1414,6 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
 
 
 // ---- forward in one kernel ----------------------------------------------------------------------
-// workspace: [records grid x ws_len f32][flags (grid + 1) u64][flags2 grid u64][pad to 128][B-operand image]
-static int64_t fused_ws_prepared_off(int grid, int64_t ws_len) {
-    const int64_t off = (int64_t)grid * ws_len * 4 + (int64_t)(2 * grid + 1) * 8;
-    return (off + 127) & ~(int64_t)127;
-}
-
 int64_t simple_fused_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
     if (!simple_tc_supported(N, H, Hv, M, D)) return 0;
     int grid;
@@ -1702,8 +1429,7 @@ static int launch_fused(const FusedArgs& a, const CUtensorMap& map, int grid, cu
         attr_set = true;
     }
     void* args[] = {(void*)&a, (void*)&map};
-    DIF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)simple_fused_kernel<H>, dim3(grid), dim3(kThreadsTC), args, (size_t)smem_fused_bytes<H>(), st));
-    return DIF_OK;
+    return launch_persistent((const void*)simple_fused_kernel<H>, grid, kThreadsTC, (size_t)smem_fused_bytes<H>(), st, args);
 }
 
 int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
@@ -1725,11 +1451,13 @@ int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N,
     a.q = q; a.k = k; a.v = v; a.N = N; a.rows_per_cta = rpc;
     a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
     fa.flags2 = a.flags + grid + 1;
-    a.epoch = (epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull) & ~2ull;      // epoch + 1 (second barrier) never collides with an epoch
+    a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
     a.partials = partials; a.prepared = (uint8_t*)ws + poff;
     a.vbar = nullptr;
     static const int hints = env_int("DIF_TC_P1_HINTS", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1), rev = env_int("DIF_TC_FUSED_REVERSE", 1);
+    static const int pft = env_int("DIF_TC_FUSED_PF_TILES", 3);
     a.l2_hints = hints;
+    fa.pf_tiles = pft;
     a.n_total = (float)n_total;
     a.sh.world = 1;
     if (peer_bufs != nullptr && world > 1) {

@@ -1,0 +1,344 @@
+// Shared by the tcgen05 'simple' kernels (simple_sm100.cu: fp32 I/O; simple_lp_sm100.cu: bf16 / fp16 I/O): compile-time
+// geometry, kernel argument structs, host-side partition / workspace helpers and the fused tail that turns the per-CTA
+// pass-1 records into the grid-wide (and cross-GPU) sum plus the pass-2 operand image inside a cooperative kernel.
+#pragma once
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dif {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// compile-time geometry for H heads of 64 columns
+// ------------------------------------------------------------------------------------------
+template <int H>
+struct Geo {
+    static_assert(H == 1 || H == 2 || H == 4, "tcgen05 path: H in {1, 2, 4}");
+    static constexpr int kRowF = H * kDim;              // floats per node row
+    static constexpr int kRowB = kRowF * 4;             // bytes per node row
+    // pass 1: the UMMA is M = N = 128 = two 64-wide MN blocks.  A block is a head (H >= 2) or, for H = 1, one of the
+    // two 16-node halves of a 32-node stage (both halves accumulate S; the two diagonal blocks are added at the end).
+    static constexpr int kBlocks = H < 2 ? 2 : H;
+    static constexpr int kPairs = kBlocks / 2;
+    static constexpr int kNodes = 16 * kBlocks / H;     // nodes per stage (32 for H = 1, else 16)
+    static constexpr int kBlockTile = 16 * 128;         // [16 nodes][64 bf16]
+    static constexpr int kOp = kBlocks * kBlockTile;    // one operand (Khi | Klo | Vhi | Vlo) of a stage
+    static constexpr int kOpStage = 4 * kOp;
+    static constexpr int kStgT = kNodes * kRowB;        // fp32 staging bytes of one tensor of a stage (= kBlocks * 4 KB)
+    static constexpr int kStg = 3 * kStgT;              // K | V | Q
+    static constexpr int kNSG = 3, kNO = 2;             // staging / operand ring depths
+    static constexpr int kSmem1 = kNSG * kStg + kNO * kOpStage + 1024;
+    static constexpr int kChunksPerRow = kRowB / 16;    // 16-byte chunks per node row (16 H)
+    static constexpr int kChunksPerThread = kStgT / 16 / 256;   // = kBlocks (256 converter threads)
+    static constexpr int kTmemCols1 = kPairs * 128 < 32 ? 32 : kPairs * 128;
+    // partials layout [S | z | u | sq | sk]
+    static constexpr int offZ = H * kDim * kDim, offU = offZ + H * kDim, offSq = offU + H * kDim, kP = offSq + 2;
+    // pass 2
+    static constexpr int kBBytes = H * 2 * 80 * 128;    // prepared B operands: per head hi | lo, 80 rows x 128 B
+};
+
+constexpr int kBOp = 80 * 128;                        // one (head, hi|lo) B-operand tile of pass 2
+using ShardArgs = CommPeers;  // multi-GPU: peer-mapped LL exchange buffers (common.cuh, csrc/comm.cu)
+constexpr int kThreadsT = 10 * 32;                    // pass 1: warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
+constexpr int kSlices = 148;                          // column slices of the record for the fused cross-CTA sum
+
+struct ReduceArgs1 {
+    const float *q, *k, *v;
+    int64_t N;
+    int rows_per_cta;
+    float* ws;                    // per-CTA records [grid][ws_len]
+    int64_t ws_len;
+    unsigned long long* flags;    // [grid] record-ready flags
+    unsigned long long epoch;
+    float* partials;
+    uint8_t* prepared;            // optional pass-2 operand image
+    int l2_hints;
+    ShardArgs sh;
+    uint64_t* dbg;
+    // backward (BWD): q -> A role, g -> B role (scaled to dnum = g/den on the fly), out -> third stream
+    const float* fwd_partials;    // forward partials (S, z, u, sq, sk)
+    float n_total;
+    float* rowscal;               // [N][H][2] = (1/den, dden) per (node, head), consumed by the dq kernel
+    float* vbar;                  // fwd, optional: mean over heads of V, [N][64] (feeds the gcn SpMM of the fused layer)
+};
+
+
+constexpr int kTile2 = 128;                           // rows per tile = UMMA M
+constexpr int kQOp = kTile2 * 128;                    // 16 KB: [128 rows][64 bf16] of one head
+constexpr int kStage2 = 2 * kQOp;                     // Qhi | Qlo
+constexpr int kNS2 = 3;
+constexpr int kBN = 80;                               // UMMA N: 64 columns of S + z column + padding
+constexpr int kNAcc = 4, kAccCols = 128;              // TMEM accumulator ring (4 x 128 columns)
+constexpr int kOutBox = 32 * 128;                     // TMA store box: 32 rows x 32 floats, 128B swizzle
+constexpr int kOutStage = 4 * 2 * kOutBox;            // per epilogue warp: two boxes (column halves of a head)
+template <int H>
+constexpr int smem2_bytes() { return Geo<H>::kBBytes + kNS2 * kStage2 + kOutStage + H * kDim * 4 + 1024; }
+
+
+struct FusedArgs {
+    ReduceArgs1 r;            // pass 1 (+ tail, exchange) arguments; r.prepared = global scratch for the B-operand image (required)
+    float* out;
+    int store_hint, reverse;
+    int pf_tiles;             // Q tiles of this CTA's rows prefetched into L2 while the tail runs (HBM is idle there)
+    unsigned long long* flags2;   // [grid] second grid barrier (B image complete)
+};
+template <int H>
+constexpr int smem_fused_bytes() { return (Geo<H>::kSmem1 > smem2_bytes<H>() ? Geo<H>::kSmem1 : smem2_bytes<H>()); }
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+
+int tc_grid(int64_t units) {
+    const int sms = sm_count();
+    return (int)(units < sms ? (units < 1 ? 1 : units) : sms);
+}
+
+// Row partition shared by both passes: contiguous ranges of whole 128-row tiles, one per CTA.
+int tc_rows_per_cta(int64_t N, int H, int* grid) {
+    (void)H;      // whole 128-row tiles per CTA: a multiple of the pass-1 stage (16 or 32 nodes) for every H
+    int g = tc_grid((N + kTile2 - 1) / kTile2);
+    int64_t rpc = (N + g - 1) / g;
+    rpc = (rpc + kTile2 - 1) / kTile2 * kTile2;
+    g = (int)((N + rpc - 1) / rpc);
+    *grid = g;
+    return (int)rpc;
+}
+
+// DIF_TC_DEBUG_TIMES=1: per-CTA %globaltimer stamps, summarised on stderr after a device sync (debug only)
+uint64_t* dbg_buffer() {
+    static uint64_t* buf = nullptr;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DIF_TC_DEBUG_TIMES"); on = (e && atoi(e)) ? 1 : 0; }
+    if (!on) return nullptr;
+    if (!buf) cudaMalloc(&buf, 256 * kDbgSlots * sizeof(uint64_t));
+    cudaMemset(buf, 0, 256 * kDbgSlots * sizeof(uint64_t));
+    return buf;
+}
+void dbg_report(const char* name, uint64_t* buf, int grid) {
+    if (!buf) return;
+    cudaDeviceSynchronize();
+    static uint64_t h[256 * kDbgSlots];
+    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+    uint64_t t0 = ~0ull;
+    for (int b = 0; b < grid; ++b) if (h[b * kDbgSlots] && h[b * kDbgSlots] < t0) t0 = h[b * kDbgSlots];
+    fprintf(stderr, "[%s] slot: min/avg/max us since first CTA start\n", name);
+    for (int s = 0; s < kDbgSlots; ++s) {
+        double mn = 1e30, mx = 0, sum = 0; int n = 0;
+        for (int b = 0; b < grid; ++b) { if (!h[b * kDbgSlots + s]) continue; double t = (h[b * kDbgSlots + s] - t0) * 1e-3; mn = t < mn ? t : mn; mx = t > mx ? t : mx; sum += t; ++n; }
+        if (n) fprintf(stderr, "  stamp %d: %7.2f %7.2f %7.2f  (n=%d)\n", s, mn, sum / n, mx, n);
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+
+// Launch of a persistent kernel whose CTAs synchronise with each other through global flags (grid <= #SMs, 1 CTA/SM).
+//   DIF_TC_LAUNCH=0 (default) cooperative launch: the runtime guarantees co-residency or refuses the launch
+//   DIF_TC_LAUNCH=1           plain launch (co-resident in practice when nothing else occupies the SMs; checked once
+//                             against the occupancy calculator) -- saves the cooperative-launch overhead
+//   DIF_TC_LAUNCH=2           plain launch + programmatic dependent launch: the kernel's prologue (barrier init, TMEM
+//                             allocation) overlaps the tail of the previous kernel in the stream; the kernels execute
+//                             griddepcontrol.wait before their first global access
+inline int launch_persistent(const void* kernel, int grid, int threads, size_t smem, cudaStream_t st, void** args) {
+    static const int mode = env_int("DIF_TC_LAUNCH", 0);
+    if (mode == 0) {
+        DIF_CUDA_OK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), args, smem, st));
+        return DIF_OK;
+    }
+    int nb = 0;
+    DIF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
+    DIF_REQUIRE(nb >= 1 && grid <= sm_count(), DIF_ECUDA, "persistent kernel cannot be co-resident (grid %d, %d CTA/SM)", grid, nb);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = mode == 2 ? 1 : 0;
+    DIF_CUDA_OK(cudaLaunchKernelExC(&cfg, kernel, args));
+    return DIF_OK;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int64_t tc_ws_len(int H) { return (SimpleLayout{H, H, kDim, kDim}.len() + 7) & ~(int64_t)7; }   // 32-byte aligned records (256-bit stores)
+
+// workspace: [records grid x ws_len f32][flags (grid + 1) u64][flags2 grid u64][pad to 128][B-operand image]
+int64_t fused_ws_prepared_off(int grid, int64_t ws_len) {
+    const int64_t off = (int64_t)grid * ws_len * 4 + (int64_t)(2 * grid + 1) * 8;
+    return (off + 127) & ~(int64_t)127;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Fused tail of a one-kernel forward, executed by the 128 threads of the four tail / epilogue warps (te = 0..127,
+// ew = warp % 4 = TMEM lane quadrant).  On entry: all pass-1 MMAs have completed and z, u, sum q^2, sum k^2 of this CTA
+// are already in its record `rec`.  The function
+//   1. drains the S accumulators (TMEM) into the record and publishes it (flag = epoch, release),
+//   2. waits for every CTA's record (all CTAs are resident: 1 CTA/SM, grid <= #SMs), reads "its" column slices of all
+//      records from L2 and sums them in a fixed order (fp64) -- deterministic, no float atomics,
+//   3. multi-GPU: exchanges each slice with the peers (LL push over NVLink, common.cuh) and adds the ranks in rank order,
+//   4. writes the reduced partials and the pass-2 B-operand image (bf16 hi/lo, 128B-swizzled, un-scaled) to global memory,
+//   5. runs a second grid barrier (flags2) after which partials and image are complete and visible to every CTA.
+// `red` : >= 64*65 floats of shared scratch when H == 1 (block halves of S), unused otherwise.
+// Uses named barrier 2 (128 threads).  No shared memory of the pipelines is touched: the Q prefetch of pass 2 may run.
+// ------------------------------------------------------------------------------------------
+template <int H>
+__device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long long* flags2, float* rec, int te, int ew, int lane,
+                                           uint32_t tmem, bool have_rows, float* red) {
+    using G = Geo<H>;
+    uint64_t* dbg = a.dbg;
+    if (te == 0)
+        for (int64_t i = G::kP; i < a.ws_len; ++i) rec[i] = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < G::kPairs; ++p) {
+        const int wq = ew, hp = wq >> 1, m = (wq * 32 + lane) & 63;
+        uint32_t r[2][32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (have_rows) {
+                tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + p * 128 + hp * 64 + c * 32, r[c]);
+                tmem_ld_wait32(r[c]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[c][j] = 0u;
+            }
+        }
+        if (H == 1) {
+            if (hp == 1) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) red[m * 65 + c * 32 + j] = __uint_as_float(r[c][j]);
+            }
+            bar_sync_named(2, 128);
+            if (hp == 0) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[c][j] = __float_as_uint(__uint_as_float(r[c][j]) + red[m * 65 + c * 32 + j]);
+            }
+        }
+        if (H != 1 || hp == 0) {
+            const int blk = (H == 1) ? 0 : 2 * p + hp;
+            float* dst = rec + ((int64_t)blk * kDim + m) * kDim;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 :: "l"(dst + c * 32 + j), "r"(r[c][j]), "r"(r[c][j + 1]), "r"(r[c][j + 2]), "r"(r[c][j + 3]),
+                                    "r"(r[c][j + 4]), "r"(r[c][j + 5]), "r"(r[c][j + 6]), "r"(r[c][j + 7]) : "memory");
+        }
+    }
+    tc_fence_before();
+    __threadfence();
+    bar_sync_named(2, 128);
+    if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 5] = gtime();
+    const int grid = gridDim.x;
+    const unsigned long long gen = *reinterpret_cast<volatile unsigned long long*>(a.flags + grid);
+    const unsigned long long epoch = a.epoch + gen * 0x9E3779B97F4A7C15ull;
+    if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(epoch) : "memory");
+    const int chunk = (int)((((a.ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
+    const ShardArgs& sh = a.sh;
+    const bool sharded = sh.world > 1;
+    const int xslot = (int)(sh.seq & 1);
+    if (sharded && blockIdx.x == 0 && te == 0) comm_check_status(sh);
+    bool waited = false;
+    for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
+        const int64_t j0 = (int64_t)sl * chunk;
+        const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
+        if (slice <= 0) break;
+        if (!waited) {
+            for (int r = te; r < grid; r += 128) {
+                unsigned long long f;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
+                } while (f != epoch);
+            }
+            bar_sync_named(2, 128);                      // every record is published and (through the acquiring threads) visible
+            if (blockIdx.x == 0 && te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + grid) = gen + 1;
+            waited = true;
+            if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 8] = gtime();
+        }
+        const int64_t j = j0 + te;
+        const bool live = te < slice && j < G::kP;
+        float local = 0.f;
+        if (live) {
+            // element j of every record, straight from L2 (ld.cg: never a stale L1 line), 16 loads in flight; four
+            // independent fp64 chains (records r = 4i + k), combined in a fixed order: deterministic
+            const float* col = a.ws + j;
+            const int64_t ld = a.ws_len;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int r = 0;
+            for (; r + 15 < grid; r += 16) {
+                float x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = __ldcg(col + (int64_t)(r + i) * ld);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) { a0 += (double)x[i]; a1 += (double)x[i + 1]; a2 += (double)x[i + 2]; a3 += (double)x[i + 3]; }
+            }
+            for (; r + 3 < grid; r += 4) {
+                const float x0 = __ldcg(col + (int64_t)(r + 0) * ld), x1 = __ldcg(col + (int64_t)(r + 1) * ld);
+                const float x2 = __ldcg(col + (int64_t)(r + 2) * ld), x3 = __ldcg(col + (int64_t)(r + 3) * ld);
+                a0 += (double)x0; a1 += (double)x1; a2 += (double)x2; a3 += (double)x3;
+            }
+            for (; r < grid; ++r) a0 += (double)__ldcg(col + (int64_t)r * ld);
+            local = (float)((a0 + a1) + (a2 + a3));
+        }
+        float sum = local;
+        if (sharded && live) {
+            const uint32_t tag = (uint32_t)sh.seq;
+            for (int p = 1; p < sh.world; ++p) {
+                int r = sh.rank + p;
+                if (r >= sh.world) r -= sh.world;
+                comm_ll_send(comm_ll_ptr(sh.bufs[r], sh.lenpad, xslot, sh.rank) + j, local, tag);
+            }
+            sum = 0.f;
+            for (int r = 0; r < sh.world; ++r)
+                sum += r == sh.rank ? local : comm_ll_recv(comm_ll_ptr(sh.bufs[sh.rank], sh.lenpad, xslot, r) + j, tag, sh);
+        }
+        if (live) {
+            a.partials[j] = sum;
+            if (j < G::offU) {
+                int h, n, m;
+                if (j < G::offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
+                else { h = (int)(j - G::offZ) >> 6; m = (int)(j - G::offZ) & 63; n = kDim; }
+                const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(sum - __bfloat162float(hi));
+                uint8_t* img = a.prepared + (size_t)h * 2 * kBOp + sw128(n, m >> 3) + (m & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(img) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(img + kBOp) = lo;
+            }
+        }
+    }
+    if (blockIdx.x == grid - 1) {
+        for (int i = te; i < H * 2 * 15 * 8; i += 128) {
+            const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
+            *reinterpret_cast<uint4*>(a.prepared + (size_t)t * kBOp + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    // ---- second grid barrier: the B-operand image and the partials are complete
+    if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 9] = gtime();
+    __threadfence();
+    bar_sync_named(2, 128);
+    const unsigned long long epoch2 = epoch + 1;
+    if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flags2 + blockIdx.x), "l"(epoch2) : "memory");
+    for (int r = te; r < grid; r += 128) {
+        unsigned long long f;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags2 + r) : "memory");
+        } while (f != epoch2);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    bar_sync_named(2, 128);
+    if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 6] = gtime();
+}
+
+}  // namespace
+}  // namespace dif

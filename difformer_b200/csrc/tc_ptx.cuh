@@ -13,6 +13,7 @@ namespace {
 constexpr int kDim = 64;
 constexpr int kWarps = 13;
 constexpr int kThreadsTC = kWarps * 32;
+constexpr int kDbgSlots = 16;                       // per-CTA %globaltimer stamps of the debug timeline
 
 // ---- descriptor conventions (verified on hardware by csrc/probe_umma.cu) --------------------
 constexpr uint32_t kSwizzle128 = 2;
@@ -28,7 +29,7 @@ __device__ __forceinline__ uint64_t gtime() {
 }
 #define DIF_STAMP(buf, slot)                                                        \
     do {                                                                            \
-        if ((buf) != nullptr && threadIdx.x == 0) (buf)[blockIdx.x * 8 + (slot)] = gtime(); \
+        if ((buf) != nullptr && threadIdx.x == 0) (buf)[blockIdx.x * kDbgSlots + (slot)] = gtime(); \
     } while (0)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -193,6 +194,10 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 :: "r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -111,6 +111,7 @@ def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_p
 
 
 _FUSED_FORWARD = True
+_DTYPES = {torch.float32: _lib.DIF_DTYPE_F32, torch.bfloat16: _lib.DIF_DTYPE_BF16, torch.float16: _lib.DIF_DTYPE_F16}
 
 
 def set_fused_forward(on: bool) -> None:
@@ -130,8 +131,10 @@ def simple_forward(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, n_total
     if wsb <= 0:
         return None
     dev = qs.device
+    if not (qs.dtype == ks.dtype == vs.dtype) or qs.dtype not in _DTYPES:
+        raise TypeError(f"difformer_b200: qs/ks/vs must share one of float32 / bfloat16 / float16, got {qs.dtype}, {ks.dtype}, {vs.dtype}")
     partials = torch.empty(int(lib.dif_simple_partials_len(H, Hv, M, D)), dtype=torch.float32, device=dev)
-    out = torch.empty((N, H, D), dtype=torch.float32, device=dev)
+    out = torch.empty((N, H, D), dtype=qs.dtype, device=dev)
     ws = workspace(dev, wsb)
     if exchange is not None:
         exchange.raise_if_failed()
@@ -140,7 +143,7 @@ def simple_forward(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, n_total
     else:
         peers, rank, world, seq = None, 0, 1, 0
     with torch.cuda.device(dev):
-        check(lib.dif_simple_forward(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, H, Hv, M, D, float(N if n_total is None else n_total),
+        check(lib.dif_simple_forward(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), _DTYPES[qs.dtype], N, H, Hv, M, D, float(N if n_total is None else n_total),
                                      partials.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), peers, rank, world, seq, _stream(qs)),
               "dif_simple_forward")
     return out, partials
@@ -214,30 +217,77 @@ class _SimpleAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         qs, ks, vs, out, partials = ctx.saved_tensors
+        return (*_simple_backward(qs, ks, vs, out, partials, _f32c(g), ctx.n_tot, ctx.group), None, None)
+
+
+def _simple_backward(qs, ks, vs, out, partials, g, n_tot, group):
+    """Analytic backward of 'simple'  on fp32 tensors: pass 1 (dS, dz, du, t_q) -> [all-reduce] -> dq, dk, dv."""
+    N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+    dev = qs.device
+    bwd = torch.zeros(lib.dif_simple_bwd_partials_len(H, M, D), dtype=torch.float32, device=dev)
+    ws = workspace(dev, lib.dif_simple_workspace_bytes(N, H, Hv, M, D))
+    dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
+    rsl = int(lib.dif_simple_bwd_rowscal_len(N, H, Hv, M, D)) if _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC else 0
+    rowscal = torch.empty(rsl, dtype=torch.float32, device=dev) if rsl > 0 else None    # tcgen05 backward scratch
+    rs_ptr = None if rowscal is None else rowscal.data_ptr()
+    with torch.cuda.device(dev):
+        st = _stream(qs)
+        check(lib.dif_simple_bwd_reduce(qs.data_ptr(), g.data_ptr(), out.data_ptr(), partials.data_ptr(), n_tot,
+                                        N, H, Hv, M, D, bwd.data_ptr(), rs_ptr, ws.data_ptr(), ws.numel(), _SIMPLE_IMPL, st),
+              "dif_simple_bwd_reduce")
+        xch = getattr(group, "exchange", None)
+        if xch is not None:
+            bwd = xch(bwd.numel(), dev).allreduce(bwd)
+        else:
+            _allreduce(bwd, group)
+        check(lib.dif_simple_bwd_apply(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
+                                       partials.data_ptr(), bwd.data_ptr(), rs_ptr, n_tot, N, H, Hv, M, D,
+                                       dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _SIMPLE_IMPL, st),
+              "dif_simple_bwd_apply")
+    return dq, dk, dv
+
+
+class _SimpleAttention16(torch.autograd.Function):
+    """'simple' on bfloat16 / float16 node tensors (the Linear outputs under autocast): the forward runs the 16-bit one-kernel
+    path (dif_simple_forward with DIF_DTYPE_BF16/F16: TMA-landed tiles go straight to the tensor cores, fp32 accumulation and
+    partials, 16-bit output -- half the HBM bytes).  Shapes outside the tcgen05 set compute in fp32 and round the result.
+    The backward up-casts the saved tensors and runs the fp32 kernels; gradients are returned in the input dtype."""
+
+    @staticmethod
+    def forward(ctx, qs, ks, vs, group, n_total):
+        _need_cuda(qs, ks, vs)
+        qs, ks, vs = qs.contiguous(), ks.contiguous(), vs.contiguous()
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
-        g = _f32c(g)
-        dev = qs.device
-        bwd = torch.zeros(lib.dif_simple_bwd_partials_len(H, M, D), dtype=torch.float32, device=dev)
-        ws = workspace(dev, lib.dif_simple_workspace_bytes(N, H, Hv, M, D))
-        dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
-        rsl = int(lib.dif_simple_bwd_rowscal_len(N, H, Hv, M, D)) if _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC else 0
-        rowscal = torch.empty(rsl, dtype=torch.float32, device=dev) if rsl > 0 else None    # tcgen05 backward scratch
-        rs_ptr = None if rowscal is None else rowscal.data_ptr()
-        with torch.cuda.device(dev):
-            st = _stream(qs)
-            check(lib.dif_simple_bwd_reduce(qs.data_ptr(), g.data_ptr(), out.data_ptr(), partials.data_ptr(), ctx.n_tot,
-                                            N, H, Hv, M, D, bwd.data_ptr(), rs_ptr, ws.data_ptr(), ws.numel(), _SIMPLE_IMPL, st),
-                  "dif_simple_bwd_reduce")
+        if N != L:
+            raise ValueError("kernel='simple' requires N == L (difformer.py:22,29)")
+        xch = getattr(group, "exchange", None)
+        n_tot = float(N if n_total is None else n_total)
+        nccl = xch is None and group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+        ex = xch(int(lib.dif_simple_partials_len(H, Hv, M, D)), qs.device) if xch is not None else None
+        one = None if nccl else simple_forward(qs, ks, vs, n_tot, ex)
+        if one is not None:
+            out, partials = one
+        else:
+            with torch.no_grad():
+                o32 = _SimpleAttention.apply(qs.float(), ks.float(), vs.float(), group, n_total)
+            out, partials = o32.to(qs.dtype), None
+        ctx.save_for_backward(qs, ks, vs, out, partials)
+        ctx.group, ctx.n_tot = group, n_tot
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qs, ks, vs, out, partials = ctx.saved_tensors
+        q32, k32, v32 = qs.float(), ks.float(), vs.float()
+        if partials is None:
+            partials = simple_partials(q32, k32, v32)
             xch = getattr(ctx.group, "exchange", None)
             if xch is not None:
-                bwd = xch(bwd.numel(), dev).allreduce(bwd)
+                partials = xch(partials.numel(), qs.device).allreduce(partials)
             else:
-                _allreduce(bwd, ctx.group)
-            check(lib.dif_simple_bwd_apply(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(),
-                                           partials.data_ptr(), bwd.data_ptr(), rs_ptr, ctx.n_tot, N, H, Hv, M, D,
-                                           dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _SIMPLE_IMPL, st),
-                  "dif_simple_bwd_apply")
-        return dq, dk, dv, None, None
+                _allreduce(partials, ctx.group)
+        dq, dk, dv = _simple_backward(q32, k32, v32, out.float(), partials, g.float().contiguous(), ctx.n_tot, ctx.group)
+        return dq.to(qs.dtype), dk.to(ks.dtype), dv.to(vs.dtype), None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -325,12 +375,14 @@ def full_attention_conv(qs, ks, vs, kernel, output_attn=False, *, group=None, n_
             raise NotImplementedError("row-sharded propagation needs M, D <= 128 (the native kernels)")
         out = _wide_torch_ops(qs, ks, vs, kernel, n_total)
         return (out, _dense_attention(qs, ks, kernel)) if output_attn else out
+    lp = qs.dtype in (torch.bfloat16, torch.float16)
     if kernel == "simple":
-        out = _SimpleAttention.apply(qs, ks, vs, group, n_total)
+        out = (_SimpleAttention16 if lp else _SimpleAttention).apply(qs, ks, vs, group, n_total)
     elif kernel == "sigmoid":
         if group is not None:
             raise NotImplementedError("kernel='sigmoid' is replicas-only across GPUs (SURVEY.md 8e)")
-        out = _SigmoidAttention.apply(qs, ks, vs)
+        # 16-bit inputs: the 'sigmoid' kernels compute in fp32 (the forward already splits every operand into bf16 hi + lo)
+        out = _SigmoidAttention.apply(qs.float(), ks.float(), vs.float()).to(qs.dtype) if lp else _SigmoidAttention.apply(qs, ks, vs)
     else:
         raise ValueError(f"unknown kernel {kernel!r} (expected 'simple' or 'sigmoid')")
     if output_attn:

@@ -41,6 +41,11 @@ extern "C" {
 #define DIF_ECUDA (-3)
 
 /* kernel implementation selector for the 'simple' path */
+/* element type of the node tensors (partials are always fp32) */
+#define DIF_DTYPE_F32 0
+#define DIF_DTYPE_BF16 1
+#define DIF_DTYPE_F16 2
+
 #define DIF_IMPL_AUTO 0     /* tcgen05 path when the shape qualifies, else generic */
 #define DIF_IMPL_GENERIC 1  /* FFMA kernels, any H, M%4==0, D%4==0, M,D <= 128 */
 #define DIF_IMPL_TCGEN05 2  /* tcgen05/TMEM kernels: M == D == 64, Hv == H, H in {1, 2, 4} */
@@ -103,11 +108,14 @@ DIF_API int dif_simple_apply(const float* q, const float* partials, const void* 
  * of pass 2 are prefetched while the sum is in flight.  out[N,H,D] = full_attention_conv(q,k,v,'simple'); `partials`
  * receives the (all-reduced) pass-1 partials, which the backward needs.  n_total = global row count (= N unsharded).
  * `workspace` must be 128-byte aligned.  peer_bufs / rank / world / seq as in dif_simple_reduce_allreduce (NULL, 0, 1, 0
- * for a single GPU).  Other shapes return DIF_EUNSUPPORTED: call dif_simple_reduce + dif_simple_apply. */
+ * for a single GPU).  Other shapes return DIF_EUNSUPPORTED: call dif_simple_reduce + dif_simple_apply.
+ * `dtype` = element type of q, k, v AND out: DIF_DTYPE_F32, or DIF_DTYPE_BF16 / DIF_DTYPE_F16 (the Linear outputs under
+ * autocast): the 16-bit kernel feeds the TMA-landed tiles straight to the tensor cores (no conversion pass, exact products,
+ * fp32 accumulation and fp32 partials) and moves 2048 instead of 4096 algorithmic bytes per node at H = 4, D = 64. */
 DIF_API int64_t dif_simple_forward_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
-DIF_API int dif_simple_forward(const float* q, const float* k, const float* v,
+DIF_API int dif_simple_forward(const void* q, const void* k, const void* v, int dtype,
                        int64_t N, int H, int Hv, int M, int D, double n_total,
-                       float* partials, float* out, void* workspace, int64_t workspace_bytes,
+                       float* partials, void* out, void* workspace, int64_t workspace_bytes,
                        void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream);
 
 /* Backward of the 'simple' path (derived analytically; the reference uses autograd).

@@ -192,6 +192,54 @@ def test_one_kernel_forward_equals_two_pass(h, n):
     assert torch.equal(o1, o2) and torch.equal(qb.grad, qa.grad) and torch.equal(kb.grad, ka.grad) and torch.equal(vb.grad, va.grad)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("h", [1, 2, 4])
+@pytest.mark.parametrize("n", [1, 33, 4097, 50000])
+def test_simple_16bit_io(dtype, h, n):
+    """bf16 / fp16 node tensors (the Linear outputs under autocast): the 16-bit one-kernel forward (TMA-landed tiles straight
+    into tcgen05, fp32 accumulation) against the fp64 oracle evaluated on the SAME 16-bit-rounded inputs: the fp32
+    partials (S, z, u, norms) at 1e-4, the output against the oracle's output rounded to the I/O type."""
+    q, k, v = (t.to(dtype) for t in O.synthetic_qkv(n, h, 64, seed=17 * h + n, adversarial=True))
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    res = ops.simple_forward(qg, kg, vg)
+    assert res is not None
+    out, flat = res
+    assert out.dtype == dtype and flat.dtype == torch.float32
+    qd, kd, vd = q.double(), k.double(), v.double()
+    want_p = O.simple_partials(qd, kd, vd)
+    S, z, u, sq, sk = _unpack(flat, h, h, 64, 64)
+    assert O.rel_err(S, want_p["S"]) < 1e-4 and O.rel_err(z, want_p["z"]) < 1e-4 and O.rel_err(u, want_p["u"]) < 1e-4
+    assert abs(float(sq) / float(want_p["sq"]) - 1) < 1e-5 and abs(float(sk) / float(want_p["sk"]) - 1) < 1e-5
+    want = O.simple_apply(qd, want_p)
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert O.rel_err(out.double(), want) < eps                                  # within the rounding of the output type
+    assert O.rel_err(out.double(), want.to(dtype).double()) < 0.25 * eps         # and mostly the very same rounded values
+    # repeated calls are bit-identical (deterministic; exercises the barrier epochs)
+    assert torch.equal(ops.simple_forward(qg, kg, vg)[0], out)
+    # the public op: forward = this kernel, backward = fp32 kernels on the up-cast tensors, gradients in the input type
+    qa, ka, va = (t.clone().requires_grad_(True) for t in (qg, kg, vg))
+    o = difformer.full_attention_conv(qa, ka, va, "simple")
+    assert torch.equal(o, out)
+    g = torch.randn(n, h, 64, generator=torch.Generator().manual_seed(3))
+    o.backward(dev(g).to(dtype))
+    dq, dk, dv = O.simple_attention_backward(qd, kd, vd, g.to(dtype).double())
+    for got, w in zip((qa.grad, ka.grad, va.grad), (dq, dk, dv)):
+        assert got.dtype == dtype and O.rel_err(got.double(), w) < 4 * eps
+
+
+def test_simple_16bit_other_shapes_and_sigmoid():
+    """16-bit inputs outside the tcgen05 shapes (and kernel='sigmoid') compute in fp32 and round the result."""
+    for (n, h, hv, d) in ((300, 3, 3, 32), (65, 4, 1, 64)):
+        q, k, v = (t.bfloat16() for t in O.synthetic_qkv(n, h, d, seed=n, hv=hv, adversarial=True))
+        out = difformer.full_attention_conv(dev(q), dev(k), dev(v), "simple")
+        assert out.dtype == torch.bfloat16
+        assert O.rel_err(out.double(), O.simple_attention(q.double(), k.double(), v.double())) < 2.0 ** -8
+    q, k, v = (t.half() for t in O.synthetic_qkv(200, 2, 64, seed=5))
+    out = difformer.full_attention_conv(dev(q) * 0.25, dev(k) * 0.25, dev(v), "sigmoid")
+    assert out.dtype == torch.float16
+    assert O.rel_err(out.double(), O.sigmoid_attention((q * 0.25).double(), (k * 0.25).double(), v.double())) < 2.0 ** -10
+
+
 def test_simple_rejects_n_ne_l():
     q = torch.randn(10, 1, 64, device="cuda")
     with pytest.raises(ValueError, match="N == L"):

@@ -15,6 +15,9 @@ ap.add_argument("--tag", default="")
 ap.add_argument("--h", type=int, default=4)
 ap.add_argument("--noref", action="store_true")
 ap.add_argument("--fused", action="store_true", help="also time the one-kernel forward (dif_simple_forward)")
+ap.add_argument("--only-fused", action="store_true", help="time nothing but the one-kernel forward")
+ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
+ap.add_argument("--membw", action="store_true", help="plain-torch read / write / copy bandwidth of this GPU")
 a = ap.parse_args()
 ops.set_simple_impl(a.impl)
 H = a.h
@@ -35,6 +38,21 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
+if a.membw:
+    g = torch.empty(1 << 28, device="cuda").normal_(); g2 = torch.empty_like(g)
+    t_w = timeit(lambda: g2.zero_(), 20)
+    t_r = timeit(lambda: g.sum(), 20)
+    t_c = timeit(lambda: g2.copy_(g), 20)
+    print(f"1 GiB fp32: memset {g.numel()*4/t_w/1e3:5.0f} GB/s | sum (read) {g.numel()*4/t_r/1e3:5.0f} GB/s | copy {2*g.numel()*4/t_c/1e3:5.0f} GB/s (read+write)", flush=True)
+    sys.exit(0)
+if a.only_fused or a.dtype != "f32":
+    dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
+    q, k, v = q.to(dt), k.to(dt), v.to(dt)
+    assert ops.simple_forward(q, k, v) is not None
+    t_f = timeit(lambda: ops.simple_forward(q, k, v), a.iters)
+    Tb = T * q.element_size() // 4
+    print(f"{a.tag} dtype={a.dtype} H={H} n={a.n} one-kernel forward {t_f:7.1f} us  roofline(4T) {4*Tb/t_f/1e3/6571.2:5.3f}", flush=True)
+    sys.exit(0)
 part, prep = ops.simple_partials(q, k, v, with_prepared=True)
 t_red = timeit(lambda: ops.simple_partials(q, k, v, with_prepared=True), a.iters)
 t_app = timeit(lambda: ops.simple_apply(q, part, float(a.n), H, 64, prepared=prep), a.iters)
