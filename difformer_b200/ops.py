@@ -296,6 +296,10 @@ class _SimpleAttention16(torch.autograd.Function):
 class _SigmoidAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qs, ks, vs):
+        return _SigmoidAttention._run(ctx, qs, ks, vs)[0]
+
+    @staticmethod
+    def _run(ctx, qs, ks, vs):
         _need_cuda(qs, ks, vs)
         qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
@@ -306,7 +310,7 @@ class _SigmoidAttention(torch.autograd.Function):
             check(lib.dif_sigmoid_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), N, L, H, Hv, M, D,
                                       out.data_ptr(), rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream(qs)), "dif_sigmoid_fwd")
         ctx.save_for_backward(qs, ks, vs, out, rowsum)
-        return out
+        return out, rowsum
 
     @staticmethod
     def backward(ctx, g):
@@ -321,6 +325,21 @@ class _SigmoidAttention(torch.autograd.Function):
                                       rowsum.data_ptr(), N, L, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                       ws.data_ptr(), ws.numel(), _stream(qs)), "dif_sigmoid_bwd")
         return dq, dk, dv
+
+
+class _SigmoidAttentionRS(_SigmoidAttention):
+    """Same kernels; also hands out the row sums (non-differentiable) for callers that post-scale the rows."""
+
+    @staticmethod
+    def forward(ctx, qs, ks, vs):
+        out, rowsum = _SigmoidAttention._run(ctx, qs, ks, vs)
+        rowsum = rowsum.clone()                           # the saved tensor itself must not be handed out
+        ctx.mark_non_differentiable(rowsum)
+        return out, rowsum
+
+    @staticmethod
+    def backward(ctx, g, _g_rowsum):
+        return _SigmoidAttention.backward(ctx, g)
 
 
 def _dense_attention(qs, ks, kernel):
@@ -498,10 +517,28 @@ def gcn_conv(x, edge_index, edge_weight):
 # ----------------------------------------------------------------------------------------------
 # batched graphs (difformer-v2.py:80-111)
 # ----------------------------------------------------------------------------------------------
+_SEG_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
 def _seg_ptr(n_nodes: torch.Tensor, total: int, device) -> torch.Tensor:
+    """seg_ptr = [0, cumsum(n_nodes)] (int32, device).  Validated once per `n_nodes` tensor (storage + version): B >= 1 and
+    sum(n_nodes) == number of rows -- the reference would fail on a mismatch, the kernels would read or leave rows
+    uninitialised.  The one host read this costs is cached, like the reference's own `n_nodes.max().item()` per call."""
+    key = (n_nodes.data_ptr(), n_nodes._version, int(n_nodes.numel()), str(n_nodes.device), int(total), str(device))
+    hit = _SEG_CACHE.get(key)
+    if hit is not None:
+        _SEG_CACHE.move_to_end(key)
+        return hit[0]
     nn_ = n_nodes.to(device=device, dtype=torch.int64)
+    if nn_.numel() < 1:
+        raise ValueError("n_nodes is empty but there are rows to process")
     ptr = torch.zeros(nn_.numel() + 1, dtype=torch.int32, device=device)
     ptr[1:] = torch.cumsum(nn_, 0).to(torch.int32)      # one cumsum on device; no Python loops, no padding
+    if int(ptr[-1]) != int(total) or bool((nn_ < 0).any()):
+        raise ValueError(f"sum(n_nodes) = {int(ptr[-1])} does not match the {int(total)} rows of qs / ks / vs (or a count is negative)")
+    _SEG_CACHE[key] = (ptr, n_nodes)
+    while len(_SEG_CACHE) > 16:
+        _SEG_CACHE.popitem(last=False)
     return ptr
 
 
@@ -543,12 +580,45 @@ class _SegmentedSimple(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+def _segmented_sigmoid(qs, ks, vs, n_nodes):
+    """kernel='sigmoid' of the batched variant, reproduced literally (difformer-v2.py:113-135): the reference pads every graph
+    to max_node rows and contracts "abcd,ebcd->aebc", so node b of graph a attends to node b of EVERY graph e (padded slots are
+    zero rows: sigmoid(0) = 0.5 in the row sum, nothing in the value sum).  In the padded layout [B, max_node, H, D] that is
+    exactly the dense 'sigmoid' attention over N = L = B rows with max_node * H independent "heads", so the flash-style
+    sigmoid kernels run it as is (never materialising the reference's [B, B, max_node, H] tensors); the padding itself is
+    one index_copy / index_select on the device (no Python loops).  The reference's `+ 1e-9` on the row sums is applied as
+    the factor r / (r + 1e-9) on the output (treated as a constant by the backward: it differs from 1 by < 1e-8 unless every
+    score of a row is below about -18)."""
+    _need_cuda(qs, ks, vs)
+    N, L, H, Hv, M, D = _shapes(qs, ks, vs)
+    dev = qs.device
+    nn_ = n_nodes.to(device=dev, dtype=torch.int64)
+    B = int(nn_.numel())
+    if int(nn_.sum()) != N:                                  # the same host read the reference does for max_node (:9)
+        raise ValueError(f"sum(n_nodes) = {int(nn_.sum())} != number of rows {N}")
+    maxn = int(nn_.max())
+    start = torch.cumsum(nn_, 0) - nn_
+    batch = torch.repeat_interleave(torch.arange(B, device=dev), nn_, output_size=N)
+    idx = batch * maxn + (torch.arange(N, device=dev) - start[batch])            # row of node i in the padded [B*maxn] layout
+
+    def pad(t):
+        return torch.zeros((B * maxn,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev).index_copy(0, idx, t) \
+            .reshape(B, maxn * t.shape[1], t.shape[2])
+
+    out, rowsum = _SigmoidAttentionRS.apply(pad(qs), pad(ks), pad(vs))
+    out = out * (rowsum / (rowsum + 1e-9)).detach().unsqueeze(-1)
+    return out.reshape(B * maxn, H, D).index_select(0, idx)
+
+
 def segmented_full_attention(qs, ks, vs, kernel, n_nodes, *, group=None):
-    """Drop-in for TransConv.full_attention (difformer-v2.py:71-140), kernel='simple'."""
+    """Drop-in for TransConv.full_attention (difformer-v2.py:71-140)."""
+    if kernel == "sigmoid":
+        if group is not None:
+            raise NotImplementedError("v2 kernel='sigmoid' couples all graphs of the batch: replicas only across GPUs")
+        if int(qs.shape[0]) == 0:
+            return qs.new_empty((0, qs.shape[1], vs.shape[2]))
+        return _segmented_sigmoid(qs, ks, vs, n_nodes)
     if kernel != "simple":
-        if kernel == "sigmoid":
-            raise NotImplementedError("v2 kernel='sigmoid' (cross-graph same-slot attention, difformer-v2.py:113-135) "
-                                      "is a 'next' row of SURVEY.md 8f and is not built")
         raise ValueError(f"unknown kernel {kernel!r}")
     if int(qs.shape[0]) == 0:
         return qs.new_empty((0, qs.shape[1], vs.shape[2]))

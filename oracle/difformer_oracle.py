@@ -298,6 +298,34 @@ def segmented_simple_attention_backward(qs, ks, vs, n_nodes, g):
     return dq, dk, dv
 
 
+# --------------------------------------------------------------------------------------------
+# a-7  batched-graph 'sigmoid'   physical particle/difformer-v2.py:113-135
+# --------------------------------------------------------------------------------------------
+def segmented_sigmoid_attention(qs: Tensor, ks: Tensor, vs: Tensor, n_nodes: Tensor) -> Tensor:
+    """The reference pads every graph to max_node rows (:116-120) and contracts "abcd,ebcd->aebc" (:123): the score couples
+    graph a and graph e AT THE SAME PADDED SLOT b, i.e. node b of graph a attends to node b of every graph e (padded slots
+    are zero rows: sigmoid(0) = 0.5 in the row sum, zero in the value sum).  Row sums get +1e-9 (:127-128).  Restated slot
+    by slot without building the [B,B,M,H] tensors."""
+    nn_ = [int(t) for t in n_nodes]
+    B, maxn = len(nn_), max(nn_)
+    starts = [0]
+    for n in nn_:
+        starts.append(starts[-1] + n)
+    H, D = qs.shape[1], vs.shape[2]
+    out = torch.empty(qs.shape[0], H, D, dtype=qs.dtype)
+    for b in range(maxn):
+        has = [a for a in range(B) if b < nn_[a]]
+        idx = torch.tensor([starts[a] + b for a in has], dtype=torch.long)
+        qb = torch.zeros(B, H, qs.shape[2], dtype=qs.dtype)
+        kb, vb = torch.zeros_like(qb), torch.zeros(B, H, D, dtype=qs.dtype)
+        qb[has], kb[has], vb[has] = qs[idx], ks[idx], vs[idx]
+        p = torch.sigmoid(torch.matmul(qb.permute(1, 0, 2), kb.permute(1, 2, 0)))     # [H, B(a), B(e)]
+        att = p / (p.sum(-1, keepdim=True) + 1e-9)
+        ob = torch.matmul(att, vb.permute(1, 0, 2)).permute(1, 0, 2)                   # [B, H, D]
+        out[idx] = ob[has]
+    return out
+
+
 def difformer_v2_forward(sd: Dict[str, Tensor], x: Tensor, edge_index, n_nodes, *, hidden_channels,
                          num_layers=2, alpha=0.5, use_bn=True, use_residual=True, use_graph=True,
                          graph_weight=-1) -> Tensor:

@@ -151,6 +151,18 @@ def v2_cases(ref2):
     for k_, v_ in m.state_dict().items():
         d["sd_" + k_] = v_
     cases["v2_model_simple"] = _np(d)
+    # kernel='sigmoid' of the batched variant (difformer-v2.py:113-135): cross-graph attention between the nodes that share
+    # a padded slot; appended last so that the random draws of the cases above stay what they were
+    gen2 = torch.Generator().manual_seed(77)
+    nn2 = torch.tensor([4, 9, 1, 12, 7])
+    tot2 = int(nn2.sum())
+    for name, h, d, scale in (("v2_sigmoid_segments", 1, 64, 0.3), ("v2_sigmoid_segments_h2", 2, 32, 0.5)):
+        q, k, v = (torch.randn(tot2, h, d, generator=gen2) * s_ for s_ in (scale, scale, 1.0))
+        q, k, v = (t.clone().requires_grad_(True) for t in (q, k, v))
+        out = conv.full_attention(q, k, v, "sigmoid", nn2)
+        g = torch.randn(out.shape, generator=gen2)
+        out.backward(g)
+        cases[name] = _np(dict(q=q, k=k, v=v, n_nodes=nn2, out=out, g=g, dq=q.grad, dk=k.grad, dv=v.grad))
     return cases
 
 

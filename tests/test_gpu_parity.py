@@ -596,3 +596,72 @@ def test_v2_model_forward():
     out = m(dev(c["x"]), dev(c["edge_index"]), dev(c["n_nodes"]))
     assert O.rel_err(out, c["out"]) < TOL
     out.sum().backward()      # the particle harness trains through it
+
+
+@pytest.mark.parametrize("name", ["v2_sigmoid_segments", "v2_sigmoid_segments_h2"])
+def test_v2_sigmoid_matches_reference(name, sigmoid_impl):
+    """a-7: kernel='sigmoid' of the batched variant (cross-graph same-slot attention) reproduced literally: reference golden
+    forward + autograd gradients, through the flash-style sigmoid kernels on the padded-heads layout."""
+    c = V2[name]
+    q, k, v = (dev(c[n]).requires_grad_(True) for n in ("q", "k", "v"))
+    out = ops.segmented_full_attention(q, k, v, "sigmoid", dev(c["n_nodes"]))
+    assert O.rel_err(out, c["out"]) < TOL
+    out.backward(dev(c["g"]))
+    for got, want in ((q.grad, c["dq"]), (k.grad, c["dk"]), (v.grad, c["dv"])):
+        assert O.rel_err(got, want) < TOL
+    # a bigger ragged batch against the fp64 oracle
+    gen = torch.Generator().manual_seed(9)
+    nn_ = torch.randint(1, 30, (57,), generator=gen)
+    tot = int(nn_.sum())
+    q, k, v = O.synthetic_qkv(tot, 1, 64, seed=3)
+    got = ops.segmented_full_attention(dev(q) * 0.3, dev(k) * 0.3, dev(v), "sigmoid", dev(nn_))
+    assert O.rel_err(got, O.segmented_sigmoid_attention(q.double() * 0.3, k.double() * 0.3, v.double(), nn_)) < TOL
+
+
+def test_v2_rejects_inconsistent_n_nodes():
+    q = torch.randn(10, 1, 64, device="cuda")
+    with pytest.raises(ValueError, match="n_nodes"):
+        ops.segmented_full_attention(q, q, q, "simple", torch.tensor([3, 4], device="cuda"))
+    with pytest.raises(ValueError, match="n_nodes"):
+        ops.segmented_full_attention(q, q, q, "sigmoid", torch.tensor([3, 4], device="cuda"))
+
+
+def test_training_step_cuda_graph_capture():
+    """f-3: the whole training step (forward + backward through the hand-written kernels) captured with
+    torch.cuda.make_graphed_callables: the C ABI neither allocates nor synchronises, scratch comes from torch's allocator (the
+    graph's private pool while capturing) and the in-kernel grid barriers carry a device-side generation word, so replays are
+    valid.  Gradients of the replayed step must equal the eager ones."""
+    gen = torch.Generator().manual_seed(11)
+    n = 700
+    x = dev(torch.randn(n, 32, generator=gen))
+    ei = dev(O.synthetic_graph(n, 2000, seed=5))
+    for kern, heads in (("simple", 4), ("sigmoid", 1)):
+        torch.manual_seed(0)
+        m = difformer.DIFFormer(32, 64, 6, num_layers=2, num_heads=heads, kernel=kern, dropout=0.0, use_graph=True).cuda().train()
+        ref = difformer.DIFFormer(32, 64, 6, num_layers=2, num_heads=heads, kernel=kern, dropout=0.0, use_graph=True).cuda().train()
+        ref.load_state_dict(m.state_dict())
+        ops.graph_csr(ei, None, n)                              # the CSR build (one validation sync) happens outside the capture
+
+        class Step(torch.nn.Module):
+            def __init__(self, net):
+                super().__init__()
+                self.net = net
+
+            def forward(self, feats):
+                return self.net(feats, ei)
+
+        xs = x.clone().requires_grad_(True)
+        graphed = torch.cuda.make_graphed_callables(Step(m), (xs,))
+        for rep in range(2):
+            x_in = dev(torch.randn(n, 32, generator=gen)).requires_grad_(True)
+            out = graphed(x_in)
+            out.square().mean().backward()
+            x_ref = x_in.detach().clone().requires_grad_(True)
+            out_ref = ref(x_ref, ei)
+            out_ref.square().mean().backward()
+            assert O.rel_err(out, out_ref) < 1e-5, (kern, rep)
+            assert O.rel_err(x_in.grad, x_ref.grad) < 1e-4, (kern, rep)
+            for (name, p), (_, pr) in zip(m.named_parameters(), ref.named_parameters()):
+                assert O.rel_err(p.grad, pr.grad) < 1e-4, (kern, rep, name)
+            m.zero_grad(set_to_none=False)
+            ref.zero_grad(set_to_none=False)

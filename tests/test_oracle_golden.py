@@ -145,3 +145,16 @@ def test_vendored_reference_is_a_byte_copy():
         pytest.skip("needs both /root/reference and oracle/_ref")
     for rel in B.FILES:
         assert filecmp.cmp(os.path.join(B.SRC, rel), os.path.join(B.DST, rel), shallow=False)
+
+
+def test_v2_sigmoid_oracle_matches_reference_golden():
+    """a-7: the slot-by-slot restatement of the batched 'sigmoid' (difformer-v2.py:113-135) against the reference's outputs."""
+    v2 = load_golden("v2")
+    for name in ("v2_sigmoid_segments", "v2_sigmoid_segments_h2"):
+        c = v2[name]
+        got = O.segmented_sigmoid_attention(c["q"], c["k"], c["v"], c["n_nodes"])
+        assert O.rel_err(got, c["out"]) < 1e-5, name
+        q, k, v = (c[n].double().requires_grad_(True) for n in ("q", "k", "v"))     # autograd of the restatement = the reference's grads
+        O.segmented_sigmoid_attention(q, k, v, c["n_nodes"]).backward(c["g"].double())
+        for got_g, want in ((q.grad, c["dq"]), (k.grad, c["dk"]), (v.grad, c["dv"])):
+            assert O.rel_err(got_g, want) < 1e-4, name
