@@ -43,11 +43,17 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
     else:
         value = source_input.reshape(-1, 1, C)                      # difformer.py:120
     segmented = n_nodes is not None
+    shard = getattr(conv, "_row_shard", None)             # sharded.shard_model: these rows are a shard of a larger graph
+    if shard is not None and shard.world < 2:
+        shard = None
+    if shard is not None and (segmented or output_attn or conv.kernel != "simple"):
+        raise NotImplementedError("row-sharded propagation covers kernel='simple' (one all-reduce of the partials); 'sigmoid', "
+                                  "batched graphs and attention maps need every row: run them as replicas (SURVEY.md 8e)")
     use_source = getattr(conv, "use_source", False)
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
 
-    if (not output_attn) and (not segmented) and C <= ops._MAX_NATIVE_WIDTH and _fusable(conv.kernel, query, key, value, x_0,
+    if (not output_attn) and (not segmented) and shard is None and C <= ops._MAX_NATIVE_WIDTH and _fusable(conv.kernel, query, key, value, x_0,
                                                           None if residual is None else residual[1]):
         # ---- fused inference path: everything after the Linears is two kernels (+ one SpMM)
         q, k, v = ops._f32c(query), ops._f32c(key), ops._f32c(value)
@@ -81,10 +87,12 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         attention_output = ops.segmented_full_attention(query, key, value, conv.kernel, n_nodes)
     elif output_attn:
         attention_output, attn = ops.full_attention_conv(query, key, value, conv.kernel, True)
+    elif shard is not None:
+        attention_output = ops.full_attention_conv(query, key, value, conv.kernel, group=shard.attn_group, n_total=shard.n_total)
     else:
         attention_output = ops.full_attention_conv(query, key, value, conv.kernel)
     if conv.use_graph:
-        g = ops.gcn_conv(value, edge_index, edge_weight)
+        g = ops.gcn_conv(value, edge_index, edge_weight, shard=shard)
         final_output = w_attn * attention_output + w_gcn * g if gw > 0 else attention_output + g
     else:
         final_output = attention_output

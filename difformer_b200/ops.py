@@ -473,14 +473,21 @@ def graph_csr(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num
     return csr
 
 
-def spmm(csr: GraphCSR, x: torch.Tensor, transpose: bool = False, head_mean: bool = False) -> torch.Tensor:
+def spmm(csr: GraphCSR, x: torch.Tensor, transpose: bool = False, head_mean: bool = False, rows=None) -> torch.Tensor:
+    """out[r] = sum over the CSR slots of row r of val * x[idx].  `rows=(b, e)`: only the output rows [b, e) (a row shard of the
+    graph: x still holds every source row)."""
     N, Hx, D = x.shape
     if N != csr.N:
         raise ValueError(f"x has {N} rows, graph has {csr.N} nodes")
-    out = torch.empty((N, D) if head_mean else (N, Hx, D), dtype=torch.float32, device=x.device)
+    b, e = (0, N) if rows is None else (int(rows[0]), int(rows[1]))
+    if not (0 <= b <= e <= N):
+        raise ValueError(f"row range {rows} outside [0, {N}]")
+    out = torch.empty((e - b, D) if head_mean else (e - b, Hx, D), dtype=torch.float32, device=x.device)
+    if e == b:
+        return out
     rp, idx, val = (csr.rowptr_t, csr.dst_t, csr.val_t) if transpose else (csr.rowptr, csr.src, csr.val)
     with torch.cuda.device(x.device):
-        check(lib.dif_gcn_spmm(x.data_ptr(), rp.data_ptr(), idx.data_ptr(), val.data_ptr(), N, Hx, D,
+        check(lib.dif_gcn_spmm(x.data_ptr(), rp.data_ptr() + 4 * b, idx.data_ptr(), val.data_ptr(), e - b, Hx, D,
                                1 if head_mean else 0, out.data_ptr(), _stream(x)), "dif_gcn_spmm")
     return out
 
@@ -496,22 +503,35 @@ def head_mean(x: torch.Tensor) -> torch.Tensor:
 
 class _GCNConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, csr):
+    def forward(ctx, x, csr, rows):
         _need_cuda(x)
         x = _f32c(x)
-        ctx.csr = csr
-        return spmm(csr, x)
+        ctx.csr, ctx.rows = csr, rows
+        return spmm(csr, x, rows=rows)
 
     @staticmethod
     def backward(ctx, g):
-        return spmm(ctx.csr, _f32c(g), transpose=True), None
+        g = _f32c(g)
+        if ctx.rows is not None:            # row shard: only this rank's target rows carry a gradient
+            full = torch.zeros((ctx.csr.N,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+            full[ctx.rows[0]:ctx.rows[1]] = g
+            g = full
+        return spmm(ctx.csr, g, transpose=True), None, None
 
 
-def gcn_conv(x, edge_index, edge_weight):
-    """Drop-in for difformer.py:63-79: x [N,H,D] -> [N,H,D] (no grad to edge_index / edge_weight)."""
+def gcn_conv(x, edge_index, edge_weight, *, shard=None):
+    """Drop-in for difformer.py:63-79: x [N,H,D] -> [N,H,D] (no grad to edge_index / edge_weight).
+    `shard` (sharded.RowShard): x holds this rank's rows of an n_total-node graph, `edge_index` is the GLOBAL edge list: the
+    source rows are all-gathered over the process group and the SpMM covers this rank's target rows."""
     if x.dim() != 3:
         raise ValueError("x must be [N,H,D]")
-    return _GCNConv.apply(x, graph_csr(edge_index, edge_weight, x.shape[0]))
+    if shard is not None and shard.world > 1:
+        from .sharded import gather_rows
+        if x.shape[0] != shard.end - shard.begin:
+            raise ValueError(f"row shard expects {shard.end - shard.begin} local rows, got {x.shape[0]}")
+        x_all = gather_rows(x, shard.pg, shard.n_total)
+        return _GCNConv.apply(x_all, graph_csr(edge_index, edge_weight, shard.n_total), (shard.begin, shard.end))
+    return _GCNConv.apply(x, graph_csr(edge_index, edge_weight, x.shape[0]), None)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -171,3 +171,74 @@ class RowShardedAttention:
 
     def apply(self, qs, partials, hv: int, d: int) -> torch.Tensor:
         return ops.simple_apply(qs, partials, float(self.n_total), hv, d)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# module-level row sharding: DIFFormer / DIFFormerConv built by the reference harness (parse_method), run on a row shard
+# ----------------------------------------------------------------------------------------------------------------
+class _GatherRows(torch.autograd.Function):
+    """x_local [n_r, ...] on every rank -> x_all [n_total, ...] (rows in rank order); backward = reduce-scatter(sum) of the
+    gradient rows to their owners.  Shards differ by at most one row (shard_rows): padded to equal chunks for the collective."""
+
+    @staticmethod
+    def forward(ctx, x, group, n_total):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        sizes = [shard_rows(n_total, r, world) for r in range(world)]
+        chunk = max(e - b for b, e in sizes)
+        pad = x.new_zeros((chunk,) + tuple(x.shape[1:]))
+        pad[:x.shape[0]] = x
+        out = x.new_empty((world * chunk,) + tuple(x.shape[1:]))
+        dist.all_gather_into_tensor(out, pad, group=group)
+        ctx.group, ctx.sizes, ctx.chunk, ctx.rank = group, sizes, chunk, rank
+        if all(e - b == chunk for b, e in sizes):
+            return out
+        return torch.cat([out[r * chunk:r * chunk + (e - b)] for r, (b, e) in enumerate(sizes)], 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        world, chunk = len(ctx.sizes), ctx.chunk
+        g = g.contiguous()
+        padded = g.new_zeros((world * chunk,) + tuple(g.shape[1:]))
+        for r, (b, e) in enumerate(ctx.sizes):
+            padded[r * chunk:r * chunk + (e - b)] = g[b:e]
+        mine = g.new_empty((chunk,) + tuple(g.shape[1:]))
+        dist.reduce_scatter_tensor(mine, padded, op=dist.ReduceOp.SUM, group=ctx.group)
+        b, e = ctx.sizes[ctx.rank]
+        return mine[:e - b], None, None
+
+
+def gather_rows(x: torch.Tensor, group, n_total: int) -> torch.Tensor:
+    """All-gather of the row shards (autograd-aware); identity without a multi-rank group."""
+    if group is None or not dist.is_initialized() or dist.get_world_size(group) < 2:
+        return x
+    return _GatherRows.apply(x, group, int(n_total))
+
+
+class RowShard:
+    """What a `DIFFormer` needs to run on rows [begin, end) of an n_total-node graph (one process per GPU):
+      * 'simple' attention: pass 1 on the local rows, ONE all-reduce of the 67.6 KB partials (fused into the kernel over
+        NVLink with `nvlink=True`, NCCL otherwise), pass 2 on the local rows -- SURVEY.md 8e;
+      * `gcn_conv`: the target rows are local, their neighbours are anywhere: the value rows are all-gathered (T bytes over
+        NVLink) and the SpMM runs over this rank's rows of the CSR of the GLOBAL `edge_index` (replicated, built once and
+        cached); backward = transposed SpMM + reduce-scatter -- SURVEY.md 8f-2.
+    `edge_index` handed to the model stays the global edge list; `x` is the local row block."""
+
+    def __init__(self, n_total: int, group=None, nvlink: bool = True):
+        self.n_total = int(n_total)
+        self.pg = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.world = dist.get_world_size(self.pg) if self.pg is not None else 1
+        self.rank = dist.get_rank(self.pg) if self.pg is not None else 0
+        self.begin, self.end = shard_rows(self.n_total, self.rank, self.world)
+        # what ops.full_attention_conv takes as `group=`
+        self.attn_group = (RowShardComm(self.pg) if nvlink else self.pg) if self.world > 1 else None
+
+
+def shard_model(model, n_total: int, group=None, nvlink: bool = True) -> RowShard:
+    """Switch a `DIFFormer` (e.g. the one `parse_method` built) to row-sharded propagation: every rank then calls
+    `model(x_local, edge_index_global[, edge_weight])` with its rows [shard.begin, shard.end) of x and gets its rows of the
+    logits.  Parameters are replicated: wrap the model in DDP (or all-reduce the gradients) as usual.  Returns the RowShard."""
+    shard = RowShard(n_total, group, nvlink)
+    model._row_shard = shard
+    for conv in getattr(model, "convs", []):
+        conv._row_shard = shard
+    return shard

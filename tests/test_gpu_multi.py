@@ -61,6 +61,30 @@ for (n, h, hv, d) in ((20011, 4, 4, 64), (4999, 1, 1, 64), (3001, 3, 3, 32), (25
             assert torch.equal(mine, ref), "reduced partials differ between ranks"
             assert not attn.group.exchange(flat.numel(), dev).timed_out()
     assert O.rel_err(outs[True], outs[False]) < 1e-5
+# module level (SURVEY 8b/8e/8f-2): a DIFFormer as parse_method builds it, switched to row-sharded propagation by shard_model --
+# attention through the fused exchange, gcn_conv through the row all-gather -- against the same model run unsharded
+import copy
+import difformer
+from difformer_b200.sharded import shard_model
+torch.manual_seed(0)
+n, cin = 3001, 24
+x = torch.randn(n, cin)
+ei = O.synthetic_graph(n, 9000, seed=4).to(dev)
+ew = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(2)).to(dev)
+m = difformer.DIFFormer(cin, 64, 5, num_layers=2, num_heads=4, kernel="simple", dropout=0.0, use_graph=True, use_source=True).to(dev)
+ref = copy.deepcopy(m)
+out_ref = ref(x.to(dev), ei, ew)
+out_ref.square().sum().backward()
+for nvlink in (False, True):
+    ms = copy.deepcopy(m)
+    sh = shard_model(ms, n, dist.group.WORLD, nvlink=nvlink)
+    out = ms(x[sh.begin:sh.end].to(dev), ei, ew)
+    assert O.rel_err(out, out_ref[sh.begin:sh.end]) < 1e-4, (nvlink, O.rel_err(out, out_ref[sh.begin:sh.end]))
+    out.square().sum().backward()
+    for (name, p), (_, pr) in zip(ms.named_parameters(), ref.named_parameters()):
+        g = p.grad.clone()
+        dist.all_reduce(g)                                   # what DDP would do with the replicated parameters
+        assert O.rel_err(g, pr.grad) < 1e-3, (nvlink, name, O.rel_err(g, pr.grad))
 dist.barrier()
 if world == 2 and os.environ.get("DIF_TEST_WATCHDOG", "1") == "1":
     # watchdog: rank 0 launches an exchange its peer never joins -> the kernel gives up (DIF_COMM_TIMEOUT_MS) instead of

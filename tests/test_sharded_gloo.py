@@ -59,3 +59,35 @@ def test_row_sharded_equals_unsharded(tmp_path, n, h, hv, d):
         b, e = blob["span"]
         got[b:e] = blob["out"]
     assert O.rel_err(got, want) < 1e-12
+
+
+def _gather_worker(rank, world, port, n, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from difformer_b200.sharded import RowShard, gather_rows, shard_model, shard_rows
+        x = torch.arange(n * 6, dtype=torch.float64).reshape(n, 2, 3)
+        b, e = shard_rows(n, rank, world)
+        xl = x[b:e].clone().requires_grad_(True)
+        full = gather_rows(xl, dist.group.WORLD, n)
+        assert torch.equal(full.detach(), x)                       # rows arrive in rank order, padding removed
+        w = torch.arange(n, dtype=torch.float64).reshape(n, 1, 1) + 1.0 + rank      # a different weighting on every rank
+        (full * w).sum().backward()                                # d/dx_local = sum over ranks of their weights on my rows
+        want = sum(torch.arange(n, dtype=torch.float64)[b:e] + 1.0 + r for r in range(world)).reshape(-1, 1, 1).expand(-1, 2, 3)
+        assert torch.equal(xl.grad, want)
+        # module plumbing: shard_model marks the model and every conv with the same RowShard
+        import difformer
+        m = difformer.DIFFormer(8, 16, 3, num_layers=2)
+        sh = shard_model(m, n, dist.group.WORLD, nvlink=False)
+        assert isinstance(sh, RowShard) and (sh.begin, sh.end) == (b, e) and all(c._row_shard is sh for c in m.convs)
+        torch.save({"ok": True}, os.path.join(out_dir, f"g{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 11])
+def test_gather_rows_and_its_gradient(tmp_path, n):
+    """Row all-gather of the sharded gcn_conv: forward order / padding and backward = reduce-scatter(sum)."""
+    world, port = 2, _free_port()
+    mp.spawn(_gather_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.isfile(os.path.join(str(tmp_path), f"g{r}.pt")) for r in range(world))
