@@ -100,8 +100,9 @@ extern "C" int dif_simple_forward(const void* q, const void* k, const void* v, i
                                   void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream) {
     DIF_REQUIRE(q && k && v && partials && out && workspace, DIF_EARG, "simple_forward: null pointer");
     DIF_REQUIRE(n_total > 0, DIF_EARG, "simple_forward: n_total must be positive");
-    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED,
-                "simple_forward: the one-kernel forward needs the tcgen05 shapes (M == D == 64, Hv == H, H in {1, 2, 4}); use dif_simple_reduce + dif_simple_apply");
+    DIF_REQUIRE(simple_fused_workspace_bytes(N, H, Hv, M, D) > 0, DIF_EUNSUPPORTED,
+                "simple_forward: the one-kernel forward needs M == D == 64, Hv == H, H in {1, 2, 4}, or one head of M == D == 128 (fp32); "
+                "use dif_simple_reduce + dif_simple_apply");
     if (dtype == DIF_DTYPE_BF16 || dtype == DIF_DTYPE_F16)
         return simple_forward_lp(q, k, v, dtype, N, H, Hv, M, D, n_total, partials, out, workspace, workspace_bytes, (cudaStream_t)stream,
                                  peer_bufs, rank, world, seq);

@@ -945,9 +945,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) bwd_apply_tc_kernel(const __gri
 // Shared memory: the two passes alias one dynamic allocation ([stg | ops] vs [Bop | Q stages | out staging | u]); the
 // slice-sum buffer of the tail lies over Bop (loaded afterwards), so the Q stages are free for the prefetch.
 // ------------------------------------------------------------------------------------------
-template <int H>
+template <int H, bool W = false>
 __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __grid_constant__ FusedArgs fa, const __grid_constant__ CUtensorMap out_map) {
     using G = Geo<H>;
+    using P = PLay<H, W>;
     const ReduceArgs1& a = fa.r;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -956,7 +957,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
     uint8_t* ops = stg + G::kNSG * G::kStg;
     // pass 2 view
     uint8_t* Bop = base;                                             // [h][hi|lo][80 rows][128 B]
-    uint8_t* stages = base + G::kBBytes;
+    uint8_t* stages = base + P::kBBytes;
     uint8_t* ostage = stages + kNS2 * kStage2;                       // [4 warps][2 boxes][32 rows][128 B], 1024-aligned
     float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
     __shared__ uint64_t sfull[G::kNSG], sempty[G::kNSG], ofull[G::kNO], oempty[G::kNO], done;
@@ -1133,37 +1134,41 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
         for (int col = te; col < G::kRowF; col += 128) {
             float z = 0.f, u = 0.f;
             for (int t = col >> 2; t < 256; t += G::kChunksPerRow) { z += red[t * 4 + (col & 3)]; u += red[1024 + t * 4 + (col & 3)]; }
-            rec[G::offZ + col] = z;
-            rec[G::offU + col] = u;
+            rec[P::offZ + col] = z;
+            rec[P::offU + col] = u;
         }
         if (te == 0) {
             float sk = 0.f, sq = 0.f;
             for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
-            rec[G::offSq] = sq;
-            rec[G::offSq + 1] = sk;
+            rec[P::offSq] = sq;
+            rec[P::offSq + 1] = sk;
         }
         if (H == 1) bar_sync_named(2, 128);              // `red` is re-used by the tail
-        fused_tail<H>(a, fa.flags2, rec, te, ew, lane, tmem, iters > 0, red);
+        fused_tail<H, W>(a, fa.flags2, rec, te, ew, lane, tmem, iters > 0, red);
         if (te == 0) {
-            mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
-            for (int i = 0; i < H * 2; ++i)
+            mbar_expect_tx(&bbar, (uint32_t)P::kBBytes);
+            for (int i = 0; i < P::kBTiles * 2; ++i)
                 tma_load_1d(smem_u32(Bop) + i * kBOp, a.prepared + (size_t)i * kBOp, (uint32_t)kBOp, &bbar);
         }
-        for (int i = te; i < H * kDim; i += 128) us[i] = __ldcg(a.partials + G::offU + i);
-        const float cscale = 1.f / (sqrtf(__ldcg(a.partials + G::offSq)) * sqrtf(__ldcg(a.partials + G::offSq + 1)));
+        for (int i = te; i < H * kDim; i += 128) us[i] = __ldcg(a.partials + P::offU + i);
+        const float cscale = 1.f / (sqrtf(__ldcg(a.partials + P::offSq)) * sqrtf(__ldcg(a.partials + P::offSq + 1)));
         bar_sync_named(2, 128);
         // =================== pass 2: epilogue (see apply_tc_kernel, MODE 0) ===================
         const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
         const uint64_t pol = policy_evict_first();
+        float inv_den = 0.f;
         for (int sc = 0; sc < nsc; ++sc) {
             const int64_t trow = row0_of(sc);
             const int h = sc % H, slot = sc % kNAcc;
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
-            uint32_t qz_bits = tmem_ld1(taddr + kDim);
-            tmem_ld_wait1(qz_bits);
-            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, a.n_total));
+            // wide: h = output half dh; the denominator column only exists in the dh = 0 accumulator and serves both halves
+            if (!W || h == 0) {
+                uint32_t qz_bits = tmem_ld1(taddr + kDim);
+                tmem_ld_wait1(qz_bits);
+                inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, a.n_total));
+            }
             if (lane == 0) tma_wait_read0();
             __syncwarp();
 #pragma unroll
@@ -1233,23 +1238,58 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
         const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
         pdl_launch_dependents();                        // the next kernel of the stream may start its prologue as SMs free up
         mbar_wait(&bbar, 0);
-        for (int sc = 0; sc < nsc; ++sc) {
-            const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
-            if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
-            mbar_wait(&full[s], (sc / kNS2) & 1);
-            tc_fence_after();
-            const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
-            const uint32_t d = tmem + slot * kAccCols;
+        if (!W) {
+            for (int sc = 0; sc < nsc; ++sc) {
+                const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
+                if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+                mbar_wait(&full[s], (sc / kNS2) & 1);
+                tc_fence_after();
+                const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
+                const uint32_t d = tmem + slot * kAccCols;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
-                const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
-                umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
-                umma(d, qlo, bhi, idesc, 1u);
-                umma(d, qhi, blo, idesc, 1u);
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                    const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                    umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
+                    umma(d, qlo, bhi, idesc, 1u);
+                    umma(d, qhi, blo, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[slot]);
             }
-            umma_commit(&empty[s]);
-            umma_commit(&tfull[slot]);
+        } else {
+            // wide: stage sc = (tile, K block kb); accumulator slot = (tile, output half dh) = the epilogue's stage index.
+            // Both K blocks of a tile feed both halves: 2 x 2 x 4 K steps x 3 MMAs per tile.
+            for (int sc = 0; sc < nsc; sc += 2) {
+                const int slot0 = sc % kNAcc, slot1 = (sc + 1) % kNAcc;
+                if (sc >= kNAcc) {
+                    mbar_wait(&tempty[slot0], ((sc / kNAcc) - 1) & 1);
+                    mbar_wait(&tempty[slot1], (((sc + 1) / kNAcc) - 1) & 1);
+                }
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const int st_ = sc + kb, s = st_ % kNS2;
+                    mbar_wait(&full[s], (st_ / kNS2) & 1);
+                    tc_fence_after();
+                    const uint32_t sb = stage_base + s * kStage2;
+#pragma unroll
+                    for (int dh = 0; dh < 2; ++dh) {
+                        const uint32_t bb = b_base + (2 * dh + kb) * 2 * kBOp;
+                        const uint32_t d = tmem + (dh == 0 ? slot0 : slot1) * kAccCols;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                            const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                            umma(d, qhi, bhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                            umma(d, qlo, bhi, idesc, 1u);
+                            umma(d, qhi, blo, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tfull[slot0]);
+                umma_commit(&tfull[slot1]);
+            }
         }
     }
     __syncwarp();
@@ -1414,36 +1454,42 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
 
 
 // ---- forward in one kernel ----------------------------------------------------------------------
+// ONE head of M = D = 128 (hidden_channels 128): the "wide" variant of the one-kernel forward (fp32 I/O)
+bool simple_wide_supported(int64_t N, int H, int Hv, int M, int D) { return N >= 1 && H == 1 && Hv == 1 && M == 128 && D == 128; }
+
 int64_t simple_fused_workspace_bytes(int64_t N, int H, int Hv, int M, int D) {
-    if (!simple_tc_supported(N, H, Hv, M, D)) return 0;
+    const bool wide = simple_wide_supported(N, H, Hv, M, D);
+    if (!wide && !simple_tc_supported(N, H, Hv, M, D)) return 0;
     int grid;
     tc_rows_per_cta(N, H, &grid);
-    return fused_ws_prepared_off(grid, tc_ws_len(H)) + (int64_t)H * 2 * kBOp + 128;
+    const int64_t ws_len = wide ? PLay<2, true>::kWsLen : tc_ws_len(H);
+    return fused_ws_prepared_off(grid, ws_len) + (wide ? (int64_t)PLay<2, true>::kBBytes : (int64_t)H * 2 * kBOp) + 128;
 }
 
-template <int H>
+template <int H, bool W = false>
 static int launch_fused(const FusedArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        DIF_CUDA_OK(cudaFuncSetAttribute(simple_fused_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused_bytes<H>()));
+        DIF_CUDA_OK(cudaFuncSetAttribute(simple_fused_kernel<H, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused_bytes<H, W>()));
         attr_set = true;
     }
     void* args[] = {(void*)&a, (void*)&map};
-    return launch_persistent((const void*)simple_fused_kernel<H>, grid, kThreadsTC, (size_t)smem_fused_bytes<H>(), st, args);
+    return launch_persistent((const void*)simple_fused_kernel<H, W>, grid, kThreadsTC, (size_t)smem_fused_bytes<H, W>(), st, args);
 }
 
 int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
                       float* partials, float* out, void* ws, int64_t ws_bytes, cudaStream_t st,
                       void* const* peer_bufs, int rank, int world, unsigned long long seq) {
-    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    const bool wide = simple_wide_supported(N, H, Hv, M, D);
+    DIF_REQUIRE(wide || simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG, "simple_forward: q/k/v must be 32-byte, out 16-byte aligned");
     DIF_REQUIRE(((uintptr_t)ws & 127) == 0, DIF_EARG, "simple_forward: workspace must be 128-byte aligned");
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
     int grid;
     const int rpc = tc_rows_per_cta(N, H, &grid);
-    const int64_t ws_len = tc_ws_len(H);
+    const int64_t ws_len = wide ? PLay<2, true>::kWsLen : tc_ws_len(H);
     const int64_t poff = fused_ws_prepared_off(grid, ws_len);
-    DIF_REQUIRE(ws_bytes >= poff + (int64_t)H * 2 * kBOp, DIF_EARG, "simple_forward: workspace too small");
+    DIF_REQUIRE(ws_bytes >= poff + (wide ? (int64_t)PLay<2, true>::kBBytes : (int64_t)H * 2 * kBOp), DIF_EARG, "simple_forward: workspace too small");
     DIF_REQUIRE((((ws_len + kSlices - 1) / kSlices + 3) & ~(int64_t)3) <= 128, DIF_EUNSUPPORTED, "simple_forward: slice wider than the tail warps");
     static std::atomic<unsigned long long> epoch_src{0xA24BAED4963EE407ull ^ (unsigned long long)(uintptr_t)&epoch_src};
     FusedArgs fa{};
@@ -1470,9 +1516,10 @@ int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N,
     a.dbg = dbg_buffer();
     fa.out = out; fa.store_hint = sth; fa.reverse = rev;
     CUtensorMap map;
-    int rc = make_out_map(&map, out, N, (int64_t)H * kDim);
+    int rc = make_out_map(&map, out, N, (int64_t)H * D);
     if (rc) return rc;
-    rc = H == 4 ? launch_fused<4>(fa, map, grid, st) : H == 2 ? launch_fused<2>(fa, map, grid, st) : launch_fused<1>(fa, map, grid, st);
+    rc = wide ? launch_fused<2, true>(fa, map, grid, st)
+       : H == 4 ? launch_fused<4>(fa, map, grid, st) : H == 2 ? launch_fused<2>(fa, map, grid, st) : launch_fused<1>(fa, map, grid, st);
     if (rc) return rc;
     dbg_report("simple_fused", a.dbg, grid);
     return DIF_OK;

@@ -40,6 +40,21 @@ struct Geo {
 };
 
 constexpr int kBOp = 80 * 128;                        // one (head, hi|lo) B-operand tile of pass 2
+
+// Partials / B-image geometry of the one-kernel forward.  W ("wide") = ONE head of M = D = 128 (hidden_channels 128,
+// run.sh:43,70,75) executed with the H = 2 geometry: the node rows have the same 512-byte layout, pass 1 is the very same
+// M = N = 128 UMMA whose accumulator now is the whole S[128][128] (all four 64 x 64 blocks instead of the two diagonal ones),
+// pass 2 contracts over K = 128 (two 64-column stages of Q) into the two 64-column halves of the output.
+template <int H, bool W>
+struct PLay {
+    static_assert(!W || H == 2, "wide mode runs on the H = 2 geometry");
+    static constexpr int kS = W ? 128 * 128 : H * kDim * kDim;          // floats of S
+    static constexpr int kV = H * kDim;                                  // floats of z (= of u): 128 in wide mode
+    static constexpr int offZ = kS, offU = offZ + kV, offSq = offU + kV, kP = offSq + 2;
+    static constexpr int kBTiles = W ? 4 : H;                            // (head) or (output half dh, K block kb) tiles, each hi | lo
+    static constexpr int kBBytes = kBTiles * 2 * kBOp;
+    static constexpr int64_t kWsLen = (kP + 7) & ~7;                     // 32-byte aligned records (256-bit stores)
+};
 using ShardArgs = CommPeers;  // multi-GPU: peer-mapped LL exchange buffers (common.cuh, csrc/comm.cu)
 constexpr int kThreadsT = 10 * 32;                    // pass 1: warps 0-7 converters, 8 TMA issuer, 9 MMA issuer
 constexpr int kSlices = 148;                          // column slices of the record for the fused cross-CTA sum
@@ -84,8 +99,11 @@ struct FusedArgs {
     int pf_tiles;             // Q tiles of this CTA's rows prefetched into L2 while the tail runs (HBM is idle there)
     unsigned long long* flags2;   // [grid] second grid barrier (B image complete)
 };
-template <int H>
-constexpr int smem_fused_bytes() { return (Geo<H>::kSmem1 > smem2_bytes<H>() ? Geo<H>::kSmem1 : smem2_bytes<H>()); }
+template <int H, bool W = false>
+constexpr int smem_fused_bytes() {
+    constexpr int p2 = PLay<H, W>::kBBytes + kNS2 * kStage2 + kOutStage + H * kDim * 4 + 1024;
+    return Geo<H>::kSmem1 > p2 ? Geo<H>::kSmem1 : p2;
+}
 
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive_named(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
@@ -188,15 +206,37 @@ int64_t fused_ws_prepared_off(int grid, int64_t ws_len) {
 // `red` : >= 64*65 floats of shared scratch when H == 1 (block halves of S), unused otherwise.
 // Uses named barrier 2 (128 threads).  No shared memory of the pipelines is touched: the Q prefetch of pass 2 may run.
 // ------------------------------------------------------------------------------------------
-template <int H>
+template <int H, bool W = false>
 __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long long* flags2, float* rec, int te, int ew, int lane,
                                            uint32_t tmem, bool have_rows, float* red) {
     using G = Geo<H>;
+    using P = PLay<H, W>;
     uint64_t* dbg = a.dbg;
     if (te == 0)
-        for (int64_t i = G::kP; i < a.ws_len; ++i) rec[i] = 0.f;
+        for (int64_t i = P::kP; i < a.ws_len; ++i) rec[i] = 0.f;
+    if (W) {
+        // wide: the accumulator IS S[128][128]: warp quadrant ew holds rows m = 32 ew + lane, all 128 columns
+        const int m = ew * 32 + lane;
 #pragma unroll 1
-    for (int p = 0; p < G::kPairs; ++p) {
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t r[32];
+            if (have_rows) {
+                tmem_ld32(tmem + ((uint32_t)(ew * 32) << 16) + cb * 32, r);
+                tmem_ld_wait32(r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            float* dst = rec + (int64_t)m * 128 + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                             :: "l"(dst + j), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]),
+                                "r"(r[j + 4]), "r"(r[j + 5]), "r"(r[j + 6]), "r"(r[j + 7]) : "memory");
+        }
+    }
+#pragma unroll 1
+    for (int p = 0; p < (W ? 0 : G::kPairs); ++p) {
         const int wq = ew, hp = wq >> 1, m = (wq * 32 + lane) & 63;
         uint32_t r[2][32];
 #pragma unroll
@@ -267,7 +307,7 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
             if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 8] = gtime();
         }
         const int64_t j = j0 + te;
-        const bool live = te < slice && j < G::kP;
+        const bool live = te < slice && j < P::kP;
         float local = 0.f;
         if (live) {
             // element j of every record, straight from L2 (ld.cg: never a stale L1 line), 16 loads in flight; four
@@ -305,10 +345,17 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
         }
         if (live) {
             a.partials[j] = sum;
-            if (j < G::offU) {
+            if (j < P::offU) {
+                // B tile t, row n (output column), k (contraction index) of this element.  Narrow: t = head.  Wide: t = 2 dh + kb
+                // (dh = output half, kb = K block); the z column (row 64) lives in the dh = 0 tiles.
                 int h, n, m;
-                if (j < G::offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
-                else { h = (int)(j - G::offZ) >> 6; m = (int)(j - G::offZ) & 63; n = kDim; }
+                if (!W) {
+                    if (j < P::offZ) { h = (int)(j >> 12); m = (int)(j >> 6) & 63; n = (int)j & 63; }
+                    else { h = (int)(j - P::offZ) >> 6; m = (int)(j - P::offZ) & 63; n = kDim; }
+                } else {
+                    if (j < P::offZ) { const int mm = (int)(j >> 7), d = (int)j & 127; h = 2 * (d >> 6) + (mm >> 6); m = mm & 63; n = d & 63; }
+                    else { const int mm = (int)(j - P::offZ); h = mm >> 6; m = mm & 63; n = kDim; }
+                }
                 const __nv_bfloat16 hi = __float2bfloat16_rn(sum);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(sum - __bfloat162float(hi));
                 uint8_t* img = a.prepared + (size_t)h * 2 * kBOp + sw128(n, m >> 3) + (m & 7) * 2;
@@ -318,8 +365,11 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
         }
     }
     if (blockIdx.x == grid - 1) {
-        for (int i = te; i < H * 2 * 15 * 8; i += 128) {
-            const int c = i & 7, rr = (i >> 3) % 15 + 65, t = i / (8 * 15);
+        // rows 65..79 of every (tile, hi|lo) image are zero padding (N = 80 of the pass-2 UMMA); wide: the dh = 1 tiles have no
+        // z row either (row 64)
+        for (int i = te; i < P::kBTiles * 2 * 16 * 8; i += 128) {
+            const int c = i & 7, rr = (i >> 3) % 16 + 64, t = i / (8 * 16);
+            if (rr == 64 && !(W && (t >> 1) >= 2)) continue;           // t = 2 * tile + (hi|lo): tiles 2, 3 are dh = 1
             *reinterpret_cast<uint4*>(a.prepared + (size_t)t * kBOp + sw128(rr, c)) = make_uint4(0u, 0u, 0u, 0u);
         }
     }

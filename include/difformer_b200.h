@@ -102,7 +102,8 @@ DIF_API int dif_simple_apply(const float* q, const float* partials, const void* 
                      float* out, const dif_epilogue_t* epilogue,
                      int impl, void* stream);
 
-/* The forward in ONE kernel (tcgen05 shapes: dif_simple_forward_workspace_bytes() > 0): a cooperative persistent launch runs
+/* The forward in ONE kernel (dif_simple_forward_workspace_bytes() > 0: M == D == 64 with Hv == H in {1, 2, 4}, any dtype; or one
+ * head of M == D == 128, fp32 -- hidden_channels 128 of run.sh:43,70,75): a cooperative persistent launch runs
  * pass 1, the grid-wide deterministic sum of the partials (with `peer_bufs` != NULL and world > 1 also the cross-GPU
  * LL-push all-reduce, see dif_comm_* below) and pass 2 on the rows each CTA just streamed -- no second launch, the Q rows
  * of pass 2 are prefetched while the sum is in flight.  out[N,H,D] = full_attention_conv(q,k,v,'simple'); `partials`

@@ -240,6 +240,38 @@ def test_simple_16bit_other_shapes_and_sigmoid():
     assert O.rel_err(out.double(), O.sigmoid_attention((q * 0.25).double(), (k * 0.25).double(), v.double())) < 2.0 ** -10
 
 
+@pytest.mark.parametrize("n", [1, 129, 5000, 132534])
+def test_one_kernel_forward_hidden_128(n):
+    """hidden_channels 128 with one head (run.sh:43 pokec, :70, :75): the wide variant of the one-kernel forward (the H = 2
+    geometry with the full 128 x 128 accumulator) against the FFMA kernels and the fp64 oracle, intermediates included."""
+    q, k, v = O.synthetic_qkv(n, 1, 128, seed=n, adversarial=True)
+    qg, kg, vg = dev(q), dev(k), dev(v)
+    res = ops.simple_forward(qg, kg, vg)
+    assert res is not None, "M = D = 128, H = 1 must take the tcgen05 one-kernel forward"
+    out, flat = res
+    want = O.simple_partials(q.double(), k.double(), v.double())
+    S, z, u, sq, sk = _unpack(flat, 1, 1, 128, 128)
+    assert O.rel_err(S, want["S"]) < 1e-4 and O.rel_err(z, want["z"]) < 1e-5 and O.rel_err(u, want["u"]) < 1e-5
+    assert abs(float(sq) / float(want["sq"]) - 1) < 1e-5 and abs(float(sk) / float(want["sk"]) - 1) < 1e-5
+    assert O.rel_err(out, O.simple_apply(q.double(), want)) < 1e-4
+    try:
+        ops.set_simple_impl("generic")
+        flat_g = ops.simple_partials(qg, kg, vg)
+        out_g = ops.simple_apply(qg, flat_g, float(n), 1, 128)
+    finally:
+        ops.set_simple_impl("auto")
+    assert O.rel_err(flat, flat_g) < 1e-4 and O.rel_err(out, out_g) < 1e-5
+    assert torch.equal(ops.simple_forward(qg, kg, vg)[0], out)          # deterministic
+    # the public op with autograd: forward = this kernel, backward = the FFMA kernels fed with its partials
+    qa, ka, va = (t.clone().requires_grad_(True) for t in (qg, kg, vg))
+    o = difformer.full_attention_conv(qa, ka, va, "simple")
+    assert torch.equal(o, out)
+    g = torch.randn(n, 1, 128, generator=torch.Generator().manual_seed(2))
+    o.backward(dev(g))
+    for got, w in zip((qa.grad, ka.grad, va.grad), O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())):
+        assert O.rel_err(got, w) < TOL
+
+
 def test_simple_rejects_n_ne_l():
     q = torch.randn(10, 1, 64, device="cuda")
     with pytest.raises(ValueError, match="N == L"):
