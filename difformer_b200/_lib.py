@@ -18,7 +18,8 @@ c_i32, c_i64, c_f64, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctype
 class Epilogue(ctypes.Structure):
     """dif_epilogue_t"""
     _fields_ = [("mode", c_i32), ("attn_scale", ctypes.c_float), ("n_add", c_i32),
-                ("add", c_vp * 3), ("add_scale", ctypes.c_float * 3)]
+                ("add", c_vp * 3), ("add_scale", ctypes.c_float * 3),
+                ("ln_weight", c_vp), ("ln_bias", c_vp), ("ln_eps", ctypes.c_float), ("relu", c_i32)]
 
 
 # name -> (restype, argtypes); mirrors include/difformer_b200.h one to one

@@ -610,6 +610,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             if (MODE == 1 && h == H - 1) {
                 const int64_t row = tile * kTile2 + ew * 32 + lane;
                 const bool ok = row < p.N;
+                // layer epilogue on the thread's whole output row (64 values in registers): head mean + addends, then --
+                // optionally -- the LayerNorm that follows the layer (difformer.py:202-203) and a ReLU
 #pragma unroll
                 for (int j = 0; j < kDim; j += 4) {
                     float4 o = make_float4(hs[j] * p.ep.attn_scale, hs[j + 1] * p.ep.attn_scale, hs[j + 2] * p.ep.attn_scale,
@@ -621,9 +623,32 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                             o.x = fmaf(s, x.x, o.x); o.y = fmaf(s, x.y, o.y); o.z = fmaf(s, x.z, o.z); o.w = fmaf(s, x.w, o.w);
                         }
                     }
-                    sts128(obox + (j >> 5) * kOutBox + sw128(lane, (j & 31) >> 2),
-                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                    hs[j] = o.x; hs[j + 1] = o.y; hs[j + 2] = o.z; hs[j + 3] = o.w;
                 }
+                if (p.ep.ln_weight != nullptr) {
+                    float mean = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kDim; ++j) mean += hs[j];
+                    mean *= 1.f / kDim;
+                    float var = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kDim; ++j) { const float d_ = hs[j] - mean; var = fmaf(d_, d_, var); }
+                    const float rstd = rsqrtf(var * (1.f / kDim) + p.ep.ln_eps);
+#pragma unroll
+                    for (int j = 0; j < kDim; j += 4) {
+                        const float4 w4 = ldg4(p.ep.ln_weight + j), b4 = ldg4(p.ep.ln_bias + j);
+                        hs[j] = fmaf((hs[j] - mean) * rstd, w4.x, b4.x); hs[j + 1] = fmaf((hs[j + 1] - mean) * rstd, w4.y, b4.y);
+                        hs[j + 2] = fmaf((hs[j + 2] - mean) * rstd, w4.z, b4.z); hs[j + 3] = fmaf((hs[j + 3] - mean) * rstd, w4.w, b4.w);
+                    }
+                }
+                if (p.ep.relu) {
+#pragma unroll
+                    for (int j = 0; j < kDim; ++j) hs[j] = fmaxf(hs[j], 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < kDim; j += 4)
+                    sts128(obox + (j >> 5) * kOutBox + sw128(lane, (j & 31) >> 2),
+                           make_uint4(__float_as_uint(hs[j]), __float_as_uint(hs[j + 1]), __float_as_uint(hs[j + 2]), __float_as_uint(hs[j + 3])));
             }
             if (MODE == 0 || h == H - 1) {
                 fence_proxy_async();
@@ -1433,8 +1458,10 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     a.q = q; a.partials = partials; a.n_total = (float)n_total; a.N = N; a.out = out;
     a.prepared = (const uint8_t*)prepared;
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_apply(tcgen05): prepared buffer must be 16-byte aligned");
-    if (ep) a.ep = *ep; else { a.ep.mode = 0; a.ep.n_add = 0; }
+    if (ep) a.ep = *ep; else { a.ep = dif_epilogue_t{}; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
+    DIF_REQUIRE(a.ep.ln_weight == nullptr || (a.ep.ln_bias != nullptr && (((uintptr_t)a.ep.ln_weight | (uintptr_t)a.ep.ln_bias) & 15) == 0), DIF_EARG,
+                "simple_apply: LayerNorm weight and bias must both be given, 16-byte aligned");
     static const int pf = env_int("DIF_TC_P2_PREFETCH", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1);
     a.pf_tiles = pf;
     a.store_hint = sth;

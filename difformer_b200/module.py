@@ -30,11 +30,12 @@ def _fusable(kernel, *tensors):
 
 
 def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0, output_attn,
-                  residual=None, n_nodes=None):
+                  residual=None, n_nodes=None, layer_norm=None):
     """Shared body of DIFFormerConv.forward / TransConv.forward.
 
     residual = (alpha, prev) folds `alpha*x + (1-alpha)*prev` (difformer.py:200-201) into the fused
-    epilogue; the return flag says whether it was applied."""
+    epilogue; the return flag says whether it was applied.  layer_norm = the nn.LayerNorm that follows the layer
+    (difformer.py:202-203): folded into the same epilogue when the tcgen05 kernel runs it (flag value 2)."""
     H, C = conv.num_heads, conv.out_channels
     query = conv.Wq(query_input).reshape(-1, H, C)
     key = conv.Wk(source_input).reshape(-1, H, C)
@@ -77,9 +78,13 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
             addends.append((ops._f32c(x_0), alpha))
         if residual is not None:
             addends.append((ops._f32c(residual[1]), 1.0 - alpha))
-        ep = ops.make_epilogue(alpha * w_attn / H, addends)
-        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=addends, prepared=prepared)
-        return out, None, residual is not None
+        ln = None
+        if (layer_norm is not None and residual is not None and layer_norm.elementwise_affine and layer_norm.bias is not None
+                and tuple(layer_norm.normalized_shape) == (v.shape[2],) and ops.layer_tail_fusable(H, v.shape[1], C, v.shape[2])):
+            ln = (layer_norm.weight.detach().float().contiguous(), layer_norm.bias.detach().float().contiguous(), layer_norm.eps)
+        ep = ops.make_epilogue(alpha * w_attn / H, addends, layer_norm=ln)
+        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=(addends, ln), prepared=prepared)
+        return out, None, (2 if ln is not None else 1) if residual is not None else 0
 
     # ---- unfused path (training, sigmoid, batched graphs, attention visualisation)
     attn = None
@@ -127,9 +132,9 @@ class DIFFormerConv(nn.Module):
             self.Wv.reset_parameters()
 
     def forward(self, query_input, source_input, edge_index=None, edge_weight=None, x_0=None, output_attn=False,
-                _residual=None):
+                _residual=None, _layer_norm=None):
         out, attn, fused_res = _conv_forward(self, query_input, source_input, edge_index, edge_weight, x_0,
-                                             output_attn, residual=_residual)
+                                             output_attn, residual=_residual, layer_norm=_layer_norm)
         if _residual is not None:
             return out, fused_res
         return (out, attn) if output_attn else out
@@ -178,13 +183,16 @@ class DIFFormer(nn.Module):
         layer_.append(x)
         for i, conv in enumerate(self.convs):
             res = (self.alpha, layer_[i]) if self.residual else (1.0, None)
+            fused = 0
             if self.residual:
-                x, fused = conv(x, x, edge_index, edge_weight, layer_[0], _residual=res)
+                # no-grad path: the residual blend AND the LayerNorm that follows go into the kernel's epilogue
+                x, fused = conv(x, x, edge_index, edge_weight, layer_[0], _residual=res,
+                                _layer_norm=self.bns[i + 1] if self.use_bn else None)
                 if not fused:
                     x = self.alpha * x + (1 - self.alpha) * layer_[i]
             else:
                 x = conv(x, x, edge_index, edge_weight, layer_[0])
-            if self.use_bn:
+            if self.use_bn and fused != 2:
                 x = self.bns[i + 1](x)
             x = F.dropout(x, p=self.dropout, training=self.training)
             layer_.append(x)

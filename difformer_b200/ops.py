@@ -164,14 +164,25 @@ def simple_apply(qs: torch.Tensor, partials: torch.Tensor, n_total: float, Hv: i
     return out
 
 
-def make_epilogue(attn_scale: float, addends) -> Epilogue:
-    """addends: list of (tensor [N,D] fp32 contiguous, scale)."""
+def make_epilogue(attn_scale: float, addends, layer_norm=None, relu: bool = False) -> Epilogue:
+    """addends: list of (tensor [N,D] fp32 contiguous, scale).  layer_norm = (weight [D], bias [D], eps): the LayerNorm that
+    follows the layer (difformer.py:202-203) applied to the finished row inside the kernel (tcgen05 shapes only, see
+    `layer_tail_fusable`); relu: ReLU after it.  Keep the tensors alive until the kernel has been enqueued."""
     ep = Epilogue()
     ep.mode, ep.attn_scale, ep.n_add = 1, float(attn_scale), len(addends)
     for j, (t, s) in enumerate(addends):
         ep.add[j] = t.data_ptr()
         ep.add_scale[j] = float(s)
+    if layer_norm is not None:
+        w, b, eps = layer_norm
+        ep.ln_weight, ep.ln_bias, ep.ln_eps = w.data_ptr(), b.data_ptr(), float(eps)
+    ep.relu = 1 if relu else 0
     return ep
+
+
+def layer_tail_fusable(H: int, Hv: int, M: int, D: int) -> bool:
+    """True when pass 2 runs the tcgen05 kernel, whose layer epilogue can also carry the LayerNorm / ReLU tail."""
+    return _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC and int(lib.dif_simple_prepared_bytes(H, Hv, M, D)) > 0
 
 
 def _allreduce(t: torch.Tensor, group) -> None:

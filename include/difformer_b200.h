@@ -95,6 +95,12 @@ typedef struct {
     int n_add;              /* 0..3 */
     const float* add[3];    /* each [N,D] or NULL */
     float add_scale[3];
+    /* optional tail of the layer, applied to the finished [N,D] row (tcgen05 kernels only: DIF_EUNSUPPORTED on the FFMA path):
+     * LayerNorm over D (difformer.py:202-203: weight / bias [D], eps) when ln_weight != NULL, then ReLU when relu != 0 */
+    const float* ln_weight;
+    const float* ln_bias;
+    float ln_eps;
+    int relu;
 } dif_epilogue_t;
 
 DIF_API int dif_simple_apply(const float* q, const float* partials, const void* prepared, double n_total,
