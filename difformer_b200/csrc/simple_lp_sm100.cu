@@ -152,15 +152,6 @@ __global__ void __launch_bounds__(kLpThreads, 1) simple_lp_kernel(const __grid_c
                     }
                 }
             }
-            // HBM idles from here until pass 2 starts (CTA finish spread + tail): pull the Q tiles pass 2 reads LAST into L2 now
-            {
-                const int npf = min(la.pf_tiles, my_tiles);
-                const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q);      // 16-bit elements of either type
-                for (int t = 0; t < npf; ++t) {
-                    const int64_t prow = r0 + (int64_t)t * kTile2;
-                    prefetch_l2(qg + prow * (H * kDim), (uint32_t)(min((int64_t)kTile2, r1 - prow) * H * kDim * 2));
-                }
-            }
             // drain: every stage that was used must have been consumed (MMA + column sums) before pass 2 re-uses the memory
             for (int it = iters; it < iters + kLpNS; ++it)
                 if (it >= kLpNS) mbar_wait(&empty[it % kLpNS], ((it / kLpNS) - 1) & 1);
@@ -298,7 +289,9 @@ __global__ void __launch_bounds__(kLpThreads, 1) simple_lp_kernel(const __grid_c
                 rec[G::offSq + 1] = sk;
             }
             if (H == 1) bar_sync_named(2, 128);
-            fused_tail<H>(a, la.flags2, rec, te, ew, lane, tmem, iters > 0, red);
+            const int64_t pf_rows = min((int64_t)min(la.pf_tiles, my_tiles) * kTile2, r1 - r0);
+            fused_tail<H>(a, la.flags2, rec, te, ew, lane, tmem, iters > 0, red, reinterpret_cast<const __nv_bfloat16*>(a.q) + r0 * (H * kDim),
+                          (uint32_t)(max((int64_t)0, pf_rows) * H * kDim * 2));
             if (te == 0) {
                 mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
                 for (int i = 0; i < H * 2; ++i)
@@ -443,7 +436,7 @@ int simple_forward_lp(const void* q, const void* k, const void* v, int dtype, in
         a.sh.timeout_ns = comm_timeout_ns();
     }
     static const int hints = env_int("DIF_TC_P1_HINTS", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1), rev = env_int("DIF_TC_FUSED_REVERSE", 1);
-    static const int pft = env_int("DIF_TC_FUSED_PF_TILES", 3);
+    static const int pft = env_int("DIF_TC_FUSED_PF_TILES", 0);
     la.l2_hints = hints; la.store_hint = sth; la.reverse = rev; la.pf_tiles = pft;
     a.q = reinterpret_cast<const float*>(q);            // only used as the base address of the L2 prefetch
     a.dbg = dbg_buffer();

@@ -1141,13 +1141,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
                     tma_load_1d(stg_base + s * G::kStg + 2 * G::kStgT, a.q + row * G::kRowF, bytes, &sfull[s]);
                 }
             }
-            // HBM idles from here until pass 2 starts (CTA finish spread + tail): pull the Q tiles pass 2 will read LAST
-            // (the ones pass 1 streamed first, least likely still in L2) into L2 now
-            const int npf = min(fa.pf_tiles, my_tiles);
-            for (int t = 0; t < npf; ++t) {
-                const int64_t prow = r0 + (int64_t)t * kTile2;
-                prefetch_l2(a.q + prow * G::kRowF, (uint32_t)(min((int64_t)kTile2, r1 - prow) * G::kRowB));
-            }
         }
         __syncwarp();
         // =================== tail (see reduce_tma_kernel): record, grid-wide slice sum (+ cross-GPU LL exchange) ===================
@@ -1169,7 +1162,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
             rec[P::offSq + 1] = sk;
         }
         if (H == 1) bar_sync_named(2, 128);              // `red` is re-used by the tail
-        fused_tail<H, W>(a, fa.flags2, rec, te, ew, lane, tmem, iters > 0, red);
+        const int64_t pf_rows = min((int64_t)min(fa.pf_tiles, my_tiles) * kTile2, r1 - r0);
+        fused_tail<H, W>(a, fa.flags2, rec, te, ew, lane, tmem, iters > 0, red, a.q + r0 * G::kRowF, (uint32_t)(max((int64_t)0, pf_rows) * G::kRowB));
         if (te == 0) {
             mbar_expect_tx(&bbar, (uint32_t)P::kBBytes);
             for (int i = 0; i < P::kBTiles * 2; ++i)
@@ -1528,7 +1522,7 @@ int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N,
     a.partials = partials; a.prepared = (uint8_t*)ws + poff;
     a.vbar = nullptr;
     static const int hints = env_int("DIF_TC_P1_HINTS", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1), rev = env_int("DIF_TC_FUSED_REVERSE", 1);
-    static const int pft = env_int("DIF_TC_FUSED_PF_TILES", 3);
+    static const int pft = env_int("DIF_TC_FUSED_PF_TILES", 0);
     a.l2_hints = hints;
     fa.pf_tiles = pft;
     a.n_total = (float)n_total;

@@ -140,10 +140,20 @@ void dbg_report(const char* name, uint64_t* buf, int grid) {
     cudaDeviceSynchronize();
     static uint64_t h[256 * kDbgSlots];
     cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+    if (const char* path = getenv("DIF_TC_DEBUG_CSV")) {         // per-CTA stamps (slot 15 = %smid + 1) for offline analysis
+        if (FILE* f = fopen(path, "a")) {
+            for (int b = 0; b < grid; ++b) {
+                fprintf(f, "%s,%d", name, b);
+                for (int s_ = 0; s_ < kDbgSlots; ++s_) fprintf(f, ",%llu", (unsigned long long)h[b * kDbgSlots + s_]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     uint64_t t0 = ~0ull;
     for (int b = 0; b < grid; ++b) if (h[b * kDbgSlots] && h[b * kDbgSlots] < t0) t0 = h[b * kDbgSlots];
     fprintf(stderr, "[%s] slot: min/avg/max us since first CTA start\n", name);
-    for (int s = 0; s < kDbgSlots; ++s) {
+    for (int s = 0; s < kDbgSlots - 1; ++s) {
         double mn = 1e30, mx = 0, sum = 0; int n = 0;
         for (int b = 0; b < grid; ++b) { if (!h[b * kDbgSlots + s]) continue; double t = (h[b * kDbgSlots + s] - t0) * 1e-3; mn = t < mn ? t : mn; mx = t > mx ? t : mx; sum += t; ++n; }
         if (n) fprintf(stderr, "  stamp %d: %7.2f %7.2f %7.2f  (n=%d)\n", s, mn, sum / n, mx, n);
@@ -165,6 +175,12 @@ int env_int(const char* name, int dflt) {
 //                             griddepcontrol.wait before their first global access
 inline int launch_persistent(const void* kernel, int grid, int threads, size_t smem, cudaStream_t st, void** args) {
     static const int mode = env_int("DIF_TC_LAUNCH", 0);
+    static const int persist_mb = env_int("DIF_TC_L2_PERSIST_MB", -1);      // experiment: L2 set-aside for evict_last lines
+    static bool persist_set = false;
+    if (persist_mb >= 0 && !persist_set) {
+        DIF_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20));
+        persist_set = true;
+    }
     if (mode == 0) {
         DIF_CUDA_OK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), args, smem, st));
         return DIF_OK;
@@ -203,12 +219,13 @@ int64_t fused_ws_prepared_off(int grid, int64_t ws_len) {
 //   3. multi-GPU: exchanges each slice with the peers (LL push over NVLink, common.cuh) and adds the ranks in rank order,
 //   4. writes the reduced partials and the pass-2 B-operand image (bf16 hi/lo, 128B-swizzled, un-scaled) to global memory,
 //   5. runs a second grid barrier (flags2) after which partials and image are complete and visible to every CTA.
-// `red` : >= 64*65 floats of shared scratch when H == 1 (block halves of S), unused otherwise.
+// `red` : shared scratch, >= 64*65 floats when H == 1 (block halves of S), >= 1024 floats otherwise (chains of the slice sum).
 // Uses named barrier 2 (128 threads).  No shared memory of the pipelines is touched: the Q prefetch of pass 2 may run.
 // ------------------------------------------------------------------------------------------
 template <int H, bool W = false>
 __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long long* flags2, float* rec, int te, int ew, int lane,
-                                           uint32_t tmem, bool have_rows, float* red) {
+                                           uint32_t tmem, bool have_rows, float* red, const void* pf_ptr = nullptr,
+                                           uint32_t pf_bytes = 0) {
     using G = Geo<H>;
     using P = PLay<H, W>;
     uint64_t* dbg = a.dbg;
@@ -290,47 +307,79 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
     const int xslot = (int)(sh.seq & 1);
     if (sharded && blockIdx.x == 0 && te == 0) comm_check_status(sh);
     bool waited = false;
+    double* gsum = reinterpret_cast<double*>(red);       // [3 groups][128] partial chains of the slice sum (3 KB of `red`)
     for (int sl = blockIdx.x; sl < kSlices; sl += grid) {
         const int64_t j0 = (int64_t)sl * chunk;
         const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
         if (slice <= 0) break;
         if (!waited) {
+            // relaxed polling, ONE acquire fence after the last flag: an acquire load per poll costs a fence each
             for (int r = te; r < grid; r += 128) {
                 unsigned long long f;
                 do {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
                 } while (f != epoch);
             }
+            __threadfence();
             bar_sync_named(2, 128);                      // every record is published and (through the acquiring threads) visible
             if (blockIdx.x == 0 && te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + grid) = gen + 1;
             waited = true;
             if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 8] = gtime();
+            // every CTA has finished pass 1: HBM idles until pass 2 starts -- pull the Q rows pass 2 reads LAST into L2 now
+            // (earlier would steal bandwidth from the CTAs still streaming pass 1: measured)
+            if (pf_bytes > 0 && te == 32) {
+                for (uint32_t o = 0; o < pf_bytes; o += 32768u)
+                    prefetch_l2(reinterpret_cast<const char*>(pf_ptr) + o, min(32768u, pf_bytes - o));
+            }
+        }
+        // Slice sum.  Four groups of 32 threads; group g walks the records r = 4i + g (the four fixed chains of the sum), lane l
+        // owns the four consecutive elements 4l..4l+3 of the slice and reads them as ONE 16-byte load per record straight from
+        // L2 (ld.cg), 13 loads in flight: ~3 L2 round trips for the whole slice.  Chains are fp64 and are combined in the
+        // fixed order (c0 + c1) + (c2 + c3): deterministic, identical to the two-launch path.
+        {
+            const int g = te >> 5, l = te & 31;
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+            if (4 * l < slice) {
+                const float* col = a.ws + j0 + 4 * l;
+                const int64_t ld = a.ws_len;
+                const int gmain = grid & ~3;             // records beyond the last full group of four all belong to chain 0
+                int r = g;
+                for (; r + 4 * 12 < gmain; r += 4 * 13) {
+                    float4 x[13];
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) x[i] = __ldcg(reinterpret_cast<const float4*>(col + (int64_t)(r + 4 * i) * ld));
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) { c0 += (double)x[i].x; c1 += (double)x[i].y; c2 += (double)x[i].z; c3 += (double)x[i].w; }
+                }
+                for (; r < gmain; r += 4) {
+                    const float4 x = __ldcg(reinterpret_cast<const float4*>(col + (int64_t)r * ld));
+                    c0 += (double)x.x; c1 += (double)x.y; c2 += (double)x.z; c3 += (double)x.w;
+                }
+                if (g == 0)
+                    for (r = gmain; r < grid; ++r) {
+                        const float4 x = __ldcg(reinterpret_cast<const float4*>(col + (int64_t)r * ld));
+                        c0 += (double)x.x; c1 += (double)x.y; c2 += (double)x.z; c3 += (double)x.w;
+                    }
+            }
+            if (g > 0) {
+                double* d = gsum + (g - 1) * 128 + 4 * l;
+                d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3;
+            }
+            bar_sync_named(2, 128);
+            // group 0 holds chain 0 of its four elements in registers; hand the combined values to the element-owning threads
+            if (g == 0 && 4 * l < slice) {
+                const double* d = gsum + 4 * l;
+                float* o = reinterpret_cast<float*>(gsum + 3 * 128);        // [128] floats behind the chains
+                o[4 * l + 0] = (float)((c0 + d[0]) + (d[128 + 0] + d[256 + 0]));
+                o[4 * l + 1] = (float)((c1 + d[1]) + (d[128 + 1] + d[256 + 1]));
+                o[4 * l + 2] = (float)((c2 + d[2]) + (d[128 + 2] + d[256 + 2]));
+                o[4 * l + 3] = (float)((c3 + d[3]) + (d[128 + 3] + d[256 + 3]));
+            }
+            bar_sync_named(2, 128);
         }
         const int64_t j = j0 + te;
         const bool live = te < slice && j < P::kP;
-        float local = 0.f;
-        if (live) {
-            // element j of every record, straight from L2 (ld.cg: never a stale L1 line), 16 loads in flight; four
-            // independent fp64 chains (records r = 4i + k), combined in a fixed order: deterministic
-            const float* col = a.ws + j;
-            const int64_t ld = a.ws_len;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int r = 0;
-            for (; r + 15 < grid; r += 16) {
-                float x[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = __ldcg(col + (int64_t)(r + i) * ld);
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) { a0 += (double)x[i]; a1 += (double)x[i + 1]; a2 += (double)x[i + 2]; a3 += (double)x[i + 3]; }
-            }
-            for (; r + 3 < grid; r += 4) {
-                const float x0 = __ldcg(col + (int64_t)(r + 0) * ld), x1 = __ldcg(col + (int64_t)(r + 1) * ld);
-                const float x2 = __ldcg(col + (int64_t)(r + 2) * ld), x3 = __ldcg(col + (int64_t)(r + 3) * ld);
-                a0 += (double)x0; a1 += (double)x1; a2 += (double)x2; a3 += (double)x3;
-            }
-            for (; r < grid; ++r) a0 += (double)__ldcg(col + (int64_t)r * ld);
-            local = (float)((a0 + a1) + (a2 + a3));
-        }
+        const float local = live ? reinterpret_cast<const float*>(gsum + 3 * 128)[te] : 0.f;
         float sum = local;
         if (sharded && live) {
             const uint32_t tag = (uint32_t)sh.seq;
@@ -378,13 +427,15 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
     __threadfence();
     bar_sync_named(2, 128);
     const unsigned long long epoch2 = epoch + 1;
-    if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flags2 + blockIdx.x), "l"(epoch2) : "memory");
+    if (te == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(flags2 + blockIdx.x), "l"(epoch2) : "memory");   // ordered by the fence above
+    if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 10] = gtime();
     for (int r = te; r < grid; r += 128) {
         unsigned long long f;
         do {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags2 + r) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags2 + r) : "memory");
         } while (f != epoch2);
     }
+    __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     bar_sync_named(2, 128);
     if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 6] = gtime();

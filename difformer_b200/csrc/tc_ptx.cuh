@@ -27,9 +27,13 @@ __device__ __forceinline__ uint64_t gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define DIF_STAMP(buf, slot)                                                        \
     do {                                                                            \
-        if ((buf) != nullptr && threadIdx.x == 0) (buf)[blockIdx.x * kDbgSlots + (slot)] = gtime(); \
+        if ((buf) != nullptr && threadIdx.x == 0) {                                 \
+            (buf)[blockIdx.x * kDbgSlots + (slot)] = gtime();                       \
+            if ((slot) == 0) (buf)[blockIdx.x * kDbgSlots + kDbgSlots - 1] = smid() + 1; \
+        }                                                                           \
     } while (0)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
