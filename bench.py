@@ -112,6 +112,25 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(dev):
+    """Multi-GPU e2e: pin this rank's threads (and with them its pinned host buffers: first touch) to the CPUs of the NUMA node its
+    GPU hangs off, so that 8 ranks do not push their H2D / D2H traffic through one socket's memory and the inter-socket link."""
+    try:
+        props = torch.cuda.get_device_properties(dev)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        cpus = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"cpus {cpus} (NUMA node {open(f'/sys/bus/pci/devices/{bdf}/numa_node').read().strip()})"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+    return "not bound"
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -308,6 +327,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     group = None
+    numa = bind_to_gpu_numa_node(dev) if world > 1 else "single GPU: not bound"
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         group = dist.group.WORLD
@@ -532,7 +552,7 @@ def run_ours(args):
                      f"row-shard x{world}, one all-reduce of 16898 fp32 per step: " +
                      ("fused into the pass-1 kernel tail, LL push over peer-mapped NVLink memory (no NCCL call)" if collective == "nvlink" else "NCCL")),
                  "l2": "inputs 407 MB + output 136 MB per step exceed the 126 MB L2; no flush between steps (roofline.cold: flushed)",
-                 "simple_impl": args.simple_impl or "auto", "path": args.path}
+                 "simple_impl": args.simple_impl or "auto", "path": args.path, "host_numa_binding_rank0": numa}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg, "notes": notes,

@@ -165,6 +165,13 @@ int sigmoid_tc_ksplit(int64_t N, int64_t L, int H);
 int64_t sigmoid_tc_image_bytes(int64_t L, int H, int Hv);
 int sigmoid_fwd_tc(const float* q, const float* k, const float* v, int64_t N, int64_t L, int H, int Hv, float* out, float* rowsum,
                    float* pout, float* prs, int ksplit, void* images, cudaStream_t st);
+// sigmoid_bwd_sm100.cu
+bool sigmoid_bwd_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D);
+int sigmoid_bwd_tc_split(int64_t own_rows, int64_t streamed_rows, int H);
+int64_t sigmoid_bwd_tc_image_bytes(int64_t N, int64_t L, int H);
+int sigmoid_bwd_tc(const float* q, const float* k, const float* v, const float* g, const float* drow, const float* rowsum,
+                   int64_t N, int64_t L, int H, float* dq, float* dk, float* dv, void* images, int split_k, float* part_dq,
+                   int split_q, float* part_dk, float* part_dv, cudaStream_t st);
 int64_t simple_tc_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D);
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,

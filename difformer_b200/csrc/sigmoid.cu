@@ -459,12 +459,20 @@ static int sigmoid_bwd_split(int64_t rows, int64_t other, int heads) {
     return s < 1 ? 1 : (int)s;
 }
 
+static int64_t drow_floats(int64_t N, int H) { return (N * H + 15) & ~(int64_t)15; }    // 64-byte aligned
+
 extern "C" int64_t dif_sigmoid_bwd_workspace_bytes(int64_t N, int64_t L, int H, int Hv, int M, int D) {
     const int sq = sigmoid_bwd_split(N, L, H), skv = sigmoid_bwd_split(L, N, Hv == H ? H : 1);
     int64_t fl = N * H;                                                   // D_n = g.out
     int64_t a = sq > 1 ? (int64_t)sq * N * H * M : 0;                      // dq partials
     int64_t b = skv > 1 ? (int64_t)skv * (L * H * M + L * Hv * D) : 0;     // dk, dv partials
-    return (fl + (a > b ? a : b) + 64) * (int64_t)sizeof(float);
+    int64_t generic = (fl + (a > b ? a : b) + 64) * (int64_t)sizeof(float);
+    if (!sigmoid_bwd_tc_supported(N, L, H, Hv, M, D)) return generic;
+    // tcgen05 backward: D_n | bf16 hi/lo operand images of Qs, G, K, V + (D, 1/r) scalars | split partials
+    const int tq = sigmoid_bwd_tc_split(N, L, H), tkv = sigmoid_bwd_tc_split(L, N, H);
+    const int64_t pa = tq > 1 ? (int64_t)tq * N * H * M : 0, pb = tkv > 1 ? (int64_t)tkv * 2 * L * H * M : 0;
+    const int64_t tc = drow_floats(N, H) * 4 + sigmoid_bwd_tc_image_bytes(N, L, H) + (pa + pb) * 4 + 256;
+    return tc > generic ? tc : generic;
 }
 
 extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
@@ -476,12 +484,33 @@ extern "C" int dif_sigmoid_bwd(const float* q, const float* k, const float* v, c
     DIF_REQUIRE(workspace_bytes >= dif_sigmoid_bwd_workspace_bytes(N, L, H, Hv, M, D), DIF_EARG, "sigmoid_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     float* drow = (float*)workspace;
-    float* pbuf = drow + ((N * H + 15) & ~(int64_t)15);                   // 64-byte aligned partial buffers
+    float* pbuf = drow + drow_floats(N, H);                               // 64-byte aligned partial buffers
     {
         const int64_t rows = N * H;
         const int64_t threads = rows * 32;
         sigmoid_drow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g, out, rows, D, drow);
         DIF_LAUNCH_OK();
+    }
+    if (g_sigmoid_impl != DIF_IMPL_GENERIC && sigmoid_bwd_tc_supported(N, L, H, Hv, M, D)) {
+        // ---- tensor-core backward (sigmoid_bwd_sm100.cu): operand images, then the dq kernel and the dk/dv kernel
+        uint8_t* images = reinterpret_cast<uint8_t*>(pbuf);
+        float* part_dq = reinterpret_cast<float*>(images + sigmoid_bwd_tc_image_bytes(N, L, H));
+        const int tq = sigmoid_bwd_tc_split(N, L, H), tkv = sigmoid_bwd_tc_split(L, N, H);
+        float* part_dk = part_dq + (tq > 1 ? (int64_t)tq * N * H * M : 0);
+        float* part_dv = part_dk + (int64_t)tkv * L * H * M;
+        if ((rc = sigmoid_bwd_tc(q, k, v, g, drow, rowsum, N, L, H, dq, dk, dv, images, tq, part_dq, tkv, part_dk, part_dv, st))) return rc;
+        if (tq > 1) {
+            const int64_t c4 = N * H * M / 4;
+            sum_partials_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, st>>>(part_dq, tq, c4, dq);
+            DIF_LAUNCH_OK();
+        }
+        if (tkv > 1) {
+            const int64_t c4 = L * H * M / 4;
+            sum_partials_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, st>>>(part_dk, tkv, c4, dk);
+            sum_partials_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, st>>>(part_dv, tkv, c4, dv);
+            DIF_LAUNCH_OK();
+        }
+        return DIF_OK;
     }
     SigArgs a{};
     a.q = q; a.k = k; a.v = v; a.g = g; a.out = out; a.rowsum = rowsum; a.drow = drow;

@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
     __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], bbar;
     __shared__ uint32_t tmem_slot;
     __shared__ float part[16];
-    __shared__ float red[H == 1 ? 64 * 65 : 2048];                  // z / u partial sums of the converters (H == 1: + block-1 half of S)
+    __shared__ __align__(16) float red[H == 1 ? 64 * 65 : 2048];    // z / u partial sums of the converters, S halves (H == 1), fp64 chains of the tail
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
     const int64_t r1 = min(a.N, r0 + (int64_t)a.rows_per_cta);

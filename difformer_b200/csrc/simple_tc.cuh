@@ -178,7 +178,13 @@ inline int launch_persistent(const void* kernel, int grid, int threads, size_t s
     static const int persist_mb = env_int("DIF_TC_L2_PERSIST_MB", -1);      // experiment: L2 set-aside for evict_last lines
     static bool persist_set = false;
     if (persist_mb >= 0 && !persist_set) {
-        DIF_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20));
+        int dev = 0, mx = 0;
+        DIF_CUDA_OK(cudaGetDevice(&dev));
+        DIF_CUDA_OK(cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, dev));
+        size_t want = (size_t)persist_mb << 20;
+        if (want > (size_t)mx) want = (size_t)mx;
+        fprintf(stderr, "[difformer_b200] persisting L2 set-aside: %zu MB (device maximum %d MB)\n", want >> 20, mx >> 20);
+        DIF_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
         persist_set = true;
     }
     if (mode == 0) {
