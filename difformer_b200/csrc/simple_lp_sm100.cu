@@ -422,8 +422,8 @@ int simple_forward_lp(const void* q, const void* k, const void* v, int dtype, in
     LpArgs la{};
     ReduceArgs1& a = la.r;
     a.N = N; a.rows_per_cta = rpc;
-    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
-    la.flags2 = a.flags + grid + 1;
+    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((char*)ws + fused_ws_flags_off(grid, ws_len));
+    la.flags2 = a.flags + (int64_t)(grid + 1) * kFlagStride;
     a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
     a.partials = partials; a.prepared = (uint8_t*)ws + poff;
     a.n_total = (float)n_total;

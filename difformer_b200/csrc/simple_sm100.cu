@@ -1516,8 +1516,8 @@ int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N,
     FusedArgs fa{};
     ReduceArgs1& a = fa.r;
     a.q = q; a.k = k; a.v = v; a.N = N; a.rows_per_cta = rpc;
-    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((float*)ws + (int64_t)grid * ws_len);
-    fa.flags2 = a.flags + grid + 1;
+    a.ws = (float*)ws; a.ws_len = ws_len; a.flags = (unsigned long long*)((char*)ws + fused_ws_flags_off(grid, ws_len));
+    fa.flags2 = a.flags + (int64_t)(grid + 1) * kFlagStride;
     a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
     a.partials = partials; a.prepared = (uint8_t*)ws + poff;
     a.vbar = nullptr;

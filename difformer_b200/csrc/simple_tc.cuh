@@ -208,11 +208,12 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 int64_t tc_ws_len(int H) { return (SimpleLayout{H, H, kDim, kDim}.len() + 7) & ~(int64_t)7; }   // 32-byte aligned records (256-bit stores)
 
-// workspace: [records grid x ws_len f32][flags (grid + 1) u64][flags2 grid u64][pad to 128][B-operand image]
-int64_t fused_ws_prepared_off(int grid, int64_t ws_len) {
-    const int64_t off = (int64_t)grid * ws_len * 4 + (int64_t)(2 * grid + 1) * 8;
-    return (off + 127) & ~(int64_t)127;
-}
+// Grid-barrier flags of the one-kernel forward: one 128-byte line per CTA.  All CTAs poll all flags: with the flags packed 16 to
+// a line, ~19 000 polling threads hammer ten L2 lines and the flag STORES queue behind the polls (measured: a 5 us barrier).
+constexpr int kFlagStride = 16;      // u64 per flag slot
+// workspace: [records grid x ws_len f32][pad to 128][flags (grid + 1) lines][flags2 grid lines][B-operand image]
+int64_t fused_ws_flags_off(int grid, int64_t ws_len) { return ((int64_t)grid * ws_len * 4 + 127) & ~(int64_t)127; }
+int64_t fused_ws_prepared_off(int grid, int64_t ws_len) { return fused_ws_flags_off(grid, ws_len) + (int64_t)(2 * grid + 1) * kFlagStride * 8; }
 
 
 // ------------------------------------------------------------------------------------------
@@ -304,9 +305,9 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
     bar_sync_named(2, 128);
     if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 5] = gtime();
     const int grid = gridDim.x;
-    const unsigned long long gen = *reinterpret_cast<volatile unsigned long long*>(a.flags + grid);
+    const unsigned long long gen = *reinterpret_cast<volatile unsigned long long*>(a.flags + (int64_t)grid * kFlagStride);
     const unsigned long long epoch = a.epoch + gen * 0x9E3779B97F4A7C15ull;
-    if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + blockIdx.x), "l"(epoch) : "memory");
+    if (te == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.flags + (int64_t)blockIdx.x * kFlagStride), "l"(epoch) : "memory");
     const int chunk = (int)((((a.ws_len + kSlices - 1) / kSlices) + 3) & ~(int64_t)3);
     const ShardArgs& sh = a.sh;
     const bool sharded = sh.world > 1;
@@ -319,16 +320,18 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
         const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
         if (slice <= 0) break;
         if (!waited) {
-            // relaxed polling, ONE acquire fence after the last flag: an acquire load per poll costs a fence each
-            for (int r = te; r < grid; r += 128) {
-                unsigned long long f;
-                do {
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + r) : "memory");
-                } while (f != epoch);
+            // ONE warp polls (relaxed loads, one acquire fence after the last flag): few pollers, one flag per L2 line
+            if (te < 32) {
+                for (int r = te; r < grid; r += 32) {
+                    unsigned long long f;
+                    do {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + (int64_t)r * kFlagStride) : "memory");
+                    } while (f != epoch);
+                }
+                __threadfence();
             }
-            __threadfence();
             bar_sync_named(2, 128);                      // every record is published and (through the acquiring threads) visible
-            if (blockIdx.x == 0 && te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + grid) = gen + 1;
+            if (blockIdx.x == 0 && te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + (int64_t)grid * kFlagStride) = gen + 1;
             waited = true;
             if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 8] = gtime();
             // every CTA has finished pass 1: HBM idles until pass 2 starts -- pull the Q rows pass 2 reads LAST into L2 now
@@ -433,15 +436,17 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
     __threadfence();
     bar_sync_named(2, 128);
     const unsigned long long epoch2 = epoch + 1;
-    if (te == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(flags2 + blockIdx.x), "l"(epoch2) : "memory");   // ordered by the fence above
+    if (te == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(flags2 + (int64_t)blockIdx.x * kFlagStride), "l"(epoch2) : "memory");   // ordered by the fence above
     if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 10] = gtime();
-    for (int r = te; r < grid; r += 128) {
-        unsigned long long f;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags2 + r) : "memory");
-        } while (f != epoch2);
+    if (te < 32) {
+        for (int r = te; r < grid; r += 32) {
+            unsigned long long f;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags2 + (int64_t)r * kFlagStride) : "memory");
+            } while (f != epoch2);
+        }
+        __threadfence();
     }
-    __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     bar_sync_named(2, 128);
     if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 6] = gtime();
