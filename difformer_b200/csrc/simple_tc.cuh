@@ -173,6 +173,9 @@ int env_int(const char* name, int dflt) {
 //   DIF_TC_LAUNCH=2           plain launch + programmatic dependent launch: the kernel's prologue (barrier init, TMEM
 //                             allocation) overlaps the tail of the previous kernel in the stream; the kernels execute
 //                             griddepcontrol.wait before their first global access
+//   DIF_TC_LAUNCH=3           cooperative + programmatic dependent launch
+// The plain modes are opt-in: two such kernels on two streams can each hold part of the SMs and wait for the rest forever;
+// the cooperative launch is what rules that out.
 inline int launch_persistent(const void* kernel, int grid, int threads, size_t smem, cudaStream_t st, void** args) {
     static const int mode = env_int("DIF_TC_LAUNCH", 0);
     static const int persist_mb = env_int("DIF_TC_L2_PERSIST_MB", -1);      // experiment: L2 set-aside for evict_last lines
@@ -189,6 +192,18 @@ inline int launch_persistent(const void* kernel, int grid, int threads, size_t s
     }
     if (mode == 0) {
         DIF_CUDA_OK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), args, smem, st));
+        return DIF_OK;
+    }
+    if (mode == 3) {          // cooperative AND programmatic dependent launch (experiment: is the combination accepted?)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 2;
+        DIF_CUDA_OK(cudaLaunchKernelExC(&cfg, kernel, args));
         return DIF_OK;
     }
     int nb = 0;

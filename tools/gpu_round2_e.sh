@@ -8,7 +8,7 @@ tail -12 gpurun_out/r2_pytest_e.log
 rm -f gpurun_out/r2_stamps_e.csv
 DIF_TC_DEBUG_TIMES=1 DIF_TC_DEBUG_CSV=gpurun_out/r2_stamps_e.csv timeout 200 python tools/kbench.py --iters 3 --only-fused > gpurun_out/r2_timeline_fused_e.log 2>&1
 tail -16 gpurun_out/r2_timeline_fused_e.log
-( for cfg in "0 0 -1" "2 0 -1" "2 2 -1" "2 4 -1" "2 0 32" "2 0 64" "2 0 96" "2 4 64"; do set -- $cfg
+( for cfg in "0 0 -1" "2 0 -1" "3 0 -1" "2 2 -1" "2 4 -1" "2 0 32" "2 0 64" "2 0 96" "2 4 64"; do set -- $cfg
 DIF_TC_LAUNCH=$1 DIF_TC_FUSED_PF_TILES=$2 DIF_TC_L2_PERSIST_MB=$3 timeout 200 python tools/kbench.py --iters 400 --only-fused --tag "launch=$1 pf=$2 persist=$3" 2>&1 | tail -2
 done
 DIF_TC_LAUNCH=2 timeout 200 python tools/kbench.py --iters 400 --dtype f16 --tag "launch=2" 2>&1 | tail -1
