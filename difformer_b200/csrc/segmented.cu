@@ -793,10 +793,13 @@ extern "C" int dif_segmented_simple_fwd(const float* q, const float* k, const fl
     return DIF_OK;
 }
 
-extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
-                                        const int32_t* seg_ptr, int32_t B, const float* norms,
-                                        int64_t N, int H, int Hv, int M, int D, float* dq, float* dk, float* dv,
-                                        void* workspace, int64_t workspace_bytes, void* stream) {
+// phase 0: everything.  Graphs sharded over ranks: phase 1 stops once the batch-wide scalars (t_q, t_k) of THIS rank's graphs
+// are at workspace float offset 2 B; the caller all-reduces those two floats; phase 2 finishes (dq, dk, dv) with the totals.
+extern "C" int dif_segmented_simple_bwd_phase(const float* q, const float* k, const float* v, const float* g, const float* out,
+                                              const int32_t* seg_ptr, int32_t B, const float* norms,
+                                              int64_t N, int H, int Hv, int M, int D, float* dq, float* dk, float* dv,
+                                              void* workspace, int64_t workspace_bytes, int phase, void* stream) {
+    DIF_REQUIRE(phase >= 0 && phase <= 2, DIF_EARG, "segmented_bwd: phase %d", phase);
     int rc = seg_check(N, B, H, Hv, M, D, true);
     if (rc) return rc;
     DIF_REQUIRE(q && k && v && g && out && seg_ptr && norms && dq && dk && dv && workspace, DIF_EARG, "segmented_bwd: null pointer");
@@ -809,7 +812,7 @@ extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const fl
     const int grid = B < 148 * 16 ? B : 148 * 16;
     cudaStream_t st = (cudaStream_t)stream;
     const bool warp_path = (M == 64 && D == 64);
-    if (warp_path) {
+    if (warp_path && phase != 2) {
         // graphs with <= 64 rows: one warp per graph, direct form; writes dq, dk (without the t terms), dv and part[g]
         const size_t wsmem = (size_t)kWarpsPerCta * (2 * kWarpBufFloats + 2 * kWarpMaxRows) * sizeof(float);
         static bool attr = false;
@@ -817,10 +820,10 @@ extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const fl
         const int wgrid = (int)std::min<int64_t>(((int64_t)B + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 16);
         seg_bwd_warp_kernel<<<wgrid, kWarpsPerCta * 32, wsmem, st>>>(a);
         DIF_LAUNCH_OK();
-        a.min_rows = kWarpMaxRows;       // the CTA kernels below only take the larger graphs
     }
+    if (warp_path) a.min_rows = kWarpMaxRows;       // the CTA kernels below only take the larger graphs
     // M,D <= 64 => (M/4)*(D/4) <= 256 => one 4x4 tile per thread
-    {
+    if (phase != 2) {
         const size_t smem = ((size_t)M * D + M + D + (size_t)kSegRows * (M + 4) + 2 * (size_t)kSegRows * (D + 4) + kSegRows + 33) * sizeof(float);
         if ((rc = seg_smem(seg_bwd_scalars_kernel<1>, smem))) return rc;
         seg_bwd_scalars_kernel<1><<<grid, kThreads, smem, st>>>(a);
@@ -828,6 +831,7 @@ extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const fl
         seg_sum_pairs_kernel<<<1, 1024, 0, st>>>(part, B, scal);
         DIF_LAUNCH_OK();
     }
+    if (phase == 1) return DIF_OK;
     {
         const size_t smem = (2 * (size_t)M * D + 2 * (size_t)(M + D) + (size_t)kSegRows * (M + 4) + 2 * (size_t)kSegRows * (D + 4) + kSegRows) * sizeof(float);
         if ((rc = seg_smem(seg_bwd_main_kernel<1>, smem))) return rc;
@@ -839,4 +843,11 @@ extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const fl
         DIF_LAUNCH_OK();
     }
     return DIF_OK;
+}
+
+extern "C" int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,
+                                        const int32_t* seg_ptr, int32_t B, const float* norms,
+                                        int64_t N, int H, int Hv, int M, int D, float* dq, float* dk, float* dv,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    return dif_segmented_simple_bwd_phase(q, k, v, g, out, seg_ptr, B, norms, N, H, Hv, M, D, dq, dk, dv, workspace, workspace_bytes, 0, stream);
 }

@@ -597,17 +597,21 @@ class _SegmentedSimple(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         qs, ks, vs, seg_ptr, norms, out = ctx.saved_tensors
-        if ctx.group is not None and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
-            raise NotImplementedError("segmented backward across ranks needs an all-reduce of (t_q, t_k); single rank only")
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
         B = seg_ptr.numel() - 1
         g = _f32c(g)
         dq, dk, dv = torch.empty_like(qs), torch.empty_like(ks), torch.empty_like(vs)
-        ws = workspace(qs.device, lib.dif_segmented_workspace_bytes(B))
+        sharded = ctx.group is not None and dist.is_initialized() and dist.get_world_size(getattr(ctx.group, "group", ctx.group)) > 1
+        # graphs sharded over ranks: a private workspace (it must survive the all-reduce between the two phases)
+        wsb = max(int(lib.dif_segmented_workspace_bytes(B)), 16)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=qs.device) if sharded else workspace(qs.device, wsb)
         with torch.cuda.device(qs.device):
-            check(lib.dif_segmented_simple_bwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(), seg_ptr.data_ptr(), B,
-                                               norms.data_ptr(), N, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                               ws.data_ptr(), ws.numel(), _stream(qs)), "dif_segmented_simple_bwd")
+            for phase in ((1, 2) if sharded else (0,)):
+                check(lib.dif_segmented_simple_bwd_phase(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(), seg_ptr.data_ptr(), B,
+                                                         norms.data_ptr(), N, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                         ws.data_ptr(), ws.numel(), phase, _stream(qs)), "dif_segmented_simple_bwd")
+                if phase == 1:       # the batch-wide scalars (t_q, t_k): this rank's graphs -> all graphs
+                    _allreduce(ws.view(torch.float32)[2 * B:2 * B + 2], ctx.group)
         return dq, dk, dv, None, None
 
 

@@ -158,6 +158,14 @@ DIF_API int dif_segmented_simple_bwd(const float* q, const float* k, const float
                              int64_t N, int H, int Hv, int M, int D,
                              float* dq, float* dk, float* dv,
                              void* workspace, int64_t workspace_bytes, void* stream);
+/* Graphs sharded over ranks (whole graphs per rank): the backward needs the batch-wide scalars (t_q, t_k) summed over ALL ranks.
+ * phase 1 leaves this rank's two sums at workspace float offset 2*B and returns; all-reduce those two floats; phase 2 (same
+ * arguments, same workspace) finishes dq, dk, dv.  phase 0 = dif_segmented_simple_bwd. */
+DIF_API int dif_segmented_simple_bwd_phase(const float* q, const float* k, const float* v, const float* g, const float* out,
+                             const int32_t* seg_ptr, int32_t B, const float* norms,
+                             int64_t N, int H, int Hv, int M, int D,
+                             float* dq, float* dk, float* dv,
+                             void* workspace, int64_t workspace_bytes, int phase, void* stream);
 DIF_API int64_t dif_segmented_workspace_bytes(int32_t B);
 
 /* ------------------------------------------------------------------------------------------

@@ -85,6 +85,21 @@ for nvlink in (False, True):
         g = p.grad.clone()
         dist.all_reduce(g)                                   # what DDP would do with the replicated parameters
         assert O.rel_err(g, pr.grad) < 1e-3, (nvlink, name, O.rel_err(g, pr.grad))
+# batched graphs (difformer-v2) sharded by whole graphs: only the two norms (forward) and (t_q, t_k) (backward) cross ranks
+gen = torch.Generator().manual_seed(21)
+nn_all = torch.randint(1, 90, (64 * world + 3,), generator=gen)
+tot = int(nn_all.sum())
+q, k, v = O.synthetic_qkv(tot, 1, 64, seed=8, adversarial=True)
+g = torch.randn(tot, 1, 64, generator=gen)
+want = O.segmented_simple_attention(q.double(), k.double(), v.double(), nn_all)
+dq, dk, dv = O.segmented_simple_attention_backward(q.double(), k.double(), v.double(), nn_all, g.double())
+gb, ge = shard_rows(nn_all.numel(), rank, world)            # graphs [gb, ge) live on this rank
+rb, re_ = int(nn_all[:gb].sum()), int(nn_all[:ge].sum())
+qs, ks, vs = (t[rb:re_].to(dev).requires_grad_(True) for t in (q, k, v))
+out = ops.segmented_full_attention(qs, ks, vs, "simple", nn_all[gb:ge].to(dev), group=dist.group.WORLD)
+out.backward(g[rb:re_].to(dev))
+errs = [O.rel_err(out, want[rb:re_]), O.rel_err(qs.grad, dq[rb:re_]), O.rel_err(ks.grad, dk[rb:re_]), O.rel_err(vs.grad, dv[rb:re_])]
+assert max(errs) < 1e-3, ("segmented", errs)
 dist.barrier()
 if world == 2 and os.environ.get("DIF_TEST_WATCHDOG", "1") == "1":
     # watchdog: rank 0 launches an exchange its peer never joins -> the kernel gives up (DIF_COMM_TIMEOUT_MS) instead of
