@@ -130,6 +130,8 @@ def simple_forward(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, n_total
     wsb = int(lib.dif_simple_forward_workspace_bytes(N, H, Hv, M, D))
     if wsb <= 0 or (qs.dtype != torch.float32 and (M != 64 or D != 64)):      # the 128-wide variant is fp32 only
         return None
+    if qs.dtype == torch.float16:                                               # native 16-bit kernel: bf16 only
+        return None
     dev = qs.device
     if not (qs.dtype == ks.dtype == vs.dtype) or qs.dtype not in _DTYPES:
         raise TypeError(f"difformer_b200: qs/ks/vs must share one of float32 / bfloat16 / float16, got {qs.dtype}, {ks.dtype}, {vs.dtype}")
@@ -259,10 +261,11 @@ def _simple_backward(qs, ks, vs, out, partials, g, n_tot, group):
 
 
 class _SimpleAttention16(torch.autograd.Function):
-    """'simple' on bfloat16 / float16 node tensors (the Linear outputs under autocast): the forward runs the 16-bit one-kernel
-    path (dif_simple_forward with DIF_DTYPE_BF16/F16: TMA-landed tiles go straight to the tensor cores, fp32 accumulation and
-    partials, 16-bit output -- half the HBM bytes).  Shapes outside the tcgen05 set compute in fp32 and round the result.
-    The backward up-casts the saved tensors and runs the fp32 kernels; gradients are returned in the input dtype."""
+    """'simple' on bfloat16 / float16 node tensors (the Linear outputs under autocast).  bfloat16: the forward runs the 16-bit
+    one-kernel path (dif_simple_forward with DIF_DTYPE_BF16: TMA-landed tiles go straight to the tensor cores, fp32
+    accumulation and partials, bf16 output -- half the HBM bytes).  float16, and shapes outside the tcgen05 set, compute in
+    fp32 (up-cast, fp32 kernels) and round the result.  The backward up-casts the saved tensors and runs the fp32 kernels;
+    gradients are returned in the input dtype."""
 
     @staticmethod
     def forward(ctx, qs, ks, vs, group, n_total):

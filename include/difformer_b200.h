@@ -116,9 +116,10 @@ DIF_API int dif_simple_apply(const float* q, const float* partials, const void* 
  * receives the (all-reduced) pass-1 partials, which the backward needs.  n_total = global row count (= N unsharded).
  * `workspace` must be 128-byte aligned.  peer_bufs / rank / world / seq as in dif_simple_reduce_allreduce (NULL, 0, 1, 0
  * for a single GPU).  Other shapes return DIF_EUNSUPPORTED: call dif_simple_reduce + dif_simple_apply.
- * `dtype` = element type of q, k, v AND out: DIF_DTYPE_F32, or DIF_DTYPE_BF16 / DIF_DTYPE_F16 (the Linear outputs under
- * autocast): the 16-bit kernel feeds the TMA-landed tiles straight to the tensor cores (no conversion pass, exact products,
- * fp32 accumulation and fp32 partials) and moves 2048 instead of 4096 algorithmic bytes per node at H = 4, D = 64. */
+ * `dtype` = element type of q, k, v AND out: DIF_DTYPE_F32 or DIF_DTYPE_BF16 (the Linear outputs under bf16 autocast): the
+ * bf16 kernel feeds the TMA-landed tiles straight to the tensor cores (no conversion pass, exact products, fp32 accumulation
+ * and fp32 partials) and moves 2048 instead of 4096 algorithmic bytes per node at H = 4, D = 64.  DIF_DTYPE_F16 returns
+ * DIF_EUNSUPPORTED: up-cast fp16 tensors and use the fp32 kernel (what difformer_b200.ops does). */
 DIF_API int64_t dif_simple_forward_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 DIF_API int dif_simple_forward(const void* q, const void* k, const void* v, int dtype,
                        int64_t N, int H, int Hv, int M, int D, double n_total,
