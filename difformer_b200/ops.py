@@ -285,13 +285,13 @@ class _SimpleAttention16(torch.autograd.Function):
             with torch.no_grad():
                 o32 = _SimpleAttention.apply(qs.float(), ks.float(), vs.float(), group, n_total)
             out, partials = o32.to(qs.dtype), None
-        ctx.save_for_backward(qs, ks, vs, out, partials)
+        ctx.save_for_backward(qs, ks, vs, partials)
         ctx.group, ctx.n_tot = group, n_tot
         return out
 
     @staticmethod
     def backward(ctx, g):
-        qs, ks, vs, out, partials = ctx.saved_tensors
+        qs, ks, vs, partials = ctx.saved_tensors
         q32, k32, v32 = qs.float(), ks.float(), vs.float()
         if partials is None:
             partials = simple_partials(q32, k32, v32)
@@ -300,7 +300,10 @@ class _SimpleAttention16(torch.autograd.Function):
                 partials = xch(partials.numel(), qs.device).allreduce(partials)
             else:
                 _allreduce(partials, ctx.group)
-        dq, dk, dv = _simple_backward(q32, k32, v32, out.float(), partials, g.float().contiguous(), ctx.n_tot, ctx.group)
+        # the saved output is rounded to 16 bits; dden = -(g . out)/den is a cancellation that needs the fp32 values: pass 2 again
+        # on the up-cast rows (T read + T write of fp32, a fraction of the backward)
+        out32 = simple_apply(q32, partials, ctx.n_tot, vs.shape[1], vs.shape[2])
+        dq, dk, dv = _simple_backward(q32, k32, v32, out32, partials, g.float().contiguous(), ctx.n_tot, ctx.group)
         return dq.to(qs.dtype), dk.to(ks.dtype), dv.to(vs.dtype), None, None
 
 
