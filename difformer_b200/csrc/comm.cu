@@ -40,10 +40,7 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const __grid_constant__ 
             if (r >= c.world) r -= c.world;
             comm_ll_send(comm_ll_ptr(c.bufs[r], c.lenpad, slot, c.rank) + i, mine, tag);
         }
-        float s = 0.f;
-        for (int r = 0; r < c.world; ++r)
-            s += r == c.rank ? mine : comm_ll_recv(comm_ll_ptr(c.bufs[c.rank], c.lenpad, slot, r) + i, tag, c);
-        a.out[i] = s;
+        a.out[i] = comm_ll_sum(c, slot, i, tag, mine);
     }
 }
 

@@ -159,6 +159,40 @@ __device__ __forceinline__ float comm_ll_recv(const unsigned long long* src, uin
         }
     }
 }
+// Receive element j of every peer's contribution (LL words of call `tag` in this rank's own buffer) and return the sum over ALL ranks
+// in rank order, `mine` being this rank's term.  The pending words are loaded back to back each polling round (one L2 round trip
+// per round, not one per peer); bounded like comm_ll_recv.
+static __device__ __noinline__ float comm_ll_sum(const CommPeers& c, int slot, int64_t j, uint32_t tag, float mine) {
+    float v[kCommMaxRanks];
+    unsigned int pending = 0;
+    for (int r = 0; r < c.world; ++r)
+        if (r != c.rank) pending |= 1u << r;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (pending) {
+        unsigned long long w[kCommMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kCommMaxRanks; ++r)
+            if (pending & (1u << r))
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[r]) : "l"(comm_ll_ptr(c.bufs[c.rank], c.lenpad, slot, r) + j) : "memory");
+#pragma unroll
+        for (int r = 0; r < kCommMaxRanks; ++r)
+            if ((pending & (1u << r)) && (uint32_t)(w[r] >> 32) == tag) { v[r] = __uint_as_float((uint32_t)w[r]); pending &= ~(1u << r); }
+        if (pending && (++spins & 1023u) == 0) {
+            unsigned long long now, s;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(comm_status_ptr(c.bufs[c.rank])) : "memory");
+            if (now - t0 > c.timeout_ns || s != 0) { comm_fail(c); return 0.f; }
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r)
+        if (r < c.world) sum += r == c.rank ? mine : v[r];
+    return sum;
+}
+
 // sigmoid_sm100.cu
 bool sigmoid_tc_supported(int64_t N, int64_t L, int H, int Hv, int M, int D);
 int sigmoid_tc_ksplit(int64_t N, int64_t L, int H);

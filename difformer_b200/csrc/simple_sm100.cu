@@ -376,9 +376,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                     if (r >= sh.world) r -= sh.world;
                     comm_ll_send(comm_ll_ptr(sh.bufs[r], sh.lenpad, xslot, sh.rank) + j, local, tag);
                 }
-                sum = 0.f;
-                for (int r = 0; r < sh.world; ++r)
-                    sum += r == sh.rank ? local : comm_ll_recv(comm_ll_ptr(sh.bufs[sh.rank], sh.lenpad, xslot, r) + j, tag, sh);
+                sum = comm_ll_sum(sh, xslot, j, tag, local);
             }
         }
         if (live) {

@@ -244,6 +244,25 @@ int64_t fused_ws_prepared_off(int grid, int64_t ws_len) { return fused_ws_flags_
 // `red` : shared scratch, >= 64*65 floats when H == 1 (block halves of S), >= 1024 floats otherwise (chains of the slice sum).
 // Uses named barrier 2 (128 threads).  No shared memory of the pipelines is touched: the Q prefetch of pass 2 may run.
 // ------------------------------------------------------------------------------------------
+// lane `l` of the polling warp waits until flags l, l + 32, ... (< grid, one per 128-byte line) all hold `epoch`, then fences (acquire)
+__device__ __forceinline__ void poll_flags(const unsigned long long* flags, int grid, int l, unsigned long long epoch) {
+    constexpr int kMax = 8;                               // grid <= 256
+    bool ok;
+    do {
+        unsigned long long f[kMax];
+#pragma unroll
+        for (int i = 0; i < kMax; ++i) {
+            const int r = l + 32 * i;
+            f[i] = epoch;
+            if (r < grid) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f[i]) : "l"(flags + (int64_t)r * kFlagStride) : "memory");
+        }
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < kMax; ++i) ok = ok && f[i] == epoch;
+    } while (!ok);
+    __threadfence();
+}
+
 template <int H, bool W = false>
 __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long long* flags2, float* rec, int te, int ew, int lane,
                                            uint32_t tmem, bool have_rows, float* red, const void* pf_ptr = nullptr,
@@ -335,16 +354,9 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
         const int slice = (int)max((int64_t)0, min(a.ws_len, j0 + chunk) - j0);
         if (slice <= 0) break;
         if (!waited) {
-            // ONE warp polls (relaxed loads, one acquire fence after the last flag): few pollers, one flag per L2 line
-            if (te < 32) {
-                for (int r = te; r < grid; r += 32) {
-                    unsigned long long f;
-                    do {
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(a.flags + (int64_t)r * kFlagStride) : "memory");
-                    } while (f != epoch);
-                }
-                __threadfence();
-            }
+            // ONE warp polls (relaxed loads, one acquire fence after the last flag): few pollers, one flag per L2 line; a lane's
+            // (up to 5) flags are loaded back to back -- one L2 round trip per polling round, not one per flag
+            if (te < 32) poll_flags(a.flags, grid, te, epoch);
             bar_sync_named(2, 128);                      // every record is published and (through the acquiring threads) visible
             if (blockIdx.x == 0 && te == 0) *reinterpret_cast<volatile unsigned long long*>(a.flags + (int64_t)grid * kFlagStride) = gen + 1;
             waited = true;
@@ -358,7 +370,7 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
         }
         // Slice sum.  Four groups of 32 threads; group g walks the records r = 4i + g (the four fixed chains of the sum), lane l
         // owns the four consecutive elements 4l..4l+3 of the slice and reads them as ONE 16-byte load per record straight from
-        // L2 (ld.cg), 13 loads in flight: ~3 L2 round trips for the whole slice.  Chains are fp64 and are combined in the
+        // L2 (ld.cg), 19 loads in flight: 2 L2 round trips for the whole slice at 148 records.  Chains are fp64 and are combined in the
         // fixed order (c0 + c1) + (c2 + c3): deterministic, identical to the two-launch path.
         {
             const int g = te >> 5, l = te & 31;
@@ -368,12 +380,12 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
                 const int64_t ld = a.ws_len;
                 const int gmain = grid & ~3;             // records beyond the last full group of four all belong to chain 0
                 int r = g;
-                for (; r + 4 * 12 < gmain; r += 4 * 13) {
-                    float4 x[13];
+                for (; r + 4 * 18 < gmain; r += 4 * 19) {
+                    float4 x[19];
 #pragma unroll
-                    for (int i = 0; i < 13; ++i) x[i] = __ldcg(reinterpret_cast<const float4*>(col + (int64_t)(r + 4 * i) * ld));
+                    for (int i = 0; i < 19; ++i) x[i] = __ldcg(reinterpret_cast<const float4*>(col + (int64_t)(r + 4 * i) * ld));
 #pragma unroll
-                    for (int i = 0; i < 13; ++i) { c0 += (double)x[i].x; c1 += (double)x[i].y; c2 += (double)x[i].z; c3 += (double)x[i].w; }
+                    for (int i = 0; i < 19; ++i) { c0 += (double)x[i].x; c1 += (double)x[i].y; c2 += (double)x[i].z; c3 += (double)x[i].w; }
                 }
                 for (; r < gmain; r += 4) {
                     const float4 x = __ldcg(reinterpret_cast<const float4*>(col + (int64_t)r * ld));
@@ -412,9 +424,7 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
                 if (r >= sh.world) r -= sh.world;
                 comm_ll_send(comm_ll_ptr(sh.bufs[r], sh.lenpad, xslot, sh.rank) + j, local, tag);
             }
-            sum = 0.f;
-            for (int r = 0; r < sh.world; ++r)
-                sum += r == sh.rank ? local : comm_ll_recv(comm_ll_ptr(sh.bufs[sh.rank], sh.lenpad, xslot, r) + j, tag, sh);
+            sum = comm_ll_sum(sh, xslot, j, tag, local);
         }
         if (live) {
             a.partials[j] = sum;
@@ -453,15 +463,7 @@ __device__ __forceinline__ void fused_tail(const ReduceArgs1& a, unsigned long l
     const unsigned long long epoch2 = epoch + 1;
     if (te == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(flags2 + (int64_t)blockIdx.x * kFlagStride), "l"(epoch2) : "memory");   // ordered by the fence above
     if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 10] = gtime();
-    if (te < 32) {
-        for (int r = te; r < grid; r += 32) {
-            unsigned long long f;
-            do {
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags2 + (int64_t)r * kFlagStride) : "memory");
-            } while (f != epoch2);
-        }
-        __threadfence();
-    }
+    if (te < 32) poll_flags(flags2, grid, te, epoch2);
     asm volatile("fence.proxy.async;" ::: "memory");
     bar_sync_named(2, 128);
     if (dbg != nullptr && te == 0) dbg[blockIdx.x * kDbgSlots + 6] = gtime();
