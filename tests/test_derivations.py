@@ -1,7 +1,7 @@
 """CPU: the closed forms the CUDA kernels implement, restated in a few lines of fp64 torch and checked against the
 oracle (which is itself pinned to the reference by tests/golden/).  These are the derivations a reader needs to trust
 before reading the kernels: csrc/segmented.cu (warp-per-graph direct form + t fix-up), csrc/sigmoid_sm100.cu
-(paired reciprocal, hi/lo operand split, [hi | lo] accumulate) and drafts/sigmoid_bwd_sm100.cu (e P^2 form)."""
+(paired reciprocal, hi/lo operand split, [hi | lo] accumulate) and csrc/sigmoid_bwd_sm100.cu (e P^2 form)."""
 import math
 
 import torch
