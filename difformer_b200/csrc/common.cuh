@@ -214,6 +214,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st);
 
+bool simple_wide_supported(int64_t N, int H, int Hv, int M, int D);
 int64_t simple_fused_workspace_bytes(int64_t N, int H, int Hv, int M, int D);
 int simple_forward_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D, double n_total,
                       float* partials, float* out, void* ws, int64_t ws_bytes, cudaStream_t st,

@@ -38,11 +38,11 @@ constexpr int kLpNQ = 4;                      // pass-2 Q stages
 constexpr int kLpOutBox = 32 * 128;           // per epilogue warp: [32 rows][64 x 16 bit]
 constexpr int kLpOutStage = 4 * 2 * kLpOutBox;   // 4 warps x double buffer
 
-template <int H>
+template <int H, bool W = false>
 struct LpGeo {
     static constexpr int kStage = 3 * H * kLpTile;                      // K | V | Q tiles of all heads
     static constexpr int kSmem1 = kLpNS * kStage;
-    static constexpr int kSmem2 = Geo<H>::kBBytes + kLpNQ * kLpQTile + kLpOutStage + H * kDim * 4;
+    static constexpr int kSmem2 = PLay<H, W>::kBBytes + kLpNQ * kLpQTile + kLpOutStage + H * kDim * 4;
     static constexpr int kSmem = (kSmem1 > kSmem2 ? kSmem1 : kSmem2) + 1024;
     static constexpr int kChunks = H * 8;                               // 16-byte chunks per node row of one tensor
     static constexpr int kRowGroups = 256 / kChunks;                    // sum threads = 256
@@ -73,18 +73,22 @@ struct LpArgs {
     int store_hint, reverse, l2_hints, pf_tiles;
 };
 
-template <int H, class T>
+// W ("wide"): ONE head of M = D = 128 on the H = 2 geometry (see PLay, simple_tc.cuh): the two 64-column halves of a row play the
+// two heads in pass 1 (whose accumulator then is the whole S[128][128]); pass 2 contracts over K = 128 (two Q stages per tile) into
+// the two output halves.
+template <int H, class T, bool W = false>
 __global__ void __launch_bounds__(kLpThreads, 1) simple_lp_kernel(const __grid_constant__ LpArgs la, const __grid_constant__ CUtensorMap mq,
                                                                  const __grid_constant__ CUtensorMap mk, const __grid_constant__ CUtensorMap mv,
                                                                  const __grid_constant__ CUtensorMap mo) {
     using G = Geo<H>;
-    using L = LpGeo<H>;
+    using L = LpGeo<H, W>;
+    using P = PLay<H, W>;
     const ReduceArgs1& a = la.r;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // pass 2 view
     uint8_t* Bop = base;
-    uint8_t* qring = base + G::kBBytes;
+    uint8_t* qring = base + P::kBBytes;
     uint8_t* ostage = qring + kLpNQ * kLpQTile;
     float* us = reinterpret_cast<float*>(ostage + kLpOutStage);
     __shared__ uint64_t full[kLpNS], empty[kLpNS], done;
@@ -191,22 +195,55 @@ __global__ void __launch_bounds__(kLpThreads, 1) simple_lp_kernel(const __grid_c
             const uint32_t qb = smem_u32(qring), b_base = smem_u32(Bop);
             pdl_launch_dependents();                    // the next kernel of the stream may start its prologue as SMs free up
             mbar_wait(&bbar, 0);
-            for (int sc = 0; sc < nsc; ++sc) {
-                const int s = sc % kLpNQ, slot = sc % kNAcc, h = sc % H;
-                if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
-                mbar_wait(&qfull[s], (sc / kLpNQ) & 1);
-                tc_fence_after();
-                const uint32_t sb = qb + s * kLpQTile, bb = b_base + h * 2 * kBOp;
-                const uint32_t d = tmem + slot * kAccCols;
+            if (!W) {
+                for (int sc = 0; sc < nsc; ++sc) {
+                    const int s = sc % kLpNQ, slot = sc % kNAcc, h = sc % H;
+                    if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+                    mbar_wait(&qfull[s], (sc / kLpNQ) & 1);
+                    tc_fence_after();
+                    const uint32_t sb = qb + s * kLpQTile, bb = b_base + h * 2 * kBOp;
+                    const uint32_t d = tmem + slot * kAccCols;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t qd = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO);
-                    const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
-                    umma(d, qd, bhi, idesc, ks > 0 ? 1u : 0u);
-                    umma(d, qd, blo, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t qd = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO);
+                        const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                        umma(d, qd, bhi, idesc, ks > 0 ? 1u : 0u);
+                        umma(d, qd, blo, idesc, 1u);
+                    }
+                    umma_commit(&qempty[s]);
+                    umma_commit(&tfull[slot]);
                 }
-                umma_commit(&qempty[s]);
-                umma_commit(&tfull[slot]);
+            } else {
+                // wide: stage = (tile, K block kb), accumulator slot = (tile, output half dh): both K blocks feed both halves
+                for (int sc = 0; sc < nsc; sc += 2) {
+                    const int slot0 = sc % kNAcc, slot1 = (sc + 1) % kNAcc;
+                    if (sc >= kNAcc) {
+                        mbar_wait(&tempty[slot0], ((sc / kNAcc) - 1) & 1);
+                        mbar_wait(&tempty[slot1], (((sc + 1) / kNAcc) - 1) & 1);
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const int st_ = sc + kb, s = st_ % kLpNQ;
+                        mbar_wait(&qfull[s], (st_ / kLpNQ) & 1);
+                        tc_fence_after();
+                        const uint32_t sb = qb + s * kLpQTile;
+#pragma unroll
+                        for (int dh = 0; dh < 2; ++dh) {
+                            const uint32_t bb = b_base + (2 * dh + kb) * 2 * kBOp;
+                            const uint32_t d = tmem + (dh == 0 ? slot0 : slot1) * kAccCols;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t qd = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO);
+                                const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                                umma(d, qd, bhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                                umma(d, qd, blo, idesc, 1u);
+                            }
+                        }
+                        umma_commit(&qempty[s]);
+                    }
+                    umma_commit(&tfull[slot0]);
+                    umma_commit(&tfull[slot1]);
+                }
             }
         }
     } else if (warp >= 4) {
@@ -269,39 +306,42 @@ __global__ void __launch_bounds__(kLpThreads, 1) simple_lp_kernel(const __grid_c
                 const int ccid = col >> 3, e = col & 7;
                 float zs = 0.f, usum = 0.f;
                 for (int g = 0; g < L::kRowGroups; ++g) { zs += red[(g * L::kChunks + ccid) * 16 + e]; usum += red[(g * L::kChunks + ccid) * 16 + 8 + e]; }
-                rec[G::offZ + col] = zs;
-                rec[G::offU + col] = usum;
+                rec[P::offZ + col] = zs;
+                rec[P::offU + col] = usum;
             }
             if (te == 0) {
                 float sk = 0.f, sq = 0.f;
                 for (int w = 0; w < 8; ++w) { sk += part[w]; sq += part[8 + w]; }
-                rec[G::offSq] = sq;
-                rec[G::offSq + 1] = sk;
+                rec[P::offSq] = sq;
+                rec[P::offSq + 1] = sk;
             }
             if (H == 1) bar_sync_named(2, 128);
             const int64_t pf_rows = min((int64_t)min(la.pf_tiles, my_tiles) * kTile2, r1 - r0);
-            fused_tail<H>(a, la.flags2, rec, te, ew, lane, tmem, iters > 0, red, reinterpret_cast<const __nv_bfloat16*>(a.q) + r0 * (H * kDim),
+            fused_tail<H, W>(a, la.flags2, rec, te, ew, lane, tmem, iters > 0, red, reinterpret_cast<const __nv_bfloat16*>(a.q) + r0 * (H * kDim),
                           (uint32_t)(max((int64_t)0, pf_rows) * H * kDim * 2));
             if (te == 0) {
-                mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
-                for (int i = 0; i < H * 2; ++i)
+                mbar_expect_tx(&bbar, (uint32_t)P::kBBytes);
+                for (int i = 0; i < P::kBTiles * 2; ++i)
                     tma_load_1d(smem_u32(Bop) + i * kBOp, a.prepared + (size_t)i * kBOp, (uint32_t)kBOp, &bbar);
             }
-            for (int i = te; i < H * kDim; i += 128) us[i] = __ldcg(a.partials + G::offU + i);
-            const float cscale = 1.f / (sqrtf(__ldcg(a.partials + G::offSq)) * sqrtf(__ldcg(a.partials + G::offSq + 1)));
+            for (int i = te; i < H * kDim; i += 128) us[i] = __ldcg(a.partials + P::offU + i);
+            const float cscale = 1.f / (sqrtf(__ldcg(a.partials + P::offSq)) * sqrtf(__ldcg(a.partials + P::offSq + 1)));
             bar_sync_named(2, 128);
             // =================== pass 2: epilogue: thread = one row; (c acc + u) / (c qz + N) -> 16-bit -> swizzled box -> TMA store ===================
             const uint32_t obox = smem_u32(ostage) + ew * 2 * kLpOutBox;
             const uint64_t pol = policy_evict_first();
+            float inv_den = 0.f;
             for (int sc = 0; sc < nsc; ++sc) {
                 const int64_t trow = row0_of(sc);
                 const int h = sc % H, slot = sc % kNAcc;
                 mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
-                uint32_t qz_bits = tmem_ld1(taddr + kDim);
-                tmem_ld_wait1(qz_bits);
-                const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, a.n_total));
+                if (!W || h == 0) {          // wide: the denominator column lives in the dh = 0 accumulator and serves both halves
+                    uint32_t qz_bits = tmem_ld1(taddr + kDim);
+                    tmem_ld_wait1(qz_bits);
+                    inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, a.n_total));
+                }
                 const uint32_t ob = obox + (sc & 1) * kLpOutBox;
                 if (lane == 0) tma_wait_read1();          // the store that used this buffer two stages ago has read it
                 __syncwarp();
@@ -383,30 +423,31 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
     return DIF_OK;
 }
 
-template <int H, class T>
+template <int H, class T, bool W = false>
 static int launch_lp(const LpArgs& a, const CUtensorMap* maps, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        DIF_CUDA_OK(cudaFuncSetAttribute(simple_lp_kernel<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LpGeo<H>::kSmem));
+        DIF_CUDA_OK(cudaFuncSetAttribute(simple_lp_kernel<H, T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, LpGeo<H, W>::kSmem));
         attr_set = true;
     }
     void* args[] = {(void*)&a, (void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3]};
-    return launch_persistent((const void*)simple_lp_kernel<H, T>, grid, kLpThreads, (size_t)LpGeo<H>::kSmem, st, args);
+    return launch_persistent((const void*)simple_lp_kernel<H, T, W>, grid, kLpThreads, (size_t)LpGeo<H, W>::kSmem, st, args);
 }
 
 int simple_forward_lp(const void* q, const void* k, const void* v, int dtype, int64_t N, int H, int Hv, int M, int D, double n_total,
                       float* partials, void* out, void* ws, int64_t ws_bytes, cudaStream_t st,
                       void* const* peer_bufs, int rank, int world, unsigned long long seq) {
-    DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
+    const bool wide = simple_wide_supported(N, H, Hv, M, D);
+    DIF_REQUIRE(wide || simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE(dtype == DIF_DTYPE_BF16, DIF_EUNSUPPORTED, "simple_forward(16-bit): bf16 only (dtype %d): up-cast fp16 and use the fp32 kernel", dtype);
     DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0, DIF_EARG, "simple_forward(16-bit): q/k/v/out must be 16-byte aligned");
     DIF_REQUIRE(((uintptr_t)ws & 127) == 0, DIF_EARG, "simple_forward: workspace must be 128-byte aligned");
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
     int grid;
     const int rpc = tc_rows_per_cta(N, H, &grid);
-    const int64_t ws_len = tc_ws_len(H);
+    const int64_t ws_len = wide ? PLay<2, true>::kWsLen : tc_ws_len(H);
     const int64_t poff = fused_ws_prepared_off(grid, ws_len);
-    DIF_REQUIRE(ws_bytes >= poff + (int64_t)H * 2 * kBOp, DIF_EARG, "simple_forward: workspace too small");
+    DIF_REQUIRE(ws_bytes >= poff + (wide ? (int64_t)PLay<2, true>::kBBytes : (int64_t)H * 2 * kBOp), DIF_EARG, "simple_forward: workspace too small");
     DIF_REQUIRE((((ws_len + kSlices - 1) / kSlices + 3) & ~(int64_t)3) <= 128, DIF_EUNSUPPORTED, "simple_forward: slice wider than the tail warps");
     static std::atomic<unsigned long long> epoch_src{0x5851F42D4C957F2Dull ^ (unsigned long long)(uintptr_t)&epoch_src};
     LpArgs la{};
@@ -433,12 +474,12 @@ int simple_forward_lp(const void* q, const void* k, const void* v, int dtype, in
     const int fp16 = 0;
     CUtensorMap maps[4];
     int rc;
-    if ((rc = make_map16(&maps[0], q, N, (int64_t)H * kDim, fp16))) return rc;
-    if ((rc = make_map16(&maps[1], k, N, (int64_t)H * kDim, fp16))) return rc;
-    if ((rc = make_map16(&maps[2], v, N, (int64_t)H * kDim, fp16))) return rc;
-    if ((rc = make_map16(&maps[3], out, N, (int64_t)H * kDim, fp16))) return rc;
+    if ((rc = make_map16(&maps[0], q, N, (int64_t)H * M, fp16))) return rc;
+    if ((rc = make_map16(&maps[1], k, N, (int64_t)H * M, fp16))) return rc;
+    if ((rc = make_map16(&maps[2], v, N, (int64_t)H * D, fp16))) return rc;
+    if ((rc = make_map16(&maps[3], out, N, (int64_t)H * D, fp16))) return rc;
 #define DIF_LP(T) (H == 4 ? launch_lp<4, T>(la, maps, grid, st) : H == 2 ? launch_lp<2, T>(la, maps, grid, st) : launch_lp<1, T>(la, maps, grid, st))
-    rc = DIF_LP(Bf16);
+    rc = wide ? launch_lp<2, Bf16, true>(la, maps, grid, st) : DIF_LP(Bf16);
 #undef DIF_LP
     if (rc) return rc;
     dbg_report("simple_lp", a.dbg, grid);

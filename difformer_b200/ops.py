@@ -128,7 +128,7 @@ def simple_forward(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, n_total
     if not _FUSED_FORWARD or _SIMPLE_IMPL == _lib.DIF_IMPL_GENERIC or N != L:
         return None
     wsb = int(lib.dif_simple_forward_workspace_bytes(N, H, Hv, M, D))
-    if wsb <= 0 or (qs.dtype != torch.float32 and (M != 64 or D != 64)):      # the 128-wide variant is fp32 only
+    if wsb <= 0:
         return None
     if qs.dtype == torch.float16:                                               # native 16-bit kernel: bf16 only
         return None

@@ -273,6 +273,15 @@ def test_one_kernel_forward_hidden_128(n):
         ops.set_simple_impl("auto")
     assert O.rel_err(flat, flat_g) < 1e-4 and O.rel_err(out, out_g) < 1e-5
     assert torch.equal(ops.simple_forward(qg, kg, vg)[0], out)          # deterministic
+    # bf16 I/O at the same width (simple_lp_kernel<2, Bf16, wide>): oracle on the rounded inputs
+    qb, kb, vb = (t.bfloat16() for t in (q, k, v))
+    res16 = ops.simple_forward(dev(qb), dev(kb), dev(vb))
+    assert res16 is not None
+    out16, flat16 = res16
+    want16 = O.simple_partials(qb.double(), kb.double(), vb.double())
+    S16, z16, u16, _, _ = _unpack(flat16, 1, 1, 128, 128)
+    assert O.rel_err(S16, want16["S"]) < 1e-4 and O.rel_err(z16, want16["z"]) < 1e-4 and O.rel_err(u16, want16["u"]) < 1e-4
+    assert out16.dtype == torch.bfloat16 and O.rel_err(out16.double(), O.simple_apply(qb.double(), want16)) < 2.0 ** -8
     # the public op with autograd: forward = this kernel, backward = the FFMA kernels fed with its partials
     qa, ka, va = (t.clone().requires_grad_(True) for t in (qg, kg, vg))
     o = difformer.full_attention_conv(qa, ka, va, "simple")
