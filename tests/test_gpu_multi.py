@@ -141,7 +141,14 @@ def _run(world, tmp_path, extra_env=None):
     env.update(extra_env or {})
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-4000:]
+    if res.returncode != 0 or res.stdout.count(" ok ") != world:
+        try:                                   # keep the workers' output where a remote run brings it back
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"multi_worker_world{world}.log"), "w") as f:
+                f.write(res.stdout)
+        except OSError:
+            pass
+    assert res.returncode == 0, res.stdout[-6000:]
     assert res.stdout.count(" ok ") == world
 
 
