@@ -626,8 +626,8 @@ def run_extra(args):
         def layer():
             vb_ = torch.empty((n, d), dtype=torch.float32, device=dev)
             part, prep = ops.simple_partials(q, k, v, with_prepared=True, vbar=vb_)
-            g = ops.spmm(csr, vb_.view(n, 1, d)).view(n, d)
-            ep = ops.make_epilogue(0.5 / h, [(g, 0.5), (prev, 0.5)])
+            # the gcn term is gathered by the pass-2 epilogue itself (CSR rows of mean_h V from L2): two launches per layer
+            ep = ops.make_epilogue(0.5 / h, [(prev, 0.5)], gcn=(csr, vb_, 0.5))
             return ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)
         ms = timeit(layer, steps)
         alg = n * (3 * h * d * 4 + 2 * d * 4) + E * 8 + (n + 1) * 4

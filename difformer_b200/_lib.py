@@ -19,7 +19,8 @@ class Epilogue(ctypes.Structure):
     """dif_epilogue_t"""
     _fields_ = [("mode", c_i32), ("attn_scale", ctypes.c_float), ("n_add", c_i32),
                 ("add", c_vp * 3), ("add_scale", ctypes.c_float * 3),
-                ("ln_weight", c_vp), ("ln_bias", c_vp), ("ln_eps", ctypes.c_float), ("relu", c_i32)]
+                ("ln_weight", c_vp), ("ln_bias", c_vp), ("ln_eps", ctypes.c_float), ("relu", c_i32),
+                ("gcn_rowptr", c_vp), ("gcn_idx", c_vp), ("gcn_val", c_vp), ("gcn_x", c_vp), ("gcn_scale", ctypes.c_float)]
 
 
 # name -> (restype, argtypes); mirrors include/difformer_b200.h one to one

@@ -636,8 +636,8 @@ int simple_apply_generic(const float* q, const float* partials, double n_total, 
     if (ep) a.ep = *ep; else { a.ep = dif_epilogue_t{}; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
     DIF_REQUIRE(a.ep.n_add >= 0 && a.ep.n_add <= 3, DIF_EARG, "simple_apply: n_add %d", a.ep.n_add);
-    DIF_REQUIRE(a.ep.mode == 0 || (a.ep.ln_weight == nullptr && a.ep.relu == 0), DIF_EUNSUPPORTED,
-                "simple_apply: the LayerNorm / ReLU tail of the layer epilogue is fused on the tcgen05 kernels only");
+    DIF_REQUIRE(a.ep.mode == 0 || (a.ep.ln_weight == nullptr && a.ep.relu == 0 && a.ep.gcn_rowptr == nullptr), DIF_EUNSUPPORTED,
+                "simple_apply: the LayerNorm / ReLU tail and the in-epilogue gcn term are fused on the tcgen05 kernels only");
     const size_t smem = ((size_t)M * D + M + D + (size_t)kAppRows * (M + 4) + kAppRows) * sizeof(float);
     const int grid = (int)((N + kAppRows - 1) / kAppRows);
     const int ntile = (kAppRows / 4) * (D / 4);

@@ -623,6 +623,40 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                     }
                     hs[j] = o.x; hs[j + 1] = o.y; hs[j + 2] = o.z; hs[j + 3] = o.w;
                 }
+                if (p.ep.gcn_rowptr != nullptr && ok) {
+                    // gcn_conv term (difformer.py:63-79) gathered here: this thread's row of the normalised adjacency times the
+                    // head-meaned values.  The source rows (256 B each) come from L2; two slots (32 x 16-byte loads) in flight.
+                    const int beg = __ldg(p.ep.gcn_rowptr + row), end = __ldg(p.ep.gcn_rowptr + row + 1);
+                    int s_ = beg;
+                    for (; s_ + 1 < end; s_ += 2) {
+                        const float w0 = __ldg(p.ep.gcn_val + s_) * p.ep.gcn_scale, w1 = __ldg(p.ep.gcn_val + s_ + 1) * p.ep.gcn_scale;
+                        const float* x0 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_) * kDim;
+                        const float* x1 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_ + 1) * kDim;
+                        float4 a[16], b[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { a[j] = ldg4(x0 + 4 * j); b[j] = ldg4(x1 + 4 * j); }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            hs[4 * j] = fmaf(w0, a[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(w0, a[j].y, hs[4 * j + 1]);
+                            hs[4 * j + 2] = fmaf(w0, a[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w0, a[j].w, hs[4 * j + 3]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            hs[4 * j] = fmaf(w1, b[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(w1, b[j].y, hs[4 * j + 1]);
+                            hs[4 * j + 2] = fmaf(w1, b[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w1, b[j].w, hs[4 * j + 3]);
+                        }
+                    }
+                    if (s_ < end) {
+                        const float w0 = __ldg(p.ep.gcn_val + s_) * p.ep.gcn_scale;
+                        const float* x0 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_) * kDim;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 a = ldg4(x0 + 4 * j);
+                            hs[4 * j] = fmaf(w0, a.x, hs[4 * j]); hs[4 * j + 1] = fmaf(w0, a.y, hs[4 * j + 1]);
+                            hs[4 * j + 2] = fmaf(w0, a.z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w0, a.w, hs[4 * j + 3]);
+                        }
+                    }
+                }
                 if (p.ep.ln_weight != nullptr) {
                     float mean = 0.f;
 #pragma unroll
@@ -1452,6 +1486,8 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_apply(tcgen05): prepared buffer must be 16-byte aligned");
     if (ep) a.ep = *ep; else { a.ep = dif_epilogue_t{}; }
     DIF_REQUIRE(a.ep.mode == 0 || a.ep.mode == 1, DIF_EARG, "simple_apply: epilogue mode %d", a.ep.mode);
+    DIF_REQUIRE(a.ep.gcn_rowptr == nullptr || (a.ep.mode == 1 && a.ep.gcn_idx && a.ep.gcn_val && a.ep.gcn_x && ((uintptr_t)a.ep.gcn_x & 15) == 0), DIF_EARG,
+                "simple_apply: the in-epilogue gcn term needs mode 1 and rowptr / idx / val / x (x 16-byte aligned)");
     DIF_REQUIRE(a.ep.ln_weight == nullptr || (a.ep.ln_bias != nullptr && (((uintptr_t)a.ep.ln_weight | (uintptr_t)a.ep.ln_bias) & 15) == 0), DIF_EARG,
                 "simple_apply: LayerNorm weight and bias must both be given, 16-byte aligned");
     static const int pf = env_int("DIF_TC_P2_PREFETCH", 1), sth = env_int("DIF_TC_P2_STORE_HINT", 1);

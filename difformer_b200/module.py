@@ -66,14 +66,18 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         if conv.use_graph and v.shape[1] > 1:
             vbar = torch.empty((N, v.shape[2]), dtype=torch.float32, device=v.device)
         partials, prepared = ops.simple_partials(q, k, v, with_prepared=True, vbar=vbar)
-        addends = []
+        addends, gcn = [], None
         if conv.use_graph:
             csr = ops.graph_csr(edge_index, edge_weight, N)
             # the head mean commutes with the SpMM: gather 256 B rows of mean_h(V) (L2-resident, T/H bytes)
             # instead of H x 256 B rows of V
             src = vbar if vbar is not None else v
-            gmean = ops.spmm(csr, src.view(N, 1, v.shape[2])).view(N, v.shape[2])
-            addends.append((gmean, alpha * w_gcn))
+            if (csr.max_degree is not None and csr.max_degree <= ops.GCN_EPILOGUE_MAX_DEGREE and v.shape[2] == 64
+                    and ops.layer_tail_fusable(H, v.shape[1], C, v.shape[2])):
+                gcn = (csr, src.reshape(N, v.shape[2]), alpha * w_gcn)      # gathered inside the pass-2 epilogue: never written to HBM
+            else:
+                gmean = ops.spmm(csr, src.view(N, 1, v.shape[2])).view(N, v.shape[2])
+                addends.append((gmean, alpha * w_gcn))
         if use_source:
             addends.append((ops._f32c(x_0), alpha))
         if residual is not None:
@@ -82,8 +86,8 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         if (layer_norm is not None and residual is not None and layer_norm.elementwise_affine and layer_norm.bias is not None
                 and tuple(layer_norm.normalized_shape) == (v.shape[2],) and ops.layer_tail_fusable(H, v.shape[1], C, v.shape[2])):
             ln = (layer_norm.weight.detach().float().contiguous(), layer_norm.bias.detach().float().contiguous(), layer_norm.eps)
-        ep = ops.make_epilogue(alpha * w_attn / H, addends, layer_norm=ln)
-        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=(addends, ln), prepared=prepared)
+        ep = ops.make_epilogue(alpha * w_attn / H, addends, layer_norm=ln, gcn=gcn)
+        out = ops.simple_apply(q, partials, float(N), v.shape[1], v.shape[2], ep, keep=(addends, ln, gcn), prepared=prepared)
         return out, None, (2 if ln is not None else 1) if residual is not None else 0
 
     # ---- unfused path (training, sigmoid, batched graphs, attention visualisation)

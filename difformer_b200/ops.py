@@ -166,10 +166,14 @@ def simple_apply(qs: torch.Tensor, partials: torch.Tensor, n_total: float, Hv: i
     return out
 
 
-def make_epilogue(attn_scale: float, addends, layer_norm=None, relu: bool = False) -> Epilogue:
+GCN_EPILOGUE_MAX_DEGREE = 128      # rows above this degree would serialise an epilogue thread: use the SpMM kernel instead
+
+
+def make_epilogue(attn_scale: float, addends, layer_norm=None, relu: bool = False, gcn=None) -> Epilogue:
     """addends: list of (tensor [N,D] fp32 contiguous, scale).  layer_norm = (weight [D], bias [D], eps): the LayerNorm that
     follows the layer (difformer.py:202-203) applied to the finished row inside the kernel (tcgen05 shapes only, see
-    `layer_tail_fusable`); relu: ReLU after it.  Keep the tensors alive until the kernel has been enqueued."""
+    `layer_tail_fusable`); relu: ReLU after it.  gcn = (GraphCSR, x [N,D] = mean_h(V), scale): the gcn_conv term is gathered by
+    the epilogue itself (never written to HBM; tcgen05 shapes only).  Keep the tensors alive until the kernel has been enqueued."""
     ep = Epilogue()
     ep.mode, ep.attn_scale, ep.n_add = 1, float(attn_scale), len(addends)
     for j, (t, s) in enumerate(addends):
@@ -179,6 +183,10 @@ def make_epilogue(attn_scale: float, addends, layer_norm=None, relu: bool = Fals
         w, b, eps = layer_norm
         ep.ln_weight, ep.ln_bias, ep.ln_eps = w.data_ptr(), b.data_ptr(), float(eps)
     ep.relu = 1 if relu else 0
+    if gcn is not None:
+        csr, x, scale = gcn
+        ep.gcn_rowptr, ep.gcn_idx, ep.gcn_val = csr.rowptr.data_ptr(), csr.src.data_ptr(), csr.val.data_ptr()
+        ep.gcn_x, ep.gcn_scale = x.data_ptr(), float(scale)
     return ep
 
 
@@ -460,8 +468,12 @@ class GraphCSR:
         # one validation sync per graph build (cached afterwards): out-of-range node ids are skipped
         # by the histogram, so the row pointer falls short of E exactly when some id is invalid
         # (skipped when the build is being captured into a CUDA graph: the ids were validated by the eager warm-up run)
-        if validate and int(self.rowptr[-1]) != E:
-            raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+        self.max_degree = None                 # largest in-degree (rows of the target CSR); None = unknown (built during capture)
+        if validate:
+            chk = torch.stack([self.rowptr[-1], (self.rowptr[1:] - self.rowptr[:-1]).max() if N > 0 else self.rowptr[-1]]).tolist()
+            if int(chk[0]) != E:
+                raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+            self.max_degree = int(chk[1])
         self._keep = (ei, w)
 
 

@@ -101,6 +101,17 @@ typedef struct {
     const float* ln_bias;
     float ln_eps;
     int relu;
+    /* optional gcn_conv term gathered INSIDE the epilogue (tcgen05 kernels only), so that it is never written to HBM:
+     * out[n,:] += gcn_scale * sum over the CSR slots s of row n of gcn_val[s] * gcn_x[gcn_idx[s], :]
+     * with gcn_x = mean_h(V) [N,D] (the `vbar` output of dif_simple_reduce; the head mean commutes with the SpMM) and
+     * (gcn_rowptr, gcn_idx, gcn_val) the target-sorted CSR of dif_csr_build.  Each epilogue thread owns one output row and walks
+     * its slots (L2-resident 256-byte rows): meant for graphs without very high-degree rows -- otherwise run dif_gcn_spmm and pass
+     * its result as an addend. */
+    const int32_t* gcn_rowptr;
+    const int32_t* gcn_idx;
+    const float* gcn_val;
+    const float* gcn_x;
+    float gcn_scale;
 } dif_epilogue_t;
 
 DIF_API int dif_simple_apply(const float* q, const float* partials, const void* prepared, double n_total,

@@ -720,3 +720,31 @@ def test_training_step_cuda_graph_capture():
                 assert O.rel_err(p.grad, pr.grad) < 1e-4, (kern, rep, name)
             m.zero_grad(set_to_none=True)        # the graphed backward hands out its static gradient buffers: never accumulate into them
             ref.zero_grad(set_to_none=True)
+
+
+@pytest.mark.parametrize("h", [1, 4])
+def test_layer_epilogue_gcn_gather_and_layernorm(h):
+    """Mode-1 epilogue of pass 2 with the gcn_conv term gathered inside the epilogue (CSR rows of mean_h V, never written to HBM) and
+    the LayerNorm tail, against the same layer assembled from the separate SpMM + torch LayerNorm and against the fp64 oracle."""
+    n, d = 5000, 64
+    q, k, v = O.synthetic_qkv(n, h, d, seed=40 + h, adversarial=True)
+    ei = O.synthetic_graph(n, 20000, seed=6)
+    w = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(1))
+    qg, kg, vg, eig, wg = dev(q), dev(k), dev(v), dev(ei), dev(w)
+    prev = dev(torch.randn(n, d, generator=torch.Generator().manual_seed(2)))
+    lnw, lnb = dev(torch.rand(d) + 0.5), dev(torch.randn(d) * 0.1)
+    csr = ops.graph_csr(eig, wg, n)
+    assert csr.max_degree is not None and csr.max_degree <= ops.GCN_EPILOGUE_MAX_DEGREE
+    vbar = torch.empty((n, d), dtype=torch.float32, device="cuda") if h > 1 else None
+    part, prep = ops.simple_partials(qg, kg, vg, with_prepared=True, vbar=vbar)
+    x = vbar if vbar is not None else vg.reshape(n, d)
+    fused = ops.simple_apply(qg, part, float(n), h, d, ops.make_epilogue(0.5 / h, [(prev, 0.5)], layer_norm=(lnw, lnb, 1e-5), gcn=(csr, x, 0.5)),
+                             prepared=prep)
+    gterm = ops.spmm(csr, x.view(n, 1, d)).view(n, d)
+    plain = ops.simple_apply(qg, part, float(n), h, d, ops.make_epilogue(0.5 / h, [(gterm, 0.5), (prev, 0.5)]), prepared=prep)
+    plain = torch.nn.functional.layer_norm(plain, (d,), lnw, lnb, 1e-5)
+    assert O.rel_err(fused, plain) < 1e-5
+    attn = O.simple_attention(q.double(), k.double(), v.double())
+    gcn = O.gcn_conv(v.double(), ei, w.double())
+    want = torch.nn.functional.layer_norm(0.5 * (attn + gcn).mean(1) + 0.5 * prev.double().cpu(), (d,), lnw.double().cpu(), lnb.double().cpu(), 1e-5)
+    assert O.rel_err(fused, want) < TOL

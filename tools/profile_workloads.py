@@ -40,7 +40,9 @@ for _ in range(reps):
     part, prep = ops.simple_partials(q, k, v, with_prepared=True, vbar=vb_)
     g = ops.spmm(csr, vb_.view(n, 1, d)).view(n, d)                    # spmm_kernel
     ep = ops.make_epilogue(0.5 / h, [(g, 0.5), (prev, 0.5)], layer_norm=(lnw, lnb, 1e-5))
-    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # apply_tc_kernel<1, 4>
+    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # apply_tc_kernel<1, 4> (gcn as an addend)
+    ep = ops.make_epilogue(0.5 / h, [(prev, 0.5)], layer_norm=(lnw, lnb, 1e-5), gcn=(csr, vb_, 0.5))
+    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # apply_tc_kernel<1, 4> with the gcn gather in the epilogue
     ops.spmm(csr, v)                                                   # spmm_kernel, all heads
 # sigmoid: N = 10 000 (main-batch.py mini-batch) forward + backward on tcgen05, then the FFMA kernels
 n2 = 10000
