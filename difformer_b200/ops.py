@@ -166,7 +166,11 @@ def simple_apply(qs: torch.Tensor, partials: torch.Tensor, n_total: float, Hv: i
     return out
 
 
-GCN_EPILOGUE_MAX_DEGREE = 128      # rows above this degree would serialise an epilogue thread: use the SpMM kernel instead
+# In-epilogue gather of the gcn term (dif_epilogue_t.gcn_*): the module uses it for graphs whose largest in-degree is <= this value.
+# 0 = off (default).  Measured at config A with E = 17 N (round 2, `bench.py --workload layer`): 370 us per layer with the gather in
+# the epilogue against 252 us with the stand-alone SpMM + addend -- four epilogue warps per SM cannot keep enough 256-byte row loads
+# in flight, the SpMM kernel (64 warps per SM) can.  Kept as an option for small, sparse graphs; see DESIGN.md 3.4.
+GCN_EPILOGUE_MAX_DEGREE = 0
 
 
 def make_epilogue(attn_scale: float, addends, layer_norm=None, relu: bool = False, gcn=None) -> Epilogue:
@@ -488,7 +492,12 @@ def graph_csr(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num
         # CUDA-graph capture (GraphedForward): the values of `edge_weight` may change between replays, so the build of
         # the normalised CSR values is recorded INTO the graph (kernels + CUB on caller-owned scratch: capture-safe)
         # instead of being served from the cache
-        return GraphCSR(edge_index, edge_weight, num_nodes, validate=False)
+        csr = GraphCSR(edge_index, edge_weight, num_nodes, validate=False)
+        for (k_ptr, _, k_shape, k_dev, k_n, _), (cached, _, _) in _CSR_CACHE.items():     # the degrees only depend on edge_index:
+            if (k_ptr, k_shape, k_dev, k_n) == (edge_index.data_ptr(), tuple(edge_index.shape), str(edge_index.device), int(num_nodes)):
+                csr.max_degree = cached.max_degree                                      # keep the eager run's choice of path
+                break
+        return csr
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), int(num_nodes),
            None if edge_weight is None else (edge_weight.data_ptr(), edge_weight._version))
     hit = _CSR_CACHE.get(key)
