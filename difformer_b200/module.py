@@ -47,9 +47,9 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
     shard = getattr(conv, "_row_shard", None)             # sharded.shard_model: these rows are a shard of a larger graph
     if shard is not None and shard.world < 2:
         shard = None
-    if shard is not None and (segmented or output_attn or conv.kernel != "simple"):
-        raise NotImplementedError("row-sharded propagation covers kernel='simple' (one all-reduce of the partials); 'sigmoid', "
-                                  "batched graphs and attention maps need every row: run them as replicas (SURVEY.md 8e)")
+    if shard is not None and (segmented or output_attn):
+        raise NotImplementedError("row-sharded propagation covers full_attention_conv and gcn_conv; batched graphs shard by graph "
+                                  "(ops.segmented_full_attention(..., group=)), attention maps need every row")
     use_source = getattr(conv, "use_source", False)
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
@@ -96,6 +96,12 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
         attention_output = ops.segmented_full_attention(query, key, value, conv.kernel, n_nodes)
     elif output_attn:
         attention_output, attn = ops.full_attention_conv(query, key, value, conv.kernel, True)
+    elif shard is not None and conv.kernel == "sigmoid":
+        # every query row needs every key / value row: K and V are all-gathered over the process group (autograd: reduce-scatter of
+        # dK, dV), the O(N L) work itself is sharded by query rows
+        from .sharded import gather_rows
+        attention_output = ops.full_attention_conv(query, gather_rows(key, shard.pg, shard.n_total),
+                                                   gather_rows(value, shard.pg, shard.n_total), "sigmoid")
     elif shard is not None:
         attention_output = ops.full_attention_conv(query, key, value, conv.kernel, group=shard.attn_group, n_total=shard.n_total)
     else:

@@ -572,6 +572,20 @@ def gcn_conv(x, edge_index, edge_weight, *, shard=None):
     return _GCNConv.apply(x, graph_csr(edge_index, edge_weight, x.shape[0]), None)
 
 
+def subgraph(subset: torch.Tensor, edge_index: torch.Tensor, num_nodes: int, edge_weight: Optional[torch.Tensor] = None):
+    """Induced subgraph on the device, for the mini-batch loop of `main-batch.py:131` (`torch_geometric.utils.subgraph(idx, edge_index,
+    num_nodes=n, relabel_nodes=True)`, done there on the host per batch): keeps the edges whose two endpoints are in `subset` (node
+    ids, any order, unique) and relabels them to positions in `subset`.  Returns (edge_index_sub [2,E'], edge_weight_sub or None), edge
+    order preserved.  Plain torch index ops on the GPU (plumbing: one mask, one gather), no host round trip."""
+    _need_cuda(subset, edge_index, edge_weight)
+    pos = torch.full((int(num_nodes),), -1, dtype=torch.int64, device=edge_index.device)
+    pos[subset] = torch.arange(subset.numel(), device=edge_index.device)
+    src, dst = pos[edge_index[0]], pos[edge_index[1]]
+    keep = (src >= 0) & (dst >= 0)
+    sub = torch.stack([src[keep], dst[keep]])
+    return sub, (None if edge_weight is None else edge_weight[keep])
+
+
 # ----------------------------------------------------------------------------------------------
 # batched graphs (difformer-v2.py:80-111)
 # ----------------------------------------------------------------------------------------------

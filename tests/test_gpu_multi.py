@@ -88,6 +88,24 @@ for nvlink in (False, True):
         # k barely changes the normalised attention): both the sharded and the unsharded fp32 value carry a relative error of ~1e-3 there
         tol = 2e-2 if (name.endswith("bias") and (".Wk." in name or ".Wq." in name)) else 1e-3
         assert O.rel_err(g, pr.grad) < tol, (nvlink, name, O.rel_err(g, pr.grad))
+# kernel='sigmoid' row-sharded: the query rows are sharded, K and V all-gathered (autograd: reduce-scatter of dK, dV)
+torch.manual_seed(1)
+n, cin = 1501, 16
+x = torch.randn(n, cin)
+ei = O.synthetic_graph(n, 4000, seed=9).to(dev)
+m = difformer.DIFFormer(cin, 64, 4, num_layers=2, num_heads=2, kernel="sigmoid", dropout=0.0, use_graph=True).to(dev)
+ref = copy.deepcopy(m)
+out_ref = ref(x.to(dev), ei)
+out_ref.square().sum().backward()
+ms = copy.deepcopy(m)
+sh = shard_model(ms, n, dist.group.WORLD)
+out = ms(x[sh.begin:sh.end].to(dev), ei)
+assert O.rel_err(out, out_ref[sh.begin:sh.end]) < 1e-4, ("sigmoid sharded", O.rel_err(out, out_ref[sh.begin:sh.end]))
+out.square().sum().backward()
+for (name, p), (_, pr) in zip(ms.named_parameters(), ref.named_parameters()):
+    g = p.grad.clone()
+    dist.all_reduce(g)
+    assert O.rel_err(g, pr.grad) < 2e-3, ("sigmoid sharded", name, O.rel_err(g, pr.grad))
 # batched graphs (difformer-v2) sharded by whole graphs: only the two norms (forward) and (t_q, t_k) (backward) cross ranks
 gen = torch.Generator().manual_seed(21)
 nn_all = torch.randint(1, 90, (64 * world + 3,), generator=gen)

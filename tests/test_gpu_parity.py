@@ -748,3 +748,19 @@ def test_layer_epilogue_gcn_gather_and_layernorm(h):
     gcn = O.gcn_conv(v.double(), ei, w.double())
     want = torch.nn.functional.layer_norm(0.5 * (attn + gcn).mean(1) + 0.5 * prev.double().cpu(), (d,), lnw.double().cpu(), lnb.double().cpu(), 1e-5)
     assert O.rel_err(fused, want) < TOL
+
+
+def test_subgraph_on_device_matches_host_definition():
+    """main-batch.py:131 extracts the induced subgraph of every mini-batch on the host; ops.subgraph does it on the GPU."""
+    gen = torch.Generator().manual_seed(3)
+    n = 2000
+    ei = O.synthetic_graph(n, 9000, seed=1)
+    w = torch.rand(ei.shape[1], generator=gen)
+    idx = torch.randperm(n, generator=gen)[:700]
+    sub, ws = ops.subgraph(dev(idx), dev(ei), n, dev(w))
+    # host definition: keep edges with both endpoints in idx, relabel to positions in idx, keep the order
+    pos = {int(v): i for i, v in enumerate(idx.tolist())}
+    want = [(pos[int(a)], pos[int(b)], float(x)) for a, b, x in zip(ei[0].tolist(), ei[1].tolist(), w.tolist()) if int(a) in pos and int(b) in pos]
+    assert sub.shape[1] == len(want)
+    assert sub.cpu().t().tolist() == [[a, b] for a, b, _ in want]
+    assert torch.equal(ws.cpu(), torch.tensor([x for _, _, x in want]))
