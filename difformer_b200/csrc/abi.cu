@@ -125,3 +125,21 @@ extern "C" int dif_simple_apply(const float* q, const float* partials, const voi
     return tc ? simple_apply_tc(q, partials, prepared, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream)
               : simple_apply_generic(q, partials, n_total, N, H, Hv, M, D, out, epilogue, (cudaStream_t)stream);
 }
+
+// Pass 2 with the Wq projection folded into its operands (node classification/difformer.py:115-118): the A operand is
+// the layer input x [N,64] itself (row stride ldx floats), shared by the H heads, and `vpartials` holds, in the partials layout of
+// (H, Hv = H, M = 64, D = 64), the projected operands  S'_h = Wq_h^T S_h,  z'_h = Wq_h^T z_h,  u'_h = u_h + c bq_h^T S_h  and the two
+// squared norms (sum q^2, sum k^2); n_total_vec[h] = N + c bq_h . z_h (device, H floats).  Then
+//     out[n,h,:] = (c x_n S'_h + u'_h) / (c x_n . z'_h + n_total_vec[h])  =  full_attention_conv(x Wq^T + bq, K, V, 'simple')[n,h,:]
+// without Q (nor K, V: their reductions follow from the Gram matrix X^T X, see difformer_b200/projected.py) ever being written.
+extern "C" int dif_simple_apply_projected(const float* x, int64_t ldx, const float* vpartials, const float* n_total_vec, int64_t N, int H,
+                                          float* out, const dif_epilogue_t* epilogue, void* stream) {
+    DIF_REQUIRE(x && vpartials && n_total_vec && out, DIF_EARG, "simple_apply_projected: null pointer");
+    DIF_REQUIRE(simple_tc_supported(N, H, H, 64, 64), DIF_EUNSUPPORTED, "simple_apply_projected: needs hidden = 64 and H in {1, 2, 4}");
+    DIF_REQUIRE(ldx >= 64 && (ldx % 8) == 0, DIF_EARG, "simple_apply_projected: ldx must be >= 64 and a multiple of 8 floats");
+    if (epilogue) {
+        DIF_REQUIRE(epilogue->n_add >= 0 && epilogue->n_add <= 3, DIF_EARG, "simple_apply_projected: n_add=%d", epilogue->n_add);
+        for (int j = 0; j < epilogue->n_add; ++j) DIF_REQUIRE(epilogue->add[j], DIF_EARG, "simple_apply_projected: addend %d is null", j);
+    }
+    return simple_apply_tc(x, vpartials, nullptr, 1.0, N, H, H, 64, 64, out, epilogue, (cudaStream_t)stream, ldx, 0, n_total_vec);
+}

@@ -212,7 +212,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
                      float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st,
                      void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0, float* vbar = nullptr);
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
-                    float* out, const dif_epilogue_t* ep, cudaStream_t st);
+                    float* out, const dif_epilogue_t* ep, cudaStream_t st, int64_t q_ld = 0, int q_hs = 0, const float* nvec = nullptr);
 
 bool simple_wide_supported(int64_t N, int H, int Hv, int M, int D);
 int64_t simple_fused_workspace_bytes(int64_t N, int H, int Hv, int M, int D);

@@ -412,6 +412,12 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
 // pass 2
 // ------------------------------------------------------------------------------------------
 struct ApplyTcArgs {
+    // A operand rows: element (row, head h, column c) at q[row * q_ld + h * q_hs + c].  Plain [N,H,64] queries: q_ld = 64 H, q_hs = 64.
+    // Projection folded into the operands (dif_simple_apply_projected): q = the layer input x [N,64], q_ld = 64, q_hs = 0 (every head
+    // re-reads the same x tile, from L2) and `nvec` holds one denominator constant per head.
+    int64_t q_ld;
+    int q_hs;
+    const float* nvec;
     const float* q;
     const float* partials;
     float n_total;
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             const int64_t prow = tile_of(H * i) * kTile2;
             const int64_t nrows = min((int64_t)kTile2, p.N - prow);
             for (int64_t r = 0; r < nrows; r += 16)
-                prefetch_l2(p.q + (prow + r) * G::kRowF, (uint32_t)(min((int64_t)16, nrows - r) * G::kRowB));
+                prefetch_l2(p.q + (prow + r) * p.q_ld, (uint32_t)(min((int64_t)16, nrows - r) * p.q_ld * 4));
         }
     }
     if (tid == 0) {
@@ -520,7 +526,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             const int t = tid + 256 * j;
             const int64_t row = tile * kTile2 + (t >> 3);
             if (row < p.N) {
-                ldg256_stream(p.q + row * G::kRowF + (sc % H) * kDim + (t & 7) * 8, dst);
+                if (p.q_hs != 0) ldg256_stream(p.q + row * p.q_ld + (sc % H) * p.q_hs + (t & 7) * 8, dst);
+                else ldg256_keep(p.q + row * p.q_ld + (t & 7) * 8, dst);         // shared by the heads: let it stay in L2
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dst[i] = 0.f;
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
             uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q . z
             tmem_ld_wait1(qz_bits);
-            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.n_total));   // one division per (row, head)
+            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.nvec != nullptr ? __ldg(p.nvec + h) : p.n_total));   // one division per (row, head)
             if (MODE == 1 && h == 0) {
 #pragma unroll
                 for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
@@ -711,7 +718,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                 const int64_t prow = tile_of(sc + H * p.pf_tiles) * kTile2;
                 const int64_t nrows = min((int64_t)kTile2, p.N - prow);
                 for (int64_t r = 0; r < nrows; r += 16)
-                    prefetch_l2(p.q + (prow + r) * G::kRowF, (uint32_t)(min((int64_t)16, nrows - r) * G::kRowB));
+                    prefetch_l2(p.q + (prow + r) * p.q_ld, (uint32_t)(min((int64_t)16, nrows - r) * p.q_ld * 4));
             }
             if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
             mbar_wait(&full[s], (sc / kNS2) & 1);
@@ -1476,12 +1483,16 @@ static int launch_apply(const ApplyTcArgs& a, const CUtensorMap& map, int grid, 
 }
 
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
-                    float* out, const dif_epilogue_t* ep, cudaStream_t st) {
+                    float* out, const dif_epilogue_t* ep, cudaStream_t st, int64_t q_ld, int q_hs, const float* nvec) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
     DIF_REQUIRE(((uintptr_t)q & 31) == 0 && ((uintptr_t)out & 15) == 0, DIF_EARG, "tcgen05 path: q must be 32-byte, out 16-byte aligned");
     DIF_REQUIRE(N < (1ll << 31), DIF_EUNSUPPORTED, "tcgen05 path: N must fit a 32-bit TMA coordinate");
     ApplyTcArgs a{};
     a.q = q; a.partials = partials; a.n_total = (float)n_total; a.N = N; a.out = out;
+    a.q_ld = q_ld > 0 ? q_ld : (int64_t)H * kDim;
+    a.q_hs = q_ld > 0 ? q_hs : kDim;
+    a.nvec = nvec;
+    DIF_REQUIRE((a.q_ld % 8) == 0 && (a.q_hs % 8) == 0, DIF_EARG, "simple_apply(tcgen05): row / head strides must be multiples of 8 floats");
     a.prepared = (const uint8_t*)prepared;
     DIF_REQUIRE(prepared == nullptr || ((uintptr_t)prepared & 15) == 0, DIF_EARG, "simple_apply(tcgen05): prepared buffer must be 16-byte aligned");
     if (ep) a.ep = *ep; else { a.ep = dif_epilogue_t{}; }

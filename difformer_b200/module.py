@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, projected
 
 
 def _fusable(kernel, *tensors):
@@ -29,6 +29,37 @@ def _fusable(kernel, *tensors):
     return not any(t is not None and t.requires_grad for t in tensors)
 
 
+def _conv_forward_projected(conv, x, edge_index, edge_weight, x_0, residual, layer_norm):
+    """No-grad layer with the Wq / Wk / Wv projections folded into the propagation (projected.py): one pass over x for
+    the Gram matrix, a few 64 x 64 products, one pass over x that writes the finished [N, 64] row (head mean, gcn term, x_0, residual
+    blend, LayerNorm in the epilogue).  Q, K and V are never formed."""
+    H = conv.num_heads
+    x = ops._f32c(x)
+    N = x.shape[0]
+    alpha = 1.0 if residual is None else float(residual[0])
+    gw = conv.graph_weight
+    w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
+    G, s = projected.gram(x)
+    vpart, nvec, wbar, bbar = projected.projected_operands(G, s, float(N), conv)
+    addends = []
+    if conv.use_graph:
+        csr = ops.graph_csr(edge_index, edge_weight, N)
+        vbar = torch.addmm(bbar, x, wbar.t()) if conv.use_weight else x            # mean_h V [N, 64] (commutes with the SpMM)
+        gmean = ops.spmm(csr, vbar.view(N, 1, projected.HID)).view(N, projected.HID)
+        addends.append((gmean, alpha * w_gcn))
+    if getattr(conv, "use_source", False):
+        addends.append((ops._f32c(x_0), alpha))
+    if residual is not None:
+        addends.append((ops._f32c(residual[1]), 1.0 - alpha))
+    ln = None
+    if (layer_norm is not None and residual is not None and layer_norm.elementwise_affine and layer_norm.bias is not None
+            and tuple(layer_norm.normalized_shape) == (projected.HID,)):
+        ln = (layer_norm.weight.detach().float().contiguous(), layer_norm.bias.detach().float().contiguous(), layer_norm.eps)
+    ep = ops.make_epilogue(alpha * w_attn / H, addends, layer_norm=ln)
+    out = projected.apply(x, vpart, nvec, H, ep, keep=(addends, ln))
+    return out, None, (2 if ln is not None else 1) if residual is not None else 0
+
+
 def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0, output_attn,
                   residual=None, n_nodes=None, layer_norm=None):
     """Shared body of DIFFormerConv.forward / TransConv.forward.
@@ -37,6 +68,13 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
     epilogue; the return flag says whether it was applied.  layer_norm = the nn.LayerNorm that follows the layer
     (difformer.py:202-203): folded into the same epilogue when the tcgen05 kernel runs it (flag value 2)."""
     H, C = conv.num_heads, conv.out_channels
+    segmented_ = n_nodes is not None
+    shard_ = getattr(conv, "_row_shard", None)
+    if (ops._PROJECTION_FOLDING and not output_attn and not segmented_ and (shard_ is None or shard_.world < 2) and conv.kernel == "simple"
+            and _fusable("simple", query_input, source_input, x_0, None if residual is None else residual[1],
+                         *[p_ for p_ in conv.parameters()])
+            and projected.supported(conv, query_input, source_input)):
+        return _conv_forward_projected(conv, query_input, edge_index, edge_weight, x_0, residual, layer_norm)
     query = conv.Wq(query_input).reshape(-1, H, C)
     key = conv.Wk(source_input).reshape(-1, H, C)
     if conv.use_weight:

@@ -111,6 +111,14 @@ def simple_partials(qs: torch.Tensor, ks: torch.Tensor, vs: torch.Tensor, with_p
 
 
 _FUSED_FORWARD = True
+_PROJECTION_FOLDING = True
+
+
+def set_projection_folding(on: bool) -> None:
+    """No-grad `DIFFormerConv` layers with hidden = 64: fold the Wq / Wk / Wv projections into the propagation (projected.py; default on)."""
+    global _PROJECTION_FOLDING
+    _PROJECTION_FOLDING = bool(on)
+
 _DTYPES = {torch.float32: _lib.DIF_DTYPE_F32, torch.bfloat16: _lib.DIF_DTYPE_BF16, torch.float16: _lib.DIF_DTYPE_F16}
 
 

@@ -1,0 +1,96 @@
+"""The Wq / Wk / Wv projections folded into the 'simple' propagation (node classification/difformer.py:115-140).
+
+`DIFFormerConv.forward` computes Q = x Wq^T + bq, K = x Wk^T + bk, V = x Wv^T + bv from the SAME layer input x [N, C] (difformer.py
+:195: `conv(x, x, ...)`) and hands the three [N, H, 64] tensors to `full_attention_conv`.  Everything pass 1 of 'simple' extracts from
+K, V and Q is a row reduction, and row reductions of affine images of x follow from the Gram matrix G = X^T X and the column sums
+s = X^T 1 of x itself (one pass over x: 256 B per node instead of 3 KB):
+
+    S_h = K_h^T V_h = Wk_h G Wv_h^T + (Wk_h s) bv_h^T + bk_h (Wv_h s)^T + N bk_h bv_h^T         [M, D]
+    z_h = Wk_h s + N bk_h          u_h = Wv_h s + N bv_h
+    sum k^2 = <Wk G, Wk> + 2 bk.(Wk s) + N |bk|^2          (sum q^2 alike with Wq, bq)
+
+and pass 2 needs q_h only inside the products q_h S_h and q_h . z_h, which are affine in x too:
+
+    q_h S_h = x (Wq_h^T S_h) + bq_h^T S_h            q_h . z_h = x . (Wq_h^T z_h) + bq_h . z_h
+
+So a layer runs as  [pass 1 on x: G, s]  ->  [this file: a few 64 x 64 products per head, fp64]  ->  [pass 2 on x with the
+projected operands, dif_simple_apply_projected]  and Q, K, V are never formed, written or read: 256 B (pass 1) + 256 B (pass 2) of
+input per node instead of 3 KB + 1 KB, and the three Linear GEMMs disappear.  Inference path (no autograd), hidden = 64, H in
+{1, 2, 4}; `use_weight=False` (V = x, one head) is the case Wv = I, bv = 0.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+HID = 64
+
+
+def supported(conv, query_input: torch.Tensor, source_input: torch.Tensor) -> bool:
+    """Same input for Q and K/V, hidden size 64 in and out, a tensor-core head count, fp32 CUDA rows."""
+    return (query_input is source_input and query_input.dim() == 2 and query_input.shape[1] == HID and conv.out_channels == HID
+            and conv.num_heads in (1, 2, 4) and query_input.dtype == torch.float32 and query_input.is_cuda
+            and ops._SIMPLE_IMPL != ops._lib.DIF_IMPL_GENERIC and conv.Wq.in_features == HID)
+
+
+def gram(x: torch.Tensor):
+    """One pass over x [N, 64]: G = X^T X [64, 64], s = column sums [64], sum x^2 -- pass 1 of 'simple' with q = k = v = x, H = 1
+    (tcgen05 kernel, deterministic)."""
+    x3 = x.view(-1, 1, HID)
+    flat = ops.simple_partials(x3, x3, x3)
+    return flat[:HID * HID].view(HID, HID), flat[HID * HID:HID * HID + HID]
+
+
+def projected_operands(G: torch.Tensor, s: torch.Tensor, n_total: float, conv, out_dtype=torch.float32):
+    """The pass-2 operands of every head from (G, s) and the layer's weights: (vpartials fp32 in the partials layout of
+    (H, Hv = H, 64, 64), nvec fp32 [H], vbar weight [64, 64] and bias [64] of mean_h V).  Tiny (64 x 64 per head): fp64 torch ops."""
+    H = conv.num_heads
+    G, s = G.double(), s.double()
+    Wq, bq = conv.Wq.weight.double().view(H, HID, HID), conv.Wq.bias.double().view(H, HID)
+    Wk, bk = conv.Wk.weight.double().view(H, HID, HID), conv.Wk.bias.double().view(H, HID)
+    if conv.use_weight:
+        Wv, bv = conv.Wv.weight.double().view(H, HID, HID), conv.Wv.bias.double().view(H, HID)
+    else:                                                   # value = source_input.reshape(-1, 1, C) (difformer.py:120): V_h = x for every head
+        Wv = torch.eye(HID, dtype=torch.float64, device=G.device).expand(H, HID, HID)
+        bv = torch.zeros(H, HID, dtype=torch.float64, device=G.device)
+    n = float(n_total)
+    ks, vs, qs = Wk @ s, Wv @ s, Wq @ s                                       # [H, 64] each: W_h s
+    S = Wk @ G @ Wv.transpose(1, 2) + ks.unsqueeze(2) * bv.unsqueeze(1) + bk.unsqueeze(2) * vs.unsqueeze(1) \
+        + n * bk.unsqueeze(2) * bv.unsqueeze(1)                               # [H, M, D]
+    z = ks + n * bk
+    u = vs + n * bv
+    sk = ((Wk @ G) * Wk).sum() + 2.0 * (bk * ks).sum() + n * (bk * bk).sum()
+    sq = ((Wq @ G) * Wq).sum() + 2.0 * (bq * qs).sum() + n * (bq * bq).sum()
+    c = 1.0 / torch.sqrt(sq * sk)
+    A = Wq.transpose(1, 2) @ S                                                # [H, C, D] = Wq_h^T S_h
+    a = (bq.unsqueeze(1) @ S).squeeze(1)                                      # [H, D]    = bq_h^T S_h
+    w = (Wq.transpose(1, 2) @ z.unsqueeze(2)).squeeze(2)                      # [H, C]    = Wq_h^T z_h
+    beta = (bq * z).sum(1)                                                    # [H]
+    vpart = torch.cat([A.reshape(-1), w.reshape(-1), (u + c * a).reshape(-1), sq.reshape(1), sk.reshape(1)]).to(out_dtype).contiguous()
+    nvec = (n + c * beta).to(out_dtype).contiguous()
+    wbar, bbar = Wv.mean(0).to(out_dtype).contiguous(), bv.mean(0).to(out_dtype).contiguous()     # mean_h V = x wbar^T + bbar
+    return vpart, nvec, wbar, bbar
+
+
+def apply(x: torch.Tensor, vpart: torch.Tensor, nvec: torch.Tensor, H: int, epilogue: Optional[ops.Epilogue] = None, keep=()) -> torch.Tensor:
+    """Pass 2 on x with the projected operands -> [N, H, 64] (epilogue None) or [N, 64] (mode-1 layer epilogue)."""
+    N = x.shape[0]
+    fused = epilogue is not None and epilogue.mode == 1
+    out = torch.empty((N, HID) if fused else (N, H, HID), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.dif_simple_apply_projected(x.data_ptr(), x.stride(0), vpart.data_ptr(), nvec.data_ptr(), N, H, out.data_ptr(),
+                                             ctypes.byref(epilogue) if epilogue is not None else None, ops._stream(x)),
+              "dif_simple_apply_projected")
+    del keep
+    return out
+
+
+def attention(x: torch.Tensor, conv, n_total: Optional[float] = None) -> torch.Tensor:
+    """full_attention_conv(Wq x, Wk x, Wv x, 'simple') -> [N, H, 64] without forming Q, K, V (no autograd)."""
+    x = x.contiguous()
+    G, s = gram(x)
+    vpart, nvec, _, _ = projected_operands(G, s, float(x.shape[0] if n_total is None else n_total), conv)
+    return apply(x, vpart, nvec, conv.num_heads)

@@ -137,6 +137,15 @@ DIF_API int dif_simple_forward(const void* q, const void* k, const void* v, int 
                        float* partials, void* out, void* workspace, int64_t workspace_bytes,
                        void* const* peer_bufs, int rank, int world, unsigned long long seq, void* stream);
 
+/* Pass 2 with the Wq projection folded into its operands (difformer.py:115-118).  The A operand is the layer input
+ * x [N,64] itself (row stride ldx floats, shared by the H heads); `vpartials` holds, in the partials layout of (H, Hv = H, M = 64, D = 64),
+ * S'_h = Wq_h^T S_h, z'_h = Wq_h^T z_h, u'_h = u_h + c bq_h^T S_h and (sum q^2, sum k^2); n_total_vec[h] = N + c bq_h . z_h (device).
+ * out[n,h,:] = (c x_n S'_h + u'_h) / (c x_n . z'_h + n_total_vec[h]) = full_attention_conv(x Wq^T + bq, K, V, 'simple')[n,h,:]; with the
+ * reductions of pass 1 taken from the Gram matrix X^T X (dif_simple_reduce(x, x, x, H = 1)) neither Q nor K nor V is ever written.
+ * hidden = 64, H in {1, 2, 4}; the mode-1 epilogue (head mean, addends, LayerNorm) applies as in dif_simple_apply. */
+DIF_API int dif_simple_apply_projected(const float* x, int64_t ldx, const float* vpartials, const float* n_total_vec,
+                               int64_t N, int H, float* out, const dif_epilogue_t* epilogue, void* stream);
+
 /* Backward of the 'simple' path (derived analytically; the reference uses autograd).
  *   bwd_partials = [ dS : H*M*D | dz : H*M | du : H*D | t_q | t_k ]  (raw, additive over shards;
  *   t_k is filled by dif_simple_bwd_apply after any all-reduce). `out` is the saved forward

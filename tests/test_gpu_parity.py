@@ -764,3 +764,42 @@ def test_subgraph_on_device_matches_host_definition():
     assert sub.shape[1] == len(want)
     assert sub.cpu().t().tolist() == [[a, b] for a, b, _ in want]
     assert torch.equal(ws.cpu(), torch.tensor([x for _, _, x in want]))
+
+
+@pytest.mark.parametrize("h,use_weight", [(1, True), (1, False), (2, True), (4, True), (4, False)])
+def test_projection_folded_into_the_propagation(h, use_weight):
+    """full_attention_conv(Wq x, Wk x, Wv x) from the Gram matrix of x and the projected pass-2 operands (Q, K, V are never
+    formed) against the explicit Linears + the attention kernels, and against the fp64 oracle; then whole models with the folding on / off."""
+    from difformer_b200 import projected
+    torch.manual_seed(h)
+    n = 6000
+    conv = difformer.DIFFormerConv(64, 64, num_heads=h, kernel="simple", use_weight=use_weight).cuda().eval()
+    with torch.no_grad():
+        for p_ in conv.parameters():
+            p_.mul_(3.0)                                   # away from the near-zero initialisation: biases and weights matter
+        x = dev(torch.randn(n, 64, generator=torch.Generator().manual_seed(5)) + 0.3)
+        assert projected.supported(conv, x, x)
+        got = projected.attention(x, conv)
+        q = conv.Wq(x).reshape(n, h, 64)
+        k = conv.Wk(x).reshape(n, h, 64)
+        v = conv.Wv(x).reshape(n, h, 64) if use_weight else x.reshape(n, 1, 64)
+        ref = difformer.full_attention_conv(q, k, v, "simple")
+    want = O.simple_attention(q.double().cpu(), k.double().cpu(), v.double().cpu())
+    assert O.rel_err(ref, want) < 1e-4
+    assert O.rel_err(got, want) < 1e-4
+    # mean-collapse guard: the part of the output that is NOT mean(V) must agree too
+    dev_part = want - want.mean(0, keepdim=True)
+    err_ref = O.rel_err(ref.cpu().double() - want.mean(0, keepdim=True), dev_part)
+    assert O.rel_err(got.cpu().double() - want.mean(0, keepdim=True), dev_part) < max(5e-3, 3 * err_ref)
+    # whole model, inference: folding on == folding off (same epilogue, different route to its operands)
+    m = difformer.DIFFormer(20, 64, 5, num_layers=2, num_heads=h, kernel="simple", use_weight=use_weight, use_graph=True, use_source=True).cuda().eval()
+    xs = dev(torch.randn(900, 20, generator=torch.Generator().manual_seed(6)))
+    ei = dev(O.synthetic_graph(900, 2500, seed=3))
+    with torch.no_grad():
+        on = m(xs, ei)
+        try:
+            ops.set_projection_folding(False)
+            off = m(xs, ei)
+        finally:
+            ops.set_projection_folding(True)
+    assert O.rel_err(on, off) < 1e-4

@@ -155,3 +155,35 @@ def test_reference_parse_method_builds_this_model():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.parametrize("h,use_weight", [(1, True), (2, False), (4, True)])
+def test_projection_folding_algebra(h, use_weight):
+    """SURVEY 8f-1 on the CPU: the operands `projected.projected_operands` derives from the Gram matrix X^T X, the column sums and the
+    layer's weights reproduce full_attention_conv(Wq x, Wk x, Wv x, 'simple') exactly (fp64) -- the algebra the GPU path rests on."""
+    from difformer_b200 import projected
+    from oracle import difformer_oracle as O
+    torch.manual_seed(h)
+    n = 700
+    conv = difformer.DIFFormerConv(64, 64, num_heads=h, kernel="simple", use_weight=use_weight).double()
+    with torch.no_grad():
+        for p_ in conv.parameters():
+            p_.mul_(3.0)
+        x = torch.randn(n, 64, dtype=torch.float64) + 0.3
+        G, s = x.t() @ x, x.sum(0)
+        vpart, nvec, wbar, bbar = projected.projected_operands(G, s, float(n), conv, out_dtype=torch.float64)
+        A = vpart[:h * 4096].double().view(h, 64, 64)
+        w = vpart[h * 4096:h * 4096 + h * 64].double().view(h, 64)
+        u = vpart[h * 4096 + h * 64:h * 4096 + 2 * h * 64].double().view(h, 64)
+        c = 1.0 / torch.sqrt(vpart[-2].double() * vpart[-1].double())
+        num = c * torch.einsum("nc,hcd->nhd", x, A) + u.unsqueeze(0)
+        den = c * torch.einsum("nc,hc->nh", x, w) + nvec.double().unsqueeze(0)
+        got = num / den.unsqueeze(-1)
+        q, k = conv.Wq(x).reshape(n, h, 64), conv.Wk(x).reshape(n, h, 64)
+        v = conv.Wv(x).reshape(n, h, 64) if use_weight else x.reshape(n, 1, 64)
+        want = O.simple_attention(q, k, v)
+        assert O.rel_err(got, want) < 1e-10
+        dev_part = want - want.mean(0, keepdim=True)            # mean-collapse guard: the part of the output that is not mean(V)
+        assert O.rel_err(got - want.mean(0, keepdim=True), dev_part) < 1e-6
+        vmean = v.mean(1) if use_weight else x
+        assert O.rel_err(x @ wbar.double().t() + bbar.double(), vmean) < 1e-6
