@@ -642,6 +642,40 @@ def run_extra(args):
                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": alg / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": alg},
                      "parity": {"out": O.rel_err(layer(), want)}})
+    elif w == "layer_x":             # f-1: one whole DIFFormerConv layer from its input x [N, 64] (Linears included), no grad, config A, E = 17 N
+        from difformer_b200 import module as M_
+        n, h, d = N_NODES, HEADS, DIM
+        torch.manual_seed(11)
+        conv = difformer.DIFFormerConv(d, d, num_heads=h, kernel="simple", use_graph=True, use_weight=True).to(dev)
+        ln = torch.nn.LayerNorm(d).to(dev)
+        x = torch.randn(n, d, device=dev)
+        prev = torch.randn(n, d, device=dev)
+        ei = O.synthetic_graph(n, 8 * n, seed=4).to(dev)
+        E = ei.shape[1]
+        ops.graph_csr(ei, None, n)
+
+        def layer():
+            with torch.no_grad():
+                return M_._conv_forward(conv, x, x, ei, None, x, False, residual=(0.5, prev), layer_norm=ln)[0]
+        res = {}
+        for fold in (False, True):
+            ops.set_projection_folding(fold)
+            res[fold] = timeit(layer, steps)
+        xd = x.double().cpu()
+        qd, kd, vd = (torch.nn.functional.linear(xd, l.weight.double().cpu(), l.bias.double().cpu()).view(n, h, d) for l in (conv.Wq, conv.Wk, conv.Wv))
+        body = (O.simple_attention(qd, kd, vd) + O.gcn_conv(vd, ei.cpu(), None)).mean(1)          # difformer.py:137-140
+        want = torch.nn.functional.layer_norm(0.5 * body + 0.5 * prev.double().cpu(), (d,), ln.weight.double().cpu(), ln.bias.double().cpu(), ln.eps)
+        par = {}
+        for fold in (False, True):
+            ops.set_projection_folding(fold)
+            par["folded" if fold else "unfolded"] = O.rel_err(layer(), want)
+        ms = res[True]
+        alg = n * (3 * d * 4) + E * 8 + (n + 1) * 4        # x read (pass 1; pass 2 and the vbar GEMM re-read it from L2), prev, out
+        line.update({"metric": f"node-updates/s, DIFFormerConv layer from x (Wq/Wk/Wv + attention + gcn E={E} + head mean + residual + LayerNorm) N={n} H=4 hidden=64 fp32",
+                     "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_unfolded": res[False], "dtype": "f32",
+                     "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": alg / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": alg},
+                     "parity": par})
     elif w == "segmented":           # BASELINE configs[4]: B = 8192 graphs, n_g ~ U[10,40], H = 1, D = 64
         gen = torch.Generator().manual_seed(5)
         nn_ = torch.randint(10, 41, (8192,), generator=gen)
@@ -692,7 +726,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="simple", choices=["simple", "sigmoid_cora", "layer", "segmented", "fwdbwd"])
+    ap.add_argument("--workload", default="simple", choices=["simple", "sigmoid_cora", "layer", "layer_x", "segmented", "fwdbwd"])
     ap.add_argument("--simple-impl", default=None, choices=[None, "auto", "generic", "tcgen05"])
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"], help="'simple' forward: one cooperative kernel, or pass 1 / pass 2 as two launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
