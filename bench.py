@@ -636,7 +636,7 @@ def run_extra(args):
         alg = n * (3 * h * d * 4 + 2 * d * 4) + E * 8 + (n + 1) * 4
         attn = O.simple_attention(q.double().cpu(), k.double().cpu(), v.double().cpu())
         gcn = O.gcn_conv(v.double().cpu(), ei.cpu(), None)
-        want = 0.5 * (0.5 * attn + 0.5 * gcn).mean(1) + 0.5 * prev.double().cpu()
+        want = 0.5 * (attn + gcn).mean(1) + 0.5 * prev.double().cpu()      # alpha = 0.5, graph_weight < 0 (difformer.py:137-140, 200-201)
         line.update({"metric": f"node-updates/s, fused propagation layer (attention + gcn E={E} + head mean + residual) N={n} H=4 D=64 fp32",
                      "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f32",
                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",

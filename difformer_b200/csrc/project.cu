@@ -1,0 +1,250 @@
+// The per-layer algebra of the folded projections (reference: node classification/difformer.py:115-140 computes
+// Q = x Wq^T + bq, K = x Wk^T + bk, V = x Wv^T + bv and hands them to full_attention_conv :18-39).
+//
+// Pass 1 of 'simple' run on x itself gives the Gram matrix G = X^T X [64,64] and the column sums s = X^T 1 [64].  Everything the
+// second pass needs follows from (G, s) and the layer's weights with a few 64 x 64 products per head, in fp64 (FP64 FMAs: 1 M per
+// head -- microseconds on a handful of SMs, where the same algebra through torch ops is ~50 launches):
+//
+//     T   = Wk_h G                                   S_h = T Wv_h^T + (Wk_h s) bv_h^T + bk_h (Wv_h s)^T + n bk_h bv_h^T
+//     z_h = Wk_h s + n bk_h                          u_h = Wv_h s + n bv_h
+//     sum k^2 = sum_h <T, Wk_h> + 2 bk_h.(Wk_h s) + n |bk_h|^2          (sum q^2 alike with Wq, bq)
+//     A_h = Wq_h^T S_h     a_h = bq_h^T S_h     w_h = Wq_h^T z_h     beta_h = bq_h . z_h
+//     c   = 1 / sqrt(sum q^2 sum k^2)
+//     vpartials = [A | w | u + c a | sum q^2 | sum k^2]       n_total_vec[h] = n + c beta_h
+//
+// project_head_kernel: grid (4 column slabs, H heads); project_finish_kernel: the cross-head scalars (c) and the head-mean of Wv.
+#include "common.cuh"
+
+namespace dif {
+namespace {
+
+constexpr int kC = 64;                 // hidden size (in = out = 64)
+constexpr int kSlabs = 4;              // 16 columns of S / A per block
+constexpr int kSlabW = kC / kSlabs;
+constexpr int kThreads = 256;
+
+// workspace (doubles) per head: a[64] | u[64] | beta | sk | sq[kSlabs]
+constexpr int kWsHead = 2 * kC + 2 + kSlabs;
+
+struct ProjectArgs {
+    const float* gram;                 // partials layout of (H=1, Hv=1, 64, 64): G[4096] | s[64] | s[64] | sum x^2 | sum x^2
+    const float *Wq, *bq, *Wk, *bk, *Wv, *bv;     // nn.Linear layout: weight [H*64, 64] row-major, bias [H*64]; Wv null: V_h = x
+    double n;
+    int H;
+    float* vpartials;
+    double* ws;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w];      // fixed order: deterministic
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sG = reinterpret_cast<float*>(smem_raw);           // [64][64]
+    float* sWk = sG + kC * kC;
+    float* sWq = sWk + kC * kC;
+    float* sWv = sWq + kC * kC;
+    double* sT = reinterpret_cast<double*>(sWv + kC * kC);    // [64][64]  Wk_h G
+    double* sS = sT + kC * kC;                                // [64][kSlabW]
+    double* sv = sS + kC * kSlabW;                            // s | ks | vs | qs | bk | bv | bq | z : 8 x 64
+    double* red = sv + 8 * kC;                                // 8
+    double *s_ = sv, *ks = sv + kC, *vs = sv + 2 * kC, *qs = sv + 3 * kC, *bk = sv + 4 * kC, *bv = sv + 5 * kC, *bq = sv + 6 * kC,
+           *z = sv + 7 * kC;
+
+    const int t = threadIdx.x, slab = blockIdx.x, h = blockIdx.y;
+    const int H = p.H;
+    for (int i = t; i < kC * kC; i += kThreads) {
+        sG[i] = p.gram[i];
+        sWk[i] = p.Wk[(size_t)h * kC * kC + i];
+        sWq[i] = p.Wq[(size_t)h * kC * kC + i];
+        sWv[i] = p.Wv ? p.Wv[(size_t)h * kC * kC + i] : ((i / kC) == (i % kC) ? 1.f : 0.f);
+    }
+    if (t < kC) {
+        s_[t] = p.gram[kC * kC + t];
+        bk[t] = p.bk[h * kC + t];
+        bq[t] = p.bq[h * kC + t];
+        bv[t] = p.Wv ? (double)p.bv[h * kC + t] : 0.0;
+    }
+    __syncthreads();
+
+    if (t < 3 * kC) {                                         // ks = Wk s, vs = Wv s, qs = Wq s
+        const float* W = t < kC ? sWk : (t < 2 * kC ? sWv : sWq);
+        const int r = t & (kC - 1);
+        double acc = 0.0;
+        for (int j = 0; j < kC; ++j) acc += (double)W[r * kC + ((j + r) & (kC - 1))] * s_[(j + r) & (kC - 1)];   // rotated: no bank conflicts
+        (t < kC ? ks : (t < 2 * kC ? vs : qs))[r] = acc;
+    }
+
+    // T = Wk G: thread -> row m, 16 columns
+    double skp = 0.0;
+    {
+        const int m = t >> 2, c0 = (t & 3) * 16;
+        double acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+        for (int j = 0; j < kC; ++j) {
+            const double w = sWk[m * kC + j];
+            const float4* g = reinterpret_cast<const float4*>(sG + j * kC + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 gv = g[i];
+                acc[4 * i + 0] += w * gv.x; acc[4 * i + 1] += w * gv.y; acc[4 * i + 2] += w * gv.z; acc[4 * i + 3] += w * gv.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            sT[m * kC + c0 + i] = acc[i];
+            skp += acc[i] * sWk[m * kC + c0 + i];
+        }
+    }
+    // 16 rows of Wq G (this slab's share of sum q^2): thread -> row r, 4 columns
+    double sqp = 0.0;
+    {
+        const int r = slab * kSlabW + (t >> 4), c0 = (t & 15) * 4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < kC; ++j) {
+            const double w = sWq[r * kC + j];
+            const float4 gv = *reinterpret_cast<const float4*>(sG + j * kC + c0);
+            acc[0] += w * gv.x; acc[1] += w * gv.y; acc[2] += w * gv.z; acc[3] += w * gv.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sqp += acc[i] * sWq[r * kC + c0 + i];
+    }
+    __syncthreads();                                          // sT, ks, vs, qs complete
+    if (t < kC) z[t] = ks[t] + p.n * bk[t];
+
+    // S slab: S[m][d] = sum_c T[m][c] Wv[d][c] + ks[m] bv[d] + bk[m] vs[d] + n bk[m] bv[d]
+    {
+        const int m = t >> 2, dl0 = (t & 3) * 4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < kC; ++c) {
+            const int cc = (c + m) & (kC - 1);
+            const double tv = sT[m * kC + cc];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += tv * (double)sWv[(slab * kSlabW + dl0 + i) * kC + cc];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int d = slab * kSlabW + dl0 + i;
+            sS[m * kSlabW + dl0 + i] = acc[i] + ks[m] * bv[d] + bk[m] * vs[d] + p.n * bk[m] * bv[d];
+        }
+    }
+    __syncthreads();
+
+    // A slab: A[c][d] = sum_m Wq[m][c] S[m][d]
+    {
+        const int c = t >> 2, dl0 = (t & 3) * 4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int m = 0; m < kC; ++m) {
+            const double w = sWq[m * kC + c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += w * sS[m * kSlabW + dl0 + i];
+        }
+        float4 o = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
+        *reinterpret_cast<float4*>(p.vpartials + (size_t)h * kC * kC + c * kC + slab * kSlabW + dl0) = o;
+    }
+    double* wsh = p.ws + (size_t)h * kWsHead;
+    if (t < kSlabW) {                                         // a[d] = bq^T S, u[d] = vs + n bv
+        const int d = slab * kSlabW + t;
+        double acc = 0.0;
+        for (int m = 0; m < kC; ++m) acc += bq[m] * sS[m * kSlabW + t];
+        wsh[d] = acc;
+        wsh[kC + d] = vs[d] + p.n * bv[d];
+    }
+    if (slab == 0 && t >= 64 && t < 64 + kC) {                // w[c] = Wq^T z
+        const int c = t - 64;
+        double acc = 0.0;
+        for (int m = 0; m < kC; ++m) acc += (double)sWq[m * kC + c] * z[m];
+        p.vpartials[(size_t)H * kC * kC + h * kC + c] = (float)acc;
+    }
+    // scalars
+    double e_q = 0.0, e_k = 0.0, e_b = 0.0;
+    if (t < kC) {
+        e_k = 2.0 * bk[t] * ks[t] + p.n * bk[t] * bk[t];
+        e_q = 2.0 * bq[t] * qs[t] + p.n * bq[t] * bq[t];
+        e_b = bq[t] * z[t];
+    }
+    const double sk = block_sum(skp + e_k, red);
+    const double sq = block_sum(sqp + (slab == 0 ? e_q : 0.0), red);
+    const double beta = block_sum(e_b, red);
+    if (t == 0) {
+        wsh[2 * kC + 2 + slab] = sq;
+        if (slab == 0) {
+            wsh[2 * kC] = beta;
+            wsh[2 * kC + 1] = sk;
+        }
+    }
+}
+
+struct FinishArgs {
+    const double* ws;
+    const float *Wv, *bv;
+    double n;
+    int H;
+    float *vpartials, *nvec, *wbar, *bbar;
+};
+
+__global__ void __launch_bounds__(kThreads) project_finish_kernel(FinishArgs p) {
+    const int t = threadIdx.x, H = p.H;
+    double sq = 0.0, sk = 0.0;
+    for (int h = 0; h < H; ++h) {                             // every thread: the same fixed-order sum
+        const double* w = p.ws + (size_t)h * kWsHead;
+        sk += w[2 * kC + 1];
+        for (int j = 0; j < kSlabs; ++j) sq += w[2 * kC + 2 + j];
+    }
+    const double c = 1.0 / sqrt(sq * sk);
+    float* uo = p.vpartials + (size_t)H * kC * kC + H * kC;
+    for (int i = t; i < H * kC; i += kThreads) {
+        const double* w = p.ws + (size_t)(i / kC) * kWsHead;
+        uo[i] = (float)(w[kC + (i % kC)] + c * w[i % kC]);
+    }
+    if (t < H) p.nvec[t] = (float)(p.n + c * p.ws[(size_t)t * kWsHead + 2 * kC]);
+    if (t == 0) {
+        uo[H * kC] = (float)sq;
+        uo[H * kC + 1] = (float)sk;
+    }
+    for (int i = t; i < kC * kC; i += kThreads) {             // mean_h V = x wbar^T + bbar
+        double acc = 0.0;
+        if (p.Wv) { for (int h = 0; h < H; ++h) acc += p.Wv[(size_t)h * kC * kC + i]; acc /= H; }
+        else acc = (i / kC) == (i % kC) ? 1.0 : 0.0;
+        p.wbar[i] = (float)acc;
+    }
+    if (t < kC) {
+        double acc = 0.0;
+        if (p.Wv) { for (int h = 0; h < H; ++h) acc += p.bv[h * kC + t]; acc /= H; }
+        p.bbar[t] = (float)acc;
+    }
+}
+
+constexpr size_t kSmemHead = 4 * kC * kC * sizeof(float) + (kC * kC + kC * kSlabW + 8 * kC + 8) * sizeof(double);
+
+}  // namespace
+
+int64_t simple_project_workspace_bytes(int H) { return (int64_t)H * kWsHead * (int64_t)sizeof(double); }
+
+int simple_project(const float* gram, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv, const float* bv,
+                   double n_total, int H, float* vpartials, float* nvec, float* wbar, float* bbar, void* ws, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    DIF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(project_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHead));
+        attr_set[dev] = true;
+    }
+    ProjectArgs a{gram, Wq, bq, Wk, bk, Wv, bv, n_total, H, vpartials, reinterpret_cast<double*>(ws)};
+    project_head_kernel<<<dim3(kSlabs, H), kThreads, kSmemHead, st>>>(a);
+    DIF_LAUNCH_OK();
+    FinishArgs f{reinterpret_cast<const double*>(ws), Wv, bv, n_total, H, vpartials, nvec, wbar, bbar};
+    project_finish_kernel<<<1, kThreads, 0, st>>>(f);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+}  // namespace dif

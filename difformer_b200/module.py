@@ -39,8 +39,7 @@ def _conv_forward_projected(conv, x, edge_index, edge_weight, x_0, residual, lay
     alpha = 1.0 if residual is None else float(residual[0])
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
-    G, s = projected.gram(x)
-    vpart, nvec, wbar, bbar = projected.projected_operands(G, s, float(N), conv)
+    vpart, nvec, wbar, bbar = projected.projected_operands(projected.gram(x), float(N), conv)
     addends = []
     if conv.use_graph:
         csr = ops.graph_csr(edge_index, edge_weight, N)

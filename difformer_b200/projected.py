@@ -13,7 +13,7 @@ and pass 2 needs q_h only inside the products q_h S_h and q_h . z_h, which are a
 
     q_h S_h = x (Wq_h^T S_h) + bq_h^T S_h            q_h . z_h = x . (Wq_h^T z_h) + bq_h . z_h
 
-So a layer runs as  [pass 1 on x: G, s]  ->  [this file: a few 64 x 64 products per head, fp64]  ->  [pass 2 on x with the
+So a layer runs as  [pass 1 on x: G, s]  ->  [dif_simple_project: a few 64 x 64 products per head, fp64]  ->  [pass 2 on x with the
 projected operands, dif_simple_apply_projected]  and Q, K, V are never formed, written or read: 256 B (pass 1) + 256 B (pass 2) of
 input per node instead of 3 KB + 1 KB, and the three Linear GEMMs disappear.  Inference path (no autograd), hidden = 64, H in
 {1, 2, 4}; `use_weight=False` (V = x, one head) is the case Wv = I, bv = 0.
@@ -36,42 +36,36 @@ def supported(conv, query_input: torch.Tensor, source_input: torch.Tensor) -> bo
             and ops._SIMPLE_IMPL != ops._lib.DIF_IMPL_GENERIC and conv.Wq.in_features == HID)
 
 
-def gram(x: torch.Tensor):
-    """One pass over x [N, 64]: G = X^T X [64, 64], s = column sums [64], sum x^2 -- pass 1 of 'simple' with q = k = v = x, H = 1
-    (tcgen05 kernel, deterministic)."""
+def gram(x: torch.Tensor) -> torch.Tensor:
+    """One pass over x [N, 64] -> the partials of (H = Hv = 1, 64, 64): [X^T X | X^T 1 | X^T 1 | sum x^2 | sum x^2] -- pass 1 of 'simple'
+    with q = k = v = x (tcgen05 kernel, deterministic).  Additive over row shards."""
     x3 = x.view(-1, 1, HID)
-    flat = ops.simple_partials(x3, x3, x3)
-    return flat[:HID * HID].view(HID, HID), flat[HID * HID:HID * HID + HID]
+    return ops.simple_partials(x3, x3, x3)
 
 
-def projected_operands(G: torch.Tensor, s: torch.Tensor, n_total: float, conv, out_dtype=torch.float32):
-    """The pass-2 operands of every head from (G, s) and the layer's weights: (vpartials fp32 in the partials layout of
-    (H, Hv = H, 64, 64), nvec fp32 [H], vbar weight [64, 64] and bias [64] of mean_h V).  Tiny (64 x 64 per head): fp64 torch ops."""
+def _w(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def projected_operands(gram_partials: torch.Tensor, n_total: float, conv):
+    """The pass-2 operands of every head from the Gram partials and the layer's weights (dif_simple_project: fp64 arithmetic, two small
+    launches): (vpartials fp32 in the partials layout of (H, Hv = H, 64, 64), nvec fp32 [H], weight [64, 64] and bias [64] of mean_h V).
+    The same algebra in torch fp64, which the tests check this against: oracle.difformer_oracle.projected_operands."""
     H = conv.num_heads
-    G, s = G.double(), s.double()
-    Wq, bq = conv.Wq.weight.double().view(H, HID, HID), conv.Wq.bias.double().view(H, HID)
-    Wk, bk = conv.Wk.weight.double().view(H, HID, HID), conv.Wk.bias.double().view(H, HID)
-    if conv.use_weight:
-        Wv, bv = conv.Wv.weight.double().view(H, HID, HID), conv.Wv.bias.double().view(H, HID)
-    else:                                                   # value = source_input.reshape(-1, 1, C) (difformer.py:120): V_h = x for every head
-        Wv = torch.eye(HID, dtype=torch.float64, device=G.device).expand(H, HID, HID)
-        bv = torch.zeros(H, HID, dtype=torch.float64, device=G.device)
-    n = float(n_total)
-    ks, vs, qs = Wk @ s, Wv @ s, Wq @ s                                       # [H, 64] each: W_h s
-    S = Wk @ G @ Wv.transpose(1, 2) + ks.unsqueeze(2) * bv.unsqueeze(1) + bk.unsqueeze(2) * vs.unsqueeze(1) \
-        + n * bk.unsqueeze(2) * bv.unsqueeze(1)                               # [H, M, D]
-    z = ks + n * bk
-    u = vs + n * bv
-    sk = ((Wk @ G) * Wk).sum() + 2.0 * (bk * ks).sum() + n * (bk * bk).sum()
-    sq = ((Wq @ G) * Wq).sum() + 2.0 * (bq * qs).sum() + n * (bq * bq).sum()
-    c = 1.0 / torch.sqrt(sq * sk)
-    A = Wq.transpose(1, 2) @ S                                                # [H, C, D] = Wq_h^T S_h
-    a = (bq.unsqueeze(1) @ S).squeeze(1)                                      # [H, D]    = bq_h^T S_h
-    w = (Wq.transpose(1, 2) @ z.unsqueeze(2)).squeeze(2)                      # [H, C]    = Wq_h^T z_h
-    beta = (bq * z).sum(1)                                                    # [H]
-    vpart = torch.cat([A.reshape(-1), w.reshape(-1), (u + c * a).reshape(-1), sq.reshape(1), sk.reshape(1)]).to(out_dtype).contiguous()
-    nvec = (n + c * beta).to(out_dtype).contiguous()
-    wbar, bbar = Wv.mean(0).to(out_dtype).contiguous(), bv.mean(0).to(out_dtype).contiguous()     # mean_h V = x wbar^T + bbar
+    dev = gram_partials.device
+    Wq, bq, Wk, bk = _w(conv.Wq.weight), _w(conv.Wq.bias), _w(conv.Wk.weight), _w(conv.Wk.bias)
+    Wv, bv = (_w(conv.Wv.weight), _w(conv.Wv.bias)) if conv.use_weight else (None, None)
+    vpart = torch.empty(H * HID * HID + 2 * H * HID + 2, dtype=torch.float32, device=dev)
+    nvec = torch.empty(H, dtype=torch.float32, device=dev)
+    wbar = torch.empty(HID, HID, dtype=torch.float32, device=dev)
+    bbar = torch.empty(HID, dtype=torch.float32, device=dev)
+    ws = ops.workspace(dev, lib.dif_simple_project_workspace_bytes(H))
+    with torch.cuda.device(dev):
+        check(lib.dif_simple_project(gram_partials.data_ptr(), Wq.data_ptr(), bq.data_ptr(), Wk.data_ptr(), bk.data_ptr(),
+                                     None if Wv is None else Wv.data_ptr(), None if bv is None else bv.data_ptr(), float(n_total), H,
+                                     vpart.data_ptr(), nvec.data_ptr(), wbar.data_ptr(), bbar.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     ops._stream(gram_partials)), "dif_simple_project")
     return vpart, nvec, wbar, bbar
 
 
@@ -91,6 +85,5 @@ def apply(x: torch.Tensor, vpart: torch.Tensor, nvec: torch.Tensor, H: int, epil
 def attention(x: torch.Tensor, conv, n_total: Optional[float] = None) -> torch.Tensor:
     """full_attention_conv(Wq x, Wk x, Wv x, 'simple') -> [N, H, 64] without forming Q, K, V (no autograd)."""
     x = x.contiguous()
-    G, s = gram(x)
-    vpart, nvec, _, _ = projected_operands(G, s, float(x.shape[0] if n_total is None else n_total), conv)
+    vpart, nvec, _, _ = projected_operands(gram(x), float(x.shape[0] if n_total is None else n_total), conv)
     return apply(x, vpart, nvec, conv.num_heads)

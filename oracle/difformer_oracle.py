@@ -399,3 +399,37 @@ def rel_err(x: Tensor, ref: Tensor) -> float:
     x, ref = x.detach().to(dev, torch.float64), ref.detach().to(dev, torch.float64)
     den = float(torch.linalg.vector_norm(ref))
     return float(torch.linalg.vector_norm(x - ref)) / (den if den > 0 else 1.0)
+
+
+def projected_operands(G: Tensor, s: Tensor, n_total: float, Wq: Tensor, bq: Tensor, Wk: Tensor, bk: Tensor,
+                       Wv: Optional[Tensor], bv: Optional[Tensor], H: int):
+    """The pass-2 operands of 'simple' attention when Q = x Wq^T + bq, K = x Wk^T + bk, V = x Wv^T + bv (difformer.py:115-120) are
+    never formed: everything full_attention_conv (difformer.py:18-39) reduces over the rows follows from G = X^T X and s = X^T 1.
+    fp64 torch restatement of difformer_b200/csrc/project.cu (test infrastructure).  Weights in nn.Linear layout [H*C, C] / [H*C];
+    Wv = None: V_h = x.  Returns (vpartials [H*C*C + 2*H*C + 2], nvec [H], wbar [C, C], bbar [C]) in fp64:
+        vpartials = [Wq_h^T S_h | Wq_h^T z_h | u_h + c bq_h^T S_h | sum q^2 | sum k^2],  nvec[h] = n + c bq_h . z_h."""
+    C = G.shape[0]
+    G, s = G.double(), s.double()
+    Wq, bq = Wq.double().view(H, C, C), bq.double().view(H, C)
+    Wk, bk = Wk.double().view(H, C, C), bk.double().view(H, C)
+    if Wv is not None:
+        Wv, bv = Wv.double().view(H, C, C), bv.double().view(H, C)
+    else:
+        Wv = torch.eye(C, dtype=torch.float64).expand(H, C, C)
+        bv = torch.zeros(H, C, dtype=torch.float64)
+    n = float(n_total)
+    ks, vs, qs = Wk @ s, Wv @ s, Wq @ s
+    S = Wk @ G @ Wv.transpose(1, 2) + ks.unsqueeze(2) * bv.unsqueeze(1) + bk.unsqueeze(2) * vs.unsqueeze(1) \
+        + n * bk.unsqueeze(2) * bv.unsqueeze(1)
+    z = ks + n * bk
+    u = vs + n * bv
+    sk = ((Wk @ G) * Wk).sum() + 2.0 * (bk * ks).sum() + n * (bk * bk).sum()
+    sq = ((Wq @ G) * Wq).sum() + 2.0 * (bq * qs).sum() + n * (bq * bq).sum()
+    c = 1.0 / torch.sqrt(sq * sk)
+    A = Wq.transpose(1, 2) @ S
+    a = (bq.unsqueeze(1) @ S).squeeze(1)
+    w = (Wq.transpose(1, 2) @ z.unsqueeze(2)).squeeze(2)
+    beta = (bq * z).sum(1)
+    vpart = torch.cat([A.reshape(-1), w.reshape(-1), (u + c * a).reshape(-1), sq.reshape(1), sk.reshape(1)])
+    return vpart, n + c * beta, Wv.mean(0), bv.mean(0)
+

@@ -780,6 +780,16 @@ def test_projection_folded_into_the_propagation(h, use_weight):
         x = dev(torch.randn(n, 64, generator=torch.Generator().manual_seed(5)) + 0.3)
         assert projected.supported(conv, x, x)
         got = projected.attention(x, conv)
+        # dif_simple_project against its fp64 restatement, on the exact Gram matrix the kernel saw
+        gp = projected.gram(x)
+        ops_k = projected.projected_operands(gp, float(n), conv)
+        cw = lambda t: None if t is None else t.detach().cpu()
+        ops_o = O.projected_operands(gp[:4096].view(64, 64).cpu(), gp[4096:4160].cpu(), float(n), cw(conv.Wq.weight), cw(conv.Wq.bias),
+                                     cw(conv.Wk.weight), cw(conv.Wk.bias), cw(conv.Wv.weight if use_weight else None),
+                                     cw(conv.Wv.bias if use_weight else None), h)
+        for name, a_, b_ in zip(("vpartials", "nvec", "wbar", "bbar"), ops_k, ops_o):
+            assert O.rel_err(a_, b_) < 1e-6, name
+        assert O.rel_err(gp[:4096].view(64, 64), x.double().t() @ x.double()) < 1e-5
         q = conv.Wq(x).reshape(n, h, 64)
         k = conv.Wk(x).reshape(n, h, 64)
         v = conv.Wv(x).reshape(n, h, 64) if use_weight else x.reshape(n, 1, 64)

@@ -159,9 +159,9 @@ def test_reference_parse_method_builds_this_model():
 
 @pytest.mark.parametrize("h,use_weight", [(1, True), (2, False), (4, True)])
 def test_projection_folding_algebra(h, use_weight):
-    """SURVEY 8f-1 on the CPU: the operands `projected.projected_operands` derives from the Gram matrix X^T X, the column sums and the
-    layer's weights reproduce full_attention_conv(Wq x, Wk x, Wv x, 'simple') exactly (fp64) -- the algebra the GPU path rests on."""
-    from difformer_b200 import projected
+    """SURVEY 8f-1 on the CPU: the operands `oracle.projected_operands` (the fp64 restatement of csrc/project.cu) derives from the Gram
+    matrix X^T X, the column sums and the layer's weights reproduce full_attention_conv(Wq x, Wk x, Wv x, 'simple') exactly (fp64) --
+    the algebra the GPU path rests on; the GPU tests check the kernel against this restatement."""
     from oracle import difformer_oracle as O
     torch.manual_seed(h)
     n = 700
@@ -171,7 +171,8 @@ def test_projection_folding_algebra(h, use_weight):
             p_.mul_(3.0)
         x = torch.randn(n, 64, dtype=torch.float64) + 0.3
         G, s = x.t() @ x, x.sum(0)
-        vpart, nvec, wbar, bbar = projected.projected_operands(G, s, float(n), conv, out_dtype=torch.float64)
+        vpart, nvec, wbar, bbar = O.projected_operands(G, s, float(n), conv.Wq.weight, conv.Wq.bias, conv.Wk.weight, conv.Wk.bias,
+                                                       conv.Wv.weight if use_weight else None, conv.Wv.bias if use_weight else None, h)
         A = vpart[:h * 4096].double().view(h, 64, 64)
         w = vpart[h * 4096:h * 4096 + h * 64].double().view(h, 64)
         u = vpart[h * 4096 + h * 64:h * 4096 + 2 * h * 64].double().view(h, 64)
