@@ -657,10 +657,16 @@ def run_extra(args):
         def layer():
             with torch.no_grad():
                 return M_._conv_forward(conv, x, x, ei, None, x, False, residual=(0.5, prev), layer_norm=ln)[0]
-        res = {}
+        res, host = {}, {}
         for fold in (False, True):
             ops.set_projection_folding(fold)
             res[fold] = timeit(layer, steps)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                layer()
+            host[fold] = (time.perf_counter() - t0) / steps * 1e3        # enqueue cost of one layer (no sync): the floor the GPU time must stay above
+            torch.cuda.synchronize()
         xd = x.double().cpu()
         qd, kd, vd = (torch.nn.functional.linear(xd, l.weight.double().cpu(), l.bias.double().cpu()).view(n, h, d) for l in (conv.Wq, conv.Wk, conv.Wv))
         body = (O.simple_attention(qd, kd, vd) + O.gcn_conv(vd, ei.cpu(), None)).mean(1)          # difformer.py:137-140
@@ -672,7 +678,8 @@ def run_extra(args):
         ms = res[True]
         alg = n * (3 * d * 4) + E * 8 + (n + 1) * 4        # x read (pass 1; pass 2 and the vbar GEMM re-read it from L2), prev, out
         line.update({"metric": f"node-updates/s, DIFFormerConv layer from x (Wq/Wk/Wv + attention + gcn E={E} + head mean + residual + LayerNorm) N={n} H=4 hidden=64 fp32",
-                     "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_unfolded": res[False], "dtype": "f32",
+                     "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_unfolded": res[False], "host_enqueue_ms": host[True],
+                     "host_enqueue_ms_unfolded": host[False], "dtype": "f32",
                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": alg / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": alg},
                      "parity": par})

@@ -148,14 +148,14 @@ extern "C" int dif_simple_apply_projected(const float* x, int64_t ldx, const flo
 extern "C" int64_t dif_simple_project_workspace_bytes(int H) { return (H == 1 || H == 2 || H == 4) ? simple_project_workspace_bytes(H) : 0; }
 
 extern "C" int dif_simple_project(const float* gram_partials, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
-                                  const float* bv, double n_total, int H, float* vpartials, float* n_total_vec, float* wbar, float* bbar,
+                                  const float* bv, double n_total, int H, float* vpartials, float* n_total_vec, float* vbar_partials,
                                   void* workspace, int64_t workspace_bytes, void* stream) {
-    DIF_REQUIRE(gram_partials && Wq && bq && Wk && bk && vpartials && n_total_vec && wbar && bbar && workspace, DIF_EARG,
+    DIF_REQUIRE(gram_partials && Wq && bq && Wk && bk && vpartials && n_total_vec && vbar_partials && workspace, DIF_EARG,
                 "simple_project: null pointer");
     DIF_REQUIRE((Wv == nullptr) == (bv == nullptr), DIF_EARG, "simple_project: Wv and bv must both be given or both be null");
     DIF_REQUIRE(H == 1 || H == 2 || H == 4, DIF_EUNSUPPORTED, "simple_project: H=%d (needs H in {1, 2, 4}, hidden = 64)", H);
     DIF_REQUIRE(n_total > 0, DIF_EARG, "simple_project: n_total must be positive");
     DIF_REQUIRE(workspace_bytes >= simple_project_workspace_bytes(H) && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0, DIF_EARG,
                 "simple_project: workspace too small or not 8-byte aligned");
-    return simple_project(gram_partials, Wq, bq, Wk, bk, Wv, bv, n_total, H, vpartials, n_total_vec, wbar, bbar, workspace, (cudaStream_t)stream);
+    return simple_project(gram_partials, Wq, bq, Wk, bk, Wv, bv, n_total, H, vpartials, n_total_vec, vbar_partials, workspace, (cudaStream_t)stream);
 }

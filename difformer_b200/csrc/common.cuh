@@ -213,7 +213,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
                      void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0, float* vbar = nullptr);
 int64_t simple_project_workspace_bytes(int H);
 int simple_project(const float* gram, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv, const float* bv,
-                   double n_total, int H, float* vpartials, float* nvec, float* wbar, float* bbar, void* ws, cudaStream_t st);
+                   double n_total, int H, float* vpartials, float* nvec, float* vbar_partials, void* ws, cudaStream_t st);
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st, int64_t q_ld = 0, int q_hs = 0, const float* nvec = nullptr);
 

@@ -12,7 +12,7 @@
 //     c   = 1 / sqrt(sum q^2 sum k^2)
 //     vpartials = [A | w | u + c a | sum q^2 | sum k^2]       n_total_vec[h] = n + c beta_h
 //
-// project_head_kernel: grid (4 column slabs, H heads); project_finish_kernel: the cross-head scalars (c) and the head-mean of Wv.
+// project_head_kernel: grid (4 column slabs, H heads), also the head mean of Wv; project_finish_kernel: the cross-head scalar c.
 #include "common.cuh"
 
 namespace dif {
@@ -32,6 +32,7 @@ struct ProjectArgs {
     double n;
     int H;
     float* vpartials;
+    float* vbar_partials;              // partials layout of (1, 1, 64, 64) that makes pass 2 compute mean_h V = x wbar^T + bbar
     double* ws;
 };
 
@@ -47,11 +48,12 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sG = reinterpret_cast<float*>(smem_raw);           // [64][64]
-    float* sWk = sG + kC * kC;
-    float* sWq = sWk + kC * kC;
-    float* sWv = sWq + kC * kC;
-    double* sT = reinterpret_cast<double*>(sWv + kC * kC);    // [64][64]  Wk_h G
+    // everything is widened to fp64 once on the way in: an F2F per FMA would run at a quarter of the DFMA rate
+    double* sG = reinterpret_cast<double*>(smem_raw);         // [64][64]
+    double* sWk = sG + kC * kC;
+    double* sWq = sWk + kC * kC;
+    double* sWv = sWq + kC * kC;
+    double* sT = sWv + kC * kC;                               // [64][64]  Wk_h G
     double* sS = sT + kC * kC;                                // [64][kSlabW]
     double* sv = sS + kC * kSlabW;                            // s | ks | vs | qs | bk | bv | bq | z : 8 x 64
     double* red = sv + 8 * kC;                                // 8
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
         sG[i] = p.gram[i];
         sWk[i] = p.Wk[(size_t)h * kC * kC + i];
         sWq[i] = p.Wq[(size_t)h * kC * kC + i];
-        sWv[i] = p.Wv ? p.Wv[(size_t)h * kC * kC + i] : ((i / kC) == (i % kC) ? 1.f : 0.f);
+        sWv[i] = p.Wv ? (double)p.Wv[(size_t)h * kC * kC + i] : ((i / kC) == (i % kC) ? 1.0 : 0.0);
     }
     if (t < kC) {
         s_[t] = p.gram[kC * kC + t];
@@ -75,10 +77,10 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     __syncthreads();
 
     if (t < 3 * kC) {                                         // ks = Wk s, vs = Wv s, qs = Wq s
-        const float* W = t < kC ? sWk : (t < 2 * kC ? sWv : sWq);
+        const double* W = t < kC ? sWk : (t < 2 * kC ? sWv : sWq);
         const int r = t & (kC - 1);
         double acc = 0.0;
-        for (int j = 0; j < kC; ++j) acc += (double)W[r * kC + ((j + r) & (kC - 1))] * s_[(j + r) & (kC - 1)];   // rotated: no bank conflicts
+        for (int j = 0; j < kC; ++j) acc += W[r * kC + ((j + r) & (kC - 1))] * s_[(j + r) & (kC - 1)];   // rotated: no bank conflicts
         (t < kC ? ks : (t < 2 * kC ? vs : qs))[r] = acc;
     }
 
@@ -91,11 +93,11 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         for (int j = 0; j < kC; ++j) {
             const double w = sWk[m * kC + j];
-            const float4* g = reinterpret_cast<const float4*>(sG + j * kC + c0);
+            const double2* g = reinterpret_cast<const double2*>(sG + j * kC + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 gv = g[i];
-                acc[4 * i + 0] += w * gv.x; acc[4 * i + 1] += w * gv.y; acc[4 * i + 2] += w * gv.z; acc[4 * i + 3] += w * gv.w;
+            for (int i = 0; i < 8; ++i) {
+                const double2 gv = g[i];
+                acc[2 * i + 0] += w * gv.x; acc[2 * i + 1] += w * gv.y;
             }
         }
 #pragma unroll
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j = 0; j < kC; ++j) {
             const double w = sWq[r * kC + j];
-            const float4 gv = *reinterpret_cast<const float4*>(sG + j * kC + c0);
-            acc[0] += w * gv.x; acc[1] += w * gv.y; acc[2] += w * gv.z; acc[3] += w * gv.w;
+            const double2 g0 = *reinterpret_cast<const double2*>(sG + j * kC + c0), g1 = *reinterpret_cast<const double2*>(sG + j * kC + c0 + 2);
+            acc[0] += w * g0.x; acc[1] += w * g0.y; acc[2] += w * g1.x; acc[3] += w * g1.y;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) sqp += acc[i] * sWq[r * kC + c0 + i];
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
             const int cc = (c + m) & (kC - 1);
             const double tv = sT[m * kC + cc];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += tv * (double)sWv[(slab * kSlabW + dl0 + i) * kC + cc];
+            for (int i = 0; i < 4; ++i) acc[i] += tv * sWv[(slab * kSlabW + dl0 + i) * kC + cc];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -161,8 +163,27 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     if (slab == 0 && t >= 64 && t < 64 + kC) {                // w[c] = Wq^T z
         const int c = t - 64;
         double acc = 0.0;
-        for (int m = 0; m < kC; ++m) acc += (double)sWq[m * kC + c] * z[m];
+        for (int m = 0; m < kC; ++m) acc += sWq[m * kC + c] * z[m];
         p.vpartials[(size_t)H * kC * kC + h * kC + c] = (float)acc;
+    }
+    if (h == 0) {
+        // mean_h V = x wbar^T + bbar (the input of the gcn term, difformer.py:139) as a pass-2 problem with one head:
+        // S[m][d] = mean_h Wv_h[d][m], z = 0, u = bbar, sum q^2 = sum k^2 = 1 (c = 1), denominator constant 1
+        float* vb = p.vbar_partials;
+        for (int i = slab * (kC * kC / kSlabs) + t; i < (slab + 1) * (kC * kC / kSlabs); i += kThreads) {
+            const int m = i / kC, d = i % kC;
+            double acc = 0.0;
+            if (p.Wv) { for (int hh = 0; hh < H; ++hh) acc += (double)p.Wv[((size_t)hh * kC + d) * kC + m]; acc /= H; }
+            else acc = m == d ? 1.0 : 0.0;
+            vb[i] = (float)acc;
+        }
+        if (slab == 0 && t < kC) {
+            double acc = 0.0;
+            if (p.Wv) { for (int hh = 0; hh < H; ++hh) acc += (double)p.bv[hh * kC + t]; acc /= H; }
+            vb[kC * kC + t] = 0.f;
+            vb[kC * kC + kC + t] = (float)acc;
+            if (t < 2) vb[kC * kC + 2 * kC + t] = 1.f;
+        }
     }
     // scalars
     double e_q = 0.0, e_k = 0.0, e_b = 0.0;
@@ -188,7 +209,7 @@ struct FinishArgs {
     const float *Wv, *bv;
     double n;
     int H;
-    float *vpartials, *nvec, *wbar, *bbar;
+    float *vpartials, *nvec;
 };
 
 __global__ void __launch_bounds__(kThreads) project_finish_kernel(FinishArgs p) {
@@ -206,42 +227,32 @@ __global__ void __launch_bounds__(kThreads) project_finish_kernel(FinishArgs p) 
         uo[i] = (float)(w[kC + (i % kC)] + c * w[i % kC]);
     }
     if (t < H) p.nvec[t] = (float)(p.n + c * p.ws[(size_t)t * kWsHead + 2 * kC]);
+    if (t == H) p.nvec[H] = 1.f;                              // the denominator constant of the vbar problem
     if (t == 0) {
         uo[H * kC] = (float)sq;
         uo[H * kC + 1] = (float)sk;
     }
-    for (int i = t; i < kC * kC; i += kThreads) {             // mean_h V = x wbar^T + bbar
-        double acc = 0.0;
-        if (p.Wv) { for (int h = 0; h < H; ++h) acc += p.Wv[(size_t)h * kC * kC + i]; acc /= H; }
-        else acc = (i / kC) == (i % kC) ? 1.0 : 0.0;
-        p.wbar[i] = (float)acc;
-    }
-    if (t < kC) {
-        double acc = 0.0;
-        if (p.Wv) { for (int h = 0; h < H; ++h) acc += p.bv[h * kC + t]; acc /= H; }
-        p.bbar[t] = (float)acc;
-    }
 }
 
-constexpr size_t kSmemHead = 4 * kC * kC * sizeof(float) + (kC * kC + kC * kSlabW + 8 * kC + 8) * sizeof(double);
+constexpr size_t kSmemHead = (5 * kC * kC + kC * kSlabW + 8 * kC + 8) * sizeof(double);
 
 }  // namespace
 
 int64_t simple_project_workspace_bytes(int H) { return (int64_t)H * kWsHead * (int64_t)sizeof(double); }
 
 int simple_project(const float* gram, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv, const float* bv,
-                   double n_total, int H, float* vpartials, float* nvec, float* wbar, float* bbar, void* ws, cudaStream_t st) {
+                   double n_total, int H, float* vpartials, float* nvec, float* vbar_partials, void* ws, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     DIF_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
+    if (dev >= 64 || !attr_set[dev]) {
         DIF_CUDA_OK(cudaFuncSetAttribute(project_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemHead));
-        attr_set[dev] = true;
+        if (dev < 64) attr_set[dev] = true;
     }
-    ProjectArgs a{gram, Wq, bq, Wk, bk, Wv, bv, n_total, H, vpartials, reinterpret_cast<double*>(ws)};
+    ProjectArgs a{gram, Wq, bq, Wk, bk, Wv, bv, n_total, H, vpartials, vbar_partials, reinterpret_cast<double*>(ws)};
     project_head_kernel<<<dim3(kSlabs, H), kThreads, kSmemHead, st>>>(a);
     DIF_LAUNCH_OK();
-    FinishArgs f{reinterpret_cast<const double*>(ws), Wv, bv, n_total, H, vpartials, nvec, wbar, bbar};
+    FinishArgs f{reinterpret_cast<const double*>(ws), Wv, bv, n_total, H, vpartials, nvec};
     project_finish_kernel<<<1, kThreads, 0, st>>>(f);
     DIF_LAUNCH_OK();
     return DIF_OK;

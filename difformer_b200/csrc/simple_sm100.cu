@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     x[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (node < nrows) x[i][t] = lds128(stg_base + s * G::kStg + t * G::kStgT + u * 16);
+                    if (node < nrows && (t == 0 || BWD || !a.gram)) x[i][t] = lds128(stg_base + s * G::kStg + t * G::kStgT + u * 16);
                 }
             }
             if (!BWD && H > 1 && a.vbar != nullptr) {
@@ -129,10 +129,12 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                     split4(x[i][0], hi, lo);
                     sts64(ob + 0 * G::kOp + off, hi[0], hi[1]);
                     sts64(ob + 1 * G::kOp + off, lo[0], lo[1]);
-                    split4(x[i][1], hi, lo);
-                    sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
-                    sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
-                    const float4 kk = x[i][0], vv = x[i][1], qq = x[i][2];
+                    if (!a.gram) {
+                        split4(x[i][1], hi, lo);
+                        sts64(ob + 2 * G::kOp + off, hi[0], hi[1]);
+                        sts64(ob + 3 * G::kOp + off, lo[0], lo[1]);
+                    }
+                    const float4 kk = x[i][0], vv = a.gram ? x[i][0] : x[i][1], qq = a.gram ? x[i][0] : x[i][2];
                     zacc[0] += kk.x; zacc[1] += kk.y; zacc[2] += kk.z; zacc[3] += kk.w;
                     uacc[0] += vv.x; uacc[1] += vv.y; uacc[2] += vv.z; uacc[3] += vv.w;
                     ssk = fmaf(kk.x, kk.x, ssk); ssk = fmaf(kk.y, kk.y, ssk); ssk = fmaf(kk.z, kk.z, ssk); ssk = fmaf(kk.w, kk.w, ssk);
@@ -183,6 +185,11 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
                 if (it >= G::kNSG) mbar_wait(&sempty[s], ((it / G::kNSG) - 1) & 1);
                 const int64_t row = r0 + (int64_t)it * G::kNodes;
                 const uint32_t bytes = (uint32_t)(min((int64_t)G::kNodes, r1 - row) * G::kRowB);
+                if (!BWD && a.gram) {   // K = V = Q = the layer input: one copy; pass 2 reads it again
+                    mbar_expect_tx(&sfull[s], bytes);
+                    tma_load_1d_hint(stg_base + s * G::kStg + 0 * G::kStgT, a.k + row * G::kRowF, bytes, &sfull[s], pol_last);
+                    continue;
+                }
                 mbar_expect_tx(&sfull[s], 3 * bytes);
                 if (a.l2_hints) {     // K, V are dead after this pass; Q is read again by pass 2
                     tma_load_1d_hint(stg_base + s * G::kStg + 0 * G::kStgT, a.k + row * G::kRowF, bytes, &sfull[s], pol_first);
@@ -209,7 +216,8 @@ __global__ void __launch_bounds__(kThreadsT, 1) reduce_tma_kernel(const __grid_c
             for (int p = 0; p < G::kPairs; ++p) {
                 const uint32_t ho = p * 2 * G::kBlockTile;
                 const uint64_t khi = make_desc(sb + 0 * G::kOp + ho, lbo, sbo), klo = make_desc(sb + 1 * G::kOp + ho, lbo, sbo);
-                const uint64_t vhi = make_desc(sb + 2 * G::kOp + ho, lbo, sbo), vlo = make_desc(sb + 3 * G::kOp + ho, lbo, sbo);
+                const bool same = !BWD && a.gram;      // X^T X: the K operand on both sides
+                const uint64_t vhi = same ? khi : make_desc(sb + 2 * G::kOp + ho, lbo, sbo), vlo = same ? klo : make_desc(sb + 3 * G::kOp + ho, lbo, sbo);
                 umma(tmem + p * 128, khi, vhi, idesc, it > 0 ? 1u : 0u);
                 umma(tmem + p * 128, khi, vlo, idesc, 1u);
                 umma(tmem + p * 128, klo, vhi, idesc, 1u);
@@ -430,7 +438,9 @@ struct ApplyTcArgs {
     dif_epilogue_t ep;
 };
 
-template <int MODE, int H>
+// SHARED: the H heads of a tile use ONE A operand (q_hs == 0: the projected form, A = the layer input x): a stage is a tile, loaded and
+// split once, and the issuer runs the H head MMAs (N = 80 each, their own accumulator slots) off it.
+template <int MODE, int H, bool SHARED = false>
 __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_constant__ ApplyTcArgs p, const __grid_constant__ CUtensorMap out_map) {
     using G = Geo<H>;
     extern __shared__ uint8_t smem_raw[];
@@ -444,7 +454,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
     const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
-    const int nsc = my_tiles * H;                       // (tile, head) stages of this CTA
+    const int nsc = my_tiles * H;                       // (tile, head) units of this CTA
+    const int nst = SHARED ? my_tiles : nsc;            // A-operand stages
     auto tile_of = [&](int sc) -> int64_t { return blockIdx.x + (int64_t)(sc / H) * gridDim.x; };
 
     DIF_STAMP(p.dbg, 0);
@@ -520,13 +531,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         // ===== Q producers: stage = (tile, head): 128 rows x 256 B; task t -> row t>>3, chunk t&7.
         // Whole-stage double buffer: buf[0] = current, buf[1] = next (its loads are in flight while buf[0] is converted).
         float buf[2][4][8];
-        auto issue = [&](int sc, int j, float (&dst)[8]) {
-            if (sc >= nsc) return;
-            const int64_t tile = tile_of(sc);
+        auto issue = [&](int st, int j, float (&dst)[8]) {
+            if (st >= nst) return;
+            const int64_t tile = tile_of(SHARED ? st * H : st);
             const int t = tid + 256 * j;
             const int64_t row = tile * kTile2 + (t >> 3);
             if (row < p.N) {
-                if (p.q_hs != 0) ldg256_stream(p.q + row * p.q_ld + (sc % H) * p.q_hs + (t & 7) * 8, dst);
+                if (!SHARED && p.q_hs != 0) ldg256_stream(p.q + row * p.q_ld + (st % H) * p.q_hs + (t & 7) * 8, dst);
                 else ldg256_keep(p.q + row * p.q_ld + (t & 7) * 8, dst);         // shared by the heads: let it stay in L2
             } else {
 #pragma unroll
@@ -538,9 +549,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
         const uint32_t stage_base = smem_u32(stages);
-        for (int sc = 0; sc < nsc; ++sc) {
-            const int s = sc % kNS2;
-            if (sc >= kNS2) mbar_wait(&empty[s], ((sc / kNS2) - 1) & 1);
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % kNS2;
+            if (st >= kNS2) mbar_wait(&empty[s], ((st / kNS2) - 1) & 1);
             const uint32_t sb = stage_base + s * kStage2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -558,7 +569,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
-                issue(sc + 2, j, buf[1][j]);
+                issue(st + 2, j, buf[1][j]);
             }
         }
     } else if (warp < 12) {
@@ -572,16 +583,36 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         for (int sc = 0; sc < nsc; ++sc) {
             const int64_t tile = tile_of(sc);
             const int h = sc % H, slot = sc % kNAcc;
+            if (MODE == 1 && h == 0) {
+                // the row starts as the sum of its scaled addends (gcn term, x_0, residual): their loads are in flight while the
+                // tile's first MMA completes; the heads then accumulate on top (attn_scale folded into 1/den)
+                const int64_t row = tile * kTile2 + ew * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
+                if (row < p.N) {
+                    for (int a = 0; a < p.ep.n_add; ++a) {
+                        const float s = p.ep.add_scale[a];
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {       // 8 x 16-byte loads in flight per batch
+                            float4 x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = ldg4(p.ep.add[a] + row * kDim + 32 * half + 4 * j);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float* o = hs + 32 * half + 4 * j;
+                                o[0] = fmaf(s, x[j].x, o[0]); o[1] = fmaf(s, x[j].y, o[1]); o[2] = fmaf(s, x[j].z, o[2]); o[3] = fmaf(s, x[j].w, o[3]);
+                            }
+                        }
+                    }
+                }
+            }
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
             uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q . z
             tmem_ld_wait1(qz_bits);
-            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.nvec != nullptr ? __ldg(p.nvec + h) : p.n_total));   // one division per (row, head)
-            if (MODE == 1 && h == 0) {
-#pragma unroll
-                for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
-            }
+            float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.nvec != nullptr ? __ldg(p.nvec + h) : p.n_total));   // one division per (row, head)
+            if (MODE == 1) inv_den *= p.ep.attn_scale;
             if (MODE == 0 || h == H - 1) {        // staging is about to be rewritten: previous TMA reads must be done
                 if (lane == 0) tma_wait_read0();
                 __syncwarp();
@@ -615,21 +646,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             if (MODE == 1 && h == H - 1) {
                 const int64_t row = tile * kTile2 + ew * 32 + lane;
                 const bool ok = row < p.N;
-                // layer epilogue on the thread's whole output row (64 values in registers): head mean + addends, then --
-                // optionally -- the LayerNorm that follows the layer (difformer.py:202-203) and a ReLU
-#pragma unroll
-                for (int j = 0; j < kDim; j += 4) {
-                    float4 o = make_float4(hs[j] * p.ep.attn_scale, hs[j + 1] * p.ep.attn_scale, hs[j + 2] * p.ep.attn_scale,
-                                           hs[j + 3] * p.ep.attn_scale);
-                    for (int a = 0; a < p.ep.n_add; ++a) {
-                        if (ok) {
-                            const float4 x = ldg4(p.ep.add[a] + row * kDim + j);
-                            const float s = p.ep.add_scale[a];
-                            o.x = fmaf(s, x.x, o.x); o.y = fmaf(s, x.y, o.y); o.z = fmaf(s, x.z, o.z); o.w = fmaf(s, x.w, o.w);
-                        }
-                    }
-                    hs[j] = o.x; hs[j + 1] = o.y; hs[j + 2] = o.z; hs[j + 3] = o.w;
-                }
+                // layer epilogue on the thread's whole output row (64 values in registers: head mean + addends), then --
+                // optionally -- the gcn gather, the LayerNorm that follows the layer (difformer.py:202-203) and a ReLU
                 if (p.ep.gcn_rowptr != nullptr && ok) {
                     // gcn_conv term (difformer.py:63-79) gathered here: this thread's row of the normalised adjacency times the
                     // head-meaned values.  The source rows (256 B each) come from L2; two slots (32 x 16-byte loads) in flight.
@@ -639,18 +657,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                         const float w0 = __ldg(p.ep.gcn_val + s_) * p.ep.gcn_scale, w1 = __ldg(p.ep.gcn_val + s_ + 1) * p.ep.gcn_scale;
                         const float* x0 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_) * kDim;
                         const float* x1 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_ + 1) * kDim;
-                        float4 a[16], b[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { a[j] = ldg4(x0 + 4 * j); b[j] = ldg4(x1 + 4 * j); }
+                        for (int half = 0; half < 2; ++half) {
+                            float4 a[8], b[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            hs[4 * j] = fmaf(w0, a[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(w0, a[j].y, hs[4 * j + 1]);
-                            hs[4 * j + 2] = fmaf(w0, a[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w0, a[j].w, hs[4 * j + 3]);
-                        }
+                            for (int j = 0; j < 8; ++j) { a[j] = ldg4(x0 + 32 * half + 4 * j); b[j] = ldg4(x1 + 32 * half + 4 * j); }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            hs[4 * j] = fmaf(w1, b[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(w1, b[j].y, hs[4 * j + 1]);
-                            hs[4 * j + 2] = fmaf(w1, b[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w1, b[j].w, hs[4 * j + 3]);
+                            for (int j = 0; j < 8; ++j) {
+                                float* o = hs + 32 * half + 4 * j;
+                                o[0] = fmaf(w0, a[j].x, o[0]); o[1] = fmaf(w0, a[j].y, o[1]); o[2] = fmaf(w0, a[j].z, o[2]); o[3] = fmaf(w0, a[j].w, o[3]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float* o = hs + 32 * half + 4 * j;
+                                o[0] = fmaf(w1, b[j].x, o[0]); o[1] = fmaf(w1, b[j].y, o[1]); o[2] = fmaf(w1, b[j].z, o[2]); o[3] = fmaf(w1, b[j].w, o[3]);
+                            }
                         }
                     }
                     if (s_ < end) {
@@ -712,29 +733,35 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
         const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
         if (p.prepared != nullptr) mbar_wait(&bbar, 0);
-        for (int sc = 0; sc < nsc; ++sc) {
-            const int s = sc % kNS2, slot = sc % kNAcc, h = sc % H;
-            if (p.pf_tiles > 0 && h == 0 && sc + H * p.pf_tiles < nsc) {
-                const int64_t prow = tile_of(sc + H * p.pf_tiles) * kTile2;
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % kNS2;
+            const int sc0 = SHARED ? st * H : st;
+            if (p.pf_tiles > 0 && sc0 % H == 0 && sc0 + H * p.pf_tiles < nsc) {
+                const int64_t prow = tile_of(sc0 + H * p.pf_tiles) * kTile2;
                 const int64_t nrows = min((int64_t)kTile2, p.N - prow);
                 for (int64_t r = 0; r < nrows; r += 16)
                     prefetch_l2(p.q + (prow + r) * p.q_ld, (uint32_t)(min((int64_t)16, nrows - r) * p.q_ld * 4));
             }
-            if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
-            mbar_wait(&full[s], (sc / kNS2) & 1);
-            tc_fence_after();
-            const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
-            const uint32_t d = tmem + slot * kAccCols;
+            bool have_a = false;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
-                const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
-                umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
-                umma(d, qlo, bhi, idesc, 1u);
-                umma(d, qhi, blo, idesc, 1u);
+            for (int hh = 0; hh < (SHARED ? H : 1); ++hh) {
+                const int sc = sc0 + hh, slot = sc % kNAcc, h = sc % H;
+                if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+                if (!have_a) { mbar_wait(&full[s], (st / kNS2) & 1); have_a = true; }
+                tc_fence_after();
+                const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
+                const uint32_t d = tmem + slot * kAccCols;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                    const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                    umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
+                    umma(d, qlo, bhi, idesc, 1u);
+                    umma(d, qhi, blo, idesc, 1u);
+                }
+                if (hh == (SHARED ? H : 1) - 1) umma_commit(&empty[s]);
+                umma_commit(&tfull[slot]);
             }
-            umma_commit(&empty[s]);
-            umma_commit(&tfull[slot]);
         }
     }
     __syncwarp();
@@ -1453,6 +1480,7 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     a.epoch = epoch_src.fetch_add(0x632BE59BD9B4E019ull) | 1ull;
     a.partials = partials; a.prepared = (uint8_t*)prepared;
     a.vbar = vbar;
+    a.gram = (H == 1 && q == k && k == v) ? 1 : 0;
     static const int hints = env_int("DIF_TC_P1_HINTS", 1);
     a.l2_hints = hints;
     a.sh.world = 1;
@@ -1470,14 +1498,14 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     return DIF_OK;
 }
 
-template <int MODE, int H>
+template <int MODE, int H, bool SHARED = false>
 static int launch_apply(const ApplyTcArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
+        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, H, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
         attr_set = true;
     }
-    apply_tc_kernel<MODE, H><<<grid, kThreadsTC, smem2_bytes<H>(), st>>>(a, map);
+    apply_tc_kernel<MODE, H, SHARED><<<grid, kThreadsTC, smem2_bytes<H>(), st>>>(a, map);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }
@@ -1511,7 +1539,11 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     if (rc) return rc;
 #define DIF_P2(MODE)                                                                                                  \
     (H == 4 ? launch_apply<MODE, 4>(a, map, grid, st) : H == 2 ? launch_apply<MODE, 2>(a, map, grid, st) : launch_apply<MODE, 1>(a, map, grid, st))
-    rc = a.ep.mode == 0 ? DIF_P2(0) : DIF_P2(1);
+#define DIF_P2S(MODE) (H == 4 ? launch_apply<MODE, 4, true>(a, map, grid, st) : launch_apply<MODE, 2, true>(a, map, grid, st))
+    static const int share = env_int("DIF_TC_P2_SHARED_A", 1);
+    if (a.q_hs == 0 && H > 1 && share) rc = a.ep.mode == 0 ? DIF_P2S(0) : DIF_P2S(1);   // one A operand for the H heads of a tile
+    else rc = a.ep.mode == 0 ? DIF_P2(0) : DIF_P2(1);
+#undef DIF_P2S
 #undef DIF_P2
     if (rc) return rc;
     dbg_report("apply_tc", a.dbg, grid);

@@ -77,6 +77,7 @@ struct ReduceArgs1 {
     float n_total;
     float* rowscal;               // [N][H][2] = (1/den, dden) per (node, head), consumed by the dq kernel
     float* vbar;                  // fwd, optional: mean over heads of V, [N][64] (feeds the gcn SpMM of the fused layer)
+    int gram;                     // fwd, H = 1, q == k == v (Gram matrix of the layer input, projected.py): one stream instead of three
 };
 
 

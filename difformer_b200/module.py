@@ -39,11 +39,11 @@ def _conv_forward_projected(conv, x, edge_index, edge_weight, x_0, residual, lay
     alpha = 1.0 if residual is None else float(residual[0])
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
-    vpart, nvec, wbar, bbar = projected.projected_operands(projected.gram(x), float(N), conv)
+    vpart, nvec, vbar_part = projected.projected_operands(projected.gram(x), float(N), conv)
     addends = []
     if conv.use_graph:
         csr = ops.graph_csr(edge_index, edge_weight, N)
-        vbar = torch.addmm(bbar, x, wbar.t()) if conv.use_weight else x            # mean_h V [N, 64] (commutes with the SpMM)
+        vbar = projected.head_mean_values(x, vbar_part, nvec, H) if conv.use_weight else x     # mean_h V [N, 64] (commutes with the SpMM)
         gmean = ops.spmm(csr, vbar.view(N, 1, projected.HID)).view(N, projected.HID)
         addends.append((gmean, alpha * w_gcn))
     if getattr(conv, "use_source", False):

@@ -50,23 +50,29 @@ def _w(t: torch.Tensor) -> torch.Tensor:
 
 def projected_operands(gram_partials: torch.Tensor, n_total: float, conv):
     """The pass-2 operands of every head from the Gram partials and the layer's weights (dif_simple_project: fp64 arithmetic, two small
-    launches): (vpartials fp32 in the partials layout of (H, Hv = H, 64, 64), nvec fp32 [H], weight [64, 64] and bias [64] of mean_h V).
+    launches): (vpartials fp32 in the partials layout of (H, Hv = H, 64, 64), nvec fp32 [H + 1], vbar_partials fp32 [4226]: the one-head
+    pass-2 problem whose solution is mean_h V, with nvec[H:] as its denominator constant).
     The same algebra in torch fp64, which the tests check this against: oracle.difformer_oracle.projected_operands."""
     H = conv.num_heads
     dev = gram_partials.device
     Wq, bq, Wk, bk = _w(conv.Wq.weight), _w(conv.Wq.bias), _w(conv.Wk.weight), _w(conv.Wk.bias)
     Wv, bv = (_w(conv.Wv.weight), _w(conv.Wv.bias)) if conv.use_weight else (None, None)
-    vpart = torch.empty(H * HID * HID + 2 * H * HID + 2, dtype=torch.float32, device=dev)
-    nvec = torch.empty(H, dtype=torch.float32, device=dev)
-    wbar = torch.empty(HID, HID, dtype=torch.float32, device=dev)
-    bbar = torch.empty(HID, dtype=torch.float32, device=dev)
+    nv = H * HID * HID + 2 * H * HID + 2
+    nb = HID * HID + 2 * HID + 2
+    buf = torch.empty(nv + nb + (-(nv + nb)) % 8 + H + 1, dtype=torch.float32, device=dev)      # one allocation for the three outputs
+    vpart, vbar_part, nvec = buf[:nv], buf[nv:nv + nb], buf[buf.numel() - (H + 1):]
     ws = ops.workspace(dev, lib.dif_simple_project_workspace_bytes(H))
     with torch.cuda.device(dev):
         check(lib.dif_simple_project(gram_partials.data_ptr(), Wq.data_ptr(), bq.data_ptr(), Wk.data_ptr(), bk.data_ptr(),
                                      None if Wv is None else Wv.data_ptr(), None if bv is None else bv.data_ptr(), float(n_total), H,
-                                     vpart.data_ptr(), nvec.data_ptr(), wbar.data_ptr(), bbar.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     vpart.data_ptr(), nvec.data_ptr(), vbar_part.data_ptr(), ws.data_ptr(), ws.numel(),
                                      ops._stream(gram_partials)), "dif_simple_project")
-    return vpart, nvec, wbar, bbar
+    return vpart, nvec, vbar_part
+
+
+def head_mean_values(x: torch.Tensor, vbar_part: torch.Tensor, nvec: torch.Tensor, H: int) -> torch.Tensor:
+    """mean_h V = x wbar^T + bbar [N, 64] through the pass-2 kernel (one head, A = x): the input of the gcn term."""
+    return apply(x, vbar_part, nvec[H:], 1).view(-1, HID)
 
 
 def apply(x: torch.Tensor, vpart: torch.Tensor, nvec: torch.Tensor, H: int, epilogue: Optional[ops.Epilogue] = None, keep=()) -> torch.Tensor:
@@ -85,5 +91,5 @@ def apply(x: torch.Tensor, vpart: torch.Tensor, nvec: torch.Tensor, H: int, epil
 def attention(x: torch.Tensor, conv, n_total: Optional[float] = None) -> torch.Tensor:
     """full_attention_conv(Wq x, Wk x, Wv x, 'simple') -> [N, H, 64] without forming Q, K, V (no autograd)."""
     x = x.contiguous()
-    vpart, nvec, _, _ = projected_operands(gram(x), float(x.shape[0] if n_total is None else n_total), conv)
+    vpart, nvec, _ = projected_operands(gram(x), float(x.shape[0] if n_total is None else n_total), conv)
     return apply(x, vpart, nvec, conv.num_heads)

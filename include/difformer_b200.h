@@ -150,13 +150,15 @@ DIF_API int dif_simple_apply_projected(const float* x, int64_t ldx, const float*
  * difformer.py:115-120 together with pass 1 of full_attention_conv :18-39).  `gram_partials` = the output of dif_simple_reduce(x, x, x,
  * H = Hv = 1, M = D = 64): [X^T X | X^T 1 | X^T 1 | sum x^2 | sum x^2] (all-reduced over row shards when x is sharded; n_total = global
  * row count).  Wq/Wk/Wv: nn.Linear weights [H*64, 64] row-major with biases [H*64] (device, fp32); Wv = bv = NULL means V = x
- * (use_weight=False, difformer.py:120).  Writes vpartials [H*4096 + 2*H*64 + 2] and n_total_vec [H] (see dif_simple_apply_projected),
- * and the head mean of the value projection, wbar [64,64] / bbar [64]: mean_h V = x wbar^T + bbar, the input of the gcn term.
+ * (use_weight=False, difformer.py:120).  Writes vpartials [H*4096 + 2*H*64 + 2] and n_total_vec [H + 1] (see
+ * dif_simple_apply_projected), and vbar_partials [4096 + 2*64 + 2]: the head mean of the value projection posed as a one-head pass-2
+ * problem -- dif_simple_apply_projected(x, ldx, vbar_partials, n_total_vec + H, N, 1, vbar, NULL) writes mean_h V = x wbar^T + bbar,
+ * the input of the gcn term (difformer.py:139; the head mean commutes with the SpMM).
  * fp64 arithmetic, deterministic, two small launches.  workspace: dif_simple_project_workspace_bytes(H), 8-byte aligned. */
 DIF_API int64_t dif_simple_project_workspace_bytes(int H);
 DIF_API int dif_simple_project(const float* gram_partials, const float* Wq, const float* bq, const float* Wk, const float* bk,
                        const float* Wv, const float* bv, double n_total, int H, float* vpartials, float* n_total_vec,
-                       float* wbar, float* bbar, void* workspace, int64_t workspace_bytes, void* stream);
+                       float* vbar_partials, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Backward of the 'simple' path (derived analytically; the reference uses autograd).
  *   bwd_partials = [ dS : H*M*D | dz : H*M | du : H*D | t_q | t_k ]  (raw, additive over shards;

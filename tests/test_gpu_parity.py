@@ -787,8 +787,13 @@ def test_projection_folded_into_the_propagation(h, use_weight):
         ops_o = O.projected_operands(gp[:4096].view(64, 64).cpu(), gp[4096:4160].cpu(), float(n), cw(conv.Wq.weight), cw(conv.Wq.bias),
                                      cw(conv.Wk.weight), cw(conv.Wk.bias), cw(conv.Wv.weight if use_weight else None),
                                      cw(conv.Wv.bias if use_weight else None), h)
-        for name, a_, b_ in zip(("vpartials", "nvec", "wbar", "bbar"), ops_k, ops_o):
-            assert O.rel_err(a_, b_) < 1e-6, name
+        vpart_k, nvec_k, vbar_k = ops_k
+        vpart_o, nvec_o, wbar_o, bbar_o = ops_o
+        assert O.rel_err(vpart_k, vpart_o) < 1e-6 and O.rel_err(nvec_k[:h], nvec_o) < 1e-6 and float(nvec_k[h]) == 1.0
+        vbar_o = torch.cat([wbar_o.t().reshape(-1), torch.zeros(64, dtype=torch.float64), bbar_o, torch.ones(2, dtype=torch.float64)])
+        assert O.rel_err(vbar_k, vbar_o) < 1e-6
+        # mean_h V through the pass-2 kernel (one head, A = x) against the explicit projection
+        assert O.rel_err(projected.head_mean_values(x, vbar_k, nvec_k, h), x.double().cpu() @ wbar_o.t() + bbar_o) < 1e-5
         assert O.rel_err(gp[:4096].view(64, 64), x.double().t() @ x.double()) < 1e-5
         q = conv.Wq(x).reshape(n, h, 64)
         k = conv.Wk(x).reshape(n, h, 64)
