@@ -46,15 +46,19 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// Shared-memory matrices are fp64 (widened once on the way in: an F2F per FMA would cost more than the DFMA) with a leading dimension of
+// 66 doubles, and every product reads BOTH operands k-major (row k = one contraction index): per k a thread loads a few consecutive
+// doubles of each operand (LDS.128, broadcast across the warp's other threads) and does a register-tiled outer product.
+constexpr int kLd = kC + 2;
+
 __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // everything is widened to fp64 once on the way in: an F2F per FMA would run at a quarter of the DFMA rate
-    double* sG = reinterpret_cast<double*>(smem_raw);         // [64][64]
-    double* sWk = sG + kC * kC;
-    double* sWq = sWk + kC * kC;
-    double* sWv = sWq + kC * kC;
-    double* sT = sWv + kC * kC;                               // [64][64]  Wk_h G
-    double* sS = sT + kC * kC;                                // [64][kSlabW]
+    double* sG = reinterpret_cast<double*>(smem_raw);         // G[j][c]
+    double* sWkT = sG + kC * kLd;                             // Wk^T[j][m]
+    double* sWq = sWkT + kC * kLd;                            // Wq[m][c]
+    double* sWvT = sWq + kC * kLd;                            // Wv^T[c][d]
+    double* sTT = sWvT + kC * kLd;                            // T^T[c][m], T = Wk G
+    double* sS = sTT + kC * kLd;                              // S slab [m][kSlabW]
     double* sv = sS + kC * kSlabW;                            // s | ks | vs | qs | bk | bv | bq | z : 8 x 64
     double* red = sv + 8 * kC;                                // 8
     double *s_ = sv, *ks = sv + kC, *vs = sv + 2 * kC, *qs = sv + 3 * kC, *bk = sv + 4 * kC, *bv = sv + 5 * kC, *bq = sv + 6 * kC,
@@ -63,10 +67,11 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     const int t = threadIdx.x, slab = blockIdx.x, h = blockIdx.y;
     const int H = p.H;
     for (int i = t; i < kC * kC; i += kThreads) {
-        sG[i] = p.gram[i];
-        sWk[i] = p.Wk[(size_t)h * kC * kC + i];
-        sWq[i] = p.Wq[(size_t)h * kC * kC + i];
-        sWv[i] = p.Wv ? (double)p.Wv[(size_t)h * kC * kC + i] : ((i / kC) == (i % kC) ? 1.0 : 0.0);
+        const int r = i / kC, c = i % kC;
+        sG[r * kLd + c] = p.gram[i];
+        sWkT[c * kLd + r] = p.Wk[(size_t)h * kC * kC + i];
+        sWq[r * kLd + c] = p.Wq[(size_t)h * kC * kC + i];
+        sWvT[c * kLd + r] = p.Wv ? (double)p.Wv[(size_t)h * kC * kC + i] : (r == c ? 1.0 : 0.0);
     }
     if (t < kC) {
         s_[t] = p.gram[kC * kC + t];
@@ -77,77 +82,81 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     __syncthreads();
 
     if (t < 3 * kC) {                                         // ks = Wk s, vs = Wv s, qs = Wq s
-        const double* W = t < kC ? sWk : (t < 2 * kC ? sWv : sWq);
         const int r = t & (kC - 1);
         double acc = 0.0;
-        for (int j = 0; j < kC; ++j) acc += W[r * kC + ((j + r) & (kC - 1))] * s_[(j + r) & (kC - 1)];   // rotated: no bank conflicts
-        (t < kC ? ks : (t < 2 * kC ? vs : qs))[r] = acc;
+        if (t < kC) { for (int j = 0; j < kC; ++j) acc += sWkT[j * kLd + r] * s_[j]; ks[r] = acc; }
+        else if (t < 2 * kC) { for (int j = 0; j < kC; ++j) acc += sWvT[j * kLd + r] * s_[j]; vs[r] = acc; }
+        else { for (int j = 0; j < kC; ++j) acc += sWq[r * kLd + ((j + r) & (kC - 1))] * s_[(j + r) & (kC - 1)]; qs[r] = acc; }
     }
 
-    // T = Wk G: thread -> row m, 16 columns
+    // T = Wk G (64 x 64): thread -> rows 4 ty .. +3, columns {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx}
     double skp = 0.0;
     {
-        const int m = t >> 2, c0 = (t & 3) * 16;
-        double acc[16];
+        const int ty = t >> 4, tx = t & 15;
+        double acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        for (int j = 0; j < kC; ++j) {
-            const double w = sWk[m * kC + j];
-            const double2* g = reinterpret_cast<const double2*>(sG + j * kC + c0);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const double2 gv = g[i];
-                acc[2 * i + 0] += w * gv.x; acc[2 * i + 1] += w * gv.y;
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int k = 0; k < kC; ++k) {
+            const double2 a0 = *reinterpret_cast<const double2*>(sWkT + k * kLd + 4 * ty), a1 = *reinterpret_cast<const double2*>(sWkT + k * kLd + 4 * ty + 2);
+            const double2 b0 = *reinterpret_cast<const double2*>(sG + k * kLd + 2 * tx), b1 = *reinterpret_cast<const double2*>(sG + k * kLd + 32 + 2 * tx);
+            const double a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = 4 * ty + i, c = (j < 2 ? 2 * tx + j : 32 + 2 * tx + (j - 2));
+                sTT[c * kLd + m] = acc[i][j];
+                skp += acc[i][j] * sWkT[c * kLd + m];         // <T, Wk>
             }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            sT[m * kC + c0 + i] = acc[i];
-            skp += acc[i] * sWk[m * kC + c0 + i];
-        }
     }
-    // 16 rows of Wq G (this slab's share of sum q^2): thread -> row r, 4 columns
+    // this slab's 16 rows of P = Wq^T Wq (sum q^2 = <G, P>): thread -> rows slab*16 + 4 ty .. +3 (ty < 4), column tx (64)
     double sqp = 0.0;
     {
-        const int r = slab * kSlabW + (t >> 4), c0 = (t & 15) * 4;
+        const int ty = t >> 6, tx = t & 63, j0 = slab * kSlabW + 4 * ty;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int j = 0; j < kC; ++j) {
-            const double w = sWq[r * kC + j];
-            const double2 g0 = *reinterpret_cast<const double2*>(sG + j * kC + c0), g1 = *reinterpret_cast<const double2*>(sG + j * kC + c0 + 2);
-            acc[0] += w * g0.x; acc[1] += w * g0.y; acc[2] += w * g1.x; acc[3] += w * g1.y;
+        for (int k = 0; k < kC; ++k) {
+            const double2 a0 = *reinterpret_cast<const double2*>(sWq + k * kLd + j0), a1 = *reinterpret_cast<const double2*>(sWq + k * kLd + j0 + 2);
+            const double b = sWq[k * kLd + tx];
+            acc[0] += a0.x * b; acc[1] += a0.y * b; acc[2] += a1.x * b; acc[3] += a1.y * b;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sqp += acc[i] * sWq[r * kC + c0 + i];
+        for (int i = 0; i < 4; ++i) sqp += acc[i] * sG[(j0 + i) * kLd + tx];
     }
-    __syncthreads();                                          // sT, ks, vs, qs complete
+    __syncthreads();                                          // sTT, ks, vs, qs complete
     if (t < kC) z[t] = ks[t] + p.n * bk[t];
 
-    // S slab: S[m][d] = sum_c T[m][c] Wv[d][c] + ks[m] bv[d] + bk[m] vs[d] + n bk[m] bv[d]
+    // S slab: S[m][d] = sum_c T[m][c] Wv[d][c] + ks[m] bv[d] + bk[m] vs[d] + n bk[m] bv[d]; thread -> row m = t >> 2, 4 columns
     {
-        const int m = t >> 2, dl0 = (t & 3) * 4;
+        const int m = t >> 2, dl0 = (t & 3) * 4, d0 = slab * kSlabW + dl0;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int c = 0; c < kC; ++c) {
-            const int cc = (c + m) & (kC - 1);
-            const double tv = sT[m * kC + cc];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += tv * sWv[(slab * kSlabW + dl0 + i) * kC + cc];
+            const double tv = sTT[c * kLd + m];
+            const double2 b0 = *reinterpret_cast<const double2*>(sWvT + c * kLd + d0), b1 = *reinterpret_cast<const double2*>(sWvT + c * kLd + d0 + 2);
+            acc[0] += tv * b0.x; acc[1] += tv * b0.y; acc[2] += tv * b1.x; acc[3] += tv * b1.y;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int d = slab * kSlabW + dl0 + i;
+            const int d = d0 + i;
             sS[m * kSlabW + dl0 + i] = acc[i] + ks[m] * bv[d] + bk[m] * vs[d] + p.n * bk[m] * bv[d];
         }
     }
     __syncthreads();
 
-    // A slab: A[c][d] = sum_m Wq[m][c] S[m][d]
+    // A slab: A[c][d] = sum_m Wq[m][c] S[m][d]; thread -> row c = t >> 2, 4 columns
     {
         const int c = t >> 2, dl0 = (t & 3) * 4;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int m = 0; m < kC; ++m) {
-            const double w = sWq[m * kC + c];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += w * sS[m * kSlabW + dl0 + i];
+            const double w = sWq[m * kLd + c];
+            const double2 b0 = *reinterpret_cast<const double2*>(sS + m * kSlabW + dl0), b1 = *reinterpret_cast<const double2*>(sS + m * kSlabW + dl0 + 2);
+            acc[0] += w * b0.x; acc[1] += w * b0.y; acc[2] += w * b1.x; acc[3] += w * b1.y;
         }
         float4 o = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
         *reinterpret_cast<float4*>(p.vpartials + (size_t)h * kC * kC + c * kC + slab * kSlabW + dl0) = o;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     if (slab == 0 && t >= 64 && t < 64 + kC) {                // w[c] = Wq^T z
         const int c = t - 64;
         double acc = 0.0;
-        for (int m = 0; m < kC; ++m) acc += sWq[m * kC + c] * z[m];
+        for (int m = 0; m < kC; ++m) acc += sWq[m * kLd + c] * z[m];
         p.vpartials[(size_t)H * kC * kC + h * kC + c] = (float)acc;
     }
     if (h == 0) {
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) project_finish_kernel(FinishArgs p) 
     }
 }
 
-constexpr size_t kSmemHead = (5 * kC * kC + kC * kSlabW + 8 * kC + 8) * sizeof(double);
+constexpr size_t kSmemHead = (5 * kC * kLd + kC * kSlabW + 8 * kC + 8) * sizeof(double);
 
 }  // namespace
 

@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+            if (st == 0) DIF_STAMP(p.dbg, 2);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -726,8 +727,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                     tma_commit();
                 }
             }
+            if (sc == H - 1 && ew == 0 && lane == 0) DIF_STAMP_ANY(p.dbg, 6);
         }
+        if (ew == 0 && lane == 0) DIF_STAMP_ANY(p.dbg, 8);
         if (lane == 0) tma_wait_all0();      // stores must have landed before the CTA exits
+        if (ew == 0 && lane == 0) DIF_STAMP_ANY(p.dbg, 9);
     } else if (lane == 0) {
         // ===== MMA issuer: per (tile, head): 4 K-steps x (hi*hi + lo*hi + hi*lo), M=128 N=80 K=16
         const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
@@ -763,6 +767,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                 umma_commit(&tfull[slot]);
             }
         }
+        DIF_STAMP_ANY(p.dbg, 7);
     }
     __syncwarp();
     if (warp == 0) DIF_STAMP(p.dbg, 3);

@@ -36,6 +36,12 @@ __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %
         }                                                                           \
     } while (0)
 
+// the same from any single thread the caller elects (role warps other than warp 0)
+#define DIF_STAMP_ANY(buf, slot)                                                    \
+    do {                                                                            \
+        if ((buf) != nullptr) (buf)[blockIdx.x * kDbgSlots + (slot)] = gtime();     \
+    } while (0)
+
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
