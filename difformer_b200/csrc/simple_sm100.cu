@@ -778,6 +778,287 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// Pass 2 with the layer epilogue (mode 1: head mean, gcn / x_0 / residual addends, LayerNorm, ReLU; difformer.py:129-140, 200-203),
+// 17 warps.  Same producers, stage ring, B operands and MMA issue as apply_tc_kernel; what differs is the epilogue, which was the
+// limiter of apply_tc_kernel<1,...> (one thread per output row: ~1400 dependent instructions per tile on one warp per scheduler,
+// 8.5 us per tile): here TWO threads share a row -- warps 8-11 take columns 0-31 of every head, warps 12-15 columns 32-63 (a warp
+// may read the TMEM lanes 32 (warp % 4) .. +31, so the pair (w, w + 4) sees the same rows) -- and the LayerNorm statistics cross the
+// pair through shared memory and a 64-thread named barrier.  Half the work per thread, two epilogue warps per scheduler.
+// ------------------------------------------------------------------------------------------
+constexpr int kLayerWarps = 17, kLayerThreads = kLayerWarps * 32;
+
+template <int H, bool SHARED>
+__global__ void __launch_bounds__(kLayerThreads, 1) layer_tc_kernel(const __grid_constant__ ApplyTcArgs p, const __grid_constant__ CUtensorMap out_map) {
+    using G = Geo<H>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* Bop = base;                                             // [h][hi|lo][80 rows][128 B]
+    uint8_t* stages = base + G::kBBytes;
+    uint8_t* ostage = stages + kNS2 * kStage2;                       // [8 warps][32 rows][128 B], 1024-aligned
+    float* us = reinterpret_cast<float*>(ostage + kOutStage);        // [H][64]
+    __shared__ uint64_t full[kNS2], empty[kNS2], tfull[kNAcc], tempty[kNAcc], bbar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float ln_sum[2][kTile2], ln_var[2][kTile2];           // LayerNorm partial statistics of the two column halves
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (p.N + kTile2 - 1) / kTile2;
+    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const int nsc = my_tiles * H;                       // (tile, head) units of this CTA
+    const int nst = SHARED ? my_tiles : nsc;            // A-operand stages
+    auto tile_of = [&](int sc) -> int64_t { return blockIdx.x + (int64_t)(sc / H) * gridDim.x; };
+
+    DIF_STAMP(p.dbg, 0);
+    if (tid == 0) {
+        for (int s = 0; s < kNS2; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kNAcc; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        mbar_init(&bbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.prepared != nullptr) {
+            mbar_expect_tx(&bbar, (uint32_t)G::kBBytes);
+            for (int i = 0; i < H * 2; ++i)
+                tma_load_1d(smem_u32(Bop) + i * kBOp, p.prepared + (size_t)i * kBOp, (uint32_t)kBOp, &bbar);
+        }
+    }
+    if (warp == 16) tmem_alloc(&tmem_slot, 512);
+
+    // ---- B operands (see apply_tc_kernel): row n < 64: S[h][:, n]; row 64: z[h]; rows 65..79: 0   (K-major SW128, hi/lo split)
+    const float c = 1.f / (sqrtf(p.partials[G::offSq]) * sqrtf(p.partials[G::offSq + 1]));
+    const float cscale = p.prepared != nullptr ? c : 1.f;
+    if (p.prepared == nullptr) {
+        constexpr int kTasks = H * 8 * kBN, kPer = (kTasks + kLayerThreads - 1) / kLayerThreads;
+        float x[kPer][8];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int task = tid + u * kLayerThreads;
+            const int n = task % kBN, hc = task / kBN, ch = hc & 7, h = hc >> 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = ch * 8 + i;
+                x[u][i] = 0.f;
+                if (task < kTasks) {
+                    if (n < kDim) x[u][i] = __ldg(p.partials + ((int64_t)h * kDim + m) * kDim + n);
+                    else if (n == kDim) x[u][i] = __ldg(p.partials + G::offZ + h * kDim + m);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int task = tid + u * kLayerThreads;
+            if (task < kTasks) {
+                const int n = task % kBN, hc = task / kBN, ch = hc & 7, h = hc >> 3;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[u][i] *= c;
+                uint4 hi, lo;
+                split8(x[u], hi, lo);
+                const uint32_t off = (uint32_t)(h * 2 * kBOp) + sw128(n, ch);
+                sts128(smem_u32(Bop) + off, hi);
+                sts128(smem_u32(Bop) + kBOp + off, lo);
+            }
+        }
+    }
+    for (int i = tid; i < H * kDim; i += kLayerThreads) us[i] = p.partials[G::offU + i];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    DIF_STAMP(p.dbg, 1);
+
+    if (warp < 8) {
+        // ===== A producers (see apply_tc_kernel): stage = tile (SHARED) or (tile, head)
+        float buf[2][4][8];
+        auto issue = [&](int st, int j, float (&dst)[8]) {
+            if (st >= nst) return;
+            const int64_t tile = tile_of(SHARED ? st * H : st);
+            const int t = tid + 256 * j;
+            const int64_t row = tile * kTile2 + (t >> 3);
+            if (row < p.N) {
+                if (!SHARED && p.q_hs != 0) ldg256_stream(p.q + row * p.q_ld + (st % H) * p.q_hs + (t & 7) * 8, dst);
+                else ldg256_keep(p.q + row * p.q_ld + (t & 7) * 8, dst);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = 0.f;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(0, j, buf[0][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) issue(1, j, buf[1][j]);
+        const uint32_t stage_base = smem_u32(stages);
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % kNS2;
+            if (st >= kNS2) mbar_wait(&empty[s], ((st / kNS2) - 1) & 1);
+            const uint32_t sb = stage_base + s * kStage2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = tid + 256 * j;
+                uint4 hi, lo;
+                split8(buf[0][j], hi, lo);
+                const uint32_t off = sw128(t >> 3, t & 7);
+                sts128(sb + off, hi);
+                sts128(sb + kQOp + off, lo);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (st == 0) DIF_STAMP(p.dbg, 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) buf[0][j][i] = buf[1][j][i];
+                issue(st + 2, j, buf[1][j]);
+            }
+        }
+    } else if (warp < 16) {
+        // ===== epilogue: thread = (row, column half).  TMEM lane = 32 * quad + lane, columns 32 * half .. +31 of each head
+        const int ew = warp - 8, quad = ew & 3, half = ew >> 2;
+        const uint32_t obox = smem_u32(ostage) + ew * kOutBox;
+        const uint64_t pol = policy_evict_first();
+        const int lrow = quad * 32 + lane;              // row inside the tile
+        float hs[32];
+        for (int sc = 0; sc < nsc; ++sc) {
+            const int64_t tile = tile_of(sc);
+            const int h = sc % H, slot = sc % kNAcc;
+            const int64_t row = tile * kTile2 + lrow;
+            const bool ok = row < p.N;
+            if (h == 0) {
+                // the half row starts as the sum of its scaled addends: their loads are in flight while the tile's first MMA completes
+#pragma unroll
+                for (int i = 0; i < 32; ++i) hs[i] = 0.f;
+                if (ok) {
+                    for (int a = 0; a < p.ep.n_add; ++a) {
+                        const float s = p.ep.add_scale[a];
+                        float4 x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = ldg4(p.ep.add[a] + row * kDim + 32 * half + 4 * j);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            hs[4 * j] = fmaf(s, x[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(s, x[j].y, hs[4 * j + 1]);
+                            hs[4 * j + 2] = fmaf(s, x[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(s, x[j].w, hs[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + slot * kAccCols;
+            uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q . z
+            uint32_t r[32];
+            tmem_ld32(taddr + 32 * half, r);
+            tmem_ld_wait32(r);
+            tmem_ld_wait1(qz_bits);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[slot]);             // everything of this slot is in registers
+            const float inv_den = p.ep.attn_scale / fmaf(__uint_as_float(qz_bits), cscale, p.nvec != nullptr ? __ldg(p.nvec + h) : p.n_total);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 u4 = *reinterpret_cast<const float4*>(us + h * kDim + 32 * half + j);
+                hs[j] = fmaf(fmaf(__uint_as_float(r[j]), cscale, u4.x), inv_den, hs[j]);
+                hs[j + 1] = fmaf(fmaf(__uint_as_float(r[j + 1]), cscale, u4.y), inv_den, hs[j + 1]);
+                hs[j + 2] = fmaf(fmaf(__uint_as_float(r[j + 2]), cscale, u4.z), inv_den, hs[j + 2]);
+                hs[j + 3] = fmaf(fmaf(__uint_as_float(r[j + 3]), cscale, u4.w), inv_den, hs[j + 3]);
+            }
+            if (h != H - 1) continue;
+            if (p.ep.gcn_rowptr != nullptr && ok) {
+                // gcn_conv term gathered here (optional, see apply_tc_kernel): this thread's half of the neighbour rows
+                const int beg = __ldg(p.ep.gcn_rowptr + row), end = __ldg(p.ep.gcn_rowptr + row + 1);
+                for (int s_ = beg; s_ < end; ++s_) {
+                    const float w0 = __ldg(p.ep.gcn_val + s_) * p.ep.gcn_scale;
+                    const float* x0 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_) * kDim + 32 * half;
+                    float4 x[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = ldg4(x0 + 4 * j);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hs[4 * j] = fmaf(w0, x[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(w0, x[j].y, hs[4 * j + 1]);
+                        hs[4 * j + 2] = fmaf(w0, x[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w0, x[j].w, hs[4 * j + 3]);
+                    }
+                }
+            }
+            if (p.ep.ln_weight != nullptr) {
+                // LayerNorm over the 64 columns of the row = this thread's 32 + the partner's 32 (warp +-4, same lane): two-pass
+                // statistics, each exchanged through shared memory under a 64-thread named barrier (id 1 + quad)
+                float s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s1 += hs[j];
+                ln_sum[half][lrow] = s1;
+                bar_sync_named(1 + quad, 64);
+                const float mean = (ln_sum[0][lrow] + ln_sum[1][lrow]) * (1.f / kDim);
+                float s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float d_ = hs[j] - mean; s2 = fmaf(d_, d_, s2); }
+                ln_var[half][lrow] = s2;
+                bar_sync_named(1 + quad, 64);
+                const float rstd = rsqrtf((ln_var[0][lrow] + ln_var[1][lrow]) * (1.f / kDim) + p.ep.ln_eps);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 w4 = ldg4(p.ep.ln_weight + 32 * half + j), b4 = ldg4(p.ep.ln_bias + 32 * half + j);
+                    hs[j] = fmaf((hs[j] - mean) * rstd, w4.x, b4.x); hs[j + 1] = fmaf((hs[j + 1] - mean) * rstd, w4.y, b4.y);
+                    hs[j + 2] = fmaf((hs[j + 2] - mean) * rstd, w4.z, b4.z); hs[j + 3] = fmaf((hs[j + 3] - mean) * rstd, w4.w, b4.w);
+                }
+            }
+            if (p.ep.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hs[j] = fmaxf(hs[j], 0.f);
+            }
+            if (lane == 0) tma_wait_read0();     // the previous tile's TMA store has read the staging box
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                sts128(obox + sw128(lane, j >> 2),
+                       make_uint4(__float_as_uint(hs[j]), __float_as_uint(hs[j + 1]), __float_as_uint(hs[j + 2]), __float_as_uint(hs[j + 3])));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int row0 = (int)(tile * kTile2) + quad * 32;
+                if (p.store_hint) tma_store_2d_hint(&out_map, obox, 32 * half, row0, pol);
+                else tma_store_2d(&out_map, obox, 32 * half, row0);
+                tma_commit();
+            }
+            if (sc == H - 1 && ew == 0 && lane == 0) DIF_STAMP_ANY(p.dbg, 6);
+        }
+        if (ew == 0 && lane == 0) DIF_STAMP_ANY(p.dbg, 8);
+        if (lane == 0) tma_wait_all0();      // stores must have landed before the CTA exits
+    } else if (lane == 0) {
+        // ===== MMA issuer (see apply_tc_kernel)
+        const uint32_t idesc = make_idesc(kTile2, kBN, 0, 0);
+        const uint32_t stage_base = smem_u32(stages), b_base = smem_u32(Bop);
+        if (p.prepared != nullptr) mbar_wait(&bbar, 0);
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % kNS2;
+            const int sc0 = SHARED ? st * H : st;
+            bool have_a = false;
+#pragma unroll
+            for (int hh = 0; hh < (SHARED ? H : 1); ++hh) {
+                const int sc = sc0 + hh, slot = sc % kNAcc, h = sc % H;
+                if (sc >= kNAcc) mbar_wait(&tempty[slot], ((sc / kNAcc) - 1) & 1);
+                if (!have_a) { mbar_wait(&full[s], (st / kNS2) & 1); have_a = true; }
+                tc_fence_after();
+                const uint32_t sb = stage_base + s * kStage2, bb = b_base + h * 2 * kBOp;
+                const uint32_t d = tmem + slot * kAccCols;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t qhi = make_desc(sb + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(sb + kQOp + ks * 32, kKmajLBO, kKmajSBO);
+                    const uint64_t bhi = make_desc(bb + ks * 32, kKmajLBO, kKmajSBO), blo = make_desc(bb + kBOp + ks * 32, kKmajLBO, kKmajSBO);
+                    umma(d, qhi, bhi, idesc, ks > 0 ? 1u : 0u);
+                    umma(d, qlo, bhi, idesc, 1u);
+                    umma(d, qhi, blo, idesc, 1u);
+                }
+                if (hh == (SHARED ? H : 1) - 1) umma_commit(&empty[s]);
+                umma_commit(&tfull[slot]);
+            }
+        }
+        DIF_STAMP_ANY(p.dbg, 7);
+    }
+    __syncwarp();
+    if (warp == 0) DIF_STAMP(p.dbg, 3);
+    tc_fence_before();
+    __syncthreads();
+    DIF_STAMP(p.dbg, 5);
+    if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // backward pass 2: three streaming contractions with the same skeleton as apply_tc_kernel
 //   KIND 0  dq = c (dnum S^T + dden z) - q t_q / sum q^2     A = g * (1/den)   B[n=m][k=d] = c S      rows from q
 //   KIND 1  dk = c (v dS^T + dz)       - k t_k / sum k^2     A = v             B[n=m][k=d] = c dS     rows from k
@@ -1515,6 +1796,18 @@ static int launch_apply(const ApplyTcArgs& a, const CUtensorMap& map, int grid, 
     return DIF_OK;
 }
 
+template <int H, bool SHARED>
+static int launch_layer(const ApplyTcArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(layer_tc_kernel<H, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
+        attr_set = true;
+    }
+    layer_tc_kernel<H, SHARED><<<grid, kLayerThreads, smem2_bytes<H>(), st>>>(a, map);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
 int simple_apply_tc(const float* q, const float* partials, const void* prepared, double n_total, int64_t N, int H, int Hv, int M, int D,
                     float* out, const dif_epilogue_t* ep, cudaStream_t st, int64_t q_ld, int q_hs, const float* nvec) {
     DIF_REQUIRE(simple_tc_supported(N, H, Hv, M, D), DIF_EUNSUPPORTED, "tcgen05 path: unsupported shape");
@@ -1545,8 +1838,12 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
 #define DIF_P2(MODE)                                                                                                  \
     (H == 4 ? launch_apply<MODE, 4>(a, map, grid, st) : H == 2 ? launch_apply<MODE, 2>(a, map, grid, st) : launch_apply<MODE, 1>(a, map, grid, st))
 #define DIF_P2S(MODE) (H == 4 ? launch_apply<MODE, 4, true>(a, map, grid, st) : launch_apply<MODE, 2, true>(a, map, grid, st))
-    static const int share = env_int("DIF_TC_P2_SHARED_A", 1);
-    if (a.q_hs == 0 && H > 1 && share) rc = a.ep.mode == 0 ? DIF_P2S(0) : DIF_P2S(1);   // one A operand for the H heads of a tile
+    static const int share = env_int("DIF_TC_P2_SHARED_A", 1), layer17 = env_int("DIF_TC_LAYER_KERNEL", 1);
+    const bool shared_a = a.q_hs == 0 && H > 1 && share;
+    if (a.ep.mode == 1 && layer17) {         // two threads per output row (layer_tc_kernel); DIF_TC_LAYER_KERNEL=0: apply_tc_kernel<1,...>
+        rc = shared_a ? (H == 4 ? launch_layer<4, true>(a, map, grid, st) : launch_layer<2, true>(a, map, grid, st))
+                      : (H == 4 ? launch_layer<4, false>(a, map, grid, st) : H == 2 ? launch_layer<2, false>(a, map, grid, st) : launch_layer<1, false>(a, map, grid, st));
+    } else if (shared_a) rc = a.ep.mode == 0 ? DIF_P2S(0) : DIF_P2S(1);   // one A operand for the H heads of a tile
     else rc = a.ep.mode == 0 ? DIF_P2(0) : DIF_P2(1);
 #undef DIF_P2S
 #undef DIF_P2
