@@ -915,28 +915,46 @@ __global__ void __launch_bounds__(kLayerThreads, 1) layer_tc_kernel(const __grid
         const uint64_t pol = policy_evict_first();
         const int lrow = quad * 32 + lane;              // row inside the tile
         float hs[32];
+        int inflight = -1, pending = 0;                 // addend whose copy is in flight / next addend to fetch
+        int64_t row = 0;
+        auto cp_issue = [&](int a) {
+            const float* src = p.ep.add[a] + row * kDim + 32 * half;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp_async16(obox + sw128(lane, j), src + 4 * j);
+            cp_async_commit();
+        };
+        auto cp_fold = [&]() {                          // wait for the addend in flight, add it, start the next one
+            cp_async_wait_all();
+            const float s = p.ep.add_scale[inflight];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 x = lds128(obox + sw128(lane, j));
+                hs[4 * j] = fmaf(s, x.x, hs[4 * j]); hs[4 * j + 1] = fmaf(s, x.y, hs[4 * j + 1]);
+                hs[4 * j + 2] = fmaf(s, x.z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(s, x.w, hs[4 * j + 3]);
+            }
+            inflight = -1;
+            if (pending < p.ep.n_add) { cp_issue(pending); inflight = pending++; }
+        };
         for (int sc = 0; sc < nsc; ++sc) {
             const int64_t tile = tile_of(sc);
             const int h = sc % H, slot = sc % kNAcc;
-            const int64_t row = tile * kTile2 + lrow;
+            row = tile * kTile2 + lrow;
             const bool ok = row < p.N;
             if (h == 0) {
-                // the half row starts as the sum of its scaled addends: their loads are in flight while the tile's first MMA completes
+                // Addends (gcn term, x_0, residual): this thread's 128-byte piece of each goes global -> its row of the warp's staging
+                // box by cp.async (no registers in flight) and is folded in after the next head's arithmetic, one addend behind one
+                // head; the rows of the CTA's next tile are pulled into L2 meanwhile.  The box is free once the previous tile's TMA
+                // store has read it.
 #pragma unroll
                 for (int i = 0; i < 32; ++i) hs[i] = 0.f;
-                if (ok) {
-                    for (int a = 0; a < p.ep.n_add; ++a) {
-                        const float s = p.ep.add_scale[a];
-                        float4 x[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) x[j] = ldg4(p.ep.add[a] + row * kDim + 32 * half + 4 * j);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            hs[4 * j] = fmaf(s, x[j].x, hs[4 * j]); hs[4 * j + 1] = fmaf(s, x[j].y, hs[4 * j + 1]);
-                            hs[4 * j + 2] = fmaf(s, x[j].z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(s, x[j].w, hs[4 * j + 3]);
-                        }
-                    }
-                }
+                if (lane == 0) tma_wait_read0();
+                __syncwarp();
+                inflight = -1;
+                pending = 0;
+                if (ok && p.ep.n_add > 0) { cp_issue(0); inflight = 0; pending = 1; }
+                const int64_t nrow = row + (int64_t)gridDim.x * kTile2;
+                if (nrow < p.N)
+                    for (int a = 0; a < p.ep.n_add; ++a) prefetch_l2_line(p.ep.add[a] + nrow * kDim + 32 * half);
             }
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
@@ -958,7 +976,9 @@ __global__ void __launch_bounds__(kLayerThreads, 1) layer_tc_kernel(const __grid
                 hs[j + 2] = fmaf(fmaf(__uint_as_float(r[j + 2]), cscale, u4.z), inv_den, hs[j + 2]);
                 hs[j + 3] = fmaf(fmaf(__uint_as_float(r[j + 3]), cscale, u4.w), inv_den, hs[j + 3]);
             }
+            if (inflight >= 0) cp_fold();
             if (h != H - 1) continue;
+            while (inflight >= 0) cp_fold();             // more addends than heads
             if (p.ep.gcn_rowptr != nullptr && ok) {
                 // gcn_conv term gathered here (optional, see apply_tc_kernel): this thread's half of the neighbour rows
                 const int beg = __ldg(p.ep.gcn_rowptr + row), end = __ldg(p.ep.gcn_rowptr + row + 1);
@@ -1001,8 +1021,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) layer_tc_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < 32; ++j) hs[j] = fmaxf(hs[j], 0.f);
             }
-            if (lane == 0) tma_wait_read0();     // the previous tile's TMA store has read the staging box
-            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 sts128(obox + sw128(lane, j >> 2),
