@@ -29,22 +29,33 @@ def _fusable(kernel, *tensors):
     return not any(t is not None and t.requires_grad for t in tensors)
 
 
-def _conv_forward_projected(conv, x, edge_index, edge_weight, x_0, residual, layer_norm):
+def _conv_forward_projected(conv, x, edge_index, edge_weight, x_0, residual, layer_norm, shard=None):
     """No-grad layer with the Wq / Wk / Wv projections folded into the propagation (projected.py): one pass over x for
     the Gram matrix, a few 64 x 64 products, one pass over x that writes the finished [N, 64] row (head mean, gcn term, x_0, residual
-    blend, LayerNorm in the epilogue).  Q, K and V are never formed."""
+    blend, LayerNorm in the epilogue).  Q, K and V are never formed.
+    Row-sharded (`shard`, sharded.shard_model): the Gram partials (4226 floats) are additive over the shards -- the same in-kernel NVLink
+    all-reduce as the explicit path, 16 x smaller -- the operand algebra is replicated, mean_h V rows are all-gathered for the SpMM over
+    this rank's target rows, pass 2 is local."""
     H = conv.num_heads
     x = ops._f32c(x)
     N = x.shape[0]
+    n_total = N if shard is None else shard.n_total
     alpha = 1.0 if residual is None else float(residual[0])
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
-    vpart, nvec, vbar_part = projected.projected_operands(projected.gram(x), float(N), conv)
+    vpart, nvec, vbar_part = projected.projected_operands(projected.gram(x, shard), float(n_total), conv)
     addends = []
     if conv.use_graph:
-        csr = ops.graph_csr(edge_index, edge_weight, N)
         vbar = projected.head_mean_values(x, vbar_part, nvec, H) if conv.use_weight else x     # mean_h V [N, 64] (commutes with the SpMM)
-        gmean = ops.spmm(csr, vbar.view(N, 1, projected.HID)).view(N, projected.HID)
+        if shard is None:
+            gmean = ops.spmm(ops.graph_csr(edge_index, edge_weight, N), vbar.view(N, 1, projected.HID)).view(N, projected.HID)
+        else:
+            from .sharded import gather_rows
+            if N != shard.end - shard.begin:
+                raise ValueError(f"row shard expects {shard.end - shard.begin} local rows, got {N}")
+            v_all = gather_rows(vbar, shard.pg, n_total)
+            gmean = ops.spmm(ops.graph_csr(edge_index, edge_weight, n_total), v_all.view(n_total, 1, projected.HID),
+                             rows=(shard.begin, shard.end)).view(N, projected.HID)
         addends.append((gmean, alpha * w_gcn))
     if getattr(conv, "use_source", False):
         addends.append((ops._f32c(x_0), alpha))
@@ -69,11 +80,13 @@ def _conv_forward(conv, query_input, source_input, edge_index, edge_weight, x_0,
     H, C = conv.num_heads, conv.out_channels
     segmented_ = n_nodes is not None
     shard_ = getattr(conv, "_row_shard", None)
-    if (ops._PROJECTION_FOLDING and not output_attn and not segmented_ and (shard_ is None or shard_.world < 2) and conv.kernel == "simple"
+    if shard_ is not None and shard_.world < 2:
+        shard_ = None
+    if (ops._PROJECTION_FOLDING and not output_attn and not segmented_ and conv.kernel == "simple"
             and _fusable("simple", query_input, source_input, x_0, None if residual is None else residual[1],
                          *[p_ for p_ in conv.parameters()])
             and projected.supported(conv, query_input, source_input)):
-        return _conv_forward_projected(conv, query_input, edge_index, edge_weight, x_0, residual, layer_norm)
+        return _conv_forward_projected(conv, query_input, edge_index, edge_weight, x_0, residual, layer_norm, shard_)
     query = conv.Wq(query_input).reshape(-1, H, C)
     key = conv.Wk(source_input).reshape(-1, H, C)
     if conv.use_weight:

@@ -36,11 +36,20 @@ def supported(conv, query_input: torch.Tensor, source_input: torch.Tensor) -> bo
             and ops._SIMPLE_IMPL != ops._lib.DIF_IMPL_GENERIC and conv.Wq.in_features == HID)
 
 
-def gram(x: torch.Tensor) -> torch.Tensor:
+def gram(x: torch.Tensor, shard=None) -> torch.Tensor:
     """One pass over x [N, 64] -> the partials of (H = Hv = 1, 64, 64): [X^T X | X^T 1 | X^T 1 | sum x^2 | sum x^2] -- pass 1 of 'simple'
-    with q = k = v = x (tcgen05 kernel, deterministic).  Additive over row shards."""
+    with q = k = v = x (tcgen05 kernel in Gram mode, deterministic).  Additive over row shards: with `shard` (sharded.RowShard) the sum
+    over the ranks is taken inside the same kernel over NVLink (RowShardComm) or by NCCL (plain process group)."""
     x3 = x.view(-1, 1, HID)
-    return ops.simple_partials(x3, x3, x3)
+    if shard is None or shard.world < 2:
+        return ops.simple_partials(x3, x3, x3)
+    from . import sharded
+    grp = shard.attn_group
+    if isinstance(grp, sharded.RowShardComm):
+        ex = grp.exchange(lib.dif_simple_partials_len(1, 1, HID, HID), x.device)
+        fused = ex.fused_reduce(x3, x3, x3)
+        return fused[0] if fused is not None else ex.allreduce(ops.simple_partials(x3, x3, x3))
+    return sharded.allreduce_partials(ops.simple_partials(x3, x3, x3), grp)
 
 
 def _w(t: torch.Tensor) -> torch.Tensor:

@@ -88,6 +88,19 @@ for nvlink in (False, True):
         # k barely changes the normalised attention): both the sharded and the unsharded fp32 value carry a relative error of ~1e-3 there
         tol = 2e-2 if (name.endswith("bias") and (".Wk." in name or ".Wq." in name)) else 1e-3
         assert O.rel_err(g, pr.grad) < tol, (nvlink, name, O.rel_err(g, pr.grad))
+# inference (no autograd): the sharded layers run with the projections folded into the propagation (SURVEY 8f-1 x 8e): Gram partials
+# all-reduced in the kernel, mean_h V rows all-gathered for the SpMM -- against the unsharded model with the folding on and off
+with torch.no_grad():
+    ops.set_projection_folding(False)
+    out_plain = ref.eval()(x.to(dev), ei, ew)
+    ops.set_projection_folding(True)
+    out_fold = ref(x.to(dev), ei, ew)
+    assert O.rel_err(out_fold, out_plain) < 1e-4, ("folded vs explicit, unsharded", O.rel_err(out_fold, out_plain))
+    for nvlink in (False, True):
+        ms = copy.deepcopy(m).eval()
+        sh = shard_model(ms, n, dist.group.WORLD, nvlink=nvlink)
+        out = ms(x[sh.begin:sh.end].to(dev), ei, ew)
+        assert O.rel_err(out, out_plain[sh.begin:sh.end]) < 1e-4, ("folded sharded", nvlink, O.rel_err(out, out_plain[sh.begin:sh.end]))
 # kernel='sigmoid' row-sharded: the query rows are sharded, K and V all-gathered (autograd: reduce-scatter of dK, dV)
 torch.manual_seed(1)
 n, cin = 1501, 16
