@@ -159,3 +159,23 @@ extern "C" int dif_simple_project(const float* gram_partials, const float* Wq, c
                 "simple_project: workspace too small or not 8-byte aligned");
     return simple_project(gram_partials, Wq, bq, Wk, bk, Wv, bv, n_total, H, vpartials, n_total_vec, vbar_partials, workspace, (cudaStream_t)stream);
 }
+
+// Batched-graph 'simple' forward on the tensor cores (segmented_sm100.cu): plan + kernel.
+extern "C" int64_t dif_segmented_plan_bytes(int64_t N, int max_nodes) { return segmented_plan_bytes(N, max_nodes); }
+
+extern "C" int dif_segmented_plan_build(const int32_t* seg_ptr, int32_t B, int64_t N, int max_nodes, void* plan, int64_t plan_bytes, void* stream) {
+    DIF_REQUIRE(seg_ptr && plan && B >= 1, DIF_EARG, "segmented_plan_build: bad argument");
+    const int64_t need = segmented_plan_bytes(N, max_nodes);
+    DIF_REQUIRE(need > 0, DIF_EUNSUPPORTED, "segmented_plan_build: needs 1 <= max_nodes <= 128 and 1 <= N < 2^31");
+    DIF_REQUIRE(plan_bytes >= need && (reinterpret_cast<uintptr_t>(plan) & 15) == 0, DIF_EARG, "segmented_plan_build: plan buffer too small or misaligned");
+    return segmented_plan_build(seg_ptr, B, N, max_nodes, plan, (cudaStream_t)stream);
+}
+
+extern "C" int dif_segmented_simple_fwd_tc(const float* q, const float* k, const float* v, const void* plan, int64_t plan_bytes, const float* norms,
+                                           int64_t N, int max_nodes, float* out, void* stream) {
+    DIF_REQUIRE(q && k && v && plan && norms && out, DIF_EARG, "segmented_fwd(tcgen05): null pointer");
+    const int64_t need = segmented_plan_bytes(N, max_nodes);
+    DIF_REQUIRE(need > 0, DIF_EUNSUPPORTED, "segmented_fwd(tcgen05): needs 1 <= max_nodes <= 128 and 1 <= N < 2^31");
+    DIF_REQUIRE(plan_bytes >= need, DIF_EARG, "segmented_fwd(tcgen05): plan buffer too small");
+    return segmented_fwd_tc(q, k, v, plan, N, max_nodes, norms, out, (cudaStream_t)stream);
+}

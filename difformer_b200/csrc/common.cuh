@@ -211,6 +211,10 @@ int64_t simple_tc_prepared_bytes(int H, int Hv, int M, int D);
 int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, int H, int Hv, int M, int D,
                      float* partials, void* prepared, void* ws, int64_t ws_bytes, cudaStream_t st,
                      void* const* peer_bufs = nullptr, int rank = 0, int world = 1, unsigned long long seq = 0, float* vbar = nullptr);
+int64_t segmented_plan_bytes(int64_t N, int max_nodes);
+int segmented_plan_build(const int32_t* seg_ptr, int B, int64_t N, int max_nodes, void* plan, cudaStream_t st);
+int segmented_fwd_tc(const float* q, const float* k, const float* v, const void* plan, int64_t N, int max_nodes, const float* norms, float* out,
+                     cudaStream_t st);
 int64_t simple_project_workspace_bytes(int H);
 int simple_project(const float* gram, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv, const float* bv,
                    double n_total, int H, float* vpartials, float* nvec, float* vbar_partials, void* ws, cudaStream_t st);

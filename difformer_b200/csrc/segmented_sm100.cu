@@ -1,0 +1,307 @@
+// Batched-graph kernel='simple' forward on the tensor cores (sm_100a) -- TransConv.full_attention(..., 'simple', n_nodes),
+// physical particle/difformer-v2.py:80-111: every graph g of the batch attends only inside itself,
+//     out_i = sum_{j in g(i)} (1 + c q_i.k_j) v_j / sum_{j in g(i)} (1 + c q_i.k_j),      c = 1 / (|Q|_F |K|_F) over the whole batch.
+//
+// The particle graphs have 10-40 nodes: per graph the O(n) form (S_g = K_g^T V_g, 64 x 64 x n) is more arithmetic than the direct
+// O(n^2) form, and one warp per graph (segmented.cu) is issue-bound at ~7000 instructions per graph.  Here whole graphs are packed
+// into 128-row tiles (contiguous row ranges, no data movement: the plan below) and a tile runs as block-diagonal dense attention:
+//   Sc = Q K^T            tcgen05.mma M = N = 128, K = 64, both operands K-major, bf16 hi/lo split (3 MMAs per product)
+//   W  = mask o (1 + c Sc) 256 threads (row x column half): tcgen05.ld, the row's graph is a column range [gs, ge) -> no per-column
+//                         lookup; W is split into bf16 hi + lo (hi = 1 exactly for the usual tiny c s, lo carries c s) and written
+//                         as the K-major A operand of the second product; the fp32 row sums are the denominators
+//   O  = W [Vhi | Vlo]    tcgen05.mma M = 128, N = 128, K = 128: B = the V tile read MN-major (nodes = K index); the epilogue adds the
+//                         two 64-column halves and divides by the row sum
+// Warp roles: 0-7 load + split Q, K, V (global -> registers -> swizzled operands), 8-15 W pass + epilogue, 16 MMA issuer.
+//
+// Plan (dif_segmented_plan_build, once per batch layout): tile b holds the graphs whose FIRST row lies in [b S, (b+1) S) with
+// S = 129 - max_nodes, so a tile spans < S + max_nodes = 129 rows, tiles are independent of each other (no sequential packing) and
+// the fill is S / 128 (70 % at max_nodes = 40); row_range[r] = (first row, end row) of the graph of row r.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dif {
+namespace {
+
+constexpr int kST = 128;                 // rows per tile
+constexpr int kSOp = kST * 128;          // one bf16 operand tile [128 rows][64]: 16 KB
+constexpr int kSegTcWarps = 17, kSegTcThreads = kSegTcWarps * 32;
+constexpr int kSegTcSmem = 3 * 2 * kSOp + 4 * kSOp + 1024;      // Q, K, V (hi | lo) + W (hi: 2 K blocks, lo: 2 K blocks)
+
+struct SegTcArgs {
+    const float *q, *k, *v;
+    const int2* row_range;
+    const int* tile_row0;
+    int ntiles;
+    const float* norms;                  // [sum q^2, sum k^2] over the whole batch
+    float* out;
+};
+
+__device__ __forceinline__ void seg_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void seg_plan_kernel(const int32_t* __restrict__ seg, int B, int64_t N, int S, int ntiles, int* __restrict__ tile_row0,
+                                int2* __restrict__ row_range) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B) return;
+    const int s = seg[g], e = seg[g + 1];
+    if (e <= s) return;                                       // empty graph: owns no rows
+    for (int r = s; r < e; ++r) row_range[r] = make_int2(s, e);
+    int pb = -1;                                              // bucket of the previous non-empty graph
+    if (s > 0) {
+        int gp = g - 1;
+        while (gp > 0 && seg[gp] == s) --gp;                  // skip empty graphs
+        pb = seg[gp] / S;
+    }
+    const int b = s / S;
+    for (int bb = pb + 1; bb <= b; ++bb) tile_row0[bb] = s;   // this graph opens bucket b (and any empty buckets before it)
+    if (e == (int)N)
+        for (int bb = b + 1; bb <= ntiles; ++bb) tile_row0[bb] = (int)N;
+}
+
+// 128 rows x 64 floats of `src` starting at row0 (rows >= row1 read as zero) -> bf16 hi | lo K-major SW128 operand at s_hi.  256 threads.
+__device__ __forceinline__ void seg_load(const float* src, int64_t row0, int64_t row1, int tid, float (&x)[4][8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = tid + 256 * j;
+        const int64_t row = row0 + (t >> 3);
+        if (row < row1) ldg256_keep(src + row * kDim + (t & 7) * 8, x[j]);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[j][i] = 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void seg_store(uint32_t s_hi, int tid, const float (&x)[4][8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = tid + 256 * j;
+        uint4 hi, lo;
+        split8(x[j], hi, lo);
+        const uint32_t off = sw128(t >> 3, t & 7);
+        sts128(s_hi + off, hi);
+        sts128(s_hi + kSOp + off, lo);
+    }
+}
+
+__global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __grid_constant__ SegTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t Qop = smem_u32(base), Kop = Qop + 2 * kSOp, Vop = Kop + 2 * kSOp, Whi = Vop + 2 * kSOp, Wlo = Whi + 2 * kSOp;
+    __shared__ uint64_t qk_full, v_full, s_full, w_full, o_full, s_free, o_free;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float den_s[2][2][kST];                        // [tile parity][column half][row]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = (int)blockIdx.x < p.ntiles ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        mbar_init(&qk_full, 8); mbar_init(&v_full, 8); mbar_init(&w_full, 8);
+        mbar_init(&s_full, 1); mbar_init(&o_full, 1);
+        mbar_init(&s_free, 8); mbar_init(&o_free, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tmemS = tmem, tmemO = tmem + kST;          // columns 0-127: Sc ; 128-255: O = [W Vhi | W Vlo]
+
+    if (warp < 8) {
+        // ===== producers: Q, K then V of the tile -> operands.  Q and K may be overwritten once the previous tile's first product has
+        // completed (s_full), V once its second product has (o_full); the loads themselves are issued before those waits.
+        // Register schedule: Q and K of the NEXT tile are in flight while this tile's V is converted and its products run.
+        float xa[4][8], xb[4][8];
+        if (my_tiles > 0) {
+            const int64_t r0 = p.tile_row0[blockIdx.x], r1 = p.tile_row0[blockIdx.x + 1];
+            seg_load(p.q, r0, r1, tid, xa);
+            seg_load(p.k, r0, r1, tid, xb);
+        }
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int64_t r0 = p.tile_row0[tile], r1 = p.tile_row0[tile + 1];
+            if (it > 0) mbar_wait(&s_full, (it - 1) & 1);
+            seg_store(Qop, tid, xa);
+            seg_store(Kop, tid, xb);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qk_full);
+            seg_load(p.v, r0, r1, tid, xa);
+            if (it + 1 < my_tiles) {
+                const int64_t n0 = p.tile_row0[tile + gridDim.x], n1 = p.tile_row0[tile + gridDim.x + 1];
+                seg_load(p.k, n0, n1, tid, xb);
+                if (it > 0) mbar_wait(&o_full, (it - 1) & 1);
+                seg_store(Vop, tid, xa);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&v_full);
+                seg_load(p.q, n0, n1, tid, xa);
+            } else {
+                if (it > 0) mbar_wait(&o_full, (it - 1) & 1);
+                seg_store(Vop, tid, xa);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&v_full);
+            }
+        }
+    } else if (warp < 16) {
+        // ===== W pass + epilogue: thread = (tile row i, column half).  TMEM lane = 32 quad + lane.
+        const int ew = warp - 8, quad = ew & 3, half = ew >> 2;
+        const int i = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int r0 = p.tile_row0[tile], r1 = p.tile_row0[tile + 1];
+            const int row = r0 + i;
+            const bool valid = row < r1;
+            int gs = 0, ge = 0;                                // this row's graph as a column range of the tile
+            if (valid) { const int2 rg = p.row_range[row]; gs = rg.x - r0; ge = rg.y - r0; }
+            mbar_wait(&s_full, it & 1);
+            tc_fence_after();
+            float den = 0.f;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmemS + tlane + 64 * half + c0, r);
+                tmem_ld_wait32(r);
+                if (c0 == 32) {                                // the row's scores are in registers: Sc may be overwritten
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_free);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 8) {
+                    float w[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = 64 * half + c0 + jj + e;
+                        w[e] = (j >= gs && j < ge) ? fmaf(c, __uint_as_float(r[jj + e]), 1.f) : 0.f;
+                        den += w[e];
+                    }
+                    uint4 hi, lo;
+                    split8(w, hi, lo);
+                    const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, (c0 + jj) >> 3);      // K block = column half
+                    sts128(Whi + off, hi);
+                    sts128(Wlo + off, lo);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&w_full);
+            den_s[it & 1][half][i] = den;
+            seg_bar_sync(1 + quad, 64);                      // the two column halves of the rows 32 quad .. +31
+            const float inv = 1.f / (den_s[it & 1][0][i] + den_s[it & 1][1][i]);
+            mbar_wait(&o_full, it & 1);
+            tc_fence_after();
+            float* dst = p.out + (int64_t)row * kDim + 32 * half;
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                uint32_t a[16], b[16];
+                tmem_ld16(tmemO + tlane + 32 * half + c0, a);
+                tmem_ld16(tmemO + tlane + kDim + 32 * half + c0, b);
+                tmem_ld_wait16(a);
+                tmem_ld_wait16(b);
+                if (c0 == 16) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&o_free);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o;
+                        o.x = (__uint_as_float(a[j]) + __uint_as_float(b[j])) * inv;
+                        o.y = (__uint_as_float(a[j + 1]) + __uint_as_float(b[j + 1])) * inv;
+                        o.z = (__uint_as_float(a[j + 2]) + __uint_as_float(b[j + 2])) * inv;
+                        o.w = (__uint_as_float(a[j + 3]) + __uint_as_float(b[j + 3])) * inv;
+                        *reinterpret_cast<float4*>(dst + c0 + j) = o;
+                    }
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer
+        const uint32_t idS = make_idesc(kST, kST, 0, 0);          // Sc = Q K^T: both operands K-major
+        const uint32_t idO = make_idesc(kST, 2 * kDim, 0, 1);     // [W Vhi | W Vlo]: A = W K-major, B = V MN-major (hi | lo: two 64-blocks, LBO apart)
+        for (int it = 0; it < my_tiles; ++it) {
+            if (it > 0) mbar_wait(&s_free, (it - 1) & 1);
+            mbar_wait(&qk_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t qhi = make_desc(Qop + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(Qop + kSOp + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t khi = make_desc(Kop + ks * 32, kKmajLBO, kKmajSBO), klo = make_desc(Kop + kSOp + ks * 32, kKmajLBO, kKmajSBO);
+                umma(tmemS, qhi, khi, idS, ks > 0 ? 1u : 0u);
+                umma(tmemS, qlo, khi, idS, 1u);
+                umma(tmemS, qhi, klo, idS, 1u);
+            }
+            umma_commit(&s_full);
+            if (it > 0) mbar_wait(&o_free, (it - 1) & 1);
+            mbar_wait(&v_full, it & 1);
+            mbar_wait(&w_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t wo = (uint32_t)((ks >> 2) * kSOp + (ks & 3) * 32);
+                const uint64_t whi = make_desc(Whi + wo, kKmajLBO, kKmajSBO), wlo = make_desc(Wlo + wo, kKmajLBO, kKmajSBO);
+                const uint64_t vb = make_desc(Vop + ks * 2048, kSOp, 1024);
+                umma(tmemO, whi, vb, idO, ks > 0 ? 1u : 0u);
+                umma(tmemO, wlo, vb, idO, 1u);
+            }
+            umma_commit(&o_full);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+// plan = tile_row0 [ntiles + 1] (int32, padded to 16 bytes) | row_range [N] (int2)
+static int seg_plan_layout(int64_t N, int max_nodes, int* S, int* ntiles, int64_t* off_rows) {
+    if (N < 1 || N >= (1ll << 31) || max_nodes < 1 || max_nodes > kST) return 1;
+    *S = kST + 1 - max_nodes;
+    *ntiles = (int)((N + *S - 1) / *S);
+    *off_rows = (((int64_t)(*ntiles + 1) * 4 + 15) / 16) * 16;
+    return 0;
+}
+
+int64_t segmented_plan_bytes(int64_t N, int max_nodes) {
+    int S, nt;
+    int64_t off;
+    if (seg_plan_layout(N, max_nodes, &S, &nt, &off)) return 0;
+    return off + N * 8;
+}
+
+int segmented_plan_build(const int32_t* seg_ptr, int B, int64_t N, int max_nodes, void* plan, cudaStream_t st) {
+    int S, nt;
+    int64_t off;
+    DIF_REQUIRE(!seg_plan_layout(N, max_nodes, &S, &nt, &off), DIF_EUNSUPPORTED, "segmented plan: needs 1 <= max_nodes <= 128 and N < 2^31");
+    seg_plan_kernel<<<(B + 255) / 256, 256, 0, st>>>(seg_ptr, B, N, S, nt, (int*)plan, (int2*)((uint8_t*)plan + off));
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+int segmented_fwd_tc(const float* q, const float* k, const float* v, const void* plan, int64_t N, int max_nodes, const float* norms, float* out,
+                     cudaStream_t st) {
+    int S, nt;
+    int64_t off;
+    DIF_REQUIRE(!seg_plan_layout(N, max_nodes, &S, &nt, &off), DIF_EUNSUPPORTED, "segmented_fwd(tcgen05): needs 1 <= max_nodes <= 128 and N < 2^31");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 31) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)plan & 15) == 0, DIF_EARG,
+                "segmented_fwd(tcgen05): q / k / v must be 32-byte, out and plan 16-byte aligned");
+    static bool attr_set = false;
+    if (!attr_set) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(seg_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegTcSmem));
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    DIF_CUDA_OK(cudaGetDevice(&dev));
+    DIF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SegTcArgs a{q, k, v, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, out};
+    seg_fwd_tc_kernel<<<nt < sms ? nt : sms, kSegTcThreads, kSegTcSmem, st>>>(a);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+}  // namespace dif

@@ -25,6 +25,20 @@ def set_simple_impl(impl: str) -> None:
     _SIMPLE_IMPL = {"auto": _lib.DIF_IMPL_AUTO, "generic": _lib.DIF_IMPL_GENERIC, "tcgen05": _lib.DIF_IMPL_TCGEN05}[impl]
 
 
+_SEGMENTED_IMPL = "auto"
+SEGMENTED_TC_MIN_ROWS = 4096       # below this the batch is a handful of tiles: the warp-per-graph kernel wins
+SEGMENTED_TC_MAX_NODES = 64        # larger graphs: the plan's tile fill (129 - max_nodes) / 128 drops below one half
+
+
+def set_segmented_impl(impl: str) -> None:
+    """Forward of the batched-graph 'simple' kernel: 'auto' (tensor cores for H = 1, hidden 64, graphs of <= 64 nodes, >= 4096 rows),
+    'generic' (one warp / CTA per graph, FFMA), 'tcgen05' (tensor cores whenever the shape allows: H = 1, hidden 64, graphs <= 128 nodes)."""
+    global _SEGMENTED_IMPL
+    if impl not in ("auto", "generic", "tcgen05"):
+        raise ValueError(impl)
+    _SEGMENTED_IMPL = impl
+
+
 def set_sigmoid_impl(impl: str) -> None:
     """Select the 'sigmoid' forward kernel: 'auto' (tcgen05 when M == D == 64), 'generic' (fp32 FFMA), 'tcgen05'."""
     check(lib.dif_sigmoid_set_impl({"auto": _lib.DIF_IMPL_AUTO, "generic": _lib.DIF_IMPL_GENERIC,
@@ -600,7 +614,25 @@ def subgraph(subset: torch.Tensor, edge_index: torch.Tensor, num_nodes: int, edg
 _SEG_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 
 
-def _seg_ptr(n_nodes: torch.Tensor, total: int, device) -> torch.Tensor:
+class _SegLayout:
+    """seg_ptr of a batch layout + (lazily) the tensor-core plan of csrc/segmented_sm100.cu."""
+    __slots__ = ("ptr", "n_nodes", "max_nodes", "total", "_plan")
+
+    def __init__(self, ptr, n_nodes, max_nodes, total):
+        self.ptr, self.n_nodes, self.max_nodes, self.total, self._plan = ptr, n_nodes, max_nodes, total, None
+
+    def plan(self):
+        if self._plan is None:
+            nbytes = int(lib.dif_segmented_plan_bytes(self.total, self.max_nodes))
+            plan = torch.empty(nbytes, dtype=torch.uint8, device=self.ptr.device)
+            with torch.cuda.device(self.ptr.device):
+                check(lib.dif_segmented_plan_build(self.ptr.data_ptr(), self.ptr.numel() - 1, self.total, self.max_nodes, plan.data_ptr(),
+                                                   nbytes, _stream(self.ptr)), "dif_segmented_plan_build")
+            self._plan = plan
+        return self._plan
+
+
+def _seg_layout(n_nodes: torch.Tensor, total: int, device) -> _SegLayout:
     """seg_ptr = [0, cumsum(n_nodes)] (int32, device).  Validated once per `n_nodes` tensor (storage + version): B >= 1 and
     sum(n_nodes) == number of rows -- the reference would fail on a mismatch, the kernels would read or leave rows
     uninitialised.  The one host read this costs is cached, like the reference's own `n_nodes.max().item()` per call."""
@@ -608,27 +640,44 @@ def _seg_ptr(n_nodes: torch.Tensor, total: int, device) -> torch.Tensor:
     hit = _SEG_CACHE.get(key)
     if hit is not None:
         _SEG_CACHE.move_to_end(key)
-        return hit[0]
+        return hit
     nn_ = n_nodes.to(device=device, dtype=torch.int64)
     if nn_.numel() < 1:
         raise ValueError("n_nodes is empty but there are rows to process")
     ptr = torch.zeros(nn_.numel() + 1, dtype=torch.int32, device=device)
     ptr[1:] = torch.cumsum(nn_, 0).to(torch.int32)      # one cumsum on device; no Python loops, no padding
-    if int(ptr[-1]) != int(total) or bool((nn_ < 0).any()):
-        raise ValueError(f"sum(n_nodes) = {int(ptr[-1])} does not match the {int(total)} rows of qs / ks / vs (or a count is negative)")
-    _SEG_CACHE[key] = (ptr, n_nodes)
+    tot, mn, mx = (int(v) for v in torch.stack([nn_.sum(), nn_.min(), nn_.max()]).tolist())     # one host read
+    if tot != int(total) or mn < 0:
+        raise ValueError(f"sum(n_nodes) = {tot} does not match the {int(total)} rows of qs / ks / vs (or a count is negative)")
+    lay = _SegLayout(ptr, n_nodes, mx, int(total))
+    _SEG_CACHE[key] = lay
     while len(_SEG_CACHE) > 16:
         _SEG_CACHE.popitem(last=False)
-    return ptr
+    return lay
+
+
+def _seg_ptr(n_nodes: torch.Tensor, total: int, device) -> torch.Tensor:
+    return _seg_layout(n_nodes, total, device).ptr
+
+
+def _segmented_tc_plan(lay: _SegLayout, H: int, Hv: int, M: int, D: int):
+    """The tensor-core plan when the forward should run on tcgen05, else None."""
+    if _SEGMENTED_IMPL == "generic" or not (H == 1 and Hv == 1 and M == 64 and D == 64) or not (1 <= lay.max_nodes <= 128):
+        return None
+    if _SEGMENTED_IMPL == "auto" and not (lay.max_nodes <= SEGMENTED_TC_MAX_NODES and lay.total >= SEGMENTED_TC_MIN_ROWS):
+        return None
+    return lay.plan()
 
 
 class _SegmentedSimple(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qs, ks, vs, seg_ptr, group):
+    def forward(ctx, qs, ks, vs, lay, group):
+        seg_ptr = lay.ptr
         _need_cuda(qs, ks, vs, seg_ptr)
         qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
         B = seg_ptr.numel() - 1
+        plan = _segmented_tc_plan(lay, H, Hv, M, D)
         dev = qs.device
         norms = torch.empty(2, dtype=torch.float32, device=dev)
         ws = workspace(dev, lib.dif_segmented_workspace_bytes(B))
@@ -637,8 +686,12 @@ class _SegmentedSimple(torch.autograd.Function):
             st = _stream(qs)
             check(lib.dif_sumsq2(qs.data_ptr(), ks.data_ptr(), qs.numel(), norms.data_ptr(), ws.data_ptr(), ws.numel(), st), "dif_sumsq2")
             _allreduce(norms, group)      # graphs shard whole; only the two norms cross ranks
-            check(lib.dif_segmented_simple_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), seg_ptr.data_ptr(), B,
-                                               norms.data_ptr(), N, H, Hv, M, D, out.data_ptr(), st), "dif_segmented_simple_fwd")
+            if plan is not None:     # whole graphs packed into 128-row tiles, block-diagonal attention on the tensor cores
+                check(lib.dif_segmented_simple_fwd_tc(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), plan.data_ptr(), plan.numel(),
+                                                      norms.data_ptr(), N, lay.max_nodes, out.data_ptr(), st), "dif_segmented_simple_fwd_tc")
+            else:
+                check(lib.dif_segmented_simple_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), seg_ptr.data_ptr(), B,
+                                                   norms.data_ptr(), N, H, Hv, M, D, out.data_ptr(), st), "dif_segmented_simple_fwd")
         ctx.save_for_backward(qs, ks, vs, seg_ptr, norms, out)
         ctx.group = group
         return out
@@ -706,4 +759,4 @@ def segmented_full_attention(qs, ks, vs, kernel, n_nodes, *, group=None):
         raise ValueError(f"unknown kernel {kernel!r}")
     if int(qs.shape[0]) == 0:
         return qs.new_empty((0, qs.shape[1], vs.shape[2]))
-    return _SegmentedSimple.apply(qs, ks, vs, _seg_ptr(n_nodes, qs.shape[0], qs.device), group)
+    return _SegmentedSimple.apply(qs, ks, vs, _seg_layout(n_nodes, qs.shape[0], qs.device), group)

@@ -186,6 +186,15 @@ DIF_API int dif_sumsq2(const float* q, const float* k, int64_t count, float* nor
 DIF_API int dif_segmented_simple_fwd(const float* q, const float* k, const float* v, const int32_t* seg_ptr,
                              int32_t B, const float* norms, int64_t N, int H, int Hv, int M, int D,
                              float* out, void* stream);
+/* The same forward on the tensor cores (tcgen05): H = Hv = 1, M = D = 64, every graph <= max_nodes <= 128 rows.  Whole graphs are
+ * packed into 128-row tiles that run as block-diagonal dense attention (scores Q K^T, weights mask o (1 + c s), W V), see
+ * csrc/segmented_sm100.cu.  The packing is a device-side plan built once per batch layout from seg_ptr (no host loop, no data
+ * movement): dif_segmented_plan_bytes(N, max_nodes) bytes (0: unsupported), 16-byte aligned, valid for any q / k / v of that layout.
+ * q, k, v 32-byte aligned.  Results equal dif_segmented_simple_fwd to fp32 rounding. */
+DIF_API int64_t dif_segmented_plan_bytes(int64_t N, int max_nodes);
+DIF_API int dif_segmented_plan_build(const int32_t* seg_ptr, int32_t B, int64_t N, int max_nodes, void* plan, int64_t plan_bytes, void* stream);
+DIF_API int dif_segmented_simple_fwd_tc(const float* q, const float* k, const float* v, const void* plan, int64_t plan_bytes,
+                                const float* norms, int64_t N, int max_nodes, float* out, void* stream);
 /* backward: `out` is the saved forward output, g = dL/dout; M in {16,32,64}, D <= 64.  M == D == 64: graphs of up to
  * 64 rows run one warp per graph (direct O(n^2) form), larger ones one CTA per graph; no atomics, deterministic. */
 DIF_API int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,

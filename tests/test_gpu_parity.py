@@ -641,6 +641,78 @@ def test_v2_backward_mixed_sizes(h):
     assert torch.equal(out, out2) and torch.equal(q2, qd.grad)
 
 
+def _seg_layouts():
+    gen = torch.Generator().manual_seed(41)
+    return {
+        "particles": torch.randint(10, 41, (600,), generator=gen),                     # BASELINE configs[4] distribution
+        "tiny_and_empty": torch.cat([torch.tensor([0, 1, 0, 2, 1, 1, 0]), torch.randint(0, 6, (900,), generator=gen), torch.tensor([0, 0])]),
+        "edge_64": torch.cat([torch.tensor([64, 64, 1, 63, 64, 2]), torch.randint(30, 65, (100,), generator=gen)]),
+        "max_128": torch.cat([torch.tensor([128, 1, 127, 128, 65]), torch.randint(1, 129, (40,), generator=gen)]),
+        "one_graph": torch.tensor([97]),
+        "uniform_32": torch.full((256,), 32),                                          # graph boundaries on every tile boundary candidate
+    }
+
+
+@pytest.mark.parametrize("name", list(_seg_layouts()))
+def test_v2_simple_tensor_core_forward(name):
+    """Batched-graph 'simple' on the tensor cores (whole graphs packed into 128-row tiles, block-diagonal attention) against the fp64
+    oracle and the warp-per-graph kernel; the plan's invariants; the part of the output that is not the per-graph mean of V."""
+    n_nodes = _seg_layouts()[name]
+    tot = int(n_nodes.sum())
+    q, k, v = O.synthetic_qkv(tot, 1, 64, seed=13, adversarial=True)
+    want = O.segmented_simple_attention(q.double(), k.double(), v.double(), n_nodes)
+    qd, kd, vd, nd = dev(q), dev(k), dev(v), n_nodes.cuda()
+    try:
+        ops.set_segmented_impl("generic")
+        ref = ops.segmented_full_attention(qd, kd, vd, "simple", nd)
+        ops.set_segmented_impl("tcgen05")
+        got = ops.segmented_full_attention(qd, kd, vd, "simple", nd)
+        got2 = ops.segmented_full_attention(qd, kd, vd, "simple", nd)
+    finally:
+        ops.set_segmented_impl("auto")
+    assert torch.equal(got, got2)                                   # deterministic
+    assert O.rel_err(ref, want) < TOL and O.rel_err(got, want) < TOL
+    assert O.rel_err(got, ref) < 1e-5
+    # per-graph mean of V removed: what is left is the attention's own contribution (tiny when the batch is large: c ~ 1 / rows)
+    seg = torch.repeat_interleave(torch.arange(n_nodes.numel()), n_nodes)
+    vmean = torch.zeros(n_nodes.numel(), 64, dtype=torch.float64).index_add_(0, seg, v.double()[:, 0]) / n_nodes.clamp(min=1).unsqueeze(1)
+    dev_part = want[:, 0] - vmean[seg]
+    err_ref = O.rel_err(ref.cpu().double()[:, 0] - vmean[seg], dev_part)
+    assert O.rel_err(got.cpu().double()[:, 0] - vmean[seg], dev_part) < max(5e-3, 3 * err_ref)
+    # the plan: tiles are whole graphs, at most 128 rows, cover every row once; row ranges are the graphs
+    lay = ops._seg_layout(nd, tot, qd.device)
+    plan = lay.plan().cpu()
+    S = 129 - lay.max_nodes
+    nt = (tot + S - 1) // S
+    tiles = plan[:4 * (nt + 1)].view(torch.int32)
+    rr = plan[((4 * (nt + 1) + 15) // 16) * 16:].view(torch.int32).view(tot, 2)
+    ptr = lay.ptr.cpu()
+    assert int(tiles[0]) == 0 and int(tiles[-1]) == tot
+    d = tiles[1:] - tiles[:-1]
+    assert int(d.min()) >= 0 and int(d.max()) <= 128
+    assert bool(torch.isin(tiles, ptr).all())
+    starts = ptr[:-1][n_nodes > 0].repeat_interleave(n_nodes[n_nodes > 0])
+    ends = ptr[1:][n_nodes > 0].repeat_interleave(n_nodes[n_nodes > 0])
+    assert torch.equal(rr[:, 0], starts.to(torch.int32)) and torch.equal(rr[:, 1], ends.to(torch.int32))
+
+
+def test_v2_simple_tensor_core_training_step():
+    """auto dispatch at batch scale: forward on the tensor cores, backward through the FFMA kernels (they take the saved output)."""
+    gen = torch.Generator().manual_seed(5)
+    n_nodes = torch.randint(10, 41, (400,), generator=gen)
+    tot = int(n_nodes.sum())
+    assert tot >= ops.SEGMENTED_TC_MIN_ROWS
+    q, k, v = O.synthetic_qkv(tot, 1, 64, seed=2, adversarial=True)
+    g = torch.randn(tot, 1, 64, generator=gen)
+    qd, kd, vd = (dev(t).requires_grad_(True) for t in (q, k, v))
+    out = ops.segmented_full_attention(qd, kd, vd, "simple", n_nodes.cuda())
+    assert O.rel_err(out, O.segmented_simple_attention(q.double(), k.double(), v.double(), n_nodes)) < TOL
+    out.backward(dev(g))
+    want = O.segmented_simple_attention_backward(q.double(), k.double(), v.double(), n_nodes, g.double())
+    for got, w64 in ((qd.grad, want[0]), (kd.grad, want[1]), (vd.grad, want[2])):
+        assert O.rel_err(got, w64) < TOL
+
+
 def test_v2_model_forward():
     c = V2["v2_model_simple"]
     m = difformer.DIFFormer_v2(16, 64, 3, num_layers=2, kernel="simple", use_graph=True)
