@@ -678,7 +678,9 @@ def test_v2_simple_tensor_core_forward(name):
     vmean = torch.zeros(n_nodes.numel(), 64, dtype=torch.float64).index_add_(0, seg, v.double()[:, 0]) / n_nodes.clamp(min=1).unsqueeze(1)
     dev_part = want[:, 0] - vmean[seg]
     err_ref = O.rel_err(ref.cpu().double()[:, 0] - vmean[seg], dev_part)
-    assert O.rel_err(got.cpu().double()[:, 0] - vmean[seg], dev_part) < max(5e-3, 3 * err_ref)
+    # ... as far as fp32 output can resolve it: bf16 hi + lo of V carries 16 mantissa bits, i.e. ~4e-6 of the output scale
+    floor = 4e-6 * float(torch.linalg.vector_norm(want)) / max(float(torch.linalg.vector_norm(dev_part)), 1e-30)
+    assert O.rel_err(got.cpu().double()[:, 0] - vmean[seg], dev_part) < max(5e-3, 3 * err_ref, floor)
     # the plan: tiles are whole graphs, at most 128 rows, cover every row once; row ranges are the graphs
     lay = ops._seg_layout(nd, tot, qd.device)
     plan = lay.plan().cpu()
