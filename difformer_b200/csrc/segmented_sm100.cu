@@ -108,39 +108,50 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
     if (warp < 8) {
         // ===== producers: Q, K then V of the tile -> operands.  Q and K may be overwritten once the previous tile's first product has
         // completed (s_full), V once its second product has (o_full); the loads themselves are issued before those waits.
-        // Register schedule: Q and K of the NEXT tile are in flight while this tile's V is converted and its products run.
+        // Register schedule (two sets of 32 floats per thread, swapped every tile): on entry A = Q(it), B = K(it); V(it) and Q(it+1) are
+        // requested together right after the first product's operands are published, K(it+1) right after V is; the rows of tile it+2
+        // are pulled into L2 meanwhile, so the register loads are L2 hits.
         float xa[4][8], xb[4][8];
+        auto l2_ahead = [&](int tile) {
+            if (tid != 0 || tile >= p.ntiles) return;
+            const int64_t r0 = p.tile_row0[tile], r1 = p.tile_row0[tile + 1];
+            if (r1 <= r0) return;
+            const uint32_t bytes = (uint32_t)((r1 - r0) * kDim * 4);
+            prefetch_l2(p.q + r0 * kDim, bytes);
+            prefetch_l2(p.k + r0 * kDim, bytes);
+            prefetch_l2(p.v + r0 * kDim, bytes);
+        };
+        auto body = [&](int it, float (&A)[4][8], float (&B)[4][8]) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int64_t r0 = p.tile_row0[tile], r1 = p.tile_row0[tile + 1];
+            const bool has_next = it + 1 < my_tiles;
+            int64_t n0 = 0, n1 = 0;
+            if (has_next) { n0 = p.tile_row0[tile + gridDim.x]; n1 = p.tile_row0[tile + gridDim.x + 1]; }
+            l2_ahead(tile + 2 * gridDim.x);
+            if (it > 0) mbar_wait(&s_full, (it - 1) & 1);
+            seg_store(Qop, tid, A);
+            seg_store(Kop, tid, B);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qk_full);
+            seg_load(p.v, r0, r1, tid, A);
+            if (has_next) seg_load(p.q, n0, n1, tid, B);
+            if (it > 0) mbar_wait(&o_full, (it - 1) & 1);
+            seg_store(Vop, tid, A);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&v_full);
+            if (has_next) seg_load(p.k, n0, n1, tid, A);       // exit: B = Q(it+1), A = K(it+1)
+        };
         if (my_tiles > 0) {
             const int64_t r0 = p.tile_row0[blockIdx.x], r1 = p.tile_row0[blockIdx.x + 1];
             seg_load(p.q, r0, r1, tid, xa);
             seg_load(p.k, r0, r1, tid, xb);
+            l2_ahead(blockIdx.x + gridDim.x);
         }
-        for (int it = 0; it < my_tiles; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int64_t r0 = p.tile_row0[tile], r1 = p.tile_row0[tile + 1];
-            if (it > 0) mbar_wait(&s_full, (it - 1) & 1);
-            seg_store(Qop, tid, xa);
-            seg_store(Kop, tid, xb);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&qk_full);
-            seg_load(p.v, r0, r1, tid, xa);
-            if (it + 1 < my_tiles) {
-                const int64_t n0 = p.tile_row0[tile + gridDim.x], n1 = p.tile_row0[tile + gridDim.x + 1];
-                seg_load(p.k, n0, n1, tid, xb);
-                if (it > 0) mbar_wait(&o_full, (it - 1) & 1);
-                seg_store(Vop, tid, xa);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&v_full);
-                seg_load(p.q, n0, n1, tid, xa);
-            } else {
-                if (it > 0) mbar_wait(&o_full, (it - 1) & 1);
-                seg_store(Vop, tid, xa);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&v_full);
-            }
+        for (int it = 0; it < my_tiles; it += 2) {
+            body(it, xa, xb);
+            if (it + 1 < my_tiles) body(it + 1, xb, xa);
         }
     } else if (warp < 16) {
         // ===== W pass + epilogue: thread = (tile row i, column half).  TMEM lane = 32 quad + lane.

@@ -672,7 +672,7 @@ def test_v2_simple_tensor_core_forward(name):
         ops.set_segmented_impl("auto")
     assert torch.equal(got, got2)                                   # deterministic
     assert O.rel_err(ref, want) < TOL and O.rel_err(got, want) < TOL
-    assert O.rel_err(got, ref) < 1e-5
+    assert O.rel_err(got, ref) < 3e-5                               # bf16 hi + lo of the weights and of V: 16 mantissa bits
     # per-graph mean of V removed: what is left is the attention's own contribution (tiny when the batch is large: c ~ 1 / rows)
     seg = torch.repeat_interleave(torch.arange(n_nodes.numel()), n_nodes)
     vmean = torch.zeros(n_nodes.numel(), 64, dtype=torch.float64).index_add_(0, seg, v.double()[:, 0]) / n_nodes.clamp(min=1).unsqueeze(1)
