@@ -34,7 +34,13 @@ struct SegTcArgs {
     int ntiles;
     const float* norms;                  // [sum q^2, sum k^2] over the whole batch
     float* out;
+    unsigned long long* dbg;             // optional timeline of CTA 0 (DIF_SEG_DEBUG=1): [tile < 8][event < 8] %globaltimer
 };
+
+#define SEG_STAMP(ev)                                                                                   \
+    do {                                                                                                \
+        if (p.dbg != nullptr && blockIdx.x == 0 && it < 8) p.dbg[it * 8 + (ev)] = gtime();             \
+    } while (0)
 
 __device__ __forceinline__ void seg_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 
@@ -134,6 +140,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&qk_full);
+            if (tid == 0) SEG_STAMP(0);
             seg_load(p.v, r0, r1, tid, A);
             if (has_next) seg_load(p.q, n0, n1, tid, B);
             if (it > 0) mbar_wait(&o_full, (it - 1) & 1);
@@ -141,6 +148,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&v_full);
+            if (tid == 0) SEG_STAMP(1);
             if (has_next) seg_load(p.k, n0, n1, tid, A);       // exit: B = Q(it+1), A = K(it+1)
         };
         if (my_tiles > 0) {
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             if (valid) { const int2 rg = p.row_range[row]; gs = rg.x - r0; ge = rg.y - r0; }
             mbar_wait(&s_full, it & 1);
             tc_fence_after();
+            if (ew == 0 && lane == 0) SEG_STAMP(2);
             float den = 0.f;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -198,11 +207,13 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&w_full);
+            if (ew == 0 && lane == 0) SEG_STAMP(3);
             den_s[it & 1][half][i] = den;
             seg_bar_sync(1 + quad, 64);                      // the two column halves of the rows 32 quad .. +31
             const float inv = 1.f / (den_s[it & 1][0][i] + den_s[it & 1][1][i]);
             mbar_wait(&o_full, it & 1);
             tc_fence_after();
+            if (ew == 0 && lane == 0) SEG_STAMP(4);
             float* dst = p.out + (int64_t)row * kDim + 32 * half;
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -228,6 +239,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
                     }
                 }
             }
+            if (ew == 0 && lane == 0) SEG_STAMP(5);
         }
     } else if (lane == 0) {
         // ===== MMA issuer
@@ -246,6 +258,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
                 umma(tmemS, qhi, klo, idS, 1u);
             }
             umma_commit(&s_full);
+            SEG_STAMP(6);
             if (it > 0) mbar_wait(&o_free, (it - 1) & 1);
             mbar_wait(&v_full, it & 1);
             mbar_wait(&w_full, it & 1);
@@ -259,6 +272,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
                 umma(tmemO, wlo, vb, idO, 1u);
             }
             umma_commit(&o_full);
+            SEG_STAMP(7);
         }
     }
     __syncwarp();
@@ -309,9 +323,26 @@ int segmented_fwd_tc(const float* q, const float* k, const float* v, const void*
     int dev = 0, sms = 148;
     DIF_CUDA_OK(cudaGetDevice(&dev));
     DIF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SegTcArgs a{q, k, v, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, out};
+    static unsigned long long* dbg = nullptr;
+    static const bool debug = getenv("DIF_SEG_DEBUG") && atoi(getenv("DIF_SEG_DEBUG"));
+    if (debug && !dbg) DIF_CUDA_OK(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
+    if (debug) DIF_CUDA_OK(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), st));
+    SegTcArgs a{q, k, v, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, out, debug ? dbg : nullptr};
     seg_fwd_tc_kernel<<<nt < sms ? nt : sms, kSegTcThreads, kSegTcSmem, st>>>(a);
     DIF_LAUNCH_OK();
+    if (debug) {   // CTA 0: events per tile in ns since its first stamp: qk published, v published, scores seen, W published, O seen, epilogue done, MMA1 issued, MMA2 issued
+        unsigned long long h[64];
+        DIF_CUDA_OK(cudaStreamSynchronize(st));
+        DIF_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 64; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+        fprintf(stderr, "[seg_fwd_tc] tile: qk_full v_full | s_seen w_full o_seen epi_done | mma1_issued mma2_issued (ns)\n");
+        for (int t = 0; t < 8; ++t) {
+            fprintf(stderr, "  %d:", t);
+            for (int e = 0; e < 8; ++e) fprintf(stderr, " %7lld", h[t * 8 + e] ? (long long)(h[t * 8 + e] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+    }
     return DIF_OK;
 }
 
