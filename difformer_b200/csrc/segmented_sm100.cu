@@ -163,43 +163,55 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
         }
     } else if (warp < 16) {
         // ===== W pass + epilogue: thread = (tile row i, column half).  TMEM lane = 32 quad + lane.
+        // These eight warps are the critical resource of a tile (scores -> W -> wait for W V -> output), so: the tile's row range and
+        // the row's graph come from registers loaded during the previous tile's wait; both 32-column TMEM loads of a phase are in
+        // flight together; 8-column groups outside the row's graph are stored as zeros without touching the scores.
         const int ew = warp - 8, quad = ew & 3, half = ew >> 2;
         const int i = quad * 32 + lane;
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+        int r0 = 0, r1 = 0, gs = 0, ge = 0;                    // tile rows [r0, r1); this row's graph = columns [gs, ge) of the tile
+        auto tile_rows = [&](int it_, int& a0, int& a1, int& s_, int& e_) {
+            const int tile = blockIdx.x + it_ * gridDim.x;
+            a0 = p.tile_row0[tile];
+            a1 = p.tile_row0[tile + 1];
+            s_ = e_ = 0;
+            if (a0 + i < a1) { const int2 rg = p.row_range[a0 + i]; s_ = rg.x - a0; e_ = rg.y - a0; }
+        };
+        if (my_tiles > 0) tile_rows(0, r0, r1, gs, ge);
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int r0 = p.tile_row0[tile], r1 = p.tile_row0[tile + 1];
             const int row = r0 + i;
             const bool valid = row < r1;
-            int gs = 0, ge = 0;                                // this row's graph as a column range of the tile
-            if (valid) { const int2 rg = p.row_range[row]; gs = rg.x - r0; ge = rg.y - r0; }
             mbar_wait(&s_full, it & 1);
             tc_fence_after();
             if (ew == 0 && lane == 0) SEG_STAMP(2);
+            uint32_t ra[32], rb[32];
+            tmem_ld32(tmemS + tlane + 64 * half, ra);
+            tmem_ld32(tmemS + tlane + 64 * half + 32, rb);
+            tmem_ld_wait32(ra);
+            tmem_ld_wait32(rb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free);              // the row's scores are in registers: Sc may be overwritten
             float den = 0.f;
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmemS + tlane + 64 * half + c0, r);
-                tmem_ld_wait32(r);
-                if (c0 == 32) {                                // the row's scores are in registers: Sc may be overwritten
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_free);
-                }
-#pragma unroll
-                for (int jj = 0; jj < 32; jj += 8) {
+            for (int g8 = 0; g8 < 8; ++g8) {
+                const int jb = 64 * half + 8 * g8;
+                const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, g8);          // K block = column half
+                if (jb + 8 <= gs || jb >= ge) {
+                    sts128(Whi + off, make_uint4(0u, 0u, 0u, 0u));
+                    sts128(Wlo + off, make_uint4(0u, 0u, 0u, 0u));
+                } else {
                     float w[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int j = 64 * half + c0 + jj + e;
-                        w[e] = (j >= gs && j < ge) ? fmaf(c, __uint_as_float(r[jj + e]), 1.f) : 0.f;
+                        const int j = jb + e;
+                        const uint32_t sc = g8 < 4 ? ra[8 * g8 + e] : rb[8 * (g8 - 4) + e];
+                        w[e] = (j >= gs && j < ge) ? fmaf(c, __uint_as_float(sc), 1.f) : 0.f;
                         den += w[e];
                     }
                     uint4 hi, lo;
                     split8(w, hi, lo);
-                    const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, (c0 + jj) >> 3);      // K block = column half
                     sts128(Whi + off, hi);
                     sts128(Wlo + off, lo);
                 }
@@ -209,42 +221,40 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             if (lane == 0) mbar_arrive(&w_full);
             if (ew == 0 && lane == 0) SEG_STAMP(3);
             den_s[it & 1][half][i] = den;
-            seg_bar_sync(1 + quad, 64);                      // the two column halves of the rows 32 quad .. +31
+            int nr0 = 0, nr1 = 0, ngs = 0, nge = 0;
+            if (it + 1 < my_tiles) tile_rows(it + 1, nr0, nr1, ngs, nge);     // in flight while the second product runs
+            seg_bar_sync(1 + quad, 64);                        // the two column halves of the rows 32 quad .. +31
             const float inv = 1.f / (den_s[it & 1][0][i] + den_s[it & 1][1][i]);
             mbar_wait(&o_full, it & 1);
             tc_fence_after();
             if (ew == 0 && lane == 0) SEG_STAMP(4);
-            float* dst = p.out + (int64_t)row * kDim + 32 * half;
+            tmem_ld32(tmemO + tlane + 32 * half, ra);
+            tmem_ld32(tmemO + tlane + kDim + 32 * half, rb);
+            tmem_ld_wait32(ra);
+            tmem_ld_wait32(rb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free);
+            if (valid) {
+                float* dst = p.out + (int64_t)row * kDim + 32 * half;
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                uint32_t a[16], b[16];
-                tmem_ld16(tmemO + tlane + 32 * half + c0, a);
-                tmem_ld16(tmemO + tlane + kDim + 32 * half + c0, b);
-                tmem_ld_wait16(a);
-                tmem_ld_wait16(b);
-                if (c0 == 16) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&o_free);
-                }
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 o;
-                        o.x = (__uint_as_float(a[j]) + __uint_as_float(b[j])) * inv;
-                        o.y = (__uint_as_float(a[j + 1]) + __uint_as_float(b[j + 1])) * inv;
-                        o.z = (__uint_as_float(a[j + 2]) + __uint_as_float(b[j + 2])) * inv;
-                        o.w = (__uint_as_float(a[j + 3]) + __uint_as_float(b[j + 3])) * inv;
-                        *reinterpret_cast<float4*>(dst + c0 + j) = o;
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = (__uint_as_float(ra[j]) + __uint_as_float(rb[j])) * inv;
+                    o.y = (__uint_as_float(ra[j + 1]) + __uint_as_float(rb[j + 1])) * inv;
+                    o.z = (__uint_as_float(ra[j + 2]) + __uint_as_float(rb[j + 2])) * inv;
+                    o.w = (__uint_as_float(ra[j + 3]) + __uint_as_float(rb[j + 3])) * inv;
+                    *reinterpret_cast<float4*>(dst + j) = o;
                 }
             }
             if (ew == 0 && lane == 0) SEG_STAMP(5);
+            r0 = nr0; r1 = nr1; gs = ngs; ge = nge;
         }
     } else if (lane == 0) {
         // ===== MMA issuer
         const uint32_t idS = make_idesc(kST, kST, 0, 0);          // Sc = Q K^T: both operands K-major
         const uint32_t idO = make_idesc(kST, 2 * kDim, 0, 1);     // [W Vhi | W Vlo]: A = W K-major, B = V MN-major (hi | lo: two 64-blocks, LBO apart)
+        const uint32_t idOl = make_idesc(kST, kDim, 0, 1);        // N = 64: the hi block of V only
         for (int it = 0; it < my_tiles; ++it) {
             if (it > 0) mbar_wait(&s_free, (it - 1) & 1);
             mbar_wait(&qk_full, it & 1);
@@ -268,8 +278,8 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
                 const uint32_t wo = (uint32_t)((ks >> 2) * kSOp + (ks & 3) * 32);
                 const uint64_t whi = make_desc(Whi + wo, kKmajLBO, kKmajSBO), wlo = make_desc(Wlo + wo, kKmajLBO, kKmajSBO);
                 const uint64_t vb = make_desc(Vop + ks * 2048, kSOp, 1024);
-                umma(tmemO, whi, vb, idO, ks > 0 ? 1u : 0u);
-                umma(tmemO, wlo, vb, idO, 1u);
+                umma(tmemO, whi, vb, idO, ks > 0 ? 1u : 0u);      // Whi [Vhi | Vlo]
+                umma(tmemO, wlo, vb, idOl, 1u);                    // Wlo Vhi onto the first 64 columns (Wlo Vlo is below fp32 resolution)
             }
             umma_commit(&o_full);
             SEG_STAMP(7);
