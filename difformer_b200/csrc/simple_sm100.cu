@@ -21,9 +21,10 @@
 //   warps 0-7 converters: LDS.128 -> bf16 hi/lo split -> swizzled MN-major UMMA operand ring (+ sum k, sum v, sum k^2, sum q^2)
 //   warp 9   MMA issuer (one thread): M = N = 128 (two 64-wide blocks: two heads, or two node halves when H = 1), K = 16
 //   tail     TMEM -> per-CTA record, flag publish, fused deterministic cross-CTA (and cross-GPU) slice sum, pass-2 operand image
-// Pass 2 (apply_tc_kernel<MODE,H>, 13 warps, persistent over 128-row tiles):
+// Pass 2 (apply_tc_kernel<H,SHARED>, 13 warps, persistent over 128-row tiles):
 //   warps 0-7 Q producers (LDG.256 -> bf16 hi/lo -> K-major SW128), warps 8-11 epilogue (tcgen05.ld -> (c acc + u)/(c qz + N)
-//   -> swizzled staging -> TMA tensor store; mode 1 = fused layer epilogue), warp 12 MMA issuer.
+//   -> swizzled staging -> TMA tensor store), warp 12 MMA issuer.
+// Pass 2 with the layer epilogue (layer_tc_kernel<H,SHARED>, 17 warps): the same with 8 epilogue warps, two threads per output row.
 #include <stdlib.h>
 
 #include <atomic>
@@ -440,7 +441,7 @@ struct ApplyTcArgs {
 
 // SHARED: the H heads of a tile use ONE A operand (q_hs == 0: the projected form, A = the layer input x): a stage is a tile, loaded and
 // split once, and the issuer runs the H head MMAs (N = 80 each, their own accumulator slots) off it.
-template <int MODE, int H, bool SHARED = false>
+template <int H, bool SHARED = false>
 __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_constant__ ApplyTcArgs p, const __grid_constant__ CUtensorMap out_map) {
     using G = Geo<H>;
     extern __shared__ uint8_t smem_raw[];
@@ -580,44 +581,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
         const int ew = warp - 8;
         const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
         const uint64_t pol = policy_evict_first();
-        float hs[MODE == 1 ? kDim : 1];
         for (int sc = 0; sc < nsc; ++sc) {
             const int64_t tile = tile_of(sc);
             const int h = sc % H, slot = sc % kNAcc;
-            if (MODE == 1 && h == 0) {
-                // the row starts as the sum of its scaled addends (gcn term, x_0, residual): their loads are in flight while the
-                // tile's first MMA completes; the heads then accumulate on top (attn_scale folded into 1/den)
-                const int64_t row = tile * kTile2 + ew * 32 + lane;
-#pragma unroll
-                for (int i = 0; i < kDim; ++i) hs[i] = 0.f;
-                if (row < p.N) {
-                    for (int a = 0; a < p.ep.n_add; ++a) {
-                        const float s = p.ep.add_scale[a];
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {       // 8 x 16-byte loads in flight per batch
-                            float4 x[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = ldg4(p.ep.add[a] + row * kDim + 32 * half + 4 * j);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float* o = hs + 32 * half + 4 * j;
-                                o[0] = fmaf(s, x[j].x, o[0]); o[1] = fmaf(s, x[j].y, o[1]); o[2] = fmaf(s, x[j].z, o[2]); o[3] = fmaf(s, x[j].w, o[3]);
-                            }
-                        }
-                    }
-                }
-            }
             mbar_wait(&tfull[slot], (sc / kNAcc) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + slot * kAccCols;
             uint32_t qz_bits = tmem_ld1(taddr + kDim);            // column 64 = q . z
             tmem_ld_wait1(qz_bits);
-            float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.nvec != nullptr ? __ldg(p.nvec + h) : p.n_total));   // one division per (row, head)
-            if (MODE == 1) inv_den *= p.ep.attn_scale;
-            if (MODE == 0 || h == H - 1) {        // staging is about to be rewritten: previous TMA reads must be done
-                if (lane == 0) tma_wait_read0();
-                __syncwarp();
-            }
+            const float inv_den = 1.f / (fmaf(__uint_as_float(qz_bits), cscale, p.nvec != nullptr ? __ldg(p.nvec + h) : p.n_total));   // one division per (row, head)
+            if (lane == 0) tma_wait_read0();      // staging is about to be rewritten: previous TMA reads must be done
+            __syncwarp();
 #pragma unroll
             for (int c0 = 0; c0 < kDim; c0 += 32) {
                 uint32_t r[32];
@@ -636,96 +610,23 @@ __global__ void __launch_bounds__(kThreadsTC, 1) apply_tc_kernel(const __grid_co
                     o.y = fmaf(__uint_as_float(r[j + 1]), cscale, u4.y) * inv_den;
                     o.z = fmaf(__uint_as_float(r[j + 2]), cscale, u4.z) * inv_den;
                     o.w = fmaf(__uint_as_float(r[j + 3]), cscale, u4.w) * inv_den;
-                    if (MODE == 0) {
-                        sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
-                               make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
-                    } else {
-                        hs[c0 + j] += o.x; hs[c0 + j + 1] += o.y; hs[c0 + j + 2] += o.z; hs[c0 + j + 3] += o.w;
-                    }
+                    sts128(obox + (c0 >> 5) * kOutBox + sw128(lane, j >> 2),
+                           make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
                 }
             }
-            if (MODE == 1 && h == H - 1) {
-                const int64_t row = tile * kTile2 + ew * 32 + lane;
-                const bool ok = row < p.N;
-                // layer epilogue on the thread's whole output row (64 values in registers: head mean + addends), then --
-                // optionally -- the gcn gather, the LayerNorm that follows the layer (difformer.py:202-203) and a ReLU
-                if (p.ep.gcn_rowptr != nullptr && ok) {
-                    // gcn_conv term (difformer.py:63-79) gathered here: this thread's row of the normalised adjacency times the
-                    // head-meaned values.  The source rows (256 B each) come from L2; two slots (32 x 16-byte loads) in flight.
-                    const int beg = __ldg(p.ep.gcn_rowptr + row), end = __ldg(p.ep.gcn_rowptr + row + 1);
-                    int s_ = beg;
-                    for (; s_ + 1 < end; s_ += 2) {
-                        const float w0 = __ldg(p.ep.gcn_val + s_) * p.ep.gcn_scale, w1 = __ldg(p.ep.gcn_val + s_ + 1) * p.ep.gcn_scale;
-                        const float* x0 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_) * kDim;
-                        const float* x1 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_ + 1) * kDim;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            float4 a[8], b[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) { a[j] = ldg4(x0 + 32 * half + 4 * j); b[j] = ldg4(x1 + 32 * half + 4 * j); }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float* o = hs + 32 * half + 4 * j;
-                                o[0] = fmaf(w0, a[j].x, o[0]); o[1] = fmaf(w0, a[j].y, o[1]); o[2] = fmaf(w0, a[j].z, o[2]); o[3] = fmaf(w0, a[j].w, o[3]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float* o = hs + 32 * half + 4 * j;
-                                o[0] = fmaf(w1, b[j].x, o[0]); o[1] = fmaf(w1, b[j].y, o[1]); o[2] = fmaf(w1, b[j].z, o[2]); o[3] = fmaf(w1, b[j].w, o[3]);
-                            }
-                        }
-                    }
-                    if (s_ < end) {
-                        const float w0 = __ldg(p.ep.gcn_val + s_) * p.ep.gcn_scale;
-                        const float* x0 = p.ep.gcn_x + (int64_t)__ldg(p.ep.gcn_idx + s_) * kDim;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float4 a = ldg4(x0 + 4 * j);
-                            hs[4 * j] = fmaf(w0, a.x, hs[4 * j]); hs[4 * j + 1] = fmaf(w0, a.y, hs[4 * j + 1]);
-                            hs[4 * j + 2] = fmaf(w0, a.z, hs[4 * j + 2]); hs[4 * j + 3] = fmaf(w0, a.w, hs[4 * j + 3]);
-                        }
-                    }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int col = h * kDim;
+                const int row0 = (int)(tile * kTile2) + ew * 32;
+                if (p.store_hint) {
+                    tma_store_2d_hint(&out_map, obox, col, row0, pol);
+                    tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
+                } else {
+                    tma_store_2d(&out_map, obox, col, row0);
+                    tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
                 }
-                if (p.ep.ln_weight != nullptr) {
-                    float mean = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kDim; ++j) mean += hs[j];
-                    mean *= 1.f / kDim;
-                    float var = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kDim; ++j) { const float d_ = hs[j] - mean; var = fmaf(d_, d_, var); }
-                    const float rstd = rsqrtf(var * (1.f / kDim) + p.ep.ln_eps);
-#pragma unroll
-                    for (int j = 0; j < kDim; j += 4) {
-                        const float4 w4 = ldg4(p.ep.ln_weight + j), b4 = ldg4(p.ep.ln_bias + j);
-                        hs[j] = fmaf((hs[j] - mean) * rstd, w4.x, b4.x); hs[j + 1] = fmaf((hs[j + 1] - mean) * rstd, w4.y, b4.y);
-                        hs[j + 2] = fmaf((hs[j + 2] - mean) * rstd, w4.z, b4.z); hs[j + 3] = fmaf((hs[j + 3] - mean) * rstd, w4.w, b4.w);
-                    }
-                }
-                if (p.ep.relu) {
-#pragma unroll
-                    for (int j = 0; j < kDim; ++j) hs[j] = fmaxf(hs[j], 0.f);
-                }
-#pragma unroll
-                for (int j = 0; j < kDim; j += 4)
-                    sts128(obox + (j >> 5) * kOutBox + sw128(lane, (j & 31) >> 2),
-                           make_uint4(__float_as_uint(hs[j]), __float_as_uint(hs[j + 1]), __float_as_uint(hs[j + 2]), __float_as_uint(hs[j + 3])));
-            }
-            if (MODE == 0 || h == H - 1) {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    const int col = MODE == 0 ? h * kDim : 0;
-                    const int row0 = (int)(tile * kTile2) + ew * 32;
-                    if (p.store_hint) {
-                        tma_store_2d_hint(&out_map, obox, col, row0, pol);
-                        tma_store_2d_hint(&out_map, obox + kOutBox, col + 32, row0, pol);
-                    } else {
-                        tma_store_2d(&out_map, obox, col, row0);
-                        tma_store_2d(&out_map, obox + kOutBox, col + 32, row0);
-                    }
-                    tma_commit();
-                }
+                tma_commit();
             }
             if (sc == H - 1 && ew == 0 && lane == 0) DIF_STAMP_ANY(p.dbg, 6);
         }
@@ -1542,7 +1443,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) simple_fused_kernel(const __gri
         for (int i = te; i < H * kDim; i += 128) us[i] = __ldcg(a.partials + P::offU + i);
         const float cscale = 1.f / (sqrtf(__ldcg(a.partials + P::offSq)) * sqrtf(__ldcg(a.partials + P::offSq + 1)));
         bar_sync_named(2, 128);
-        // =================== pass 2: epilogue (see apply_tc_kernel, MODE 0) ===================
+        // =================== pass 2: epilogue (see apply_tc_kernel) ===================
         const uint32_t obox = smem_u32(ostage) + ew * 2 * kOutBox;
         const uint64_t pol = policy_evict_first();
         float inv_den = 0.f;
@@ -1802,14 +1703,14 @@ int simple_reduce_tc(const float* q, const float* k, const float* v, int64_t N, 
     return DIF_OK;
 }
 
-template <int MODE, int H, bool SHARED = false>
+template <int H, bool SHARED = false>
 static int launch_apply(const ApplyTcArgs& a, const CUtensorMap& map, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<MODE, H, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
+        DIF_CUDA_OK(cudaFuncSetAttribute(apply_tc_kernel<H, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<H>()));
         attr_set = true;
     }
-    apply_tc_kernel<MODE, H, SHARED><<<grid, kThreadsTC, smem2_bytes<H>(), st>>>(a, map);
+    apply_tc_kernel<H, SHARED><<<grid, kThreadsTC, smem2_bytes<H>(), st>>>(a, map);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }
@@ -1853,18 +1754,16 @@ int simple_apply_tc(const float* q, const float* partials, const void* prepared,
     CUtensorMap map;
     int rc = make_out_map(&map, out, N, a.ep.mode == 0 ? (int64_t)H * kDim : (int64_t)kDim);
     if (rc) return rc;
-#define DIF_P2(MODE)                                                                                                  \
-    (H == 4 ? launch_apply<MODE, 4>(a, map, grid, st) : H == 2 ? launch_apply<MODE, 2>(a, map, grid, st) : launch_apply<MODE, 1>(a, map, grid, st))
-#define DIF_P2S(MODE) (H == 4 ? launch_apply<MODE, 4, true>(a, map, grid, st) : launch_apply<MODE, 2, true>(a, map, grid, st))
-    static const int share = env_int("DIF_TC_P2_SHARED_A", 1), layer17 = env_int("DIF_TC_LAYER_KERNEL", 1);
-    const bool shared_a = a.q_hs == 0 && H > 1 && share;
-    if (a.ep.mode == 1 && layer17) {         // two threads per output row (layer_tc_kernel); DIF_TC_LAYER_KERNEL=0: apply_tc_kernel<1,...>
+    static const int share = env_int("DIF_TC_P2_SHARED_A", 1);
+    const bool shared_a = a.q_hs == 0 && H > 1 && share;            // one A operand for the H heads of a tile (projected form)
+    if (a.ep.mode == 1) {       // layer epilogue: two threads per output row (layer_tc_kernel)
         rc = shared_a ? (H == 4 ? launch_layer<4, true>(a, map, grid, st) : launch_layer<2, true>(a, map, grid, st))
                       : (H == 4 ? launch_layer<4, false>(a, map, grid, st) : H == 2 ? launch_layer<2, false>(a, map, grid, st) : launch_layer<1, false>(a, map, grid, st));
-    } else if (shared_a) rc = a.ep.mode == 0 ? DIF_P2S(0) : DIF_P2S(1);   // one A operand for the H heads of a tile
-    else rc = a.ep.mode == 0 ? DIF_P2(0) : DIF_P2(1);
-#undef DIF_P2S
-#undef DIF_P2
+    } else if (shared_a) {
+        rc = H == 4 ? launch_apply<4, true>(a, map, grid, st) : launch_apply<2, true>(a, map, grid, st);
+    } else {
+        rc = H == 4 ? launch_apply<4>(a, map, grid, st) : H == 2 ? launch_apply<2>(a, map, grid, st) : launch_apply<1>(a, map, grid, st);
+    }
     if (rc) return rc;
     dbg_report("apply_tc", a.dbg, grid);
     return DIF_OK;

@@ -40,10 +40,19 @@ for _ in range(reps):
     part, prep = ops.simple_partials(q, k, v, with_prepared=True, vbar=vb_)
     g = ops.spmm(csr, vb_.view(n, 1, d)).view(n, d)                    # spmm_kernel
     ep = ops.make_epilogue(0.5 / h, [(g, 0.5), (prev, 0.5)], layer_norm=(lnw, lnb, 1e-5))
-    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # apply_tc_kernel<1, 4> (gcn as an addend)
+    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # layer_tc_kernel<4, false> (gcn as an addend)
     ep = ops.make_epilogue(0.5 / h, [(prev, 0.5)], layer_norm=(lnw, lnb, 1e-5), gcn=(csr, vb_, 0.5))
-    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # apply_tc_kernel<1, 4> with the gcn gather in the epilogue
+    ops.simple_apply(q, part, float(n), h, d, ep, prepared=prep)       # layer_tc_kernel<4, false> with the gcn gather in the epilogue
     ops.spmm(csr, v)                                                   # spmm_kernel, all heads
+# whole layer from x with the projections folded into the propagation
+from difformer_b200 import module as M_
+torch.manual_seed(11)
+conv = difformer.DIFFormerConv(d, d, num_heads=h, kernel="simple", use_graph=True, use_weight=True).to(dev)
+ln = torch.nn.LayerNorm(d).to(dev)
+x = torch.randn(n, d, device=dev)
+for _ in range(reps):
+    with torch.no_grad():                                              # reduce_tma_kernel<1, false> (Gram mode), project_head_kernel,
+        M_._conv_forward(conv, x, x, ei, None, x, False, residual=(0.5, prev), layer_norm=ln)   # project_finish_kernel, apply_tc_kernel<1, false>, spmm_kernel, layer_tc_kernel<4, true>
 # sigmoid: N = 10 000 (main-batch.py mini-batch) forward + backward on tcgen05, then the FFMA kernels
 n2 = 10000
 q2, k2, v2 = (t.to(dev) for t in O.synthetic_qkv(n2, 1, 64, seed=2))
@@ -64,8 +73,13 @@ qs, ks, vs = (t.to(dev).requires_grad_(True) for t in O.synthetic_qkv(tot, 1, 64
 nn_d = nn_.to(dev)
 for _ in range(reps):
     qs.grad = ks.grad = vs.grad = None
-    o = ops.segmented_full_attention(qs, ks, vs, "simple", nn_d)       # seg_fwd_warp_kernel
+    o = ops.segmented_full_attention(qs, ks, vs, "simple", nn_d)       # seg_fwd_tc_kernel (tensor cores)
     o.backward(torch.ones_like(o))                                     # seg_bwd_warp_kernel, seg_bwd_fixup_kernel
+ops.set_segmented_impl("generic")
+for _ in range(reps):
+    with torch.no_grad():
+        ops.segmented_full_attention(qs, ks, vs, "simple", nn_d)       # seg_fwd_warp_kernel
+ops.set_segmented_impl("auto")
 # generic FFMA 'simple' (H = 3: no tensor-core shape)
 q3, k3, v3 = (t.to(dev) for t in O.synthetic_qkv(40000, 3, 32, seed=7))
 for _ in range(reps):
