@@ -52,6 +52,7 @@ SIGNATURES = {
     "dif_segmented_workspace_bytes": (c_i64, [c_i32]),
     "dif_segmented_plan_bytes": (c_i64, [c_i64, c_i32]),
     "dif_segmented_plan_build": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    "dif_segmented_simple_bwd_tc": (c_i32, [c_vp] * 6 + [c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "dif_segmented_simple_fwd_tc": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "dif_sigmoid_set_impl": (c_i32, [c_i32]),
     "dif_sigmoid_fwd_workspace_bytes": (c_i64, [c_i64, c_i64, c_i32, c_i32, c_i32, c_i32]),

@@ -179,3 +179,17 @@ extern "C" int dif_segmented_simple_fwd_tc(const float* q, const float* k, const
     DIF_REQUIRE(plan_bytes >= need, DIF_EARG, "segmented_fwd(tcgen05): plan buffer too small");
     return segmented_fwd_tc(q, k, v, plan, N, max_nodes, norms, out, (cudaStream_t)stream);
 }
+
+extern "C" int dif_segmented_simple_bwd_tc(const float* q, const float* k, const float* v, const float* g, const float* out, const void* plan,
+                                           int64_t plan_bytes, const float* norms, int64_t N, int max_nodes, int32_t B, float* dq, float* dk,
+                                           float* dv, void* workspace, int64_t workspace_bytes, int phase, void* stream) {
+    DIF_REQUIRE(q && k && v && g && out && plan && norms && dq && dk && dv && workspace, DIF_EARG, "segmented_bwd(tcgen05): null pointer");
+    DIF_REQUIRE(phase >= 0 && phase <= 2 && B >= 1, DIF_EARG, "segmented_bwd(tcgen05): phase %d, B %d", phase, (int)B);
+    const int64_t need = segmented_plan_bytes(N, max_nodes);
+    DIF_REQUIRE(need > 0, DIF_EUNSUPPORTED, "segmented_bwd(tcgen05): needs 1 <= max_nodes <= 128 and 1 <= N < 2^31");
+    DIF_REQUIRE(plan_bytes >= need, DIF_EARG, "segmented_bwd(tcgen05): plan buffer too small");
+    DIF_REQUIRE(workspace_bytes >= dif_segmented_workspace_bytes(B) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, DIF_EARG,
+                "segmented_bwd(tcgen05): workspace too small (dif_segmented_workspace_bytes) or misaligned");
+    float* scal = (float*)workspace + 2 * (int64_t)B;          // same place as dif_segmented_simple_bwd_phase: the caller all-reduces it between phases
+    return segmented_bwd_tc(q, k, v, g, out, plan, N, max_nodes, norms, dq, dk, dv, scal + 2, scal, phase, (cudaStream_t)stream);
+}

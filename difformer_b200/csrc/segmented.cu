@@ -748,7 +748,7 @@ int seg_smem(K kernel, size_t bytes) {
 using namespace dif;
 
 extern "C" int64_t dif_segmented_workspace_bytes(int32_t B) {
-    const int64_t n = (int64_t)(B > kSumBlocks ? B : kSumBlocks) * 2 + 2;
+    const int64_t n = (int64_t)(B > kSumBlocks ? B : kSumBlocks) * 2 + 2 + 2 * 512;     // + per-CTA shares of the tensor-core backward
     return n * (int64_t)sizeof(float);
 }
 

@@ -291,6 +291,328 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
     if (warp == 16) tmem_dealloc(tmem, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Backward of the tiled form (same plan, same tiles).  With W = mask o (1 + c S), den = W 1, out = W V / den and G = dL/dout:
+//     dV  = W'^T G,   W' = diag(1/den) W
+//     dW  = mask o (diag(1/den) G V^T + dden 1^T),   dden_i = -(g_i . out_i) / den_i
+//     dS  = c dW,     dQ' = dS K,   dK' = dS^T Q,    t = sum dW o (c S)    (c = 1/(|Q||K|) is global: dQ = dQ' - Q t/|Q|^2, dK alike,
+//                                                     applied by seg_fixup_rows_kernel once t has been summed over the batch)
+// Per tile: [S = Q K^T | P = G V^T] -> pass 1 of the eight weight warps writes W' (bf16 hi/lo, K-major) -> dV = W'^T G (W' read as the
+// MN-major A operand) -> pass 2 re-reads S and P from tensor memory and overwrites the same buffer with dS -> dQ' = dS K and
+// dK' = dS^T Q -> the three 64-column accumulators are stored.  Tensor memory: S | P | dV | dQ | dK = 448 columns.
+struct SegBwdTcArgs {
+    const float *q, *k, *v, *g, *out;
+    const int2* row_range;
+    const int* tile_row0;
+    int ntiles;
+    const float* norms;
+    float *dq, *dk, *dv;
+    float* part;                         // per-CTA share of t: part[2 cta] = part[2 cta + 1]
+};
+
+constexpr int kSegBwdSmem = 4 * 2 * kSOp + 4 * kSOp + 1024;     // Q, K, V, G (hi | lo) + the W' / dS buffer (hi: 2 K blocks, lo: 2 K blocks)
+
+__global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __grid_constant__ SegBwdTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t Qop = smem_u32(base), Kop = Qop + 2 * kSOp, Vop = Kop + 2 * kSOp, Gop = Vop + 2 * kSOp, Xhi = Gop + 2 * kSOp, Xlo = Xhi + 2 * kSOp;
+    __shared__ uint64_t in_full, sp_full, x1_full, dv_full, x2_full, c_full, e_free;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float den_s[2][2][kST], gdo_s[2][2][kST];      // [tile parity][column half][row]: row sums of W, g . out
+    __shared__ float t_red[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = (int)blockIdx.x < p.ntiles ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        mbar_init(&in_full, 8); mbar_init(&x1_full, 8); mbar_init(&x2_full, 8); mbar_init(&e_free, 8);
+        mbar_init(&sp_full, 1); mbar_init(&dv_full, 1); mbar_init(&c_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tmS = tmem, tmP = tmem + 128, tmDV = tmem + 256, tmDQ = tmem + 320, tmDK = tmem + 384;
+
+    if (warp < 8) {
+        // ===== producers.  V is free once S | P of the previous tile are complete, G once its dV is, Q and K once its dQ | dK are.
+        // Two register sets: V, G of the next tile are requested as soon as this tile's operands are published.
+        float xa[4][8], xb[4][8];
+        auto rows = [&](int it_, int64_t& a0, int64_t& a1) {
+            const int tile = blockIdx.x + it_ * gridDim.x;
+            a0 = p.tile_row0[tile];
+            a1 = p.tile_row0[tile + 1];
+        };
+        auto l2_ahead = [&](int it_) {
+            if (tid != 0 || it_ >= my_tiles) return;
+            int64_t a0, a1;
+            rows(it_, a0, a1);
+            if (a1 <= a0) return;
+            const uint32_t bytes = (uint32_t)((a1 - a0) * kDim * 4);
+            prefetch_l2(p.q + a0 * kDim, bytes); prefetch_l2(p.k + a0 * kDim, bytes);
+            prefetch_l2(p.v + a0 * kDim, bytes); prefetch_l2(p.g + a0 * kDim, bytes);
+        };
+        int64_t r0 = 0, r1 = 0;
+        if (my_tiles > 0) {
+            rows(0, r0, r1);
+            seg_load(p.v, r0, r1, tid, xa);
+            seg_load(p.g, r0, r1, tid, xb);
+            l2_ahead(1);
+        }
+        for (int it = 0; it < my_tiles; ++it) {
+            if (it > 0) mbar_wait(&sp_full, (it - 1) & 1);
+            seg_store(Vop, tid, xa);
+            if (it > 0) mbar_wait(&dv_full, (it - 1) & 1);
+            seg_store(Gop, tid, xb);
+            seg_load(p.q, r0, r1, tid, xa);
+            seg_load(p.k, r0, r1, tid, xb);
+            l2_ahead(it + 2);
+            if (it > 0) mbar_wait(&c_full, (it - 1) & 1);
+            seg_store(Qop, tid, xa);
+            seg_store(Kop, tid, xb);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&in_full);
+            if (it + 1 < my_tiles) {
+                rows(it + 1, r0, r1);
+                seg_load(p.v, r0, r1, tid, xa);
+                seg_load(p.g, r0, r1, tid, xb);
+            }
+        }
+    } else if (warp < 16) {
+        // ===== weight passes + epilogue: thread = (tile row i, column half)
+        const int ew = warp - 8, quad = ew & 3, half = ew >> 2;
+        const int i = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        const float c = 1.f / (sqrtf(p.norms[0]) * sqrtf(p.norms[1]));
+        int r0 = 0, r1 = 0, gs = 0, ge = 0;
+        float gdo = 0.f;                                       // this thread's half of g_i . out_i
+        auto tile_rows = [&](int it_, int& a0, int& a1, int& s_, int& e_, float& gd_) {
+            const int tile = blockIdx.x + it_ * gridDim.x;
+            a0 = p.tile_row0[tile];
+            a1 = p.tile_row0[tile + 1];
+            s_ = e_ = 0;
+            gd_ = 0.f;
+            if (a0 + i < a1) {
+                const int2 rg = p.row_range[a0 + i];
+                s_ = rg.x - a0; e_ = rg.y - a0;
+                const float* gp = p.g + (int64_t)(a0 + i) * kDim + 32 * half;
+                const float* op = p.out + (int64_t)(a0 + i) * kDim + 32 * half;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 a = ldg4(gp + 4 * j), b = ldg4(op + 4 * j);
+                    gd_ = fmaf(a.x, b.x, gd_); gd_ = fmaf(a.y, b.y, gd_); gd_ = fmaf(a.z, b.z, gd_); gd_ = fmaf(a.w, b.w, gd_);
+                }
+            }
+        };
+        if (my_tiles > 0) tile_rows(0, r0, r1, gs, ge, gdo);
+        float t_acc = 0.f;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int row = r0 + i;
+            const bool valid = row < r1;
+            // ---- pass 1: W' = diag(1/den) mask o (1 + c S)
+            mbar_wait(&sp_full, it & 1);
+            tc_fence_after();
+            uint32_t ra[32], rb[32];
+            tmem_ld32(tmS + tlane + 64 * half, ra);
+            tmem_ld32(tmS + tlane + 64 * half + 32, rb);
+            tmem_ld_wait32(ra);
+            tmem_ld_wait32(rb);
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int col = 64 * half + j;
+                uint32_t& x = j < 32 ? ra[j] : rb[j - 32];
+                const float w = (col >= gs && col < ge) ? fmaf(c, __uint_as_float(x), 1.f) : 0.f;
+                den += w;
+                x = __float_as_uint(w);
+            }
+            den_s[it & 1][half][i] = den;
+            gdo_s[it & 1][half][i] = gdo;
+            seg_bar_sync(1 + quad, 64);
+            const float inv = valid ? 1.f / (den_s[it & 1][0][i] + den_s[it & 1][1][i]) : 0.f;
+            const float dden = -(gdo_s[it & 1][0][i] + gdo_s[it & 1][1][i]) * inv;
+#pragma unroll
+            for (int g8 = 0; g8 < 8; ++g8) {
+                const int jb = 64 * half + 8 * g8;
+                const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, g8);
+                if (jb + 8 <= gs || jb >= ge) {
+                    sts128(Xhi + off, make_uint4(0u, 0u, 0u, 0u));
+                    sts128(Xlo + off, make_uint4(0u, 0u, 0u, 0u));
+                } else {
+                    float w[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(g8 < 4 ? ra[8 * g8 + e] : rb[8 * (g8 - 4) + e]) * inv;
+                    uint4 hi, lo;
+                    split8(w, hi, lo);
+                    sts128(Xhi + off, hi);
+                    sts128(Xlo + off, lo);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x1_full);
+            // ---- pass 2: dS = c mask o (P / den + dden) over the same buffer, once dV = W'^T G has read it
+            mbar_wait(&dv_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                tmem_ld32(tmS + tlane + 64 * half + 32 * ch, ra);
+                tmem_ld32(tmP + tlane + 64 * half + 32 * ch, rb);
+                tmem_ld_wait32(ra);
+                tmem_ld_wait32(rb);
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const int jb = 64 * half + 32 * ch + 8 * g8;
+                    const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, 4 * ch + g8);
+                    if (jb + 8 <= gs || jb >= ge) {
+                        sts128(Xhi + off, make_uint4(0u, 0u, 0u, 0u));
+                        sts128(Xlo + off, make_uint4(0u, 0u, 0u, 0u));
+                    } else {
+                        float ds[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int col = jb + e;
+                            const float dw = (col >= gs && col < ge) ? fmaf(__uint_as_float(rb[8 * g8 + e]), inv, dden) : 0.f;
+                            const float cdw = c * dw;
+                            t_acc = fmaf(cdw, __uint_as_float(ra[8 * g8 + e]), t_acc);
+                            ds[e] = cdw;
+                        }
+                        uint4 hi, lo;
+                        split8(ds, hi, lo);
+                        sts128(Xhi + off, hi);
+                        sts128(Xlo + off, lo);
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x2_full);
+            int nr0 = 0, nr1 = 0, ngs = 0, nge = 0;
+            float ngdo = 0.f;
+            if (it + 1 < my_tiles) tile_rows(it + 1, nr0, nr1, ngs, nge, ngdo);       // in flight while dQ | dK run
+            // ---- epilogue: dV, dQ', dK' rows
+            mbar_wait(&c_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                tmem_ld32((o == 0 ? tmDV : o == 1 ? tmDQ : tmDK) + tlane + 32 * half, ra);
+                tmem_ld_wait32(ra);
+                if (o == 2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&e_free);
+                }
+                if (valid) {
+                    float* dst = (o == 0 ? p.dv : o == 1 ? p.dq : p.dk) + (int64_t)row * kDim + 32 * half;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(dst + j) = make_uint4(ra[j], ra[j + 1], ra[j + 2], ra[j + 3]);
+                }
+            }
+            r0 = nr0; r1 = nr1; gs = ngs; ge = nge; gdo = ngdo;
+        }
+        // this CTA's share of t (fixed order: lanes, then warps)
+        for (int o = 16; o > 0; o >>= 1) t_acc += __shfl_xor_sync(0xffffffffu, t_acc, o);
+        if (lane == 0) t_red[ew] = t_acc;
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += t_red[w];
+            p.part[2 * blockIdx.x] = t;
+            p.part[2 * blockIdx.x + 1] = t;
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer
+        const uint32_t idKK = make_idesc(kST, kST, 0, 0);         // S, P: both operands K-major, N = 128
+        const uint32_t idMM = make_idesc(kST, kDim, 1, 1);        // dV = W'^T G, dK' = dS^T Q: A and B MN-major, N = 64
+        const uint32_t idKM = make_idesc(kST, kDim, 0, 1);        // dQ' = dS K: A K-major, B MN-major, N = 64
+        for (int it = 0; it < my_tiles; ++it) {
+            mbar_wait(&in_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t qhi = make_desc(Qop + ks * 32, kKmajLBO, kKmajSBO), qlo = make_desc(Qop + kSOp + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t khi = make_desc(Kop + ks * 32, kKmajLBO, kKmajSBO), klo = make_desc(Kop + kSOp + ks * 32, kKmajLBO, kKmajSBO);
+                umma(tmS, qhi, khi, idKK, ks > 0 ? 1u : 0u);
+                umma(tmS, qlo, khi, idKK, 1u);
+                umma(tmS, qhi, klo, idKK, 1u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ghi = make_desc(Gop + ks * 32, kKmajLBO, kKmajSBO), glo = make_desc(Gop + kSOp + ks * 32, kKmajLBO, kKmajSBO);
+                const uint64_t vhi = make_desc(Vop + ks * 32, kKmajLBO, kKmajSBO), vlo = make_desc(Vop + kSOp + ks * 32, kKmajLBO, kKmajSBO);
+                umma(tmP, ghi, vhi, idKK, ks > 0 ? 1u : 0u);
+                umma(tmP, glo, vhi, idKK, 1u);
+                umma(tmP, ghi, vlo, idKK, 1u);
+            }
+            umma_commit(&sp_full);
+            mbar_wait(&x1_full, it & 1);
+            if (it > 0) mbar_wait(&e_free, (it - 1) & 1);          // the previous tile's dV | dQ | dK have been read
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {          // K index = tile row i: 16 rows of the buffer / of G per step
+                const uint64_t xhi = make_desc(Xhi + ks * 2048, kSOp, 1024), xlo = make_desc(Xlo + ks * 2048, kSOp, 1024);
+                const uint64_t ghi = make_desc(Gop + ks * 2048, kSOp, 1024), glo = make_desc(Gop + kSOp + ks * 2048, kSOp, 1024);
+                umma(tmDV, xhi, ghi, idMM, ks > 0 ? 1u : 0u);
+                umma(tmDV, xlo, ghi, idMM, 1u);
+                umma(tmDV, xhi, glo, idMM, 1u);
+            }
+            umma_commit(&dv_full);
+            mbar_wait(&x2_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {          // dQ': K index = column j of dS (K-major A), rows j of K (MN-major B)
+                const uint32_t wo = (uint32_t)((ks >> 2) * kSOp + (ks & 3) * 32);
+                const uint64_t shi = make_desc(Xhi + wo, kKmajLBO, kKmajSBO), slo = make_desc(Xlo + wo, kKmajLBO, kKmajSBO);
+                const uint64_t khi = make_desc(Kop + ks * 2048, kSOp, 1024), klo = make_desc(Kop + kSOp + ks * 2048, kSOp, 1024);
+                umma(tmDQ, shi, khi, idKM, ks > 0 ? 1u : 0u);
+                umma(tmDQ, slo, khi, idKM, 1u);
+                umma(tmDQ, shi, klo, idKM, 1u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {          // dK': K index = row i of dS (MN-major A), rows i of Q (MN-major B)
+                const uint64_t shi = make_desc(Xhi + ks * 2048, kSOp, 1024), slo = make_desc(Xlo + ks * 2048, kSOp, 1024);
+                const uint64_t qhi = make_desc(Qop + ks * 2048, kSOp, 1024), qlo = make_desc(Qop + kSOp + ks * 2048, kSOp, 1024);
+                umma(tmDK, shi, qhi, idMM, ks > 0 ? 1u : 0u);
+                umma(tmDK, slo, qhi, idMM, 1u);
+                umma(tmDK, shi, qlo, idMM, 1u);
+            }
+            umma_commit(&c_full);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+// t = sum of the per-CTA shares (fixed order) -> scal[0] = scal[1]
+__global__ void seg_bwd_tc_sum_kernel(const float* __restrict__ part, int n, float* __restrict__ scal) {
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += (double)part[2 * i];
+        scal[0] = scal[1] = (float)t;
+    }
+}
+
+// dq -= q t / |Q|^2, dk -= k t / |K|^2 over all rows
+__global__ void __launch_bounds__(256) seg_fixup_rows_kernel(const float4* __restrict__ q, const float4* __restrict__ k, float4* __restrict__ dq,
+                                                             float4* __restrict__ dk, int64_t count, const float* __restrict__ scal,
+                                                             const float* __restrict__ norms) {
+    const float aq = scal[0] / norms[0], ak = scal[1] / norms[1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 q4 = q[i], k4 = k[i];
+        float4 a = dq[i], b = dk[i];
+        a.x = fmaf(-aq, q4.x, a.x); a.y = fmaf(-aq, q4.y, a.y); a.z = fmaf(-aq, q4.z, a.z); a.w = fmaf(-aq, q4.w, a.w);
+        b.x = fmaf(-ak, k4.x, b.x); b.y = fmaf(-ak, k4.y, b.y); b.z = fmaf(-ak, k4.z, b.z); b.w = fmaf(-ak, k4.w, b.w);
+        dq[i] = a;
+        dk[i] = b;
+    }
+}
+
 }  // namespace
 
 // plan = tile_row0 [ntiles + 1] (int32, padded to 16 bytes) | row_range [N] (int2)
@@ -353,6 +675,38 @@ int segmented_fwd_tc(const float* q, const float* k, const float* v, const void*
             fprintf(stderr, "\n");
         }
     }
+    return DIF_OK;
+}
+
+// phase 0: everything; phase 1: up to the batch-wide scalar t (scal[0] = scal[1], this rank's graphs) ; phase 2: the t terms only.
+// `part`: 2 floats per CTA, `scal`: 2 floats.
+int segmented_bwd_tc(const float* q, const float* k, const float* v, const float* g, const float* out, const void* plan, int64_t N, int max_nodes,
+                     const float* norms, float* dq, float* dk, float* dv, float* part, float* scal, int phase, cudaStream_t st) {
+    int S, nt;
+    int64_t off;
+    DIF_REQUIRE(!seg_plan_layout(N, max_nodes, &S, &nt, &off), DIF_EUNSUPPORTED, "segmented_bwd(tcgen05): needs 1 <= max_nodes <= 128 and N < 2^31");
+    DIF_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)g) & 31) == 0 &&
+                (((uintptr_t)out | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)plan) & 15) == 0, DIF_EARG,
+                "segmented_bwd(tcgen05): q / k / v / g must be 32-byte, out / dq / dk / dv / plan 16-byte aligned");
+    int dev = 0, sms = 148;
+    DIF_CUDA_OK(cudaGetDevice(&dev));
+    DIF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = nt < sms ? nt : sms;
+    if (phase != 2) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            DIF_CUDA_OK(cudaFuncSetAttribute(seg_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegBwdSmem));
+            attr_set = true;
+        }
+        SegBwdTcArgs a{q, k, v, g, out, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, dq, dk, dv, part};
+        seg_bwd_tc_kernel<<<grid, kSegTcThreads, kSegBwdSmem, st>>>(a);
+        DIF_LAUNCH_OK();
+        seg_bwd_tc_sum_kernel<<<1, 32, 0, st>>>(part, grid, scal);
+        DIF_LAUNCH_OK();
+    }
+    if (phase == 1) return DIF_OK;
+    seg_fixup_rows_kernel<<<sms * 8, 256, 0, st>>>((const float4*)q, (const float4*)k, (float4*)dq, (float4*)dk, N * (kDim / 4), scal, norms);
+    DIF_LAUNCH_OK();
     return DIF_OK;
 }
 

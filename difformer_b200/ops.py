@@ -694,6 +694,7 @@ class _SegmentedSimple(torch.autograd.Function):
                                                    norms.data_ptr(), N, H, Hv, M, D, out.data_ptr(), st), "dif_segmented_simple_fwd")
         ctx.save_for_backward(qs, ks, vs, seg_ptr, norms, out)
         ctx.group = group
+        ctx.lay = lay
         return out
 
     @staticmethod
@@ -707,8 +708,16 @@ class _SegmentedSimple(torch.autograd.Function):
         # graphs sharded over ranks: a private workspace (it must survive the all-reduce between the two phases)
         wsb = max(int(lib.dif_segmented_workspace_bytes(B)), 16)
         ws = torch.empty(wsb, dtype=torch.uint8, device=qs.device) if sharded else workspace(qs.device, wsb)
+        plan = _segmented_tc_plan(ctx.lay, H, Hv, M, D)
         with torch.cuda.device(qs.device):
             for phase in ((1, 2) if sharded else (0,)):
+                if plan is not None:       # the same tiles as the forward: five tensor-core products per tile
+                    check(lib.dif_segmented_simple_bwd_tc(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(), plan.data_ptr(),
+                                                          plan.numel(), norms.data_ptr(), N, ctx.lay.max_nodes, B, dq.data_ptr(), dk.data_ptr(),
+                                                          dv.data_ptr(), ws.data_ptr(), ws.numel(), phase, _stream(qs)), "dif_segmented_simple_bwd_tc")
+                    if phase == 1:
+                        _allreduce(ws.view(torch.float32)[2 * B:2 * B + 2], ctx.group)
+                    continue
                 check(lib.dif_segmented_simple_bwd_phase(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), g.data_ptr(), out.data_ptr(), seg_ptr.data_ptr(), B,
                                                          norms.data_ptr(), N, H, Hv, M, D, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                                          ws.data_ptr(), ws.numel(), phase, _stream(qs)), "dif_segmented_simple_bwd")

@@ -195,6 +195,12 @@ DIF_API int64_t dif_segmented_plan_bytes(int64_t N, int max_nodes);
 DIF_API int dif_segmented_plan_build(const int32_t* seg_ptr, int32_t B, int64_t N, int max_nodes, void* plan, int64_t plan_bytes, void* stream);
 DIF_API int dif_segmented_simple_fwd_tc(const float* q, const float* k, const float* v, const void* plan, int64_t plan_bytes,
                                 const float* norms, int64_t N, int max_nodes, float* out, void* stream);
+/* Backward on the same tiles (scores and dO V^T, weights, dV = W'^T dO, dS, dQ = dS K, dK = dS^T Q: five tensor-core products per
+ * tile).  phase / workspace as dif_segmented_simple_bwd_phase: the batch-wide scalars end up at workspace float offset 2 B after
+ * phase 1 (all-reduce them across ranks when the graphs are sharded), phase 2 applies them; phase 0 = both. */
+DIF_API int dif_segmented_simple_bwd_tc(const float* q, const float* k, const float* v, const float* g, const float* out,
+                                const void* plan, int64_t plan_bytes, const float* norms, int64_t N, int max_nodes, int32_t B,
+                                float* dq, float* dk, float* dv, void* workspace, int64_t workspace_bytes, int phase, void* stream);
 /* backward: `out` is the saved forward output, g = dL/dout; M in {16,32,64}, D <= 64.  M == D == 64: graphs of up to
  * 64 rows run one warp per graph (direct O(n^2) form), larger ones one CTA per graph; no atomics, deterministic. */
 DIF_API int dif_segmented_simple_bwd(const float* q, const float* k, const float* v, const float* g, const float* out,

@@ -671,6 +671,23 @@ def test_v2_simple_tensor_core_forward(name):
     finally:
         ops.set_segmented_impl("auto")
     assert torch.equal(got, got2)                                   # deterministic
+    # backward on the same tiles (five tensor-core products per tile) against the fp64 oracle and the warp-per-graph kernels
+    g = torch.randn(tot, 1, 64, generator=torch.Generator().manual_seed(7))
+    wq, wk, wv = O.segmented_simple_attention_backward(q.double(), k.double(), v.double(), n_nodes, g.double())
+    grads = {}
+    try:
+        for impl in ("generic", "tcgen05"):
+            ops.set_segmented_impl(impl)
+            qg, kg, vg = (t.clone().requires_grad_(True) for t in (qd, kd, vd))
+            ops.segmented_full_attention(qg, kg, vg, "simple", nd).backward(dev(g))
+            grads[impl] = (qg.grad, kg.grad, vg.grad)
+    finally:
+        ops.set_segmented_impl("auto")
+    for nm, a_, b_, w_ in zip(("dq", "dk", "dv"), grads["tcgen05"], grads["generic"], (wq, wk, wv)):
+        if float(w_.abs().max()) < 1e-12:
+            continue
+        assert O.rel_err(b_, w_) < TOL, (nm, "generic")
+        assert O.rel_err(a_, w_) < TOL, (nm, "tcgen05", O.rel_err(a_, w_))
     assert O.rel_err(ref, want) < TOL and O.rel_err(got, want) < TOL
     assert O.rel_err(got, ref) < 3e-5                               # bf16 hi + lo of the weights and of V: 16 mantissa bits
     # per-graph mean of V removed: what is left is the attention's own contribution (tiny when the batch is large: c ~ 1 / rows)
