@@ -309,6 +309,7 @@ struct SegBwdTcArgs {
     const float* norms;
     float *dq, *dk, *dv;
     float* part;                         // per-CTA share of t: part[2 cta] = part[2 cta + 1]
+    unsigned long long* dbg;             // optional timeline of CTA 0 (DIF_SEG_DEBUG=1)
 };
 
 constexpr int kSegBwdSmem = 4 * 2 * kSOp + 4 * kSOp + 1024;     // Q, K, V, G (hi | lo) + the W' / dS buffer (hi: 2 K blocks, lo: 2 K blocks)
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&in_full);
+            if (tid == 0) SEG_STAMP(0);
             if (it + 1 < my_tiles) {
                 rows(it + 1, r0, r1);
                 seg_load(p.v, r0, r1, tid, xa);
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             // ---- pass 1: W' = diag(1/den) mask o (1 + c S)
             mbar_wait(&sp_full, it & 1);
             tc_fence_after();
+            if (ew == 0 && lane == 0) SEG_STAMP(1);
             uint32_t ra[32], rb[32];
             tmem_ld32(tmS + tlane + 64 * half, ra);
             tmem_ld32(tmS + tlane + 64 * half + 32, rb);
@@ -454,9 +457,11 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&x1_full);
+            if (ew == 0 && lane == 0) SEG_STAMP(2);
             // ---- pass 2: dS = c mask o (P / den + dden) over the same buffer, once dV = W'^T G has read it
             mbar_wait(&dv_full, it & 1);
             tc_fence_after();
+            if (ew == 0 && lane == 0) SEG_STAMP(3);
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 tmem_ld32(tmS + tlane + 64 * half + 32 * ch, ra);
@@ -490,12 +495,14 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&x2_full);
+            if (ew == 0 && lane == 0) SEG_STAMP(4);
             int nr0 = 0, nr1 = 0, ngs = 0, nge = 0;
             float ngdo = 0.f;
             if (it + 1 < my_tiles) tile_rows(it + 1, nr0, nr1, ngs, nge, ngdo);       // in flight while dQ | dK run
             // ---- epilogue: dV, dQ', dK' rows
             mbar_wait(&c_full, it & 1);
             tc_fence_after();
+            if (ew == 0 && lane == 0) SEG_STAMP(5);
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
                 tmem_ld32((o == 0 ? tmDV : o == 1 ? tmDQ : tmDK) + tlane + 32 * half, ra);
@@ -512,6 +519,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
                         *reinterpret_cast<uint4*>(dst + j) = make_uint4(ra[j], ra[j + 1], ra[j + 2], ra[j + 3]);
                 }
             }
+            if (ew == 0 && lane == 0) SEG_STAMP(6);
             r0 = nr0; r1 = nr1; gs = ngs; ge = nge; gdo = ngdo;
         }
         // this CTA's share of t (fixed order: lanes, then warps)
@@ -581,6 +589,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
                 umma(tmDK, shi, qlo, idMM, 1u);
             }
             umma_commit(&c_full);
+            SEG_STAMP(7);
         }
     }
     __syncwarp();
@@ -698,9 +707,26 @@ int segmented_bwd_tc(const float* q, const float* k, const float* v, const float
             DIF_CUDA_OK(cudaFuncSetAttribute(seg_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegBwdSmem));
             attr_set = true;
         }
-        SegBwdTcArgs a{q, k, v, g, out, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, dq, dk, dv, part};
+        static unsigned long long* dbg = nullptr;
+        static const bool debug = getenv("DIF_SEG_DEBUG") && atoi(getenv("DIF_SEG_DEBUG"));
+        if (debug && !dbg) DIF_CUDA_OK(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
+        if (debug) DIF_CUDA_OK(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), st));
+        SegBwdTcArgs a{q, k, v, g, out, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, dq, dk, dv, part, debug ? dbg : nullptr};
         seg_bwd_tc_kernel<<<grid, kSegTcThreads, kSegBwdSmem, st>>>(a);
         DIF_LAUNCH_OK();
+        if (debug) {
+            unsigned long long h[64];
+            DIF_CUDA_OK(cudaStreamSynchronize(st));
+            DIF_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < 64; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+            fprintf(stderr, "[seg_bwd_tc] tile: in_full | sp_seen x1_full dv_seen x2_full c_seen epi_done | mmaC_issued (ns)\n");
+            for (int t = 0; t < 8; ++t) {
+                fprintf(stderr, "  %d:", t);
+                for (int e = 0; e < 8; ++e) fprintf(stderr, " %7lld", h[t * 8 + e] ? (long long)(h[t * 8 + e] - t0) : -1ll);
+                fprintf(stderr, "\n");
+            }
+        }
         seg_bwd_tc_sum_kernel<<<1, 32, 0, st>>>(part, grid, scal);
         DIF_LAUNCH_OK();
     }
