@@ -20,6 +20,8 @@
 #include "tc_ptx.cuh"
 
 namespace dif {
+int make_out_map(CUtensorMap* map, float* base, int64_t rows, int64_t cols);      // simple_sm100.cu: [rows, cols] fp32, box 32 x 32, 128B swizzle (cached)
+
 namespace {
 
 constexpr int kST = 128;                 // rows per tile
@@ -88,7 +90,10 @@ __device__ __forceinline__ void seg_store(uint32_t s_hi, int tid, const float (&
     }
 }
 
-__global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __grid_constant__ SegTcArgs p) {
+// Output rows leave through TMA: a warp's 32 rows x 32 columns are staged in the (by then idle) weight buffer, in the very 4 KB the warp
+// itself fills during the weight pass, and stored with one cp.async.bulk.tensor; 32 scattered 16-byte st.global per instruction cost a
+// wavefront each on the LSU that the operand warps need.  Warps whose rows straddle the end of the tile store directly.
+__global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __grid_constant__ SegTcArgs p, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t Qop = smem_u32(base), Kop = Qop + 2 * kSOp, Vop = Kop + 2 * kSOp, Whi = Vop + 2 * kSOp, Wlo = Whi + 2 * kSOp;
@@ -192,7 +197,8 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             tmem_ld_wait32(rb);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free);              // the row's scores are in registers: Sc may be overwritten
+            if (lane == 0) { mbar_arrive(&s_free); tma_wait_read0(); }      // scores in registers; the previous output store has read this warp's part of the buffer
+            __syncwarp();
             float den = 0.f;
 #pragma unroll
             for (int g8 = 0; g8 < 8; ++g8) {
@@ -235,21 +241,28 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_fwd_tc_kernel(const __gr
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_free);
-            if (valid) {
-                float* dst = p.out + (int64_t)row * kDim + 32 * half;
+            const bool whole = r0 + 32 * quad + 32 <= r1;      // warp-uniform: all 32 rows of this warp belong to the tile
+            const uint32_t box = Whi + (uint32_t)(half * kSOp + quad * 4096);
+            float* dst = p.out + (int64_t)row * kDim + 32 * half;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = (__uint_as_float(ra[j]) + __uint_as_float(rb[j])) * inv;
-                    o.y = (__uint_as_float(ra[j + 1]) + __uint_as_float(rb[j + 1])) * inv;
-                    o.z = (__uint_as_float(ra[j + 2]) + __uint_as_float(rb[j + 2])) * inv;
-                    o.w = (__uint_as_float(ra[j + 3]) + __uint_as_float(rb[j + 3])) * inv;
-                    *reinterpret_cast<float4*>(dst + j) = o;
-                }
+            for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = (__uint_as_float(ra[j]) + __uint_as_float(rb[j])) * inv;
+                o.y = (__uint_as_float(ra[j + 1]) + __uint_as_float(rb[j + 1])) * inv;
+                o.z = (__uint_as_float(ra[j + 2]) + __uint_as_float(rb[j + 2])) * inv;
+                o.w = (__uint_as_float(ra[j + 3]) + __uint_as_float(rb[j + 3])) * inv;
+                if (whole) sts128(box + sw128(lane, j >> 2), make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                else if (valid) *reinterpret_cast<float4*>(dst + j) = o;
+            }
+            if (whole) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { tma_store_2d(&out_map, box, 32 * half, r0 + 32 * quad); tma_commit(); }
             }
             if (ew == 0 && lane == 0) SEG_STAMP(5);
             r0 = nr0; r1 = nr1; gs = ngs; ge = nge;
         }
+        if (lane == 0) tma_wait_all0();                        // stores must have landed before the CTA exits
     } else if (lane == 0) {
         // ===== MMA issuer
         const uint32_t idS = make_idesc(kST, kST, 0, 0);          // Sc = Q K^T: both operands K-major
@@ -314,7 +327,8 @@ struct SegBwdTcArgs {
 
 constexpr int kSegBwdSmem = 4 * 2 * kSOp + 4 * kSOp + 1024;     // Q, K, V, G (hi | lo) + the W' / dS buffer (hi: 2 K blocks, lo: 2 K blocks)
 
-__global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __grid_constant__ SegBwdTcArgs p) {
+__global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __grid_constant__ SegBwdTcArgs p, const __grid_constant__ CUtensorMap dv_map,
+                                                                       const __grid_constant__ CUtensorMap dq_map, const __grid_constant__ CUtensorMap dk_map) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t Qop = smem_u32(base), Kop = Qop + 2 * kSOp, Vop = Kop + 2 * kSOp, Gop = Vop + 2 * kSOp, Xhi = Gop + 2 * kSOp, Xlo = Xhi + 2 * kSOp;
@@ -434,6 +448,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             }
             den_s[it & 1][half][i] = den;
             gdo_s[it & 1][half][i] = gdo;
+            if (lane == 0) tma_wait_read0();                   // the previous tile's output stores have read this warp's part of the buffer
             seg_bar_sync(1 + quad, 64);
             const float inv = valid ? 1.f / (den_s[it & 1][0][i] + den_s[it & 1][1][i]) : 0.f;
             const float dden = -(gdo_s[it & 1][0][i] + gdo_s[it & 1][1][i]) * inv;
@@ -503,6 +518,9 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             mbar_wait(&c_full, it & 1);
             tc_fence_after();
             if (ew == 0 && lane == 0) SEG_STAMP(5);
+            // rows leave through TMA, staged in this warp's own 4 KB of the (now idle) W' / dS buffer (see seg_fwd_tc_kernel)
+            const bool whole = r0 + 32 * quad + 32 <= r1;
+            const uint32_t box = Xhi + (uint32_t)(half * kSOp + quad * 4096);
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
                 tmem_ld32((o == 0 ? tmDV : o == 1 ? tmDQ : tmDK) + tlane + 32 * half, ra);
@@ -512,7 +530,17 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&e_free);
                 }
-                if (valid) {
+                if (whole) {
+                    if (o > 0) {
+                        if (lane == 0) tma_wait_read0();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) sts128(box + sw128(lane, j >> 2), make_uint4(ra[j], ra[j + 1], ra[j + 2], ra[j + 3]));
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(o == 0 ? &dv_map : o == 1 ? &dq_map : &dk_map, box, 32 * half, r0 + 32 * quad); tma_commit(); }
+                } else if (valid) {
                     float* dst = (o == 0 ? p.dv : o == 1 ? p.dq : p.dk) + (int64_t)row * kDim + 32 * half;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -522,6 +550,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             if (ew == 0 && lane == 0) SEG_STAMP(6);
             r0 = nr0; r1 = nr1; gs = ngs; ge = nge; gdo = ngdo;
         }
+        if (lane == 0) tma_wait_all0();                        // stores must have landed before the CTA exits
         // this CTA's share of t (fixed order: lanes, then warps)
         for (int o = 16; o > 0; o >>= 1) t_acc += __shfl_xor_sync(0xffffffffu, t_acc, o);
         if (lane == 0) t_red[ew] = t_acc;
@@ -669,7 +698,10 @@ int segmented_fwd_tc(const float* q, const float* k, const float* v, const void*
     if (debug && !dbg) DIF_CUDA_OK(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
     if (debug) DIF_CUDA_OK(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), st));
     SegTcArgs a{q, k, v, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, out, debug ? dbg : nullptr};
-    seg_fwd_tc_kernel<<<nt < sms ? nt : sms, kSegTcThreads, kSegTcSmem, st>>>(a);
+    CUtensorMap omap;
+    int rc = make_out_map(&omap, out, N, kDim);
+    if (rc) return rc;
+    seg_fwd_tc_kernel<<<nt < sms ? nt : sms, kSegTcThreads, kSegTcSmem, st>>>(a, omap);
     DIF_LAUNCH_OK();
     if (debug) {   // CTA 0: events per tile in ns since its first stamp: qk published, v published, scores seen, W published, O seen, epilogue done, MMA1 issued, MMA2 issued
         unsigned long long h[64];
@@ -712,7 +744,12 @@ int segmented_bwd_tc(const float* q, const float* k, const float* v, const float
         if (debug && !dbg) DIF_CUDA_OK(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
         if (debug) DIF_CUDA_OK(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), st));
         SegBwdTcArgs a{q, k, v, g, out, (const int2*)((const uint8_t*)plan + off), (const int*)plan, nt, norms, dq, dk, dv, part, debug ? dbg : nullptr};
-        seg_bwd_tc_kernel<<<grid, kSegTcThreads, kSegBwdSmem, st>>>(a);
+        CUtensorMap mv, mq, mk;
+        int rc = make_out_map(&mv, dv, N, kDim);
+        if (!rc) rc = make_out_map(&mq, dq, N, kDim);
+        if (!rc) rc = make_out_map(&mk, dk, N, kDim);
+        if (rc) return rc;
+        seg_bwd_tc_kernel<<<grid, kSegTcThreads, kSegBwdSmem, st>>>(a, mv, mq, mk);
         DIF_LAUNCH_OK();
         if (debug) {
             unsigned long long h[64];
