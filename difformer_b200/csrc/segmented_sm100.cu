@@ -428,23 +428,25 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
         for (int it = 0; it < my_tiles; ++it) {
             const int row = r0 + i;
             const bool valid = row < r1;
-            // ---- pass 1: W' = diag(1/den) mask o (1 + c S)
+            // ---- pass 1: W' = diag(1/den) mask o (1 + c S).  Two sweeps over the row's 64 scores (row sum, then the scaled weights):
+            // tensor memory is re-read rather than 64 values kept in registers; 8-column groups outside the row's graph cost nothing.
             mbar_wait(&sp_full, it & 1);
             tc_fence_after();
             if (ew == 0 && lane == 0) SEG_STAMP(1);
             uint32_t ra[32], rb[32];
-            tmem_ld32(tmS + tlane + 64 * half, ra);
-            tmem_ld32(tmS + tlane + 64 * half + 32, rb);
-            tmem_ld_wait32(ra);
-            tmem_ld_wait32(rb);
             float den = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int col = 64 * half + j;
-                uint32_t& x = j < 32 ? ra[j] : rb[j - 32];
-                const float w = (col >= gs && col < ge) ? fmaf(c, __uint_as_float(x), 1.f) : 0.f;
-                den += w;
-                x = __float_as_uint(w);
+            for (int ch = 0; ch < 2; ++ch) {
+                tmem_ld32(tmS + tlane + 64 * half + 32 * ch, ra);
+                tmem_ld_wait32(ra);
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const int jb = 64 * half + 32 * ch + 8 * g8;
+                    if (jb + 8 <= gs || jb >= ge) continue;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        den += (jb + e >= gs && jb + e < ge) ? fmaf(c, __uint_as_float(ra[8 * g8 + e]), 1.f) : 0.f;
+                }
             }
             den_s[it & 1][half][i] = den;
             gdo_s[it & 1][half][i] = gdo;
@@ -453,20 +455,26 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             const float inv = valid ? 1.f / (den_s[it & 1][0][i] + den_s[it & 1][1][i]) : 0.f;
             const float dden = -(gdo_s[it & 1][0][i] + gdo_s[it & 1][1][i]) * inv;
 #pragma unroll
-            for (int g8 = 0; g8 < 8; ++g8) {
-                const int jb = 64 * half + 8 * g8;
-                const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, g8);
-                if (jb + 8 <= gs || jb >= ge) {
-                    sts128(Xhi + off, make_uint4(0u, 0u, 0u, 0u));
-                    sts128(Xlo + off, make_uint4(0u, 0u, 0u, 0u));
-                } else {
-                    float w[8];
+            for (int ch = 0; ch < 2; ++ch) {
+                tmem_ld32(tmS + tlane + 64 * half + 32 * ch, ra);
+                tmem_ld_wait32(ra);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(g8 < 4 ? ra[8 * g8 + e] : rb[8 * (g8 - 4) + e]) * inv;
-                    uint4 hi, lo;
-                    split8(w, hi, lo);
-                    sts128(Xhi + off, hi);
-                    sts128(Xlo + off, lo);
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const int jb = 64 * half + 32 * ch + 8 * g8;
+                    const uint32_t off = (uint32_t)(half * kSOp) + sw128(i, 4 * ch + g8);
+                    if (jb + 8 <= gs || jb >= ge) {
+                        sts128(Xhi + off, make_uint4(0u, 0u, 0u, 0u));
+                        sts128(Xlo + off, make_uint4(0u, 0u, 0u, 0u));
+                    } else {
+                        float w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            w[e] = (jb + e >= gs && jb + e < ge) ? fmaf(c, __uint_as_float(ra[8 * g8 + e]), 1.f) * inv : 0.f;
+                        uint4 hi, lo;
+                        split8(w, hi, lo);
+                        sts128(Xhi + off, hi);
+                        sts128(Xlo + off, lo);
+                    }
                 }
             }
             fence_proxy_async();
@@ -494,8 +502,7 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
                         float ds[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const int col = jb + e;
-                            const float dw = (col >= gs && col < ge) ? fmaf(__uint_as_float(rb[8 * g8 + e]), inv, dden) : 0.f;
+                            const float dw = (jb + e >= gs && jb + e < ge) ? fmaf(__uint_as_float(rb[8 * g8 + e]), inv, dden) : 0.f;
                             const float cdw = c * dw;
                             t_acc = fmaf(cdw, __uint_as_float(ra[8 * g8 + e]), t_acc);
                             ds[e] = cdw;
@@ -520,9 +527,10 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
             if (ew == 0 && lane == 0) SEG_STAMP(5);
             // rows leave through TMA, staged in this warp's own 4 KB of the (now idle) W' / dS buffer (see seg_fwd_tc_kernel)
             const bool whole = r0 + 32 * quad + 32 <= r1;
-            const uint32_t box = Xhi + (uint32_t)(half * kSOp + quad * 4096);
+            const uint32_t box0 = Xhi + (uint32_t)(half * kSOp + quad * 4096), box1 = Xlo + (uint32_t)(half * kSOp + quad * 4096);
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
+                const uint32_t box = o == 1 ? box1 : box0;             // two boxes: the store of dV is being read while dQ' is staged
                 tmem_ld32((o == 0 ? tmDV : o == 1 ? tmDQ : tmDK) + tlane + 32 * half, ra);
                 tmem_ld_wait32(ra);
                 if (o == 2) {
@@ -531,8 +539,8 @@ __global__ void __launch_bounds__(kSegTcThreads, 1) seg_bwd_tc_kernel(const __gr
                     if (lane == 0) mbar_arrive(&e_free);
                 }
                 if (whole) {
-                    if (o > 0) {
-                        if (lane == 0) tma_wait_read0();
+                    if (o == 2) {                                     // dV's store (two groups back) has read box0
+                        if (lane == 0) tma_wait_read1();
                         __syncwarp();
                     }
 #pragma unroll
