@@ -65,7 +65,6 @@ __device__ __forceinline__ uint32_t make_idesc_fmt(int M, int N, int a_mn, int b
     d |= (uint32_t)(M >> 4) << 24;
     return d;
 }
-__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 struct LpArgs {
     ReduceArgs1 r;            // q/k/v pointers unused (tensor maps); N, rows_per_cta, ws, flags, epoch, partials, prepared, sh, n_total, dbg
