@@ -694,6 +694,7 @@ def run_extra(args):
         gs = torch.randn(tot, 1, 64, device=dev)
 
         def fb3():
+            qsg.grad = ksg.grad = vsg.grad = None
             o = ops.segmented_full_attention(qsg, ksg, vsg, "simple", nn_d)
             o.backward(gs)
         ms_fb = timeit(fb3, steps)

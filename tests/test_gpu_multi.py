@@ -129,11 +129,14 @@ want = O.segmented_simple_attention(q.double(), k.double(), v.double(), nn_all)
 dq, dk, dv = O.segmented_simple_attention_backward(q.double(), k.double(), v.double(), nn_all, g.double())
 gb, ge = shard_rows(nn_all.numel(), rank, world)            # graphs [gb, ge) live on this rank
 rb, re_ = int(nn_all[:gb].sum()), int(nn_all[:ge].sum())
-qs, ks, vs = (t[rb:re_].to(dev).requires_grad_(True) for t in (q, k, v))
-out = ops.segmented_full_attention(qs, ks, vs, "simple", nn_all[gb:ge].to(dev), group=dist.group.WORLD)
-out.backward(g[rb:re_].to(dev))
-errs = [O.rel_err(out, want[rb:re_]), O.rel_err(qs.grad, dq[rb:re_]), O.rel_err(ks.grad, dk[rb:re_]), O.rel_err(vs.grad, dv[rb:re_])]
-assert max(errs) < 1e-3, ("segmented", errs)
+for seg_impl in ("auto", "tcgen05"):      # warp-per-graph kernels (graphs of up to 89 nodes), then the tensor-core tiles: two-phase backward either way
+    ops.set_segmented_impl(seg_impl)
+    qs, ks, vs = (t[rb:re_].to(dev).requires_grad_(True) for t in (q, k, v))
+    out = ops.segmented_full_attention(qs, ks, vs, "simple", nn_all[gb:ge].to(dev), group=dist.group.WORLD)
+    out.backward(g[rb:re_].to(dev))
+    errs = [O.rel_err(out, want[rb:re_]), O.rel_err(qs.grad, dq[rb:re_]), O.rel_err(ks.grad, dk[rb:re_]), O.rel_err(vs.grad, dv[rb:re_])]
+    assert max(errs) < 1e-3, ("segmented", seg_impl, errs)
+ops.set_segmented_impl("auto")
 dist.barrier()
 if world == 2 and os.environ.get("DIF_TEST_WATCHDOG", "1") == "1":
     # watchdog: rank 0 launches an exchange its peer never joins -> the kernel gives up (DIF_COMM_TIMEOUT_MS) instead of
