@@ -628,6 +628,8 @@ class _SegLayout:
             with torch.cuda.device(self.ptr.device):
                 check(lib.dif_segmented_plan_build(self.ptr.data_ptr(), self.ptr.numel() - 1, self.total, self.max_nodes, plan.data_ptr(),
                                                    nbytes, _stream(self.ptr)), "dif_segmented_plan_build")
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(self.ptr.device).synchronize()      # cached across streams: complete before anyone else reads it
             self._plan = plan
         return self._plan
 
