@@ -447,6 +447,11 @@ def full_attention_conv(qs, ks, vs, kernel, output_attn=False, *, group=None, n_
         return (out, _dense_attention(qs, ks, kernel)) if output_attn else out
     lp = qs.dtype in (torch.bfloat16, torch.float16)
     if kernel == "simple":
+        if (vs.shape[1] == 1 and qs.shape[1] in (2, 4) and qs.shape[2] == 64 and vs.shape[2] == 64 and qs.is_cuda
+                and _SIMPLE_IMPL != _lib.DIF_IMPL_GENERIC):
+            # one value head shared by H key / query heads (`use_weight=False`, difformer.py:120): the tensor-core kernels want Hv == H,
+            # so the value rows are repeated per head (one extra pass over V; autograd sums the head gradients back)
+            vs = vs.expand(-1, qs.shape[1], -1)
         out = (_SimpleAttention16 if lp else _SimpleAttention).apply(qs, ks, vs, group, n_total)
     elif kernel == "sigmoid":
         if group is not None:

@@ -307,6 +307,33 @@ def test_simple_shapes_and_edges(n, h, hv, d, impl):
     assert O.rel_err(out, O.simple_attention(q.double(), k.double(), v.double())) < TOL
 
 
+@pytest.mark.parametrize("n,h", [(65, 4), (5000, 4), (3001, 2)])
+def test_shared_value_head_on_tensor_cores(n, h):
+    """H key / query heads over ONE value head (`use_weight=False`, difformer.py:120; Hv = 1 < H): pinned to the tcgen05 kernels (the
+    value rows are repeated per head), forward and backward against the fp64 oracle and the FFMA kernels."""
+    q, k, v = O.synthetic_qkv(n, h, 64, seed=n, hv=1, adversarial=True)
+    g = torch.randn(n, h, 64, generator=torch.Generator().manual_seed(3))
+    want = O.simple_attention(q.double(), k.double(), v.double())
+    grads = O.simple_attention_backward(q.double(), k.double(), v.double(), g.double())
+    res = {}
+    try:
+        for impl_ in ("tcgen05", "generic"):
+            ops.set_simple_impl(impl_)
+            qa, ka, va = (dev(t).requires_grad_(True) for t in (q, k, v))
+            out = difformer.full_attention_conv(qa, ka, va, "simple")
+            out.backward(dev(g))
+            res[impl_] = (out, qa.grad, ka.grad, va.grad)
+    finally:
+        ops.set_simple_impl("auto")
+    for impl_ in res:
+        assert O.rel_err(res[impl_][0], want) < TOL, impl_
+        assert res[impl_][3].shape == v.shape
+        for got, w in zip(res[impl_][1:], grads):
+            if n > 1 and float(w.abs().max()) > 1e-9:
+                assert O.rel_err(got, w) < TOL, impl_
+    assert O.rel_err(res["tcgen05"][0], res["generic"][0]) < 1e-4
+
+
 @pytest.mark.parametrize("kernel", ["simple", "sigmoid"])
 def test_wide_hidden_channels_300_400(kernel):
     """`image and text/run.sh` runs hidden_channels 300 / 400 with one head: wider than the hand-written kernels (M, D <= 128),
