@@ -683,6 +683,38 @@ def run_extra(args):
                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": alg / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": alg},
                      "parity": par})
+    elif w == "model":               # the reference's ogbn-proteins model (run.sh:37-39) on the full graph, inference: 3 layers, hidden 64, 1 head
+        from difformer_b200 import GraphedForward
+        n, cin, cout = N_NODES, 8, 112
+        torch.manual_seed(3)
+        m = difformer.DIFFormer(cin, 64, cout, num_layers=3, num_heads=1, kernel="simple", use_bn=True, use_residual=True, use_weight=True,
+                                use_graph=True).to(dev).eval()
+        x = torch.randn(n, cin, device=dev)
+        ei = O.synthetic_graph(n, 8 * n, seed=4).to(dev)
+        E = ei.shape[1]
+
+        def fwd():
+            with torch.no_grad():
+                return m(x, ei)
+        res = {}
+        for fold in (False, True):
+            ops.set_projection_folding(fold)
+            res[fold] = timeit(fwd, steps)
+        out_plain = None
+        par = {}
+        sd = {k_: v_.double().cpu() for k_, v_ in m.state_dict().items()}
+        want = O.difformer_forward(sd, x.double().cpu(), ei.cpu(), None, hidden_channels=64, num_layers=3, num_heads=1, kernel="simple", use_bn=True, use_residual=True,
+                                   use_weight=True, use_graph=True)
+        for fold in (False, True):
+            ops.set_projection_folding(fold)
+            par["folded" if fold else "explicit"] = O.rel_err(fwd(), want)
+        gf = GraphedForward(m, x, ei)                    # CUDA-graph replay of the folded forward: no host enqueue cost
+        ms_graph = timeit(lambda: gf(x, ei), steps)
+        par["graphed"] = O.rel_err(gf(x, ei), want)
+        ms = res[True]
+        line.update({"metric": f"node-updates/s, DIFFormer model forward (ogbn-proteins config: 3 layers, hidden 64, 1 head, bn + residual + gcn E={E}) N={n} fp32, inference",
+                     "value": n / (ms_graph * 1e-3), "unit": UNIT, "ms_per_step": ms_graph, "ms_eager_folded": ms, "ms_eager_explicit": res[False],
+                     "dtype": "f32", "parity": par})
     elif w == "segmented":           # BASELINE configs[4]: B = 8192 graphs, n_g ~ U[10,40], H = 1, D = 64
         gen = torch.Generator().manual_seed(5)
         nn_ = torch.randint(10, 41, (8192,), generator=gen)
@@ -734,7 +766,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="simple", choices=["simple", "sigmoid_cora", "layer", "layer_x", "segmented", "fwdbwd"])
+    ap.add_argument("--workload", default="simple", choices=["simple", "sigmoid_cora", "layer", "layer_x", "model", "segmented", "fwdbwd"])
     ap.add_argument("--simple-impl", default=None, choices=[None, "auto", "generic", "tcgen05"])
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"], help="'simple' forward: one cooperative kernel, or pass 1 / pass 2 as two launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
