@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
 
     const int t = threadIdx.x, slab = blockIdx.x, h = blockIdx.y;
     const int H = p.H;
+#pragma unroll 4
     for (int i = t; i < kC * kC; i += kThreads) {
         const int r = i / kC, c = i % kC;
         sG[r * kLd + c] = p.gram[i];
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
         for (int k = 0; k < kC; ++k) {
             const double2 a0 = *reinterpret_cast<const double2*>(sWkT + k * kLd + 4 * ty), a1 = *reinterpret_cast<const double2*>(sWkT + k * kLd + 4 * ty + 2);
             const double2 b0 = *reinterpret_cast<const double2*>(sG + k * kLd + 2 * tx), b1 = *reinterpret_cast<const double2*>(sG + k * kLd + 32 + 2 * tx);
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     {
         const int ty = t >> 6, tx = t & 63, j0 = slab * kSlabW + 4 * ty;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
         for (int k = 0; k < kC; ++k) {
             const double2 a0 = *reinterpret_cast<const double2*>(sWq + k * kLd + j0), a1 = *reinterpret_cast<const double2*>(sWq + k * kLd + j0 + 2);
             const double b = sWq[k * kLd + tx];
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     {
         const int m = t >> 2, dl0 = (t & 3) * 4, d0 = slab * kSlabW + dl0;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
         for (int c = 0; c < kC; ++c) {
             const double tv = sTT[c * kLd + m];
             const double2 b0 = *reinterpret_cast<const double2*>(sWvT + c * kLd + d0), b1 = *reinterpret_cast<const double2*>(sWvT + c * kLd + d0 + 2);
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
     {
         const int c = t >> 2, dl0 = (t & 3) * 4;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
         for (int m = 0; m < kC; ++m) {
             const double w = sWq[m * kLd + c];
             const double2 b0 = *reinterpret_cast<const double2*>(sS + m * kSlabW + dl0), b1 = *reinterpret_cast<const double2*>(sS + m * kSlabW + dl0 + 2);
