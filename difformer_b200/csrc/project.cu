@@ -36,6 +36,11 @@ struct ProjectArgs {
     double* ws;
 };
 
+// D(8x8) += A(8x4) B(4x8), fp64 on the tensor cores
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ double block_sum(double v, double* red) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -46,9 +51,8 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
-// Shared-memory matrices are fp64 (widened once on the way in: an F2F per FMA would cost more than the DFMA) with a leading dimension of
-// 66 doubles, and every product reads BOTH operands k-major (row k = one contraction index): per k a thread loads a few consecutive
-// doubles of each operand (LDS.128, broadcast across the warp's other threads) and does a register-tiled outer product.
+// Shared-memory matrices are fp64 (widened once on the way in) with a leading dimension of 66 doubles, and every product reads BOTH
+// operands k-major (row k = one contraction index), which is what the m8n8k4 fragments want.
 constexpr int kLd = kC + 2;
 
 __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
@@ -90,81 +94,83 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
         else { for (int j = 0; j < kC; ++j) acc += sWq[r * kLd + ((j + r) & (kC - 1))] * s_[(j + r) & (kC - 1)]; qs[r] = acc; }
     }
 
-    // T = Wk G (64 x 64): thread -> rows 4 ty .. +3, columns {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx}
+    // The four 64^3-class products run on the FP64 tensor cores (mma.sync m8n8k4): the vector DFMA pipe of this part sustains only a few
+    // FMAs per clock and SM (the scalar version of this kernel spent 29 us there).  Fragments: A(8x4) a = [lane/4][lane%4],
+    // B(4x8) b = [lane%4][lane/4], C(8x8) c0,c1 = [lane/4][2 (lane%4) + {0,1}]; both operands are read k-major from shared memory.
+    const int warp = t >> 5, lane = t & 31, gid = lane >> 2, tig = lane & 3;
+    // T = Wk G (64 x 64): warp -> rows 8 warp .. +7, all 64 columns
     double skp = 0.0;
     {
-        const int ty = t >> 4, tx = t & 15;
-        double acc[4][4];
+        double acc[8][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+            const double a = sWkT[(4 * ks + tig) * kLd + 8 * warp + gid];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < kC; ++k) {
-            const double2 a0 = *reinterpret_cast<const double2*>(sWkT + k * kLd + 4 * ty), a1 = *reinterpret_cast<const double2*>(sWkT + k * kLd + 4 * ty + 2);
-            const double2 b0 = *reinterpret_cast<const double2*>(sG + k * kLd + 2 * tx), b1 = *reinterpret_cast<const double2*>(sG + k * kLd + 32 + 2 * tx);
-            const double a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+            for (int nt = 0; nt < 8; ++nt) dmma(acc[nt], a, sG[(4 * ks + tig) * kLd + 8 * nt + gid]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int m = 4 * ty + i, c = (j < 2 ? 2 * tx + j : 32 + 2 * tx + (j - 2));
-                sTT[c * kLd + m] = acc[i][j];
-                skp += acc[i][j] * sWkT[c * kLd + m];         // <T, Wk>
+            for (int e = 0; e < 2; ++e) {
+                const int m = 8 * warp + gid, c = 8 * nt + 2 * tig + e;
+                sTT[c * kLd + m] = acc[nt][e];
+                skp += acc[nt][e] * sWkT[c * kLd + m];        // <T, Wk>
             }
     }
-    // this slab's 16 rows of P = Wq^T Wq (sum q^2 = <G, P>): thread -> rows slab*16 + 4 ty .. +3 (ty < 4), column tx (64)
+    // this slab's 16 rows of P = Wq^T Wq (sum q^2 = <G, P>): warp -> row tile warp / 4, column tiles 2 (warp % 4), +1
     double sqp = 0.0;
     {
-        const int ty = t >> 6, tx = t & 63, j0 = slab * kSlabW + 4 * ty;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-        for (int k = 0; k < kC; ++k) {
-            const double2 a0 = *reinterpret_cast<const double2*>(sWq + k * kLd + j0), a1 = *reinterpret_cast<const double2*>(sWq + k * kLd + j0 + 2);
-            const double b = sWq[k * kLd + tx];
-            acc[0] += a0.x * b; acc[1] += a0.y * b; acc[2] += a1.x * b; acc[3] += a1.y * b;
+        const int j0 = slab * kSlabW + 8 * (warp >> 2), n0 = 16 * (warp & 3);
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+            const double a = sWq[(4 * ks + tig) * kLd + j0 + gid];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma(acc[nt], a, sWq[(4 * ks + tig) * kLd + n0 + 8 * nt + gid]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sqp += acc[i] * sG[(j0 + i) * kLd + tx];
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) sqp += acc[nt][e] * sG[(j0 + gid) * kLd + n0 + 8 * nt + 2 * tig + e];
     }
     __syncthreads();                                          // sTT, ks, vs, qs complete
     if (t < kC) z[t] = ks[t] + p.n * bk[t];
 
-    // S slab: S[m][d] = sum_c T[m][c] Wv[d][c] + ks[m] bv[d] + bk[m] vs[d] + n bk[m] bv[d]; thread -> row m = t >> 2, 4 columns
+    // S slab (64 x 16): S[m][d] = sum_c T[m][c] Wv[d][c] + ks[m] bv[d] + bk[m] vs[d] + n bk[m] bv[d]; warp -> rows 8 warp .. +7
     {
-        const int m = t >> 2, dl0 = (t & 3) * 4, d0 = slab * kSlabW + dl0;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-        for (int c = 0; c < kC; ++c) {
-            const double tv = sTT[c * kLd + m];
-            const double2 b0 = *reinterpret_cast<const double2*>(sWvT + c * kLd + d0), b1 = *reinterpret_cast<const double2*>(sWvT + c * kLd + d0 + 2);
-            acc[0] += tv * b0.x; acc[1] += tv * b0.y; acc[2] += tv * b1.x; acc[3] += tv * b1.y;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 4
+        for (int ks_ = 0; ks_ < 16; ++ks_) {
+            const double a = sTT[(4 * ks_ + tig) * kLd + 8 * warp + gid];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma(acc[nt], a, sWvT[(4 * ks_ + tig) * kLd + slab * kSlabW + 8 * nt + gid]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int d = d0 + i;
-            sS[m * kSlabW + dl0 + i] = acc[i] + ks[m] * bv[d] + bk[m] * vs[d] + p.n * bk[m] * bv[d];
-        }
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = 8 * warp + gid, dl = 8 * nt + 2 * tig + e, d = slab * kSlabW + dl;
+                sS[m * kSlabW + dl] = acc[nt][e] + ks[m] * bv[d] + bk[m] * vs[d] + p.n * bk[m] * bv[d];
+            }
     }
     __syncthreads();
 
-    // A slab: A[c][d] = sum_m Wq[m][c] S[m][d]; thread -> row c = t >> 2, 4 columns
+    // A slab (64 x 16): A[c][d] = sum_m Wq[m][c] S[m][d]; warp -> rows c = 8 warp .. +7
     {
-        const int c = t >> 2, dl0 = (t & 3) * 4;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-        for (int m = 0; m < kC; ++m) {
-            const double w = sWq[m * kLd + c];
-            const double2 b0 = *reinterpret_cast<const double2*>(sS + m * kSlabW + dl0), b1 = *reinterpret_cast<const double2*>(sS + m * kSlabW + dl0 + 2);
-            acc[0] += w * b0.x; acc[1] += w * b0.y; acc[2] += w * b1.x; acc[3] += w * b1.y;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 4
+        for (int ks_ = 0; ks_ < 16; ++ks_) {
+            const double a = sWq[(4 * ks_ + tig) * kLd + 8 * warp + gid];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma(acc[nt], a, sS[(4 * ks_ + tig) * kSlabW + 8 * nt + gid]);
         }
-        float4 o = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
-        *reinterpret_cast<float4*>(p.vpartials + (size_t)h * kC * kC + c * kC + slab * kSlabW + dl0) = o;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int c = 8 * warp + gid, d = slab * kSlabW + 8 * nt + 2 * tig;
+            *reinterpret_cast<float2*>(p.vpartials + (size_t)h * kC * kC + c * kC + d) = make_float2((float)acc[nt][0], (float)acc[nt][1]);
+        }
     }
     double* wsh = p.ws + (size_t)h * kWsHead;
     if (t < kSlabW) {                                         // a[d] = bq^T S, u[d] = vs + n bv
