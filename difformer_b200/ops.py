@@ -667,9 +667,12 @@ def _seg_ptr(n_nodes: torch.Tensor, total: int, device) -> torch.Tensor:
     return _seg_layout(n_nodes, total, device).ptr
 
 
-def _segmented_tc_plan(lay: _SegLayout, H: int, Hv: int, M: int, D: int):
-    """The tensor-core plan when the forward should run on tcgen05, else None."""
+def _segmented_tc_plan(lay: _SegLayout, H: int, Hv: int, M: int, D: int, tensors=()):
+    """The tensor-core plan when the pass should run on tcgen05, else None (`tensors`: the row tensors the kernel will read with
+    256-bit loads -- a view that starts off a 32-byte boundary takes the FFMA kernels)."""
     if _SEGMENTED_IMPL == "generic" or not (H == 1 and Hv == 1 and M == 64 and D == 64) or not (1 <= lay.max_nodes <= 128):
+        return None
+    if any(t.data_ptr() % 32 for t in tensors):
         return None
     if _SEGMENTED_IMPL == "auto" and not (lay.max_nodes <= SEGMENTED_TC_MAX_NODES and lay.total >= SEGMENTED_TC_MIN_ROWS):
         return None
@@ -684,7 +687,7 @@ class _SegmentedSimple(torch.autograd.Function):
         qs, ks, vs = _f32c(qs), _f32c(ks), _f32c(vs)
         N, L, H, Hv, M, D = _shapes(qs, ks, vs)
         B = seg_ptr.numel() - 1
-        plan = _segmented_tc_plan(lay, H, Hv, M, D)
+        plan = _segmented_tc_plan(lay, H, Hv, M, D, (qs, ks, vs))
         dev = qs.device
         norms = torch.empty(2, dtype=torch.float32, device=dev)
         ws = workspace(dev, lib.dif_segmented_workspace_bytes(B))
@@ -715,7 +718,7 @@ class _SegmentedSimple(torch.autograd.Function):
         # graphs sharded over ranks: a private workspace (it must survive the all-reduce between the two phases)
         wsb = max(int(lib.dif_segmented_workspace_bytes(B)), 16)
         ws = torch.empty(wsb, dtype=torch.uint8, device=qs.device) if sharded else workspace(qs.device, wsb)
-        plan = _segmented_tc_plan(ctx.lay, H, Hv, M, D)
+        plan = _segmented_tc_plan(ctx.lay, H, Hv, M, D, (qs, ks, vs, g, out))
         with torch.cuda.device(qs.device):
             for phase in ((1, 2) if sharded else (0,)):
                 if plan is not None:       # the same tiles as the forward: five tensor-core products per tile

@@ -33,7 +33,9 @@ def supported(conv, query_input: torch.Tensor, source_input: torch.Tensor) -> bo
     """Same input for Q and K/V, hidden size 64 in and out, a tensor-core head count, fp32 CUDA rows."""
     return (query_input is source_input and query_input.dim() == 2 and query_input.shape[1] == HID and conv.out_channels == HID
             and conv.num_heads in (1, 2, 4) and query_input.dtype == torch.float32 and query_input.is_cuda
-            and ops._SIMPLE_IMPL != ops._lib.DIF_IMPL_GENERIC and conv.Wq.in_features == HID)
+            and ops._SIMPLE_IMPL != ops._lib.DIF_IMPL_GENERIC and conv.Wq.in_features == HID
+            and conv.Wq.bias is not None and conv.Wk.bias is not None and (not conv.use_weight or conv.Wv.bias is not None)
+            and (not query_input.is_contiguous() or query_input.data_ptr() % 32 == 0))
 
 
 def gram(x: torch.Tensor, shard=None) -> torch.Tensor:

@@ -759,6 +759,21 @@ def test_v2_simple_tensor_core_training_step():
         assert O.rel_err(got, w64) < TOL
 
 
+def test_v2_simple_misaligned_rows_take_the_ffma_kernels():
+    """Row tensors that start off a 32-byte boundary (a view into a larger buffer) cannot use the 256-bit loads of the tensor-core
+    kernels: the dispatch must notice and still return the right answer."""
+    gen = torch.Generator().manual_seed(9)
+    n_nodes = torch.randint(10, 41, (300,), generator=gen)
+    tot = int(n_nodes.sum())
+    q, k, v = O.synthetic_qkv(tot, 1, 64, seed=4, adversarial=True)
+    buf = torch.zeros(tot * 64 + 8, device="cuda")
+    qv = buf[4:4 + tot * 64].view(tot, 1, 64)
+    qv.copy_(dev(q))
+    assert qv.data_ptr() % 32 != 0 and qv.is_contiguous()
+    out = ops.segmented_full_attention(qv, dev(k), dev(v), "simple", n_nodes.cuda())
+    assert O.rel_err(out, O.segmented_simple_attention(q.double(), k.double(), v.double(), n_nodes)) < TOL
+
+
 def test_v2_model_forward():
     c = V2["v2_model_simple"]
     m = difformer.DIFFormer_v2(16, 64, 3, num_layers=2, kernel="simple", use_graph=True)
