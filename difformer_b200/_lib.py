@@ -38,6 +38,7 @@ SIGNATURES = {
                                    ctypes.POINTER(c_vp), c_i32, c_i32, ctypes.c_uint64, c_vp]),
     "dif_simple_project_workspace_bytes": (c_i64, [c_i32]),
     "dif_simple_project": (c_i32, [c_vp] * 7 + [c_f64, c_i32] + [c_vp] * 4 + [c_i64, c_vp]),
+    "dif_simple_project_values": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "dif_simple_apply_projected": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, ctypes.POINTER(Epilogue), c_vp]),
     "dif_simple_bwd_partials_len": (c_i64, [c_i32] * 3),
     "dif_simple_bwd_rowscal_len": (c_i64, [c_i64, c_i32, c_i32, c_i32, c_i32]),

@@ -150,7 +150,7 @@ extern "C" int64_t dif_simple_project_workspace_bytes(int H) { return (H == 1 ||
 extern "C" int dif_simple_project(const float* gram_partials, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
                                   const float* bv, double n_total, int H, float* vpartials, float* n_total_vec, float* vbar_partials,
                                   void* workspace, int64_t workspace_bytes, void* stream) {
-    DIF_REQUIRE(gram_partials && Wq && bq && Wk && bk && vpartials && n_total_vec && vbar_partials && workspace, DIF_EARG,
+    DIF_REQUIRE(gram_partials && Wq && bq && Wk && bk && vpartials && n_total_vec && workspace, DIF_EARG,
                 "simple_project: null pointer");
     DIF_REQUIRE((Wv == nullptr) == (bv == nullptr), DIF_EARG, "simple_project: Wv and bv must both be given or both be null");
     DIF_REQUIRE(H == 1 || H == 2 || H == 4, DIF_EUNSUPPORTED, "simple_project: H=%d (needs H in {1, 2, 4}, hidden = 64)", H);
@@ -192,4 +192,12 @@ extern "C" int dif_segmented_simple_bwd_tc(const float* q, const float* k, const
                 "segmented_bwd(tcgen05): workspace too small (dif_segmented_workspace_bytes) or misaligned");
     float* scal = (float*)workspace + 2 * (int64_t)B;          // same place as dif_segmented_simple_bwd_phase: the caller all-reduces it between phases
     return segmented_bwd_tc(q, k, v, g, out, plan, N, max_nodes, norms, dq, dk, dv, scal + 2, scal, phase, (cudaStream_t)stream);
+}
+
+// mean_h V as a one-head pass-2 problem, from the weights alone (project.cu): the value branch of a folded layer does not wait for G.
+extern "C" int dif_simple_project_values(const float* Wv, const float* bv, int H, float* vbar_partials, float* one, void* stream) {
+    DIF_REQUIRE(vbar_partials && one, DIF_EARG, "simple_project_values: null pointer");
+    DIF_REQUIRE((Wv == nullptr) == (bv == nullptr), DIF_EARG, "simple_project_values: Wv and bv must both be given or both be null");
+    DIF_REQUIRE(H == 1 || H == 2 || H == 4, DIF_EUNSUPPORTED, "simple_project_values: H=%d (needs H in {1, 2, 4}, hidden = 64)", H);
+    return simple_project_values(Wv, bv, H, vbar_partials, one, (cudaStream_t)stream);
 }

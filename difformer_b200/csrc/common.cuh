@@ -217,6 +217,7 @@ int segmented_fwd_tc(const float* q, const float* k, const float* v, const void*
                      cudaStream_t st);
 int segmented_bwd_tc(const float* q, const float* k, const float* v, const float* g, const float* out, const void* plan, int64_t N, int max_nodes,
                      const float* norms, float* dq, float* dk, float* dv, float* part, float* scal, int phase, cudaStream_t st);
+int simple_project_values(const float* Wv, const float* bv, int H, float* vbar_partials, float* one, cudaStream_t st);
 int64_t simple_project_workspace_bytes(int H);
 int simple_project(const float* gram, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv, const float* bv,
                    double n_total, int H, float* vpartials, float* nvec, float* vbar_partials, void* ws, cudaStream_t st);

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
         for (int m = 0; m < kC; ++m) acc += sWq[m * kLd + c] * z[m];
         p.vpartials[(size_t)H * kC * kC + h * kC + c] = (float)acc;
     }
-    if (h == 0) {
+    if (h == 0 && p.vbar_partials != nullptr) {
         // mean_h V = x wbar^T + bbar (the input of the gcn term, difformer.py:139) as a pass-2 problem with one head:
         // S[m][d] = mean_h Wv_h[d][m], z = 0, u = bbar, sum q^2 = sum k^2 = 1 (c = 1), denominator constant 1
         float* vb = p.vbar_partials;
@@ -221,6 +221,28 @@ __global__ void __launch_bounds__(kThreads) project_head_kernel(ProjectArgs p) {
             wsh[2 * kC] = beta;
             wsh[2 * kC + 1] = sk;
         }
+    }
+}
+
+// The same one-head pass-2 problem from the weights alone (no dependence on G): lets the value branch of a layer (mean_h V -> SpMM) start
+// before / beside the Gram pass.  vb = [S (64 x 64) | z = 0 | u = bbar | 1 | 1], one[0] = 1 (the denominator constant).
+__global__ void __launch_bounds__(kThreads) project_values_kernel(const float* __restrict__ Wv, const float* __restrict__ bv, int H,
+                                                                  float* __restrict__ vb, float* __restrict__ one) {
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    for (int i = t; i < kC * kC; i += gridDim.x * kThreads) {
+        const int m = i / kC, d = i % kC;
+        double acc = 0.0;
+        if (Wv) { for (int hh = 0; hh < H; ++hh) acc += (double)Wv[((size_t)hh * kC + d) * kC + m]; acc /= H; }
+        else acc = m == d ? 1.0 : 0.0;
+        vb[i] = (float)acc;
+    }
+    if (t < kC) {
+        double acc = 0.0;
+        if (Wv) { for (int hh = 0; hh < H; ++hh) acc += (double)bv[hh * kC + t]; acc /= H; }
+        vb[kC * kC + t] = 0.f;
+        vb[kC * kC + kC + t] = (float)acc;
+        if (t < 2) vb[kC * kC + 2 * kC + t] = 1.f;
+        if (t == 0) one[0] = 1.f;
     }
 }
 
@@ -274,6 +296,12 @@ int simple_project(const float* gram, const float* Wq, const float* bq, const fl
     DIF_LAUNCH_OK();
     FinishArgs f{reinterpret_cast<const double*>(ws), Wv, bv, n_total, H, vpartials, nvec};
     project_finish_kernel<<<1, kThreads, 0, st>>>(f);
+    DIF_LAUNCH_OK();
+    return DIF_OK;
+}
+
+int simple_project_values(const float* Wv, const float* bv, int H, float* vbar_partials, float* one, cudaStream_t st) {
+    project_values_kernel<<<4, kThreads, 0, st>>>(Wv, bv, H, vbar_partials, one);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }

@@ -43,19 +43,33 @@ def _conv_forward_projected(conv, x, edge_index, edge_weight, x_0, residual, lay
     alpha = 1.0 if residual is None else float(residual[0])
     gw = conv.graph_weight
     w_attn, w_gcn = ((1.0 - gw), gw) if (conv.use_graph and gw > 0) else (1.0, 1.0)
-    vpart, nvec, vbar_part = projected.projected_operands(projected.gram(x, shard), float(n_total), conv)
     addends = []
-    if conv.use_graph:
-        vbar = projected.head_mean_values(x, vbar_part, nvec, H) if conv.use_weight else x     # mean_h V [N, 64] (commutes with the SpMM)
-        if shard is None:
+    if conv.use_graph and shard is None:
+        # single GPU: the value branch (mean_h V from the weights alone -> SpMM) runs on a side stream beside the Gram pass and the
+        # operand algebra; the SpMM (no shared memory) shares the SMs with both.  Joined before pass 2.
+        main, side = torch.cuda.current_stream(x.device), projected.side_stream(x.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if conv.use_weight:
+                vbar_part, one = projected.value_operands(conv, x.device)
+                vbar = projected.head_mean_values(x, vbar_part, one, 0)
+            else:
+                vbar = x
             gmean = ops.spmm(ops.graph_csr(edge_index, edge_weight, N), vbar.view(N, 1, projected.HID)).view(N, projected.HID)
-        else:
-            from .sharded import gather_rows
-            if N != shard.end - shard.begin:
-                raise ValueError(f"row shard expects {shard.end - shard.begin} local rows, got {N}")
-            v_all = gather_rows(vbar, shard.pg, n_total)
-            gmean = ops.spmm(ops.graph_csr(edge_index, edge_weight, n_total), v_all.view(n_total, 1, projected.HID),
-                             rows=(shard.begin, shard.end)).view(N, projected.HID)
+        vpart, nvec, _ = projected.projected_operands(projected.gram(x, None), float(n_total), conv, with_values=False)
+        main.wait_stream(side)       # fork / join per layer: every buffer of one stream that the other touches is ordered by these two waits
+        addends.append((gmean, alpha * w_gcn))
+    else:
+        vpart, nvec, vbar_part = projected.projected_operands(projected.gram(x, shard), float(n_total), conv, with_values=conv.use_graph and conv.use_weight)
+    if conv.use_graph and shard is not None:
+        # row-sharded: one stream (the in-kernel NVLink exchange of the Gram pass and the NCCL all-gather must not wait on each other)
+        vbar = projected.head_mean_values(x, vbar_part, nvec, H) if conv.use_weight else x     # mean_h V [N, 64] (commutes with the SpMM)
+        from .sharded import gather_rows
+        if N != shard.end - shard.begin:
+            raise ValueError(f"row shard expects {shard.end - shard.begin} local rows, got {N}")
+        v_all = gather_rows(vbar, shard.pg, n_total)
+        gmean = ops.spmm(ops.graph_csr(edge_index, edge_weight, n_total), v_all.view(n_total, 1, projected.HID),
+                         rows=(shard.begin, shard.end)).view(N, projected.HID)
         addends.append((gmean, alpha * w_gcn))
     if getattr(conv, "use_source", False):
         addends.append((ops._f32c(x_0), alpha))

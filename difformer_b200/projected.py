@@ -59,31 +59,55 @@ def _w(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
-def projected_operands(gram_partials: torch.Tensor, n_total: float, conv):
+def projected_operands(gram_partials: torch.Tensor, n_total: float, conv, with_values: bool = True):
     """The pass-2 operands of every head from the Gram partials and the layer's weights (dif_simple_project: fp64 arithmetic, two small
-    launches): (vpartials fp32 in the partials layout of (H, Hv = H, 64, 64), nvec fp32 [H + 1], vbar_partials fp32 [4226]: the one-head
-    pass-2 problem whose solution is mean_h V, with nvec[H:] as its denominator constant).
+    launches): (vpartials fp32 in the partials layout of (H, Hv = H, 64, 64), nvec fp32 [H + 1], vbar_partials fp32 [4226] or None: the
+    one-head pass-2 problem whose solution is mean_h V, with nvec[H:] as its denominator constant).
     The same algebra in torch fp64, which the tests check this against: oracle.difformer_oracle.projected_operands."""
     H = conv.num_heads
     dev = gram_partials.device
     Wq, bq, Wk, bk = _w(conv.Wq.weight), _w(conv.Wq.bias), _w(conv.Wk.weight), _w(conv.Wk.bias)
     Wv, bv = (_w(conv.Wv.weight), _w(conv.Wv.bias)) if conv.use_weight else (None, None)
     nv = H * HID * HID + 2 * H * HID + 2
-    nb = HID * HID + 2 * HID + 2
-    buf = torch.empty(nv + nb + (-(nv + nb)) % 8 + H + 1, dtype=torch.float32, device=dev)      # one allocation for the three outputs
-    vpart, vbar_part, nvec = buf[:nv], buf[nv:nv + nb], buf[buf.numel() - (H + 1):]
+    nb = (HID * HID + 2 * HID + 2) if with_values else 0
+    buf = torch.empty(nv + nb + (-(nv + nb)) % 8 + H + 1, dtype=torch.float32, device=dev)      # one allocation for the outputs
+    vpart, vbar_part, nvec = buf[:nv], (buf[nv:nv + nb] if with_values else None), buf[buf.numel() - (H + 1):]
     ws = ops.workspace(dev, lib.dif_simple_project_workspace_bytes(H))
     with torch.cuda.device(dev):
         check(lib.dif_simple_project(gram_partials.data_ptr(), Wq.data_ptr(), bq.data_ptr(), Wk.data_ptr(), bk.data_ptr(),
                                      None if Wv is None else Wv.data_ptr(), None if bv is None else bv.data_ptr(), float(n_total), H,
-                                     vpart.data_ptr(), nvec.data_ptr(), vbar_part.data_ptr(), ws.data_ptr(), ws.numel(),
-                                     ops._stream(gram_partials)), "dif_simple_project")
+                                     vpart.data_ptr(), nvec.data_ptr(), None if vbar_part is None else vbar_part.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), ops._stream(gram_partials)), "dif_simple_project")
     return vpart, nvec, vbar_part
 
 
+def value_operands(conv, device):
+    """(vbar_partials, one): the one-head pass-2 problem whose solution is mean_h V = x wbar^T + bbar, from the weights alone
+    (dif_simple_project_values) -- the value branch of a layer (mean_h V -> SpMM) does not depend on the Gram matrix."""
+    Wv, bv = _w(conv.Wv.weight), _w(conv.Wv.bias)
+    buf = torch.empty(HID * HID + 2 * HID + 2 + 6 + 1, dtype=torch.float32, device=device)
+    vbar_part, one = buf[:HID * HID + 2 * HID + 2], buf[-1:]
+    with torch.cuda.device(device):
+        check(lib.dif_simple_project_values(Wv.data_ptr(), bv.data_ptr(), conv.num_heads, vbar_part.data_ptr(), one.data_ptr(),
+                                            torch.cuda.current_stream(device).cuda_stream), "dif_simple_project_values")
+    return vbar_part, one
+
+
 def head_mean_values(x: torch.Tensor, vbar_part: torch.Tensor, nvec: torch.Tensor, H: int) -> torch.Tensor:
-    """mean_h V = x wbar^T + bbar [N, 64] through the pass-2 kernel (one head, A = x): the input of the gcn term."""
+    """mean_h V = x wbar^T + bbar [N, 64] through the pass-2 kernel (one head, A = x): the input of the gcn term.  `nvec`: the [H + 1]
+    vector of projected_operands (its last entry is the constant) with H, or the `one` of value_operands with H = 0."""
     return apply(x, vbar_part, nvec[H:], 1).view(-1, HID)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    """One extra stream per device for the value branch of the folded layer (created on first use, outside any graph capture)."""
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def apply(x: torch.Tensor, vpart: torch.Tensor, nvec: torch.Tensor, H: int, epilogue: Optional[ops.Epilogue] = None, keep=()) -> torch.Tensor:

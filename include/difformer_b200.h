@@ -154,11 +154,15 @@ DIF_API int dif_simple_apply_projected(const float* x, int64_t ldx, const float*
  * dif_simple_apply_projected), and vbar_partials [4096 + 2*64 + 2]: the head mean of the value projection posed as a one-head pass-2
  * problem -- dif_simple_apply_projected(x, ldx, vbar_partials, n_total_vec + H, N, 1, vbar, NULL) writes mean_h V = x wbar^T + bbar,
  * the input of the gcn term (difformer.py:139; the head mean commutes with the SpMM).
- * fp64 arithmetic, deterministic, two small launches.  workspace: dif_simple_project_workspace_bytes(H), 8-byte aligned. */
+ * vbar_partials may be NULL; dif_simple_project_values writes the same vbar_partials (and the denominator constant `one[0]` = 1) from
+ * the weights alone, so the value branch of a layer (mean_h V -> SpMM) need not wait for the Gram matrix.
+ * fp64 arithmetic (the 64 x 64 products on the FP64 tensor cores), deterministic, two small launches.
+ * workspace: dif_simple_project_workspace_bytes(H), 8-byte aligned. */
 DIF_API int64_t dif_simple_project_workspace_bytes(int H);
 DIF_API int dif_simple_project(const float* gram_partials, const float* Wq, const float* bq, const float* Wk, const float* bk,
                        const float* Wv, const float* bv, double n_total, int H, float* vpartials, float* n_total_vec,
                        float* vbar_partials, void* workspace, int64_t workspace_bytes, void* stream);
+DIF_API int dif_simple_project_values(const float* Wv, const float* bv, int H, float* vbar_partials, float* one, void* stream);
 
 /* Backward of the 'simple' path (derived analytically; the reference uses autograd).
  *   bwd_partials = [ dS : H*M*D | dz : H*M | du : H*D | t_q | t_k ]  (raw, additive over shards;

@@ -921,6 +921,9 @@ def test_projection_folded_into_the_propagation(h, use_weight):
                                      cw(conv.Wk.weight), cw(conv.Wk.bias), cw(conv.Wv.weight if use_weight else None),
                                      cw(conv.Wv.bias if use_weight else None), h)
         vpart_k, nvec_k, vbar_k = ops_k
+        if use_weight:        # the weights-only route to the same value operands
+            vb2, one = projected.value_operands(conv, x.device)
+            assert torch.equal(vb2, vbar_k) and float(one) == 1.0
         vpart_o, nvec_o, wbar_o, bbar_o = ops_o
         assert O.rel_err(vpart_k, vpart_o) < 1e-6 and O.rel_err(nvec_k[:h], nvec_o) < 1e-6 and float(nvec_k[h]) == 1.0
         vbar_o = torch.cat([wbar_o.t().reshape(-1), torch.zeros(64, dtype=torch.float64), bbar_o, torch.ones(2, dtype=torch.float64)])
