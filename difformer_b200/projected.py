@@ -84,12 +84,18 @@ def projected_operands(gram_partials: torch.Tensor, n_total: float, conv, with_v
 def value_operands(conv, device):
     """(vbar_partials, one): the one-head pass-2 problem whose solution is mean_h V = x wbar^T + bbar, from the weights alone
     (dif_simple_project_values) -- the value branch of a layer (mean_h V -> SpMM) does not depend on the Gram matrix."""
+    key = (conv.Wv.weight.data_ptr(), conv.Wv.weight._version, conv.Wv.bias.data_ptr(), conv.Wv.bias._version, str(device))
+    hit = getattr(conv, "_value_operands", None)
+    if hit is not None and hit[0] == key and not torch.cuda.is_current_stream_capturing():
+        return hit[1], hit[2]                  # inference: the weights do not change between calls (in-place updates bump _version)
     Wv, bv = _w(conv.Wv.weight), _w(conv.Wv.bias)
     buf = torch.empty(HID * HID + 2 * HID + 2 + 6 + 1, dtype=torch.float32, device=device)
     vbar_part, one = buf[:HID * HID + 2 * HID + 2], buf[-1:]
     with torch.cuda.device(device):
         check(lib.dif_simple_project_values(Wv.data_ptr(), bv.data_ptr(), conv.num_heads, vbar_part.data_ptr(), one.data_ptr(),
                                             torch.cuda.current_stream(device).cuda_stream), "dif_simple_project_values")
+    if not torch.cuda.is_current_stream_capturing():
+        object.__setattr__(conv, "_value_operands", (key, vbar_part, one))
     return vbar_part, one
 
 
