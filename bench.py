@@ -667,6 +667,17 @@ def run_extra(args):
                 layer()
             host[fold] = (time.perf_counter() - t0) / steps * 1e3        # enqueue cost of one layer (no sync): the floor the GPU time must stay above
             torch.cuda.synchronize()
+        # the same folded layer as a CUDA graph: what the GPU needs once the host enqueue (several small launches, two streams) is out of the way
+        ops.set_projection_folding(True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            layer()
+        torch.cuda.current_stream().wait_stream(side)
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            out_g = layer()
+        ms_graph = timeit(cg.replay, steps)
         xd = x.double().cpu()
         qd, kd, vd = (torch.nn.functional.linear(xd, l.weight.double().cpu(), l.bias.double().cpu()).view(n, h, d) for l in (conv.Wq, conv.Wk, conv.Wv))
         body = (O.simple_attention(qd, kd, vd) + O.gcn_conv(vd, ei.cpu(), None)).mean(1)          # difformer.py:137-140
@@ -675,10 +686,12 @@ def run_extra(args):
         for fold in (False, True):
             ops.set_projection_folding(fold)
             par["folded" if fold else "unfolded"] = O.rel_err(layer(), want)
+        cg.replay()
+        par["folded_graphed"] = O.rel_err(out_g, want)
         ms = res[True]
         alg = n * (3 * d * 4) + E * 8 + (n + 1) * 4        # x read (pass 1; pass 2 and the vbar GEMM re-read it from L2), prev, out
         line.update({"metric": f"node-updates/s, DIFFormerConv layer from x (Wq/Wk/Wv + attention + gcn E={E} + head mean + residual + LayerNorm) N={n} H=4 hidden=64 fp32",
-                     "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_unfolded": res[False], "host_enqueue_ms": host[True],
+                     "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_graphed": ms_graph, "ms_per_step_unfolded": res[False], "host_enqueue_ms": host[True],
                      "host_enqueue_ms_unfolded": host[False], "dtype": "f32",
                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": alg / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": alg},
