@@ -188,3 +188,34 @@ def test_projection_folding_algebra(h, use_weight):
         assert O.rel_err(got - want.mean(0, keepdim=True), dev_part) < 1e-6
         vmean = v.mean(1) if use_weight else x
         assert O.rel_err(x @ wbar.double().t() + bbar.double(), vmean) < 1e-6
+
+
+def test_segmented_tensor_core_dispatch_rules():
+    """Host-side choice between the tensor-core tiles and the warp-per-graph kernels for the batched-graph 'simple' op (no GPU needed:
+    the plan itself is only built when the rules say yes)."""
+    class Lay:                       # what ops._seg_layout caches, minus the device plan
+        def __init__(self, max_nodes, total):
+            self.max_nodes, self.total, self.built = max_nodes, total, 0
+
+        def plan(self):
+            self.built += 1
+            return "plan"
+    try:
+        ops.set_segmented_impl("auto")
+        assert ops._segmented_tc_plan(Lay(40, 200000), 1, 1, 64, 64) == "plan"
+        assert ops._segmented_tc_plan(Lay(40, 100), 1, 1, 64, 64) is None            # a handful of tiles: not worth it
+        assert ops._segmented_tc_plan(Lay(90, 200000), 1, 1, 64, 64) is None          # tile fill below one half
+        assert ops._segmented_tc_plan(Lay(40, 200000), 2, 2, 64, 64) is None          # one head only
+        assert ops._segmented_tc_plan(Lay(40, 200000), 1, 1, 32, 32) is None          # hidden 64 only
+        ops.set_segmented_impl("tcgen05")
+        assert ops._segmented_tc_plan(Lay(128, 50), 1, 1, 64, 64) == "plan"           # pinned: whenever the shape allows
+        assert ops._segmented_tc_plan(Lay(129, 5000), 1, 1, 64, 64) is None
+        assert ops._segmented_tc_plan(Lay(0, 0), 1, 1, 64, 64) is None
+        ops.set_segmented_impl("generic")
+        lay = Lay(40, 200000)
+        assert ops._segmented_tc_plan(lay, 1, 1, 64, 64) is None and lay.built == 0
+        with pytest.raises(ValueError):
+            ops.set_segmented_impl("fast")
+    finally:
+        ops.set_segmented_impl("auto")
+
