@@ -644,11 +644,30 @@ __global__ void seg_bwd_tc_sum_kernel(const float* __restrict__ part, int n, flo
     }
 }
 
-// dq -= q t / |Q|^2, dk -= k t / |K|^2 over all rows
+// dq -= q t / |Q|^2, dk -= k t / |K|^2 over all rows.  npart > 0: t is still spread over the CTAs' shares (`part`, single-GPU call): every
+// block adds them up itself in the same fixed order and block 0 publishes the total; npart == 0: t has been reduced (and all-reduced) into scal.
 __global__ void __launch_bounds__(256) seg_fixup_rows_kernel(const float4* __restrict__ q, const float4* __restrict__ k, float4* __restrict__ dq,
-                                                             float4* __restrict__ dk, int64_t count, const float* __restrict__ scal,
-                                                             const float* __restrict__ norms) {
-    const float aq = scal[0] / norms[0], ak = scal[1] / norms[1];
+                                                             float4* __restrict__ dk, int64_t count, float* __restrict__ scal,
+                                                             const float* __restrict__ part, int npart, const float* __restrict__ norms) {
+    __shared__ float tsh;
+    float tq = 0.f, tk = 0.f;
+    if (npart > 0) {
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+            for (int i = threadIdx.x; i < npart; i += 32) t += (double)part[2 * i];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) {
+                tsh = (float)t;
+                if (blockIdx.x == 0) scal[0] = scal[1] = (float)t;
+            }
+        }
+        __syncthreads();
+        tq = tk = tsh;
+    } else {
+        tq = scal[0];
+        tk = scal[1];
+    }
+    const float aq = tq / norms[0], ak = tk / norms[1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 q4 = q[i], k4 = k[i];
         float4 a = dq[i], b = dk[i];
@@ -772,11 +791,14 @@ int segmented_bwd_tc(const float* q, const float* k, const float* v, const float
                 fprintf(stderr, "\n");
             }
         }
-        seg_bwd_tc_sum_kernel<<<1, 32, 0, st>>>(part, grid, scal);
-        DIF_LAUNCH_OK();
+        if (phase == 1) {            // sharded graphs: the caller all-reduces scal before phase 2
+            seg_bwd_tc_sum_kernel<<<1, 32, 0, st>>>(part, grid, scal);
+            DIF_LAUNCH_OK();
+        }
     }
     if (phase == 1) return DIF_OK;
-    seg_fixup_rows_kernel<<<sms * 8, 256, 0, st>>>((const float4*)q, (const float4*)k, (float4*)dq, (float4*)dk, N * (kDim / 4), scal, norms);
+    seg_fixup_rows_kernel<<<sms * 8, 256, 0, st>>>((const float4*)q, (const float4*)k, (float4*)dq, (float4*)dk, N * (kDim / 4), scal, part,
+                                                   phase == 0 ? grid : 0, norms);
     DIF_LAUNCH_OK();
     return DIF_OK;
 }
