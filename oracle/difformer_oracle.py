@@ -433,3 +433,31 @@ def projected_operands(G: Tensor, s: Tensor, n_total: float, Wq: Tensor, bq: Ten
     vpart = torch.cat([A.reshape(-1), w.reshape(-1), (u + c * a).reshape(-1), sq.reshape(1), sk.reshape(1)])
     return vpart, n + c * beta, Wv.mean(0), bv.mean(0)
 
+
+def segmented_tile_plan(n_nodes: Tensor, max_nodes: Optional[int] = None):
+    """Restatement of the device-side plan of the tensor-core batched-graph kernels (difformer_b200/csrc/segmented_sm100.cu,
+    seg_plan_kernel): whole graphs packed into tiles of at most 128 rows without a sequential pass.  Tile b holds the graphs whose FIRST
+    row lies in [b S, (b + 1) S), S = 129 - max_nodes.  Returns (tile_row0 [ntiles + 1], row_range [N, 2]) as int64 tensors."""
+    nn_ = n_nodes.to(torch.int64)
+    ptr = torch.zeros(nn_.numel() + 1, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(nn_, 0)
+    N = int(ptr[-1])
+    mx = int(nn_.max()) if max_nodes is None else int(max_nodes)
+    S = 129 - mx
+    ntiles = (N + S - 1) // S
+    tile_row0 = torch.full((ntiles + 1,), -1, dtype=torch.int64)
+    row_range = torch.zeros((N, 2), dtype=torch.int64)
+    prev_bucket = -1
+    for g in range(nn_.numel()):
+        s_, e_ = int(ptr[g]), int(ptr[g + 1])
+        if e_ <= s_:
+            continue                                   # an empty graph owns no rows
+        row_range[s_:e_, 0] = s_
+        row_range[s_:e_, 1] = e_
+        b = s_ // S
+        tile_row0[prev_bucket + 1:b + 1] = s_          # this graph opens bucket b (and any empty buckets before it)
+        prev_bucket = b
+        if e_ == N:
+            tile_row0[b + 1:] = N
+    return tile_row0, row_range
+

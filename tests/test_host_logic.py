@@ -219,3 +219,32 @@ def test_segmented_tensor_core_dispatch_rules():
     finally:
         ops.set_segmented_impl("auto")
 
+
+def test_segmented_tile_plan_invariants():
+    """The packing rule of the tensor-core batched-graph kernels (restated in oracle.segmented_tile_plan): for ANY batch layout with graphs
+    of up to max_nodes <= 128 rows, tiles are whole graphs, at most 128 rows, in order, and cover every row exactly once."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import difformer_oracle as O
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(1, 128).flatmap(lambda mx: st.tuples(st.just(mx), st.lists(st.integers(0, mx), min_size=1, max_size=120))))
+    def check(arg):
+        mx, sizes = arg
+        n_nodes = torch.tensor(sizes)
+        if int(n_nodes.sum()) == 0:
+            return
+        mx = max(int(n_nodes.max()), 1)
+        tiles, rr = O.segmented_tile_plan(n_nodes, mx)
+        N = int(n_nodes.sum())
+        ptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(n_nodes.to(torch.int64), 0)])
+        assert int(tiles[0]) == 0 and int(tiles[-1]) == N and int(tiles.min()) >= 0
+        d = tiles[1:] - tiles[:-1]
+        assert int(d.min()) >= 0 and int(d.max()) <= 128                      # ordered, at most 128 rows
+        assert bool(torch.isin(tiles, ptr).all())                             # boundaries are graph boundaries
+        nz = n_nodes > 0
+        assert torch.equal(rr[:, 0], ptr[:-1][nz].repeat_interleave(n_nodes[nz]))
+        assert torch.equal(rr[:, 1], ptr[1:][nz].repeat_interleave(n_nodes[nz]))
+        if mx <= 64:                                                          # the regime the dispatcher picks: no empty tiles, fill >= 1/2 on average
+            assert int(d[:-1].min()) > 0 if d.numel() > 1 else True
+    check()
+
